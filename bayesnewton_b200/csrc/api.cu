@@ -1,0 +1,83 @@
+// Library-level pieces of the C ABI: error slot, sizing queries and the stand-alone
+// discretisation kernel (As, Qs materialised for callers that want the reference's arrays:
+// vmap(kernel.state_transition)(dt), vmap(process_noise_covariance), ops.py:274-278).
+#include "common.cuh"
+#include "core.cuh"
+#include "scan.cuh"
+
+namespace bn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+template <class Gen>
+__global__ void discretise_kernel(Gen gen, long long N, double* As, double* Qs) {
+    constexpr int d = Gen::d;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    double A[d * d], Q[symn(d)];
+    gen.step(k, A, Q);
+    double* a = As + k * (d * d);
+    double* q = Qs + k * (d * d);
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+#pragma unroll
+        for (int j = 0; j < d; ++j) {
+            a[i * d + j] = A[i * d + j];
+            q[i * d + j] = Q[sidx(i, j)];
+        }
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" const char* bn_last_error(void) { return g_err; }
+extern "C" int bn_version(void) { return 100; }
+
+extern "C" int bn_state_dim(const bn_kernel_spec* k) {
+    if (!k || k->n_components < 1 || k->n_components > BN_MAX_COMPONENTS) return -1;
+    int n = family_dim(k->family);
+    return n ? n * k->n_components : -1;
+}
+
+extern "C" int bn_rts_carry_len(int d) { return 2 * d * d + d; }
+
+extern "C" size_t bn_workspace_bytes(int64_t N, int d, int D) {
+    (void)D;
+    if (N < 0 || d < 1) return 0;
+    ChunkPlan cp = plan_chunks(N > 0 ? N : 1);
+    long long elem = (long long)d * d + 2 * d + 2 * symn(d);
+    long long doubles = 64 + scan_plan_doubles(cp.nchunks, (int)elem) + cp.nchunks;
+    long long site_partials = 4 * ((N + 127) / 128 + 1024);
+    if (site_partials > doubles) doubles = site_partials;
+    return (size_t)(doubles + 1024) * sizeof(double);
+}
+
+extern "C" int bn_discretise(const bn_kernel_spec* k, int64_t N, const double* dt, double* As, double* Qs,
+                             void* stream) {
+    BN_REQUIRE(k != nullptr, "kernel spec is null");
+    BN_REQUIRE(N >= 0, "N must be non-negative");
+    if (N == 0) return 0;
+    BN_REQUIRE(dt && As && Qs, "null array");
+    unsigned grid = (unsigned)((N + 255) / 256);
+#define X(FAM, NC)                                                                      \
+    if (k->family == FAM && k->n_components == NC) {                                    \
+        MaternGen<FAM, NC> gen;                                                         \
+        gen.spec = *k;                                                                  \
+        gen.dt = dt;                                                                    \
+        discretise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gen, N, As, Qs);      \
+        BN_CUDA(cudaGetLastError());                                                    \
+        return 0;                                                                       \
+    }
+    BN_FOR_EACH_MATERN(X)
+#undef X
+    set_error("unsupported kernel spec: family %d with %d components", k->family, k->n_components);
+    return -1;
+}

@@ -1,0 +1,204 @@
+/*
+ * bn_b200.h -- C ABI of the B200-native Markov-GP inference hot path.
+ *
+ * Drop-in boundary for the one path of AaltoML/BayesNewton this library
+ * replaces.  The reference has no FFI of its own (it is pure
+ * Python on JAX); each entry point below names the reference function whose
+ * array-level contract it reproduces (paths relative to the reference root):
+ *
+ *   bn_discretise          vmap(kernel.state_transition)(dt) + process_noise_covariance
+ *                          bayesnewton/ops.py:149-151,274-278; kernels.py:158-165,216-224,273-286,344-365
+ *   bn_kf_arrays           _sequential_kf / _parallel_kf          ops.py:154-180, 237-253
+ *   bn_rts_arrays          _sequential_rts / _parallel_rts        ops.py:288-311, 338-354
+ *   bn_kalman_filter       kalman_filter                          ops.py:256-285
+ *   bn_rts_smoother        rauch_tung_striebel_smoother           ops.py:357-380
+ *   bn_kf_shard_*          the same filter, split in the three phases a time-sharded
+ *   bn_rts_shard_*         (multi-GPU) two-level scan needs       ops.py:203-219, 328-335
+ *   bn_site_update         update_variational_params + newton_update + damped update_nat_params
+ *                          inference.py:21-39,65-90,105-128,170-195,238-284,339-371; basemodels.py:85-100
+ *   bn_expected_density    the value-only likelihood term of energy()
+ *                          inference.py:130-154,197-222,286-325,373-428
+ *   bn_gaussian_expected_log_lik   vmap(gaussian_expected_log_lik) utils.py:510-531, basemodels.py:715-721
+ *   bn_kalman_filter_grad  d(ell)/d(kernel hyper-parameters) that objax.GradValues obtains by
+ *                          reverse-mode AD through kalman_filter (README.md:59, basemodels.py:726-741)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns
+ *     all buffers including outputs and the workspace; nothing is allocated, freed or
+ *     retained; calls are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - arrays are contiguous row-major with the time axis leading, exactly as in the
+ *     reference: means [N,d,1] -> N*d doubles, covariances [N,d,d] -> N*d*d doubles,
+ *     masks [N,D,1] bool -> N*D bytes (non-zero = missing).
+ *   - dtype is IEEE double (the reference runs with jax_enable_x64, basemodels.py:46-47).
+ *   - return value: 0 ok, <0 bad argument (see bn_last_error), >0 a cudaError_t.
+ *     Numerical failure is not an error: a non-PD Cholesky yields NaN as in JAX.
+ *   - form: BN_SEQUENTIAL is the reference's lax.scan recursion executed in time order
+ *     by a single GPU thread (bit-for-bit the sequential rounding order);
+ *     BN_SCAN is the temporally-parallel form (`parallel=True`).
+ */
+#ifndef BN_B200_H
+#define BN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BN_MAX_COMPONENTS 4
+
+enum { BN_SEQUENTIAL = 0, BN_SCAN = 1 };
+
+/* kernel families with a closed-form discretisation (kernels.py:123-382) */
+enum { BN_MATERN12 = 1, BN_MATERN32 = 2, BN_MATERN52 = 3, BN_MATERN72 = 4 };
+
+/* A stationary prior = `Independent` stack (kernels.py:1499-1616) of n_components Matern
+ * kernels of ONE family (n_components = 1 is the plain kernel).  State dim d =
+ * n_components * family order dim, latent dim D = n_components, H = blockdiag([1,0,..]). */
+typedef struct {
+    int32_t family;
+    int32_t n_components;
+    double variance[BN_MAX_COMPONENTS];
+    double lengthscale[BN_MAX_COMPONENTS];
+} bn_kernel_spec;
+
+/* likelihoods of the site kernels (likelihoods.py:684-860, 1244-1281) */
+enum { BN_LIK_GAUSSIAN = 1, BN_LIK_BERNOULLI_PROBIT = 2, BN_LIK_BERNOULLI_LOGIT = 3,
+       BN_LIK_HETEROSCEDASTIC_SOFTPLUS = 4, BN_LIK_HETEROSCEDASTIC_EXP = 5 };
+
+/* inference schemes (inference.py:99-428) */
+enum { BN_METHOD_VI = 1, BN_METHOD_EP = 2, BN_METHOD_NEWTON = 3, BN_METHOD_PL = 4 };
+
+const char* bn_last_error(void);
+int bn_version(void);
+
+/* ---- discretisation: As[N,d,d], Qs[N,d,d] from dt[N] -------------------------------------- */
+int bn_state_dim(const bn_kernel_spec* k);
+int bn_discretise(const bn_kernel_spec* k, int64_t N, const double* dt, double* As, double* Qs, void* stream);
+
+/* ---- workspace ------------------------------------------------------------------------- */
+/* bytes of caller-provided scratch any filter/smoother call below needs for (N, d, D) */
+size_t bn_workspace_bytes(int64_t N, int d, int D);
+
+/* ---- array-level filter / smoother ----------------------------------------------------- */
+/* H[D,d]; ys[N,D,1]; Rs[N,D,D]; m0[d,1]; P0[d,d]; masks[N,D,1] (nullable = nothing missing).
+ * ell: one double (nullable: skip the log-likelihood); fms[N,d,1], fPs[N,d,d] (both nullable
+ * together: log-likelihood only).  return_predict as ops.py:175-178. */
+int bn_kf_arrays(int form, int64_t N, int d, int D,
+                 const double* As, const double* Qs, const double* H,
+                 const double* ys, const double* Rs, const double* m0, const double* P0,
+                 const uint8_t* masks, int return_predict,
+                 double* ell, double* fms, double* fPs,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* return_full=0: sms[N,Df,1] = H sm, sPs[N,Df,Df] = H sP H^T; return_full=1: sms[N,d,1], sPs[N,d,d].
+ * gains[N,d,d] nullable (update_posterior discards them, basemodels.py:701). */
+int bn_rts_arrays(int form, int64_t N, int d, int Df,
+                  const double* fms, const double* fPs,
+                  const double* As, const double* Qs, const double* H, int return_full,
+                  double* sms, double* sPs, double* gains,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- kernel-level filter / smoother: A_k, Q_k generated in-kernel from dt --------------- */
+int bn_kalman_filter(const bn_kernel_spec* k, int form, int64_t N,
+                     const double* dt, const double* y, const double* noise_cov, const uint8_t* mask,
+                     int return_predict, double* ell, double* means, double* covs,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+int bn_rts_smoother(const bn_kernel_spec* k, int form, int64_t N,
+                    const double* dt, const double* filter_mean, const double* filter_cov, int return_full,
+                    double* means, double* covs, double* gains,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- time-sharded (multi-GPU) scan: reduce -> exchange carries -> apply ------------------ */
+/* number of doubles in one filtering carry (A,b,C,J,eta full storage: 3d^2+2d) / smoothing carry
+ * (E,g,L: 2d^2+d) -- the O(d^2) messages ranks all-gather. */
+int bn_kf_carry_len(int d);
+int bn_rts_carry_len(int d);
+/* phase 1: reduce this rank's N local steps to one carry (device, bn_kf_carry_len doubles).
+ * is_first != 0 on the rank that owns global step 0 (the Q_0 := P_0 rule of ops.py:222-229). */
+int bn_kf_shard_reduce(const bn_kernel_spec* k, int64_t N, int is_first,
+                       const double* dt, const double* y, const double* noise_cov,
+                       double* carry, void* workspace, size_t workspace_bytes, void* stream);
+/* phase 2+3: given the carries of all ranks (carries[world, carry_len], device) and this rank's
+ * index, fold the lower ranks' carries into the incoming state and run the local filter.
+ * ell receives this rank's partial log-likelihood (sum over its steps). */
+int bn_kf_shard_apply(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* carries,
+                      const double* dt, const double* y, const double* noise_cov, const uint8_t* mask,
+                      int return_predict, double* ell, double* means, double* covs,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* smoother: dt is the shifted step array of THIS shard (dt'[k] = step out of k; the last entry of
+ * the last rank is 0, every other rank's last entry is its right neighbour's first dt). */
+int bn_rts_shard_reduce(const bn_kernel_spec* k, int64_t N, int is_last,
+                        const double* dt, const double* filter_mean, const double* filter_cov,
+                        double* carry, void* workspace, size_t workspace_bytes, void* stream);
+int bn_rts_shard_apply(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* carries,
+                       const double* dt, const double* filter_mean, const double* filter_cov, int return_full,
+                       double* means, double* covs, double* gains,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- hyper-parameter gradient of the filter log-likelihood ------------------------------ */
+/* grad[2*n_components]: d ell / d variance_c, d ell / d lengthscale_c (untransformed; the host
+ * applies the softplus chain rule of kernels.py:80-95).  Forward-sensitivity recursion fused
+ * into the filter. */
+int bn_kalman_filter_grad(const bn_kernel_spec* k, int form, int64_t N,
+                          const double* dt, const double* y, const double* noise_cov, const uint8_t* mask,
+                          double* ell, double* grad,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- sites ------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t method;        /* BN_METHOD_* */
+    int32_t likelihood;    /* BN_LIK_* */
+    double lik_param;      /* Gaussian: observation variance */
+    int64_t N;
+    int32_t D;             /* latent dim per step (1, or 2 for the heteroscedastic likelihood) */
+    int32_t Q;             /* number of cubature points */
+    const double* cub_x;   /* [D,Q] sigma points of the unit Gaussian (cubature.py:76-84) */
+    const double* cub_w;   /* [Q] */
+    const double* y;       /* [N] observations; NaN = missing */
+    const double* post_mean;  /* [N,D,1] */
+    const double* post_cov;   /* [N,D,D] */
+    double lr;             /* damping (inference.py:83-86) */
+    double power;          /* EP power */
+    int32_t ensure_psd;    /* utils.py:89-96 */
+    int32_t pad_;
+    /* site natural parameters, read (old) and overwritten (new) in place */
+    double* nat1;          /* [N,D,1] */
+    double* nat2;          /* [N,D,D] */
+    /* outputs (each nullable) */
+    double* site_mean;     /* [N,D,1]  reparametrised new sites = the next filter's pseudo_y */
+    double* site_cov;      /* [N,D,D]                                          pseudo_var */
+    double* out_mean;      /* [N,D,1]  the (mean, jacobian, hessian) triple inference() returns */
+    double* out_jac;       /* [N,D,1] */
+    double* out_hess;      /* [N,D,D] */
+    double* diffs;         /* [2] mean |delta nat1|, mean |delta nat2| (inference.py:79-80) */
+} bn_site_args;
+
+int bn_site_update(const bn_site_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* per-step value of the likelihood term of energy(): VI E_q[log p], Newton log p(y|m),
+ * EP/PL log Z at the cavity (computed in-kernel from post + nat).  values[N] nullable;
+ * sum: one double = nansum of the values (inference.py:218,321). */
+int bn_expected_density(const bn_site_args* a, double* values, double* sum,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* sum_n gaussian_expected_log_lik(pseudo_y_n, post_mean_n, post_cov_n, pseudo_var_n, mask_n) */
+int bn_gaussian_expected_log_lik(int64_t N, int D, const double* pseudo_y, const double* post_mean,
+                                 const double* post_cov, const double* pseudo_var, const uint8_t* mask,
+                                 double* values, double* sum,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* EP energy helper: sum_n [ log N(pseudo_y | cav_mean, pseudo_var/power + cav_cov) + pep_constant ]
+ * (basemodels.py:247-262; with_pep_constant=0 gives the PL variant, inference.py:406-411) */
+int bn_ep_pseudo_density(int64_t N, int D, double power, int with_pep_constant,
+                         const double* pseudo_y, const double* pseudo_var,
+                         const double* post_mean, const double* post_cov,
+                         const double* nat1, const double* nat2, const uint8_t* mask,
+                         double* sum, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BN_B200_H */

@@ -1,0 +1,186 @@
+// Host emulation of the filter / smoother kernels (TEST INFRASTRUCTURE, CPU only).
+//
+// The per-chunk bodies in csrc/filter_impl.cuh and csrc/smoother_impl.cuh are __host__ __device__;
+// this harness runs them in plain host loops (one iteration per GPU thread) with the same chunk
+// planning, SoA workspace layout, carry fold and first/last-step rules as the CUDA drivers, so the
+// arithmetic and indexing of the product kernels can be checked against the oracle on a machine
+// with no GPU.  Only the warp-shuffle scan kernel is replaced (by a sequential fold with the same
+// Alg::combine).  Never loaded by the product.
+#include <vector>
+#include <cstring>
+#include "../../bayesnewton_b200/csrc/filter_impl.cuh"
+#include "../../bayesnewton_b200/csrc/smoother_impl.cuh"
+
+namespace bn {
+void set_error(const char*, ...) {}
+
+template <class Alg>
+static void host_scan(const double* in, long long n, double* prefix) {
+    typename Alg::Elem acc, e, r;
+    for (long long i = 0; i < n; ++i) {
+        Alg::load(in, n, i, e);
+        if (i == 0) acc = e; else { Alg::combine(acc, e, r); acc = r; }
+        Alg::store(prefix, n, i, acc);
+    }
+}
+
+// time-sharded filter over `world` emulated ranks
+template <class MakeGen>
+static int emu_kf(MakeGen make, int d_unused, int form, long long N, int L, int world, const double* y, int D,
+                  const double* R, const unsigned char* mask, int return_predict, double* ell, double* fms,
+                  double* fPs, int dstate) {
+    (void)d_unused;
+    using Gen = decltype(make(0LL));
+    constexpr int d = Gen::d;
+    using Alg = FilterAlg<d>;
+    if (form == BN_SEQUENTIAL) {
+        Gen gen = make(0LL);
+        KfIO io{N, y, R, mask, fms, fPs, return_predict};
+        if (ell) kf_seq_body<Gen, true>(gen, io, ell); else kf_seq_body<Gen, false>(gen, io, nullptr);
+        return 0;
+    }
+    std::vector<long long> off(world + 1);
+    for (int r = 0; r <= world; ++r) off[r] = N * r / world;
+    std::vector<double> carries((size_t)world * Alg::kCarry);
+    std::vector<std::vector<double>> prefixes(world);
+    std::vector<long long> nch(world);
+    auto shard_io = [&](int r) {
+        long long o = off[r];
+        return KfIO{off[r + 1] - o, y + o * D, R + o * D * D, mask ? mask + o * D : nullptr,
+                    fms ? fms + o * dstate : nullptr, fPs ? fPs + o * dstate * dstate : nullptr, return_predict};
+    };
+    for (int r = 0; r < world; ++r) {
+        Gen gen = make(off[r]);
+        KfIO io = shard_io(r);
+        long long nc = (io.N + L - 1) / L;
+        nch[r] = nc;
+        std::vector<double> agg((size_t)nc * Alg::kElem);
+        prefixes[r].assign((size_t)nc * Alg::kElem, 0.0);
+        for (long long c = 0; c < nc; ++c) kf_reduce_chunk(gen, io, L, nc, r == 0, agg.data(), c);
+        host_scan<Alg>(agg.data(), nc, prefixes[r].data());
+        export_carry_body<Alg>(prefixes[r].data(), nc, carries.data() + (size_t)r * Alg::kCarry);
+    }
+    double total = 0.0;
+    for (int r = 0; r < world; ++r) {
+        Gen gen = make(off[r]);
+        KfIO io = shard_io(r);
+        double s0[64];
+        fold_carries_body<Alg>(carries.data(), 0, r, 1, s0);
+        std::vector<double> partials(nch[r]);
+        for (long long c = 0; c < nch[r]; ++c) {
+            if (ell) kf_apply_chunk<Gen, true>(gen, io, L, nch[r], r == 0, prefixes[r].data(), s0, partials.data(), c);
+            else kf_apply_chunk<Gen, false>(gen, io, L, nch[r], r == 0, prefixes[r].data(), s0, nullptr, c);
+        }
+        for (long long c = 0; c < nch[r]; ++c) total += partials[c];
+    }
+    if (ell) *ell = total;
+    return 0;
+}
+
+template <class MakeGen>
+static int emu_rts(MakeGen make, int form, long long N, int L, int world, const double* fms, const double* fPs,
+                   int return_full, double* sms, double* sPs, double* gains) {
+    using Gen = decltype(make(0LL));
+    constexpr int d = Gen::d, Df = Gen::D;
+    using Alg = SmootherAlg<d>;
+    const int od = return_full ? d : Df;
+    if (form == BN_SEQUENTIAL) {
+        Gen gen = make(0LL);
+        RtsIO io{N, fms, fPs, sms, sPs, gains, return_full};
+        rts_seq_body(gen, io);
+        return 0;
+    }
+    std::vector<long long> off(world + 1);
+    for (int r = 0; r <= world; ++r) off[r] = N * r / world;
+    std::vector<double> carries((size_t)world * Alg::kCarry);
+    std::vector<std::vector<double>> prefixes(world);
+    std::vector<long long> nch(world);
+    auto shard_io = [&](int r) {
+        long long o = off[r];
+        return RtsIO{off[r + 1] - o, fms + o * d, fPs + o * d * d, sms + o * od, sPs + o * od * od,
+                     gains ? gains + o * d * d : nullptr, return_full};
+    };
+    for (int r = 0; r < world; ++r) {
+        Gen gen = make(off[r]);
+        RtsIO io = shard_io(r);
+        long long nc = (io.N + L - 1) / L;
+        nch[r] = nc;
+        std::vector<double> agg((size_t)nc * Alg::kElem);
+        prefixes[r].assign((size_t)nc * Alg::kElem, 0.0);
+        for (long long c = 0; c < nc; ++c) rts_reduce_chunk(gen, io, L, nc, r == world - 1, agg.data(), c);
+        host_scan<Alg>(agg.data(), nc, prefixes[r].data());
+        export_carry_body<Alg>(prefixes[r].data(), nc, carries.data() + (size_t)r * Alg::kCarry);
+    }
+    for (int r = 0; r < world; ++r) {
+        Gen gen = make(off[r]);
+        RtsIO io = shard_io(r);
+        double s0[64];
+        fold_carries_body<Alg>(carries.data(), world - 1, r, -1, s0);
+        for (long long c = 0; c < nch[r]; ++c)
+            rts_apply_chunk(gen, io, L, nch[r], r == world - 1, prefixes[r].data(), s0, c);
+    }
+    return 0;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+#define EMU_MATERN(X) X(BN_MATERN12, 1) X(BN_MATERN32, 1) X(BN_MATERN32, 2) X(BN_MATERN52, 1) X(BN_MATERN52, 2) \
+    X(BN_MATERN72, 1)
+#define EMU_ARR(X) X(3, 1) X(4, 2) X(2, 2)
+
+extern "C" int emu_kalman_filter(const bn_kernel_spec* k, int form, long long N, int L, int world, const double* dt,
+                                 const double* y, const double* R, const unsigned char* mask, int return_predict,
+                                 double* ell, double* means, double* covs) {
+#define X(FAM, NC)                                                                                          \
+    if (k->family == FAM && k->n_components == NC) {                                                        \
+        auto make = [&](long long o) { MaternGen<FAM, NC> g; g.spec = *k; g.dt = dt + o; return g; };        \
+        return emu_kf(make, 0, form, N, L, world, y, NC, R, mask, return_predict, ell, means, covs,         \
+                      MaternGen<FAM, NC>::d);                                                               \
+    }
+    EMU_MATERN(X)
+#undef X
+    return -1;
+}
+
+extern "C" int emu_rts_smoother(const bn_kernel_spec* k, int form, long long N, int L, int world, const double* dt,
+                                const double* fm, const double* fP, int return_full, double* means, double* covs,
+                                double* gains) {
+#define X(FAM, NC)                                                                                          \
+    if (k->family == FAM && k->n_components == NC) {                                                        \
+        auto make = [&](long long o) { MaternGen<FAM, NC> g; g.spec = *k; g.dt = dt + o; return g; };        \
+        return emu_rts(make, form, N, L, world, fm, fP, return_full, means, covs, gains);                   \
+    }
+    EMU_MATERN(X)
+#undef X
+    return -1;
+}
+
+extern "C" int emu_kf_arrays(int form, long long N, int L, int d, int D, const double* As, const double* Qs,
+                             const double* H, const double* ys, const double* Rs, const double* m0, const double* P0,
+                             const unsigned char* masks, int return_predict, double* ell, double* fms, double* fPs) {
+#define X(DD, OD)                                                                                           \
+    if (d == DD && D == OD) {                                                                               \
+        auto make = [&](long long o) { return ArrayGen<DD, OD>{As + o * DD * DD, Qs + o * DD * DD, H, m0, P0}; }; \
+        return emu_kf(make, 0, form, N, L, 1, ys, OD, Rs, masks, return_predict, ell, fms, fPs, DD);        \
+    }
+    EMU_ARR(X)
+#undef X
+    return -1;
+}
+
+extern "C" int emu_rts_arrays(int form, long long N, int L, int d, int Df, const double* fms, const double* fPs,
+                              const double* As, const double* Qs, const double* H, int return_full, double* sms,
+                              double* sPs, double* gains) {
+#define X(DD, OD)                                                                                           \
+    if (d == DD && Df == OD) {                                                                              \
+        auto make = [&](long long o) {                                                                      \
+            return ArrayGen<DD, OD>{As + o * DD * DD, Qs + o * DD * DD, H, nullptr, nullptr};               \
+        };                                                                                                  \
+        return emu_rts(make, form, N, L, 1, fms, fPs, return_full, sms, sPs, gains);                        \
+    }
+    EMU_ARR(X)
+#undef X
+    return -1;
+}
