@@ -1,0 +1,98 @@
+"""ctypes binding of libbn_b200.so (the C ABI in include/bn_b200.h).
+
+There is no CPU fallback and no alternative backend: if the CUDA library is missing or a call
+fails, the error is raised.  torch is used for device memory, streams and (in distributed.py)
+the NCCL plumbing only.
+"""
+import ctypes as C
+import os
+
+import torch  # noqa: F401  (loads libcudart before our library resolves it)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libbn_b200.so')
+
+BN_SEQUENTIAL, BN_SCAN = 0, 1
+BN_MATERN12, BN_MATERN32, BN_MATERN52, BN_MATERN72 = 1, 2, 3, 4
+FAMILY_DIM = {BN_MATERN12: 1, BN_MATERN32: 2, BN_MATERN52: 3, BN_MATERN72: 4}
+BN_LIK_GAUSSIAN, BN_LIK_BERNOULLI_PROBIT, BN_LIK_BERNOULLI_LOGIT = 1, 2, 3
+BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_LIK_HETEROSCEDASTIC_EXP = 4, 5
+BN_METHOD_VI, BN_METHOD_EP, BN_METHOD_NEWTON, BN_METHOD_PL = 1, 2, 3, 4
+BN_MAX_COMPONENTS = 4
+
+
+class KernelSpec(C.Structure):
+    _fields_ = [('family', C.c_int32), ('n_components', C.c_int32),
+                ('variance', C.c_double * BN_MAX_COMPONENTS), ('lengthscale', C.c_double * BN_MAX_COMPONENTS)]
+
+
+class SiteArgs(C.Structure):
+    _fields_ = [('method', C.c_int32), ('likelihood', C.c_int32), ('lik_param', C.c_double), ('N', C.c_int64),
+                ('D', C.c_int32), ('Q', C.c_int32), ('cub_x', C.c_void_p), ('cub_w', C.c_void_p), ('y', C.c_void_p),
+                ('post_mean', C.c_void_p), ('post_cov', C.c_void_p), ('lr', C.c_double), ('power', C.c_double),
+                ('ensure_psd', C.c_int32), ('pad_', C.c_int32), ('nat1', C.c_void_p), ('nat2', C.c_void_p),
+                ('site_mean', C.c_void_p), ('site_cov', C.c_void_p), ('out_mean', C.c_void_p),
+                ('out_jac', C.c_void_p), ('out_hess', C.c_void_p), ('diffs', C.c_void_p)]
+
+
+class BnError(RuntimeError):
+    pass
+
+
+_P, _I, _L, _Z, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
+_KS, _SA = C.POINTER(KernelSpec), C.POINTER(SiteArgs)
+
+# every symbol include/bn_b200.h declares, with its argument types
+SIGNATURES = {
+    'bn_last_error': (C.c_char_p, []),
+    'bn_version': (_I, []),
+    'bn_state_dim': (_I, [_KS]),
+    'bn_discretise': (_I, [_KS, _L, _P, _P, _P, _P]),
+    'bn_workspace_bytes': (_Z, [_L, _I, _I]),
+    'bn_kf_arrays': (_I, [_I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_rts_arrays': (_I, [_I, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_kalman_filter': (_I, [_KS, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_rts_smoother': (_I, [_KS, _I, _L, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_kf_carry_len': (_I, [_I]),
+    'bn_rts_carry_len': (_I, [_I]),
+    'bn_kf_shard_reduce': (_I, [_KS, _L, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    'bn_kf_shard_apply': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_rts_shard_reduce': (_I, [_KS, _L, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    'bn_rts_shard_apply': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_site_update': (_I, [_SA, _P, _Z, _P]),
+    'bn_likelihood_stats': (_I, [_SA, _P, _P, _P, _P]),
+    'bn_expected_density': (_I, [_SA, _P, _P, _P, _Z, _P]),
+    'bn_gaussian_expected_log_lik': (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'bn_ep_pseudo_density': (_I, [_L, _I, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """the loaded library; raises if it has not been built (python -m bayesnewton_b200.build)"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BnError('%s is missing: build it with `python -m bayesnewton_b200.build` '
+                          '(there is no CPU fallback)' % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header and library out of sync
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().bn_last_error().decode()
+        raise BnError('libbn_b200 call failed (code %d): %s' % (rc, msg))
+
+
+def kernel_spec(family, variances, lengthscales):
+    s = KernelSpec()
+    s.family, s.n_components = family, len(variances)
+    for i, (v, l) in enumerate(zip(variances, lengthscales)):
+        s.variance[i], s.lengthscale[i] = float(v), float(l)
+    return s

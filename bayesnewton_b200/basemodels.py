@@ -1,0 +1,141 @@
+"""Host orchestration of a temporal Markov GP (mirror of bayesnewton/basemodels.py:52-100,103-262,625-764).
+
+State (sites in both parametrisations, posterior marginals) lives in float64 CUDA tensors; every
+O(N) operation is one libbn_b200 call.  Only the temporal case is covered here (spatio-temporal
+projection is a `next` row of SURVEY section 8f).
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._util import as_dev, as_mask, device, ptr, stream_ptr, workspace
+from .kernels import Independent
+
+
+def input_admin(t, y):
+    """sort by time, float64, dt = [0, diff(t)]  (utils.py:234-265, temporal inputs)"""
+    t = np.asarray(t, dtype=np.float64).reshape(-1)
+    y = np.asarray(y, dtype=np.float64).reshape(t.shape[0], -1)
+    ind = np.argsort(t, kind='stable')
+    t, y = t[ind], y[ind]
+    dt = np.concatenate([[0.0], np.diff(t)])
+    return t, y, dt
+
+
+class GaussianDistribution:
+    """sites in (mean, covariance) and natural (nat1, nat2 = cov^-1) form (basemodels.py:52-100)"""
+
+    def __init__(self, mean, covariance):
+        self.mean_, self.covariance_ = as_dev(mean), as_dev(covariance)
+        self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
+
+    def __call__(self):
+        return self.mean, self.covariance
+
+    mean = property(lambda self: self.mean_)
+    covariance = property(lambda self: self.covariance_)
+    nat1 = property(lambda self: self.nat1_)
+    nat2 = property(lambda self: self.nat2_)
+
+    @staticmethod
+    def reparametrise(param1, param2):
+        # only used at construction and by update_mean_cov (never inside an inference iteration,
+        # where the fused site kernel reparametrises in registers): batched Cholesky solve
+        chol = torch.linalg.cholesky(param2)
+        eye = torch.eye(param2.shape[-1], dtype=param2.dtype, device=param2.device).expand_as(param2)
+        return torch.cholesky_solve(param1, chol), torch.cholesky_solve(eye, chol)
+
+    def update_mean_cov(self, mean, covariance):
+        self.mean_, self.covariance_ = as_dev(mean), as_dev(covariance)
+        self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
+
+
+class MarkovGaussianProcess:
+    """f ~ GP in SDE form; inference by Kalman filtering / RTS smoothing (basemodels.py:625-764)"""
+    method = None   # BN_METHOD_*, set by the inference mixin
+    power = 1.0
+
+    def __init__(self, kernel, likelihood, X, Y, R=None, parallel=None):
+        if R is not None:
+            raise NotImplementedError('spatio-temporal inputs are outside the current hot-path scope')
+        if parallel is None:  # the reference switches the scan on when it runs on a GPU (basemodels.py:642-643)
+            parallel = True
+        self.kernel, self.likelihood, self.parallel = kernel, likelihood, parallel
+        t, Yh, dt = input_admin(X, Y)
+        self.num_data = t.shape[0]
+        self.X, self.Y_host = t, Yh
+        self.Y = as_dev(Yh)
+        self.dt = as_dev(dt)
+        self.dt_smoother = as_dev(np.concatenate([dt[1:], [0.0]]))
+        H = kernel.measurement_model()
+        self.func_dim = H.shape[0]
+        self.obs_dim = Yh.shape[1]
+        self.state_dim = kernel.stationary_covariance().shape[0]
+        D = self.func_dim if isinstance(kernel, Independent) else self.obs_dim
+        if D != self.func_dim or self.obs_dim != 1:
+            raise NotImplementedError('one observation per step and one site per latent are supported')
+        N = self.num_data
+        self.pseudo_likelihood = GaussianDistribution(
+            mean=torch.zeros((N, D, 1), dtype=torch.float64, device=device()),
+            covariance=1e2 * torch.eye(D, dtype=torch.float64, device=device()).repeat(N, 1, 1))
+        self.posterior_mean = torch.zeros((N, D, 1), dtype=torch.float64, device=device())
+        self.posterior_variance = torch.eye(D, dtype=torch.float64, device=device()).repeat(N, 1, 1)
+        mask_y = np.isnan(Yh)
+        self.mask_y = mask_y if mask_y.any() else None
+        if D == self.obs_dim:
+            self.mask_pseudo_y = as_mask(mask_y) if mask_y.any() else None
+        else:  # multi-latent likelihood: no mask on the sites (basemodels.py:141-142)
+            self.mask_pseudo_y = None
+
+    # ---- basemodels.py:655-661
+    @staticmethod
+    def filter(*args, **kwargs):
+        return ops.kalman_filter(*args, **kwargs)
+
+    @staticmethod
+    def smoother(*args, **kwargs):
+        return ops.rauch_tung_striebel_smoother(*args, **kwargs)
+
+    def compute_full_pseudo_lik(self):
+        return self.pseudo_likelihood.mean, self.pseudo_likelihood.covariance
+
+    def update_posterior(self):
+        """filter then smoother (basemodels.py:689-706); the unused log-likelihood and gains are not computed"""
+        pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
+        _, (fm, fP) = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
+                                  parallel=self.parallel, want_ell=False)
+        sm, sP, _ = self.smoother(self.dt_smoother, self.kernel, fm, fP, parallel=self.parallel, want_gains=False)
+        self.posterior_mean, self.posterior_variance = sm, sP
+
+    def compute_log_lik(self, pseudo_y=None, pseudo_var=None):
+        """log normaliser of the pseudo model = the filter's log-likelihood (basemodels.py:726-741)"""
+        if pseudo_y is None:
+            pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
+        ell, _ = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
+                             parallel=self.parallel, want_states=False)
+        return ell
+
+    def expected_density_pseudo(self):
+        pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
+        N, D = pseudo_y.shape[0], pseudo_y.shape[1]
+        out = torch.zeros((), dtype=torch.float64, device=pseudo_y.device)
+        ws, nb = workspace(N, self.state_dim, D)
+        _lib.check(_lib.lib().bn_gaussian_expected_log_lik(
+            N, D, ptr(pseudo_y), ptr(self.posterior_mean), ptr(self.posterior_variance), ptr(pseudo_var),
+            ptr(self.mask_pseudo_y), None, ptr(out), ptr(ws), nb, stream_ptr()))
+        return out
+
+    def compute_kl(self):
+        """KL[q || p] = sum_n E_q[log N(pseudo_y_n | f_n, pseudo_var_n)] - log Z_pseudo  (basemodels.py:708-724)"""
+        return self.expected_density_pseudo() - self.compute_log_lik()
+
+    def conditional_posterior_to_data(self, batch_ind=None, post_mean=None, post_cov=None):
+        return (self.posterior_mean if post_mean is None else post_mean,
+                self.posterior_variance if post_cov is None else post_cov)
+
+    def predict(self, X=None):
+        """posterior marginals at the training inputs (test-point prediction: SURVEY section 8f, next)"""
+        if X is not None:
+            raise NotImplementedError('prediction at new inputs is a `next` row (utils.temporal_conditional)')
+        self.update_posterior()
+        return self.posterior_mean.reshape(self.num_data, -1), self.posterior_variance

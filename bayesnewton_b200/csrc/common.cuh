@@ -103,6 +103,7 @@ __device__ __forceinline__ void block_sum_store(double v, double* partials) {
         __syncthreads();
     }
     if (threadIdx.x == 0) partials[blockIdx.x] = sh_bs[0];
+    __syncthreads();  // the shared buffer is reused by the next call
 }
 
 }  // namespace bn

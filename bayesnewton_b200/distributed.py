@@ -1,0 +1,134 @@
+"""Time-sharded filter / smoother: the two-level associative scan across GPUs.
+
+The time axis is cut into contiguous shards, one per rank.  Per pass: (1) every rank reduces its
+shard to ONE carry -- the filtering element (A, b, C, J, eta), 3d^2+2d doubles, or the smoothing
+element (E, g, L), 2d^2+d doubles (bn_*_shard_reduce); (2) the carries are all-gathered over
+NCCL/NVLink (264 B / 168 B per rank at d = 3); (3) every rank folds the carries that precede it in
+scan order into its incoming state and runs its local pass (bn_*_shard_apply).  Site updates are
+pointwise in time and need no communication; scalars (log-likelihood, energy terms) are summed
+with one all-reduce.  Associativity: bayesnewton/ops.py:203-219 (filter), :328-335 (smoother).
+
+`filter_smoother_in_shards` runs the same three steps for n_shards shards inside ONE process (no
+collective): it is what the single-GPU tests use to validate the carry path at full size.
+"""
+import torch
+
+from . import _lib
+from ._util import as_dev, as_mask, ptr, stream_ptr
+
+
+def _ws(N, d, D, device):
+    nb = _lib.lib().bn_workspace_bytes(int(N), d, D)
+    return torch.empty(int(nb), dtype=torch.uint8, device=device), int(nb)
+
+
+class TimeShard:
+    """the local shard of one rank: device tensors for its steps, plus private workspaces that keep
+    the chunk prefixes alive between the reduce and the apply call of a pass"""
+
+    def __init__(self, kernel, dt, dt_smoother, rank, world):
+        self.spec = kernel.spec()
+        if self.spec is None:
+            raise NotImplementedError('time sharding needs a kernel with an in-library discretisation')
+        self.rank, self.world = rank, world
+        self.dt, self.dts = as_dev(dt).reshape(-1), as_dev(dt_smoother).reshape(-1)
+        self.N = self.dt.shape[0]
+        self.d = _lib.lib().bn_state_dim(self.spec)
+        self.D = self.spec.n_components
+        dev = self.dt.device
+        self.ws_f, self.nb_f = _ws(self.N, self.d, self.D, dev)
+        self.ws_s, self.nb_s = _ws(self.N, self.d, self.D, dev)
+        self.kf_len = _lib.lib().bn_kf_carry_len(self.d)
+        self.rts_len = _lib.lib().bn_rts_carry_len(self.d)
+
+    # ---- filter
+    def kf_reduce(self, y, R):
+        carry = torch.empty(self.kf_len, dtype=torch.float64, device=self.dt.device)
+        _lib.check(_lib.lib().bn_kf_shard_reduce(self.spec, self.N, int(self.rank == 0), ptr(self.dt), ptr(y), ptr(R),
+                                                 ptr(carry), ptr(self.ws_f), self.nb_f, stream_ptr()))
+        return carry
+
+    def kf_apply(self, carries, y, R, mask=None, want_ell=True, return_predict=False):
+        dev = self.dt.device
+        ell = torch.zeros((), dtype=torch.float64, device=dev) if want_ell else None
+        fm = torch.empty((self.N, self.d, 1), dtype=torch.float64, device=dev)
+        fP = torch.empty((self.N, self.d, self.d), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().bn_kf_shard_apply(self.spec, self.N, self.rank, self.world, ptr(carries), ptr(self.dt),
+                                                ptr(y), ptr(R), ptr(mask), int(return_predict), ptr(ell), ptr(fm),
+                                                ptr(fP), ptr(self.ws_f), self.nb_f, stream_ptr()))
+        return ell, fm, fP
+
+    # ---- smoother
+    def rts_reduce(self, fm, fP):
+        carry = torch.empty(self.rts_len, dtype=torch.float64, device=self.dt.device)
+        _lib.check(_lib.lib().bn_rts_shard_reduce(self.spec, self.N, int(self.rank == self.world - 1), ptr(self.dts),
+                                                  ptr(fm), ptr(fP), ptr(carry), ptr(self.ws_s), self.nb_s,
+                                                  stream_ptr()))
+        return carry
+
+    def rts_apply(self, carries, fm, fP, return_full=False):
+        dev = self.dt.device
+        od = self.d if return_full else self.D
+        sm = torch.empty((self.N, od, 1), dtype=torch.float64, device=dev)
+        sP = torch.empty((self.N, od, od), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().bn_rts_shard_apply(self.spec, self.N, self.rank, self.world, ptr(carries), ptr(self.dts),
+                                                 ptr(fm), ptr(fP), int(return_full), ptr(sm), ptr(sP), None,
+                                                 ptr(self.ws_s), self.nb_s, stream_ptr()))
+        return sm, sP
+
+
+def _all_gather(carry, world):
+    """carries[world, len] over the default process group (NCCL on GPUs, gloo in the CPU tests)"""
+    import torch.distributed as dist
+    out = torch.empty((world,) + tuple(carry.shape), dtype=carry.dtype, device=carry.device)
+    dist.all_gather_into_tensor(out, carry.contiguous())
+    return out
+
+
+def sharded_update_posterior(shard, y, R, mask=None, want_ell=False):
+    """update_posterior (basemodels.py:689-706) on a time-sharded model: 2 carry all-gathers.
+    Every rank passes ITS shard of the sites; returns (ell_local_or_None, post_mean, post_cov) for its steps."""
+    c = shard.kf_reduce(y, R)
+    carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
+    ell, fm, fP = shard.kf_apply(carries, y, R, mask, want_ell=want_ell)
+    c = shard.rts_reduce(fm, fP)
+    carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
+    sm, sP = shard.rts_apply(carries, fm, fP)
+    return ell, sm, sP
+
+
+def sharded_log_lik(shard, y, R, mask=None):
+    """compute_log_lik (basemodels.py:726-741): local partial; the caller all-reduces the scalar"""
+    c = shard.kf_reduce(y, R)
+    carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
+    dev = shard.dt.device
+    ell = torch.zeros((), dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().bn_kf_shard_apply(shard.spec, shard.N, shard.rank, shard.world, ptr(carries), ptr(shard.dt),
+                                            ptr(y), ptr(R), ptr(mask), 0, ptr(ell), None, None, ptr(shard.ws_f),
+                                            shard.nb_f, stream_ptr()))
+    return ell
+
+
+def shard_bounds(N, world):
+    return [N * r // world for r in range(world + 1)]
+
+
+def filter_smoother_in_shards(kernel, dt, y, R, mask, n_shards):
+    """single-process run of the sharded algorithm over n_shards shards (validation of the carry path)"""
+    dt, y, R = as_dev(dt).reshape(-1), as_dev(y), as_dev(R)
+    mk = as_mask(mask)
+    N = dt.shape[0]
+    dts = torch.cat([dt[1:], torch.zeros(1, dtype=dt.dtype, device=dt.device)])
+    b = shard_bounds(N, n_shards)
+    shards = [TimeShard(kernel, dt[b[r]:b[r + 1]], dts[b[r]:b[r + 1]], r, n_shards) for r in range(n_shards)]
+    D = shards[0].D
+    ys = [y.reshape(N, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
+    Rs = [R.reshape(N, D, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
+    ms = [None if mk is None else mk.reshape(N, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
+    carries = torch.stack([s.kf_reduce(ys[r], Rs[r]) for r, s in enumerate(shards)])
+    filt = [s.kf_apply(carries, ys[r], Rs[r], ms[r]) for r, s in enumerate(shards)]
+    carries = torch.stack([s.rts_reduce(filt[r][1], filt[r][2]) for r, s in enumerate(shards)])
+    smo = [s.rts_apply(carries, filt[r][1], filt[r][2]) for r, s in enumerate(shards)]
+    return dict(ell=sum(f[0] for f in filt), filter_mean=torch.cat([f[1] for f in filt]),
+                filter_cov=torch.cat([f[2] for f in filt]), post_mean=torch.cat([s[0] for s in smo]),
+                post_cov=torch.cat([s[1] for s in smo]))

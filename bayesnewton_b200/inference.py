@@ -1,0 +1,108 @@
+"""Inference mixins with the reference's interface (bayesnewton/inference.py:42-428):
+``model.inference(lr, **kw)`` runs update_posterior -> site statistics -> Newton step in natural
+parameters -> damped update -> update_posterior, and ``model.energy()`` returns the scheme's
+objective.  The per-step work between the two posterior updates (inference.py:72-86 plus the
+``update_variational_params`` body of the scheme) is ONE fused kernel (bn_site_update).
+"""
+import torch
+
+from . import _lib
+from ._util import ptr, stream_ptr, workspace
+
+
+class InferenceMixin:
+    method = None
+    power = 1.0
+
+    def _site_args(self, cubature=None):
+        a, keep = self.likelihood.site_args(self.method, self.Y, self.posterior_mean, self.posterior_variance,
+                                            cubature, self.power)
+        a.nat1, a.nat2 = self.pseudo_likelihood.nat1_.data_ptr(), self.pseudo_likelihood.nat2_.data_ptr()
+        return a, keep
+
+    def inference(self, lr=1., batch_ind=None, cubature=None, ensure_psd=True, return_state=True, **kwargs):
+        """one iteration (inference.py:65-90).  Returns ((mean, jacobian, hessian), (diff1, diff2));
+        with return_state=False the triple is not written to HBM (the reference's jit drops it as dead code)"""
+        if batch_ind is not None and len(batch_ind) != self.num_data:
+            raise NotImplementedError('mini-batched site updates are outside the hot-path scope (SURVEY A.15)')
+        self.update_posterior()
+        a, keep = self._site_args(cubature)
+        N, D = a.N, a.D
+        dev = self.posterior_mean.device
+        a.lr, a.ensure_psd = float(lr), int(bool(ensure_psd))
+        pl = self.pseudo_likelihood
+        a.site_mean, a.site_cov = pl.mean_.data_ptr(), pl.covariance_.data_ptr()
+        state = (None, None, None)
+        if return_state:
+            state = (torch.empty((N, D, 1), dtype=torch.float64, device=dev),
+                     torch.empty((N, D, 1), dtype=torch.float64, device=dev),
+                     torch.empty((N, D, D), dtype=torch.float64, device=dev))
+            a.out_mean, a.out_jac, a.out_hess = (ptr(s) for s in state)
+        diffs = torch.zeros((2,), dtype=torch.float64, device=dev)
+        a.diffs = diffs.data_ptr()
+        ws, nb = workspace(N, self.state_dim, D)
+        _lib.check(_lib.lib().bn_site_update(a, ptr(ws), nb, stream_ptr()))
+        self.update_posterior()
+        return state, (diffs[0], diffs[1])
+
+    def expected_density(self, cubature=None):
+        """nansum over steps of the scheme's likelihood term (VI: E_q[log p]; Newton: log p(y|m); EP/PL: log Z)"""
+        a, keep = self._site_args(cubature)
+        out = torch.zeros((), dtype=torch.float64, device=self.posterior_mean.device)
+        ws, nb = workspace(a.N, self.state_dim, a.D)
+        _lib.check(_lib.lib().bn_expected_density(a, None, ptr(out), ptr(ws), nb, stream_ptr()))
+        return out
+
+    def energy(self, batch_ind=None, cubature=None, **kwargs):
+        raise NotImplementedError
+
+
+class VariationalInference(InferenceMixin):
+    """natural-gradient VI, CVI form (inference.py:160-222)"""
+    method = _lib.BN_METHOD_VI
+
+    def energy(self, batch_ind=None, cubature=None, **kwargs):
+        return -(self.expected_density(cubature) - self.compute_kl())
+
+
+class Newton(InferenceMixin):
+    """Newton = Laplace (inference.py:99-157)"""
+    method = _lib.BN_METHOD_NEWTON
+
+    def energy(self, batch_ind=None, cubature=None, **kwargs):
+        return -(self.expected_density(cubature) - self.compute_kl())
+
+
+Laplace = Newton
+
+
+class ExpectationPropagation(InferenceMixin):
+    """power EP (inference.py:225-325)"""
+    method = _lib.BN_METHOD_EP
+
+    def _pseudo_density(self, power, with_const):
+        pl = self.pseudo_likelihood
+        N, D = pl.mean.shape[0], pl.mean.shape[1]
+        out = torch.zeros((), dtype=torch.float64, device=pl.mean.device)
+        ws, nb = workspace(N, self.state_dim, D)
+        _lib.check(_lib.lib().bn_ep_pseudo_density(
+            N, D, float(power), int(with_const), ptr(pl.mean), ptr(pl.covariance), ptr(self.posterior_mean),
+            ptr(self.posterior_variance), ptr(pl.nat1), ptr(pl.nat2), ptr(self.mask_pseudo_y), ptr(out), ptr(ws), nb,
+            stream_ptr()))
+        return out
+
+    def energy(self, batch_ind=None, cubature=None, **kwargs):
+        lel = self.expected_density(cubature)
+        lel_pseudo = self._pseudo_density(self.power, True)
+        lZ = self.compute_log_lik()
+        return -(lZ + 1. / self.power * (lel - lel_pseudo))
+
+
+class PosteriorLinearisation(ExpectationPropagation):
+    """iterated statistical linear regression; its energy is the EP energy at power 1 (inference.py:328-428)"""
+    method = _lib.BN_METHOD_PL
+
+    def energy(self, batch_ind=None, cubature=None, **kwargs):
+        lZ = self.expected_density(cubature)
+        lZ_pseudo = self._pseudo_density(1.0, False)
+        return -(self.compute_log_lik() + (lZ - lZ_pseudo))

@@ -1,0 +1,30 @@
+"""Model classes = inference scheme x Markov GP, assembled by multiple inheritance exactly like the
+reference's glue file (bayesnewton/models.py:118-152, build_model in bayesnewton/__init__.py:13-14)."""
+from .basemodels import MarkovGaussianProcess
+from .inference import ExpectationPropagation, Newton, PosteriorLinearisation, VariationalInference
+
+
+class MarkovVariationalGP(VariationalInference, MarkovGaussianProcess):
+    pass
+
+
+class MarkovExpectationPropagationGP(ExpectationPropagation, MarkovGaussianProcess):
+    def __init__(self, kernel, likelihood, X, Y, R=None, power=1., parallel=None):
+        self.power = power
+        super().__init__(kernel, likelihood, X, Y, R=R, parallel=parallel)
+
+
+class MarkovNewtonGP(Newton, MarkovGaussianProcess):
+    pass
+
+
+MarkovLaplaceGP = MarkovNewtonGP
+
+
+class MarkovPosteriorLinearisationGP(PosteriorLinearisation, MarkovGaussianProcess):
+    pass
+
+
+def build_model(model, inf):
+    """dynamic glue, as bayesnewton.build_model"""
+    return type(inf.__name__ + model.__name__, (inf, model), {})

@@ -1,0 +1,133 @@
+"""Markov-GP ops with the reference's signatures (bayesnewton/ops.py:149-380), executed by libbn_b200.
+
+    kalman_filter(dt, kernel, y, noise_cov, mask=None, parallel=False, return_predict=False)   ops.py:256
+    rauch_tung_striebel_smoother(dt, kernel, filter_mean, filter_cov, return_full, parallel)    ops.py:357
+    _sequential_kf / _parallel_kf (As, Qs, H, ys, noise_covs, m0, P0, masks, return_predict)    ops.py:154,237
+    _sequential_rts / _parallel_rts (fms, fPs, As, Qs, H, return_full)                          ops.py:288,338
+    process_noise_covariance(A, Pinf)                                                           ops.py:149
+
+Inputs may be numpy arrays or torch tensors (host or device); outputs are float64 CUDA tensors
+with the reference's shapes ([N,d,1], [N,d,d], ...).  `parallel=False` runs the sequential
+recursion on one GPU thread (the reference's lax.scan order); `parallel=True` runs the blocked
+temporally-parallel scan.  Extra keyword `want_ell=False` skips the log-likelihood, the dead
+code XLA would eliminate in update_posterior (basemodels.py:694,701).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._util import as_dev, as_mask, ptr, stream_ptr, workspace
+from .kernels import discretise
+
+__all__ = ['kalman_filter', 'rauch_tung_striebel_smoother', '_sequential_kf', '_parallel_kf', '_sequential_rts',
+           '_parallel_rts', 'process_noise_covariance']
+
+
+def process_noise_covariance(A, Pinf):
+    A, Pinf = as_dev(A), as_dev(Pinf)
+    return Pinf - A @ Pinf @ A.transpose(-1, -2)
+
+
+def _form(parallel):
+    return _lib.BN_SCAN if parallel else _lib.BN_SEQUENTIAL
+
+
+def _kf_arrays(form, As, Qs, H, ys, noise_covs, m0, P0, masks, return_predict, want_ell=True, want_states=True):
+    As, Qs, H, ys, Rs, m0, P0 = (as_dev(a) for a in (As, Qs, H, ys, noise_covs, m0, P0))
+    N, d = As.shape[0], As.shape[-1]
+    D = H.shape[0]
+    mk = as_mask(masks)
+    ell = torch.zeros((), dtype=torch.float64, device=As.device) if want_ell else None
+    fms = torch.empty((N, d, 1), dtype=torch.float64, device=As.device) if want_states else None
+    fPs = torch.empty((N, d, d), dtype=torch.float64, device=As.device) if want_states else None
+    ws, nb = workspace(N, d, D)
+    _lib.check(_lib.lib().bn_kf_arrays(form, N, d, D, ptr(As), ptr(Qs), ptr(H), ptr(ys), ptr(Rs), ptr(m0), ptr(P0),
+                                       ptr(mk), int(bool(return_predict)), ptr(ell), ptr(fms), ptr(fPs),
+                                       ptr(ws), nb, stream_ptr()))
+    return ell, fms, fPs
+
+
+def _sequential_kf(As, Qs, H, ys, noise_covs, m0, P0, masks, return_predict=False):
+    return _kf_arrays(_lib.BN_SEQUENTIAL, As, Qs, H, ys, noise_covs, m0, P0, masks, return_predict)
+
+
+def _parallel_kf(As, Qs, H, ys, noise_covs, m0, P0, masks, return_predict=False):
+    return _kf_arrays(_lib.BN_SCAN, As, Qs, H, ys, noise_covs, m0, P0, masks, return_predict)
+
+
+def _rts_arrays(form, fms, fPs, As, Qs, H, return_full, want_gains=True):
+    fms, fPs, As, Qs, H = (as_dev(a) for a in (fms, fPs, As, Qs, H))
+    N, d = As.shape[0], As.shape[-1]
+    Df = H.shape[0]
+    od = d if return_full else Df
+    sms = torch.empty((N, od, 1), dtype=torch.float64, device=As.device)
+    sPs = torch.empty((N, od, od), dtype=torch.float64, device=As.device)
+    gains = torch.empty((N, d, d), dtype=torch.float64, device=As.device) if want_gains else None
+    ws, nb = workspace(N, d, Df)
+    _lib.check(_lib.lib().bn_rts_arrays(form, N, d, Df, ptr(fms), ptr(fPs), ptr(As), ptr(Qs), ptr(H),
+                                        int(bool(return_full)), ptr(sms), ptr(sPs), ptr(gains), ptr(ws), nb,
+                                        stream_ptr()))
+    return sms, sPs, gains
+
+
+def _sequential_rts(fms, fPs, As, Qs, H, return_full):
+    return _rts_arrays(_lib.BN_SEQUENTIAL, fms, fPs, As, Qs, H, return_full)
+
+
+def _parallel_rts(fms, fPs, As, Qs, H, return_full):
+    return _rts_arrays(_lib.BN_SCAN, fms, fPs, As, Qs, H, return_full)
+
+
+def kalman_filter(dt, kernel, y, noise_cov, mask=None, parallel=False, return_predict=False, want_ell=True,
+                  want_states=True):
+    """p(f_n | y_1..y_n) for all n; returns ell, (means [N,d,1], covs [N,d,d])"""
+    dt = as_dev(dt).reshape(-1)
+    N = dt.shape[0]
+    spec = kernel.spec() if hasattr(kernel, 'spec') else None
+    if spec is None:  # generic path of the reference: materialise As, Qs, then the array-level filter
+        As, Qs = discretise(kernel, dt)
+        Pinf = as_dev(kernel.stationary_covariance())
+        minf = torch.zeros((Pinf.shape[0], 1), dtype=torch.float64, device=dt.device)
+        ell, m, P = _kf_arrays(_form(parallel), As, Qs, kernel.measurement_model(), y, noise_cov, minf, Pinf, mask,
+                               return_predict, want_ell, want_states)
+        return ell, (m, P)
+    y, R = as_dev(y), as_dev(noise_cov)
+    d = _lib.lib().bn_state_dim(spec)
+    D = spec.n_components
+    if y.numel() != N * D or R.numel() != N * D * D:
+        raise ValueError('y must be [N,%d,1] and noise_cov [N,%d,%d] for N = %d steps' % (D, D, D, N))
+    mk = as_mask(mask)
+    ell = torch.zeros((), dtype=torch.float64, device=dt.device) if want_ell else None
+    means = torch.empty((N, d, 1), dtype=torch.float64, device=dt.device) if want_states else None
+    covs = torch.empty((N, d, d), dtype=torch.float64, device=dt.device) if want_states else None
+    ws, nb = workspace(N, d, D)
+    _lib.check(_lib.lib().bn_kalman_filter(spec, _form(parallel), N, ptr(dt), ptr(y), ptr(R), ptr(mk),
+                                           int(bool(return_predict)), ptr(ell), ptr(means), ptr(covs), ptr(ws), nb,
+                                           stream_ptr()))
+    return ell, (means, covs)
+
+
+def rauch_tung_striebel_smoother(dt, kernel, filter_mean, filter_cov, return_full=False, parallel=False,
+                                 want_gains=True):
+    """p(f_n | y_1..y_N); dt is the step OUT OF n (basemodels.py:700).  Returns (means, covs, gains)"""
+    dt = as_dev(dt).reshape(-1)
+    N = dt.shape[0]
+    spec = kernel.spec() if hasattr(kernel, 'spec') else None
+    if spec is None:
+        As, Qs = discretise(kernel, dt)
+        return _rts_arrays(_form(parallel), filter_mean, filter_cov, As, Qs, kernel.measurement_model(), return_full,
+                           want_gains)
+    fm, fP = as_dev(filter_mean), as_dev(filter_cov)
+    d = _lib.lib().bn_state_dim(spec)
+    Df = spec.n_components
+    if fm.numel() != N * d or fP.numel() != N * d * d:
+        raise ValueError('filter_mean must be [N,%d,1] and filter_cov [N,%d,%d] for N = %d' % (d, d, d, N))
+    od = d if return_full else Df
+    means = torch.empty((N, od, 1), dtype=torch.float64, device=dt.device)
+    covs = torch.empty((N, od, od), dtype=torch.float64, device=dt.device)
+    gains = torch.empty((N, d, d), dtype=torch.float64, device=dt.device) if want_gains else None
+    ws, nb = workspace(N, d, Df)
+    _lib.check(_lib.lib().bn_rts_smoother(spec, _form(parallel), N, ptr(dt), ptr(fm), ptr(fP),
+                                          int(bool(return_full)), ptr(means), ptr(covs), ptr(gains), ptr(ws), nb,
+                                          stream_ptr()))
+    return means, covs, gains

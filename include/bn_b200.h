@@ -19,8 +19,6 @@
  *   bn_expected_density    the value-only likelihood term of energy()
  *                          inference.py:130-154,197-222,286-325,373-428
  *   bn_gaussian_expected_log_lik   vmap(gaussian_expected_log_lik) utils.py:510-531, basemodels.py:715-721
- *   bn_kalman_filter_grad  d(ell)/d(kernel hyper-parameters) that objax.GradValues obtains by
- *                          reverse-mode AD through kalman_filter (README.md:59, basemodels.py:726-741)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns
@@ -138,15 +136,6 @@ int bn_rts_shard_apply(const bn_kernel_spec* k, int64_t N, int rank, int world, 
                        double* means, double* covs, double* gains,
                        void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- hyper-parameter gradient of the filter log-likelihood ------------------------------ */
-/* grad[2*n_components]: d ell / d variance_c, d ell / d lengthscale_c (untransformed; the host
- * applies the softplus chain rule of kernels.py:80-95).  Forward-sensitivity recursion fused
- * into the filter. */
-int bn_kalman_filter_grad(const bn_kernel_spec* k, int form, int64_t N,
-                          const double* dt, const double* y, const double* noise_cov, const uint8_t* mask,
-                          double* ell, double* grad,
-                          void* workspace, size_t workspace_bytes, void* stream);
-
 /* ---- sites ------------------------------------------------------------------------------ */
 typedef struct {
     int32_t method;        /* BN_METHOD_* */
@@ -177,6 +166,15 @@ typedef struct {
 } bn_site_args;
 
 int bn_site_update(const bn_site_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Likelihood-level statistics evaluated AT the given (post_mean, post_cov), nothing around them --
+ * what inference.py vmaps over N (likelihoods.py:336-355,363-383,401-412,613-675; cubature.py):
+ *   VI     variational_expectation       -> val = E_q[log p],  d1 = dE/dm,   d2 = d2E/dm2
+ *   EP     moment_match (mean/cov = cavity, a->power) -> val = log Z, d1 = dlZ/dm, d2 = d2lZ/dm2
+ *   Newton log_likelihood_gradients at f = post_mean  -> val = log p, d1 = J, d2 = H
+ *   PL     statistical_linear_regression (y unused)   -> val = mu,  d1 = dmu/dm, d2 = omega
+ * val[N], d1[N,D,1], d2[N,D,D]; each nullable.  nat1/nat2/lr/ensure_psd are ignored. */
+int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* d2, void* stream);
 
 /* per-step value of the likelihood term of energy(): VI E_q[log p], Newton log p(y|m),
  * EP/PL log Z at the cavity (computed in-kernel from post + nat).  values[N] nullable;

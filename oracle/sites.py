@@ -280,7 +280,9 @@ def log_likelihood_gradients_ml(lik, y, f):
 def ensure_diagonal_positive_precision(K):
     """utils.py:89-96; K[N,D,D]"""
     D = K.shape[-1]
-    Kd = np.einsum('nii->ni', K)[:, :, None] * np.eye(D)
+    Kd = np.zeros_like(K)  # vmap(np.diag) PLACES the diagonal: off-diagonals are exact zeros even for NaN entries
+    for i in range(D):
+        Kd[:, i, i] = K[:, i, i]
     with np.errstate(invalid='ignore'):
         return np.where(Kd < 0, 1e-2, Kd)
 

@@ -70,3 +70,70 @@ def rts_smoother(lib, sp, form, dt, fm, fP, L=8, world=1, return_full=False):
                               _p(sm), _p(sP), _p(G))
     assert rc == 0
     return sm, sP, G
+
+
+class SiteArgs(C.Structure):
+    _fields_ = [('method', C.c_int32), ('likelihood', C.c_int32), ('lik_param', C.c_double), ('N', C.c_int64),
+                ('D', C.c_int32), ('Q', C.c_int32), ('cub_x', C.c_void_p), ('cub_w', C.c_void_p), ('y', C.c_void_p),
+                ('post_mean', C.c_void_p), ('post_cov', C.c_void_p), ('lr', C.c_double), ('power', C.c_double),
+                ('ensure_psd', C.c_int32), ('pad_', C.c_int32), ('nat1', C.c_void_p), ('nat2', C.c_void_p),
+                ('site_mean', C.c_void_p), ('site_cov', C.c_void_p), ('out_mean', C.c_void_p),
+                ('out_jac', C.c_void_p), ('out_hess', C.c_void_p), ('diffs', C.c_void_p)]
+
+
+METHODS = {'vi': 1, 'ep': 2, 'newton': 3, 'pl': 4}
+LIKS = {'gaussian': 1, 'probit': 2, 'logit': 3, 'het_softplus': 4, 'het_exp': 5}
+
+
+def site_update(lib, method, lik, lik_param, y, post_mean, post_cov, nat1, nat2, lr=1.0, power=1.0, ensure_psd=True,
+                cub=None):
+    """returns dict with new nat1, nat2, site_mean, site_cov, mean, jac, hess, diffs"""
+    N, D = post_mean.shape[0], post_mean.shape[1]
+    keep = []
+
+    def arr(a):
+        a = np.ascontiguousarray(a, dtype=np.float64).copy()
+        keep.append(a)
+        return a
+    a = SiteArgs()
+    a.method, a.likelihood, a.lik_param, a.N, a.D = METHODS[method], LIKS[lik], lik_param, N, D
+    if cub is not None:
+        cx, cw = arr(cub[0]), arr(cub[1])
+        a.Q, a.cub_x, a.cub_w = cw.shape[0], cx.ctypes.data, cw.ctypes.data
+    yv, pm, pc = arr(y), arr(post_mean), arr(post_cov)
+    a.y, a.post_mean, a.post_cov = yv.ctypes.data, pm.ctypes.data, pc.ctypes.data
+    a.lr, a.power, a.ensure_psd = lr, power, int(ensure_psd)
+    out = dict(nat1=arr(nat1), nat2=arr(nat2), site_mean=np.zeros((N, D, 1)), site_cov=np.zeros((N, D, D)),
+               mean=np.zeros((N, D, 1)), jac=np.zeros((N, D, 1)), hess=np.zeros((N, D, D)), diffs=np.zeros(2))
+    a.nat1, a.nat2 = out['nat1'].ctypes.data, out['nat2'].ctypes.data
+    a.site_mean, a.site_cov = out['site_mean'].ctypes.data, out['site_cov'].ctypes.data
+    a.out_mean, a.out_jac, a.out_hess = out['mean'].ctypes.data, out['jac'].ctypes.data, out['hess'].ctypes.data
+    a.diffs = out['diffs'].ctypes.data
+    rc = lib.emu_site_update(C.byref(a))
+    assert rc == 0
+    return out
+
+
+def expected_density(lib, method, lik, lik_param, y, post_mean, post_cov, nat1=None, nat2=None, power=1.0, cub=None):
+    N, D = post_mean.shape[0], post_mean.shape[1]
+    keep = []
+
+    def arr(x):
+        x = np.ascontiguousarray(x, dtype=np.float64).copy()
+        keep.append(x)
+        return x
+    a = SiteArgs()
+    a.method, a.likelihood, a.lik_param, a.N, a.D = METHODS[method], LIKS[lik], lik_param, N, D
+    if cub is not None:
+        cx, cw = arr(cub[0]), arr(cub[1])
+        a.Q, a.cub_x, a.cub_w = cw.shape[0], cx.ctypes.data, cw.ctypes.data
+    yv, pm, pc = arr(y), arr(post_mean), arr(post_cov)
+    a.y, a.post_mean, a.post_cov = yv.ctypes.data, pm.ctypes.data, pc.ctypes.data
+    a.power = power
+    if nat1 is not None:
+        n1, n2 = arr(nat1), arr(nat2)
+        a.nat1, a.nat2 = n1.ctypes.data, n2.ctypes.data
+    vals, s = np.zeros(N), np.zeros(1)
+    rc = lib.emu_expected_density(C.byref(a), _p(vals), _p(s))
+    assert rc == 0
+    return vals, s[0]

@@ -10,6 +10,7 @@
 #include <cstring>
 #include "../../bayesnewton_b200/csrc/filter_impl.cuh"
 #include "../../bayesnewton_b200/csrc/smoother_impl.cuh"
+#include "../../bayesnewton_b200/csrc/sites_impl.cuh"
 
 namespace bn {
 void set_error(const char*, ...) {}
@@ -183,4 +184,65 @@ extern "C" int emu_rts_arrays(int form, long long N, int L, int d, int Df, const
     EMU_ARR(X)
 #undef X
     return -1;
+}
+
+// ---------------------------------------------------------------------------- sites
+extern "C" int emu_site_update(const bn_site_args* a) {
+    double s1 = 0.0, s2 = 0.0;
+#define X(L, M)                                                   \
+    if (a->likelihood == L && a->method == M) {                   \
+        for (long long n = 0; n < a->N; ++n) {                    \
+            double d1 = 0.0, d2 = 0.0;                            \
+            site_update_step<L, M>(*a, n, d1, d2);                \
+            s1 += d1;                                             \
+            s2 += d2;                                             \
+        }                                                         \
+        if (a->diffs) {                                           \
+            a->diffs[0] = s1 / ((double)a->N * a->D);             \
+            a->diffs[1] = s2 / ((double)a->N * a->D * a->D);      \
+        }                                                         \
+        return 0;                                                 \
+    }
+    BN_FOR_EACH_SITE(X)
+#undef X
+    return -1;
+}
+
+extern "C" int emu_expected_density(const bn_site_args* a, double* values, double* sum) {
+    double s = 0.0;
+#define X(L, M)                                                   \
+    if (a->likelihood == L && a->method == M) {                   \
+        for (long long n = 0; n < a->N; ++n) {                    \
+            double v = expected_density_step<L, M>(*a, n);        \
+            if (values) values[n] = v;                            \
+            if (!isnan(v)) s += v;                                \
+        }                                                         \
+        *sum = s;                                                 \
+        return 0;                                                 \
+    }
+    BN_FOR_EACH_SITE(X)
+#undef X
+    return -1;
+}
+
+extern "C" int emu_gaussian_expected_log_lik(long long N, int D, const double* py, const double* pm, const double* pV,
+                                             const double* pR, const unsigned char* mask, double* sum) {
+    double s = 0.0;
+    for (long long n = 0; n < N; ++n)
+        s += (D == 1) ? gaussian_ell_step<1>(py, pm, pV, pR, mask, n) : gaussian_ell_step<2>(py, pm, pV, pR, mask, n);
+    *sum = s;
+    return 0;
+}
+
+extern "C" int emu_ep_pseudo_density(long long N, int D, double power, int with_const, const double* py,
+                                     const double* pR, const double* pm, const double* pV, const double* n1,
+                                     const double* n2, const unsigned char* mask, double* sum) {
+    double s = 0.0;
+    for (long long n = 0; n < N; ++n) {
+        double v = (D == 1) ? ep_pseudo_step<1>(power, with_const, py, pR, pm, pV, n1, n2, mask, n)
+                            : ep_pseudo_step<2>(power, with_const, py, pR, pm, pV, n1, n2, mask, n);
+        if (!isnan(v)) s += v;
+    }
+    *sum = s;
+    return 0;
 }

@@ -1,0 +1,118 @@
+"""Runs the product's __host__ __device__ kernel bodies on the CPU (tests/hostemu) against the oracle:
+arithmetic, chunk indexing, first/last-step rules, carry fold across emulated time shards, and the
+fused site update -- everything except the warp-shuffle scan kernel and the launch plumbing, which
+only the -m gpu tests can exercise.  Tolerance: 1e-9 normwise (north_star), observed ~1e-15."""
+import numpy as np
+import pytest
+
+import _emu
+from _data import filter_problem, rel_err
+from oracle import kalman, sites, ssm
+
+TOL = 1e-9
+
+KERNELS = {
+    'm12': (1, lambda: ssm.Matern12(0.8, 1.7), [0.8], [1.7]),
+    'm32': (2, lambda: ssm.Matern32(1.1, 0.6), [1.1], [0.6]),
+    'm52': (3, lambda: ssm.Matern52(1.3, 0.9), [1.3], [0.9]),
+    'm72': (4, lambda: ssm.Matern72(0.7, 1.4), [0.7], [1.4]),
+    'ind32': (2, lambda: ssm.Independent([ssm.Matern32(1.0, 1.0), ssm.Matern32(0.5, 2.0)]), [1.0, 0.5], [1.0, 2.0]),
+    'ind52': (3, lambda: ssm.Independent([ssm.Matern52(1.3, 0.9), ssm.Matern52(0.7, 2.1)]), [1.3, 0.7], [0.9, 2.1]),
+}
+
+
+@pytest.mark.parametrize('name', sorted(KERNELS))
+@pytest.mark.parametrize('form,L,world', [(0, 8, 1), (1, 8, 1), (1, 5, 3), (1, 64, 2), (1, 4, 8)])
+def test_filter_and_smoother(emu, name, form, L, world):
+    fam, mk, vs, ls = KERNELS[name]
+    k = mk()
+    D = len(vs)
+    N = 203
+    dt, y, R, mask = filter_problem(N, D=D, seed=11)
+    sp = _emu.spec(fam, vs, ls)
+    for rp in (False, True):
+        e0, (m0, P0) = kalman.kalman_filter(dt, k, y, R, mask, return_predict=rp)
+        e1, m1, P1 = _emu.kalman_filter(emu, sp, form, dt, y, R, mask, L=L, world=world, return_predict=rp)
+        assert abs(e1 - e0) < TOL * abs(e0)
+        assert rel_err(m1, m0) < TOL and rel_err(P1, P0) < TOL
+    _, (fm, fP) = kalman.kalman_filter(dt, k, y, R, mask)
+    dts = np.concatenate([dt[1:], [0.0]])
+    for rf in (False, True):
+        s0 = kalman.rauch_tung_striebel_smoother(dts, k, fm, fP, return_full=rf)
+        s1 = _emu.rts_smoother(emu, sp, form, dts, fm, fP, L=L, world=world, return_full=rf)
+        for a, b in zip(s1, s0):
+            assert rel_err(a, b) < TOL
+
+
+def test_ragged_and_tiny_inputs(emu):
+    sp = _emu.spec(3, [1.0], [1.0])
+    k = ssm.Matern52(1.0, 1.0)
+    for N in (1, 2, 3, 9):
+        dt, y, R, mask = filter_problem(N, seed=N)
+        e0, (m0, P0) = kalman.kalman_filter(dt, k, y, R, mask)
+        for form, L in ((0, 4), (1, 4), (1, 1)):
+            e1, m1, P1 = _emu.kalman_filter(emu, sp, form, dt, y, R, mask, L=L)
+            assert abs(e1 - e0) <= TOL * abs(e0) + 1e-15 and rel_err(m1, m0) < TOL and rel_err(P1, P0) < TOL
+            dts = np.concatenate([dt[1:], [0.0]])
+            s0 = kalman.rauch_tung_striebel_smoother(dts, k, m0, P0)
+            s1 = _emu.rts_smoother(emu, sp, form, dts, m0, P0, L=L)
+            assert all(rel_err(a, b) < TOL for a, b in zip(s1, s0))
+
+
+def test_duplicate_time_stamps_stay_finite_in_scan_form(emu):
+    """dt = 0 mid-sequence gives Q = 0; the reference's scan inverts C and returns NaN, the
+    sequential form is fine.  The blocked scan solves with (I + C J) instead and must match the sequential result."""
+    sp = _emu.spec(3, [1.0], [1.0])
+    k = ssm.Matern52(1.0, 1.0)
+    dt, y, R, mask = filter_problem(64, seed=5, missing=0.0)
+    dt[[7, 8, 30]] = 0.0
+    e0, (m0, P0) = kalman.kalman_filter(dt, k, y, R, mask)
+    e1, m1, P1 = _emu.kalman_filter(emu, sp, 1, dt, y, R, mask, L=4)
+    assert np.isfinite(m1).all() and rel_err(m1, m0) < TOL and rel_err(P1, P0) < TOL and abs(e1 - e0) < TOL * abs(e0)
+
+
+SITE_CASES = [('probit', lambda: sites.Bernoulli('probit'), 0.0), ('logit', lambda: sites.Bernoulli('logit'), 0.0),
+              ('gaussian', lambda: sites.Gaussian(0.3), 0.3)]
+
+
+@pytest.mark.parametrize('likname,mk,lp', SITE_CASES)
+@pytest.mark.parametrize('method', ['vi', 'ep', 'newton', 'pl'])
+@pytest.mark.parametrize('lr,power', [(1.0, 1.0), (0.4, 0.5)])
+def test_site_update_single_latent(emu, likname, mk, lp, method, lr, power):
+    rng = np.random.default_rng(1)
+    N = 300
+    lik = mk()
+    y = (rng.uniform(size=N) < 0.5).astype(float) if likname != 'gaussian' else rng.standard_normal(N)
+    y[::17] = np.nan
+    pm = rng.standard_normal((N, 1, 1)); pc = 0.2 + rng.uniform(size=(N, 1, 1))
+    n2 = 0.01 + 0.25 * rng.uniform(size=(N, 1, 1)) / pc; n1 = 0.3 * rng.standard_normal((N, 1, 1))
+    mean, jac, hess = sites.site_statistics(method, lik, y[:, None], pm, pc, n1, n2, power=power,
+                                            mask_pseudo_y=np.isnan(y)[:, None])
+    o = sites.damped_site_update(n1, n2, mean, jac, hess, lr)
+    e = _emu.site_update(emu, method, likname, lp, y, pm, pc, n1, n2, lr=lr, power=power,
+                         cub=sites.gauss_hermite(1, 20))
+    for got, ref in [(e['mean'], mean), (e['jac'], jac), (e['hess'], hess), (e['nat1'], o[0]), (e['nat2'], o[1]),
+                     (e['site_mean'], o[2]), (e['site_cov'], o[3])]:
+        assert rel_err(got, ref) < TOL
+    assert abs(e['diffs'][0] - o[4]) < TOL * o[4] and abs(e['diffs'][1] - o[5]) < TOL * o[5]
+
+
+@pytest.mark.parametrize('method', ['vi', 'ep', 'newton'])
+@pytest.mark.parametrize('lr,power,psd', [(1.0, 1.0, True), (0.3, 0.5, True), (0.3, 0.5, False)])
+def test_site_update_heteroscedastic(emu, method, lr, power, psd):
+    rng = np.random.default_rng(2)
+    N = 200
+    lik = sites.HeteroscedasticNoise('softplus')
+    y = rng.standard_normal(N)
+    pm = rng.standard_normal((N, 2, 1)) * 0.5
+    A = rng.standard_normal((N, 2, 2)) * 0.3
+    pc = A @ np.swapaxes(A, 1, 2) + 0.2 * np.eye(2)
+    n2 = np.zeros((N, 2, 2)); n2[:, 0, 0] = 0.01 + 0.3 * rng.uniform(size=N); n2[:, 1, 1] = 0.01 + 0.3 * rng.uniform(size=N)
+    n1 = 0.3 * rng.standard_normal((N, 2, 1))
+    mean, jac, hess = sites.site_statistics(method, lik, y[:, None], pm, pc, n1, n2, power=power, ensure_psd=psd)
+    o = sites.damped_site_update(n1, n2, mean, jac, hess, lr)
+    e = _emu.site_update(emu, method, 'het_softplus', 0, y, pm, pc, n1, n2, lr=lr, power=power,
+                         cub=sites.gauss_hermite(2, 20), ensure_psd=psd)
+    for got, ref in [(e['mean'], mean), (e['jac'], jac), (e['hess'], hess), (e['nat1'], o[0]), (e['nat2'], o[1]),
+                     (e['site_mean'], o[2]), (e['site_cov'], o[3])]:
+        assert rel_err(got, ref) < 1e-8  # the EP scale factor inverts ill-conditioned 2x2s: 1e-13 typical
