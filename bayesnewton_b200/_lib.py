@@ -46,6 +46,8 @@ _KS, _SA = C.POINTER(KernelSpec), C.POINTER(SiteArgs)
 SIGNATURES = {
     'bn_last_error': (C.c_char_p, []),
     'bn_version': (_I, []),
+    'bn_timing_enable': (_I, [_I]),
+    'bn_timing_report': (_I, [C.c_char_p, _Z]),
     'bn_state_dim': (_I, [_KS]),
     'bn_discretise': (_I, [_KS, _L, _P, _P, _P, _P]),
     'bn_workspace_bytes': (_Z, [_L, _I, _I]),

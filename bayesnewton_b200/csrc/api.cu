@@ -1,6 +1,10 @@
 // Library-level pieces of the C ABI: error slot, sizing queries and the stand-alone
 // discretisation kernel (As, Qs materialised for callers that want the reference's arrays:
 // vmap(kernel.state_transition)(dt), vmap(process_noise_covariance), ops.py:274-278).
+#include <cstring>
+#include <vector>
+#include <string>
+#include <map>
 #include "common.cuh"
 #include "core.cuh"
 #include "scan.cuh"
@@ -14,6 +18,24 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- per-kernel timing ---------------------------------------------------------------------------
+struct KRec { const char* name; cudaEvent_t e0, e1; };
+static bool g_timing = false;
+static std::vector<KRec> g_recs;
+
+void ktimer_begin(const char* name, cudaStream_t st) {
+    if (!g_timing) return;
+    KRec r{name, nullptr, nullptr};
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    g_recs.push_back(r);
+}
+void ktimer_end(cudaStream_t st) {
+    if (!g_timing) return;
+    cudaEventRecord(g_recs.back().e1, st);
 }
 
 template <class Gen>
@@ -40,6 +62,40 @@ using namespace bn;
 
 extern "C" const char* bn_last_error(void) { return g_err; }
 extern "C" int bn_version(void) { return 100; }
+
+extern "C" int bn_timing_enable(int on) {
+    for (auto& r : g_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_recs.clear();
+    g_timing = on != 0;
+    return 0;
+}
+
+// "name count total_ms" per line, aggregated over the launches recorded since bn_timing_enable(1).
+// Synchronises the recorded events.  Returns the number of bytes the full report needs.
+extern "C" int bn_timing_report(char* buf, size_t len) {
+    std::map<std::string, std::pair<long, double>> agg;
+    std::vector<std::string> order;
+    for (auto& r : g_recs) {
+        cudaEventSynchronize(r.e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (!agg.count(r.name)) order.push_back(r.name);
+        agg[r.name].first += 1;
+        agg[r.name].second += ms;
+    }
+    std::string out;
+    for (auto& n : order) {
+        char line[160];
+        snprintf(line, sizeof(line), "%s %ld %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        out += line;
+    }
+    if (buf && len > 0) {
+        size_t k = out.size() < len - 1 ? out.size() : len - 1;
+        memcpy(buf, out.data(), k);
+        buf[k] = 0;
+    }
+    return (int)out.size() + 1;
+}
 
 extern "C" int bn_state_dim(const bn_kernel_spec* k) {
     if (!k || k->n_components < 1 || k->n_components > BN_MAX_COMPONENTS) return -1;

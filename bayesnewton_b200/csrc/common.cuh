@@ -28,6 +28,17 @@ void set_error(const char* fmt, ...);
         }                                                                        \
     } while (0)
 
+// Optional per-kernel device timing (bn_timing_enable / bn_timing_report): when enabled, every
+// launch made through BN_LAUNCH is bracketed by CUDA events on its own stream.
+void ktimer_begin(const char* name, cudaStream_t st);
+void ktimer_end(cudaStream_t st);
+#define BN_LAUNCH(name, st, ...)          \
+    do {                                  \
+        ::bn::ktimer_begin(name, st);     \
+        __VA_ARGS__;                      \
+        ::bn::ktimer_end(st);             \
+    } while (0)
+
 constexpr int kChunkThreads = 128;
 constexpr long long kTargetChunks = 148LL * 512;  // one resident wave of 512 threads per SM
 
@@ -68,7 +79,7 @@ constexpr int kNotHandled = -1000;
 #define BN_FOR_EACH_MATERN(X) BN_GROUP_M_A(X) BN_GROUP_M_B(X) BN_GROUP_M_C(X) BN_GROUP_M_D(X)
 // Array entry (state dim, observation dim):
 #define BN_GROUP_A_A(X) X(1, 1) X(2, 1) X(3, 1) X(4, 1)
-#define BN_GROUP_A_B(X) X(2, 2) X(4, 2) X(3, 3)
+#define BN_GROUP_A_B(X) X(2, 2) X(3, 2) X(4, 2) X(3, 3)
 #define BN_GROUP_A_C(X) X(6, 2)
 
 // sum of n doubles in a fixed order (strided partials, then a shared-memory tree): run-to-run

@@ -217,8 +217,8 @@ inline int kf_run(const Gen& gen, int form, KfIO io, double* ell, void* ws, size
         return 0;
     }
     if (form == BN_SEQUENTIAL) {
-        if (ell) kf_seq_kernel<Gen, true><<<1, 1, 0, st>>>(gen, io, ell);
-        else kf_seq_kernel<Gen, false><<<1, 1, 0, st>>>(gen, io, nullptr);
+        if (ell) BN_LAUNCH("kf_seq", st, kf_seq_kernel<Gen, true><<<1, 1, 0, st>>>(gen, io, ell));
+        else BN_LAUNCH("kf_seq", st, kf_seq_kernel<Gen, false><<<1, 1, 0, st>>>(gen, io, nullptr));
         BN_CUDA(cudaGetLastError());
         return 0;
     }
@@ -228,7 +228,9 @@ inline int kf_run(const Gen& gen, int form, KfIO io, double* ell, void* ws, size
     KfWs w = kf_ws<d>(ws, cp.nchunks);
     unsigned grid = (unsigned)((cp.nchunks + kChunkThreads - 1) / kChunkThreads);
     if (phase == PHASE_ALL || phase == PHASE_REDUCE) {
-        kf_reduce_kernel<Gen><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_first, w.plan.input0);
+        BN_LAUNCH("kf_reduce", st,
+                  kf_reduce_kernel<Gen><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_first,
+                                                                         w.plan.input0));
         BN_CUDA(cudaGetLastError());
         BN_CUDA(run_scan<Alg>(w.plan, st));
         if (carry_out) {
@@ -245,13 +247,15 @@ inline int kf_run(const Gen& gen, int form, KfIO io, double* ell, void* ws, size
             BN_CUDA(cudaMemsetAsync(w.s0, 0, Alg::kState * sizeof(double), st));
         }
         if (ell) {
-            kf_apply_kernel<Gen, true><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_first,
-                                                                        w.plan.prefix[0], w.s0, w.partials);
+            BN_LAUNCH("kf_apply", st,
+                      kf_apply_kernel<Gen, true><<<grid, kChunkThreads, 0, st>>>(
+                          gen, io, cp.L, cp.nchunks, is_first, w.plan.prefix[0], w.s0, w.partials));
             BN_CUDA(cudaGetLastError());
-            sum_kernel<false><<<1, 1024, 0, st>>>(w.partials, cp.nchunks, ell, 1.0);
+            BN_LAUNCH("sum", st, sum_kernel<false><<<1, 1024, 0, st>>>(w.partials, cp.nchunks, ell, 1.0));
         } else {
-            kf_apply_kernel<Gen, false><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_first,
-                                                                         w.plan.prefix[0], w.s0, nullptr);
+            BN_LAUNCH("kf_apply", st,
+                      kf_apply_kernel<Gen, false><<<grid, kChunkThreads, 0, st>>>(
+                          gen, io, cp.L, cp.nchunks, is_first, w.plan.prefix[0], w.s0, nullptr));
         }
         BN_CUDA(cudaGetLastError());
     }

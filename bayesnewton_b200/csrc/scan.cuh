@@ -8,6 +8,7 @@
 // fix-up combine.  The within-group inclusive prefixes stay in HBM (SoA, coalesced); the group
 // totals feed the next level.  Going back down costs ONE combine per element.
 #pragma once
+#include "common.cuh"
 #include "core.cuh"
 
 namespace bn {
@@ -134,13 +135,16 @@ inline cudaError_t run_scan(const ScanPlan& p, cudaStream_t st) {
         unsigned grid = (unsigned)((n + kScanGroup - 1) / kScanGroup);
         const double* in = (l == 0) ? p.input0 : p.prefix[l];
         bool top = (l == p.levels - 1);
-        scan_level_kernel<Alg><<<grid, kScanGroup, 0, st>>>(
-            in, n, n, p.prefix[l], n, top ? nullptr : p.prefix[l + 1], top ? 0 : p.count[l + 1]);
+        BN_LAUNCH("scan_level", st,
+                  scan_level_kernel<Alg><<<grid, kScanGroup, 0, st>>>(
+                      in, n, n, p.prefix[l], n, top ? nullptr : p.prefix[l + 1], top ? 0 : p.count[l + 1]));
     }
     for (int l = p.levels - 2; l >= 0; --l) {
         long long n = p.count[l];
         unsigned grid = (unsigned)((n + kScanGroup - 1) / kScanGroup);
-        scan_down_kernel<Alg><<<grid, kScanGroup, 0, st>>>(p.prefix[l], n, n, p.prefix[l + 1], p.count[l + 1]);
+        BN_LAUNCH("scan_down", st,
+                  scan_down_kernel<Alg><<<grid, kScanGroup, 0, st>>>(p.prefix[l], n, n, p.prefix[l + 1],
+                                                                      p.count[l + 1]));
     }
     return cudaGetLastError();
 }

@@ -96,7 +96,7 @@ extern "C" int bn_site_update(const bn_site_args* a, void* workspace, size_t wor
     }
 #define X(L, M)                                                                \
     if (a->likelihood == L && a->method == M) {                                \
-        site_update_kernel<L, M><<<grid, kSiteThreads, 0, st>>>(*a, p1, p2);   \
+        BN_LAUNCH("site_update", st, (site_update_kernel<L, M><<<grid, kSiteThreads, 0, st>>>(*a, p1, p2))); \
         BN_CUDA(cudaGetLastError());                                           \
         if (a->diffs) {                                                        \
             sum_kernel<false><<<1, 1024, 0, st>>>(p1, grid, a->diffs, 1.0 / ((double)a->N * a->D));            \
@@ -124,7 +124,8 @@ extern "C" int bn_expected_density(const bn_site_args* a, double* values, double
     double* part = (double*)workspace;
 #define X(L, M)                                                                        \
     if (a->likelihood == L && a->method == M) {                                        \
-        expected_density_kernel<L, M><<<grid, kSiteThreads, 0, st>>>(*a, values, part); \
+        BN_LAUNCH("expected_density", st,                                              \
+                  (expected_density_kernel<L, M><<<grid, kSiteThreads, 0, st>>>(*a, values, part))); \
         BN_CUDA(cudaGetLastError());                                                   \
         sum_kernel<false><<<1, 1024, 0, st>>>(part, grid, sum, 1.0);                   \
         BN_CUDA(cudaGetLastError());                                                   \
@@ -165,7 +166,7 @@ extern "C" int bn_gaussian_expected_log_lik(int64_t N, int D, const double* pseu
     unsigned grid = (unsigned)((N + kSiteThreads - 1) / kSiteThreads);
     BN_REQUIRE(workspace && workspace_bytes >= (size_t)grid * sizeof(double), "workspace too small for %u partials", grid);
     double* part = (double*)workspace;
-    if (D == 1) gaussian_ell_kernel<1><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part);
+    if (D == 1) BN_LAUNCH("gaussian_ell", st, gaussian_ell_kernel<1><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part));
     else if (D == 2) gaussian_ell_kernel<2><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part);
     else if (D == 3) gaussian_ell_kernel<3><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part);
     else { set_error("unsupported site dimension %d", D); return -1; }

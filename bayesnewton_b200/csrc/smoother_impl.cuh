@@ -184,7 +184,7 @@ inline int rts_run(const Gen& gen, int form, RtsIO io, void* ws, size_t ws_bytes
     using Alg = SmootherAlg<d>;
     if (io.N == 0) return 0;
     if (form == BN_SEQUENTIAL) {
-        rts_seq_kernel<Gen><<<1, 1, 0, st>>>(gen, io);
+        BN_LAUNCH("rts_seq", st, rts_seq_kernel<Gen><<<1, 1, 0, st>>>(gen, io));
         BN_CUDA(cudaGetLastError());
         return 0;
     }
@@ -195,7 +195,9 @@ inline int rts_run(const Gen& gen, int form, RtsIO io, void* ws, size_t ws_bytes
     ScanPlan plan = make_scan_plan(s0 + 64, cp.nchunks, Alg::kElem);
     unsigned grid = (unsigned)((cp.nchunks + kChunkThreads - 1) / kChunkThreads);
     if (phase == PHASE_ALL || phase == PHASE_REDUCE) {
-        rts_reduce_kernel<Gen><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_last, plan.input0);
+        BN_LAUNCH("rts_reduce", st,
+                  rts_reduce_kernel<Gen><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_last,
+                                                                          plan.input0));
         BN_CUDA(cudaGetLastError());
         BN_CUDA(run_scan<Alg>(plan, st));
         if (carry_out) {
@@ -211,7 +213,9 @@ inline int rts_run(const Gen& gen, int form, RtsIO io, void* ws, size_t ws_bytes
         } else {
             BN_CUDA(cudaMemsetAsync(s0, 0, Alg::kState * sizeof(double), st));
         }
-        rts_apply_kernel<Gen><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_last, plan.prefix[0], s0);
+        BN_LAUNCH("rts_apply", st,
+                  rts_apply_kernel<Gen><<<grid, kChunkThreads, 0, st>>>(gen, io, cp.L, cp.nchunks, is_last,
+                                                                         plan.prefix[0], s0));
         BN_CUDA(cudaGetLastError());
     }
     return 0;

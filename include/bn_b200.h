@@ -71,6 +71,13 @@ enum { BN_METHOD_VI = 1, BN_METHOD_EP = 2, BN_METHOD_NEWTON = 3, BN_METHOD_PL = 
 const char* bn_last_error(void);
 int bn_version(void);
 
+/* ---- optional per-kernel device timing (measurement aid, used by bench.py) --------------------- */
+/* bn_timing_enable(1) clears the log and brackets every kernel launch of this library with CUDA
+ * events on its stream; bn_timing_enable(0) stops.  bn_timing_report writes "name count total_ms"
+ * lines (one per kernel name) into buf and returns the size the full report needs. */
+int bn_timing_enable(int on);
+int bn_timing_report(char* buf_host, size_t len);
+
 /* ---- discretisation: As[N,d,d], Qs[N,d,d] from dt[N] -------------------------------------- */
 int bn_state_dim(const bn_kernel_spec* k);
 int bn_discretise(const bn_kernel_spec* k, int64_t N, const double* dt, double* As, double* Qs, void* stream);
