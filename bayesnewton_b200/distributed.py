@@ -132,3 +132,74 @@ def filter_smoother_in_shards(kernel, dt, y, R, mask, n_shards):
     return dict(ell=sum(f[0] for f in filt), filter_mean=torch.cat([f[1] for f in filt]),
                 filter_cov=torch.cat([f[2] for f in filt]), post_mean=torch.cat([s[0] for s in smo]),
                 post_cov=torch.cat([s[1] for s in smo]))
+
+
+class TimeShardedMarkovGP:
+    """One rank's view of a time-sharded temporal Markov GP: the host mirror of
+    MarkovGaussianProcess + an inference mixin (basemodels.py:625-764, inference.py:65-90) where the
+    time axis is partitioned over the ranks of the default process group.
+
+    Every rank constructs it with ITS contiguous slice of (dt, Y) -- `dt_next` is the first dt of the
+    right neighbour (0 on the last rank), needed by the smoother's shifted step array
+    (basemodels.py:700).  Per iteration: 5 carry all-gathers + 1 all-reduce of 3 scalars.
+    """
+
+    def __init__(self, kernel, likelihood, dt_local, Y_local, dt_next, method, rank, world, power=1.0):
+        from .basemodels import GaussianDistribution
+        self.kernel, self.likelihood, self.method, self.power = kernel, likelihood, method, power
+        self.rank, self.world = rank, world
+        dt = as_dev(dt_local).reshape(-1)
+        dts = torch.cat([dt[1:], torch.full((1,), float(dt_next), dtype=dt.dtype, device=dt.device)])
+        self.shard = TimeShard(kernel, dt, dts, rank, world)
+        self.Y = as_dev(Y_local).reshape(-1)
+        self.N, D = self.shard.N, self.shard.D
+        self.state_dim = self.shard.d
+        dev = dt.device
+        self.pseudo_likelihood = GaussianDistribution(
+            mean=torch.zeros((self.N, D, 1), dtype=torch.float64, device=dev),
+            covariance=1e2 * torch.eye(D, dtype=torch.float64, device=dev).repeat(self.N, 1, 1))
+        self.posterior_mean = torch.zeros((self.N, D, 1), dtype=torch.float64, device=dev)
+        self.posterior_variance = torch.eye(D, dtype=torch.float64, device=dev).repeat(self.N, 1, 1)
+        nan = torch.isnan(self.Y)
+        self.mask_pseudo_y = nan.to(torch.uint8).contiguous() if (D == 1 and bool(nan.any())) else None
+        self._ws = _ws(self.N, self.state_dim, D, dev)
+
+    def update_posterior(self):
+        pl = self.pseudo_likelihood
+        _, sm, sP = sharded_update_posterior(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y)
+        self.posterior_mean, self.posterior_variance = sm, sP
+
+    def _site_args(self, cubature=None):
+        a, keep = self.likelihood.site_args(self.method, self.Y, self.posterior_mean, self.posterior_variance,
+                                            cubature, self.power)
+        a.nat1, a.nat2 = self.pseudo_likelihood.nat1_.data_ptr(), self.pseudo_likelihood.nat2_.data_ptr()
+        return a, keep
+
+    def inference(self, lr=1.0, cubature=None, ensure_psd=True):
+        self.update_posterior()
+        a, keep = self._site_args(cubature)
+        a.lr, a.ensure_psd = float(lr), int(bool(ensure_psd))
+        pl = self.pseudo_likelihood
+        a.site_mean, a.site_cov = pl.mean_.data_ptr(), pl.covariance_.data_ptr()
+        ws, nb = self._ws
+        _lib.check(_lib.lib().bn_site_update(a, ptr(ws), nb, stream_ptr()))
+        self.update_posterior()
+
+    def energy(self, cubature=None):
+        """VI / Newton energy (inference.py:130-154,197-222): three local sums, one all-reduce"""
+        if self.method not in (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON):
+            raise NotImplementedError('time-sharded energy is implemented for VI and Newton')
+        pl = self.pseudo_likelihood
+        dev = self.Y.device
+        parts = torch.zeros(3, dtype=torch.float64, device=dev)
+        a, keep = self._site_args(cubature)
+        ws, nb = self._ws
+        _lib.check(_lib.lib().bn_expected_density(a, None, parts[0:1].data_ptr(), ptr(ws), nb, stream_ptr()))
+        _lib.check(_lib.lib().bn_gaussian_expected_log_lik(
+            self.N, a.D, ptr(pl.mean), ptr(self.posterior_mean), ptr(self.posterior_variance), ptr(pl.covariance),
+            ptr(self.mask_pseudo_y), None, parts[1:2].data_ptr(), ptr(ws), nb, stream_ptr()))
+        parts[2:3] = sharded_log_lik(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(parts)
+        return -(parts[0] - (parts[1] - parts[2]))

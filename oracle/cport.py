@@ -15,9 +15,14 @@ class CKernel(C.Structure):
 
 
 def build():
+    """compiles oracle/c/markov_c.c when its content changed (hash stamp: a copied tree does not rebuild)"""
+    import hashlib
     src = os.path.join(HERE, 'c', 'markov_c.c')
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.run(['make', '-C', HERE], check=True, capture_output=True)
+    dig = hashlib.sha256(open(src, 'rb').read()).hexdigest()
+    stamp = LIB + '.sha256'
+    if not (os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig):
+        subprocess.run(['make', '-B', '-C', HERE], check=True, capture_output=True)
+        open(stamp, 'w').write(dig)
     return LIB
 
 
