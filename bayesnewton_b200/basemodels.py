@@ -25,9 +25,12 @@ def input_admin(t, y):
 class GaussianDistribution:
     """sites in (mean, covariance) and natural (nat1, nat2 = cov^-1) form (basemodels.py:52-100)"""
 
-    def __init__(self, mean, covariance):
+    def __init__(self, mean, covariance, nat1=None, nat2=None):
         self.mean_, self.covariance_ = as_dev(mean), as_dev(covariance)
-        self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
+        if nat1 is None:
+            self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
+        else:  # the caller knows both forms (e.g. the diagonal initial sites): no factorisation needed
+            self.nat1_, self.nat2_ = as_dev(nat1), as_dev(nat2)
 
     def __call__(self):
         return self.mean, self.covariance
@@ -75,9 +78,10 @@ class MarkovGaussianProcess:
         if D != self.func_dim or self.obs_dim != 1:
             raise NotImplementedError('one observation per step and one site per latent are supported')
         N = self.num_data
-        self.pseudo_likelihood = GaussianDistribution(
-            mean=torch.zeros((N, D, 1), dtype=torch.float64, device=device()),
-            covariance=1e2 * torch.eye(D, dtype=torch.float64, device=device()).repeat(N, 1, 1))
+        eye = torch.eye(D, dtype=torch.float64, device=device()).repeat(N, 1, 1)
+        self.pseudo_likelihood = GaussianDistribution(  # mean 0, cov 100 I (basemodels.py:130-133)
+            mean=torch.zeros((N, D, 1), dtype=torch.float64, device=device()), covariance=1e2 * eye,
+            nat1=torch.zeros((N, D, 1), dtype=torch.float64, device=device()), nat2=1e-2 * eye)
         self.posterior_mean = torch.zeros((N, D, 1), dtype=torch.float64, device=device())
         self.posterior_variance = torch.eye(D, dtype=torch.float64, device=device()).repeat(N, 1, 1)
         mask_y = np.isnan(Yh)

@@ -155,9 +155,10 @@ class TimeShardedMarkovGP:
         self.N, D = self.shard.N, self.shard.D
         self.state_dim = self.shard.d
         dev = dt.device
+        eye = torch.eye(D, dtype=torch.float64, device=dev).repeat(self.N, 1, 1)
         self.pseudo_likelihood = GaussianDistribution(
-            mean=torch.zeros((self.N, D, 1), dtype=torch.float64, device=dev),
-            covariance=1e2 * torch.eye(D, dtype=torch.float64, device=dev).repeat(self.N, 1, 1))
+            mean=torch.zeros((self.N, D, 1), dtype=torch.float64, device=dev), covariance=1e2 * eye,
+            nat1=torch.zeros((self.N, D, 1), dtype=torch.float64, device=dev), nat2=1e-2 * eye)
         self.posterior_mean = torch.zeros((self.N, D, 1), dtype=torch.float64, device=dev)
         self.posterior_variance = torch.eye(D, dtype=torch.float64, device=dev).repeat(self.N, 1, 1)
         nan = torch.isnan(self.Y)
