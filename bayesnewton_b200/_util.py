@@ -48,3 +48,19 @@ def workspace(N, d, D):
         ws = torch.empty(int(need), dtype=torch.uint8, device=device())
         _workspaces[key] = ws
     return ws, ws.numel()
+
+
+_up_workspaces = {}
+
+
+def up_workspace(spec, N):
+    """cached per-device scratch of the fused posterior update (holds the filtered states: ~72 B/step at d = 3)"""
+    need = _lib.lib().bn_update_posterior_workspace_bytes(spec, int(N))
+    key = torch.cuda.current_device()
+    ws = _up_workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = None
+        _up_workspaces.pop(key, None)
+        ws = torch.empty(int(need), dtype=torch.uint8, device=device())
+        _up_workspaces[key] = ws
+    return ws, ws.numel()

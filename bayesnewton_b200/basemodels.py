@@ -26,6 +26,7 @@ class GaussianDistribution:
     """sites in (mean, covariance) and natural (nat1, nat2 = cov^-1) form (basemodels.py:52-100)"""
 
     def __init__(self, mean, covariance, nat1=None, nat2=None):
+        self.version = 0  # bumped whenever the parameters change (invalidates anything derived from them)
         self.mean_, self.covariance_ = as_dev(mean), as_dev(covariance)
         if nat1 is None:
             self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
@@ -49,6 +50,7 @@ class GaussianDistribution:
         return torch.cholesky_solve(param1, chol), torch.cholesky_solve(eye, chol)
 
     def update_mean_cov(self, mean, covariance):
+        self.version += 1
         self.mean_, self.covariance_ = as_dev(mean), as_dev(covariance)
         self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
 
@@ -103,17 +105,35 @@ class MarkovGaussianProcess:
     def compute_full_pseudo_lik(self):
         return self.pseudo_likelihood.mean, self.pseudo_likelihood.covariance
 
+    def _hyper_key(self):
+        spec = self.kernel.spec() if hasattr(self.kernel, 'spec') else None
+        if spec is None:
+            return None
+        return (spec.family, spec.n_components, tuple(spec.variance), tuple(spec.lengthscale))
+
     def update_posterior(self):
-        """filter then smoother (basemodels.py:689-706); the unused log-likelihood and gains are not computed"""
+        """filter then smoother (basemodels.py:689-706).  With the scan form and an in-library kernel this is
+        ONE fused call (ops.update_posterior); the filter log-likelihood it produces on the way is kept and
+        served to compute_log_lik() for as long as the sites and hyper-parameters it was computed from stand
+        (the reference evaluates the identical filter a second time inside energy(), basemodels.py:733)."""
         pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
-        _, (fm, fP) = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
-                                  parallel=self.parallel, want_ell=False)
-        sm, sP, _ = self.smoother(self.dt_smoother, self.kernel, fm, fP, parallel=self.parallel, want_gains=False)
+        if self.parallel and self._hyper_key() is not None:
+            ell, sm, sP = ops.update_posterior(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
+                                               want_ell=True)
+            self._ell_cache = (ell, self.pseudo_likelihood.version, self._hyper_key())
+        else:
+            _, (fm, fP) = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
+                                      parallel=self.parallel, want_ell=False)
+            sm, sP, _ = self.smoother(self.dt_smoother, self.kernel, fm, fP, parallel=self.parallel,
+                                      want_gains=False)
         self.posterior_mean, self.posterior_variance = sm, sP
 
     def compute_log_lik(self, pseudo_y=None, pseudo_var=None):
         """log normaliser of the pseudo model = the filter's log-likelihood (basemodels.py:726-741)"""
         if pseudo_y is None:
+            cache = getattr(self, '_ell_cache', None)
+            if cache is not None and cache[1] == self.pseudo_likelihood.version and cache[2] == self._hyper_key():
+                return cache[0]
             pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
         ell, _ = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
                              parallel=self.parallel, want_states=False)

@@ -42,16 +42,25 @@ struct MaternBlock {
     }
 
     // A = exp(-lam dt) (dt M + I)
+    static BN_DEV T rate(T ell) {
+        if constexpr (FAMILY == BN_MATERN12) return T(1) / ell;
+        else if constexpr (FAMILY == BN_MATERN32) return sqrt(T(3)) / ell;
+        else if constexpr (FAMILY == BN_MATERN52) return sqrt(T(5)) / ell;
+        else return sqrt(T(7)) / ell;
+    }
     static BN_DEV void transition(T ell, T dt, T* A) {
+        if constexpr (FAMILY == BN_MATERN12) A[0] = exp(-dt / ell);
+        else transition_rate(rate(ell), dt, A);
+    }
+    // the same closed forms given lam = sqrt(2 nu) / ell (hoisted out of per-step loops)
+    static BN_DEV void transition_rate(T lam, T dt, T* A) {
         if constexpr (FAMILY == BN_MATERN12) {
-            A[0] = exp(-dt / ell);
+            A[0] = exp(-dt * lam);
         } else if constexpr (FAMILY == BN_MATERN32) {
-            T lam = sqrt(T(3)) / ell;
             T e = exp(-dt * lam);
             A[0] = e * (dt * lam + T(1));           A[1] = e * dt;
             A[2] = e * (dt * (-lam * lam));         A[3] = e * (dt * (-lam) + T(1));
         } else if constexpr (FAMILY == BN_MATERN52) {
-            T lam = sqrt(T(5)) / ell;
             T dl = dt * lam;
             T e = exp(-dl);
             T l2 = lam * lam;
@@ -65,7 +74,6 @@ struct MaternBlock {
             A[7] = e * (dt * (l2 * (dl - T(3))));
             A[8] = e * (dt * (lam * (T(0.5) * dl - T(2))) + T(1));
         } else {
-            T lam = sqrt(T(7)) / ell;
             T l2 = lam * lam, l3 = l2 * lam;
             T dl = dt * lam;
             T dl2 = dl * dl;

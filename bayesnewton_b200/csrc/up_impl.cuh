@@ -1,0 +1,553 @@
+// Fused posterior update  (MarkovGaussianProcess.update_posterior, basemodels.py:689-706:
+// kalman_filter -> rauch_tung_striebel_smoother, ops.py:256-285, 357-380, `parallel=True` form)
+// for stationary Matern stacks.  Five launches:
+//   up_reduce    one thread per chunk of L steps folds its steps into a filtering element      (phase 1)
+//   run_scan     prefix "product" of the chunk elements (scan.cuh)                            (phase 2)
+//   up_filter    one thread per chunk re-runs the plain filter from its incoming state, keeps the
+//                filtered states in a warp-tiled scratch layout and sums the log-likelihood    (phase 3)
+//   up_selem     one thread per chunk turns its filtering element + the filtered states at the
+//                chunk ends into the chunk's smoothing element (fast_core.cuh); run_scan again
+//   up_smooth    one thread per chunk runs the RTS recursion down its chunk and writes H sm, H sP H^T
+// The second per-step reduction pass a stand-alone parallel smoother needs (ops.py:318-325 over
+// all N) does not exist here: the smoothing elements come from the filter's own chunk elements.
+//
+// HBM traffic per step (d = 3, D = 1, fp64): up_reduce 24 B, up_filter 24 + 72 B, up_smooth 72 + 8 + 16 B.
+// Inputs and outputs move through per-warp shared-memory tiles (coalesced row segments of kUpTJ
+// steps per chunk); the filtered-state scratch is laid out [warp tile][step][field][lane] so every
+// access is a fully coalesced 256-byte warp transaction with no staging.
+#pragma once
+#include "common.cuh"
+#include "fast_core.cuh"
+#include "scan.cuh"
+
+namespace bn {
+
+constexpr int kUpTJ = 8;       // steps per staged sub-block
+constexpr int kUpWarps = 4;    // warps per CTA
+constexpr int kUpThreads = 32 * kUpWarps;
+
+struct UpIO {
+    long long N;
+    const double* dt;           // [N]
+    const double* y;            // [N,D]     pseudo observations (site means)
+    const double* R;            // [N,D,D]   site covariances
+    const unsigned char* mask;  // [N,D] or null
+    double* post_mean;          // [N,D]     H sm
+    double* post_cov;           // [N,D,D]   H sP H^T
+};
+
+inline ChunkPlan up_plan_chunks(long long N) {
+    long long L = (N + kTargetChunks - 1) / kTargetChunks;
+    L = (L + kUpTJ - 1) / kUpTJ * kUpTJ;
+    if (L < kUpTJ) L = kUpTJ;
+    if (L > 128) L = 128;
+    ChunkPlan p;
+    p.L = (int)L;
+    p.nchunks = (N + L - 1) / L;
+    return p;
+}
+
+// filtered-state scratch: field f of step j of chunk c
+BN_DEV long long fs_index(long long c, int L, int j, int f, int nfields) {
+    return ((((c >> 5) * L + j) * nfields + f) << 5) + (c & 31);
+}
+inline long long fs_doubles(long long nchunks, int L, int nfields) {
+    return ((nchunks + 31) / 32) * 32 * (long long)L * nfields;
+}
+
+template <int d>
+BN_DEV void fs_store(double* fs, long long c, int L, int j, const double* m, const double* P) {
+    constexpr int nf = d + symn(d);
+#pragma unroll
+    for (int f = 0; f < d; ++f) fs[fs_index(c, L, j, f, nf)] = m[f];
+#pragma unroll
+    for (int f = 0; f < symn(d); ++f) fs[fs_index(c, L, j, d + f, nf)] = P[f];
+}
+template <int d>
+BN_DEV void fs_load(const double* fs, long long c, int L, int j, double* m, double* P) {
+    constexpr int nf = d + symn(d);
+#pragma unroll
+    for (int f = 0; f < d; ++f) m[f] = fs[fs_index(c, L, j, f, nf)];
+#pragma unroll
+    for (int f = 0; f < symn(d); ++f) P[f] = fs[fs_index(c, L, j, d + f, nf)];
+}
+
+// ------------------------------------------------------------------------------------------ IO contexts
+// A context feeds one lane (= one chunk) its per-step inputs and takes its per-step outputs.
+// DirectCtx touches global memory per step (host emulation harness; also valid on the device).
+template <int D>
+struct DirectCtx {
+    UpIO io;
+    BN_DEV double dt(long long k, int) const { return io.dt[k]; }
+    BN_DEV void obs(long long k, int, double* y, double* R) const {
+#pragma unroll
+        for (int i = 0; i < D; ++i) y[i] = io.y[k * D + i];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) R[i] = io.R[k * (D * D) + i];
+    }
+    BN_DEV void put(long long k, int, const double* pm, const double* pc) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) io.post_mean[k * D + i] = pm[i];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) io.post_cov[k * (D * D) + i] = pc[i];
+    }
+};
+
+#ifdef __CUDACC__
+// WarpCtx: the 32 chunks of a warp stage kUpTJ steps at a time through shared memory.  Global
+// accesses are row segments of kUpTJ * W consecutive doubles per chunk, read and written by
+// consecutive lanes; each lane then walks its own row (odd row pitch: no bank conflicts).
+template <int W>
+struct Tile {
+    static constexpr int RW = kUpTJ * W;
+    static constexpr int P = RW | 1;
+    static constexpr int kDoubles = 32 * P;
+    double* sm;
+    __device__ void load(const double* X, long long N, long long cbase, int L, int j0, int lane) {
+        for (int i = lane; i < 32 * RW; i += 32) {
+            const int r = i / RW, col = i - r * RW;
+            const long long e0 = (cbase + r) * L + j0;
+            sm[r * P + col] = (e0 + col / W < N) ? X[e0 * W + col] : 0.0;
+        }
+    }
+    __device__ void store(double* X, long long N, long long cbase, int L, int j0, int lane) const {
+        for (int i = lane; i < 32 * RW; i += 32) {
+            const int r = i / RW, col = i - r * RW;
+            const long long e0 = (cbase + r) * L + j0;
+            if (e0 + col / W < N) X[e0 * W + col] = sm[r * P + col];
+        }
+    }
+    __device__ double& at(int lane, int jj, int w) { return sm[lane * P + jj * W + w]; }
+};
+
+template <int D>
+struct WarpCtx {
+    UpIO io;
+    Tile<1> tdt;
+    Tile<D> ty;       // observations in, posterior means out (never live together)
+    Tile<D * D> tR;   // site covariances in, posterior covariances out
+    int lane;
+    static constexpr int kDoublesPerWarp = Tile<1>::kDoubles + Tile<D>::kDoubles + Tile<D * D>::kDoubles;
+
+    __device__ WarpCtx(const UpIO& io_, double* smem_warp) : io(io_) {
+        lane = threadIdx.x & 31;
+        tdt.sm = smem_warp;
+        ty.sm = tdt.sm + Tile<1>::kDoubles;
+        tR.sm = ty.sm + Tile<D>::kDoubles;
+    }
+    // cbase: first chunk of this warp
+    __device__ void begin(long long cbase, int L, int j0, bool want_obs) {
+        __syncwarp();
+        tdt.load(io.dt, io.N, cbase, L, j0, lane);
+        if (want_obs) {
+            ty.load(io.y, io.N, cbase, L, j0, lane);
+            tR.load(io.R, io.N, cbase, L, j0, lane);
+        }
+        __syncwarp();
+    }
+    __device__ void end(long long cbase, int L, int j0) {
+        __syncwarp();
+        ty.store(io.post_mean, io.N, cbase, L, j0, lane);
+        tR.store(io.post_cov, io.N, cbase, L, j0, lane);
+    }
+    __device__ double dt(long long, int jj) { return tdt.at(lane, jj, 0); }
+    __device__ void obs(long long, int jj, double* y, double* R) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) y[i] = ty.at(lane, jj, i);
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) R[i] = tR.at(lane, jj, i);
+    }
+    __device__ void put(long long, int jj, const double* pm, const double* pc) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) ty.at(lane, jj, i) = pm[i];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) tR.at(lane, jj, i) = pc[i];
+    }
+};
+#endif
+
+// DirectCtx spelling of the block hooks used by the shared chunk bodies
+template <int D> BN_DEV void ctx_begin(DirectCtx<D>&, long long, int, int, bool) {}
+template <int D> BN_DEV void ctx_end(DirectCtx<D>&, long long, int, int) {}
+#ifdef __CUDACC__
+template <int D> __device__ __forceinline__ void ctx_begin(WarpCtx<D>& cx, long long cbase, int L, int j0, bool obs) {
+    cx.begin(cbase, L, j0, obs);
+}
+template <int D> __device__ __forceinline__ void ctx_end(WarpCtx<D>& cx, long long cbase, int L, int j0) {
+    cx.end(cbase, L, j0);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------ chunk bodies
+// All bodies are called by every lane of a warp (`active` = this lane owns a real chunk) so the
+// staging hooks stay warp-uniform.
+#pragma nv_exec_check_disable
+template <class G, class Ctx>
+BN_DEV void up_reduce_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, int is_first, double* agg,
+                            long long c, bool active) {
+    constexpr int D = G::D;
+    using Alg = FilterAlg<G::d>;
+    typename Alg::Elem el;
+    Alg::identity(el);
+    const long long k0 = c * L, cbase = c & ~31LL;
+    for (int j0 = 0; j0 < L; j0 += kUpTJ) {
+        if (cbase * L + j0 >= N) break;  // warp-uniform: nothing left for any lane
+        ctx_begin(cx, cbase, L, j0, true);
+#pragma unroll 1
+        for (int jj = 0; jj < kUpTJ; ++jj) {
+            const long long k = k0 + j0 + jj;
+            if (active && k < N) {
+                double y[D], R[D * D], Ab[G::kBlockA];
+                cx.obs(k, jj, y, R);
+                g.trans(cx.dt(k, jj), Ab);
+                fkf_absorb<G>(g, el, Ab, y, R, is_first && k == 0);
+            }
+        }
+    }
+    if (active) Alg::store(agg, nchunks, c, el);
+}
+
+#pragma nv_exec_check_disable
+template <class G, bool WANT_ELL, class Ctx>
+BN_DEV void up_filter_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, int is_first,
+                            const double* prefix, const double* s0, double* fs, double* ell_partials, long long c,
+                            bool active) {
+    constexpr int d = G::d, D = G::D;
+    using Alg = FilterAlg<d>;
+    typename Alg::State s;
+    Alg::zero_state(s);
+    if (active) {
+        Alg::load_state(s0, 1, 0, s);
+        if (c > 0) {
+            typename Alg::Elem e;
+            Alg::load(prefix, nchunks, c - 1, e);
+            typename Alg::State t;
+            Alg::apply(e, s, t);
+            s = t;
+        } else if (is_first) {  // global step 0 starts from the stationary prior (m0 = 0, P0 = Pinf)
+            Alg::zero_state(s);
+            g.pinf_full(s.P);
+        }
+    }
+    double ell = 0.0;
+    const long long k0 = c * L, cbase = c & ~31LL;
+    for (int j0 = 0; j0 < L; j0 += kUpTJ) {
+        if (cbase * L + j0 >= N) break;
+        ctx_begin(cx, cbase, L, j0, true);
+#pragma unroll 1
+        for (int jj = 0; jj < kUpTJ; ++jj) {
+            const long long k = k0 + j0 + jj;
+            if (active && k < N) {
+                double y[D], R[D * D], Ab[G::kBlockA], mp[d], Pp[symn(d)];
+                unsigned char mk[D];
+                cx.obs(k, jj, y, R);
+                if (cx.io.mask) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) mk[i] = cx.io.mask[k * D + i];
+                }
+                g.trans(cx.dt(k, jj), Ab);
+                ell += fkf_step<G, WANT_ELL>(g, s.m, s.P, Ab, y, R, cx.io.mask ? mk : nullptr, mp, Pp);
+                fs_store<d>(fs, c, L, j0 + jj, s.m, s.P);
+            }
+        }
+    }
+    if (WANT_ELL && active) ell_partials[c] = ell;
+}
+
+// smoothing element of chunk c, stored at scan position nchunks-1-c (the smoother scans right to left)
+template <class G>
+BN_DEV void up_selem_chunk(long long N, int L, long long nchunks, int need_first, const double* agg,
+                           const double* s0, const double* fs, double* selems, long long c) {
+    constexpr int d = G::d;
+    using FA = FilterAlg<d>;
+    using SA = SmootherAlg<d>;
+    typename SA::Elem se;
+    if (c == 0 && !need_first) {
+        SA::identity(se);
+    } else {
+        typename FA::Elem fe;
+        FA::load(agg, nchunks, c, fe);
+        double ma[d], Pa[symn(d)], mb[d], Pb[symn(d)];
+        if (c == 0) {
+            typename FA::State s;
+            FA::load_state(s0, 1, 0, s);
+#pragma unroll
+            for (int i = 0; i < d; ++i) ma[i] = s.m[i];
+#pragma unroll
+            for (int i = 0; i < symn(d); ++i) Pa[i] = s.P[i];
+        } else {
+            fs_load<d>(fs, c - 1, L, L - 1, ma, Pa);
+        }
+        const long long kend = ((c + 1) * L < N) ? (c + 1) * L : N;
+        fs_load<d>(fs, c, L, (int)(kend - c * L) - 1, mb, Pb);
+        chunk_smoothing_element<d>(fe, ma, Pa, mb, Pb, se);
+    }
+    SA::store(selems, nchunks, nchunks - 1 - c, se);
+}
+
+#pragma nv_exec_check_disable
+template <class G, class Ctx>
+BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, const double* sprefix,
+                            const double* sinit, const double* fs, long long c, bool active) {
+    constexpr int d = G::d, D = G::D;
+    using Alg = SmootherAlg<d>;
+    typename Alg::State s;
+    Alg::zero_state(s);
+    const long long p = nchunks - 1 - c;
+    if (active) {
+        Alg::load_state(sinit, 1, 0, s);
+        if (p > 0) {
+            typename Alg::Elem e;
+            Alg::load(sprefix, nchunks, p - 1, e);
+            typename Alg::State t;
+            Alg::apply(e, s, t);
+            s = t;
+        }
+    }
+    const long long k0 = c * L, cbase = c & ~31LL;
+    const long long kend = ((c + 1) * L < N) ? (c + 1) * L : N;
+    const int j_last = (int)(kend - k0) - 1;  // s is the smoothed state of this step
+    double h_up = 0.0;                        // dt of the step above the current one
+    for (int j0 = L - kUpTJ; j0 >= 0; j0 -= kUpTJ) {
+        if (cbase * L + j0 >= N) continue;
+        ctx_begin(cx, cbase, L, j0, false);
+#pragma unroll 1
+        for (int jj = kUpTJ - 1; jj >= 0; --jj) {
+            const int j = j0 + jj;
+            const long long k = k0 + j;
+            if (active && j <= j_last) {
+                const double h_k = cx.dt(k, jj);
+                if (j < j_last) {
+                    double fm[d], fP[symn(d)], Ab[G::kBlockA], Qb[G::kBlockS];
+                    fs_load<d>(fs, c, L, j, fm, fP);
+                    g.trans(h_up, Ab);
+                    g.noise(Ab, Qb);
+                    frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
+                }
+                double pm[D], pc[D * D];
+#pragma unroll
+                for (int a = 0; a < D; ++a) {
+                    pm[a] = s.m[G::sel(a)];
+#pragma unroll
+                    for (int b = 0; b < D; ++b) pc[a * D + b] = s.P[sidx(G::sel(a), G::sel(b))];
+                }
+                cx.put(k, jj, pm, pc);
+                h_up = h_k;
+            }
+        }
+        ctx_end(cx, cbase, L, j0);
+    }
+}
+
+// state of the last step (tiled scratch -> flat state buffer): the smoother's start on the last rank
+template <int d>
+BN_DEV void up_last_state(long long N, int L, const double* fs, double* sinit) {
+    const long long c = (N - 1) / L;
+    typename SmootherAlg<d>::State s;
+    fs_load<d>(fs, c, L, (int)(N - 1 - c * L), s.m, s.P);
+    SmootherAlg<d>::store_state(sinit, 1, 0, s);
+}
+
+// carry of this rank for the smoother exchange: composition of all its chunk elements, closed on
+// the last rank by the terminal element (0, fm_N-1, fP_N-1) of ops.py:314-315
+template <int d>
+BN_DEV void up_export_scarry(const double* top_prefix, long long n_top, int is_last, long long N, int L,
+                             const double* fs, double* carry) {
+    using SA = SmootherAlg<d>;
+    typename SA::Elem tot;
+    SA::load(top_prefix, n_top, n_top - 1, tot);
+    if (is_last) {
+        typename SA::Elem term, r;
+#pragma unroll
+        for (int i = 0; i < d * d; ++i) term.E[i] = 0.0;
+        const long long c = (N - 1) / L;
+        fs_load<d>(fs, c, L, (int)(N - 1 - c * L), term.g, term.L);
+        SA::combine(term, tot, r);
+        tot = r;
+    }
+    SA::to_carry(tot, carry);
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------ kernels
+template <class G>
+__global__ void __launch_bounds__(kUpThreads)
+up_reduce_kernel(G g, UpIO io, int L, long long nchunks, int is_first, double* agg) {
+    extern __shared__ double up_smem[];
+    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp);
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    up_reduce_chunk(g, cx, io.N, L, nchunks, is_first, agg, c, c < nchunks);
+}
+
+template <class G, bool WANT_ELL>
+__global__ void __launch_bounds__(kUpThreads)
+up_filter_kernel(G g, UpIO io, int L, long long nchunks, int is_first, const double* prefix, const double* s0,
+                 double* fs, double* ell_partials) {
+    extern __shared__ double up_smem[];
+    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp);
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    up_filter_chunk<G, WANT_ELL>(g, cx, io.N, L, nchunks, is_first, prefix, s0, fs, ell_partials, c, c < nchunks);
+}
+
+template <class G>
+__global__ void __launch_bounds__(128)
+up_selem_kernel(long long N, int L, long long nchunks, int need_first, const double* agg, const double* s0,
+                const double* fs, double* selems) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nchunks) up_selem_chunk<G>(N, L, nchunks, need_first, agg, s0, fs, selems, c);
+}
+
+template <class G>
+__global__ void __launch_bounds__(kUpThreads)
+up_smooth_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, const double* sinit,
+                 const double* fs) {
+    extern __shared__ double up_smem[];
+    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp);
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    up_smooth_chunk(g, cx, io.N, L, nchunks, sprefix, sinit, fs, c, c < nchunks);
+}
+
+template <int d>
+__global__ void up_last_state_kernel(long long N, int L, const double* fs, double* sinit) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) up_last_state<d>(N, L, fs, sinit);
+}
+
+template <int d>
+__global__ void up_export_scarry_kernel(const double* top_prefix, long long n_top, int is_last, long long N, int L,
+                                        const double* fs, double* carry) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) up_export_scarry<d>(top_prefix, n_top, is_last, N, L, fs, carry);
+}
+
+// ------------------------------------------------------------------------------------------ host driver
+enum { UP_ALL = 0, UP_REDUCE = 1, UP_FILTER = 2, UP_SMOOTH = 3 };
+
+struct UpWs {
+    double *s0, *sinit, *partials, *fs;
+    ScanPlan fplan, splan;
+};
+
+template <int d>
+inline size_t up_ws_doubles(long long N) {
+    ChunkPlan cp = up_plan_chunks(N > 0 ? N : 1);
+    return 128 + scan_plan_doubles(cp.nchunks, FilterAlg<d>::kElem) + scan_plan_doubles(cp.nchunks, SmootherAlg<d>::kElem) +
+           cp.nchunks + fs_doubles(cp.nchunks, cp.L, d + symn(d));
+}
+
+template <int d>
+inline UpWs up_ws(void* ws, const ChunkPlan& cp) {
+    UpWs w;
+    double* p = (double*)ws;
+    w.s0 = p; p += 64;
+    w.sinit = p; p += 64;
+    w.fplan = make_scan_plan(p, cp.nchunks, FilterAlg<d>::kElem);
+    p += scan_plan_doubles(cp.nchunks, FilterAlg<d>::kElem);
+    w.splan = make_scan_plan(p, cp.nchunks, SmootherAlg<d>::kElem);
+    p += scan_plan_doubles(cp.nchunks, SmootherAlg<d>::kElem);
+    w.partials = p; p += cp.nchunks;
+    w.fs = p;
+    return w;
+}
+
+struct UpCall {
+    const bn_kernel_spec* spec;
+    UpIO io;
+    double* ell;
+    void* ws;
+    size_t ws_bytes;
+    cudaStream_t st;
+    int phase, rank, world;
+    double* carry_out;       // UP_REDUCE: filter carry; UP_FILTER: smoother carry
+    const double* carries;   // UP_FILTER: filter carries [world]; UP_SMOOTH: smoother carries [world]
+};
+
+template <class G>
+inline int up_run(const UpCall& c) {
+    constexpr int d = G::d;
+    using FA = FilterAlg<d>;
+    using SA = SmootherAlg<d>;
+    cudaStream_t st = c.st;
+    const UpIO& io = c.io;
+    if (io.N == 0) {
+        if (c.ell) BN_CUDA(cudaMemsetAsync(c.ell, 0, sizeof(double), st));
+        return 0;
+    }
+    G g;
+    g.prepare(*c.spec);
+    ChunkPlan cp = up_plan_chunks(io.N);
+    size_t need = up_ws_doubles<d>(io.N) * sizeof(double);
+    BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
+    UpWs w = up_ws<d>(c.ws, cp);
+    const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
+    const size_t smem = (size_t)kUpWarps * WarpCtx<G::D>::kDoublesPerWarp * sizeof(double);
+    const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
+    const bool sharded = c.phase != UP_ALL;
+    if (smem > 48 * 1024) {  // multi-latent tiles exceed the default dynamic shared-memory window
+        BN_CUDA(cudaFuncSetAttribute(up_reduce_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BN_CUDA(cudaFuncSetAttribute(up_filter_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BN_CUDA(cudaFuncSetAttribute(up_filter_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BN_CUDA(cudaFuncSetAttribute(up_smooth_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+
+    if (c.phase == UP_ALL || c.phase == UP_REDUCE) {
+        BN_LAUNCH("up_reduce", st,
+                  (up_reduce_kernel<G><<<grid, kUpThreads, smem, st>>>(g, io, cp.L, cp.nchunks, is_first, w.fplan.input0)));
+        BN_CUDA(cudaGetLastError());
+        BN_CUDA(run_scan<FA>(w.fplan, st));
+        if (c.carry_out && c.phase == UP_REDUCE) {
+            int top = w.fplan.levels - 1;
+            export_carry_kernel<FA><<<1, 1, 0, st>>>(w.fplan.prefix[top], w.fplan.count[top], c.carry_out);
+            BN_CUDA(cudaGetLastError());
+        }
+    }
+    if (c.phase == UP_ALL || c.phase == UP_FILTER) {
+        if (sharded) {
+            fold_carries_kernel<FA><<<1, 1, 0, st>>>(c.carries, 0, c.rank, 1, w.s0);
+            BN_CUDA(cudaGetLastError());
+        } else {
+            BN_CUDA(cudaMemsetAsync(w.s0, 0, FA::kState * sizeof(double), st));
+        }
+        if (c.ell) {
+            BN_LAUNCH("up_filter", st,
+                      (up_filter_kernel<G, true><<<grid, kUpThreads, smem, st>>>(
+                          g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, w.partials)));
+            BN_CUDA(cudaGetLastError());
+            BN_LAUNCH("sum", st, (sum_kernel<false><<<1, 1024, 0, st>>>(w.partials, cp.nchunks, c.ell, 1.0)));
+        } else {
+            BN_LAUNCH("up_filter", st,
+                      (up_filter_kernel<G, false><<<grid, kUpThreads, smem, st>>>(
+                          g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, nullptr)));
+        }
+        BN_CUDA(cudaGetLastError());
+        const unsigned g2 = (unsigned)((cp.nchunks + 127) / 128);
+        BN_LAUNCH("up_selem", st,
+                  (up_selem_kernel<G><<<g2, 128, 0, st>>>(io.N, cp.L, cp.nchunks, !is_first, w.fplan.input0, w.s0,
+                                                          w.fs, w.splan.input0)));
+        BN_CUDA(cudaGetLastError());
+        BN_CUDA(run_scan<SA>(w.splan, st));
+        if (c.carry_out && c.phase == UP_FILTER) {
+            int top = w.splan.levels - 1;
+            up_export_scarry_kernel<d><<<1, 1, 0, st>>>(w.splan.prefix[top], w.splan.count[top], is_last, io.N, cp.L,
+                                                        w.fs, c.carry_out);
+            BN_CUDA(cudaGetLastError());
+        }
+    }
+    if (c.phase == UP_ALL || c.phase == UP_SMOOTH) {
+        if (sharded && !is_last) {
+            fold_carries_kernel<SA><<<1, 1, 0, st>>>(c.carries, c.world - 1, c.rank, -1, w.sinit);
+        } else {
+            up_last_state_kernel<d><<<1, 1, 0, st>>>(io.N, cp.L, w.fs, w.sinit);
+        }
+        BN_CUDA(cudaGetLastError());
+        BN_LAUNCH("up_smooth", st,
+                  (up_smooth_kernel<G><<<grid, kUpThreads, smem, st>>>(g, io, cp.L, cp.nchunks, w.splan.prefix[0],
+                                                                       w.sinit, w.fs)));
+        BN_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+#define BN_UP_SPEC_CASE(FAM, NC)                                           \
+    if (c.spec->family == FAM && c.spec->n_components == NC) return up_run<FastGen<FAM, NC>>(c);
+#endif  // __CUDACC__
+
+}  // namespace bn

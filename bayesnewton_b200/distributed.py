@@ -40,6 +40,40 @@ class TimeShard:
         self.ws_s, self.nb_s = _ws(self.N, self.d, self.D, dev)
         self.kf_len = _lib.lib().bn_kf_carry_len(self.d)
         self.rts_len = _lib.lib().bn_rts_carry_len(self.d)
+        self._ws_up = None
+
+    # ---- fused posterior update (bn_up_shard_*): reduce -> [all-gather] -> filter -> [all-gather] -> smooth
+    def _up_ws(self):
+        if self._ws_up is None:
+            nb = _lib.lib().bn_update_posterior_workspace_bytes(self.spec, self.N)
+            self._ws_up = (torch.empty(int(nb), dtype=torch.uint8, device=self.dt.device), int(nb))
+        return self._ws_up
+
+    def up_reduce(self, y, R):
+        ws, nb = self._up_ws()
+        carry = torch.empty(self.kf_len, dtype=torch.float64, device=self.dt.device)
+        _lib.check(_lib.lib().bn_up_shard_reduce(self.spec, self.N, self.rank, self.world, ptr(self.dt), ptr(y), ptr(R),
+                                                 ptr(carry), ptr(ws), nb, stream_ptr()))
+        return carry
+
+    def up_filter(self, kf_carries, y, R, mask=None, want_ell=True):
+        ws, nb = self._up_ws()
+        dev = self.dt.device
+        ell = torch.zeros((), dtype=torch.float64, device=dev) if want_ell else None
+        carry = torch.empty(self.rts_len, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().bn_up_shard_filter(self.spec, self.N, self.rank, self.world, ptr(kf_carries), ptr(self.dt),
+                                                 ptr(y), ptr(R), ptr(mask), ptr(ell), ptr(carry), ptr(ws), nb,
+                                                 stream_ptr()))
+        return ell, carry
+
+    def up_smooth(self, rts_carries):
+        ws, nb = self._up_ws()
+        dev = self.dt.device
+        sm = torch.empty((self.N, self.D, 1), dtype=torch.float64, device=dev)
+        sP = torch.empty((self.N, self.D, self.D), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().bn_up_shard_smooth(self.spec, self.N, self.rank, self.world, ptr(rts_carries),
+                                                 ptr(self.dt), ptr(sm), ptr(sP), ptr(ws), nb, stream_ptr()))
+        return sm, sP
 
     # ---- filter
     def kf_reduce(self, y, R):
@@ -86,8 +120,18 @@ def _all_gather(carry, world):
 
 
 def sharded_update_posterior(shard, y, R, mask=None, want_ell=False):
-    """update_posterior (basemodels.py:689-706) on a time-sharded model: 2 carry all-gathers.
-    Every rank passes ITS shard of the sites; returns (ell_local_or_None, post_mean, post_cov) for its steps."""
+    """update_posterior (basemodels.py:689-706) on a time-sharded model: the fused library path, 2 carry
+    all-gathers.  Every rank passes ITS shard of the sites; returns (ell_local_or_None, post_mean, post_cov)."""
+    c = shard.up_reduce(y, R)
+    carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
+    ell, c = shard.up_filter(carries, y, R, mask, want_ell=want_ell)
+    carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
+    sm, sP = shard.up_smooth(carries)
+    return ell, sm, sP
+
+
+def sharded_filter_smoother(shard, y, R, mask=None, want_ell=False):
+    """the same update through the stand-alone filter and smoother entry points (bn_kf_shard_*, bn_rts_shard_*)"""
     c = shard.kf_reduce(y, R)
     carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
     ell, fm, fP = shard.kf_apply(carries, y, R, mask, want_ell=want_ell)
@@ -134,6 +178,25 @@ def filter_smoother_in_shards(kernel, dt, y, R, mask, n_shards):
                 post_cov=torch.cat([s[1] for s in smo]))
 
 
+def update_posterior_in_shards(kernel, dt, y, R, mask, n_shards):
+    """single-process run of the FUSED sharded update (bn_up_shard_*) over n_shards shards"""
+    dt, y, R = as_dev(dt).reshape(-1), as_dev(y), as_dev(R)
+    mk = as_mask(mask)
+    N = dt.shape[0]
+    b = shard_bounds(N, n_shards)
+    shards = [TimeShard(kernel, dt[b[r]:b[r + 1]], dt[b[r]:b[r + 1]], r, n_shards) for r in range(n_shards)]
+    D = shards[0].D
+    ys = [y.reshape(N, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
+    Rs = [R.reshape(N, D, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
+    ms = [None if mk is None else mk.reshape(N, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
+    carries = torch.stack([s.up_reduce(ys[r], Rs[r]) for r, s in enumerate(shards)])
+    filt = [s.up_filter(carries, ys[r], Rs[r], ms[r]) for r, s in enumerate(shards)]
+    carries = torch.stack([f[1] for f in filt])
+    smo = [s.up_smooth(carries) for s in shards]
+    return dict(ell=sum(f[0] for f in filt), post_mean=torch.cat([s[0] for s in smo]),
+                post_cov=torch.cat([s[1] for s in smo]))
+
+
 class TimeShardedMarkovGP:
     """One rank's view of a time-sharded temporal Markov GP: the host mirror of
     MarkovGaussianProcess + an inference mixin (basemodels.py:625-764, inference.py:65-90) where the
@@ -167,7 +230,8 @@ class TimeShardedMarkovGP:
 
     def update_posterior(self):
         pl = self.pseudo_likelihood
-        _, sm, sP = sharded_update_posterior(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y)
+        ell, sm, sP = sharded_update_posterior(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y, want_ell=True)
+        self._ell_cache = (ell, pl.version)  # the local log-likelihood partial of exactly these sites
         self.posterior_mean, self.posterior_variance = sm, sP
 
     def _site_args(self, cubature=None):
@@ -184,6 +248,7 @@ class TimeShardedMarkovGP:
         a.site_mean, a.site_cov = pl.mean_.data_ptr(), pl.covariance_.data_ptr()
         ws, nb = self._ws
         _lib.check(_lib.lib().bn_site_update(a, ptr(ws), nb, stream_ptr()))
+        pl.version += 1
         self.update_posterior()
 
     def energy(self, cubature=None):
@@ -199,7 +264,11 @@ class TimeShardedMarkovGP:
         _lib.check(_lib.lib().bn_gaussian_expected_log_lik(
             self.N, a.D, ptr(pl.mean), ptr(self.posterior_mean), ptr(self.posterior_variance), ptr(pl.covariance),
             ptr(self.mask_pseudo_y), None, parts[1:2].data_ptr(), ptr(ws), nb, stream_ptr()))
-        parts[2:3] = sharded_log_lik(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y)
+        cache = getattr(self, '_ell_cache', None)
+        if cache is not None and cache[1] == pl.version:  # same sites, same kernel: the filter pass of update_posterior
+            parts[2:3] = cache[0]
+        else:
+            parts[2:3] = sharded_log_lik(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(parts)

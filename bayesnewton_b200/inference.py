@@ -42,6 +42,7 @@ class InferenceMixin:
         a.diffs = diffs.data_ptr()
         ws, nb = workspace(N, self.state_dim, D)
         _lib.check(_lib.lib().bn_site_update(a, ptr(ws), nb, stream_ptr()))
+        pl.version += 1  # the sites were rewritten in place
         self.update_posterior()
         return state, (diffs[0], diffs[1])
 

@@ -16,10 +16,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._util import as_dev, as_mask, ptr, stream_ptr, workspace
+from ._util import as_dev, as_mask, ptr, stream_ptr, up_workspace, workspace
 from .kernels import discretise
 
-__all__ = ['kalman_filter', 'rauch_tung_striebel_smoother', '_sequential_kf', '_parallel_kf', '_sequential_rts',
+__all__ = ['update_posterior', 'kalman_filter', 'rauch_tung_striebel_smoother', '_sequential_kf', '_parallel_kf', '_sequential_rts',
            '_parallel_rts', 'process_noise_covariance']
 
 
@@ -131,3 +131,27 @@ def rauch_tung_striebel_smoother(dt, kernel, filter_mean, filter_cov, return_ful
                                           int(bool(return_full)), ptr(means), ptr(covs), ptr(gains), ptr(ws), nb,
                                           stream_ptr()))
     return means, covs, gains
+
+
+def update_posterior(dt, kernel, y, noise_cov, mask=None, want_ell=False):
+    """kalman_filter followed by rauch_tung_striebel_smoother, `parallel=True` form, as ONE library call
+    (MarkovGaussianProcess.update_posterior, basemodels.py:689-706).  Returns (ell or None, means [N,D,1],
+    covs [N,D,D]) = (filter log-likelihood, H sm, H sP H^T).  Needs a kernel with an in-library
+    discretisation (kernel.spec()); other kernels take the two stand-alone calls."""
+    spec = kernel.spec() if hasattr(kernel, 'spec') else None
+    if spec is None:
+        raise NotImplementedError('the fused update needs kernel.spec(); use kalman_filter + rauch_tung_striebel_smoother')
+    dt = as_dev(dt).reshape(-1)
+    N = dt.shape[0]
+    y, R = as_dev(y), as_dev(noise_cov)
+    D = spec.n_components
+    if y.numel() != N * D or R.numel() != N * D * D:
+        raise ValueError('y must be [N,%d,1] and noise_cov [N,%d,%d] for N = %d steps' % (D, D, D, N))
+    mk = as_mask(mask)
+    ell = torch.zeros((), dtype=torch.float64, device=dt.device) if want_ell else None
+    means = torch.empty((N, D, 1), dtype=torch.float64, device=dt.device)
+    covs = torch.empty((N, D, D), dtype=torch.float64, device=dt.device)
+    ws, nb = up_workspace(spec, N)
+    _lib.check(_lib.lib().bn_update_posterior(spec, N, ptr(dt), ptr(y), ptr(R), ptr(mk), ptr(ell), ptr(means),
+                                              ptr(covs), ptr(ws), nb, stream_ptr()))
+    return ell, means, covs

@@ -14,6 +14,8 @@
  *   bn_rts_smoother        rauch_tung_striebel_smoother           ops.py:357-380
  *   bn_kf_shard_*          the same filter, split in the three phases a time-sharded
  *   bn_rts_shard_*         (multi-GPU) two-level scan needs       ops.py:203-219, 328-335
+ *   bn_update_posterior    MarkovGaussianProcess.update_posterior  basemodels.py:689-706 (filter + smoother fused)
+ *   bn_up_shard_*          the same, on one time shard of a multi-GPU run
  *   bn_site_update         update_variational_params + newton_update + damped update_nat_params
  *                          inference.py:21-39,65-90,105-128,170-195,238-284,339-371; basemodels.py:85-100
  *   bn_expected_density    the value-only likelihood term of energy()
@@ -115,6 +117,39 @@ int bn_rts_smoother(const bn_kernel_spec* k, int form, int64_t N,
                     const double* dt, const double* filter_mean, const double* filter_cov, int return_full,
                     double* means, double* covs, double* gains,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused posterior update: filter + smoother in one call --------------------------------- */
+/* MarkovGaussianProcess.update_posterior (basemodels.py:689-706): kalman_filter(dt, kernel, pseudo_y,
+ * pseudo_var, mask, parallel=True) followed by rauch_tung_striebel_smoother(dt', kernel, fm, fP,
+ * parallel=True); dt' = [dt[1:], 0] is formed internally.  post_mean[N,D,1] = H sm, post_cov[N,D,D] =
+ * H sP H^T.  ell (nullable) receives the filter log-likelihood, the quantity compute_log_lik()
+ * (basemodels.py:726-741) recomputes from the same inputs.  The filtered states never leave the
+ * workspace and the smoother's per-chunk elements are derived from the filter's chunk elements, so
+ * one call moves 216 B/step at d = 3 instead of 368 B/step for the two stand-alone calls. */
+size_t bn_update_posterior_workspace_bytes(const bn_kernel_spec* k, int64_t N);
+int bn_update_posterior(const bn_kernel_spec* k, int64_t N, const double* dt,
+                        const double* pseudo_y, const double* pseudo_var, const uint8_t* mask,
+                        double* ell, double* post_mean, double* post_cov,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* The same update on a time shard (one rank of a multi-GPU run), in three phases around two carry
+ * all-gathers.  All three calls of one update must be given the SAME workspace (it keeps the chunk
+ * elements and the filtered states alive between phases).  dt here is the shard's slice of the
+ * global dt (no shifted copy, no halo: the step across a shard boundary belongs to the right shard).
+ *   reduce : local steps -> one filtering carry [bn_kf_carry_len(d)]
+ *   filter : kf_carries[world] -> local filter pass, local log-likelihood partial (nullable),
+ *            one smoothing carry [bn_rts_carry_len(d)] mapping the state at this shard's last step
+ *            to the state at the previous shard's last step (closed by the terminal element on the
+ *            last rank, ops.py:314-315)
+ *   smooth : rts_carries[world] -> local smoother pass, post_mean / post_cov of the local steps */
+int bn_up_shard_reduce(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* dt,
+                       const double* pseudo_y, const double* pseudo_var, double* kf_carry,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int bn_up_shard_filter(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* kf_carries,
+                       const double* dt, const double* pseudo_y, const double* pseudo_var, const uint8_t* mask,
+                       double* ell, double* rts_carry, void* workspace, size_t workspace_bytes, void* stream);
+int bn_up_shard_smooth(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* rts_carries,
+                       const double* dt, double* post_mean, double* post_cov,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- time-sharded (multi-GPU) scan: reduce -> exchange carries -> apply ------------------ */
 /* number of doubles in one filtering carry (A,b,C,J,eta full storage: 3d^2+2d) / smoothing carry

@@ -78,6 +78,21 @@ def rts_smoother(lib, sp, form, dt, fm, fP, L=8, world=1, return_full=False):
     return sm, sP, G
 
 
+def update_posterior(lib, sp, dt, y, R, mask=None, L=8, world=1, want_ell=True):
+    """fused filter + smoother (csrc/up_impl.cuh): returns ell, post_mean [N,D,1], post_cov [N,D,D]"""
+    N = dt.shape[0]
+    D = sp.n_components
+    dt, y, R = (np.ascontiguousarray(a, dtype=np.float64) for a in (dt, y, R))
+    mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    ell = np.zeros(1)
+    pm = np.zeros((N, D, 1))
+    pc = np.zeros((N, D, D))
+    rc = lib.emu_update_posterior(C.byref(sp), C.c_longlong(N), L, world, _p(dt), _p(y), _p(R), _p(mk),
+                                  _p(ell) if want_ell else None, _p(pm), _p(pc))
+    assert rc == 0, rc
+    return ell[0], pm, pc
+
+
 class SiteArgs(C.Structure):
     _fields_ = [('method', C.c_int32), ('likelihood', C.c_int32), ('lik_param', C.c_double), ('N', C.c_int64),
                 ('D', C.c_int32), ('Q', C.c_int32), ('cub_x', C.c_void_p), ('cub_w', C.c_void_p), ('y', C.c_void_p),

@@ -11,6 +11,7 @@
 #include "../../bayesnewton_b200/csrc/filter_impl.cuh"
 #include "../../bayesnewton_b200/csrc/smoother_impl.cuh"
 #include "../../bayesnewton_b200/csrc/sites_impl.cuh"
+#include "../../bayesnewton_b200/csrc/up_impl.cuh"
 
 namespace bn {
 void set_error(const char*, ...) {}
@@ -119,6 +120,72 @@ static int emu_rts(MakeGen make, int form, long long N, int L, int world, const 
         fold_carries_body<Alg>(carries.data(), world - 1, r, -1, s0);
         for (long long c = 0; c < nch[r]; ++c)
             rts_apply_chunk(gen, io, L, nch[r], r == world - 1, prefixes[r].data(), s0, c);
+    }
+    return 0;
+}
+
+
+// fused posterior update (up_impl.cuh) over `world` emulated ranks: the three sharded phases with
+// DirectCtx IO, host scans, the same tiled scratch layout, carry export and folds as up_run().
+template <class G>
+static int emu_up(const bn_kernel_spec* k, long long N, int L, int world, const double* dt, const double* y,
+                  const double* R, const unsigned char* mask, double* ell, double* pm, double* pc) {
+    constexpr int d = G::d, D = G::D;
+    using FA = FilterAlg<d>;
+    using SA = SmootherAlg<d>;
+    if (L % kUpTJ != 0) return -2;
+    G g;
+    g.prepare(*k);
+    std::vector<long long> off(world + 1);
+    for (int r = 0; r <= world; ++r) off[r] = N * r / world;
+    struct Rank { long long n, nc; std::vector<double> agg, fpre, sel, spre, fs, s0, sinit; UpIO io; };
+    std::vector<Rank> ranks(world);
+    std::vector<double> fcar((size_t)world * FA::kCarry), scar((size_t)world * SA::kCarry);
+    for (int r = 0; r < world; ++r) {
+        Rank& q = ranks[r];
+        long long o = off[r];
+        q.n = off[r + 1] - o;
+        q.nc = (q.n + L - 1) / L;
+        q.io = UpIO{q.n, dt + o, y + o * D, R + o * D * D, mask ? mask + o * D : nullptr, pm + o * D, pc + o * D * D};
+        q.agg.assign((size_t)q.nc * FA::kElem, 0.0);
+        q.fpre.assign((size_t)q.nc * FA::kElem, 0.0);
+        q.sel.assign((size_t)q.nc * SA::kElem, 0.0);
+        q.spre.assign((size_t)q.nc * SA::kElem, 0.0);
+        q.fs.assign((size_t)fs_doubles(q.nc, L, d + symn(d)), 0.0);
+        q.s0.assign(64, 0.0);
+        q.sinit.assign(64, 0.0);
+        DirectCtx<D> cx{q.io};
+        for (long long c = 0; c < q.nc; ++c) up_reduce_chunk(g, cx, q.n, L, q.nc, r == 0, q.agg.data(), c, true);
+        host_scan<FA>(q.agg.data(), q.nc, q.fpre.data());
+        export_carry_body<FA>(q.fpre.data(), q.nc, fcar.data() + (size_t)r * FA::kCarry);
+    }
+    double total = 0.0;
+    for (int r = 0; r < world; ++r) {
+        Rank& q = ranks[r];
+        DirectCtx<D> cx{q.io};
+        fold_carries_body<FA>(fcar.data(), 0, r, 1, q.s0.data());
+        std::vector<double> partials(q.nc, 0.0);
+        for (long long c = 0; c < q.nc; ++c) {
+            if (ell) up_filter_chunk<G, true>(g, cx, q.n, L, q.nc, r == 0, q.fpre.data(), q.s0.data(), q.fs.data(),
+                                              partials.data(), c, true);
+            else up_filter_chunk<G, false>(g, cx, q.n, L, q.nc, r == 0, q.fpre.data(), q.s0.data(), q.fs.data(),
+                                           nullptr, c, true);
+        }
+        for (double v : partials) total += v;
+        for (long long c = 0; c < q.nc; ++c)
+            up_selem_chunk<G>(q.n, L, q.nc, r != 0, q.agg.data(), q.s0.data(), q.fs.data(), q.sel.data(), c);
+        host_scan<SA>(q.sel.data(), q.nc, q.spre.data());
+        up_export_scarry<d>(q.spre.data(), q.nc, r == world - 1, q.n, L, q.fs.data(),
+                            scar.data() + (size_t)r * SA::kCarry);
+    }
+    if (ell) *ell = total;
+    for (int r = 0; r < world; ++r) {
+        Rank& q = ranks[r];
+        DirectCtx<D> cx{q.io};
+        if (r != world - 1) fold_carries_body<SA>(scar.data(), world - 1, r, -1, q.sinit.data());
+        else up_last_state<d>(q.n, L, q.fs.data(), q.sinit.data());
+        for (long long c = 0; c < q.nc; ++c)
+            up_smooth_chunk(g, cx, q.n, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, true);
     }
     return 0;
 }
@@ -245,4 +312,15 @@ extern "C" int emu_ep_pseudo_density(long long N, int D, double power, int with_
     }
     *sum = s;
     return 0;
+}
+
+extern "C" int emu_update_posterior(const bn_kernel_spec* k, long long N, int L, int world, const double* dt,
+                                    const double* y, const double* R, const unsigned char* mask, double* ell,
+                                    double* post_mean, double* post_cov) {
+#define X(FAM, NC) \
+    if (k->family == FAM && k->n_components == NC) \
+        return emu_up<FastGen<FAM, NC>>(k, N, L, world, dt, y, R, mask, ell, post_mean, post_cov);
+    EMU_MATERN(X)
+#undef X
+    return -1;
 }

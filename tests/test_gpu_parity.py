@@ -65,6 +65,37 @@ def test_filter_smoother_vs_oracle(bn, name, parallel, N):
             assert rel_err(np_(a), b) < TOL
 
 
+@pytest.mark.parametrize('name', ['m12', 'm32', 'm52', 'm72', 'ind32', 'ind52'])
+@pytest.mark.parametrize('N', [1, 7, 8, 203, 3001, 70001])
+def test_fused_update_posterior_vs_oracle(bn, name, N):
+    """bn_update_posterior (filter + smoother in one call, smoothing elements derived from the filter's chunk
+    elements) against the oracle's sequential filter -> smoother"""
+    kg, ko, D = make_kernels(bn)[name]
+    dt, y, R, mask = filter_problem(N, D=D, seed=N + 1)
+    e0, (fm, fP) = kalman.kalman_filter(dt, ko, y, R, mask)
+    sm, sP, _ = kalman.rauch_tung_striebel_smoother(np.concatenate([dt[1:], [0.0]]), ko, fm, fP)
+    e1, m1, P1 = bn.ops.update_posterior(dt, kg, y, R, mask, want_ell=True)
+    assert abs(float(e1) - e0) <= TOL * abs(e0)
+    assert rel_err(np_(m1), sm) < TOL and rel_err(np_(P1), sP) < TOL
+    e2, m2, P2 = bn.ops.update_posterior(dt, kg, y, R, None, want_ell=False)
+    assert e2 is None and rel_err(np_(m2), sm) < TOL and rel_err(np_(P2), sP) < TOL
+
+
+@pytest.mark.parametrize('name', ['m52', 'ind32'])
+@pytest.mark.parametrize('N,shards', [(9, 3), (1000, 2), (70001, 5), (70001, 8)])
+def test_fused_update_in_time_shards(bn, name, N, shards):
+    """the three-phase sharded form of the fused update (what each rank of a multi-GPU run executes),
+    all shards in one process, against the single-call result and the oracle"""
+    from bayesnewton_b200 import distributed
+    kg, ko, D = make_kernels(bn)[name]
+    dt, y, R, mask = filter_problem(N, D=D, seed=N + 2)
+    e0, (fm, fP) = kalman.kalman_filter(dt, ko, y, R, mask)
+    sm, sP, _ = kalman.rauch_tung_striebel_smoother(np.concatenate([dt[1:], [0.0]]), ko, fm, fP)
+    res = distributed.update_posterior_in_shards(kg, dt, y, R, mask, shards)
+    assert abs(float(res['ell']) - e0) <= TOL * abs(e0)
+    assert rel_err(np_(res['post_mean']), sm) < TOL and rel_err(np_(res['post_cov']), sP) < TOL
+
+
 def test_no_mask_and_skipped_outputs(bn):
     kg, ko, _ = make_kernels(bn)['m52']
     dt, y, R, _ = filter_problem(500, seed=3)
@@ -309,5 +340,12 @@ def test_full_size_properties_c2(bn):
     assert abs(float(res['ell']) - float(ell)) <= TOL * abs(float(ell))
     assert rel_err(np_(res['post_mean']), np_(m.posterior_mean)) < TOL
     assert rel_err(np_(res['post_cov']), np_(m.posterior_variance)) < TOL
-    del res, sm, sP, fm, fP
+    res2 = distributed.update_posterior_in_shards(kg, m.dt, m.pseudo_likelihood.mean, m.pseudo_likelihood.covariance,
+                                                  None, 3)
+    assert abs(float(res2['ell']) - float(ell)) <= TOL * abs(float(ell))
+    assert rel_err(np_(res2['post_mean']), np_(m.posterior_mean)) < TOL
+    assert rel_err(np_(res2['post_cov']), np_(m.posterior_variance)) < TOL
+    # the log-likelihood the fused update keeps for energy() is the stand-alone filter's
+    assert abs(float(m.compute_log_lik()) - float(ell)) <= TOL * abs(float(ell))
+    del res, res2, sm, sP, fm, fP
     torch.cuda.empty_cache()

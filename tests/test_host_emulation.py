@@ -44,6 +44,36 @@ def test_filter_and_smoother(emu, name, form, L, world):
             assert rel_err(a, b) < TOL
 
 
+@pytest.mark.parametrize('name', sorted(KERNELS))
+@pytest.mark.parametrize('N', [1, 7, 8, 9, 203, 1000])
+@pytest.mark.parametrize('L,world', [(8, 1), (16, 1), (8, 3), (24, 2), (128, 4)])
+def test_fused_update_posterior(emu, name, N, L, world):
+    """csrc/up_impl.cuh: the fused filter + smoother whose smoothing elements are derived per CHUNK from the
+    filter's chunk elements (fast_core.cuh chunk_smoothing_element), incl. the sharded carry path"""
+    if world > N:
+        pytest.skip('fewer steps than shards')
+    fam, mk, vs, ls = KERNELS[name]
+    k = mk()
+    dt, y, R, mask = filter_problem(N, D=len(vs), seed=11)
+    e0, (fm, fP) = kalman.kalman_filter(dt, k, y, R, mask)
+    sm, sP, _ = kalman.rauch_tung_striebel_smoother(np.concatenate([dt[1:], [0.0]]), k, fm, fP)
+    e1, pm, pc = _emu.update_posterior(emu, _emu.spec(fam, vs, ls), dt, y, R, mask, L=L, world=world)
+    assert abs(e1 - e0) <= TOL * abs(e0) and rel_err(pm, sm) < TOL and rel_err(pc, sP) < TOL
+
+
+@pytest.mark.parametrize('lo,hi,rscale', [(1e-3, 5e-3, 1.0), (1e-3, 5e-3, 100.0), (2.0, 5.0, 1.0), (0.1, 0.3, 100.0)])
+def test_fused_update_conditioning(emu, lo, hi, rscale):
+    """small dt / lengthscale (ill-conditioned Q), long gaps, and the vague initial sites (variance 100)"""
+    k = ssm.Matern52(1.3, 1.0)
+    dt, y, R, mask = filter_problem(4000, seed=3, dt_lo=lo, dt_hi=hi)
+    R = R * rscale
+    e0, (fm, fP) = kalman.kalman_filter(dt, k, y, R, mask)
+    sm, sP, _ = kalman.rauch_tung_striebel_smoother(np.concatenate([dt[1:], [0.0]]), k, fm, fP)
+    for L, world in ((8, 1), (128, 1), (128, 4)):
+        e1, pm, pc = _emu.update_posterior(emu, _emu.spec(3, [1.3], [1.0]), dt, y, R, mask, L=L, world=world)
+        assert abs(e1 - e0) <= TOL * abs(e0) and rel_err(pm, sm) < TOL and rel_err(pc, sP) < TOL
+
+
 def test_ragged_and_tiny_inputs(emu):
     sp = _emu.spec(3, [1.0], [1.0])
     k = ssm.Matern52(1.0, 1.0)
