@@ -1,40 +1,97 @@
 // C ABI of the site kernels (include/bn_b200.h): bn_site_update, bn_expected_density,
 // bn_gaussian_expected_log_lik, bn_ep_pseudo_density.  One thread per time step, coalesced
 // loads/stores of the per-step scalars, deterministic two-stage reductions for the sums.
+#include <cstdlib>
 #include "sites_impl.cuh"
 
 namespace bn {
 
 constexpr int kSiteThreads = 256;
+constexpr int kSiteMaxGrid = 148 * 6;  // persistent grid: 6 CTAs per SM, grid-stride over the time steps
 
+// the probit log-density table in device memory, filled once per device (probit_table.cuh)
+__device__ double g_probit_tab[kPtDoubles];
+static bool g_probit_ready[64] = {false};
+
+static int ensure_probit_table(cudaStream_t st) {
+    int dev = 0;
+    BN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return -1; }
+    if (!g_probit_ready[dev]) {
+        const std::vector<double>& t = probit_table_host();
+        BN_CUDA(cudaMemcpyToSymbolAsync(g_probit_tab, t.data(), sizeof(double) * kPtDoubles, 0, cudaMemcpyHostToDevice, st));
+        g_probit_ready[dev] = true;
+    }
+    return 0;
+}
+
+// the cubature-driven probit schemes read the table from shared memory
 template <int LIK, int METHOD>
-__global__ void __launch_bounds__(kSiteThreads) site_update_kernel(bn_site_args a, double* part1, double* part2) {
-    const long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x;
+constexpr bool kUsesTable = (LIK == BN_LIK_BERNOULLI_PROBIT) && (METHOD == BN_METHOD_VI || METHOD == BN_METHOD_EP || METHOD == BN_METHOD_PL);
+
+// BN_B200_PROBIT_TABLE=0 in the environment routes the probit schemes through erf()/log() instead
+// (validation aid: A/B of the tabulated log-density against libm on the device)
+static bool probit_table_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("BN_B200_PROBIT_TABLE");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <bool TAB>
+__device__ __forceinline__ const double* stage_table(double* sm) {
+    if constexpr (TAB) {
+        for (int i = threadIdx.x; i < kPtDoubles; i += kSiteThreads) sm[i] = g_probit_tab[i];
+        __syncthreads();
+        return sm;
+    } else {
+        return nullptr;
+    }
+}
+
+template <int LIK, int METHOD, bool TAB>
+__global__ void __launch_bounds__(kSiteThreads)
+site_update_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
+                   const double* cw2, double* part1, double* part2) {
+    extern __shared__ double site_smem[];
+    const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
     double d1 = 0.0, d2 = 0.0;
-    if (n < a.N) site_update_step<LIK, METHOD>(a, n, d1, d2);
+    for (long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x; n < a.N; n += (long long)gridDim.x * kSiteThreads) {
+        double e1, e2;
+        site_update_step<LIK, METHOD, TAB>(a, sc, n, e1, e2);
+        d1 += e1;
+        d2 += e2;
+    }
     if (part1) {
         block_sum_store<kSiteThreads>(d1, part1);
         block_sum_store<kSiteThreads>(d2, part2);
     }
 }
 
-template <int LIK, int METHOD>
-__global__ void __launch_bounds__(kSiteThreads) expected_density_kernel(bn_site_args a, double* values, double* part) {
-    const long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x;
-    double v = 0.0;
-    if (n < a.N) {
-        v = expected_density_step<LIK, METHOD>(a, n);
+template <int LIK, int METHOD, bool TAB>
+__global__ void __launch_bounds__(kSiteThreads)
+expected_density_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
+                        const double* cw2, double* values, double* part) {
+    extern __shared__ double site_smem[];
+    const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
+    double acc = 0.0;
+    for (long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x; n < a.N; n += (long long)gridDim.x * kSiteThreads) {
+        double v = expected_density_step<LIK, METHOD, TAB>(a, sc, n);
         if (values) values[n] = v;
-        if (isnan(v)) v = 0.0;  // nansum
+        if (!isnan(v)) acc += v;  // nansum
     }
-    block_sum_store<kSiteThreads>(v, part);
+    block_sum_store<kSiteThreads>(acc, part);
 }
 
-template <int LIK, int METHOD>
+template <int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(kSiteThreads)
-likelihood_stats_kernel(bn_site_args a, double* val, double* d1, double* d2) {
-    const long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x;
-    if (n < a.N) likelihood_stats_step<LIK, METHOD>(a, n, val, d1, d2);
+likelihood_stats_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
+                        const double* cw2, double* val, double* d1, double* d2) {
+    extern __shared__ double site_smem[];
+    const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
+    for (long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x; n < a.N; n += (long long)gridDim.x * kSiteThreads)
+        likelihood_stats_step<LIK, METHOD, TAB>(a, sc, n, val, d1, d2);
 }
 
 template <int D>
@@ -70,12 +127,66 @@ static int check_site_args(const bn_site_args* a, bool need_y = true) {
     BN_REQUIRE(a->D == (het ? 2 : 1), "likelihood %d needs D = %d latents, got %d", a->likelihood, het ? 2 : 1, a->D);
     BN_REQUIRE(a->N == 0 || ((a->y || !need_y) && a->post_mean && a->post_cov), "null input array");
     bool closed = a->likelihood == BN_LIK_GAUSSIAN && (a->method == BN_METHOD_VI || a->method == BN_METHOD_EP);
-    if (a->method != BN_METHOD_NEWTON && !closed)
+    if (a->method != BN_METHOD_NEWTON && !closed) {
         BN_REQUIRE(a->Q > 0 && a->cub_x && a->cub_w, "cubature table missing");
+        if (!het) BN_REQUIRE(a->Q <= kMaxQ1, "at most %d cubature points are supported for a single latent, got %d", kMaxQ1, a->Q);
+    }
     if (a->likelihood == BN_LIK_GAUSSIAN) BN_REQUIRE(a->lik_param > 0.0, "Gaussian variance must be positive");
     if (a->method == BN_METHOD_EP) BN_REQUIRE(a->power > 0.0, "EP power must be positive");
     return 0;
 }
+
+// Everything a site launch needs: grid, the 1-D rule by value, the multi-latent rule staged into the
+// caller's workspace (after `partials` doubles), dynamic shared memory for the probit table.
+struct SitePlan {
+    unsigned grid;
+    Cub1 cub;
+    const double *cx2, *cw2;
+    double* partials;
+};
+
+static int plan_sites(const bn_site_args* a, size_t partial_doubles, void* workspace, size_t workspace_bytes,
+                      cudaStream_t st, SitePlan& p) {
+    long long g = (a->N + kSiteThreads - 1) / kSiteThreads;
+    p.grid = (unsigned)(g < kSiteMaxGrid ? g : kSiteMaxGrid);
+    p.cx2 = p.cw2 = nullptr;
+    p.partials = (double*)workspace;
+    const bool het = a->D == 2;
+    const bool has_cub = a->Q > 0 && a->cub_x && a->cub_w;
+    make_cub1(het ? 0 : a->Q, has_cub ? a->cub_x : nullptr, has_cub ? a->cub_w : nullptr, p.cub);
+    size_t need = partial_doubles * p.grid * sizeof(double);
+    if (het && has_cub) need += (size_t)3 * a->Q * sizeof(double);
+    BN_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), "workspace too small: need %zu bytes, got %zu", need,
+               workspace_bytes);
+    if (het && has_cub) {  // the 2-D rule (400 points by default) lives in device memory
+        double* t = (double*)workspace + partial_doubles * p.grid;
+        BN_CUDA(cudaMemcpyAsync(t, a->cub_x, (size_t)2 * a->Q * sizeof(double), cudaMemcpyHostToDevice, st));
+        BN_CUDA(cudaMemcpyAsync(t + 2 * a->Q, a->cub_w, (size_t)a->Q * sizeof(double), cudaMemcpyHostToDevice, st));
+        p.cx2 = t;
+        p.cw2 = t + 2 * a->Q;
+    }
+    return 0;
+}
+
+template <int LIK, int METHOD>
+static size_t table_smem(cudaStream_t st, int& rc) {
+    rc = 0;
+    if constexpr (!kUsesTable<LIK, METHOD>) return 0;
+    if (!probit_table_enabled()) return 0;
+    rc = ensure_probit_table(st);
+    return sizeof(double) * kPtDoubles;
+}
+
+// launch K<L, M, TAB> with TAB decided at run time (only the table-capable pairs instantiate both)
+#define BN_SITE_LAUNCH(K, L, M, smem, ...)                                                            \
+    do {                                                                                              \
+        if (smem) { /* smem != 0 implies kUsesTable<L, M> */                                          \
+            BN_CUDA(cudaFuncSetAttribute(K<L, M, kUsesTable<L, M>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            K<L, M, kUsesTable<L, M>><<<p.grid, kSiteThreads, smem, st>>>(__VA_ARGS__);               \
+        } else {                                                                                      \
+            K<L, M, false><<<p.grid, kSiteThreads, 0, st>>>(__VA_ARGS__);                             \
+        }                                                                                             \
+    } while (0)
 
 }  // namespace bn
 
@@ -86,21 +197,19 @@ extern "C" int bn_site_update(const bn_site_args* a, void* workspace, size_t wor
     BN_REQUIRE(a->nat1 && a->nat2, "nat1/nat2 must be given (they are updated in place)");
     if (a->N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned grid = (unsigned)((a->N + kSiteThreads - 1) / kSiteThreads);
-    double *p1 = nullptr, *p2 = nullptr;
-    if (a->diffs) {
-        BN_REQUIRE(workspace && workspace_bytes >= 2ull * grid * sizeof(double), "workspace too small for %u partials",
-                   grid);
-        p1 = (double*)workspace;
-        p2 = p1 + grid;
-    }
+    SitePlan p;
+    if (int rc = plan_sites(a, a->diffs ? 2 : 0, workspace, workspace_bytes, st, p)) return rc;
+    double *p1 = a->diffs ? p.partials : nullptr, *p2 = a->diffs ? p.partials + p.grid : nullptr;
 #define X(L, M)                                                                \
     if (a->likelihood == L && a->method == M) {                                \
-        BN_LAUNCH("site_update", st, (site_update_kernel<L, M><<<grid, kSiteThreads, 0, st>>>(*a, p1, p2))); \
+        int rc;                                                                \
+        size_t smem = table_smem<L, M>(st, rc);                                \
+        if (rc) return rc;                                                     \
+        BN_LAUNCH("site_update", st, BN_SITE_LAUNCH(site_update_kernel, L, M, smem, *a, p.cub, p.cx2, p.cw2, p1, p2)); \
         BN_CUDA(cudaGetLastError());                                           \
         if (a->diffs) {                                                        \
-            sum_kernel<false><<<1, 1024, 0, st>>>(p1, grid, a->diffs, 1.0 / ((double)a->N * a->D));            \
-            sum_kernel<false><<<1, 1024, 0, st>>>(p2, grid, a->diffs + 1, 1.0 / ((double)a->N * a->D * a->D)); \
+            sum_kernel<false><<<1, 1024, 0, st>>>(p1, p.grid, a->diffs, 1.0 / ((double)a->N * a->D));            \
+            sum_kernel<false><<<1, 1024, 0, st>>>(p2, p.grid, a->diffs + 1, 1.0 / ((double)a->N * a->D * a->D)); \
             BN_CUDA(cudaGetLastError());                                       \
         }                                                                      \
         return 0;                                                              \
@@ -119,15 +228,18 @@ extern "C" int bn_expected_density(const bn_site_args* a, double* values, double
         BN_REQUIRE(a->nat1 && a->nat2, "EP/PL energies need the site natural parameters for the cavity");
     cudaStream_t st = (cudaStream_t)stream;
     if (a->N == 0) { BN_CUDA(cudaMemsetAsync(sum, 0, sizeof(double), st)); return 0; }
-    unsigned grid = (unsigned)((a->N + kSiteThreads - 1) / kSiteThreads);
-    BN_REQUIRE(workspace && workspace_bytes >= (size_t)grid * sizeof(double), "workspace too small for %u partials", grid);
-    double* part = (double*)workspace;
+    SitePlan p;
+    if (int rc = plan_sites(a, 1, workspace, workspace_bytes, st, p)) return rc;
 #define X(L, M)                                                                        \
     if (a->likelihood == L && a->method == M) {                                        \
+        constexpr int ME = (M == BN_METHOD_PL) ? BN_METHOD_EP : M;                     \
+        int rc;                                                                        \
+        size_t smem = table_smem<L, ME>(st, rc);                                       \
+        if (rc) return rc;                                                             \
         BN_LAUNCH("expected_density", st,                                              \
-                  (expected_density_kernel<L, M><<<grid, kSiteThreads, 0, st>>>(*a, values, part))); \
+                  BN_SITE_LAUNCH(expected_density_kernel, L, M, smem, *a, p.cub, p.cx2, p.cw2, values, p.partials)); \
         BN_CUDA(cudaGetLastError());                                                   \
-        sum_kernel<false><<<1, 1024, 0, st>>>(part, grid, sum, 1.0);                   \
+        sum_kernel<false><<<1, 1024, 0, st>>>(p.partials, p.grid, sum, 1.0);           \
         BN_CUDA(cudaGetLastError());                                                   \
         return 0;                                                                      \
     }
@@ -137,14 +249,19 @@ extern "C" int bn_expected_density(const bn_site_args* a, double* values, double
     return -1;
 }
 
-extern "C" int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* d2, void* stream) {
+extern "C" int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* d2, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
     if (int rc = check_site_args(a, a && a->method != BN_METHOD_PL)) return rc;
     if (a->N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned grid = (unsigned)((a->N + kSiteThreads - 1) / kSiteThreads);
+    SitePlan p;
+    if (int rc = plan_sites(a, 0, workspace, workspace_bytes, st, p)) return rc;
 #define X(L, M)                                                                         \
     if (a->likelihood == L && a->method == M) {                                         \
-        likelihood_stats_kernel<L, M><<<grid, kSiteThreads, 0, st>>>(*a, val, d1, d2);  \
+        int rc;                                                                         \
+        size_t smem = table_smem<L, M>(st, rc);                                         \
+        if (rc) return rc;                                                              \
+        BN_SITE_LAUNCH(likelihood_stats_kernel, L, M, smem, *a, p.cub, p.cx2, p.cw2, val, d1, d2); \
         BN_CUDA(cudaGetLastError());                                                    \
         return 0;                                                                       \
     }

@@ -12,16 +12,37 @@
 #pragma once
 #include "common.cuh"
 #include "core.cuh"
+#include "probit_table.cuh"
 
 namespace bn {
 
 constexpr double kSqrt2 = 1.4142135623730951;
 constexpr double kInvSqrt2Pi = 0.3989422804014327;
 
+// one-dimensional cubature rule held by value (kernel parameter -> constant bank; the sums over
+// the points then take their weights as instruction operands).  wx = w x, wxx = w x^2.
+constexpr int kMaxQ1 = 64;
+struct Cub1 {
+    int Q;
+    int pad_;
+    double x[kMaxQ1], w[kMaxQ1], wx[kMaxQ1], wxx[kMaxQ1];
+    double xmax;  // max |x|
+};
+
+// what a site kernel needs besides bn_site_args: the 1-D rule by value, the probit table (shared
+// memory on the device, null = evaluate through erf/log), the multi-latent rule in device memory
+struct SiteCtx {
+    const Cub1* cub;
+    const double* tab;
+    const double* cx2;   // [2, Q]
+    const double* cw2;   // [Q]
+};
+
 // ------------------------------------------------------------------------------ single-latent likelihoods
-template <int LIK>
+template <int LIK, bool TAB = false>
 struct Lik1 {
-    double param;  // Gaussian variance
+    double param;       // Gaussian variance
+    const double* tab;  // TAB: probit log-density table (probit_table.cuh)
 
     BN_DEV double prob(double f) const {
         if constexpr (LIK == BN_LIK_BERNOULLI_LOGIT) return 1.0 / (1.0 + exp(-f));
@@ -32,6 +53,9 @@ struct Lik1 {
             double r = y - f;
             return -0.5 * log(2.0 * 3.141592653589793 * param) - 0.5 * r * r / param;
         } else {
+            if constexpr (LIK == BN_LIK_BERNOULLI_PROBIT) {
+                if constexpr (TAB) return probit_log_phi(tab, y == 1.0 ? f : -f);  // log(1 - p(f)) = log p(-f)
+            }
             double p = prob(f);
             return log(y == 1.0 ? p : 1.0 - p);
         }
@@ -116,9 +140,12 @@ struct SiteStats1 { double mean, jac, hess, val; };
 // Likelihood.variational_expectation / moment_match / log_likelihood_gradients /
 // statistical_linear_regression -- i.e. no cavity, no EP scale factor; PL returns (mu, dmu, omega)
 // in (val, jac, hess).
-template <int LIK, int METHOD, bool RAW = false>
-BN_DEV SiteStats1 site_stats_1(const Lik1<LIK>& lik, double y, double m, double v, double n1, double n2, double power,
-                               int Q, const double* cx, const double* cw) {
+template <int LIK, int METHOD, bool RAW = false, bool TAB = false>
+BN_DEV SiteStats1 site_stats_1(const Lik1<LIK, TAB>& lik, double y, double m, double v, double n1, double n2, double power,
+                               const Cub1& cub) {
+    const int Q = cub.Q;
+    const double* cx = cub.x;
+    const double* cw = cub.w;
     SiteStats1 o;
     const bool missing = isnan(y);
     double mean = m, cov = v;
@@ -147,29 +174,58 @@ BN_DEV SiteStats1 site_stats_1(const Lik1<LIK>& lik, double y, double m, double 
         double Lc = sqrt(lik.param);  // pep_constant, utils.py:431-445
         val += 0.5 * ((1.0 - power) * kLog2Pi - log(power)) + 0.5 * (1.0 - power) * 2.0 * log(fabs(Lc));
     } else if constexpr (METHOD == BN_METHOD_VI) {
-        double sd = sqrt(cov), iv = 1.0 / cov;
-        double E = 0.0, dE = 0.0, dV = 0.0;
-        for (int q = 0; q < Q; ++q) {
-            double f = sd * cx[q] + mean;
-            double wl = cw[q] * lik.log_lik(y, f);
-            double df = f - mean;
-            E += wl;
-            dE += iv * df * wl;
-            dV += (0.5 * (iv * iv * df * df) - 0.5 * iv) * wl;
+        // cubature.py:214-246 with f_i - m = sd x_i taken exactly:
+        //   E = sum w l,  dE/dm = (sum w x l) / sd,  d2E/dm2 = (sum w x^2 l - sum w l) / v
+        const double sd = sqrt(cov);
+        double E = 0.0, S1 = 0.0, S2 = 0.0;
+        bool done = false;
+        if constexpr (TAB && LIK == BN_LIK_BERNOULLI_PROBIT) {
+            // every point inside the table's range (the usual case): evaluate in table coordinates,
+            // log p(y | f) = g(+-f) with the sign folded into the affine map, no clamping per point
+            if (fabs(mean) + cub.xmax * sd <= kPtFmax) {
+                const double sg = (y == 1.0) ? kPtInvH : -kPtInvH;
+                const double a1 = sg * sd, a0 = fma(sg, mean, kPtFmax * kPtInvH);
+#pragma unroll 4
+                for (int q = 0; q < Q; ++q) {
+                    const double l = probit_log_phi_s(lik.tab, fma(a1, cx[q], a0));
+                    E = fma(cw[q], l, E);
+                    S1 = fma(cub.wx[q], l, S1);
+                    S2 = fma(cub.wxx[q], l, S2);
+                }
+                done = true;
+            }
         }
-        val = E; j = dE; h = 2.0 * dV;
+        if (!done) {
+#pragma unroll 2
+            for (int q = 0; q < Q; ++q) {
+                const double l = lik.log_lik(y, fma(sd, cx[q], mean));
+                E = fma(cw[q], l, E);
+                S1 = fma(cub.wx[q], l, S1);
+                S2 = fma(cub.wxx[q], l, S2);
+            }
+        }
+        const double poison = (mean - mean) + (sd - sd);  // NaN / inf inputs must come out as NaN
+        val = E + poison;
+        j = S1 / sd + poison;
+        h = (S2 - E) / cov + poison;
     } else if constexpr (METHOD == BN_METHOD_EP) {
-        double sd = sqrt(cov), ic = inv1(cov);
-        double Z = 0.0, dZ = 0.0, d2Z = 0.0;
+        // cubature.py:328-371 with f_i - m = sd x_i: Z = sum w p, dZ = C^-1 sd sum w x p,
+        // d2Z = C^-1 sd^2 C^-1 sum w x^2 p - C^-1 Z,  p_i = exp(power * log-lik_i)
+        const double sd = sqrt(cov), ic = inv1(cov);
+        double Z = 0.0, Z1 = 0.0, Z2 = 0.0;
+#pragma unroll 2
         for (int q = 0; q < Q; ++q) {
-            double f = sd * cx[q] + mean;
-            double wp = cw[q] * exp(power * lik.log_lik(y, f));
-            double df = f - mean;
-            Z += wp;
-            dZ += ic * df * wp;
-            d2Z += (ic * df * df * ic - ic) * wp;
+            const double p = exp(power * lik.log_lik(y, fma(sd, cx[q], mean)));
+            Z = fma(cw[q], p, Z);
+            Z1 = fma(cub.wx[q], p, Z1);
+            Z2 = fma(cub.wxx[q], p, Z2);
         }
+        const double poison = (mean - mean) + (sd - sd);
+        Z += poison;
+        const double dZ = ic * (sd * Z1);
+        const double d2Z = ic * (sd * sd) * ic * Z2 - ic * Z;
         double Zc = fmax(Z, 1e-8);
+        if (isnan(Z)) Zc = Z;  // fmax drops NaN; jnp.maximum propagates it
         val = log(Zc);
         double Zinv = 1.0 / Zc;
         j = Zinv * dZ;
@@ -323,14 +379,14 @@ BN_DEV SiteStats2 site_stats_2(double y, const double* m, const double* V, const
 
 // ------------------------------------------------------------------------------ the fused update, one step
 // returns |delta nat1| and |delta nat2| sums of this step through d1/d2
-template <int LIK, int METHOD>
-BN_DEV void site_update_step(const bn_site_args& a, long long n, double& d1, double& d2) {
+template <int LIK, int METHOD, bool TAB = false>
+BN_DEV void site_update_step(const bn_site_args& a, const SiteCtx& sc, long long n, double& d1, double& d2) {
     if constexpr (LIK == BN_LIK_HETEROSCEDASTIC_SOFTPLUS || LIK == BN_LIK_HETEROSCEDASTIC_EXP) {
         const double* m = a.post_mean + 2 * n;
         const double* V = a.post_cov + 4 * n;
         double o1[2] = {a.nat1[2 * n], a.nat1[2 * n + 1]};
         double o2[4] = {a.nat2[4 * n], a.nat2[4 * n + 1], a.nat2[4 * n + 2], a.nat2[4 * n + 3]};
-        SiteStats2 s = site_stats_2<LIK, METHOD>(a.y[n], m, V, o1, o2, a.power, a.Q, a.cub_x, a.cub_w);
+        SiteStats2 s = site_stats_2<LIK, METHOD>(a.y[n], m, V, o1, o2, a.power, a.Q, sc.cx2, sc.cw2);
         double H[4] = {s.hess[0], s.hess[1], s.hess[2], s.hess[3]};
         if (a.ensure_psd) {  // diagonal, negatives of -H replaced by 1e-2
             double k0 = -H[0], k1 = -H[3];
@@ -377,10 +433,9 @@ BN_DEV void site_update_step(const bn_site_args& a, long long n, double& d1, dou
             }
         }
     } else {
-        Lik1<LIK> lik{a.lik_param};
+        Lik1<LIK, TAB> lik{a.lik_param, sc.tab};
         double o1 = a.nat1[n], o2 = a.nat2[n];
-        SiteStats1 s = site_stats_1<LIK, METHOD>(lik, a.y[n], a.post_mean[n], a.post_cov[n], o1, o2, a.power, a.Q,
-                                                 a.cub_x, a.cub_w);
+        SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB>(lik, a.y[n], a.post_mean[n], a.post_cov[n], o1, o2, a.power, *sc.cub);
         double h = s.hess;
         if (a.ensure_psd && METHOD != BN_METHOD_PL) h = ensure_psd1(h);
         if (a.out_mean) a.out_mean[n] = s.mean;
@@ -402,8 +457,8 @@ BN_DEV void site_update_step(const bn_site_args& a, long long n, double& d1, dou
 }
 
 // value of the likelihood term of energy() at step n (NaN-safe: missing -> 0)
-template <int LIK, int METHOD>
-BN_DEV double expected_density_step(const bn_site_args& a, long long n) {
+template <int LIK, int METHOD, bool TAB = false>
+BN_DEV double expected_density_step(const bn_site_args& a, const SiteCtx& sc, long long n) {
     if constexpr (LIK == BN_LIK_HETEROSCEDASTIC_SOFTPLUS || LIK == BN_LIK_HETEROSCEDASTIC_EXP) {
         double o1[2] = {0.0, 0.0}, o2[4] = {0.0, 0.0, 0.0, 0.0};
         if (METHOD == BN_METHOD_EP) {
@@ -412,15 +467,15 @@ BN_DEV double expected_density_step(const bn_site_args& a, long long n) {
             for (int i = 0; i < 4; ++i) o2[i] = a.nat2[4 * n + i];
         }
         SiteStats2 s = site_stats_2<LIK, METHOD>(a.y[n], a.post_mean + 2 * n, a.post_cov + 4 * n, o1, o2, a.power,
-                                                 a.Q, a.cub_x, a.cub_w);
+                                                 a.Q, sc.cx2, sc.cw2);
         return s.val;
     } else {
-        Lik1<LIK> lik{a.lik_param};
+        Lik1<LIK, TAB> lik{a.lik_param, sc.tab};
         constexpr int M = (METHOD == BN_METHOD_PL) ? BN_METHOD_EP : METHOD;  // PL energy = EP energy at power 1
         double o1 = 0.0, o2 = 0.0;
         if (M == BN_METHOD_EP) { o1 = a.nat1[n]; o2 = a.nat2[n]; }
-        SiteStats1 s = site_stats_1<LIK, M>(lik, a.y[n], a.post_mean[n], a.post_cov[n], o1, o2,
-                                            METHOD == BN_METHOD_PL ? 1.0 : a.power, a.Q, a.cub_x, a.cub_w);
+        SiteStats1 s = site_stats_1<LIK, M, false, TAB>(lik, a.y[n], a.post_mean[n], a.post_cov[n], o1, o2,
+                                            METHOD == BN_METHOD_PL ? 1.0 : a.power, *sc.cub);
         return s.val;
     }
 }
@@ -523,12 +578,13 @@ BN_DEV double ep_pseudo_step(double power, int with_const, const double* py, con
 
 // likelihood-level statistics at (m, v) exactly as given (no cavity / scale factor / ensure_psd):
 // val[N], d1[N,D,1], d2[N,D,D]
-template <int LIK, int METHOD>
-BN_DEV void likelihood_stats_step(const bn_site_args& a, long long n, double* val, double* d1, double* d2) {
+template <int LIK, int METHOD, bool TAB = false>
+BN_DEV void likelihood_stats_step(const bn_site_args& a, const SiteCtx& sc, long long n, double* val, double* d1,
+                                  double* d2) {
     if constexpr (LIK == BN_LIK_HETEROSCEDASTIC_SOFTPLUS || LIK == BN_LIK_HETEROSCEDASTIC_EXP) {
         double z1[2] = {0.0, 0.0}, z2[4] = {0.0, 0.0, 0.0, 0.0};
         SiteStats2 s = site_stats_2<LIK, METHOD, true>(a.y[n], a.post_mean + 2 * n, a.post_cov + 4 * n, z1, z2,
-                                                       a.power, a.Q, a.cub_x, a.cub_w);
+                                                       a.power, a.Q, sc.cx2, sc.cw2);
         if (val) val[n] = s.val;
         if (d1) { d1[2 * n] = s.jac[0]; d1[2 * n + 1] = s.jac[1]; }
         if (d2) {
@@ -536,12 +592,27 @@ BN_DEV void likelihood_stats_step(const bn_site_args& a, long long n, double* va
             for (int i = 0; i < 4; ++i) d2[4 * n + i] = s.hess[i];
         }
     } else {
-        Lik1<LIK> lik{a.lik_param};
-        SiteStats1 s = site_stats_1<LIK, METHOD, true>(lik, a.y ? a.y[n] : 0.0, a.post_mean[n], a.post_cov[n], 0.0,
-                                                       0.0, a.power, a.Q, a.cub_x, a.cub_w);
+        Lik1<LIK, TAB> lik{a.lik_param, sc.tab};
+        SiteStats1 s = site_stats_1<LIK, METHOD, true, TAB>(lik, a.y ? a.y[n] : 0.0, a.post_mean[n], a.post_cov[n], 0.0,
+                                                       0.0, a.power, *sc.cub);
         if (val) val[n] = s.val;
         if (d1) d1[n] = s.jac;
         if (d2) d2[n] = s.hess;
+    }
+}
+
+// 1-D rule from host arrays (cubature.py:76-84 builds them with numpy on the host as well)
+inline void make_cub1(int Q, const double* x, const double* w, Cub1& c) {
+    c.Q = Q;
+    c.pad_ = 0;
+    c.xmax = 0.0;
+    for (int q = 0; q < kMaxQ1; ++q) {
+        const bool in = q < Q && x && w;
+        c.x[q] = in ? x[q] : 0.0;
+        c.w[q] = in ? w[q] : 0.0;
+        c.wx[q] = c.w[q] * c.x[q];
+        c.wxx[q] = c.w[q] * c.x[q] * c.x[q];
+        if (fabs(c.x[q]) > c.xmax) c.xmax = fabs(c.x[q]);
     }
 }
 

@@ -1,13 +1,13 @@
 """Cubature tables (host side).  Same construction as bayesnewton/cubature.py:56-84: Gauss-Hermite
 nodes from numpy's hermgauss, product grid with the first coordinate slowest, nodes scaled by
 sqrt(2) and weights by pi^(-dim/2).  The table is tiny (Q x (dim+1) doubles); it is built once on
-the host, cached on the device, and handed to the site kernels as x[dim,Q], w[Q]."""
+the host, cached, and handed to the site kernels as HOST arrays x[dim,Q], w[Q] (the library passes
+a 1-D rule to its kernels by value and stages a 2-D rule into the workspace)."""
 import itertools
 
 import numpy as np
 from numpy.polynomial.hermite import hermgauss
 
-from ._util import as_dev
 
 _cache = {}
 
@@ -29,14 +29,14 @@ class GaussHermite:
         return gauss_hermite(dim, self.num_cub_points)
 
 
-def device_table(cubature, dim):
-    """(x_dev [dim,Q], w_dev [Q], Q) for `cubature` (None = Gauss-Hermite 20, the reference default)"""
+def host_table(cubature, dim):
+    """(x [dim,Q], w [Q], Q) as contiguous float64 numpy arrays (None = Gauss-Hermite 20, the reference default)"""
     key = ('gh20', dim) if cubature is None else (id(cubature), dim)
     hit = _cache.get(key)
     if hit is None:
         x, w = gauss_hermite(dim) if cubature is None else cubature(dim)
-        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
-        w = np.asarray(w, dtype=np.float64).reshape(-1)
-        hit = (as_dev(x), as_dev(w), int(w.shape[0]))
+        x = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)))
+        w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
+        hit = (x, w, int(w.shape[0]))
         _cache[key] = hit
     return hit

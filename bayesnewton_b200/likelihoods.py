@@ -11,8 +11,8 @@ import math
 import torch
 
 from . import _lib
-from ._util import as_dev, ptr, stream_ptr
-from .cubature import device_table
+from ._util import as_dev, ptr, stream_ptr, workspace
+from .cubature import host_table
 
 
 def softplus(x):
@@ -42,8 +42,8 @@ class Likelihood:
         keep = [mean, cov]
         closed = self.lik_id == _lib.BN_LIK_GAUSSIAN and method in (_lib.BN_METHOD_VI, _lib.BN_METHOD_EP)
         if method != _lib.BN_METHOD_NEWTON and not closed:
-            cx, cw, Q = device_table(cubature, D)
-            a.Q, a.cub_x, a.cub_w = Q, cx.data_ptr(), cw.data_ptr()
+            cx, cw, Q = host_table(cubature, D)  # host arrays: the rule is a kernel parameter
+            a.Q, a.cub_x, a.cub_w = Q, cx.ctypes.data, cw.ctypes.data
             keep += [cx, cw]
         if y is not None:
             y = as_dev(y).reshape(-1)
@@ -61,7 +61,8 @@ class Likelihood:
         val = torch.empty((N,), dtype=torch.float64, device=dev)
         d1 = torch.empty((N, D, 1), dtype=torch.float64, device=dev)
         d2 = torch.empty((N, D, D), dtype=torch.float64, device=dev)
-        _lib.check(_lib.lib().bn_likelihood_stats(a, ptr(val), ptr(d1), ptr(d2), stream_ptr()))
+        ws, nb = workspace(N, D, D)
+        _lib.check(_lib.lib().bn_likelihood_stats(a, ptr(val), ptr(d1), ptr(d2), ptr(ws), nb, stream_ptr()))
         return val, d1, d2
 
     # ---- the reference's method names, batched over N -------------------------------------------------

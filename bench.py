@@ -33,11 +33,10 @@ UNIT = 'time-steps/s'
 # algorithmic bytes per time step of each kernel at d = 3, D = 1, fp64 (the
 # reference-interface layouts of SURVEY 8d: full matrices, no As/Qs arrays, no gains)
 ALGO_BYTES = {
-    'kf_reduce': 24,          # dt, y, R
-    'kf_apply': 24 + 96,      # dt, y, R in; m[3], P[3,3] out            (= F of SURVEY 8d, 121 with a mask)
-    'kf_apply_ell': 24,       # log-likelihood-only pass (L)
-    'rts_reduce': 8 + 96,     # dt', fm, fP
-    'rts_apply': 8 + 96 + 16,  # + H sm, H sP H^T out                     (= S)
+    'up_reduce': 24,          # dt, pseudo_y, pseudo_var
+    'up_filter': 24 + 96,     # dt, pseudo_y, pseudo_var in; m[3], P[3,3] out (kept packed, 72 B, in scratch)  (= F)
+    'up_smooth': 8 + 96 + 16,  # dt', fm, fP in; H sm, H sP H^T out                                             (= S)
+    'kf_reduce': 24, 'kf_apply': 24 + 96, 'kf_apply_ell': 24, 'rts_reduce': 8 + 96, 'rts_apply': 8 + 96 + 16,
     'site_update': 72,        # y, m, v, nat1, nat2 in; nat1, nat2, mean, cov out   (= U)
     'expected_density': 24,   # y, m, v                                   (= V)
     'gaussian_ell': 32,       # pseudo_y, m, v, pseudo_var                (= X)
@@ -60,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -283,7 +282,7 @@ def main_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--n-local', type=int, default=10_000_000, help='time steps per GPU (C2: 1e7)')

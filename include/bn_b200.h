@@ -23,7 +23,7 @@
  *   bn_gaussian_expected_log_lik   vmap(gaussian_expected_log_lik) utils.py:510-531, basemodels.py:715-721
  *
  * Conventions
- *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns
+ *   - every pointer is a DEVICE pointer unless the name ends in _host or its comment says HOST; the caller owns
  *     all buffers including outputs and the workspace; nothing is allocated, freed or
  *     retained; calls are asynchronous on `stream` (a cudaStream_t passed as void*).
  *   - arrays are contiguous row-major with the time axis leading, exactly as in the
@@ -186,8 +186,9 @@ typedef struct {
     int64_t N;
     int32_t D;             /* latent dim per step (1, or 2 for the heteroscedastic likelihood) */
     int32_t Q;             /* number of cubature points */
-    const double* cub_x;   /* [D,Q] sigma points of the unit Gaussian (cubature.py:76-84) */
-    const double* cub_w;   /* [Q] */
+    const double* cub_x;   /* HOST pointer: [D,Q] sigma points of the unit Gaussian (cubature.py:76-84) */
+    const double* cub_w;   /* HOST pointer: [Q] weights.  The rule is tiny and built on the host (numpy in the
+                              reference too); it travels as a kernel parameter.  D = 1: Q <= 64. */
     const double* y;       /* [N] observations; NaN = missing */
     const double* post_mean;  /* [N,D,1] */
     const double* post_cov;   /* [N,D,D] */
@@ -216,7 +217,8 @@ int bn_site_update(const bn_site_args* a, void* workspace, size_t workspace_byte
  *   Newton log_likelihood_gradients at f = post_mean  -> val = log p, d1 = J, d2 = H
  *   PL     statistical_linear_regression (y unused)   -> val = mu,  d1 = dmu/dm, d2 = omega
  * val[N], d1[N,D,1], d2[N,D,D]; each nullable.  nat1/nat2/lr/ensure_psd are ignored. */
-int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* d2, void* stream);
+int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* d2,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* per-step value of the likelihood term of energy(): VI E_q[log p], Newton log p(y|m),
  * EP/PL log Z at the cavity (computed in-kernel from post + nat).  values[N] nullable;

@@ -107,7 +107,7 @@ LIKS = {'gaussian': 1, 'probit': 2, 'logit': 3, 'het_softplus': 4, 'het_exp': 5}
 
 
 def site_update(lib, method, lik, lik_param, y, post_mean, post_cov, nat1, nat2, lr=1.0, power=1.0, ensure_psd=True,
-                cub=None):
+                cub=None, use_table=True):
     """returns dict with new nat1, nat2, site_mean, site_cov, mean, jac, hess, diffs"""
     N, D = post_mean.shape[0], post_mean.shape[1]
     keep = []
@@ -130,12 +130,13 @@ def site_update(lib, method, lik, lik_param, y, post_mean, post_cov, nat1, nat2,
     a.site_mean, a.site_cov = out['site_mean'].ctypes.data, out['site_cov'].ctypes.data
     a.out_mean, a.out_jac, a.out_hess = out['mean'].ctypes.data, out['jac'].ctypes.data, out['hess'].ctypes.data
     a.diffs = out['diffs'].ctypes.data
-    rc = lib.emu_site_update(C.byref(a))
+    rc = lib.emu_site_update(C.byref(a), int(use_table))
     assert rc == 0
     return out
 
 
-def expected_density(lib, method, lik, lik_param, y, post_mean, post_cov, nat1=None, nat2=None, power=1.0, cub=None):
+def expected_density(lib, method, lik, lik_param, y, post_mean, post_cov, nat1=None, nat2=None, power=1.0, cub=None,
+                     use_table=True):
     N, D = post_mean.shape[0], post_mean.shape[1]
     keep = []
 
@@ -155,6 +156,6 @@ def expected_density(lib, method, lik, lik_param, y, post_mean, post_cov, nat1=N
         n1, n2 = arr(nat1), arr(nat2)
         a.nat1, a.nat2 = n1.ctypes.data, n2.ctypes.data
     vals, s = np.zeros(N), np.zeros(1)
-    rc = lib.emu_expected_density(C.byref(a), _p(vals), _p(s))
+    rc = lib.emu_expected_density(C.byref(a), _p(vals), _p(s), int(use_table))
     assert rc == 0
     return vals, s[0]

@@ -254,13 +254,28 @@ extern "C" int emu_rts_arrays(int form, long long N, int L, int d, int Df, const
 }
 
 // ---------------------------------------------------------------------------- sites
-extern "C" int emu_site_update(const bn_site_args* a) {
+// host SiteCtx: 1-D rule by value, probit table on the host (use_table), multi-latent rule = the host arrays
+struct HostSite {
+    Cub1 cub;
+    SiteCtx sc;
+    HostSite(const bn_site_args* a, int use_table) {
+        const bool het = a->D == 2;
+        make_cub1(het ? 0 : a->Q, het ? nullptr : a->cub_x, het ? nullptr : a->cub_w, cub);
+        sc = SiteCtx{&cub, use_table ? probit_table_host().data() : nullptr, a->cub_x, a->cub_w};
+    }
+};
+
+extern "C" double emu_probit_log_phi(double f) { return probit_log_phi(probit_table_host().data(), f); }
+
+extern "C" int emu_site_update(const bn_site_args* a, int use_table) {
+    HostSite hs(a, use_table);
     double s1 = 0.0, s2 = 0.0;
 #define X(L, M)                                                   \
     if (a->likelihood == L && a->method == M) {                   \
         for (long long n = 0; n < a->N; ++n) {                    \
             double d1 = 0.0, d2 = 0.0;                            \
-            site_update_step<L, M>(*a, n, d1, d2);                \
+            if (use_table) site_update_step<L, M, true>(*a, hs.sc, n, d1, d2);     \
+            else site_update_step<L, M, false>(*a, hs.sc, n, d1, d2);                \
             s1 += d1;                                             \
             s2 += d2;                                             \
         }                                                         \
@@ -275,12 +290,14 @@ extern "C" int emu_site_update(const bn_site_args* a) {
     return -1;
 }
 
-extern "C" int emu_expected_density(const bn_site_args* a, double* values, double* sum) {
+extern "C" int emu_expected_density(const bn_site_args* a, double* values, double* sum, int use_table) {
+    HostSite hs(a, use_table);
     double s = 0.0;
 #define X(L, M)                                                   \
     if (a->likelihood == L && a->method == M) {                   \
         for (long long n = 0; n < a->N; ++n) {                    \
-            double v = expected_density_step<L, M>(*a, n);        \
+            double v = use_table ? expected_density_step<L, M, true>(*a, hs.sc, n)    \
+                                 : expected_density_step<L, M, false>(*a, hs.sc, n);        \
             if (values) values[n] = v;                            \
             if (!isnan(v)) s += v;                                \
         }                                                         \
