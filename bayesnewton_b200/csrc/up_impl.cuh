@@ -39,8 +39,7 @@ struct UpIO {
 inline ChunkPlan up_plan_chunks(long long N) {
     long long L = (N + kTargetChunks - 1) / kTargetChunks;
     L = (L + kUpTJ - 1) / kUpTJ * kUpTJ;
-    if (L < kUpTJ) L = kUpTJ;
-    if (L > 128) L = 128;
+    if (L < kUpTJ) L = kUpTJ;  // no upper bound: for large N the chunk count stays at one resident wave
     ChunkPlan p;
     p.L = (int)L;
     p.nchunks = (N + L - 1) / L;
@@ -94,9 +93,20 @@ struct DirectCtx {
 };
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void cp_async_8(double* dst_smem, const double* src) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(a), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPENDING) : "memory"); }
+
 // WarpCtx: the 32 chunks of a warp stage kUpTJ steps at a time through shared memory.  Global
 // accesses are row segments of kUpTJ * W consecutive doubles per chunk, read and written by
 // consecutive lanes; each lane then walks its own row (odd row pitch: no bank conflicts).
+// For D = 1 the input tiles are double-buffered and filled with cp.async (LDGSTS): the tile of
+// the next sub-block is in flight while the warp computes the current one, so the HBM latency
+// of the staging loads is off the critical path.
 template <int W>
 struct Tile {
     static constexpr int RW = kUpTJ * W;
@@ -108,6 +118,14 @@ struct Tile {
             const int r = i / RW, col = i - r * RW;
             const long long e0 = (cbase + r) * L + j0;
             sm[r * P + col] = (e0 + col / W < N) ? X[e0 * W + col] : 0.0;
+        }
+    }
+    __device__ void load_async(const double* X, long long N, long long cbase, int L, int j0, int lane) {
+#pragma unroll 4
+        for (int i = lane; i < 32 * RW; i += 32) {
+            const int r = i / RW, col = i - r * RW;
+            const long long e0 = (cbase + r) * L + j0;
+            if (e0 + col / W < N) cp_async_8(sm + r * P + col, X + e0 * W + col);
         }
     }
     __device__ void store(double* X, long long N, long long cbase, int L, int j0, int lane) const {
@@ -122,26 +140,74 @@ struct Tile {
 
 template <int D>
 struct WarpCtx {
-    UpIO io;
-    Tile<1> tdt;
-    Tile<D> ty;       // observations in, posterior means out (never live together)
-    Tile<D * D> tR;   // site covariances in, posterior covariances out
-    int lane;
-    static constexpr int kDoublesPerWarp = Tile<1>::kDoubles + Tile<D>::kDoubles + Tile<D * D>::kDoubles;
+    static constexpr bool kAsync = (D == 1);
+    static constexpr int kBuf = kAsync ? 2 : 1;
+    static constexpr int kInDoubles = Tile<1>::kDoubles + Tile<D>::kDoubles + Tile<D * D>::kDoubles;
+    static constexpr int kOutDoubles = Tile<D>::kDoubles + Tile<D * D>::kDoubles;
+    static constexpr int kSmootherDoubles = kBuf * Tile<1>::kDoubles + kOutDoubles;
+    static constexpr int kDoublesPerWarp = (kBuf * kInDoubles > kSmootherDoubles) ? kBuf * kInDoubles : kSmootherDoubles;
 
-    __device__ WarpCtx(const UpIO& io_, double* smem_warp) : io(io_) {
+    UpIO io;
+    double* base;
+    Tile<1> tdt;
+    Tile<D> ty;       // observations in (filter) / posterior means out (smoother)
+    Tile<D * D> tR;   // site covariances in / posterior covariances out
+    int lane, cur;
+    bool smoother, primed;
+
+    // filter layout: [buf0: dt | y | R][buf1: dt | y | R];  smoother layout: [dt buf0][dt buf1][out mean | out cov]
+    __device__ WarpCtx(const UpIO& io_, double* smem_warp, bool smoother_) : io(io_), base(smem_warp) {
         lane = threadIdx.x & 31;
-        tdt.sm = smem_warp;
-        ty.sm = tdt.sm + Tile<1>::kDoubles;
-        tR.sm = ty.sm + Tile<D>::kDoubles;
+        cur = 0;
+        smoother = smoother_;
+        primed = false;
+        point_in(0);
+        if (smoother) {
+            ty.sm = base + kBuf * Tile<1>::kDoubles;
+            tR.sm = ty.sm + Tile<D>::kDoubles;
+        }
     }
-    // cbase: first chunk of this warp
-    __device__ void begin(long long cbase, int L, int j0, bool want_obs) {
-        __syncwarp();
-        tdt.load(io.dt, io.N, cbase, L, j0, lane);
-        if (want_obs) {
-            ty.load(io.y, io.N, cbase, L, j0, lane);
-            tR.load(io.R, io.N, cbase, L, j0, lane);
+    __device__ void point_in(int b) {
+        if (smoother) {
+            tdt.sm = base + b * Tile<1>::kDoubles;
+        } else {
+            tdt.sm = base + b * kInDoubles;
+            ty.sm = tdt.sm + Tile<1>::kDoubles;
+            tR.sm = ty.sm + Tile<D>::kDoubles;
+        }
+    }
+    __device__ void issue(int b, long long cbase, int L, int j0) {
+        point_in(b);
+        tdt.load_async(io.dt, io.N, cbase, L, j0, lane);
+        if (!smoother) {
+            ty.load_async(io.y, io.N, cbase, L, j0, lane);
+            tR.load_async(io.R, io.N, cbase, L, j0, lane);
+        }
+        cp_async_commit();
+    }
+    // cbase: first chunk of this warp; dir: +1 when the sub-blocks are walked forward, -1 backward
+    __device__ void begin(long long cbase, int L, int j0, int dir) {
+        __syncwarp();  // every lane is done with the tile that is about to be overwritten
+        if constexpr (kAsync) {
+            if (!primed) {
+                issue(cur, cbase, L, j0);
+                primed = true;
+            }
+            const int jn = j0 + dir * kUpTJ;
+            if (jn >= 0 && jn < L && cbase * L + jn < io.N) {
+                issue(cur ^ 1, cbase, L, jn);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            point_in(cur);
+            cur ^= 1;
+        } else {
+            tdt.load(io.dt, io.N, cbase, L, j0, lane);
+            if (!smoother) {
+                ty.load(io.y, io.N, cbase, L, j0, lane);
+                tR.load(io.R, io.N, cbase, L, j0, lane);
+            }
         }
         __syncwarp();
     }
@@ -167,11 +233,11 @@ struct WarpCtx {
 #endif
 
 // DirectCtx spelling of the block hooks used by the shared chunk bodies
-template <int D> BN_DEV void ctx_begin(DirectCtx<D>&, long long, int, int, bool) {}
+template <int D> BN_DEV void ctx_begin(DirectCtx<D>&, long long, int, int, int) {}
 template <int D> BN_DEV void ctx_end(DirectCtx<D>&, long long, int, int) {}
 #ifdef __CUDACC__
-template <int D> __device__ __forceinline__ void ctx_begin(WarpCtx<D>& cx, long long cbase, int L, int j0, bool obs) {
-    cx.begin(cbase, L, j0, obs);
+template <int D> __device__ __forceinline__ void ctx_begin(WarpCtx<D>& cx, long long cbase, int L, int j0, int dir) {
+    cx.begin(cbase, L, j0, dir);
 }
 template <int D> __device__ __forceinline__ void ctx_end(WarpCtx<D>& cx, long long cbase, int L, int j0) {
     cx.end(cbase, L, j0);
@@ -192,7 +258,7 @@ BN_DEV void up_reduce_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     const long long k0 = c * L, cbase = c & ~31LL;
     for (int j0 = 0; j0 < L; j0 += kUpTJ) {
         if (cbase * L + j0 >= N) break;  // warp-uniform: nothing left for any lane
-        ctx_begin(cx, cbase, L, j0, true);
+        ctx_begin(cx, cbase, L, j0, 1);
 #pragma unroll 1
         for (int jj = 0; jj < kUpTJ; ++jj) {
             const long long k = k0 + j0 + jj;
@@ -233,7 +299,7 @@ BN_DEV void up_filter_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     const long long k0 = c * L, cbase = c & ~31LL;
     for (int j0 = 0; j0 < L; j0 += kUpTJ) {
         if (cbase * L + j0 >= N) break;
-        ctx_begin(cx, cbase, L, j0, true);
+        ctx_begin(cx, cbase, L, j0, 1);
 #pragma unroll 1
         for (int jj = 0; jj < kUpTJ; ++jj) {
             const long long k = k0 + j0 + jj;
@@ -308,9 +374,11 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     const long long kend = ((c + 1) * L < N) ? (c + 1) * L : N;
     const int j_last = (int)(kend - k0) - 1;  // s is the smoothed state of this step
     double h_up = 0.0;                        // dt of the step above the current one
+    double nfm[d], nfP[symn(d)];              // filtered state of the next step to process, loaded one step ahead
+    if (active && j_last >= 1) fs_load<d>(fs, c, L, j_last - 1, nfm, nfP);
     for (int j0 = L - kUpTJ; j0 >= 0; j0 -= kUpTJ) {
         if (cbase * L + j0 >= N) continue;
-        ctx_begin(cx, cbase, L, j0, false);
+        ctx_begin(cx, cbase, L, j0, -1);
 #pragma unroll 1
         for (int jj = kUpTJ - 1; jj >= 0; --jj) {
             const int j = j0 + jj;
@@ -319,7 +387,11 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
                 const double h_k = cx.dt(k, jj);
                 if (j < j_last) {
                     double fm[d], fP[symn(d)], Ab[G::kBlockA], Qb[G::kBlockS];
-                    fs_load<d>(fs, c, L, j, fm, fP);
+#pragma unroll
+                    for (int i = 0; i < d; ++i) fm[i] = nfm[i];
+#pragma unroll
+                    for (int i = 0; i < symn(d); ++i) fP[i] = nfP[i];
+                    if (j >= 1) fs_load<d>(fs, c, L, j - 1, nfm, nfP);  // in flight during this step's arithmetic
                     g.trans(h_up, Ab);
                     g.noise(Ab, Qb);
                     frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
@@ -371,20 +443,20 @@ BN_DEV void up_export_scarry(const double* top_prefix, long long n_top, int is_l
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------ kernels
 template <class G>
-__global__ void __launch_bounds__(kUpThreads)
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? 4 : 1))
 up_reduce_kernel(G g, UpIO io, int L, long long nchunks, int is_first, double* agg) {
     extern __shared__ double up_smem[];
-    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp);
+    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, false);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     up_reduce_chunk(g, cx, io.N, L, nchunks, is_first, agg, c, c < nchunks);
 }
 
 template <class G, bool WANT_ELL>
-__global__ void __launch_bounds__(kUpThreads)
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? 4 : 1))
 up_filter_kernel(G g, UpIO io, int L, long long nchunks, int is_first, const double* prefix, const double* s0,
                  double* fs, double* ell_partials) {
     extern __shared__ double up_smem[];
-    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp);
+    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, false);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     up_filter_chunk<G, WANT_ELL>(g, cx, io.N, L, nchunks, is_first, prefix, s0, fs, ell_partials, c, c < nchunks);
 }
@@ -398,11 +470,11 @@ up_selem_kernel(long long N, int L, long long nchunks, int need_first, const dou
 }
 
 template <class G>
-__global__ void __launch_bounds__(kUpThreads)
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? 4 : 1))
 up_smooth_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, const double* sinit,
                  const double* fs) {
     extern __shared__ double up_smem[];
-    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp);
+    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, true);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     up_smooth_chunk(g, cx, io.N, L, nchunks, sprefix, sinit, fs, c, c < nchunks);
 }
