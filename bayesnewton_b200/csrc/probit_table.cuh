@@ -4,41 +4,48 @@
 //
 // The cubature sites evaluate it 20 times per time step; through erf() + log() that is ~100 fp64
 // instructions per point and makes the site kernels the most expensive part of an iteration.  Here
-// g is tabulated once per process as piecewise degree-6 polynomials on 577 intervals of width 1/32
-// centred on the grid -9 + i/32 (Chebyshev interpolation in long double, max abs error 2.6e-15 =
-// 3 ulp of |g| <= 6.9, measured by tests/test_probit_table.py); outside [-9, 9] g is constant to
-// fp64.  One evaluation = 4 fp64 ops of index arithmetic + 6 DFMA + 7 shared-memory loads.
-// The nearest singularities of g (zeros of eps + (1-2eps) Phi) sit ~0.95 from the real axis near
-// f = -3.2, which is what forces the narrow intervals; the error bound is measured, not assumed.
+// g is tabulated once per process as piecewise degree-4 polynomials on 4609 intervals of width
+// 1/256 centred on the grid -9 + i/256 (Chebyshev interpolation in long double); outside [-9, 9]
+// g is constant to fp64.  The nearest singularities of g (zeros of eps + (1-2eps) Phi) sit ~0.95
+// from the real axis near f = -3.2, which is what forces the narrow intervals.
+//
+// The table lives in shared memory and is gathered with a different index per lane, so the cost of
+// an evaluation is the number of shared-memory wavefronts, i.e. the number of 8-byte words per
+// interval: c0, c1, c2 are doubles, the two highest coefficients are floats packed in one word
+// (|c3 u^3| <= 1e-8: float rounding there is below 1e-15) and are combined on the fp32 pipe.
+// One evaluation = 4 words, 4 fp64 ops of index arithmetic + 3 DFMA + 1 FFMA + 2 conversions.
+// Max abs error 4e-15 (measured by tests/test_probit_table.py against long double).
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include "smallmat.cuh"
 
 namespace bn {
 
-constexpr int kPtDeg = 6;
-constexpr int kPtN = 577;            // interval centres -9 + i/32, i = 0..576
+constexpr int kPtDeg = 4;
+constexpr int kPtN = 4609;           // interval centres -9 + i/256, i = 0..4608
 constexpr double kPtFmax = 9.0;
-constexpr double kPtInvH = 32.0;
-constexpr int kPtDoubles = (kPtDeg + 1) * kPtN;   // coefficient-major: tab[k * kPtN + i]
+constexpr double kPtInvH = 256.0;
+constexpr int kPtDoubles = 4 * kPtN;   // word-major: c0[kPtN] | c1[kPtN] | c2[kPtN] | {float c3, float c4}[kPtN]
 
-// g at table coordinate s = 32 f + 288, which must lie in [0, 576]
+// g at table coordinate s = 256 f + 2304, which must lie in [0, 4608]
 BN_DEV double probit_log_phi_s(const double* tab, double s) {
 #ifdef __CUDA_ARCH__
     const double r = s + 6755399441055744.0;               // 1.5 * 2^52: round-to-nearest-integer trick
     const int i = __double2loint(r);
     const double u = s - (r - 6755399441055744.0);         // in [-0.5, 0.5]
+    const float2 c34 = reinterpret_cast<const float2*>(tab + 3 * kPtN)[i];
+    const float t = fmaf(c34.y, (float)u, c34.x);
 #else
     const double sr = nearbyint(s);
     const int i = (int)sr;
     const double u = s - sr;
+    float c34[2];
+    memcpy(c34, tab + 3 * kPtN + i, sizeof(c34));
+    const float t = fmaf(c34[1], (float)u, c34[0]);
 #endif
-    const double* c = tab + i;
-    double p = c[kPtDeg * kPtN];
-#pragma unroll
-    for (int k = kPtDeg - 1; k >= 0; --k) p = fma(p, u, c[k * kPtN]);
-    return p;
+    return fma(fma(fma((double)t, u, tab[2 * kPtN + i]), u, tab[kPtN + i]), u, tab[i]);
 }
 
 // tab -> g(f) for any f.  NaN inputs come back as a finite number (fmin/fmax drop NaN): callers poison.
@@ -86,11 +93,17 @@ inline const std::vector<double>& probit_table_host() {
                 for (int j = 0; j < M; ++j) mono[j] += ck[k] * T[j];
             }
             // v = 2u: coefficient of u^k is mono[k] * 2^k
+            double cf[M];
             long double sc = 1;
             for (int k = 0; k < M; ++k) {
-                t[(size_t)k * kPtN + i] = (double)(mono[k] * sc);
+                cf[k] = (double)(mono[k] * sc);
                 sc *= 2;
             }
+            t[i] = cf[0];
+            t[(size_t)kPtN + i] = cf[1];
+            t[(size_t)2 * kPtN + i] = cf[2];
+            const float hi[2] = {(float)cf[3], (float)cf[4]};
+            memcpy(&t[(size_t)3 * kPtN + i], hi, sizeof(hi));
         }
         return t;
     }();

@@ -8,6 +8,11 @@ namespace bn {
 
 constexpr int kSiteThreads = 256;
 constexpr int kSiteMaxGrid = 148 * 6;  // persistent grid: 6 CTAs per SM, grid-stride over the time steps
+// kernels that gather from the probit table keep all of it (147.5 KB) in shared memory: one CTA of
+// 1024 threads per SM
+constexpr int kTabThreads = 1024;
+constexpr int kTabGrid = 148;
+template <bool TAB> constexpr int kNT = TAB ? kTabThreads : kSiteThreads;
 
 // the probit log-density table in device memory, filled once per device (probit_table.cuh)
 __device__ double g_probit_tab[kPtDoubles];
@@ -42,7 +47,7 @@ static bool probit_table_enabled() {
 template <bool TAB>
 __device__ __forceinline__ const double* stage_table(double* sm) {
     if constexpr (TAB) {
-        for (int i = threadIdx.x; i < kPtDoubles; i += kSiteThreads) sm[i] = g_probit_tab[i];
+        for (int i = threadIdx.x; i < kPtDoubles; i += kTabThreads) sm[i] = g_probit_tab[i];
         __syncthreads();
         return sm;
     } else {
@@ -51,46 +56,46 @@ __device__ __forceinline__ const double* stage_table(double* sm) {
 }
 
 template <int LIK, int METHOD, bool TAB>
-__global__ void __launch_bounds__(kSiteThreads)
+__global__ void __launch_bounds__(kNT<TAB>)
 site_update_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
                    const double* cw2, double* part1, double* part2) {
     extern __shared__ double site_smem[];
     const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
     double d1 = 0.0, d2 = 0.0;
-    for (long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x; n < a.N; n += (long long)gridDim.x * kSiteThreads) {
+    for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>) {
         double e1, e2;
         site_update_step<LIK, METHOD, TAB>(a, sc, n, e1, e2);
         d1 += e1;
         d2 += e2;
     }
     if (part1) {
-        block_sum_store<kSiteThreads>(d1, part1);
-        block_sum_store<kSiteThreads>(d2, part2);
+        block_sum_store<kNT<TAB>>(d1, part1);
+        block_sum_store<kNT<TAB>>(d2, part2);
     }
 }
 
 template <int LIK, int METHOD, bool TAB>
-__global__ void __launch_bounds__(kSiteThreads)
+__global__ void __launch_bounds__(kNT<TAB>)
 expected_density_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
                         const double* cw2, double* values, double* part) {
     extern __shared__ double site_smem[];
     const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
     double acc = 0.0;
-    for (long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x; n < a.N; n += (long long)gridDim.x * kSiteThreads) {
+    for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>) {
         double v = expected_density_step<LIK, METHOD, TAB>(a, sc, n);
         if (values) values[n] = v;
         if (!isnan(v)) acc += v;  // nansum
     }
-    block_sum_store<kSiteThreads>(acc, part);
+    block_sum_store<kNT<TAB>>(acc, part);
 }
 
 template <int LIK, int METHOD, bool TAB>
-__global__ void __launch_bounds__(kSiteThreads)
+__global__ void __launch_bounds__(kNT<TAB>)
 likelihood_stats_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
                         const double* cw2, double* val, double* d1, double* d2) {
     extern __shared__ double site_smem[];
     const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
-    for (long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x; n < a.N; n += (long long)gridDim.x * kSiteThreads)
+    for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>)
         likelihood_stats_step<LIK, METHOD, TAB>(a, sc, n, val, d1, d2);
 }
 
@@ -149,6 +154,12 @@ static int plan_sites(const bn_site_args* a, size_t partial_doubles, void* works
                       cudaStream_t st, SitePlan& p) {
     long long g = (a->N + kSiteThreads - 1) / kSiteThreads;
     p.grid = (unsigned)(g < kSiteMaxGrid ? g : kSiteMaxGrid);
+    const bool tab = probit_table_enabled() && a->likelihood == BN_LIK_BERNOULLI_PROBIT &&
+                     (a->method == BN_METHOD_VI || a->method == BN_METHOD_EP || a->method == BN_METHOD_PL);
+    if (tab) {
+        g = (a->N + kTabThreads - 1) / kTabThreads;
+        p.grid = (unsigned)(g < kTabGrid ? g : kTabGrid);
+    }
     p.cx2 = p.cw2 = nullptr;
     p.partials = (double*)workspace;
     const bool het = a->D == 2;
@@ -182,7 +193,7 @@ static size_t table_smem(cudaStream_t st, int& rc) {
     do {                                                                                              \
         if (smem) { /* smem != 0 implies kUsesTable<L, M> */                                          \
             BN_CUDA(cudaFuncSetAttribute(K<L, M, kUsesTable<L, M>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            K<L, M, kUsesTable<L, M>><<<p.grid, kSiteThreads, smem, st>>>(__VA_ARGS__);               \
+            K<L, M, kUsesTable<L, M>><<<p.grid, kNT<kUsesTable<L, M>>, smem, st>>>(__VA_ARGS__);      \
         } else {                                                                                      \
             K<L, M, false><<<p.grid, kSiteThreads, 0, st>>>(__VA_ARGS__);                             \
         }                                                                                             \

@@ -77,7 +77,7 @@ BN_DEV void fs_load(const double* fs, long long c, int L, int j, double* m, doub
 template <int D>
 struct DirectCtx {
     UpIO io;
-    BN_DEV double dt(long long k, int) const { return io.dt[k]; }
+    BN_DEV double dt(long long k, int) const { return k < io.N ? io.dt[k] : 0.0; }
     BN_DEV void obs(long long k, int, double* y, double* R) const {
 #pragma unroll
         for (int i = 0; i < D; ++i) y[i] = io.y[k * D + i];
@@ -259,13 +259,19 @@ BN_DEV void up_reduce_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     for (int j0 = 0; j0 < L; j0 += kUpTJ) {
         if (cbase * L + j0 >= N) break;  // warp-uniform: nothing left for any lane
         ctx_begin(cx, cbase, L, j0, 1);
+        // the transition of step k+1 does not depend on the recursion: it is formed while step k runs,
+        // so its exp() chain fills the dependency stalls of the update (slot kUpTJ of a tile row is padding)
+        double Abn[G::kBlockA];
+        g.trans(cx.dt(k0 + j0, 0), Abn);
 #pragma unroll 1
         for (int jj = 0; jj < kUpTJ; ++jj) {
             const long long k = k0 + j0 + jj;
             if (active && k < N) {
                 double y[D], R[D * D], Ab[G::kBlockA];
                 cx.obs(k, jj, y, R);
-                g.trans(cx.dt(k, jj), Ab);
+#pragma unroll
+                for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
+                g.trans(cx.dt(k + 1, jj + 1), Abn);
                 fkf_absorb<G>(g, el, Ab, y, R, is_first && k == 0);
             }
         }
@@ -300,6 +306,8 @@ BN_DEV void up_filter_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     for (int j0 = 0; j0 < L; j0 += kUpTJ) {
         if (cbase * L + j0 >= N) break;
         ctx_begin(cx, cbase, L, j0, 1);
+        double Abn[G::kBlockA];  // transition of the next step, formed one step ahead (see up_reduce_chunk)
+        g.trans(cx.dt(k0 + j0, 0), Abn);
 #pragma unroll 1
         for (int jj = 0; jj < kUpTJ; ++jj) {
             const long long k = k0 + j0 + jj;
@@ -311,7 +319,9 @@ BN_DEV void up_filter_chunk(const G& g, Ctx& cx, long long N, int L, long long n
 #pragma unroll
                     for (int i = 0; i < D; ++i) mk[i] = cx.io.mask[k * D + i];
                 }
-                g.trans(cx.dt(k, jj), Ab);
+#pragma unroll
+                for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
+                g.trans(cx.dt(k + 1, jj + 1), Abn);
                 ell += fkf_step<G, WANT_ELL>(g, s.m, s.P, Ab, y, R, cx.io.mask ? mk : nullptr, mp, Pp);
                 fs_store<d>(fs, c, L, j0 + jj, s.m, s.P);
             }
@@ -373,8 +383,12 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     const long long k0 = c * L, cbase = c & ~31LL;
     const long long kend = ((c + 1) * L < N) ? (c + 1) * L : N;
     const int j_last = (int)(kend - k0) - 1;  // s is the smoothed state of this step
-    double h_up = 0.0;                        // dt of the step above the current one
     double nfm[d], nfP[symn(d)];              // filtered state of the next step to process, loaded one step ahead
+    double Abn[G::kBlockA], Qbn[G::kBlockS];  // discretisation of the next step to process, formed one step ahead
+#pragma unroll
+    for (int i = 0; i < G::kBlockA; ++i) Abn[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < G::kBlockS; ++i) Qbn[i] = 0.0;
     if (active && j_last >= 1) fs_load<d>(fs, c, L, j_last - 1, nfm, nfP);
     for (int j0 = L - kUpTJ; j0 >= 0; j0 -= kUpTJ) {
         if (cbase * L + j0 >= N) continue;
@@ -385,15 +399,22 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
             const long long k = k0 + j;
             if (active && j <= j_last) {
                 const double h_k = cx.dt(k, jj);
+                double Ab[G::kBlockA], Qb[G::kBlockS];
+#pragma unroll
+                for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
+#pragma unroll
+                for (int i = 0; i < G::kBlockS; ++i) Qb[i] = Qbn[i];
+                // the discretisation of the step below (k-1 -> k, length h_k) is formed while this step's
+                // dependent chain runs
+                g.trans(h_k, Abn);
+                g.noise(Abn, Qbn);
                 if (j < j_last) {
-                    double fm[d], fP[symn(d)], Ab[G::kBlockA], Qb[G::kBlockS];
+                    double fm[d], fP[symn(d)];
 #pragma unroll
                     for (int i = 0; i < d; ++i) fm[i] = nfm[i];
 #pragma unroll
                     for (int i = 0; i < symn(d); ++i) fP[i] = nfP[i];
                     if (j >= 1) fs_load<d>(fs, c, L, j - 1, nfm, nfP);  // in flight during this step's arithmetic
-                    g.trans(h_up, Ab);
-                    g.noise(Ab, Qb);
                     frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
                 }
                 double pm[D], pc[D * D];
@@ -404,7 +425,6 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
                     for (int b = 0; b < D; ++b) pc[a * D + b] = s.P[sidx(G::sel(a), G::sel(b))];
                 }
                 cx.put(k, jj, pm, pc);
-                h_up = h_k;
             }
         }
         ctx_end(cx, cbase, L, j0);
