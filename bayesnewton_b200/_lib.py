@@ -10,7 +10,7 @@ import os
 import torch  # noqa: F401  (loads libcudart before our library resolves it)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libbn_b200.so')
+LIB_PATH = os.path.join(HERE, os.environ.get('BN_B200_LIBNAME', 'libbn_b200.so'))  # tuning variants: build.py
 
 BN_SEQUENTIAL, BN_SCAN = 0, 1
 BN_MATERN12, BN_MATERN32, BN_MATERN52, BN_MATERN72 = 1, 2, 3, 4
@@ -48,6 +48,7 @@ SIGNATURES = {
     'bn_version': (_I, []),
     'bn_timing_enable': (_I, [_I]),
     'bn_timing_report': (_I, [C.c_char_p, _Z]),
+    'bn_measure_dfma_peak': (_I, [_P, _Z, C.POINTER(C.c_double)]),
     'bn_state_dim': (_I, [_KS]),
     'bn_discretise': (_I, [_KS, _L, _P, _P, _P, _P]),
     'bn_workspace_bytes': (_Z, [_L, _I, _I]),

@@ -13,8 +13,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 ROOT = os.path.dirname(HERE)
-OBJ_DIR = os.path.join(ROOT, 'build', 'obj')
-LIB = os.path.join(HERE, 'libbn_b200.so')
+OBJ_DIR = os.path.join(ROOT, 'build', 'obj' + os.environ.get('BN_B200_OBJ_SUFFIX', ''))
+LIB = os.path.join(HERE, os.environ.get('BN_B200_LIBNAME', 'libbn_b200.so'))
+EXTRA = os.environ.get('BN_B200_NVCC_EXTRA', '').split()  # e.g. -DBN_UP_TJ=4 -DBN_UP_BLOCKS=6 for tuning variants
 
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -28,7 +29,7 @@ def _newest_header():
 
 
 def _compile(src, obj, verbose):
-    cmd = [NVCC] + NVCC_FLAGS + ['-c', src, '-o', obj]
+    cmd = [NVCC] + NVCC_FLAGS + EXTRA + ['-c', src, '-o', obj]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -97,6 +97,44 @@ extern "C" int bn_timing_report(char* buf, size_t len) {
     return (int)out.size() + 1;
 }
 
+// fp64 FMA rate of the current device: 8 independent DFMA chains per thread at full occupancy (measurement
+// aid for bench.py's fp64 roofline; ~3 ms).  Synchronises the device.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    if (out) out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int bn_measure_dfma_peak(double* scratch, size_t scratch_doubles, double* dfma_per_s_host) {
+    BN_REQUIRE(dfma_per_s_host != nullptr, "output is null");
+    int dev = 0, sms = 0;
+    BN_CUDA(cudaGetDevice(&dev));
+    BN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256, iters = 20000;
+    BN_REQUIRE(scratch && scratch_doubles >= (size_t)blocks * threads, "scratch of %d doubles needed", blocks * threads);
+    cudaEvent_t e0, e1;
+    BN_CUDA(cudaEventCreate(&e0));
+    BN_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        BN_CUDA(cudaEventRecord(e0, 0));
+        dfma_peak_kernel<<<blocks, threads>>>(scratch, iters, 0.999999, 1e-6);
+        BN_CUDA(cudaEventRecord(e1, 0));
+        BN_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        BN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double r = (double)blocks * threads * iters * 8 / (ms * 1e-3);
+        if (r > best) best = r;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *dfma_per_s_host = best;
+    return 0;
+}
+
 extern "C" int bn_state_dim(const bn_kernel_spec* k) {
     if (!k || k->n_components < 1 || k->n_components > BN_MAX_COMPONENTS) return -1;
     int n = family_dim(k->family);

@@ -22,9 +22,17 @@
 
 namespace bn {
 
-constexpr int kUpTJ = 8;       // steps per staged sub-block
-constexpr int kUpWarps = 4;    // warps per CTA
+#ifndef BN_UP_TJ
+#define BN_UP_TJ 8
+#endif
+#ifndef BN_UP_BLOCKS
+#define BN_UP_BLOCKS 4
+#endif
+constexpr int kUpTJ = BN_UP_TJ;          // steps per staged sub-block
+constexpr int kUpWarps = 4;              // warps per CTA
 constexpr int kUpThreads = 32 * kUpWarps;
+constexpr int kUpBlocksPerSM = BN_UP_BLOCKS;  // resident CTAs per SM the single-latent kernels are compiled for
+constexpr long long kUpTargetChunks = 148LL * kUpBlocksPerSM * kUpThreads;  // one resident wave
 
 struct UpIO {
     long long N;
@@ -37,7 +45,7 @@ struct UpIO {
 };
 
 inline ChunkPlan up_plan_chunks(long long N) {
-    long long L = (N + kTargetChunks - 1) / kTargetChunks;
+    long long L = (N + kUpTargetChunks - 1) / kUpTargetChunks;
     L = (L + kUpTJ - 1) / kUpTJ * kUpTJ;
     if (L < kUpTJ) L = kUpTJ;  // no upper bound: for large N the chunk count stays at one resident wave
     ChunkPlan p;
@@ -463,7 +471,7 @@ BN_DEV void up_export_scarry(const double* top_prefix, long long n_top, int is_l
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------ kernels
 template <class G>
-__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? 4 : 1))
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
 up_reduce_kernel(G g, UpIO io, int L, long long nchunks, int is_first, double* agg) {
     extern __shared__ double up_smem[];
     WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, false);
@@ -472,7 +480,7 @@ up_reduce_kernel(G g, UpIO io, int L, long long nchunks, int is_first, double* a
 }
 
 template <class G, bool WANT_ELL>
-__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? 4 : 1))
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
 up_filter_kernel(G g, UpIO io, int L, long long nchunks, int is_first, const double* prefix, const double* s0,
                  double* fs, double* ell_partials) {
     extern __shared__ double up_smem[];
@@ -490,7 +498,7 @@ up_selem_kernel(long long N, int L, long long nchunks, int need_first, const dou
 }
 
 template <class G>
-__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? 4 : 1))
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
 up_smooth_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, const double* sinit,
                  const double* fs) {
     extern __shared__ double up_smem[];

@@ -114,9 +114,10 @@ class TimeShard:
 def _all_gather(carry, world):
     """carries[world, len] over the default process group (NCCL on GPUs, gloo in the CPU tests)"""
     import torch.distributed as dist
-    out = torch.empty((world,) + tuple(carry.shape), dtype=carry.dtype, device=carry.device)
-    dist.all_gather_into_tensor(out, carry.contiguous())
-    return out
+    flat = carry.contiguous().reshape(-1)
+    out = torch.empty(world * flat.numel(), dtype=carry.dtype, device=carry.device)  # flat: gloo wants the concatenated form
+    dist.all_gather_into_tensor(out, flat)
+    return out.reshape((world,) + tuple(carry.shape))
 
 
 def sharded_update_posterior(shard, y, R, mask=None, want_ell=False):

@@ -43,6 +43,15 @@ ALGO_BYTES = {
 }
 
 
+# fp64 instructions (DFMA + DMUL + DADD) per time step, from ncu's sass thread-instruction counters of the same
+# kernels (profiles/r1g_ncu_up_kernels.csv: op counts x cycles / N); the fp64 roofline uses them
+FP64_OPS = {'up_reduce': 179, 'up_filter': 163, 'up_smooth': 260}
+
+# dram__bytes_read.sum + dram__bytes_write.sum per time step of one launch, from the ncu --set full captures
+# under profiles/ (N = 1e7); reported as `traffic` (scaled by the steps a launch processes)
+NCU_DRAM_BYTES = {'up_reduce': 24.8, 'up_filter': 98.9, 'up_smooth': 95.7, 'site_update': 67.4}
+
+
 def bench_inputs(N, seed=0):
     from _data import bench_inputs as f
     return f(N, seed)
@@ -215,28 +224,57 @@ def main_gpu(args):
         kt[name] = (int(cnt), float(tot))
     energy = float(E)
 
-    # ---- end to end through the public API with HOST buffers: per step, the step's inputs (dt, Y)
-    # come from pinned host memory and the result (energy, a double) goes back to the host
-    def e2e_step():
-        model.shard.dt.copy_(dt_pin, non_blocking=True)
-        model.Y.copy_(y_pin, non_blocking=True)
-        model.shard.dts[:-1].copy_(model.shard.dt[1:])
-        model.inference(lr=1.0)
-        return float(model.energy())  # D2H read
+    # ---- end to end through the public API with HOST buffers: every step, that step's inputs (dt, Y) come from
+    # pinned host memory and the result (energy, a double) goes back to the host.  The copy of step i+1's inputs
+    # runs on a second stream into the other device buffer while step i computes (double buffering).
+    copy_stream = torch.cuda.Stream()
+    bufs = [(model.shard.dt, model.Y), (torch.empty_like(model.shard.dt), torch.empty_like(model.Y))]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
 
-    e2e_step()
+    def start_copy(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[b])      # the step that last used this buffer has finished
+            bufs[b][0].copy_(dt_pin, non_blocking=True)
+            bufs[b][1].copy_(y_pin, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_step(i):
+        b = i % 2
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[b])
+        model.shard.dt, model.Y = bufs[b]
+        start_copy(i + 1)                        # H2D of the next step's inputs overlaps this step's kernels
+        model.inference(lr=1.0)
+        e = model.energy()
+        free[b].record(cur)
+        return float(e)                          # D2H read
+
+    for b in range(2):
+        free[b].record(torch.cuda.current_stream())
+    start_copy(0)
+    e2e_step(0)
     sync_all()
     t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(args.steps):
+        e2e_step(i + 1)
     f1.record()
     sync_all()
+    copy_stream.synchronize()
     ms2 = torch.tensor([max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2) / args.steps
+
+    # fp64 FMA peak of this device, measured now (the second roofline: at d = 3 the path is fp64-pipe bound)
+    import ctypes as _C
+    scratch = torch.empty(8 * 148 * 256 * 2, dtype=torch.float64, device=dev)
+    dfma = _C.c_double(0.0)
+    L.bn_measure_dfma_peak(scratch.data_ptr(), scratch.numel(), _C.byref(dfma))
+    dfma_peak = dfma.value
 
     if rank == 0:
         total_steps = NL * world
@@ -251,10 +289,16 @@ def main_gpu(args):
             if dom == 'kf_apply':  # 2 of 3 launches per step write the states, 1 is log-likelihood only
                 ab = (2 * ALGO_BYTES['kf_apply'] + ALGO_BYTES['kf_apply_ell']) / 3.0
             achieved = ab * NL / (avg_ms * 1e-3) / 1e9
+            traffic = NCU_DRAM_BYTES[dom] * NL if (args.traffic is None and dom in NCU_DRAM_BYTES) else args.traffic
             roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': args.traffic, 'peak_source': peak_src,
+                    'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                    'traffic_source': 'ncu --set full dram bytes per step at N=1e7 (profiles/) x steps per launch',
                     'algorithmic_bytes_per_launch': ab * NL, 'avg_launch_ms': avg_ms,
                     'share_of_step': tot / (ms_per_step * args.steps)}
+            if dom in FP64_OPS and dfma_peak > 0:
+                f64 = FP64_OPS[dom] * NL / (avg_ms * 1e-3)
+                roof['fp64'] = {'achieved_fp64_inst_per_s': f64, 'peak_dfma_per_s': dfma_peak, 'frac': f64 / dfma_peak,
+                                'note': 'the kernel is bound by the fp64 pipe, not HBM (DESIGN.md section 4)'}
         line = {
             'metric': METRIC, 'value': total_steps / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -270,6 +314,9 @@ def main_gpu(args):
                                 'frac_of_hbm_peak': 636 * NL / (ms_per_step * 1e-3) / 1e9 / peak},
             'kernels_ms_per_step': {k: v[1] / args.steps for k, v in kt.items()},
             'energy': energy,
+            'fp64_peak_dfma_per_s': dfma_peak,
+            'fp64_frac_by_kernel': {k: FP64_OPS[k] * NL * kt[k][0] / (kt[k][1] * 1e-3) / dfma_peak
+                                    for k in FP64_OPS if k in kt and dfma_peak > 0},
         }
         if world == 1 and not args.no_cpu:
             r = run_cpu(args.cpu_sample, 1, 1)

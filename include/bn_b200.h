@@ -79,6 +79,9 @@ int bn_version(void);
  * lines (one per kernel name) into buf and returns the size the full report needs. */
 int bn_timing_enable(int on);
 int bn_timing_report(char* buf_host, size_t len);
+/* fp64 FMA rate of the current device (DFMA per second, 8 chains/thread, full occupancy): the
+ * denominator of the fp64 roofline bench.py reports beside the HBM one.  scratch: >= 8*SMs*256 doubles. */
+int bn_measure_dfma_peak(double* scratch, size_t scratch_doubles, double* dfma_per_s_host);
 
 /* ---- discretisation: As[N,d,d], Qs[N,d,d] from dt[N] -------------------------------------- */
 int bn_state_dim(const bn_kernel_spec* k);

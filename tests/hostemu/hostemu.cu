@@ -341,3 +341,91 @@ extern "C" int emu_update_posterior(const bn_kernel_spec* k, long long N, int L,
 #undef X
     return -1;
 }
+
+// ---------------------------------------------------------------------------- one emulated rank, phase by phase
+// Host twin of bn_up_shard_{reduce,filter,smooth} for ONE rank (the carries are exchanged by the caller --
+// tests/test_distributed_cpu.py does it with torch.distributed/gloo between real processes).
+struct EmuRankBase {
+    virtual ~EmuRankBase() {}
+    virtual int kf_len() = 0;
+    virtual int rts_len() = 0;
+    virtual void reduce(const double* dt, const double* y, const double* R, double* carry) = 0;
+    virtual void filter(const double* kf_carries, const unsigned char* mask, double* ell, double* rts_carry) = 0;
+    virtual void smooth(const double* rts_carries, double* pm, double* pc) = 0;
+};
+
+template <class G>
+struct EmuRank : EmuRankBase {
+    static constexpr int d = G::d, D = G::D;
+    using FA = FilterAlg<d>;
+    using SA = SmootherAlg<d>;
+    G g;
+    long long n, nc;
+    int L, rank, world;
+    UpIO io;
+    std::vector<double> agg, fpre, sel, spre, fs, s0, sinit;
+    EmuRank(const bn_kernel_spec* k, long long n_, int L_, int rank_, int world_) : n(n_), L(L_), rank(rank_), world(world_) {
+        g.prepare(*k);
+        nc = (n + L - 1) / L;
+        agg.assign((size_t)nc * FA::kElem, 0.0);
+        fpre = agg;
+        sel.assign((size_t)nc * SA::kElem, 0.0);
+        spre = sel;
+        fs.assign((size_t)fs_doubles(nc, L, d + symn(d)), 0.0);
+        s0.assign(64, 0.0);
+        sinit.assign(64, 0.0);
+    }
+    int kf_len() override { return FA::kCarry; }
+    int rts_len() override { return SA::kCarry; }
+    void reduce(const double* dt, const double* y, const double* R, double* carry) override {
+        io = UpIO{n, dt, y, R, nullptr, nullptr, nullptr};
+        DirectCtx<D> cx{io};
+        for (long long c = 0; c < nc; ++c) up_reduce_chunk(g, cx, n, L, nc, rank == 0, agg.data(), c, true);
+        host_scan<FA>(agg.data(), nc, fpre.data());
+        export_carry_body<FA>(fpre.data(), nc, carry);
+    }
+    void filter(const double* kf_carries, const unsigned char* mask, double* ell, double* rts_carry) override {
+        io.mask = mask;
+        DirectCtx<D> cx{io};
+        fold_carries_body<FA>(kf_carries, 0, rank, 1, s0.data());
+        std::vector<double> partials(nc, 0.0);
+        for (long long c = 0; c < nc; ++c)
+            up_filter_chunk<G, true>(g, cx, n, L, nc, rank == 0, fpre.data(), s0.data(), fs.data(), partials.data(), c, true);
+        double tot = 0.0;
+        for (double v : partials) tot += v;
+        if (ell) *ell = tot;
+        for (long long c = 0; c < nc; ++c) up_selem_chunk<G>(n, L, nc, rank != 0, agg.data(), s0.data(), fs.data(), sel.data(), c);
+        host_scan<SA>(sel.data(), nc, spre.data());
+        up_export_scarry<d>(spre.data(), nc, rank == world - 1, n, L, fs.data(), rts_carry);
+    }
+    void smooth(const double* rts_carries, double* pm, double* pc) override {
+        io.post_mean = pm;
+        io.post_cov = pc;
+        DirectCtx<D> cx{io};
+        if (rank != world - 1) fold_carries_body<SA>(rts_carries, world - 1, rank, -1, sinit.data());
+        else up_last_state<d>(n, L, fs.data(), sinit.data());
+        for (long long c = 0; c < nc; ++c) up_smooth_chunk(g, cx, n, L, nc, spre.data(), sinit.data(), fs.data(), c, true);
+    }
+};
+
+extern "C" void* emu_rank_new(const bn_kernel_spec* k, long long n, int L, int rank, int world) {
+    if (L % kUpTJ != 0) return nullptr;
+#define X(FAM, NC) \
+    if (k->family == FAM && k->n_components == NC) return new EmuRank<FastGen<FAM, NC>>(k, n, L, rank, world);
+    EMU_MATERN(X)
+#undef X
+    return nullptr;
+}
+extern "C" void emu_rank_free(void* h) { delete (EmuRankBase*)h; }
+extern "C" int emu_rank_kf_len(void* h) { return ((EmuRankBase*)h)->kf_len(); }
+extern "C" int emu_rank_rts_len(void* h) { return ((EmuRankBase*)h)->rts_len(); }
+extern "C" void emu_rank_reduce(void* h, const double* dt, const double* y, const double* R, double* carry) {
+    ((EmuRankBase*)h)->reduce(dt, y, R, carry);
+}
+extern "C" void emu_rank_filter(void* h, const double* kf_carries, const unsigned char* mask, double* ell,
+                                double* rts_carry) {
+    ((EmuRankBase*)h)->filter(kf_carries, mask, ell, rts_carry);
+}
+extern "C" void emu_rank_smooth(void* h, const double* rts_carries, double* pm, double* pc) {
+    ((EmuRankBase*)h)->smooth(rts_carries, pm, pc);
+}
