@@ -64,9 +64,10 @@ SIGNATURES = {
     'bn_rts_shard_apply': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     'bn_update_posterior_workspace_bytes': (_Z, [_KS, _L]),
     'bn_update_posterior': (_I, [_KS, _L, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
-    'bn_up_shard_reduce': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
-    'bn_up_shard_filter': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
-    'bn_up_shard_smooth': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    'bn_update_posterior_grad': (_I, [_KS, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'bn_up_shard_reduce': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    'bn_up_shard_filter': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    'bn_up_shard_smooth': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_site_update': (_I, [_SA, _P, _Z, _P]),
     'bn_likelihood_stats': (_I, [_SA, _P, _P, _P, _P, _Z, _P]),
     'bn_expected_density': (_I, [_SA, _P, _P, _P, _Z, _P]),

@@ -111,16 +111,23 @@ class MarkovGaussianProcess:
             return None
         return (spec.family, spec.n_components, tuple(spec.variance), tuple(spec.lengthscale))
 
-    def update_posterior(self):
-        """filter then smoother (basemodels.py:689-706).  With the scan form and an in-library kernel this is
+    def update_posterior(self, want_grad=False):
+        """filter then smoother (basemodels.py:689-706).  want_grad: the same pass also accumulates
+        d log-lik / d kernel hyper-parameters, kept for energy_and_grad().  With the scan form and an in-library kernel this is
         ONE fused call (ops.update_posterior); the filter log-likelihood it produces on the way is kept and
         served to compute_log_lik() for as long as the sites and hyper-parameters it was computed from stand
         (the reference evaluates the identical filter a second time inside energy(), basemodels.py:733)."""
         pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
+        self._grad_cache = None
+        if want_grad and not (self.parallel and self._hyper_key() is not None):
+            raise NotImplementedError('the hyper-gradient needs the fused scan-form update (parallel=True, kernel.spec())')
         if self.parallel and self._hyper_key() is not None:
-            ell, sm, sP = ops.update_posterior(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
-                                               want_ell=True)
+            out = ops.update_posterior(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
+                                       want_ell=True, want_grad=want_grad)
+            ell, sm, sP = out[:3]
             self._ell_cache = (ell, self.pseudo_likelihood.version, self._hyper_key())
+            if want_grad:
+                self._grad_cache = (out[3], self.pseudo_likelihood.version, self._hyper_key())
         else:
             _, (fm, fP) = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
                                       parallel=self.parallel, want_ell=False)
@@ -138,6 +145,14 @@ class MarkovGaussianProcess:
         ell, _ = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
                              parallel=self.parallel, want_states=False)
         return ell
+
+    def log_lik_grad(self):
+        """d compute_log_lik() / d [variance_c...; lengthscale_c...] ([2, NC], untransformed hyper-parameters);
+        served from the last update_posterior(want_grad=True) while sites and hyper-parameters stand"""
+        cache = getattr(self, '_grad_cache', None)
+        if cache is None or cache[1] != self.pseudo_likelihood.version or cache[2] != self._hyper_key():
+            self.update_posterior(want_grad=True)
+        return self._grad_cache[0]
 
     def expected_density_pseudo(self):
         pseudo_y, pseudo_var = self.compute_full_pseudo_lik()

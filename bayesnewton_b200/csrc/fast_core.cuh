@@ -8,6 +8,7 @@
 #pragma once
 #include "core.cuh"
 #include "gen.cuh"
+#include "dual.cuh"
 
 namespace bn {
 
@@ -68,6 +69,19 @@ struct FastGen {
                     for (int l = 0; l < n; ++l) s = fma(-X[i * n + l], A[j * n + l], s);
                     Qb[c * symn(n) + sidx(i, j)] = s;
                 }
+        }
+    }
+    // A blocks and their derivative with respect to the rate lam_c (dual-number evaluation of the same closed form)
+    BN_DEV void trans_d(double h, double* Ab, double* dAb) const {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            Dual A[n * n];
+            MaternBlock<FAMILY, Dual>::transition_rate(Dual(lam[c], 1.0), Dual(h), A);
+#pragma unroll
+            for (int i = 0; i < n * n; ++i) {
+                Ab[c * n * n + i] = A[i].v;
+                dAb[c * n * n + i] = A[i].d;
+            }
         }
     }
     // full packed Pinf (d x d)
@@ -396,11 +410,147 @@ BN_DEV void ldlt_solve(const double* S, double* B) {
     }
 }
 
+// -------------------------------------------------------------------------------- hyper-gradient of the filter log-likelihood
+// d ell / d theta, ell = the filter log-likelihood compute_log_lik() returns (basemodels.py:726-741), the only
+// route from the kernel hyper-parameters to energy() in a temporal model (sites and posterior are StateVars;
+// the reference differentiates it with objax.GradValues, README.md:56-70).  The adjoint of the PREDICTED state of
+// step k is available in closed form from the smoothed state the RTS sweep holds at that moment:
+//     d ell / d m^-_k = v_k = (P^-_k)^-1 delta_k,                      delta_k = sm_k - m^-_k
+//     d ell / d P^-_k = M_k = 1/2 (P^-_k)^-1 (sP_k - P^-_k + delta_k delta_k^T) (P^-_k)^-1
+// (the prediction is the prior of the observations k..N-1 and the smoothed state their posterior).  With
+// m^-_k = A_k m_{k-1},  P^-_k = A_k P_{k-1} A_k^T + Q_k,  Q_k = Pinf - A_k Pinf A_k^T  (ops.py:149-151):
+//     d ell = < Gamma, dPinf > + sum_k < 2 M_k A_k (P_{k-1} - Pinf) + v_k m_{k-1}^T , dA_k >,
+//     Gamma = sum_k (M_k - A_k^T M_k A_k)   (+ A_0^T M_0 A_0: the prior entering step 0 is Pinf itself).
+// Everything on the right is in registers inside frts_step (the LDL^T factor of P^-, delta, sP - P^-), so the
+// adjoint pass costs no HBM traffic at all.  A and Pinf are block diagonal: only the diagonal blocks of Gamma
+// and of the dA coefficient are needed.  Not valid with a mask (the reference's mask rule removes the masked
+// densities from ell but keeps their updates, so ell is no longer a marginal likelihood).
+template <class G>
+struct GradAcc {
+    static constexpr int kFields = G::NC * (symn(G::n) + 1);
+    double Gam[G::NC * symn(G::n)];  // diagonal blocks of Gamma, packed
+    double gl[G::NC];                // sum_k < dA-coefficient block , dA_k / d lam_c >
+    BN_DEV void zero() {
+#pragma unroll
+        for (int i = 0; i < G::NC * symn(G::n); ++i) Gam[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < G::NC; ++i) gl[i] = 0.0;
+    }
+};
+
+// F: P^- factorised by ldlt(); dm = sm - m^-; dP = sP - P^- (packed); (pm_, pP_) = (m_{k-1}, P_{k-1}).
+// first: the step whose incoming state is the stationary prior (Gamma takes the whole of M, no dA term).
+template <class G>
+BN_DEV void grad_accumulate(const G& g, const double* Ab, double h, const double* F, const double* dm,
+                            const double* dP, const double* pm_, const double* pP_, bool first, GradAcc<G>& acc) {
+    constexpr int d = G::d, n = G::n, c1 = d + 1;
+    // [X | v] = (P^-)^-1 [dP + dm dm^T | dm]
+    double B[d * c1];
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+#pragma unroll
+        for (int j = 0; j < d; ++j) B[i * c1 + j] = fma(dm[i], dm[j], dP[sidx(i, j)]);
+        B[i * c1 + d] = dm[i];
+    }
+    ldlt_solve<d, c1>(F, B);
+    // M2 = (P^-)^-1 X^T = 2 M
+    double M2[d * d], v[d];
+#pragma unroll
+    for (int i = 0; i < d; ++i) {
+        v[i] = B[i * c1 + d];
+#pragma unroll
+        for (int j = 0; j < d; ++j) M2[i * d + j] = B[j * c1 + i];
+    }
+    ldlt_solve<d, d>(F, M2);
+    if (first) {
+#pragma unroll
+        for (int c = 0; c < G::NC; ++c)
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j)
+                    acc.Gam[c * symn(n) + sidx(i, j)] += 0.25 * (M2[(c * n + i) * d + c * n + j] + M2[(c * n + j) * d + c * n + i]);
+        return;
+    }
+    // XA = M2 A  (d x d)
+    double XA[d * d];
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+#pragma unroll
+        for (int c = 0; c < G::NC; ++c)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int l = 0; l < n; ++l) s = fma(M2[i * d + c * n + l], Ab[c * n * n + l * n + j], s);
+                XA[i * d + c * n + j] = s;
+            }
+#pragma unroll
+    for (int c = 0; c < G::NC; ++c) {
+        // Gamma_c += 1/2 (M2_cc - A_c^T (M2 A)_cc)
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double s = 0.5 * (M2[(c * n + i) * d + c * n + j] + M2[(c * n + j) * d + c * n + i]);
+#pragma unroll
+                for (int l = 0; l < n; ++l) s = fma(-Ab[c * n * n + l * n + i], XA[(c * n + l) * d + c * n + j], s);
+                acc.Gam[c * symn(n) + sidx(i, j)] = fma(0.5, s, acc.Gam[c * symn(n) + sidx(i, j)]);
+            }
+        // < (M2 A (P_{k-1} - Pinf))_cc + v_c m_c^T , dA_c / d lam_c >; the derivative of the transition is formed
+        // here, at its only use, by the dual-number evaluation of the closed form (nothing extra stays live
+        // across the smoother step)
+        Dual Ad[n * n];
+        MaternBlock<G::family, Dual>::transition_rate(Dual(g.lam[c], 1.0), Dual(h), Ad);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                double z = v[c * n + i] * pm_[c * n + j];
+#pragma unroll
+                for (int l = 0; l < d; ++l) {
+                    const bool nz = (l / n == c) && ((((l % n) + j) & 1) == 0);
+                    const double dl = nz ? pP_[sidx(l, c * n + j)] - g.Pb[c * symn(n) + sidx(l % n, j)]
+                                         : pP_[sidx(l, c * n + j)];
+                    z = fma(XA[(c * n + i) * d + l], dl, z);
+                }
+                s = fma(z, Ad[i * n + j].d, s);
+            }
+        acc.gl[c] += s;
+    }
+}
+
+// (Gamma blocks, gl) -> d ell / d variance_c, d ell / d lengthscale_c.  Pinf is linear in the variance and A
+// does not depend on it; the lengthscale acts through Pinf and through lam = sqrt(2 nu) / lengthscale.
+template <class G>
+BN_DEV void grad_finish(const bn_kernel_spec& s, const double* fields, double* dvar, double* dlen) {
+    constexpr int n = G::n, NC = G::NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        Dual P[symn(n)];
+        MaternBlock<G::family, Dual>::pinf(Dual(s.variance[c]), Dual(s.lengthscale[c], 1.0), P);
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const double w = (i == j ? 1.0 : 2.0) * fields[c * symn(n) + sidx(i, j)];
+                a = fma(w, P[sidx(i, j)].v, a);
+                b = fma(w, P[sidx(i, j)].d, b);
+            }
+        const double lam = MaternBlock<G::family, double>::rate(s.lengthscale[c]);
+        dvar[c] = a / s.variance[c];
+        dlen[c] = b - fields[NC * symn(n) + c] * lam / s.lengthscale[c];
+    }
+}
+
 // -------------------------------------------------------------------------------- smoother step
 // (sm, sP) at step k+1 in, at step k out (ops.py:290-301); Ab, Qb belong to the step k -> k+1.
-template <class G>
+// With GRAD the step also accumulates the hyper-gradient terms of the transition k -> k+1 (see below).
+template <class G, bool GRAD = false>
 BN_DEV void frts_step(const double* Ab, const double* Qb, const double* fm, const double* fP, double* sm,
-                      double* sP) {
+                      double* sP, const G* g = nullptr, double h = 0.0, GradAcc<G>* acc = nullptr) {
     constexpr int d = G::d;
     double pm[d], AfP[d * d], pP[symn(d)];
     bd_matvec<G>(Ab, fm, pm);
@@ -412,6 +562,7 @@ BN_DEV void frts_step(const double* Ab, const double* Qb, const double* fm, cons
 #pragma unroll
     for (int i = 0; i < symn(d); ++i) dP[i] = sP[i] - pP[i];
     ldlt<d>(pP);
+    if constexpr (GRAD) grad_accumulate<G>(*g, Ab, h, pP, dm, dP, fm, fP, false, *acc);
     ldlt_solve<d, d>(pP, AfP);  // AfP <- pP^-1 A fP = G^T
     // sm = fm + G dm,  G[i][j] = AfP[j][i]
 #pragma unroll

@@ -53,39 +53,54 @@ extern "C" int bn_update_posterior(const bn_kernel_spec* k, int64_t N, const dou
     return up_dispatch(c);
 }
 
+extern "C" int bn_update_posterior_grad(const bn_kernel_spec* k, int64_t N, const double* dt, const double* pseudo_y,
+                                        const double* pseudo_var, double* ell, double* post_mean, double* post_cov,
+                                        double* dell_dvariance, double* dell_dlengthscale, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+    if (int rc = up_check(k, N, dt, pseudo_y, pseudo_var)) return rc;
+    BN_REQUIRE(N > 0, "the hyper-gradient needs at least one step");
+    BN_REQUIRE(post_mean && post_cov && dell_dvariance && dell_dlengthscale, "null output array");
+    UpCall c{k, UpIO{N, dt, pseudo_y, pseudo_var, nullptr, post_mean, post_cov}, ell, workspace, workspace_bytes,
+             (cudaStream_t)stream, UP_ALL, 0, 1, nullptr, nullptr, 1, dell_dvariance, dell_dlengthscale};
+    return up_dispatch(c);
+}
+
 extern "C" int bn_up_shard_reduce(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* dt,
-                                  const double* pseudo_y, const double* pseudo_var, double* carry, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
+                                  const double* pseudo_y, const double* pseudo_var, double* carry, int want_grad,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = up_check(k, N, dt, pseudo_y, pseudo_var)) return rc;
     BN_REQUIRE(N > 0, "a time shard must hold at least one step");
     BN_REQUIRE(rank >= 0 && rank < world, "rank %d outside world %d", rank, world);
     BN_REQUIRE(carry != nullptr, "carry output is null");
     UpCall c{k, UpIO{N, dt, pseudo_y, pseudo_var, nullptr, nullptr, nullptr}, nullptr, workspace, workspace_bytes,
-             (cudaStream_t)stream, UP_REDUCE, rank, world, carry, nullptr};
+             (cudaStream_t)stream, UP_REDUCE, rank, world, carry, nullptr, want_grad != 0, nullptr, nullptr};
     return up_dispatch(c);
 }
 
 extern "C" int bn_up_shard_filter(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* kf_carries,
                                   const double* dt, const double* pseudo_y, const double* pseudo_var,
-                                  const uint8_t* mask, double* ell, double* rts_carry, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
+                                  const uint8_t* mask, double* ell, double* rts_carry, int want_grad,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = up_check(k, N, dt, pseudo_y, pseudo_var)) return rc;
     BN_REQUIRE(N > 0, "a time shard must hold at least one step");
     BN_REQUIRE(rank >= 0 && rank < world, "rank %d outside world %d", rank, world);
     BN_REQUIRE(kf_carries && rts_carry, "null carry array");
+    BN_REQUIRE(!(want_grad && mask), "the hyper-gradient is not available with a mask (see bn_update_posterior_grad)");
     UpCall c{k, UpIO{N, dt, pseudo_y, pseudo_var, mask, nullptr, nullptr}, ell, workspace, workspace_bytes,
-             (cudaStream_t)stream, UP_FILTER, rank, world, rts_carry, kf_carries};
+             (cudaStream_t)stream, UP_FILTER, rank, world, rts_carry, kf_carries, want_grad != 0, nullptr, nullptr};
     return up_dispatch(c);
 }
 
 extern "C" int bn_up_shard_smooth(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* rts_carries,
-                                  const double* dt, double* post_mean, double* post_cov, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
+                                  const double* dt, double* post_mean, double* post_cov, double* dell_dvariance,
+                                  double* dell_dlengthscale, void* workspace, size_t workspace_bytes, void* stream) {
     BN_REQUIRE(k != nullptr, "kernel spec is null");
     BN_REQUIRE(N > 0, "a time shard must hold at least one step");
     BN_REQUIRE(rank >= 0 && rank < world, "rank %d outside world %d", rank, world);
     BN_REQUIRE(rts_carries && dt && post_mean && post_cov, "null array");
+    BN_REQUIRE((dell_dvariance == nullptr) == (dell_dlengthscale == nullptr), "give both gradient outputs or neither");
     UpCall c{k, UpIO{N, dt, nullptr, nullptr, nullptr, post_mean, post_cov}, nullptr, workspace, workspace_bytes,
-             (cudaStream_t)stream, UP_SMOOTH, rank, world, nullptr, rts_carries};
+             (cudaStream_t)stream, UP_SMOOTH, rank, world, nullptr, rts_carries, dell_dvariance != nullptr,
+             dell_dvariance, dell_dlengthscale};
     return up_dispatch(c);
 }

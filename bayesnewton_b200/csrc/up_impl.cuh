@@ -33,6 +33,10 @@ constexpr int kUpWarps = 4;              // warps per CTA
 constexpr int kUpThreads = 32 * kUpWarps;
 constexpr int kUpBlocksPerSM = BN_UP_BLOCKS;  // resident CTAs per SM the single-latent kernels are compiled for
 constexpr long long kUpTargetChunks = 148LL * kUpBlocksPerSM * kUpThreads;  // one resident wave
+#ifndef BN_UP_GRAD_BLOCKS
+#define BN_UP_GRAD_BLOCKS 3
+#endif
+constexpr int kUpGradBlocksPerSM = BN_UP_GRAD_BLOCKS;  // the gradient-carrying smoother keeps more registers live
 
 struct UpIO {
     long long N;
@@ -44,8 +48,9 @@ struct UpIO {
     double* post_cov;           // [N,D,D]   H sP H^T
 };
 
-inline ChunkPlan up_plan_chunks(long long N) {
-    long long L = (N + kUpTargetChunks - 1) / kUpTargetChunks;
+inline ChunkPlan up_plan_chunks(long long N, bool grad = false) {
+    const long long target = grad ? 148LL * kUpGradBlocksPerSM * kUpThreads : kUpTargetChunks;
+    long long L = (N + target - 1) / target;
     L = (L + kUpTJ - 1) / kUpTJ * kUpTJ;
     if (L < kUpTJ) L = kUpTJ;  // no upper bound: for large N the chunk count stays at one resident wave
     ChunkPlan p;
@@ -369,14 +374,22 @@ BN_DEV void up_selem_chunk(long long N, int L, long long nchunks, int need_first
     SA::store(selems, nchunks, nchunks - 1 - c, se);
 }
 
+// GRAD: the sweep also accumulates this chunk's share of d ell / d hyper-parameters (fast_core.cuh) for the
+// transitions INTO each of its steps -- inside the chunk as part of frts_step, and for its first step from the
+// last filtered state of the chunk on its left (the prior when it is global step 0, s0 on a later shard) --
+// and leaves the GradAcc fields in gpart[field * nchunks + c].
 #pragma nv_exec_check_disable
-template <class G, class Ctx>
+template <class G, bool GRAD, class Ctx>
 BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, const double* sprefix,
-                            const double* sinit, const double* fs, long long c, bool active) {
+                            const double* sinit, const double* fs, long long c, bool active, int is_first = 0,
+                            const double* s0 = nullptr, double* gpart = nullptr) {
     constexpr int d = G::d, D = G::D;
     using Alg = SmootherAlg<d>;
     typename Alg::State s;
     Alg::zero_state(s);
+    GradAcc<G> acc;
+    double h_next = 0.0;  // length of the step out of the state being processed (GRAD only)
+    if constexpr (GRAD) acc.zero();
     const long long p = nchunks - 1 - c;
     if (active) {
         Alg::load_state(sinit, 1, 0, s);
@@ -414,6 +427,8 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
                 for (int i = 0; i < G::kBlockS; ++i) Qb[i] = Qbn[i];
                 // the discretisation of the step below (k-1 -> k, length h_k) is formed while this step's
                 // dependent chain runs
+                const double h_out = h_next;
+                h_next = h_k;
                 g.trans(h_k, Abn);
                 g.noise(Abn, Qbn);
                 if (j < j_last) {
@@ -423,7 +438,8 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
 #pragma unroll
                     for (int i = 0; i < symn(d); ++i) fP[i] = nfP[i];
                     if (j >= 1) fs_load<d>(fs, c, L, j - 1, nfm, nfP);  // in flight during this step's arithmetic
-                    frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
+                    if constexpr (GRAD) frts_step<G, true>(Ab, Qb, fm, fP, s.m, s.P, &g, h_out, &acc);
+                    else frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
                 }
                 double pm[D], pc[D * D];
 #pragma unroll
@@ -436,6 +452,45 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
             }
         }
         ctx_end(cx, cbase, L, j0);
+    }
+    if constexpr (GRAD) {
+        if (active) {
+            // transition into the chunk's first step k0: s is its smoothed state, (Abn, Qbn) its discretisation, h_next its length
+            double pm_[d], pP_[symn(d)], mp[d], Pp[symn(d)], dm[d], dP[symn(d)];
+            const bool prior = (c == 0 && is_first);
+            if (prior) {
+#pragma unroll
+                for (int i = 0; i < d; ++i) pm_[i] = mp[i] = 0.0;
+                g.pinf_full(pP_);
+#pragma unroll
+                for (int i = 0; i < symn(d); ++i) Pp[i] = pP_[i];
+            } else {
+                if (c == 0) {
+                    typename FilterAlg<d>::State t;
+                    FilterAlg<d>::load_state(s0, 1, 0, t);
+#pragma unroll
+                    for (int i = 0; i < d; ++i) pm_[i] = t.m[i];
+#pragma unroll
+                    for (int i = 0; i < symn(d); ++i) pP_[i] = t.P[i];
+                } else {
+                    fs_load<d>(fs, c - 1, L, L - 1, pm_, pP_);
+                }
+                double X[d * d];
+                bd_matvec<G>(Abn, pm_, mp);
+                bd_mat_sym<G>(Abn, pP_, X);
+                bd_abt_sym<G>(X, Abn, Qbn, Pp);
+            }
+#pragma unroll
+            for (int i = 0; i < d; ++i) dm[i] = s.m[i] - mp[i];
+#pragma unroll
+            for (int i = 0; i < symn(d); ++i) dP[i] = s.P[i] - Pp[i];
+            ldlt<d>(Pp);
+            grad_accumulate<G>(g, Abn, h_next, Pp, dm, dP, pm_, pP_, prior, acc);
+#pragma unroll
+            for (int f = 0; f < G::NC * symn(G::n); ++f) gpart[f * nchunks + c] = acc.Gam[f];
+#pragma unroll
+            for (int f = 0; f < G::NC; ++f) gpart[(G::NC * symn(G::n) + f) * nchunks + c] = acc.gl[f];
+        }
     }
 }
 
@@ -504,7 +559,37 @@ up_smooth_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, 
     extern __shared__ double up_smem[];
     WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, true);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
-    up_smooth_chunk(g, cx, io.N, L, nchunks, sprefix, sinit, fs, c, c < nchunks);
+    up_smooth_chunk<G, false>(g, cx, io.N, L, nchunks, sprefix, sinit, fs, c, c < nchunks);
+}
+
+// the same sweep with the hyper-gradient accumulation (more live registers: its own occupancy bound)
+template <class G>
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpGradBlocksPerSM : 1))
+up_smooth_grad_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, const double* sinit,
+                      const double* fs, int is_first, const double* s0, double* gpart) {
+    extern __shared__ double up_smem[];
+    WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, true);
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    up_smooth_chunk<G, true>(g, cx, io.N, L, nchunks, sprefix, sinit, fs, c, c < nchunks, is_first, s0, gpart);
+}
+
+// deterministic sums of the per-chunk GradAcc fields (one block per field), then the chain to (variance, lengthscale)
+static __global__ void __launch_bounds__(1024) up_grad_sum_kernel(const double* gpart, long long nchunks, double* fields) {
+    __shared__ double sh[1024];
+    const double* x = gpart + (long long)blockIdx.x * nchunks;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < nchunks; i += 1024) s += x[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fields[blockIdx.x] = sh[0];
+}
+template <class G>
+__global__ void up_grad_finish_kernel(bn_kernel_spec spec, const double* fields, double* dvar, double* dlen) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) grad_finish<G>(spec, fields, dvar, dlen);
 }
 
 template <int d>
@@ -521,16 +606,25 @@ __global__ void up_export_scarry_kernel(const double* top_prefix, long long n_to
 // ------------------------------------------------------------------------------------------ host driver
 enum { UP_ALL = 0, UP_REDUCE = 1, UP_FILTER = 2, UP_SMOOTH = 3 };
 
+constexpr int kUpMaxGradFields = 16;  // >= NC * (symn(n) + 1) for every instantiated stack
+
 struct UpWs {
-    double *s0, *sinit, *partials, *fs;
+    double *s0, *sinit, *partials, *gpart, *gfields, *fs;
     ScanPlan fplan, splan;
 };
 
 template <int d>
 inline size_t up_ws_doubles(long long N) {
-    ChunkPlan cp = up_plan_chunks(N > 0 ? N : 1);
-    return 128 + scan_plan_doubles(cp.nchunks, FilterAlg<d>::kElem) + scan_plan_doubles(cp.nchunks, SmootherAlg<d>::kElem) +
-           cp.nchunks + fs_doubles(cp.nchunks, cp.L, d + symn(d));
+    // sized for the larger of the two chunk plans (with / without the hyper-gradient accumulation)
+    size_t need = 0;
+    for (int grad = 0; grad < 2; ++grad) {
+        ChunkPlan cp = up_plan_chunks(N > 0 ? N : 1, grad != 0);
+        size_t n = 128 + 64 + scan_plan_doubles(cp.nchunks, FilterAlg<d>::kElem) +
+                   scan_plan_doubles(cp.nchunks, SmootherAlg<d>::kElem) + cp.nchunks +
+                   (size_t)cp.nchunks * kUpMaxGradFields + fs_doubles(cp.nchunks, cp.L, d + symn(d));
+        if (n > need) need = n;
+    }
+    return need;
 }
 
 template <int d>
@@ -544,6 +638,8 @@ inline UpWs up_ws(void* ws, const ChunkPlan& cp) {
     w.splan = make_scan_plan(p, cp.nchunks, SmootherAlg<d>::kElem);
     p += scan_plan_doubles(cp.nchunks, SmootherAlg<d>::kElem);
     w.partials = p; p += cp.nchunks;
+    w.gfields = p; p += 64;
+    w.gpart = p; p += (size_t)cp.nchunks * kUpMaxGradFields;
     w.fs = p;
     return w;
 }
@@ -558,6 +654,9 @@ struct UpCall {
     int phase, rank, world;
     double* carry_out;       // UP_REDUCE: filter carry; UP_FILTER: smoother carry
     const double* carries;   // UP_FILTER: filter carries [world]; UP_SMOOTH: smoother carries [world]
+    int grad;                // 1: hyper-gradient plan; every phase of one update must agree on it
+    double* dvar;            // UP_ALL / UP_SMOOTH with grad: d ell / d variance[NC] (this shard's share)
+    double* dlen;            //                               d ell / d lengthscale[NC]
 };
 
 template <class G>
@@ -573,7 +672,8 @@ inline int up_run(const UpCall& c) {
     }
     G g;
     g.prepare(*c.spec);
-    ChunkPlan cp = up_plan_chunks(io.N);
+    static_assert(GradAcc<G>::kFields <= kUpMaxGradFields, "raise kUpMaxGradFields");
+    ChunkPlan cp = up_plan_chunks(io.N, c.grad != 0);
     size_t need = up_ws_doubles<d>(io.N) * sizeof(double);
     BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
     UpWs w = up_ws<d>(c.ws, cp);
@@ -586,6 +686,7 @@ inline int up_run(const UpCall& c) {
         BN_CUDA(cudaFuncSetAttribute(up_filter_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BN_CUDA(cudaFuncSetAttribute(up_filter_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BN_CUDA(cudaFuncSetAttribute(up_smooth_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BN_CUDA(cudaFuncSetAttribute(up_smooth_grad_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
 
     if (c.phase == UP_ALL || c.phase == UP_REDUCE) {
@@ -638,9 +739,19 @@ inline int up_run(const UpCall& c) {
             up_last_state_kernel<d><<<1, 1, 0, st>>>(io.N, cp.L, w.fs, w.sinit);
         }
         BN_CUDA(cudaGetLastError());
-        BN_LAUNCH("up_smooth", st,
-                  (up_smooth_kernel<G><<<grid, kUpThreads, smem, st>>>(g, io, cp.L, cp.nchunks, w.splan.prefix[0],
-                                                                       w.sinit, w.fs)));
+        if (c.grad && c.dvar) {
+            BN_LAUNCH("up_smooth_grad", st,
+                      (up_smooth_grad_kernel<G><<<grid, kUpThreads, smem, st>>>(
+                          g, io, cp.L, cp.nchunks, w.splan.prefix[0], w.sinit, w.fs, is_first, w.s0, w.gpart)));
+            BN_CUDA(cudaGetLastError());
+            BN_LAUNCH("up_grad_sum", st,
+                      (up_grad_sum_kernel<<<GradAcc<G>::kFields, 1024, 0, st>>>(w.gpart, cp.nchunks, w.gfields)));
+            up_grad_finish_kernel<G><<<1, 1, 0, st>>>(*c.spec, w.gfields, c.dvar, c.dlen);
+        } else {
+            BN_LAUNCH("up_smooth", st,
+                      (up_smooth_kernel<G><<<grid, kUpThreads, smem, st>>>(g, io, cp.L, cp.nchunks, w.splan.prefix[0],
+                                                                           w.sinit, w.fs)));
+        }
         BN_CUDA(cudaGetLastError());
     }
     return 0;

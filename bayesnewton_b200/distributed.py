@@ -49,30 +49,36 @@ class TimeShard:
             self._ws_up = (torch.empty(int(nb), dtype=torch.uint8, device=self.dt.device), int(nb))
         return self._ws_up
 
-    def up_reduce(self, y, R):
+    def up_reduce(self, y, R, want_grad=False):
         ws, nb = self._up_ws()
         carry = torch.empty(self.kf_len, dtype=torch.float64, device=self.dt.device)
         _lib.check(_lib.lib().bn_up_shard_reduce(self.spec, self.N, self.rank, self.world, ptr(self.dt), ptr(y), ptr(R),
-                                                 ptr(carry), ptr(ws), nb, stream_ptr()))
+                                                 ptr(carry), int(want_grad), ptr(ws), nb, stream_ptr()))
         return carry
 
-    def up_filter(self, kf_carries, y, R, mask=None, want_ell=True):
+    def up_filter(self, kf_carries, y, R, mask=None, want_ell=True, want_grad=False):
         ws, nb = self._up_ws()
         dev = self.dt.device
         ell = torch.zeros((), dtype=torch.float64, device=dev) if want_ell else None
         carry = torch.empty(self.rts_len, dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().bn_up_shard_filter(self.spec, self.N, self.rank, self.world, ptr(kf_carries), ptr(self.dt),
-                                                 ptr(y), ptr(R), ptr(mask), ptr(ell), ptr(carry), ptr(ws), nb,
-                                                 stream_ptr()))
+                                                 ptr(y), ptr(R), ptr(mask), ptr(ell), ptr(carry), int(want_grad),
+                                                 ptr(ws), nb, stream_ptr()))
         return ell, carry
 
-    def up_smooth(self, rts_carries):
+    def up_smooth(self, rts_carries, want_grad=False):
+        """want_grad: also returns this shard's share of d ell / d [variance_c..., lengthscale_c...] ([2, NC])"""
         ws, nb = self._up_ws()
         dev = self.dt.device
         sm = torch.empty((self.N, self.D, 1), dtype=torch.float64, device=dev)
         sP = torch.empty((self.N, self.D, self.D), dtype=torch.float64, device=dev)
+        g = torch.zeros((2, self.D), dtype=torch.float64, device=dev) if want_grad else None
         _lib.check(_lib.lib().bn_up_shard_smooth(self.spec, self.N, self.rank, self.world, ptr(rts_carries),
-                                                 ptr(self.dt), ptr(sm), ptr(sP), ptr(ws), nb, stream_ptr()))
+                                                 ptr(self.dt), ptr(sm), ptr(sP),
+                                                 g[0].data_ptr() if want_grad else None,
+                                                 g[1].data_ptr() if want_grad else None, ptr(ws), nb, stream_ptr()))
+        if want_grad:
+            return sm, sP, g
         return sm, sP
 
     # ---- filter
@@ -120,15 +126,15 @@ def _all_gather(carry, world):
     return out.reshape((world,) + tuple(carry.shape))
 
 
-def sharded_update_posterior(shard, y, R, mask=None, want_ell=False):
+def sharded_update_posterior(shard, y, R, mask=None, want_ell=False, want_grad=False):
     """update_posterior (basemodels.py:689-706) on a time-sharded model: the fused library path, 2 carry
-    all-gathers.  Every rank passes ITS shard of the sites; returns (ell_local_or_None, post_mean, post_cov)."""
-    c = shard.up_reduce(y, R)
+    all-gathers.  Every rank passes ITS shard of the sites; returns (ell_local_or_None, post_mean, post_cov)
+    and, with want_grad, the LOCAL share [2, NC] of d ell / d (variance, lengthscale) (sum over ranks = total)."""
+    c = shard.up_reduce(y, R, want_grad)
     carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
-    ell, c = shard.up_filter(carries, y, R, mask, want_ell=want_ell)
+    ell, c = shard.up_filter(carries, y, R, mask, want_ell=want_ell, want_grad=want_grad)
     carries = _all_gather(c, shard.world) if shard.world > 1 else c.reshape(1, -1)
-    sm, sP = shard.up_smooth(carries)
-    return ell, sm, sP
+    return (ell,) + tuple(shard.up_smooth(carries, want_grad))
 
 
 def sharded_filter_smoother(shard, y, R, mask=None, want_ell=False):
@@ -179,7 +185,7 @@ def filter_smoother_in_shards(kernel, dt, y, R, mask, n_shards):
                 post_cov=torch.cat([s[1] for s in smo]))
 
 
-def update_posterior_in_shards(kernel, dt, y, R, mask, n_shards):
+def update_posterior_in_shards(kernel, dt, y, R, mask, n_shards, want_grad=False):
     """single-process run of the FUSED sharded update (bn_up_shard_*) over n_shards shards"""
     dt, y, R = as_dev(dt).reshape(-1), as_dev(y), as_dev(R)
     mk = as_mask(mask)
@@ -190,12 +196,15 @@ def update_posterior_in_shards(kernel, dt, y, R, mask, n_shards):
     ys = [y.reshape(N, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
     Rs = [R.reshape(N, D, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
     ms = [None if mk is None else mk.reshape(N, D)[b[r]:b[r + 1]].contiguous() for r in range(n_shards)]
-    carries = torch.stack([s.up_reduce(ys[r], Rs[r]) for r, s in enumerate(shards)])
-    filt = [s.up_filter(carries, ys[r], Rs[r], ms[r]) for r, s in enumerate(shards)]
+    carries = torch.stack([s.up_reduce(ys[r], Rs[r], want_grad) for r, s in enumerate(shards)])
+    filt = [s.up_filter(carries, ys[r], Rs[r], ms[r], want_grad=want_grad) for r, s in enumerate(shards)]
     carries = torch.stack([f[1] for f in filt])
-    smo = [s.up_smooth(carries) for s in shards]
-    return dict(ell=sum(f[0] for f in filt), post_mean=torch.cat([s[0] for s in smo]),
-                post_cov=torch.cat([s[1] for s in smo]))
+    smo = [s.up_smooth(carries, want_grad) for s in shards]
+    out = dict(ell=sum(f[0] for f in filt), post_mean=torch.cat([s[0] for s in smo]),
+               post_cov=torch.cat([s[1] for s in smo]))
+    if want_grad:
+        out['grad'] = sum(s[2] for s in smo)
+    return out
 
 
 class TimeShardedMarkovGP:
@@ -229,11 +238,13 @@ class TimeShardedMarkovGP:
         self.mask_pseudo_y = nan.to(torch.uint8).contiguous() if (D == 1 and bool(nan.any())) else None
         self._ws = _ws(self.N, self.state_dim, D, dev)
 
-    def update_posterior(self):
+    def update_posterior(self, want_grad=False):
         pl = self.pseudo_likelihood
-        ell, sm, sP = sharded_update_posterior(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y, want_ell=True)
-        self._ell_cache = (ell, pl.version)  # the local log-likelihood partial of exactly these sites
-        self.posterior_mean, self.posterior_variance = sm, sP
+        out = sharded_update_posterior(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y, want_ell=True,
+                                       want_grad=want_grad)
+        self._ell_cache = (out[0], pl.version)  # the local log-likelihood partial of exactly these sites
+        self._grad_cache = (out[3], pl.version) if want_grad else None
+        self.posterior_mean, self.posterior_variance = out[1], out[2]
 
     def _site_args(self, cubature=None):
         a, keep = self.likelihood.site_args(self.method, self.Y, self.posterior_mean, self.posterior_variance,
@@ -241,7 +252,9 @@ class TimeShardedMarkovGP:
         a.nat1, a.nat2 = self.pseudo_likelihood.nat1_.data_ptr(), self.pseudo_likelihood.nat2_.data_ptr()
         return a, keep
 
-    def inference(self, lr=1.0, cubature=None, ensure_psd=True):
+    def inference(self, lr=1.0, cubature=None, ensure_psd=True, want_grad=False):
+        """want_grad: the closing posterior update also accumulates d log-lik / d hyper-parameters, which
+        energy_and_grad() then serves without another pass"""
         self.update_posterior()
         a, keep = self._site_args(cubature)
         a.lr, a.ensure_psd = float(lr), int(bool(ensure_psd))
@@ -250,7 +263,23 @@ class TimeShardedMarkovGP:
         ws, nb = self._ws
         _lib.check(_lib.lib().bn_site_update(a, ptr(ws), nb, stream_ptr()))
         pl.version += 1
-        self.update_posterior()
+        self.update_posterior(want_grad)
+
+    def energy_and_grad(self, cubature=None):
+        """(energy, d energy / d [variances; lengthscales] as a [2, NC] tensor): what
+        objax.GradValues(model.energy, model.vars()) returns for the kernel hyper-parameters (README.md:56-70),
+        before the softplus chain of kernels.py:80-95.  d energy = - d log-lik (the other terms hold the
+        kernel hyper-parameters only through StateVars)."""
+        pl = self.pseudo_likelihood
+        cache = getattr(self, '_grad_cache', None)
+        if cache is None or cache[1] != pl.version:
+            self.update_posterior(want_grad=True)
+        g = self._grad_cache[0].clone()
+        E = self.energy(cubature)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(g)
+        return E, -g
 
     def energy(self, cubature=None):
         """VI / Newton energy (inference.py:130-154,197-222): three local sums, one all-reduce"""

@@ -20,9 +20,11 @@ class InferenceMixin:
         a.nat1, a.nat2 = self.pseudo_likelihood.nat1_.data_ptr(), self.pseudo_likelihood.nat2_.data_ptr()
         return a, keep
 
-    def inference(self, lr=1., batch_ind=None, cubature=None, ensure_psd=True, return_state=True, **kwargs):
+    def inference(self, lr=1., batch_ind=None, cubature=None, ensure_psd=True, return_state=True, want_grad=False,
+                  **kwargs):
         """one iteration (inference.py:65-90).  Returns ((mean, jacobian, hessian), (diff1, diff2));
-        with return_state=False the triple is not written to HBM (the reference's jit drops it as dead code)"""
+        with return_state=False the triple is not written to HBM (the reference's jit drops it as dead code).
+        want_grad: the closing posterior update also accumulates the hyper-gradient energy_and_grad() serves."""
         if batch_ind is not None and len(batch_ind) != self.num_data:
             raise NotImplementedError('mini-batched site updates are outside the hot-path scope (SURVEY A.15)')
         self.update_posterior()
@@ -43,7 +45,10 @@ class InferenceMixin:
         ws, nb = workspace(N, self.state_dim, D)
         _lib.check(_lib.lib().bn_site_update(a, ptr(ws), nb, stream_ptr()))
         pl.version += 1  # the sites were rewritten in place
-        self.update_posterior()
+        if want_grad:
+            self.update_posterior(want_grad=True)
+        else:
+            self.update_posterior()
         return state, (diffs[0], diffs[1])
 
     def expected_density(self, cubature=None):
@@ -56,6 +61,16 @@ class InferenceMixin:
 
     def energy(self, batch_ind=None, cubature=None, **kwargs):
         raise NotImplementedError
+
+    def energy_and_grad(self, cubature=None):
+        """(energy, d energy / d [variance_c...; lengthscale_c...]): the kernel part of what
+        objax.GradValues(model.energy, model.vars()) returns (README.md:56-70, demos/regression.py:63-70), for the
+        untransformed hyper-parameters; `kernel.chain_to_transformed(grad)` applies the softplus of
+        kernels.py:80-95.  In every scheme the kernel hyper-parameters reach the energy only through the filter
+        log-likelihood (sites and posterior are StateVars): VI/Newton  E = -(L - (X - ell)),  EP/PL  E = -(ell + ...),
+        so d E = - d ell."""
+        g = self.log_lik_grad()
+        return self.energy(cubature=cubature), -g
 
 
 class VariationalInference(InferenceMixin):

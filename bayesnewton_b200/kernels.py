@@ -53,6 +53,13 @@ class StationaryKernel(Kernel):
     def spec(self):
         return _lib.kernel_spec(self.family, [self.variance], [self.lengthscale])
 
+    def chain_to_transformed(self, grad):
+        """[2, 1] gradient w.r.t. (variance, lengthscale) -> w.r.t. the stored softplus-transformed variables
+        (d softplus(x)/dx = sigmoid(x)), the quantities objax's optimiser steps on (kernels.py:80-95)"""
+        sig = lambda x: 1.0 / (1.0 + math.exp(-x))
+        return grad * torch.tensor([[sig(self.transformed_variance)], [sig(self.transformed_lengthscale)]],
+                                   dtype=grad.dtype, device=grad.device)
+
     def measurement_model(self):
         H = np.zeros((1, self.state_dim))
         H[0, 0] = 1.0

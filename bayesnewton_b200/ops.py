@@ -133,11 +133,13 @@ def rauch_tung_striebel_smoother(dt, kernel, filter_mean, filter_cov, return_ful
     return means, covs, gains
 
 
-def update_posterior(dt, kernel, y, noise_cov, mask=None, want_ell=False):
+def update_posterior(dt, kernel, y, noise_cov, mask=None, want_ell=False, want_grad=False):
     """kalman_filter followed by rauch_tung_striebel_smoother, `parallel=True` form, as ONE library call
     (MarkovGaussianProcess.update_posterior, basemodels.py:689-706).  Returns (ell or None, means [N,D,1],
     covs [N,D,D]) = (filter log-likelihood, H sm, H sP H^T).  Needs a kernel with an in-library
-    discretisation (kernel.spec()); other kernels take the two stand-alone calls."""
+    discretisation (kernel.spec()); other kernels take the two stand-alone calls.
+    want_grad appends d ell / d [variance_c...; lengthscale_c...] as a [2, NC] tensor (bn_update_posterior_grad:
+    the reverse-mode pass objax.GradValues runs through compute_log_lik, basemodels.py:726-741)."""
     spec = kernel.spec() if hasattr(kernel, 'spec') else None
     if spec is None:
         raise NotImplementedError('the fused update needs kernel.spec(); use kalman_filter + rauch_tung_striebel_smoother')
@@ -152,6 +154,14 @@ def update_posterior(dt, kernel, y, noise_cov, mask=None, want_ell=False):
     means = torch.empty((N, D, 1), dtype=torch.float64, device=dt.device)
     covs = torch.empty((N, D, D), dtype=torch.float64, device=dt.device)
     ws, nb = up_workspace(spec, N)
+    if want_grad:
+        if mk is not None:
+            raise NotImplementedError('hyper-gradient with missing-data masks is not available (see include/bn_b200.h)')
+        g = torch.zeros((2, D), dtype=torch.float64, device=dt.device)
+        _lib.check(_lib.lib().bn_update_posterior_grad(spec, N, ptr(dt), ptr(y), ptr(R), ptr(ell), ptr(means),
+                                                       ptr(covs), g[0].data_ptr(), g[1].data_ptr(), ptr(ws), nb,
+                                                       stream_ptr()))
+        return ell, means, covs, g
     _lib.check(_lib.lib().bn_update_posterior(spec, N, ptr(dt), ptr(y), ptr(R), ptr(mk), ptr(ell), ptr(means),
                                               ptr(covs), ptr(ws), nb, stream_ptr()))
     return ell, means, covs

@@ -16,6 +16,8 @@
  *   bn_rts_shard_*         (multi-GPU) two-level scan needs       ops.py:203-219, 328-335
  *   bn_update_posterior    MarkovGaussianProcess.update_posterior  basemodels.py:689-706 (filter + smoother fused)
  *   bn_up_shard_*          the same, on one time shard of a multi-GPU run
+ *   bn_update_posterior_grad   + d compute_log_lik / d kernel hyper-parameters (the reverse-mode pass of
+ *                          objax.GradValues(model.energy, ...), README.md:56-70; basemodels.py:726-741)
  *   bn_site_update         update_variational_params + newton_update + damped update_nat_params
  *                          inference.py:21-39,65-90,105-128,170-195,238-284,339-371; basemodels.py:85-100
  *   bn_expected_density    the value-only likelihood term of energy()
@@ -134,6 +136,21 @@ int bn_update_posterior(const bn_kernel_spec* k, int64_t N, const double* dt,
                         const double* pseudo_y, const double* pseudo_var, const uint8_t* mask,
                         double* ell, double* post_mean, double* post_cov,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* The same update plus the hyper-parameter gradient of the filter log-likelihood:
+ *   dell_dvariance[n_components], dell_dlengthscale[n_components] = d ell / d (variance_c, lengthscale_c)
+ * of the UNTRANSFORMED hyper-parameters (the host chains the softplus of kernels.py:80-95).  This is the
+ * only route from the kernel hyper-parameters to energy() in a temporal model, i.e. what
+ * objax.GradValues(model.energy, model.vars()) (README.md:56-70, demos/regression.py:63-70) back-propagates
+ * through compute_log_lik (basemodels.py:726-741) and the lax.scan of ops.py:154-180: d energy = -d ell.
+ * The adjoint of the predicted state of each step is formed in closed form from the smoothed state inside the
+ * smoother sweep (csrc/fast_core.cuh), so the gradient adds arithmetic but no HBM traffic.  No mask: the
+ * reference's mask rule (utils.py:376-396) drops masked densities from ell but keeps their updates, which this
+ * identity does not cover. */
+int bn_update_posterior_grad(const bn_kernel_spec* k, int64_t N, const double* dt,
+                             const double* pseudo_y, const double* pseudo_var,
+                             double* ell, double* post_mean, double* post_cov,
+                             double* dell_dvariance, double* dell_dlengthscale,
+                             void* workspace, size_t workspace_bytes, void* stream);
 /* The same update on a time shard (one rank of a multi-GPU run), in three phases around two carry
  * all-gathers.  All three calls of one update must be given the SAME workspace (it keeps the chunk
  * elements and the filtered states alive between phases).  dt here is the shard's slice of the
@@ -143,15 +160,19 @@ int bn_update_posterior(const bn_kernel_spec* k, int64_t N, const double* dt,
  *            one smoothing carry [bn_rts_carry_len(d)] mapping the state at this shard's last step
  *            to the state at the previous shard's last step (closed by the terminal element on the
  *            last rank, ops.py:314-315)
- *   smooth : rts_carries[world] -> local smoother pass, post_mean / post_cov of the local steps */
+ *   smooth : rts_carries[world] -> local smoother pass, post_mean / post_cov of the local steps
+ * want_grad (reduce, filter) and non-null dell_* (smooth: this shard's share of the hyper-gradient, to be
+ * summed over ranks) select the gradient-carrying chunk plan and must agree across the three calls. */
 int bn_up_shard_reduce(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* dt,
-                       const double* pseudo_y, const double* pseudo_var, double* kf_carry,
+                       const double* pseudo_y, const double* pseudo_var, double* kf_carry, int want_grad,
                        void* workspace, size_t workspace_bytes, void* stream);
 int bn_up_shard_filter(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* kf_carries,
                        const double* dt, const double* pseudo_y, const double* pseudo_var, const uint8_t* mask,
-                       double* ell, double* rts_carry, void* workspace, size_t workspace_bytes, void* stream);
+                       double* ell, double* rts_carry, int want_grad,
+                       void* workspace, size_t workspace_bytes, void* stream);
 int bn_up_shard_smooth(const bn_kernel_spec* k, int64_t N, int rank, int world, const double* rts_carries,
                        const double* dt, double* post_mean, double* post_cov,
+                       double* dell_dvariance, double* dell_dlengthscale,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- time-sharded (multi-GPU) scan: reduce -> exchange carries -> apply ------------------ */

@@ -78,8 +78,9 @@ def rts_smoother(lib, sp, form, dt, fm, fP, L=8, world=1, return_full=False):
     return sm, sP, G
 
 
-def update_posterior(lib, sp, dt, y, R, mask=None, L=8, world=1, want_ell=True):
-    """fused filter + smoother (csrc/up_impl.cuh): returns ell, post_mean [N,D,1], post_cov [N,D,D]"""
+def update_posterior(lib, sp, dt, y, R, mask=None, L=8, world=1, want_ell=True, want_grad=False):
+    """fused filter + smoother (csrc/up_impl.cuh): returns ell, post_mean [N,D,1], post_cov [N,D,D]
+    (+ d ell / d variance[NC], d ell / d lengthscale[NC] with want_grad)"""
     N = dt.shape[0]
     D = sp.n_components
     dt, y, R = (np.ascontiguousarray(a, dtype=np.float64) for a in (dt, y, R))
@@ -87,9 +88,13 @@ def update_posterior(lib, sp, dt, y, R, mask=None, L=8, world=1, want_ell=True):
     ell = np.zeros(1)
     pm = np.zeros((N, D, 1))
     pc = np.zeros((N, D, D))
+    dvar, dlen = np.zeros(D), np.zeros(D)
     rc = lib.emu_update_posterior(C.byref(sp), C.c_longlong(N), L, world, _p(dt), _p(y), _p(R), _p(mk),
-                                  _p(ell) if want_ell else None, _p(pm), _p(pc))
+                                  _p(ell) if want_ell else None, _p(pm), _p(pc),
+                                  _p(dvar) if want_grad else None, _p(dlen) if want_grad else None)
     assert rc == 0, rc
+    if want_grad:
+        return ell[0], pm, pc, dvar, dlen
     return ell[0], pm, pc
 
 

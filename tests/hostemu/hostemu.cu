@@ -129,7 +129,8 @@ static int emu_rts(MakeGen make, int form, long long N, int L, int world, const 
 // DirectCtx IO, host scans, the same tiled scratch layout, carry export and folds as up_run().
 template <class G>
 static int emu_up(const bn_kernel_spec* k, long long N, int L, int world, const double* dt, const double* y,
-                  const double* R, const unsigned char* mask, double* ell, double* pm, double* pc) {
+                  const double* R, const unsigned char* mask, double* ell, double* pm, double* pc,
+                  double* dvar = nullptr, double* dlen = nullptr) {
     constexpr int d = G::d, D = G::D;
     using FA = FilterAlg<d>;
     using SA = SmootherAlg<d>;
@@ -179,13 +180,27 @@ static int emu_up(const bn_kernel_spec* k, long long N, int L, int world, const 
                             scar.data() + (size_t)r * SA::kCarry);
     }
     if (ell) *ell = total;
+    if (dvar) for (int c = 0; c < G::NC; ++c) dvar[c] = dlen[c] = 0.0;
     for (int r = 0; r < world; ++r) {
         Rank& q = ranks[r];
         DirectCtx<D> cx{q.io};
         if (r != world - 1) fold_carries_body<SA>(scar.data(), world - 1, r, -1, q.sinit.data());
         else up_last_state<d>(q.n, L, q.fs.data(), q.sinit.data());
-        for (long long c = 0; c < q.nc; ++c)
-            up_smooth_chunk(g, cx, q.n, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, true);
+        if (dvar) {  // hyper-gradient: per-chunk fields -> per-rank sums -> chain rule; ranks add up (all-reduce)
+            constexpr int NF = GradAcc<G>::kFields;
+            std::vector<double> gpart((size_t)q.nc * NF, 0.0), fields(NF, 0.0);
+            for (long long c = 0; c < q.nc; ++c)
+                up_smooth_chunk<G, true>(g, cx, q.n, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, true,
+                                         r == 0, q.s0.data(), gpart.data());
+            for (int f = 0; f < NF; ++f)
+                for (long long c = 0; c < q.nc; ++c) fields[f] += gpart[(size_t)f * q.nc + c];
+            double dv[G::NC], dl[G::NC];
+            grad_finish<G>(*k, fields.data(), dv, dl);
+            for (int c = 0; c < G::NC; ++c) { dvar[c] += dv[c]; dlen[c] += dl[c]; }
+        } else {
+            for (long long c = 0; c < q.nc; ++c)
+                up_smooth_chunk<G, false>(g, cx, q.n, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, true);
+        }
     }
     return 0;
 }
@@ -333,10 +348,10 @@ extern "C" int emu_ep_pseudo_density(long long N, int D, double power, int with_
 
 extern "C" int emu_update_posterior(const bn_kernel_spec* k, long long N, int L, int world, const double* dt,
                                     const double* y, const double* R, const unsigned char* mask, double* ell,
-                                    double* post_mean, double* post_cov) {
+                                    double* post_mean, double* post_cov, double* dvar, double* dlen) {
 #define X(FAM, NC) \
     if (k->family == FAM && k->n_components == NC) \
-        return emu_up<FastGen<FAM, NC>>(k, N, L, world, dt, y, R, mask, ell, post_mean, post_cov);
+        return emu_up<FastGen<FAM, NC>>(k, N, L, world, dt, y, R, mask, ell, post_mean, post_cov, dvar, dlen);
     EMU_MATERN(X)
 #undef X
     return -1;
@@ -404,7 +419,8 @@ struct EmuRank : EmuRankBase {
         DirectCtx<D> cx{io};
         if (rank != world - 1) fold_carries_body<SA>(rts_carries, world - 1, rank, -1, sinit.data());
         else up_last_state<d>(n, L, fs.data(), sinit.data());
-        for (long long c = 0; c < nc; ++c) up_smooth_chunk(g, cx, n, L, nc, spre.data(), sinit.data(), fs.data(), c, true);
+        for (long long c = 0; c < nc; ++c)
+            up_smooth_chunk<G, false>(g, cx, n, L, nc, spre.data(), sinit.data(), fs.data(), c, true);
     }
 };
 

@@ -1,0 +1,217 @@
+"""Hyper-parameter gradient of the filter log-likelihood (the reverse-mode pass
+objax.GradValues(model.energy, model.vars()) runs through compute_log_lik, basemodels.py:726-741).
+
+CPU part: the oracle's three evaluations agree (literal reverse sweep of ops.py:154-180, the smoother
+identity the CUDA path uses, long-double central differences), and the product's __host__ __device__
+smoother body (tests/hostemu) reproduces them, single- and multi-shard.  GPU part: bn_update_posterior_grad
+and the sharded form through the C ABI against the oracle.  Tolerance: 1e-9 normwise (north_star); the
+finite-difference cross-check is looser by construction (truncation ~h^2)."""
+import numpy as np
+import pytest
+
+import _emu
+from _data import bench_inputs, classification_data, filter_problem
+from oracle import grad, model, sites, ssm
+
+TOL = 1e-9
+
+KERNELS = {
+    'm12': (1, lambda: ssm.Matern12(0.8, 1.7), [0.8], [1.7]),
+    'm32': (2, lambda: ssm.Matern32(1.1, 0.6), [1.1], [0.6]),
+    'm52': (3, lambda: ssm.Matern52(1.3, 0.9), [1.3], [0.9]),
+    'm72': (4, lambda: ssm.Matern72(0.7, 1.4), [0.7], [1.4]),
+    'ind32': (2, lambda: ssm.Independent([ssm.Matern32(1.0, 1.0), ssm.Matern32(0.5, 2.0)]), [1.0, 0.5], [1.0, 2.0]),
+    'ind52': (3, lambda: ssm.Independent([ssm.Matern52(1.3, 0.9), ssm.Matern52(0.7, 2.1)]), [1.3, 0.7], [0.9, 2.1]),
+}
+
+
+def gerr(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+
+
+def as_pairs(dvar, dlen):
+    """[variance_0, lengthscale_0, variance_1, ...] -- the oracle's ordering"""
+    return np.stack([np.asarray(dvar), np.asarray(dlen)], 1).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------ oracle pinning
+@pytest.mark.parametrize('name', sorted(KERNELS))
+def test_oracle_three_ways(name):
+    _, mk, vs, _ = KERNELS[name]
+    k = mk()
+    dt, y, R, mask = filter_problem(60, D=len(vs), seed=5)
+    ell_a, g_adj = grad.ell_grad_adjoint(k, dt, y, R)
+    ell_s, g_smo = grad.kf_grad_smoother(k, dt, y, R)
+    g_fd = grad.ell_grad_fd(k, dt, y, R)
+    assert abs(ell_a - ell_s) <= 1e-12 * abs(ell_a)
+    assert gerr(g_smo, g_adj) < 1e-11
+    assert gerr(g_adj, g_fd) < 1e-8       # long-double central differences, h = 1e-6
+    # the reverse sweep also covers the reference's mask rule (the smoother identity does not)
+    _, g_adj_m = grad.ell_grad_adjoint(k, dt, y, R, mask)
+    assert gerr(g_adj_m, grad.ell_grad_fd(k, dt, y, R, mask)) < 1e-8
+    assert gerr(g_adj_m, g_adj) > 1e-6    # ... and the mask does change the gradient
+
+
+def test_oracle_array_level_cotangents():
+    """kf_vjp w.r.t. As, Qs, ys, Rs, P0 against finite differences of _sequential_kf (ops.py:154-180)"""
+    from oracle import kalman
+    rng = np.random.default_rng(0)
+    N, d, D = 6, 3, 2
+    As = 0.6 * rng.standard_normal((N, d, d))
+    X = rng.standard_normal((N, d, d)); Qs = X @ X.transpose(0, 2, 1) + 0.1 * np.eye(d)
+    X = rng.standard_normal((N, D, D)); Rs = X @ X.transpose(0, 2, 1) + 0.5 * np.eye(D)
+    H = rng.standard_normal((D, d)); ys = rng.standard_normal((N, D, 1))
+    X = rng.standard_normal((d, d)); P0 = X @ X.T + np.eye(d); m0 = rng.standard_normal((d, 1))
+    masks = np.zeros((N, D, 1), dtype=bool)
+    _, bar = grad.kf_vjp(As, Qs, H, ys, Rs, m0, P0)
+
+    def ell(**kw):
+        a = dict(As=As, Qs=Qs, ys=ys, Rs=Rs, m0=m0, P0=P0); a.update(kw)
+        return kalman.sequential_kf(a['As'], a['Qs'], H, a['ys'], a['Rs'], a['m0'], a['P0'], masks)[0]
+
+    h = 1e-6
+    for name, arr, sym in (('As', As, False), ('Qs', Qs, True), ('ys', ys, False), ('Rs', Rs, True), ('P0', P0, True),
+                           ('m0', m0, False)):
+        dirn = rng.standard_normal(arr.shape)
+        if sym:
+            dirn = dirn + np.swapaxes(dirn, -1, -2)
+        fd = (ell(**{name: arr + h * dirn}) - ell(**{name: arr - h * dirn})) / (2 * h)
+        an = float(np.sum(bar[name] * dirn))
+        assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (name, fd, an)
+
+
+# ------------------------------------------------------------------------------------------ host emulation of the kernel body
+@pytest.mark.parametrize('name', sorted(KERNELS))
+@pytest.mark.parametrize('N,L,world', [(1, 8, 1), (7, 8, 1), (8, 8, 1), (9, 8, 1), (203, 8, 1), (203, 16, 3), (500, 8, 4),
+                                       (64, 8, 8)])
+def test_emulated_smoother_gradient(emu, name, N, L, world):
+    fam, mk, vs, ls = KERNELS[name]
+    k = mk()
+    dt, y, R, _ = filter_problem(N, D=len(vs), seed=N + 3)
+    ell0, g0 = grad.ell_grad_adjoint(k, dt, y, R)
+    ell1, pm, pc, dvar, dlen = _emu.update_posterior(emu, _emu.spec(fam, vs, ls), dt, y, R, L=L, world=world,
+                                                     want_grad=True)
+    assert abs(ell1 - ell0) <= TOL * abs(ell0)
+    assert gerr(as_pairs(dvar, dlen), g0) < TOL
+    # the gradient-carrying sweep returns the same posterior as the plain one
+    _, pm0, pc0 = _emu.update_posterior(emu, _emu.spec(fam, vs, ls), dt, y, R, L=L, world=world)
+    assert np.array_equal(pm, pm0) and np.array_equal(pc, pc0)
+
+
+def test_emulated_gradient_duplicate_time_stamps(emu):
+    """dt = 0 in mid-sequence (Q = 0, A = I): the transition contributes through P^- = P_{k-1} alone"""
+    fam, mk, vs, ls = KERNELS['m52']
+    dt, y, R, _ = filter_problem(40, D=1, seed=2)
+    dt[[5, 6, 17]] = 0.0
+    _, g0 = grad.ell_grad_adjoint(mk(), dt, y, R)
+    out = _emu.update_posterior(emu, _emu.spec(fam, vs, ls), dt, y, R, L=8, world=2, want_grad=True)
+    assert gerr(as_pairs(out[3], out[4]), g0) < TOL
+
+
+# ------------------------------------------------------------------------------------------ GPU, through the C ABI
+@pytest.fixture(scope='module')
+def bn():
+    import torch
+    assert torch.cuda.is_available(), 'the -m gpu tests need a CUDA device'
+    import bayesnewton_b200 as bn
+    return bn
+
+
+def gpu_kernels(bn):
+    K = bn.kernels
+    return {'m12': K.Matern12(0.8, 1.7), 'm32': K.Matern32(1.1, 0.6), 'm52': K.Matern52(1.3, 0.9),
+            'm72': K.Matern72(0.7, 1.4),
+            'ind32': K.Independent([K.Matern32(1.0, 1.0), K.Matern32(0.5, 2.0)]),
+            'ind52': K.Independent([K.Matern52(1.3, 0.9), K.Matern52(0.7, 2.1)])}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(KERNELS))
+@pytest.mark.parametrize('N', [1, 7, 203, 3001])
+def test_gpu_update_posterior_grad(bn, name, N):
+    _, mk, vs, _ = KERNELS[name]
+    dt, y, R, _ = filter_problem(N, D=len(vs), seed=N + 3)
+    ell0, g0 = grad.ell_grad_adjoint(mk(), dt, y, R)
+    kg = gpu_kernels(bn)[name]
+    ell1, m1, P1, g1 = bn.ops.update_posterior(dt, kg, y, R, want_ell=True, want_grad=True)
+    assert abs(float(ell1) - ell0) <= TOL * abs(ell0)
+    g1 = g1.cpu().numpy()
+    assert gerr(as_pairs(g1[0], g1[1]), g0) < TOL
+    _, m2, P2 = bn.ops.update_posterior(dt, kg, y, R, want_ell=False)
+    assert bool((m1 == m2).all()) and bool((P1 == P2).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['m52', 'ind32'])
+@pytest.mark.parametrize('shards', [2, 5])
+def test_gpu_sharded_grad(bn, name, shards):
+    from bayesnewton_b200 import distributed
+    _, mk, vs, _ = KERNELS[name]
+    N = 20011
+    dt, y, R, _ = filter_problem(N, D=len(vs), seed=9)
+    kg = gpu_kernels(bn)[name]
+    one = bn.ops.update_posterior(dt, kg, y, R, want_ell=True, want_grad=True)
+    out = distributed.update_posterior_in_shards(kg, dt, y, R, None, shards, want_grad=True)
+    g1, gs = one[3].cpu().numpy(), out['grad'].cpu().numpy()
+    assert gerr(gs, g1) < TOL
+    # against the oracle on a prefix-independent small case is covered above; here: large-N agreement with FD of ell
+    k = mk()
+    h = 1e-5
+    for c in range(len(vs)):
+        for which, row in ((0, 0), (1, 1)):
+            def ell_at(delta):
+                ks = kg.kernels if hasattr(kg, 'kernels') else [kg]
+                import copy
+                k2 = copy.deepcopy(kg)
+                kk = (k2.kernels if hasattr(k2, 'kernels') else [k2])[c]
+                if which == 0:
+                    kk.transformed_variance = bn.kernels.softplus_inv(kk.variance + delta)
+                else:
+                    kk.transformed_lengthscale = bn.kernels.softplus_inv(kk.lengthscale + delta)
+                return float(bn.ops.update_posterior(dt, k2, y, R, want_ell=True)[0])
+            fd = (ell_at(h) - ell_at(-h)) / (2 * h)
+            assert abs(fd - g1[row, c]) <= 2e-5 * max(1.0, abs(fd)), (c, which, fd, g1[row, c])
+
+
+@pytest.mark.gpu
+def test_gpu_model_energy_and_grad(bn):
+    """model level: MarkovVariationalGP (Bernoulli-probit) after one inference step; d energy = -d ell, served from
+    the closing posterior update of inference(want_grad=True), equal to a fresh evaluation and to the oracle"""
+    x, y = classification_data(400, seed=3)
+    g = bn.models.MarkovVariationalGP(kernel=bn.kernels.Matern52(1.2, 4.0), likelihood=bn.likelihoods.Bernoulli(),
+                                      X=x, Y=y, parallel=True)
+    o = model.MarkovGP(ssm.Matern52(1.2, 4.0), sites.Bernoulli(), x, y, method='vi')
+    g.inference(lr=0.7, want_grad=True)
+    o.inference(lr=0.7)
+    E, dE = g.energy_and_grad()
+    assert abs(float(E) - o.energy()) <= TOL * abs(o.energy())
+    _, g0 = grad.ell_grad_adjoint(o.kernel, o.dt, o.site_mean, o.site_cov)
+    dE = dE.cpu().numpy()
+    assert gerr(as_pairs(dE[0], dE[1]), -g0) < TOL
+    g._grad_cache = None
+    _, dE2 = g.energy_and_grad()
+    assert np.array_equal(dE2.cpu().numpy(), dE)
+
+
+@pytest.mark.gpu
+def test_gpu_grad_large_n_properties(bn):
+    """N = 10^7 (C2): shard-count independence of the gradient and agreement with a central difference of ell"""
+    from bayesnewton_b200 import distributed
+    import torch
+    N = 10_000_000
+    t, dt, yb = bench_inputs(N)
+    rng = np.random.default_rng(4)
+    y = rng.standard_normal((N, 1, 1))
+    R = (0.5 + rng.random((N, 1, 1)))
+    kg = bn.kernels.Matern52(1.0, 1.0)
+    dt_d, y_d, R_d = (torch.from_numpy(a).cuda() for a in (dt, y, R))
+    one = bn.ops.update_posterior(dt_d, kg, y_d, R_d, want_ell=True, want_grad=True)
+    out = distributed.update_posterior_in_shards(kg, dt_d, y_d, R_d, None, 3, want_grad=True)
+    g1, g3 = one[3].cpu().numpy(), out['grad'].cpu().numpy()
+    assert gerr(g3, g1) < TOL
+    h = 1e-6
+    for row, (dv, dl) in enumerate(((h, 0.0), (0.0, h))):
+        ep = float(bn.ops.update_posterior(dt_d, bn.kernels.Matern52(1.0 + dv, 1.0 + dl), y_d, R_d, want_ell=True)[0])
+        em = float(bn.ops.update_posterior(dt_d, bn.kernels.Matern52(1.0 - dv, 1.0 - dl), y_d, R_d, want_ell=True)[0])
+        fd = (ep - em) / (2 * h)
+        assert abs(fd - g1[row, 0]) <= 1e-5 * abs(fd), (row, fd, g1[row, 0])
