@@ -366,7 +366,7 @@ struct EmuRankBase {
     virtual int rts_len() = 0;
     virtual void reduce(const double* dt, const double* y, const double* R, double* carry) = 0;
     virtual void filter(const double* kf_carries, const unsigned char* mask, double* ell, double* rts_carry) = 0;
-    virtual void smooth(const double* rts_carries, double* pm, double* pc) = 0;
+    virtual void smooth(const double* rts_carries, double* pm, double* pc, double* dvar, double* dlen) = 0;
 };
 
 template <class G>
@@ -375,12 +375,14 @@ struct EmuRank : EmuRankBase {
     using FA = FilterAlg<d>;
     using SA = SmootherAlg<d>;
     G g;
+    bn_kernel_spec spec_;
     long long n, nc;
     int L, rank, world;
     UpIO io;
     std::vector<double> agg, fpre, sel, spre, fs, s0, sinit;
     EmuRank(const bn_kernel_spec* k, long long n_, int L_, int rank_, int world_) : n(n_), L(L_), rank(rank_), world(world_) {
         g.prepare(*k);
+        spec_ = *k;
         nc = (n + L - 1) / L;
         agg.assign((size_t)nc * FA::kElem, 0.0);
         fpre = agg;
@@ -413,14 +415,25 @@ struct EmuRank : EmuRankBase {
         host_scan<SA>(sel.data(), nc, spre.data());
         up_export_scarry<d>(spre.data(), nc, rank == world - 1, n, L, fs.data(), rts_carry);
     }
-    void smooth(const double* rts_carries, double* pm, double* pc) override {
+    void smooth(const double* rts_carries, double* pm, double* pc, double* dvar, double* dlen) override {
         io.post_mean = pm;
         io.post_cov = pc;
         DirectCtx<D> cx{io};
         if (rank != world - 1) fold_carries_body<SA>(rts_carries, world - 1, rank, -1, sinit.data());
         else up_last_state<d>(n, L, fs.data(), sinit.data());
+        if (!dvar) {
+            for (long long c = 0; c < nc; ++c)
+                up_smooth_chunk<G, false>(g, cx, n, L, nc, spre.data(), sinit.data(), fs.data(), c, true);
+            return;
+        }
+        constexpr int NF = GradAcc<G>::kFields;  // this rank's share of the hyper-gradient (summed over ranks by the caller)
+        std::vector<double> gpart((size_t)nc * NF, 0.0), fields(NF, 0.0);
         for (long long c = 0; c < nc; ++c)
-            up_smooth_chunk<G, false>(g, cx, n, L, nc, spre.data(), sinit.data(), fs.data(), c, true);
+            up_smooth_chunk<G, true>(g, cx, n, L, nc, spre.data(), sinit.data(), fs.data(), c, true, rank == 0,
+                                     s0.data(), gpart.data());
+        for (int f = 0; f < NF; ++f)
+            for (long long c = 0; c < nc; ++c) fields[f] += gpart[(size_t)f * nc + c];
+        grad_finish<G>(spec_, fields.data(), dvar, dlen);
     }
 };
 
@@ -442,6 +455,6 @@ extern "C" void emu_rank_filter(void* h, const double* kf_carries, const unsigne
                                 double* rts_carry) {
     ((EmuRankBase*)h)->filter(kf_carries, mask, ell, rts_carry);
 }
-extern "C" void emu_rank_smooth(void* h, const double* rts_carries, double* pm, double* pc) {
-    ((EmuRankBase*)h)->smooth(rts_carries, pm, pc);
+extern "C" void emu_rank_smooth(void* h, const double* rts_carries, double* pm, double* pc, double* dvar, double* dlen) {
+    ((EmuRankBase*)h)->smooth(rts_carries, pm, pc, dvar, dlen);
 }

@@ -31,7 +31,7 @@ class EmuShard:
         emu.emu_rank_kf_len.argtypes = emu.emu_rank_rts_len.argtypes = [C.c_void_p]
         emu.emu_rank_reduce.argtypes = [C.c_void_p] * 5
         emu.emu_rank_filter.argtypes = [C.c_void_p] * 5
-        emu.emu_rank_smooth.argtypes = [C.c_void_p] * 4
+        emu.emu_rank_smooth.argtypes = [C.c_void_p] * 6
         self.h = emu.emu_rank_new(C.addressof(spec), self.N, L, rank, world)
         assert self.h
         self.kf_len, self.rts_len = emu.emu_rank_kf_len(self.h), emu.emu_rank_rts_len(self.h)
@@ -41,14 +41,14 @@ class EmuShard:
     def _np(t):
         return np.ascontiguousarray(t.numpy() if torch.is_tensor(t) else t, dtype=np.float64)
 
-    def up_reduce(self, y, R):
+    def up_reduce(self, y, R, want_grad=False):
         y, R = self._np(y), self._np(R)
         self.keep = [y, R]
         carry = np.zeros(self.kf_len)
         self.emu.emu_rank_reduce(self.h, self.dt.ctypes.data, y.ctypes.data, R.ctypes.data, carry.ctypes.data)
         return torch.from_numpy(carry)
 
-    def up_filter(self, kf_carries, y, R, mask=None, want_ell=True):
+    def up_filter(self, kf_carries, y, R, mask=None, want_ell=True, want_grad=False):
         kc = self._np(kf_carries)
         mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         ell, carry = np.zeros(1), np.zeros(self.rts_len)
@@ -56,10 +56,14 @@ class EmuShard:
                                  carry.ctypes.data)
         return torch.from_numpy(ell)[0], torch.from_numpy(carry)
 
-    def up_smooth(self, rts_carries):
+    def up_smooth(self, rts_carries, want_grad=False):
         rc = self._np(rts_carries)
         pm, pc = np.zeros((self.N, self.D, 1)), np.zeros((self.N, self.D, self.D))
-        self.emu.emu_rank_smooth(self.h, rc.ctypes.data, pm.ctypes.data, pc.ctypes.data)
+        g = np.zeros((2, self.D))
+        self.emu.emu_rank_smooth(self.h, rc.ctypes.data, pm.ctypes.data, pc.ctypes.data,
+                                 g[0].ctypes.data if want_grad else None, g[1].ctypes.data if want_grad else None)
+        if want_grad:
+            return torch.from_numpy(pm), torch.from_numpy(pc), torch.from_numpy(g)
         return torch.from_numpy(pm), torch.from_numpy(pc)
 
 
@@ -81,7 +85,11 @@ def _worker(rank, world, port, fam, vs, ls, N, seed, out):
     ell, sm, sP = distributed.sharded_update_posterior(shard, y[lo:hi], R[lo:hi], mask[lo:hi], want_ell=True)
     tot = ell.clone().reshape(1)
     dist.all_reduce(tot)  # the scalar all-reduce of TimeShardedMarkovGP.energy
-    out[rank] = (float(tot[0]), sm.numpy().copy(), sP.numpy().copy())
+    # the hyper-gradient pass of the same update (no mask): local shares, one all-reduce
+    _, sm2, sP2, g = distributed.sharded_update_posterior(shard, y[lo:hi], R[lo:hi], None, want_ell=True, want_grad=True)
+    g = g.clone()
+    dist.all_reduce(g)
+    out[rank] = (float(tot[0]), sm.numpy().copy(), sP.numpy().copy(), g.numpy().copy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -106,3 +114,8 @@ def test_two_rank_gloo_sharded_update(fam, vs, ls):
     pm = np.concatenate([out[0][1], out[1][1]])
     pc = np.concatenate([out[0][2], out[1][2]])
     assert rel_err(pm, sm) < 1e-9 and rel_err(pc, sP) < 1e-9
+    from oracle import grad
+    _, g0 = grad.ell_grad_adjoint(k, dt, y, R)
+    for r in range(world):
+        g = out[r][3]  # [2, NC] -> the oracle's (variance_c, lengthscale_c) pairs
+        assert rel_err(np.stack([g[0], g[1]], 1).reshape(-1), g0) < 1e-9
