@@ -57,7 +57,7 @@ def test_gpu_xla_update_posterior(bn, want_grad):
     import torch
     from _data import filter_problem
     from bayesnewton_b200 import _lib, xla
-    from bayesnewton_b200._util import as_dev, stream_ptr
+    from bayesnewton_b200._util import as_dev, as_mask, stream_ptr
     N = 5003
     dt, y, R, mask = filter_problem(N, D=1, seed=1)
     k = bn.kernels.Matern52(1.3, 0.9)
@@ -65,7 +65,7 @@ def test_gpu_xla_update_posterior(bn, want_grad):
     spec = k.spec()
     nb = _lib.lib().bn_update_posterior_workspace_bytes(spec, N)
     dev = ref[1].device
-    ins = [as_dev(dt), as_dev(y), as_dev(R)] + ([] if want_grad else [as_dev(mask.astype(np.uint8))])
+    ins = [as_dev(dt), as_dev(y), as_dev(R)] + ([] if want_grad else [as_mask(mask)])
     outs = [torch.zeros((), dtype=torch.float64, device=dev), torch.empty_like(ref[1]), torch.empty_like(ref[2])]
     if want_grad:
         outs += [torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.float64, device=dev)]
@@ -85,7 +85,7 @@ def test_gpu_xla_filter_smoother_sites(bn):
     import torch
     from _data import classification_data, filter_problem
     from bayesnewton_b200 import _lib, xla
-    from bayesnewton_b200._util import as_dev, stream_ptr, workspace
+    from bayesnewton_b200._util import as_dev, as_mask, stream_ptr, workspace
     L = _lib.lib()
     N = 3001
     dt, y, R, mask = filter_problem(N, D=1, seed=2)
@@ -96,7 +96,7 @@ def test_gpu_xla_filter_smoother_sites(bn):
     nb = L.bn_workspace_bytes(N, 2, 1)
     outs = [torch.zeros((), dtype=torch.float64, device=dev), torch.empty_like(fm), torch.empty_like(fP),
             torch.empty(nb, dtype=torch.uint8, device=dev)]
-    ins = [as_dev(dt), as_dev(y), as_dev(R), as_dev(mask.astype(np.uint8))]
+    ins = [as_dev(dt), as_dev(y), as_dev(R), as_mask(mask)]
     e0 = xla.error_count()
     xla.call('bn_xla_kalman_filter', stream_ptr(), [t.data_ptr() for t in ins + outs],
              xla.markov_desc(spec, N, nb, has_mask=True))
