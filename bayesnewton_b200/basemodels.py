@@ -60,9 +60,17 @@ class MarkovGaussianProcess:
     method = None   # BN_METHOD_*, set by the inference mixin
     power = 1.0
 
+    def __new__(cls, kernel=None, *args, **kwargs):
+        # spatio-temporal inputs take the dense path: the overrides of spacetime.SpatioTemporalMixin go in front
+        if hasattr(kernel, 'temporal_kernel'):
+            from .spacetime import SpatioTemporalMixin
+            if not issubclass(cls, SpatioTemporalMixin):
+                cls = type(cls.__name__, (SpatioTemporalMixin, cls), {})
+        return object.__new__(cls)
+
     def __init__(self, kernel, likelihood, X, Y, R=None, parallel=None):
         if R is not None:
-            raise NotImplementedError('spatio-temporal inputs are outside the current hot-path scope')
+            raise NotImplementedError('spatial inputs need a SpatioTemporalKernel')
         if parallel is None:  # the reference switches the scan on when it runs on a GPU (basemodels.py:642-643)
             parallel = True
         self.kernel, self.likelihood, self.parallel = kernel, likelihood, parallel

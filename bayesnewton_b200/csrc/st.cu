@@ -1,0 +1,1019 @@
+// Dense spatio-temporal path: Kalman filter, RTS smoother and the
+// projection steps either side of them for SpatioTemporalKernel (bayesnewton/kernels.py:385-586):
+//     state x = [u_1; ...; u_M], u_i the n-dimensional temporal state of spatial inducing point i,
+//     A_k = I_M (x) A_t(dt_k),  Pinf = I_M (x) Pinf_t,  H = I_M (x) H_t   (d = M n, D = M).
+// The state covariance is a dense d x d matrix (d = 512 at C4), so one time step is a Cholesky
+// factorisation plus a few d^3 contractions; time stays sequential (the reference's lax.scan,
+// ops.py:154-180, 288-311) and the parallelism is INSIDE the step:
+//
+//   * one persistent kernel per pass, one CTA per SM, the whole time loop inside the kernel; the
+//     phases of a step are separated by a grid barrier (an L2 atomic counter), not by launches;
+//   * the Kronecker structure is never multiplied out: predict is a per-(n x n)-block rotation;
+//   * every solve of the step rides on ONE blocked Cholesky: the matrices that need L^-T applied
+//     from the right (P^- H^T, the residual, an identity for L^-1, ...) are stacked under the SPD
+//     matrix and swept by the same left-looking panels (32 columns per phase), so their rows are
+//     extra parallelism for the panel phase instead of extra triangular solves after it;
+//   * the remaining work is C = A B^T tiles (NT form only), fp64 FMA from shared-memory tiles.
+//
+// The batched projection steps (compute_full_pseudo_lik, basemodels.py:676-687, and the Gaussian
+// KL term) use the same panel code with one CTA per time step.
+#include "common.cuh"
+#include "gen.cuh"
+
+namespace bn {
+namespace st {
+
+constexpr int NB = 32;     // panel width = row-block height
+constexpr int NTH = 256;   // threads per CTA
+constexpr int BK = 16;     // k-slab of the tile product
+
+__host__ __device__ inline int pad32(int x) { return (x + 31) / 32 * 32; }
+
+__device__ __forceinline__ double ldg(const double* p) { return __ldcg(p); }  // L2: data other CTAs wrote in this kernel
+
+struct Smem {
+    double a[BK][65];      // A slab, k-major (odd pitch: conflict-free transposing stores)
+    double b[BK][65];
+    double L[NB][NB + 1];  // diagonal block / its Cholesky factor
+    double Li[NB][NB + 1]; // inverse of the factor (lower)
+    double X[NB][NB + 1];  // right-hand block before the triangular solve
+};
+
+// ---- grid barrier ---------------------------------------------------------------------------------
+// All CTAs are co-resident (grid <= number of SMs, checked on the host).  The counter only grows; the
+// host zeroes it before the launch.
+struct GridSync {
+    unsigned long long* ctr;
+    unsigned long long epoch;
+    __device__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            epoch += gridDim.x;
+            __threadfence();
+            atomicAdd(ctr, 1ULL);
+            while (*((volatile unsigned long long*)ctr) < epoch) { }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+};
+
+// ---- C tile = A B^T ---------------------------------------------------------------------------------
+// acc[r][c] (rows i0 + ty + 16 r, cols j0 + tx + 16 c) = sum_{k<K} A[row][k] * (SCALE ? s[k] : 1) * B[col][k]
+// rows >= arows / brows and k >= K read as zero.  TM, TN in {32, 64}.
+template <int TM, int TN, bool SCALE>
+__device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, int arows, const double* __restrict__ B,
+                                        int ldb, int brows, int K, int i0, int j0, const double* __restrict__ s,
+                                        double (&acc)[TM / 16][TN / 16], Smem& sm) {
+    constexpr int RM = TM / 16, RN = TN / 16;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+#pragma unroll
+        for (int c = 0; c < RN; ++c) acc[r][c] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        __syncthreads();
+        const int kk = k0 + tx;
+        const double sc = (SCALE && kk < K) ? ldg(s + kk) : 1.0;
+#pragma unroll
+        for (int r = 0; r < TM / 16; ++r) {
+            const int row = i0 + ty + 16 * r;
+            sm.a[tx][ty + 16 * r] = (row < arows && kk < K) ? ldg(A + (size_t)row * lda + kk) * sc : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < TN / 16; ++r) {
+            const int row = j0 + ty + 16 * r;
+            sm.b[tx][ty + 16 * r] = (row < brows && kk < K) ? ldg(B + (size_t)row * ldb + kk) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            double av[RM], bv[RN];
+#pragma unroll
+            for (int r = 0; r < RM; ++r) av[r] = sm.a[k][ty + 16 * r];
+#pragma unroll
+            for (int c = 0; c < RN; ++c) bv[c] = sm.b[k][tx + 16 * c];
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+#pragma unroll
+                for (int c = 0; c < RN; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+        }
+    }
+}
+
+// ---- stacked blocked Cholesky ---------------------------------------------------------------------------
+// T: rows x n (row-major, ld = n, both multiples of 32).  Rows [0,n) hold an SPD matrix S (lower triangle
+// used), the rows below hold stacked right-hand sides Wstack.  After panels 0..n/32-1:
+//     T[0:n] lower triangle = L (S = L L^T),   T[n:] = Wstack L^-T.
+// Left-looking: panel j first brings block column j up to date with the j finished block columns
+// to its left, then factors the diagonal block and applies its inverse to the blocks below.
+
+// D_j = S_jj - sum_{p<j} L_jp L_jp^T  ->  sm.L = chol(D_j), sm.Li = its inverse.  All threads call.
+__device__ void panel_factor(const double* T, int ld, int j, Smem& sm) {
+    double acc[2][2];
+    const double* rowj = T + (size_t)j * NB * ld;
+    tile_nt<32, 32, false>(rowj, ld, NB, rowj, ld, NB, j * NB, 0, 0, nullptr, acc, sm);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int rr = ty + 16 * r, cc = tx + 16 * c;
+            sm.L[rr][cc] = ldg(rowj + (size_t)rr * ld + j * NB + cc) - acc[r][c];
+        }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int r = threadIdx.x;
+        // Cholesky-Crout by columns; lane r owns row r.  A non-positive pivot gives NaN (cho_factor).
+        for (int c = 0; c < NB; ++c) {
+            double s0 = sm.L[r][c], s1 = 0.0;
+            int q = 0;
+            for (; q + 1 < c; q += 2) {
+                s0 = fma(-sm.L[r][q], sm.L[c][q], s0);
+                s1 = fma(-sm.L[r][q + 1], sm.L[c][q + 1], s1);
+            }
+            if (q < c) s0 = fma(-sm.L[r][q], sm.L[c][q], s0);
+            const double s = s0 + s1;
+            const double piv = __shfl_sync(0xffffffffu, s, c);
+            const double lcc = sqrt(piv);  // NaN for piv < 0
+            const double inv = 1.0 / lcc;
+            __syncwarp();
+            sm.L[r][c] = (r == c) ? lcc : (r > c ? s * inv : 0.0);
+            __syncwarp();
+        }
+        // Li = L^-1 (lower): lane cc solves L x = e_cc by forward substitution
+        const int cc = threadIdx.x;
+        double x[NB];
+#pragma unroll
+        for (int rr = 0; rr < NB; ++rr) {
+            double s0 = (rr == cc) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+            for (int q = 0; q + 1 < rr; q += 2) {
+                s0 = fma(-sm.L[rr][q], x[q], s0);
+                s1 = fma(-sm.L[rr][q + 1], x[q + 1], s1);
+            }
+            if (rr & 1) s0 = fma(-sm.L[rr][rr - 1], x[rr - 1], s0);
+            x[rr] = (s0 + s1) / sm.L[rr][rr];
+        }
+#pragma unroll
+        for (int rr = 0; rr < NB; ++rr) sm.Li[rr][cc] = x[rr];
+    }
+    __syncthreads();
+}
+
+// row block i of panel j: T[i, j] <- (T[i, j] - sum_{p<j} T[i, p] L_jp^T) L_jj^-T   (i != j);  T[j, j] <- L_jj
+__device__ void panel_apply(double* T, int ld, int j, int i, Smem& sm) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double* out = T + (size_t)i * NB * ld + j * NB;
+    if (i == j) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) out[(size_t)(ty + 16 * r) * ld + tx + 16 * c] = sm.L[ty + 16 * r][tx + 16 * c];
+        return;
+    }
+    double acc[2][2];
+    tile_nt<32, 32, false>(T + (size_t)i * NB * ld, ld, NB, T + (size_t)j * NB * ld, ld, NB, j * NB, 0, 0, nullptr, acc, sm);
+    __syncthreads();  // sm.X may still be read by the previous row block's solve
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int rr = ty + 16 * r, cc = tx + 16 * c;
+            sm.X[rr][cc] = ldg(out + (size_t)rr * ld + cc) - acc[r][c];
+        }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int rr = ty + 16 * r, cc = tx + 16 * c;
+            double s = 0.0;
+            for (int q = 0; q <= cc; ++q) s = fma(sm.X[rr][q], sm.Li[cc][q], s);
+            out[(size_t)rr * ld + cc] = s;
+        }
+}
+
+// all panels, row blocks spread over the CTAs of the grid (one grid barrier per panel).  An optional second,
+// independent system of the same width (T2: the masked innovation covariance of the log-likelihood) is swept in
+// the same phases by the last quarter of the grid.
+__device__ void chol_stack_grid(double* T, int n, int rows, double* T2, int rows2, Smem& sm, GridSync& gs) {
+    const int nsq = n / NB, ntot = rows / NB, ntot2 = T2 ? rows2 / NB : 0;
+    const int G = gridDim.x;
+    const int G2 = T2 ? (G / 4 > 0 ? G / 4 : 1) : 0, G1 = G - G2;
+    for (int j = 0; j < nsq; ++j) {
+        const int b = blockIdx.x;
+        if (b < G1) {
+            const int nact = ntot - j;  // row blocks j .. ntot-1
+            if (b < nact) {
+                panel_factor(T, n, j, sm);
+                for (int a = b; a < nact; a += G1) panel_apply(T, n, j, j + a, sm);
+            }
+        } else {
+            const int nact = ntot2 - j, b2 = b - G1;
+            if (b2 < nact) {
+                panel_factor(T2, n, j, sm);
+                for (int a = b2; a < nact; a += G2) panel_apply(T2, n, j, j + a, sm);
+            }
+        }
+        gs.sync();
+    }
+}
+
+// all panels inside one CTA (batched problems: one CTA per matrix)
+__device__ void chol_stack_cta(double* T, int n, int rows, Smem& sm) {
+    const int nsq = n / NB, ntot = rows / NB;
+    for (int j = 0; j < nsq; ++j) {
+        panel_factor(T, n, j, sm);
+        for (int i = j; i < ntot; ++i) panel_apply(T, n, j, i, sm);
+        __syncthreads();
+        __threadfence_block();
+    }
+}
+
+// ---- temporal block of the discretisation ----------------------------------------------------------------
+template <int FAM>
+struct TBlock {
+    static constexpr int n = FamilyDim<FAM>::value;
+    double A[n * n], Q[n * n], Pinf[n * n];
+    __device__ void init(const bn_kernel_spec& sp, double h) {
+        double Pp[symn(n)], X[n * n];
+        MaternBlock<FAM, double>::transition(sp.lengthscale[0], h, A);
+        MaternBlock<FAM, double>::pinf(sp.variance[0], sp.lengthscale[0], Pp);
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) Pinf[i * n + j] = Pp[sidx(i > j ? i : j, i > j ? j : i)];
+        // Q = Pinf - A Pinf A^T (ops.py:149-151)
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int l = 0; l < n; ++l) s = fma(A[i * n + l], Pinf[l * n + j], s);
+                X[i * n + j] = s;
+            }
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int l = 0; l < n; ++l) s = fma(X[i * n + l], A[j * n + l], s);
+                Q[i * n + j] = Pinf[i * n + j] - s;
+            }
+    }
+    // out = A B A^T (+ Q on diagonal blocks)
+    __device__ void rotate(const double* B, bool diag, double* out) const {
+        double X[n * n];
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int l = 0; l < n; ++l) s = fma(A[i * n + l], B[l * n + j], s);
+                X[i * n + j] = s;
+            }
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                double s = diag ? Q[i * n + j] : 0.0;
+#pragma unroll
+                for (int l = 0; l < n; ++l) s = fma(X[i * n + l], A[j * n + l], s);
+                out[i * n + j] = s;
+            }
+    }
+};
+
+// ---- filter ----------------------------------------------------------------------------------------------
+struct FilterArgs {
+    bn_kernel_spec spec;
+    int M;
+    long long N;
+    const double* dt;
+    const double* y;      // [N,M]
+    const double* R;      // [N,M,M]
+    const uint8_t* mask;  // [N,M] nullable
+    int return_predict;
+    double* ell;          // nullable
+    double* means;        // [N,d]
+    double* covs;         // [N,d,d]
+    double* T;            // [(Mp + dp + 32) x Mp]
+    double* T2;           // [(Mp + 32) x Mp]   masked system of the log-likelihood (mask != null)
+    double* Pcur;         // [d,d]   filtered covariance of the previous step when return_predict
+    double* mcur;         // [d]
+    double* ellacc;       // 1
+    unsigned long long* ctr;
+};
+
+template <int FAM>
+__global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
+    constexpr int n = FamilyDim<FAM>::value;
+    __shared__ Smem sm;
+    GridSync gs{a.ctr, 0ULL};
+    const int M = a.M, d = M * n, Mp = pad32(M), dp = pad32(d);
+    const int rows = Mp + dp + NB;
+    const long long tid = (long long)blockIdx.x * NTH + threadIdx.x, nthreads = (long long)gridDim.x * NTH;
+    double* T = a.T;
+    // padding of the stacked matrix: identity on the padded diagonal, zero elsewhere (the sweeps keep it so)
+    for (long long e = tid; e < (long long)rows * Mp; e += nthreads) {
+        const int r = (int)(e / Mp), c = (int)(e % Mp);
+        T[e] = (r == c && r >= M) ? 1.0 : 0.0;
+    }
+    double* T2 = a.mask ? a.T2 : nullptr;
+    const int rows2 = Mp + NB;
+    if (T2)
+        for (long long e = tid; e < (long long)rows2 * Mp; e += nthreads) {
+            const int r = (int)(e / Mp), c = (int)(e % Mp);
+            T2[e] = (r == c && r >= M) ? 1.0 : 0.0;
+        }
+    double ell_reg = 0.0;  // lives in lane 0 of warp 0 of the last CTA
+    gs.sync();
+    for (long long k = 0; k < a.N; ++k) {
+        // ---- predict + assemble: P^- = A P A^T + Q -> covs[k];  T = [H P^- H^T + R ; P^- H^T ; (y - H m^-)^T]
+        TBlock<FAM> tb;
+        tb.init(a.spec, a.dt[k]);
+        const double* Pprev = a.return_predict ? a.Pcur : a.covs + (size_t)(k > 0 ? k - 1 : 0) * d * d;
+        const double* mprev = a.return_predict ? a.mcur : a.means + (size_t)(k > 0 ? k - 1 : 0) * d;
+        double* Pk = a.covs + (size_t)k * d * d;
+        double* mk = a.means + (size_t)k * d;
+        const double* Rk = a.R + (size_t)k * M * M;
+        for (long long e = tid; e < (long long)M * M; e += nthreads) {
+            const int i = (int)(e / M), j = (int)(e % M);
+            double B[n * n], O[n * n];
+#pragma unroll
+            for (int p = 0; p < n; ++p)
+#pragma unroll
+                for (int q = 0; q < n; ++q)
+                    B[p * n + q] = (k == 0) ? (i == j ? tb.Pinf[p * n + q] : 0.0) : ldg(Pprev + (size_t)(i * n + p) * d + j * n + q);
+            tb.rotate(B, i == j, O);
+#pragma unroll
+            for (int p = 0; p < n; ++p)
+#pragma unroll
+                for (int q = 0; q < n; ++q) Pk[(size_t)(i * n + p) * d + j * n + q] = O[p * n + q];
+            const double Sij = O[0] + Rk[(size_t)i * M + j];
+            T[(size_t)i * Mp + j] = Sij;
+            if (T2) {  // mvn_logpdf with a mask (utils.py:382-388): masked rows/columns independent, variance 1/(2 pi)
+                const bool mi = a.mask[(size_t)k * M + i] != 0, mj = a.mask[(size_t)k * M + j] != 0;
+                T2[(size_t)i * Mp + j] = (mi || mj) ? ((i == j) ? 0.15915494309189535 : 0.0) : Sij;
+            }
+#pragma unroll
+            for (int p = 0; p < n; ++p) T[(size_t)(Mp + i * n + p) * Mp + j] = O[p * n];
+        }
+        for (long long i = tid; i < M; i += nthreads) {
+            double mp[n];
+#pragma unroll
+            for (int p = 0; p < n; ++p) {
+                double s = 0.0;
+                if (k > 0) {
+#pragma unroll
+                    for (int q = 0; q < n; ++q) s = fma(tb.A[p * n + q], ldg(mprev + i * n + q), s);
+                }
+                mp[p] = s;
+                mk[i * n + p] = s;
+            }
+            const double res = a.y[(size_t)k * M + i] - mp[0];
+            T[(size_t)(Mp + dp) * Mp + i] = res;
+            if (T2) T2[(size_t)Mp * Mp + i] = a.mask[(size_t)k * M + i] ? 0.0 : res;
+        }
+        gs.sync();
+        // ---- S = L L^T;  X = P^- H^T L^-T;  z = L^-1 (y - H m^-)
+        chol_stack_grid(T, Mp, rows, T2, rows2, sm, gs);
+        // ---- P = P^- - X X^T;  m = m^- + X z;  ell += log N(y | H m^-, S)   (ops.py:163-172)
+        const double* X = T + (size_t)Mp * Mp;
+        const double* z = T + (size_t)(Mp + dp) * Mp;
+        double* Pout = a.return_predict ? a.Pcur : Pk;
+        double* mout = a.return_predict ? a.mcur : mk;
+        const int tm = (d + 31) / 32, tn = (d + 63) / 64;
+        for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
+            const int i0 = (t / tn) * 32, j0 = (t % tn) * 64;
+            double acc[2][4];
+            tile_nt<32, 64, false>(X, Mp, d, X, Mp, d, Mp, i0, j0, nullptr, acc, sm);
+            const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    if (row < d && col < d) Pout[(size_t)row * d + col] = ldg(Pk + (size_t)row * d + col) - acc[r][c];
+                }
+        }
+        {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            for (int row = blockIdx.x * (NTH / 32) + warp; row < d; row += gridDim.x * (NTH / 32)) {
+                double s = 0.0;
+                for (int c = lane; c < M; c += 32) s = fma(ldg(X + (size_t)row * Mp + c), ldg(z + c), s);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lane == 0) mout[row] = ldg(mk + row) + s;
+            }
+            if (blockIdx.x == gridDim.x - 1 && warp == 0) {
+                double q = 0.0, ld = 0.0;
+                const double* Tl = T2 ? T2 : T;
+                const double* zl = T2 ? T2 + (size_t)Mp * Mp : z;
+                for (int c = lane; c < M; c += 32) {
+                    const double zc = ldg(zl + c);
+                    q = fma(zc, zc, q);
+                    ld += log(ldg(Tl + (size_t)c * Mp + c));
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    q += __shfl_xor_sync(0xffffffffu, q, off);
+                    ld += __shfl_xor_sync(0xffffffffu, ld, off);
+                }
+                if (lane == 0) ell_reg += -0.5 * (q + M * 1.8378770664093453 + 2.0 * ld);
+            }
+        }
+        gs.sync();
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && a.ell) *a.ell = ell_reg;
+}
+
+// ---- smoother ----------------------------------------------------------------------------------------------
+struct SmootherArgs {
+    bn_kernel_spec spec;
+    int M;
+    long long N;
+    const double* dt;     // step OUT OF k (basemodels.py:700)
+    const double* fm;     // [N,d]
+    const double* fP;     // [N,d,d]
+    int return_full;
+    double* means;        // [N,M] or [N,d]
+    double* covs;         // [N,M,M] or [N,d,d]
+    double* gains;        // [N,d,d] nullable
+    double* T;            // [(3 dp + 32) x dp]
+    double* sP[2];        // ping-pong full smoothed covariance [d,d]
+    double* smv[2];       // ping-pong full smoothed mean [d]
+    double* G;            // [d,d]
+    double* Dm;           // [d,d]  sP_next - P^-
+    double* Z;            // [d,d]
+    unsigned long long* ctr;
+};
+
+template <int FAM>
+__global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
+    constexpr int n = FamilyDim<FAM>::value;
+    __shared__ Smem sm;
+    GridSync gs{a.ctr, 0ULL};
+    const int M = a.M, d = M * n, dp = pad32(d);
+    const int rows = 3 * dp + NB;
+    const long long tid = (long long)blockIdx.x * NTH + threadIdx.x, nthreads = (long long)gridDim.x * NTH;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double* T = a.T;
+    for (long long e = tid; e < (long long)rows * dp; e += nthreads) {
+        const int r = (int)(e / dp), c = (int)(e % dp);
+        T[e] = (r == c && r >= d && r < dp) ? 1.0 : 0.0;
+    }
+    // the recursion starts from the last filtered state (ops.py:304-305)
+    for (long long e = tid; e < (long long)d * d; e += nthreads) a.sP[1][e] = a.fP[(size_t)(a.N - 1) * d * d + e];
+    for (long long e = tid; e < d; e += nthreads) a.smv[1][e] = a.fm[(size_t)(a.N - 1) * d + e];
+    gs.sync();
+    int cur = 1;  // buffer holding step k+1
+    for (long long k = a.N - 1; k >= 0; --k) {
+        TBlock<FAM> tb;
+        tb.init(a.spec, a.dt[k]);
+        const double* fPk = a.fP + (size_t)k * d * d;
+        const double* fmk = a.fm + (size_t)k * d;
+        const double* sPn = a.sP[cur];
+        const double* smn = a.smv[cur];
+        double* sPo = a.sP[cur ^ 1];
+        double* smo = a.smv[cur ^ 1];
+        // ---- T = [P^- ; fP A^T ; I ; (sm_next - A fm)^T],  Dm = sP_next - P^-
+        for (long long e = tid; e < (long long)M * M; e += nthreads) {
+            const int i = (int)(e / M), j = (int)(e % M);
+            double B[n * n], O[n * n];
+#pragma unroll
+            for (int p = 0; p < n; ++p)
+#pragma unroll
+                for (int q = 0; q < n; ++q) B[p * n + q] = fPk[(size_t)(i * n + p) * d + j * n + q];
+            tb.rotate(B, i == j, O);
+#pragma unroll
+            for (int p = 0; p < n; ++p)
+#pragma unroll
+                for (int q = 0; q < n; ++q) {
+                    const size_t r = i * n + p, c = j * n + q;
+                    T[r * dp + c] = O[p * n + q];
+                    a.Dm[r * d + c] = ldg(sPn + r * d + c) - O[p * n + q];
+                    double s = 0.0;  // (fP A^T)[r][c] = sum_l fP[r][j n + l] A_t[q][l]
+#pragma unroll
+                    for (int l = 0; l < n; ++l) s = fma(B[p * n + l], tb.A[q * n + l], s);
+                    T[(size_t)(dp + r) * dp + c] = s;
+                    T[(size_t)(2 * dp + r) * dp + c] = (r == c) ? 1.0 : 0.0;
+                }
+        }
+        for (long long i = tid; i < M; i += nthreads) {
+#pragma unroll
+            for (int p = 0; p < n; ++p) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < n; ++q) s = fma(tb.A[p * n + q], fmk[i * n + q], s);
+                T[(size_t)(3 * dp) * dp + i * n + p] = ldg(smn + i * n + p) - s;
+            }
+        }
+        gs.sync();
+        // ---- P^- = L L^T;  Y = fP A^T L^-T;  LiT = L^-T;  z = L^-1 (sm_next - A fm)
+        chol_stack_grid(T, dp, rows, nullptr, 0, sm, gs);
+        const double* Y = T + (size_t)dp * dp;
+        const double* LiT = T + (size_t)2 * dp * dp;
+        const double* z = T + (size_t)3 * dp * dp;
+        const int tm = (d + 31) / 32, tn = (d + 63) / 64;
+        // ---- G = Y L^-1  (the smoother gain fP A^T (P^-)^-1, ops.py:296);  sm = fm + Y z
+        double* G = a.gains ? a.gains + (size_t)k * d * d : a.G;
+        for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
+            const int i0 = (t / tn) * 32, j0 = (t % tn) * 64;
+            double acc[2][4];
+            tile_nt<32, 64, false>(Y, dp, d, LiT, dp, d, dp, i0, j0, nullptr, acc, sm);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    if (row < d && col < d) G[(size_t)row * d + col] = acc[r][c];
+                }
+        }
+        {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            for (int row = blockIdx.x * (NTH / 32) + warp; row < d; row += gridDim.x * (NTH / 32)) {
+                double s = 0.0;
+                for (int c = lane; c < d; c += 32) s = fma(ldg(Y + (size_t)row * dp + c), ldg(z + c), s);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lane == 0) {
+                    const double v = fmk[row] + s;
+                    smo[row] = v;
+                    if (a.return_full) a.means[(size_t)k * d + row] = v;
+                    else if (row % n == 0) a.means[(size_t)k * M + row / n] = v;
+                }
+            }
+        }
+        gs.sync();
+        // ---- Z = G (sP_next - P^-)   (Dm symmetric: NT form)
+        for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
+            const int i0 = (t / tn) * 32, j0 = (t % tn) * 64;
+            double acc[2][4];
+            tile_nt<32, 64, false>(G, d, d, a.Dm, d, d, d, i0, j0, nullptr, acc, sm);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    if (row < d && col < d) a.Z[(size_t)row * d + col] = acc[r][c];
+                }
+        }
+        gs.sync();
+        // ---- sP = fP + Z G^T   (ops.py:298)
+        for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
+            const int i0 = (t / tn) * 32, j0 = (t % tn) * 64;
+            double acc[2][4];
+            tile_nt<32, 64, false>(a.Z, d, d, G, d, d, d, i0, j0, nullptr, acc, sm);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    if (row < d && col < d) {
+                        const double v = fPk[(size_t)row * d + col] + acc[r][c];
+                        sPo[(size_t)row * d + col] = v;
+                        if (a.return_full) a.covs[(size_t)k * d * d + (size_t)row * d + col] = v;
+                        else if (row % n == 0 && col % n == 0)
+                            a.covs[(size_t)k * M * M + (size_t)(row / n) * M + col / n] = v;
+                    }
+                }
+        }
+        gs.sync();
+        cur ^= 1;
+    }
+}
+
+// ---- batched SPD inverse / pseudo-likelihood projection ------------------------------------------------------
+// One CTA per time step.  S_k = (PROJECT ? Bt diag(lam_k) Bt^T : A_k) + jitter I;  out_k = S_k^-1 through the
+// Cholesky factor (utils.py:22-35);  rhs -> S_k^-1 rhs;  logdet -> log det S_k.
+struct InvArgs {
+    long long N;
+    int n;                // matrix size (M)
+    int Ns;               // PROJECT: inner dimension
+    const double* A;      // [N,n,n]        (!PROJECT)
+    const double* Bt;     // [n,Ns]         (PROJECT)  B^T, time-invariant
+    const double* lam;    // [N,Ns]         (PROJECT)  diagonal of nat2
+    const double* rhs_s;  // [N,Ns]         (PROJECT)  nat1 (projected by Bt first) | [N,n] (!PROJECT) | null
+    double jitter;
+    double* S;            // [N,n,n] nullable: the matrix that was inverted (nat2_full)
+    double* inv;          // [N,n,n]
+    double* sol;          // [N,n] nullable
+    double* logdet;       // [N] nullable
+    double* T;            // per-CTA slots [(2 np + 32) x np]
+};
+
+template <bool PROJECT>
+__global__ void __launch_bounds__(NTH) st_inverse_kernel(InvArgs a) {
+    __shared__ Smem sm;
+    const int n = a.n, np = pad32(n), rows = 2 * np + NB;
+    double* T = a.T + (size_t)blockIdx.x * rows * np;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tm = (n + 63) / 64;
+    for (long long k = blockIdx.x; k < a.N; k += gridDim.x) {
+        for (int e = threadIdx.x; e < rows * np; e += NTH) {
+            const int r = e / np, c = e % np;
+            double v = 0.0;
+            if (r < np) {
+                if (r == c) v = (r < n) ? a.jitter : 1.0;
+                if (!PROJECT && r < n && c < n) v += a.A[(size_t)k * n * n + (size_t)r * n + c];
+            } else if (r < 2 * np) {
+                v = (r - np == c) ? 1.0 : 0.0;
+            } else if (r == 2 * np && c < n && a.rhs_s) {
+                if (!PROJECT) v = a.rhs_s[(size_t)k * n + c];
+            }
+            T[e] = v;
+        }
+        __syncthreads();
+        if (PROJECT) {
+            // S = Bt diag(lam) Bt^T (basemodels.py:681), rhs = Bt nat1 (:680)
+            const double* lam = a.lam + (size_t)k * a.Ns;
+            for (int t = 0; t < tm * tm; ++t) {
+                const int i0 = (t / tm) * 64, j0 = (t % tm) * 64;
+                if (j0 > i0) continue;  // lower triangle + mirror
+                double acc[4][4];
+                tile_nt<64, 64, true>(a.Bt, a.Ns, n, a.Bt, a.Ns, n, a.Ns, i0, j0, lam, acc, sm);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                        if (row < n && col < n) {
+                            T[(size_t)row * np + col] += acc[r][c];
+                            if (j0 < i0) T[(size_t)col * np + row] += acc[r][c];
+                        }
+                    }
+            }
+            if (a.rhs_s) {
+                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                const double* r1 = a.rhs_s + (size_t)k * a.Ns;
+                for (int row = warp; row < n; row += NTH / 32) {
+                    double s = 0.0;
+                    for (int c = lane; c < a.Ns; c += 32) s = fma(a.Bt[(size_t)row * a.Ns + c], r1[c], s);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if (lane == 0) T[(size_t)(2 * np) * np + row] = s;
+                }
+            }
+            __syncthreads();
+            __threadfence_block();
+        }
+        if (a.S) {
+            for (int e = threadIdx.x; e < n * n; e += NTH) {
+                const int r = e / n, c = e % n;
+                a.S[(size_t)k * n * n + e] = ldg(T + (size_t)r * np + c) - (r == c ? a.jitter : 0.0);
+            }
+        }
+        __syncthreads();
+        chol_stack_cta(T, np, rows, sm);
+        // inverse = L^-T L^-1 = LiT LiT^T with LiT = T[np:2np]  (cho_solve(L, I))
+        const double* LiT = T + (size_t)np * np;
+        for (int t = 0; t < tm * tm; ++t) {
+            const int i0 = (t / tm) * 64, j0 = (t % tm) * 64;
+            if (j0 > i0) continue;
+            double acc[4][4];
+            tile_nt<64, 64, false>(LiT, np, n, LiT, np, n, np, i0, j0, nullptr, acc, sm);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    if (row < n && col < n) {
+                        a.inv[(size_t)k * n * n + (size_t)row * n + col] = acc[r][c];
+                        if (j0 < i0) a.inv[(size_t)k * n * n + (size_t)col * n + row] = acc[r][c];
+                    }
+                }
+        }
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (a.sol) {
+            const double* z = T + (size_t)(2 * np) * np;
+            for (int row = warp; row < n; row += NTH / 32) {
+                double s = 0.0;
+                for (int c = lane; c < n; c += 32) s = fma(ldg(LiT + (size_t)row * np + c), ldg(z + c), s);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lane == 0) a.sol[(size_t)k * n + row] = s;
+            }
+        }
+        if (a.logdet && warp == 0) {
+            double ld = 0.0;
+            for (int c = lane; c < n; c += 32) ld += log(ldg(T + (size_t)c * np + c));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, off);
+            if (lane == 0) a.logdet[k] = 2.0 * ld;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- conditional_posterior_to_data (basemodels.py:743-764), marginals only --------------------------------------
+// mean_f = B m,  var_f = diag(B V B^T) + cdiag.  One CTA per time step; B [Ns,M] time-invariant.
+__global__ void __launch_bounds__(NTH) st_to_data_kernel(long long N, int Ns, int M, const double* B, const double* cdiag,
+                                                         const double* pm, const double* pV, double* mean_f,
+                                                         double* var_f) {
+    __shared__ Smem sm;
+    double* part = &sm.L[0][0];  // 64 x 16 partial sums (fits the 32 x 33 block buffer)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (long long k = blockIdx.x; k < N; k += gridDim.x) {
+        const double* V = pV + (size_t)k * M * M;
+        const double* m = pm + (size_t)k * M;
+        for (int i0 = 0; i0 < Ns; i0 += 64) {
+            double dsum[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int j0 = 0; j0 < M; j0 += 64) {
+                double acc[4][4];  // (B V)[i0.., j0..]  (V symmetric: NT form)
+                tile_nt<64, 64, false>(B, M, Ns, V, M, M, M, i0, j0, nullptr, acc, sm);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                        if (row < Ns && col < M) dsum[r] = fma(acc[r][c], B[(size_t)row * M + col], dsum[r]);
+                    }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 4; ++r) part[(ty + 16 * r) * 16 + tx] = dsum[r];
+            __syncthreads();
+            if (threadIdx.x < 64) {
+                const int row = i0 + threadIdx.x;
+                if (row < Ns) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) s += part[threadIdx.x * 16 + q];
+                    var_f[(size_t)k * Ns + row] = s + (cdiag ? cdiag[row] : 0.0);
+                    double mu = 0.0;
+                    for (int c = 0; c < M; ++c) mu = fma(B[(size_t)row * M + c], m[c], mu);
+                    mean_f[(size_t)k * Ns + row] = mu;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- Gaussian KL term with full M x M blocks (utils.py:510-531 through basemodels.py:715-721) ------------------
+// out_k = log N(y_k | m_k, R_k) - 0.5 tr(R_k^-1 V_k), both through chol(R_k).  One CTA per time step.
+// T = [R ; V ; I ; (y - m)^T]:  U = V L^-T, LiT = L^-T  =>  tr(R^-1 V) = sum_ij LiT[i][j] U[i][j].
+__global__ void __launch_bounds__(NTH) st_gell_kernel(long long N, int n, const double* y, const double* m, const double* V,
+                                                      const double* R, const uint8_t* mask, double* out, double* Tall) {
+    __shared__ Smem sm;
+    __shared__ double red[NTH];
+    const int np = pad32(n), rows = 3 * np + NB;
+    double* T = Tall + (size_t)blockIdx.x * rows * np;
+    for (long long k = blockIdx.x; k < N; k += gridDim.x) {
+        for (int e = threadIdx.x; e < rows * np; e += NTH) {
+            const int r = e / np, c = e % np;
+            double v = 0.0;
+            // mask rules of utils.py:522-527: masked entries independent, noise variance 1/(2 pi), covariance 1e-20, residual 0
+            const uint8_t* mk = mask ? mask + (size_t)k * n : nullptr;
+            if (r < np) {
+                if (r < n && c < n) {
+                    v = R[(size_t)k * n * n + (size_t)r * n + c];
+                    if (mk && (mk[r] || mk[c])) v = (r == c) ? 0.15915494309189535 : 0.0;
+                } else if (r == c) v = 1.0;
+            } else if (r < 2 * np) {
+                const int rr = r - np;
+                if (rr < n && c < n) {
+                    v = V[(size_t)k * n * n + (size_t)rr * n + c];
+                    if (mk && (mk[rr] || mk[c])) v = (rr == c) ? 1e-20 : 0.0;
+                }
+            } else if (r < 3 * np) {
+                v = (r - 2 * np == c) ? 1.0 : 0.0;
+            } else if (r == 3 * np && c < n) {
+                v = (mk && mk[c]) ? 0.0 : y[(size_t)k * n + c] - m[(size_t)k * n + c];
+            }
+            T[e] = v;
+        }
+        __syncthreads();
+        __threadfence_block();
+        chol_stack_cta(T, np, rows, sm);
+        const double* U = T + (size_t)np * np;
+        const double* LiT = T + (size_t)2 * np * np;
+        const double* z = T + (size_t)3 * np * np;
+        double s = 0.0;
+        for (int e = threadIdx.x; e < n * np; e += NTH) s = fma(ldg(LiT + e), ldg(U + e), s);
+        double q = 0.0;
+        for (int c = threadIdx.x; c < n; c += NTH) {
+            const double zc = ldg(z + c);
+            q += zc * zc + 2.0 * log(ldg(T + (size_t)c * np + c));
+        }
+        red[threadIdx.x] = -0.5 * (q + s);
+        __syncthreads();
+        for (int off = NTH / 2; off > 0; off >>= 1) {
+            if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[k] = red[0] - 0.5 * n * 1.8378770664093453;
+        __syncthreads();
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static int sm_count() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 1;
+}
+
+struct Carver {
+    char* p;
+    size_t left;
+    bool ok = true;
+    template <class X>
+    X* take(size_t count) {
+        size_t bytes = (count * sizeof(X) + 255) / 256 * 256;
+        if (bytes > left) { ok = false; return nullptr; }
+        X* r = (X*)p;
+        p += bytes;
+        left -= bytes;
+        return r;
+    }
+};
+
+static size_t filter_ws(int M, int n) {
+    size_t d = (size_t)M * n, Mp = pad32(M), dp = pad32((int)d);
+    return ((Mp + dp + NB) * Mp + (Mp + NB) * Mp + d * d + d + 64) * sizeof(double) + 8 * 256;
+}
+static size_t smoother_ws(int M, int n) {
+    size_t d = (size_t)M * n, dp = pad32((int)d);
+    return ((3 * dp + NB) * dp + 5 * d * d + 2 * d + 64) * sizeof(double) + 12 * 256;
+}
+static int batch_grid(long long N) {
+    long long g = 2LL * sm_count();
+    return (int)(N < g ? (N > 0 ? N : 1) : g);
+}
+static size_t inverse_ws(long long N, int n) {
+    size_t np = pad32(n);
+    return (size_t)batch_grid(N) * (2 * np + NB) * np * sizeof(double) + 256;
+}
+static size_t gell_ws(long long N, int n) {
+    size_t np = pad32(n);
+    return (size_t)batch_grid(N) * (3 * np + NB) * np * sizeof(double) + 256;
+}
+
+}  // namespace st
+}  // namespace bn
+
+using namespace bn;
+using namespace bn::st;
+
+#define ST_DISPATCH_FAMILY(fam, CALL)                  \
+    switch (fam) {                                     \
+        case BN_MATERN12: { CALL(BN_MATERN12); break; } \
+        case BN_MATERN32: { CALL(BN_MATERN32); break; } \
+        case BN_MATERN52: { CALL(BN_MATERN52); break; } \
+        default: break;                                \
+    }
+
+static int st_check_spec(const bn_kernel_spec* k, int M, int* n_out) {
+    BN_REQUIRE(k != nullptr, "temporal kernel spec is null");
+    BN_REQUIRE(k->n_components == 1, "the temporal kernel of a spatio-temporal prior has one component");
+    BN_REQUIRE(k->family == BN_MATERN12 || k->family == BN_MATERN32 || k->family == BN_MATERN52,
+               "temporal family %d not available on the dense path (Matern-1/2, -3/2, -5/2)", k->family);
+    BN_REQUIRE(M >= 1 && M <= 4096, "M = %d spatial points out of range", M);
+    *n_out = family_dim(k->family);
+    return 0;
+}
+
+extern "C" size_t bn_st_workspace_bytes(const bn_kernel_spec* temporal, int M, int64_t N, int Ns) {
+    int n = 0;
+    if (st_check_spec(temporal, M, &n) != 0) return 0;
+    size_t a = filter_ws(M, n), b = smoother_ws(M, n), c = inverse_ws(N, M), e = gell_ws(N, M);
+    (void)Ns;
+    size_t m = a > b ? a : b;
+    if (c > m) m = c;
+    if (e > m) m = e;
+    return m;
+}
+
+extern "C" int bn_st_kalman_filter(const bn_kernel_spec* temporal, int M, int64_t N, const double* dt, const double* y,
+                                   const double* noise_cov, const uint8_t* mask, int return_predict, double* ell,
+                                   double* means, double* covs, void* workspace, size_t workspace_bytes, void* stream) {
+    int n = 0;
+    if (int rc = st_check_spec(temporal, M, &n)) return rc;
+    BN_REQUIRE(N >= 0, "N must be non-negative");
+    if (N == 0) return 0;
+    BN_REQUIRE(dt && y && noise_cov && means && covs, "null array");
+    BN_REQUIRE(workspace && workspace_bytes >= filter_ws(M, n), "workspace too small: %zu bytes needed", filter_ws(M, n));
+    const size_t d = (size_t)M * n, Mp = pad32(M), dp = pad32((int)d);
+    Carver cv{(char*)workspace, workspace_bytes};
+    FilterArgs a;
+    a.spec = *temporal; a.M = M; a.N = N; a.dt = dt; a.y = y; a.R = noise_cov; a.mask = mask; a.return_predict = return_predict;
+    a.ell = ell; a.means = means; a.covs = covs;
+    a.ctr = cv.take<unsigned long long>(32);
+    a.ellacc = cv.take<double>(32);
+    a.T = cv.take<double>((Mp + dp + NB) * Mp);
+    a.T2 = cv.take<double>((Mp + NB) * Mp);
+    a.Pcur = cv.take<double>(d * d);
+    a.mcur = cv.take<double>(d);
+    BN_REQUIRE(cv.ok, "workspace carve failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
+    const int grid = sm_count();
+    BN_REQUIRE(grid >= 2, "the dense path needs at least 2 SMs");
+#define CALL(F) BN_LAUNCH("st_filter", s, st_filter_kernel<F><<<grid, NTH, 0, s>>>(a))
+    ST_DISPATCH_FAMILY(temporal->family, CALL)
+#undef CALL
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bn_st_rts_smoother(const bn_kernel_spec* temporal, int M, int64_t N, const double* dt,
+                                  const double* filter_mean, const double* filter_cov, int return_full, double* means,
+                                  double* covs, double* gains, void* workspace, size_t workspace_bytes, void* stream) {
+    int n = 0;
+    if (int rc = st_check_spec(temporal, M, &n)) return rc;
+    BN_REQUIRE(N >= 0, "N must be non-negative");
+    if (N == 0) return 0;
+    BN_REQUIRE(dt && filter_mean && filter_cov && means && covs, "null array");
+    BN_REQUIRE(workspace && workspace_bytes >= smoother_ws(M, n), "workspace too small: %zu bytes needed", smoother_ws(M, n));
+    const size_t d = (size_t)M * n, dp = pad32((int)d);
+    Carver cv{(char*)workspace, workspace_bytes};
+    SmootherArgs a;
+    a.spec = *temporal; a.M = M; a.N = N; a.dt = dt; a.fm = filter_mean; a.fP = filter_cov; a.return_full = return_full;
+    a.means = means; a.covs = covs; a.gains = gains;
+    a.ctr = cv.take<unsigned long long>(32);
+    a.T = cv.take<double>((3 * dp + NB) * dp);
+    a.sP[0] = cv.take<double>(d * d);
+    a.sP[1] = cv.take<double>(d * d);
+    a.smv[0] = cv.take<double>(d);
+    a.smv[1] = cv.take<double>(d);
+    a.G = cv.take<double>(d * d);
+    a.Dm = cv.take<double>(d * d);
+    a.Z = cv.take<double>(d * d);
+    BN_REQUIRE(cv.ok, "workspace carve failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
+    const int grid = sm_count();
+#define CALL(F) BN_LAUNCH("st_smoother", s, st_smoother_kernel<F><<<grid, NTH, 0, s>>>(a))
+    ST_DISPATCH_FAMILY(temporal->family, CALL)
+#undef CALL
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bn_spd_inverse_batched(int64_t N, int n, const double* A, const double* rhs, double jitter, double* inv,
+                                      double* sol, double* logdet, void* workspace, size_t workspace_bytes, void* stream) {
+    BN_REQUIRE(N >= 0 && n >= 1 && n <= 4096, "bad sizes N = %lld, n = %d", (long long)N, n);
+    if (N == 0) return 0;
+    BN_REQUIRE(A && inv, "null array");
+    BN_REQUIRE(sol == nullptr || rhs != nullptr, "sol needs rhs");
+    BN_REQUIRE(workspace && workspace_bytes >= inverse_ws(N, n), "workspace too small: %zu bytes needed", inverse_ws(N, n));
+    InvArgs a{};
+    a.N = N; a.n = n; a.Ns = 0; a.A = A; a.rhs_s = rhs; a.jitter = jitter; a.S = nullptr; a.inv = inv; a.sol = sol;
+    a.logdet = logdet; a.T = (double*)workspace;
+    cudaStream_t s = (cudaStream_t)stream;
+    BN_LAUNCH("st_inverse", s, st_inverse_kernel<false><<<batch_grid(N), NTH, 0, s>>>(a));
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bn_st_pseudo_lik(int64_t N, int Ns, int M, const double* Bt, const double* nat1, const double* nat2_diag,
+                                double jitter, double* pseudo_y, double* pseudo_var, double* nat2_full, double* logdet,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    BN_REQUIRE(N >= 0 && M >= 1 && M <= 4096 && Ns >= 1, "bad sizes N = %lld, Ns = %d, M = %d", (long long)N, Ns, M);
+    if (N == 0) return 0;
+    BN_REQUIRE(Bt && nat1 && nat2_diag && pseudo_y && pseudo_var, "null array");
+    BN_REQUIRE(workspace && workspace_bytes >= inverse_ws(N, M), "workspace too small: %zu bytes needed", inverse_ws(N, M));
+    InvArgs a{};
+    a.N = N; a.n = M; a.Ns = Ns; a.Bt = Bt; a.lam = nat2_diag; a.rhs_s = nat1; a.jitter = jitter; a.S = nat2_full;
+    a.inv = pseudo_var; a.sol = pseudo_y; a.logdet = logdet; a.T = (double*)workspace;
+    cudaStream_t s = (cudaStream_t)stream;
+    BN_LAUNCH("st_pseudo_lik", s, st_inverse_kernel<true><<<batch_grid(N), NTH, 0, s>>>(a));
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bn_st_posterior_to_data(int64_t N, int Ns, int M, const double* B, const double* cdiag,
+                                       const double* post_mean, const double* post_cov, double* mean_f, double* var_f,
+                                       void* stream) {
+    BN_REQUIRE(N >= 0 && M >= 1 && Ns >= 1, "bad sizes");
+    if (N == 0) return 0;
+    BN_REQUIRE(B && post_mean && post_cov && mean_f && var_f, "null array");
+    cudaStream_t s = (cudaStream_t)stream;
+    BN_LAUNCH("st_to_data", s, st_to_data_kernel<<<batch_grid(N), NTH, 0, s>>>(N, Ns, M, B, cdiag, post_mean, post_cov, mean_f, var_f));
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bn_st_gaussian_expected_log_lik(int64_t N, int M, const double* pseudo_y, const double* post_mean,
+                                               const double* post_cov, const double* pseudo_var, const uint8_t* mask, double* values,
+                                               double* sum, void* workspace, size_t workspace_bytes, void* stream) {
+    BN_REQUIRE(N >= 0 && M >= 1 && M <= 4096, "bad sizes");
+    if (N == 0) return 0;
+    BN_REQUIRE(pseudo_y && post_mean && post_cov && pseudo_var && values, "null array (values[N] is required)");
+    BN_REQUIRE(workspace && workspace_bytes >= gell_ws(N, M), "workspace too small: %zu bytes needed", gell_ws(N, M));
+    cudaStream_t s = (cudaStream_t)stream;
+    BN_LAUNCH("st_gell", s, st_gell_kernel<<<batch_grid(N), NTH, 0, s>>>(N, M, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, (double*)workspace));
+    BN_CUDA(cudaGetLastError());
+    if (sum) {
+        BN_LAUNCH("sum", s, sum_kernel<false><<<1, 1024, 0, s>>>(values, N, sum, 1.0));
+        BN_CUDA(cudaGetLastError());
+    }
+    return 0;
+}

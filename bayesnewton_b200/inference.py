@@ -42,7 +42,7 @@ class InferenceMixin:
             a.out_mean, a.out_jac, a.out_hess = (ptr(s) for s in state)
         diffs = torch.zeros((2,), dtype=torch.float64, device=dev)
         a.diffs = diffs.data_ptr()
-        ws, nb = workspace(N, self.state_dim, D)
+        ws, nb = workspace(N, getattr(self, '_site_state_dim', self.state_dim), D)
         _lib.check(_lib.lib().bn_site_update(a, ptr(ws), nb, stream_ptr()))
         pl.version += 1  # the sites were rewritten in place
         if want_grad:
@@ -55,7 +55,7 @@ class InferenceMixin:
         """nansum over steps of the scheme's likelihood term (VI: E_q[log p]; Newton: log p(y|m); EP/PL: log Z)"""
         a, keep = self._site_args(cubature)
         out = torch.zeros((), dtype=torch.float64, device=self.posterior_mean.device)
-        ws, nb = workspace(a.N, self.state_dim, a.D)
+        ws, nb = workspace(a.N, getattr(self, '_site_state_dim', self.state_dim), a.D)
         _lib.check(_lib.lib().bn_expected_density(a, None, ptr(out), ptr(ws), nb, stream_ptr()))
         return out
 
@@ -100,7 +100,7 @@ class ExpectationPropagation(InferenceMixin):
         pl = self.pseudo_likelihood
         N, D = pl.mean.shape[0], pl.mean.shape[1]
         out = torch.zeros((), dtype=torch.float64, device=pl.mean.device)
-        ws, nb = workspace(N, self.state_dim, D)
+        ws, nb = workspace(N, getattr(self, '_site_state_dim', self.state_dim), D)
         _lib.check(_lib.lib().bn_ep_pseudo_density(
             N, D, float(power), int(with_const), ptr(pl.mean), ptr(pl.covariance), ptr(self.posterior_mean),
             ptr(self.posterior_variance), ptr(pl.nat1), ptr(pl.nat2), ptr(self.mask_pseudo_y), ptr(out), ptr(ws), nb,

@@ -65,6 +65,15 @@ class StationaryKernel(Kernel):
         H[0, 0] = 1.0
         return H
 
+    def K(self, X, X2):
+        """covariance function on host arrays (kernels.py:97-104, clip at 1e-36); used for the per-hyper-parameter
+        constants of the spatial conditional (spacetime.py), never per time step"""
+        X = np.asarray(X, dtype=np.float64).reshape(-1, 1) / self.lengthscale
+        X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 1) / self.lengthscale
+        return self.K_r(np.sqrt(np.maximum((X - X2.T) ** 2, 1e-36)))
+
+    __call__ = K
+
     def state_transition(self, dt):
         """A = expm(F dt): [d,d] for a scalar dt, [N,d,d] for an array (the vmapped call of ops.py:277)"""
         As, _ = discretise(self, dt)
@@ -73,6 +82,9 @@ class StationaryKernel(Kernel):
 
 class Matern12(StationaryKernel):
     family, state_dim = _lib.BN_MATERN12, 1
+
+    def K_r(self, r):
+        return self.variance * np.exp(-r)
 
     def stationary_covariance(self):
         return np.array([[self.variance]])
@@ -84,6 +96,10 @@ class Matern12(StationaryKernel):
 class Matern32(StationaryKernel):
     family, state_dim = _lib.BN_MATERN32, 2
 
+    def K_r(self, r):
+        s3 = 3.0 ** 0.5
+        return self.variance * (1.0 + s3 * r) * np.exp(-s3 * r)
+
     def stationary_covariance(self):
         return np.array([[self.variance, 0.0], [0.0, 3.0 * self.variance / self.lengthscale ** 2]])
 
@@ -94,6 +110,10 @@ class Matern32(StationaryKernel):
 
 class Matern52(StationaryKernel):
     family, state_dim = _lib.BN_MATERN52, 3
+
+    def K_r(self, r):
+        s5 = 5.0 ** 0.5
+        return self.variance * (1.0 + s5 * r + 5.0 / 3.0 * r ** 2) * np.exp(-s5 * r)
 
     def stationary_covariance(self):
         kappa = 5.0 / 3.0 * self.variance / self.lengthscale ** 2
@@ -107,6 +127,10 @@ class Matern52(StationaryKernel):
 
 class Matern72(StationaryKernel):
     family, state_dim = _lib.BN_MATERN72, 4
+
+    def K_r(self, r):
+        s7 = 7.0 ** 0.5
+        return self.variance * (1. + s7 * r + 14. / 5. * r ** 2 + 7. * s7 / 15. * r ** 3) * np.exp(-s7 * r)
 
     def stationary_covariance(self):
         k1 = 7.0 / 5.0 * self.variance / self.lengthscale ** 2

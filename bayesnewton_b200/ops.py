@@ -81,6 +81,9 @@ def _parallel_rts(fms, fPs, As, Qs, H, return_full):
 def kalman_filter(dt, kernel, y, noise_cov, mask=None, parallel=False, return_predict=False, want_ell=True,
                   want_states=True):
     """p(f_n | y_1..y_n) for all n; returns ell, (means [N,d,1], covs [N,d,d])"""
+    if hasattr(kernel, 'temporal_kernel'):  # SpatioTemporalKernel: dense d = M n state (csrc/st.cu)
+        from .spacetime import st_kalman_filter
+        return st_kalman_filter(dt, kernel, y, noise_cov, mask, parallel, return_predict, want_ell)
     dt = as_dev(dt).reshape(-1)
     N = dt.shape[0]
     spec = kernel.spec() if hasattr(kernel, 'spec') else None
@@ -110,6 +113,9 @@ def kalman_filter(dt, kernel, y, noise_cov, mask=None, parallel=False, return_pr
 def rauch_tung_striebel_smoother(dt, kernel, filter_mean, filter_cov, return_full=False, parallel=False,
                                  want_gains=True):
     """p(f_n | y_1..y_N); dt is the step OUT OF n (basemodels.py:700).  Returns (means, covs, gains)"""
+    if hasattr(kernel, 'temporal_kernel'):
+        from .spacetime import st_rts_smoother
+        return st_rts_smoother(dt, kernel, filter_mean, filter_cov, return_full, parallel, want_gains)
     dt = as_dev(dt).reshape(-1)
     N = dt.shape[0]
     spec = kernel.spec() if hasattr(kernel, 'spec') else None

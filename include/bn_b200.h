@@ -23,6 +23,10 @@
  *   bn_expected_density    the value-only likelihood term of energy()
  *                          inference.py:130-154,197-222,286-325,373-428
  *   bn_gaussian_expected_log_lik   vmap(gaussian_expected_log_lik) utils.py:510-531, basemodels.py:715-721
+ *   bn_st_kalman_filter / bn_st_rts_smoother   the same two ops for SpatioTemporalKernel (dense d = M n state,
+ *                          kernels.py:385-586), and bn_st_pseudo_lik / bn_st_posterior_to_data /
+ *                          bn_st_gaussian_expected_log_lik / bn_spd_inverse_batched: the projection steps either
+ *                          side of them (basemodels.py:676-687, 743-764, 708-724; utils.py:30-35)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host or its comment says HOST; the caller owns
@@ -263,6 +267,62 @@ int bn_ep_pseudo_density(int64_t N, int D, double power, int with_pep_constant,
                          const double* post_mean, const double* post_cov,
                          const double* nat1, const double* nat2, const uint8_t* mask,
                          double* sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- dense spatio-temporal path ------------------------------------------
+ * SpatioTemporalKernel (kernels.py:385-586): state x = [u_1; ..; u_M] with u_i the temporal state of spatial
+ * inducing point i;  A_k = I_M (x) A_t(dt_k) (:543-551), Pinf = I_M (x) Pinf_t (:517-524), H = I_M (x) H_t (:534-541).
+ * d = M * dim(temporal family), D = M.  `temporal` has n_components = 1 and family Matern-1/2, -3/2 or -5/2.
+ * Time is sequential (lax.scan, ops.py:154-180, 288-311); each pass is ONE persistent kernel whose phases
+ * (predict, blocked Cholesky with the right-hand sides stacked under it, A B^T tiles) are separated by grid barriers. */
+size_t bn_st_workspace_bytes(const bn_kernel_spec* temporal, int M, int64_t N, int Ns);
+
+/* kalman_filter(dt, kernel, y, noise_cov, mask=None, parallel=False, return_predict) for a SpatioTemporalKernel
+ * (ops.py:256-285 -> _sequential_kf :154-180).  y[N,M,1], noise_cov[N,M,M] dense SPD.  mask[N,M,1] nullable: as in
+ * the reference it only enters the log-likelihood (mvn_logpdf, utils.py:376-396), the update is not masked; the
+ * reference passes one when M equals the number of observations per step (basemodels.py:136-137, 652-653).  ell nullable.
+ * means[N,d,1], covs[N,d,d]. */
+int bn_st_kalman_filter(const bn_kernel_spec* temporal, int M, int64_t N,
+                        const double* dt, const double* y, const double* noise_cov, const uint8_t* mask,
+                        int return_predict, double* ell, double* means, double* covs,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* rauch_tung_striebel_smoother(dt, kernel, filter_mean, filter_cov, return_full, parallel=False)
+ * (ops.py:357-380 -> _sequential_rts :288-311); dt is the step OUT OF n (basemodels.py:700).
+ * return_full=0: means[N,M,1] = H sm, covs[N,M,M] = H sP H^T;  =1: means[N,d,1], covs[N,d,d].  gains[N,d,d] nullable. */
+int bn_st_rts_smoother(const bn_kernel_spec* temporal, int M, int64_t N,
+                       const double* dt, const double* filter_mean, const double* filter_cov, int return_full,
+                       double* means, double* covs, double* gains,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* inv_vmap (utils.py:30-35): inv[k] = (A[k] + jitter I)^-1 through the Cholesky factor, one CTA per matrix.
+ * Optional: sol[N,n] = inv[k] rhs[k] (rhs[N,n]); logdet[N] = log det (A[k] + jitter I). */
+int bn_spd_inverse_batched(int64_t N, int n, const double* A, const double* rhs, double jitter,
+                           double* inv, double* sol, double* logdet,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* MarkovGaussianProcess.compute_full_pseudo_lik, spatio-temporal branch (basemodels.py:676-687):
+ *   nat1_full = B^T nat1, nat2_full = B^T nat2 B, pseudo_var = inv(nat2_full + jitter I), pseudo_y = pseudo_var nat1_full
+ * for a time-invariant projection B (Bt = B^T, [M,Ns] row-major; the reference recomputes the same B at every
+ * step, kernels.py:494-501) and factorising sites (nat2 diagonal: nat2_diag[N,Ns]).  jitter = 1e-12 in the reference.
+ * pseudo_y[N,M,1], pseudo_var[N,M,M]; nat2_full[N,M,M] and logdet[N] = log det(nat2_full + jitter I) nullable. */
+int bn_st_pseudo_lik(int64_t N, int Ns, int M, const double* Bt, const double* nat1, const double* nat2_diag,
+                     double jitter, double* pseudo_y, double* pseudo_var, double* nat2_full, double* logdet,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* conditional_posterior_to_data (basemodels.py:743-764), the marginals the factorising likelihoods read
+ * (likelihoods.py:371-373 takes diag(cov_f)):  mean_f[N,Ns] = B m,  var_f[N,Ns] = diag(B V B^T) + cdiag.
+ * B[Ns,M] and cdiag[Ns] (nullable) time-invariant. */
+int bn_st_posterior_to_data(int64_t N, int Ns, int M, const double* B, const double* cdiag,
+                            const double* post_mean, const double* post_cov, double* mean_f, double* var_f,
+                            void* stream);
+
+/* vmap(gaussian_expected_log_lik)(pseudo_y, post_mean, post_cov, pseudo_var, mask) with full M x M blocks
+ * (utils.py:510-531 as called from compute_kl, basemodels.py:715-721): mask[N,M] nullable, values[N] (required),
+ * sum nullable. */
+int bn_st_gaussian_expected_log_lik(int64_t N, int M, const double* pseudo_y, const double* post_mean,
+                                    const double* post_cov, const double* pseudo_var, const uint8_t* mask,
+                                    double* values, double* sum,
+                                    void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,242 @@
+"""Dense spatio-temporal path.
+
+CPU part: pins the spatio-temporal oracle the way the reference pins its own implementation -- the Markov model
+against the dense GP on the product kernel, on the parameter grid of tests/test_gp_vs_markovgp_spacetime.py:62-65
+(seeded data; energies to 1e-6 relative instead of the reference's 2 decimals) -- and against the frozen vectors
+in tests/golden/spacetime_small.npz.
+GPU part: the CUDA kernels through the C ABI against the oracle.  Tolerance: relative 1e-9 (north_star), normwise.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from _data import rel_err
+from oracle import kalman, sites, ssm
+from oracle import spacetime as ost
+
+TOL = 1e-9
+# Missing observations enter the sites as precision 1e-6 (newton_update, inference.py:30), which makes
+# nat2_full = B^T nat2 B ill-conditioned (measured 8.6e8 on the 4 x 4 case below): a 1-ulp perturbation of the
+# inputs already moves the posterior mean by 2e-9, so two correct fp64 implementations agree to ~cond * eps only.
+TOL_MISSING = 1e-7
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'spacetime_small.npz')
+
+
+def st_data(Nt, Ns, seed=0, spatial_dims=1, missing=0.0):
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0, 1, Nt)) * (1.0 + 0.3 * Nt)
+    if spatial_dims == 1:
+        r = np.linspace(0, 1, Ns)[:, None]
+    else:
+        g = int(round(Ns ** 0.5))
+        assert g * g == Ns
+        a = np.linspace(-1, 1, g)
+        r = np.array([[u, v] for u in a for v in a])
+    R = np.tile(r[None], (Nt, 1, 1))
+    Y = np.sin(3 * t)[:, None] + np.sin(4 * r[:, 0])[None, :] + 0.1 * rng.standard_normal((Nt, Ns))
+    if missing > 0:
+        Y[rng.uniform(size=Y.shape) < missing] = np.nan
+    return t, Y, R
+
+
+def oracle_kernel(fam, var_f, len_t, len_s, z, spatial_dims=1):
+    kt = getattr(ssm, fam)(var_f, len_t)
+    ks = ssm.Matern32(1.0, len_s) if spatial_dims == 1 else ost.Separable([ssm.Matern32(1.0, len_s)] * spatial_dims)
+    return ost.SpatioTemporalKernel(kt, ks, z=z)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the oracle
+@pytest.mark.parametrize('var_f', [0.5, 1.5])
+@pytest.mark.parametrize('len_f', [0.75, 2.5])
+@pytest.mark.parametrize('var_y', [0.1, 0.5])
+@pytest.mark.parametrize('N', [8, 16])
+def test_oracle_markov_vs_dense_gp(var_f, len_f, var_y, N):
+    t, Y, R = st_data(N, N, seed=N)
+    mk = lambda: ost.SpatioTemporalKernel(ssm.Matern52(var_f, len_f), ssm.Matern52(1.0, len_f), z=R[0])
+    lik = sites.Gaussian(var_y)
+    m = ost.SpatioTemporalMarkovGP(mk(), lik, t, Y, R)
+    g = ost.DenseSpatioTemporalGP(mk(), lik, t, Y, R)
+    m.update_posterior()
+    g.update_posterior()
+    assert abs(m.energy() - g.energy()) <= 1e-6 * abs(g.energy())
+    m.inference()
+    g.inference()
+    assert abs(m.energy() - g.energy()) <= 1e-6 * abs(g.energy())
+    mf, cf = m.conditional_posterior_to_data()
+    assert np.abs(mf.reshape(-1) - g.post_mean).max() < 1e-6
+    assert np.abs(np.diagonal(cf, axis1=1, axis2=2).reshape(-1) - g.post_var).max() < 1e-6
+
+
+def golden_case():
+    t, Y, R = st_data(12, 9, seed=3, spatial_dims=2, missing=0.1)
+    k = oracle_kernel('Matern32', 1.2, 0.8, 0.9, R[0], spatial_dims=2)
+    m = ost.SpatioTemporalMarkovGP(k, sites.Gaussian(0.3), t, Y, R)
+    m.inference(lr=0.7)
+    return m, dict(t=t, Y=Y, R=R, post_mean=m.post_mean, post_cov=m.post_cov, energy=np.array(m.energy()),
+                   site_nat1=m.site_nat1, site_nat2=m.site_nat2)
+
+
+def test_oracle_matches_golden():
+    _, out = golden_case()
+    ref = np.load(GOLDEN)
+    for k in ('post_mean', 'post_cov', 'energy', 'site_nat1', 'site_nat2'):
+        assert rel_err(out[k], ref[k]) < 1e-10, k
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture(scope='module')
+def bn():
+    import torch
+    assert torch.cuda.is_available(), 'the -m gpu tests need a CUDA device'
+    import bayesnewton_b200 as bn
+    return bn
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def gpu_kernel(bn, fam, var_f, len_t, len_s, z, spatial_dims=1):
+    K = bn.kernels
+    kt = getattr(K, fam)(var_f, len_t)
+    ks = K.Matern32(1.0, len_s) if spatial_dims == 1 else bn.spacetime.Separable([K.Matern32(1.0, len_s)] * spatial_dims)
+    return bn.spacetime.SpatioTemporalKernel(kt, ks, z=z)
+
+
+def spd_batch(N, n, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((N, n, n))
+    return A @ A.transpose(0, 2, 1) / n + 0.5 * np.eye(n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n', [1, 5, 32, 33, 100, 256])
+def test_gpu_spd_inverse_batched(bn, n):
+    N = 7
+    P = spd_batch(N, n, n)
+    rhs = np.random.default_rng(n + 1).standard_normal((N, n, 1))
+    inv, sol, ld = bn.spacetime.inv_vmap(P, rhs=rhs, want_logdet=True)
+    ref = np.linalg.inv(P)
+    assert rel_err(np_(inv), ref) < TOL
+    assert rel_err(np_(sol), ref @ rhs) < TOL
+    assert rel_err(np_(ld), np.linalg.slogdet(P)[1]) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fam', ['Matern12', 'Matern32', 'Matern52'])
+@pytest.mark.parametrize('M', [3, 16, 37])
+@pytest.mark.parametrize('masked', [False, True])
+def test_gpu_dense_filter_smoother_vs_oracle(bn, fam, M, masked):
+    N = 11
+    rng = np.random.default_rng(M)
+    z = np.linspace(0, 1, M)[:, None]
+    ko = oracle_kernel(fam, 1.3, 0.7, 0.5, z)
+    kg = gpu_kernel(bn, fam, 1.3, 0.7, 0.5, z)
+    dt = np.concatenate([[0.0], 0.1 + 0.4 * rng.uniform(size=N - 1)])
+    y = rng.standard_normal((N, M, 1))
+    Rn = spd_batch(N, M, M + 1)
+    mask = (rng.uniform(size=(N, M, 1)) < 0.2) if masked else None
+    for rp in (False, True):
+        e0, (m0, P0) = kalman.kalman_filter(dt, ko, y, Rn, mask, return_predict=rp)
+        e1, (m1, P1) = bn.ops.kalman_filter(dt, kg, y, Rn, mask, return_predict=rp)
+        assert abs(float(e1) - e0) <= TOL * abs(e0)
+        assert rel_err(np_(m1), m0) < TOL and rel_err(np_(P1), P0) < TOL
+    _, (fm, fP) = kalman.kalman_filter(dt, ko, y, Rn, mask)
+    dts = np.concatenate([dt[1:], [0.0]])
+    for full in (False, True):
+        s0, S0, G0 = kalman.rauch_tung_striebel_smoother(dts, ko, fm, fP, return_full=full)
+        s1, S1, G1 = bn.ops.rauch_tung_striebel_smoother(dts, kg, fm, fP, return_full=full)
+        assert rel_err(np_(s1), s0) < TOL and rel_err(np_(S1), S0) < TOL and rel_err(np_(G1), G0) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('Ns,M', [(9, 9), (16, 9), (25, 25)])
+def test_gpu_projection_steps_vs_oracle(bn, Ns, M):
+    """compute_full_pseudo_lik, conditional_posterior_to_data and the Gaussian KL term"""
+    import torch
+    Nt = 6
+    t, Y, R = st_data(Nt, Ns, seed=Ns, spatial_dims=2)
+    z = R[0] if M == Ns else st_data(1, M, spatial_dims=2)[2][0]
+    ko = oracle_kernel('Matern32', 0.9, 1.1, 0.8, z, spatial_dims=2)
+    kg = gpu_kernel(bn, 'Matern32', 0.9, 1.1, 0.8, z, spatial_dims=2)
+    rng = np.random.default_rng(5)
+    mo = ost.SpatioTemporalMarkovGP(ko, sites.Gaussian(0.2), t, Y, R)
+    mg = bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(0.2), X=t, Y=Y, R=R)
+    nat1 = rng.standard_normal((Nt, Ns))
+    nat2 = 0.5 + rng.uniform(size=(Nt, Ns))
+    mo.site_nat1 = nat1[..., None]
+    mo.site_nat2 = np.stack([np.diag(v) for v in nat2])
+    mg.pseudo_likelihood.nat1_.copy_(torch.as_tensor(nat1))
+    mg.pseudo_likelihood.nat2_.copy_(torch.as_tensor(nat2))
+    mg.pseudo_likelihood.version += 1
+    py0, pv0 = mo.compute_full_pseudo_lik()
+    py1, pv1 = mg.compute_full_pseudo_lik()
+    assert rel_err(np_(py1), py0) < TOL and rel_err(np_(pv1), pv0) < TOL
+    pm = rng.standard_normal((Nt, M, 1))
+    pV = spd_batch(Nt, M, 11)
+    mo.post_mean, mo.post_cov = pm, pV
+    mf0, cf0 = mo.conditional_posterior_to_data()
+    mf1, vf1 = mg.conditional_posterior_to_data(post_mean=pm, post_cov=pV)
+    assert rel_err(np_(mf1), mf0) < TOL
+    assert rel_err(np_(vf1)[..., 0], np.diagonal(cf0, axis1=1, axis2=2)) < TOL
+    mg.posterior_mean, mg.posterior_variance = torch.as_tensor(pm).cuda(), torch.as_tensor(pV).cuda()
+    e0 = np.sum(sites.gaussian_expected_log_lik(py0, pm, pV, pv0, None))
+    e1 = float(mg.expected_density_pseudo())
+    assert abs(e1 - e0) <= TOL * abs(e0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', ['full', 'sparse', 'missing', 'matern52_time'])
+def test_gpu_spatiotemporal_vi_iteration_vs_oracle(bn, case):
+    """MarkovVariationalGP + SpatioTemporalKernel: inference(lr) and energy() end to end"""
+    Nt, Ns = 14, 16
+    t, Y, R = st_data(Nt, Ns, seed=7, spatial_dims=2, missing=0.15 if case == 'missing' else 0.0)
+    z = st_data(1, 9, spatial_dims=2)[2][0] if case == 'sparse' else R[0]
+    fam = 'Matern52' if case == 'matern52_time' else 'Matern32'
+    ko = oracle_kernel(fam, 1.1, 0.9, 1.2, z, spatial_dims=2)
+    kg = gpu_kernel(bn, fam, 1.1, 0.9, 1.2, z, spatial_dims=2)
+    mo = ost.SpatioTemporalMarkovGP(ko, sites.Gaussian(0.3), t, Y, R)
+    mg = bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(0.3), X=t, Y=Y, R=R)
+    tol = TOL_MISSING if case == 'missing' else TOL
+    for lr in (1.0, 0.5):
+        mo.inference(lr=lr)
+        mg.inference(lr=lr)
+        E0, E1 = mo.energy(), float(mg.energy())
+        assert rel_err(np_(mg.posterior_mean), mo.post_mean) < tol
+        assert rel_err(np_(mg.posterior_variance), mo.post_cov) < tol
+        assert abs(E1 - E0) <= tol * abs(E0), (E0, E1)
+    assert rel_err(np_(mg.pseudo_likelihood.nat2), mo.site_nat2) < tol
+    assert rel_err(np_(mg.pseudo_likelihood.nat1), mo.site_nat1) < tol
+
+
+@pytest.mark.gpu
+def test_gpu_golden_spacetime(bn):
+    ref = np.load(GOLDEN)
+    t, Y, R = ref['t'], ref['Y'], ref['R']
+    kg = gpu_kernel(bn, 'Matern32', 1.2, 0.8, 0.9, R[0], spatial_dims=2)
+    mg = bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(0.3), X=t, Y=Y, R=R)
+    mg.inference(lr=0.7)
+    # the golden case has missing observations
+    assert rel_err(np_(mg.posterior_mean), ref['post_mean']) < TOL_MISSING
+    assert rel_err(np_(mg.posterior_variance), ref['post_cov']) < TOL_MISSING
+    assert abs(float(mg.energy()) - float(ref['energy'])) <= TOL_MISSING * abs(float(ref['energy']))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('missing', [0.0, 0.05])
+def test_gpu_c4_shape_iteration(bn, missing):
+    """the C4 state size (16 x 16 grid, Matern-3/2 in time: d = 512) on a short horizon against the oracle"""
+    Nt, Ns = 6, 256
+    tol = TOL_MISSING if missing else TOL
+    t, Y, R = st_data(Nt, Ns, seed=1, spatial_dims=2, missing=missing)
+    ko = oracle_kernel('Matern32', 1.0, 5.0, 1.0, R[0], spatial_dims=2)
+    kg = gpu_kernel(bn, 'Matern32', 1.0, 5.0, 1.0, R[0], spatial_dims=2)
+    mo = ost.SpatioTemporalMarkovGP(ko, sites.Gaussian(1.0), t, Y, R)
+    mg = bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(1.0), X=t, Y=Y, R=R)
+    mo.inference(lr=1.0)
+    mg.inference(lr=1.0)
+    E0, E1 = mo.energy(), float(mg.energy())
+    assert rel_err(np_(mg.posterior_mean), mo.post_mean) < tol
+    assert rel_err(np_(mg.posterior_variance), mo.post_cov) < tol
+    assert abs(E1 - E0) <= tol * abs(E0), (E0, E1)
