@@ -76,6 +76,7 @@ SIGNATURES = {
     'bn_st_workspace_bytes': (_Z, [_KS, _I, _L, _I]),
     'bn_st_kalman_filter': (_I, [_KS, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     'bn_st_rts_smoother': (_I, [_KS, _I, _L, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_st_profile': (_I, [C.POINTER(C.c_int64), _I]),
     'bn_spd_inverse_batched': (_I, [_L, _I, _P, _P, _D, _P, _P, _P, _P, _Z, _P]),
     'bn_st_pseudo_lik': (_I, [_L, _I, _I, _P, _P, _P, _D, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_st_posterior_to_data': (_I, [_L, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

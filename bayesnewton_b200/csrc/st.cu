@@ -25,11 +25,17 @@ namespace st {
 
 constexpr int NB = 32;     // panel width = row-block height
 constexpr int NTH = 256;   // threads per CTA
-constexpr int BK = 16;     // k-slab of the tile product
+constexpr int BK = 32;     // k-slab of the tile product
 
 __host__ __device__ inline int pad32(int x) { return (x + 31) / 32 * 32; }
 
 __device__ __forceinline__ double ldg(const double* p) { return __ldcg(p); }  // L2: data other CTAs wrote in this kernel
+
+// phase profile of the last filter / smoother launch (measurement aid, bn_st_profile): SM cycles summed over steps
+//  0 assemble  1 barrier after assemble  2 Cholesky sweep (CTA 0: all of it)  3 tile phases  4 their barriers
+//  5 panel solve, 6 look-ahead, 7 barrier wait (CTA owning the LAST row block)  8 factor+invert+publish (sum over owners)
+__device__ long long g_prof[16];
+#define ST_PROF(slot, t0) do { if (threadIdx.x == 0) { long long t1__ = clock64(); atomicAdd((unsigned long long*)&g_prof[slot], (unsigned long long)(t1__ - (t0))); (t0) = t1__; } } while (0)
 
 struct Smem {
     double a[BK][65];      // A slab, k-major (odd pitch: conflict-free transposing stores)
@@ -37,7 +43,11 @@ struct Smem {
     double L[NB][NB + 1];  // diagonal block / its Cholesky factor
     double Li[NB][NB + 1]; // inverse of the factor (lower)
     double X[NB][NB + 1];  // right-hand block before the triangular solve
+    double XO[NB][NB + 1]; // solved block (kept for the diagonal update)
+    double XA[NB][NB + 1]; // previous panel's column block of this row block
+    double XB[NB][NB + 1]; // previous panel's column block of the diagonal row block
 };
+constexpr size_t kSmemBytes = sizeof(Smem);  // ~84 KB: dynamic shared memory, one CTA per SM
 
 // ---- grid barrier ---------------------------------------------------------------------------------
 // All CTAs are co-resident (grid <= number of SMs, checked on the host).  The counter only grows; the
@@ -60,7 +70,8 @@ struct GridSync {
 
 // ---- C tile = A B^T ---------------------------------------------------------------------------------
 // acc[r][c] (rows i0 + ty + 16 r, cols j0 + tx + 16 c) = sum_{k<K} A[row][k] * (SCALE ? s[k] : 1) * B[col][k]
-// rows >= arows / brows and k >= K read as zero.  TM, TN in {32, 64}.
+// rows >= arows / brows and k >= K read as zero.  TM, TN in {32, 64}.  The next k-slab is fetched from L2 into
+// registers while the current one is multiplied out of shared memory.
 template <int TM, int TN, bool SCALE>
 __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, int arows, const double* __restrict__ B,
                                         int ldb, int brows, int K, int i0, int j0, const double* __restrict__ s,
@@ -71,22 +82,37 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, i
     for (int r = 0; r < RM; ++r)
 #pragma unroll
         for (int c = 0; c < RN; ++c) acc[r][c] = 0.0;
+    double pa[2][RM], pb[2][RN];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int kk = k0 + tx + 16 * h;
+            const double sc = (SCALE && kk < K) ? ldg(s + kk) : 1.0;
+#pragma unroll
+            for (int r = 0; r < RM; ++r) {
+                const int row = i0 + ty + 16 * r;
+                pa[h][r] = (row < arows && kk < K) ? ldg(A + (size_t)row * lda + kk) * sc : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < RN; ++r) {
+                const int row = j0 + ty + 16 * r;
+                pb[h][r] = (row < brows && kk < K) ? ldg(B + (size_t)row * ldb + kk) : 0.0;
+            }
+        }
+    };
+    if (K > 0) fetch(0);
     for (int k0 = 0; k0 < K; k0 += BK) {
         __syncthreads();
-        const int kk = k0 + tx;
-        const double sc = (SCALE && kk < K) ? ldg(s + kk) : 1.0;
 #pragma unroll
-        for (int r = 0; r < TM / 16; ++r) {
-            const int row = i0 + ty + 16 * r;
-            sm.a[tx][ty + 16 * r] = (row < arows && kk < K) ? ldg(A + (size_t)row * lda + kk) * sc : 0.0;
-        }
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int r = 0; r < TN / 16; ++r) {
-            const int row = j0 + ty + 16 * r;
-            sm.b[tx][ty + 16 * r] = (row < brows && kk < K) ? ldg(B + (size_t)row * ldb + kk) : 0.0;
+            for (int r = 0; r < RM; ++r) sm.a[tx + 16 * h][ty + 16 * r] = pa[h][r];
+#pragma unroll
+            for (int r = 0; r < RN; ++r) sm.b[tx + 16 * h][ty + 16 * r] = pb[h][r];
         }
         __syncthreads();
-#pragma unroll
+        if (k0 + BK < K) fetch(k0 + BK);
+#pragma unroll 8
         for (int k = 0; k < BK; ++k) {
             double av[RM], bv[RN];
 #pragma unroll
@@ -105,9 +131,56 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, i
 // T: rows x n (row-major, ld = n, both multiples of 32).  Rows [0,n) hold an SPD matrix S (lower triangle
 // used), the rows below hold stacked right-hand sides Wstack.  After panels 0..n/32-1:
 //     T[0:n] lower triangle = L (S = L L^T),   T[n:] = Wstack L^-T.
-// Left-looking: panel j first brings block column j up to date with the j finished block columns
-// to its left, then factors the diagonal block and applies its inverse to the blocks below.
 
+// sm.L (a 32 x 32 SPD block) -> its Cholesky factor in sm.L (upper part zeroed) and the inverse factor in sm.Li.
+// Executed by warp 0; a non-positive pivot gives NaN (cho_factor).  Callers sync before and after.
+// Lane r keeps row r of L in registers (fully unrolled), so a column costs one broadcast shared-memory load per
+// term, one shuffle for the pivot and one rsqrt; the inverse reuses the reciprocal pivots (no divisions).
+__device__ __forceinline__ void factor_invert_warp(Smem& sm) {
+    const int r = threadIdx.x;  // lane r owns row r
+    double lr[NB];
+    double dinv = 0.0;          // 1 / L[r][r]
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        double s0 = sm.L[r][c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int q = 0; q < c; ++q) {
+            const double lcq = sm.L[c][q];
+            if ((q & 3) == 0) s0 = fma(-lr[q], lcq, s0);
+            else if ((q & 3) == 1) s1 = fma(-lr[q], lcq, s1);
+            else if ((q & 3) == 2) s2 = fma(-lr[q], lcq, s2);
+            else s3 = fma(-lr[q], lcq, s3);
+        }
+        const double sv = (s0 + s1) + (s2 + s3);
+        const double piv = __shfl_sync(0xffffffffu, sv, c);
+        const double inv = rsqrt(piv);  // NaN for piv < 0
+        const double v = (r == c) ? piv * inv : (r > c ? sv * inv : 0.0);
+        lr[c] = v;
+        sm.L[r][c] = v;
+        if (r == c) dinv = inv;
+        __syncwarp();
+    }
+    // Li = L^-1 (lower): lane cc solves L x = e_cc by forward substitution
+    const int cc = threadIdx.x;
+    double x[NB];
+#pragma unroll
+    for (int rr = 0; rr < NB; ++rr) {
+        double s0 = (rr == cc) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int q = 0; q < rr; ++q) {
+            const double l = sm.L[rr][q];
+            if ((q & 3) == 0) s0 = fma(-l, x[q], s0);
+            else if ((q & 3) == 1) s1 = fma(-l, x[q], s1);
+            else if ((q & 3) == 2) s2 = fma(-l, x[q], s2);
+            else s3 = fma(-l, x[q], s3);
+        }
+        x[rr] = ((s0 + s1) + (s2 + s3)) * __shfl_sync(0xffffffffu, dinv, rr);
+    }
+#pragma unroll
+    for (int rr = 0; rr < NB; ++rr) sm.Li[rr][cc] = x[rr];
+}
+
+// ---- single-CTA form (batched problems: one CTA per matrix), left-looking --------------------------------
 // D_j = S_jj - sum_{p<j} L_jp L_jp^T  ->  sm.L = chol(D_j), sm.Li = its inverse.  All threads call.
 __device__ void panel_factor(const double* T, int ld, int j, Smem& sm) {
     double acc[2][2];
@@ -122,42 +195,7 @@ __device__ void panel_factor(const double* T, int ld, int j, Smem& sm) {
             sm.L[rr][cc] = ldg(rowj + (size_t)rr * ld + j * NB + cc) - acc[r][c];
         }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        const int r = threadIdx.x;
-        // Cholesky-Crout by columns; lane r owns row r.  A non-positive pivot gives NaN (cho_factor).
-        for (int c = 0; c < NB; ++c) {
-            double s0 = sm.L[r][c], s1 = 0.0;
-            int q = 0;
-            for (; q + 1 < c; q += 2) {
-                s0 = fma(-sm.L[r][q], sm.L[c][q], s0);
-                s1 = fma(-sm.L[r][q + 1], sm.L[c][q + 1], s1);
-            }
-            if (q < c) s0 = fma(-sm.L[r][q], sm.L[c][q], s0);
-            const double s = s0 + s1;
-            const double piv = __shfl_sync(0xffffffffu, s, c);
-            const double lcc = sqrt(piv);  // NaN for piv < 0
-            const double inv = 1.0 / lcc;
-            __syncwarp();
-            sm.L[r][c] = (r == c) ? lcc : (r > c ? s * inv : 0.0);
-            __syncwarp();
-        }
-        // Li = L^-1 (lower): lane cc solves L x = e_cc by forward substitution
-        const int cc = threadIdx.x;
-        double x[NB];
-#pragma unroll
-        for (int rr = 0; rr < NB; ++rr) {
-            double s0 = (rr == cc) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-            for (int q = 0; q + 1 < rr; q += 2) {
-                s0 = fma(-sm.L[rr][q], x[q], s0);
-                s1 = fma(-sm.L[rr][q + 1], x[q + 1], s1);
-            }
-            if (rr & 1) s0 = fma(-sm.L[rr][rr - 1], x[rr - 1], s0);
-            x[rr] = (s0 + s1) / sm.L[rr][rr];
-        }
-#pragma unroll
-        for (int rr = 0; rr < NB; ++rr) sm.Li[rr][cc] = x[rr];
-    }
+    if (threadIdx.x < 32) factor_invert_warp(sm);
     __syncthreads();
 }
 
@@ -194,33 +232,6 @@ __device__ void panel_apply(double* T, int ld, int j, int i, Smem& sm) {
         }
 }
 
-// all panels, row blocks spread over the CTAs of the grid (one grid barrier per panel).  An optional second,
-// independent system of the same width (T2: the masked innovation covariance of the log-likelihood) is swept in
-// the same phases by the last quarter of the grid.
-__device__ void chol_stack_grid(double* T, int n, int rows, double* T2, int rows2, Smem& sm, GridSync& gs) {
-    const int nsq = n / NB, ntot = rows / NB, ntot2 = T2 ? rows2 / NB : 0;
-    const int G = gridDim.x;
-    const int G2 = T2 ? (G / 4 > 0 ? G / 4 : 1) : 0, G1 = G - G2;
-    for (int j = 0; j < nsq; ++j) {
-        const int b = blockIdx.x;
-        if (b < G1) {
-            const int nact = ntot - j;  // row blocks j .. ntot-1
-            if (b < nact) {
-                panel_factor(T, n, j, sm);
-                for (int a = b; a < nact; a += G1) panel_apply(T, n, j, j + a, sm);
-            }
-        } else {
-            const int nact = ntot2 - j, b2 = b - G1;
-            if (b2 < nact) {
-                panel_factor(T2, n, j, sm);
-                for (int a = b2; a < nact; a += G2) panel_apply(T2, n, j, j + a, sm);
-            }
-        }
-        gs.sync();
-    }
-}
-
-// all panels inside one CTA (batched problems: one CTA per matrix)
 __device__ void chol_stack_cta(double* T, int n, int rows, Smem& sm) {
     const int nsq = n / NB, ntot = rows / NB;
     for (int j = 0; j < nsq; ++j) {
@@ -228,6 +239,196 @@ __device__ void chol_stack_cta(double* T, int n, int rows, Smem& sm) {
         for (int i = j; i < ntot; ++i) panel_apply(T, n, j, i, sm);
         __syncthreads();
         __threadfence_block();
+    }
+}
+
+// ---- grid form: row blocks owned by CTAs, one grid barrier per panel, look-ahead ---------------------------
+// The sequential chain of a blocked Cholesky is: column block j of row block j+1 -> diagonal block j+1 -> its
+// factor.  Everything else is kept off that chain:
+//   * each row block has an owner CTA; in phase j the owner forms its block of column j from the part
+//     accumulated ahead of time (Pacc, all panels p < j-1) plus ONE rank-32 term (panel j-1), and solves it
+//     against the published inverse factor of diagonal block j;
+//   * owners keep their own diagonal block up to date (right-looking, rank-32 per phase), so the owner of row
+//     block j+1 can factor and invert it at once and publish L_{j+1}^-1 (double-buffered) before the barrier;
+//   * meanwhile the other owners accumulate Pacc for phase j+1 (the long k-loop), overlapping the factorisation.
+struct ChSys {
+    double* T;      // [rows, n]
+    int n, rows;
+    double* Pacc;   // [rows/32][32*32]  look-ahead accumulators
+    double* Lpub;   // [2][32*32]        published inverse factors
+};
+
+__device__ __forceinline__ void publish_factor(const ChSys& s, int jb, Smem& sm) {
+    // sm.L holds the fully updated diagonal block jb: factor, invert, write L to T[jb, jb] and L^-1 to Lpub[jb & 1]
+    __syncthreads();
+    long long tp = clock64();
+    if (threadIdx.x < 32) factor_invert_warp(sm);
+    __syncthreads();
+    ST_PROF(8, tp);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double* out = s.T + (size_t)jb * NB * s.n + jb * NB;
+    double* lp = s.Lpub + (size_t)(jb & 1) * NB * NB;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int rr = ty + 16 * r, cc = tx + 16 * c;
+            out[(size_t)rr * s.n + cc] = sm.L[rr][cc];
+            lp[rr * NB + cc] = sm.Li[rr][cc];
+        }
+}
+
+__device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) {
+    const int nsq = s.n / NB, ntot = s.rows / NB, ld = s.n;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    // first owned row block > j:  i = lb (mod LG)
+    int i0 = lb;
+    if (i0 <= j) i0 += ((j - i0) / LG + 1) * LG;
+    if (i0 >= ntot) return;
+    const double* lp = s.Lpub + (size_t)(j & 1) * NB * NB;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) sm.Li[ty + 16 * r][tx + 16 * c] = ldg(lp + (ty + 16 * r) * NB + tx + 16 * c);
+    if (j > 0) {
+        const double* xb = s.T + (size_t)j * NB * ld + (j - 1) * NB;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) sm.XB[ty + 16 * r][tx + 16 * c] = ldg(xb + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
+    }
+    for (int i = i0; i < ntot; i += LG) {
+        double* out = s.T + (size_t)i * NB * ld + j * NB;
+        __syncthreads();
+        if (j > 0) {
+            const double* xa = s.T + (size_t)i * NB * ld + (j - 1) * NB;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) sm.XA[ty + 16 * r][tx + 16 * c] = ldg(xa + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
+        }
+        double v[2][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int rr = ty + 16 * r, cc = tx + 16 * c;
+                v[r][c] = ldg(out + (size_t)rr * ld + cc);
+                if (j > 1) v[r][c] -= ldg(s.Pacc + (size_t)i * NB * NB + rr * NB + cc);
+            }
+        __syncthreads();
+        if (j > 0) {
+#pragma unroll 8
+            for (int k = 0; k < NB; ++k) {
+                const double a0 = sm.XA[ty][k], a1 = sm.XA[ty + 16][k], b0 = sm.XB[tx][k], b1 = sm.XB[tx + 16][k];
+                v[0][0] = fma(-a0, b0, v[0][0]); v[0][1] = fma(-a0, b1, v[0][1]);
+                v[1][0] = fma(-a1, b0, v[1][0]); v[1][1] = fma(-a1, b1, v[1][1]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) sm.X[ty + 16 * r][tx + 16 * c] = v[r][c];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int rr = ty + 16 * r, cc = tx + 16 * c;
+                double s0 = 0.0, s1 = 0.0;
+                int q = 0;
+                for (; q + 1 <= cc; q += 2) {
+                    s0 = fma(sm.X[rr][q], sm.Li[cc][q], s0);
+                    s1 = fma(sm.X[rr][q + 1], sm.Li[cc][q + 1], s1);
+                }
+                if (q <= cc) s0 = fma(sm.X[rr][q], sm.Li[cc][q], s0);
+                const double o = s0 + s1;
+                out[(size_t)rr * ld + cc] = o;
+                sm.XO[rr][cc] = o;
+            }
+        __syncthreads();
+        if (i < nsq) {  // keep the own diagonal block current: T[i,i] -= X_ij X_ij^T
+            double* dg = s.T + (size_t)i * NB * ld + i * NB;
+            double w[2][2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) w[r][c] = ldg(dg + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
+#pragma unroll 8
+            for (int k = 0; k < NB; ++k) {
+                const double a0 = sm.XO[ty][k], a1 = sm.XO[ty + 16][k], b0 = sm.XO[tx][k], b1 = sm.XO[tx + 16][k];
+                w[0][0] = fma(-a0, b0, w[0][0]); w[0][1] = fma(-a0, b1, w[0][1]);
+                w[1][0] = fma(-a1, b0, w[1][0]); w[1][1] = fma(-a1, b1, w[1][1]);
+            }
+            if (i == j + 1) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) sm.L[ty + 16 * r][tx + 16 * c] = w[r][c];
+                publish_factor(s, i, sm);
+                if (i + LG < ntot) {  // more owned row blocks in this phase: bring back the inverse factor of block j
+                    __syncthreads();
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            sm.Li[ty + 16 * r][tx + 16 * c] = ldg(lp + (ty + 16 * r) * NB + tx + 16 * c);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) dg[(size_t)(ty + 16 * r) * ld + tx + 16 * c] = w[r][c];
+            }
+        }
+    }
+    // look-ahead for phase j+1: Pacc[i] = sum_{p<j} X_ip X_{j+1,p}^T  (every operand final since phase j-1)
+    if (j >= 1 && j + 1 < nsq) {
+        long long tl = clock64();
+        const bool last_owner = (ntot - 1) % LG == lb;
+        for (int i = i0; i < ntot; i += LG) {
+            if (i <= j + 1) continue;
+            double acc[2][2];
+            tile_nt<32, 32, false>(s.T + (size_t)i * NB * ld, ld, NB, s.T + (size_t)(j + 1) * NB * ld, ld, NB, j * NB, 0, 0,
+                                   nullptr, acc, sm);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    s.Pacc[(size_t)i * NB * NB + (ty + 16 * r) * NB + tx + 16 * c] = acc[r][c];
+        }
+        if (last_owner && threadIdx.x == 0) {
+            const long long dtl = clock64() - tl;
+            atomicAdd((unsigned long long*)&g_prof[6], (unsigned long long)dtl);
+            atomicAdd((unsigned long long*)&g_prof[5], (unsigned long long)(-dtl));
+        }
+    }
+}
+
+// all panels of one or two independent systems of the same width (the second one -- the masked innovation
+// covariance of the log-likelihood -- is swept in the same phases by the last quarter of the grid)
+__device__ void chol_stack_grid(const ChSys& s1, const ChSys& s2, Smem& sm, GridSync& gs) {
+    const int G = gridDim.x, b = blockIdx.x;
+    const int G2 = s2.T ? (G / 4 > 0 ? G / 4 : 1) : 0, G1 = G - G2;
+    const ChSys& s = (b < G1) ? s1 : s2;
+    const int lb = (b < G1) ? b : b - G1, LG = (b < G1) ? G1 : G2;
+    const int nsq = s1.n / NB;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    if (lb == 0) {  // diagonal block 0 needs no update
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) sm.L[ty + 16 * r][tx + 16 * c] = ldg(s.T + (size_t)(ty + 16 * r) * s.n + tx + 16 * c);
+        publish_factor(s, 0, sm);
+    }
+    gs.sync();
+    const bool last_owner = (b < G1) && ((s1.rows / NB - 1) % LG == lb);
+    for (int j = 0; j < nsq; ++j) {
+        long long t0 = clock64();
+        chol_sys_phase(s, j, lb, LG, sm);
+        if (last_owner) ST_PROF(5, t0);
+        gs.sync();
+        if (last_owner) ST_PROF(7, t0);
     }
 }
 
@@ -303,6 +504,8 @@ struct FilterArgs {
     double* covs;         // [N,d,d]
     double* T;            // [(Mp + dp + 32) x Mp]
     double* T2;           // [(Mp + 32) x Mp]   masked system of the log-likelihood (mask != null)
+    double* Pacc;         // look-ahead accumulators of both systems
+    double* Lpub;         // published inverse factors of both systems [2][2][32*32]
     double* Pcur;         // [d,d]   filtered covariance of the previous step when return_predict
     double* mcur;         // [d]
     double* ellacc;       // 1
@@ -312,7 +515,8 @@ struct FilterArgs {
 template <int FAM>
 __global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
     constexpr int n = FamilyDim<FAM>::value;
-    __shared__ Smem sm;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
     GridSync gs{a.ctr, 0ULL};
     const int M = a.M, d = M * n, Mp = pad32(M), dp = pad32(d);
     const int rows = Mp + dp + NB;
@@ -333,6 +537,7 @@ __global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
     double ell_reg = 0.0;  // lives in lane 0 of warp 0 of the last CTA
     gs.sync();
     for (long long k = 0; k < a.N; ++k) {
+        long long tp0 = clock64();
         // ---- predict + assemble: P^- = A P A^T + Q -> covs[k];  T = [H P^- H^T + R ; P^- H^T ; (y - H m^-)^T]
         TBlock<FAM> tb;
         tb.init(a.spec, a.dt[k]);
@@ -379,9 +584,16 @@ __global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
             T[(size_t)(Mp + dp) * Mp + i] = res;
             if (T2) T2[(size_t)Mp * Mp + i] = a.mask[(size_t)k * M + i] ? 0.0 : res;
         }
+        if (blockIdx.x == 0) ST_PROF(0, tp0);
         gs.sync();
+        if (blockIdx.x == 0) ST_PROF(1, tp0);
         // ---- S = L L^T;  X = P^- H^T L^-T;  z = L^-1 (y - H m^-)
-        chol_stack_grid(T, Mp, rows, T2, rows2, sm, gs);
+        {
+            const ChSys s1{T, Mp, rows, a.Pacc, a.Lpub};
+            const ChSys s2{T2, Mp, rows2, a.Pacc + (size_t)(rows / NB) * NB * NB, a.Lpub + 2 * NB * NB};
+            chol_stack_grid(s1, s2, sm, gs);
+        }
+        if (blockIdx.x == 0) ST_PROF(2, tp0);
         // ---- P = P^- - X X^T;  m = m^- + X z;  ell += log N(y | H m^-, S)   (ops.py:163-172)
         const double* X = T + (size_t)Mp * Mp;
         const double* z = T + (size_t)(Mp + dp) * Mp;
@@ -427,63 +639,48 @@ __global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
                 if (lane == 0) ell_reg += -0.5 * (q + M * 1.8378770664093453 + 2.0 * ld);
             }
         }
+        if (blockIdx.x == 0) ST_PROF(3, tp0);
         gs.sync();
+        if (blockIdx.x == 0) ST_PROF(4, tp0);
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && a.ell) *a.ell = ell_reg;
 }
 
 // ---- smoother ----------------------------------------------------------------------------------------------
-struct SmootherArgs {
+// The smoother gain G_k = fP_k A^T (A fP_k A^T + Q)^-1 (ops.py:293-296) depends on the FILTER output only, not on
+// the backward recursion, so the factorisations of all time steps are independent: a batched kernel (one CTA per
+// time step) forms every gain, and the sequential part that remains is two tile products per step,
+//     sP_k = fP_k + G_k (sP_{k+1} - P^-_k) G_k^T,    sm_k = fm_k + G_k (sm_{k+1} - A fm_k)      (ops.py:297-298).
+struct GainArgs {
     bn_kernel_spec spec;
     int M;
-    long long N;
+    long long k0, k1;     // time steps [k0, k1)
     const double* dt;     // step OUT OF k (basemodels.py:700)
-    const double* fm;     // [N,d]
     const double* fP;     // [N,d,d]
-    int return_full;
-    double* means;        // [N,M] or [N,d]
-    double* covs;         // [N,M,M] or [N,d,d]
-    double* gains;        // [N,d,d] nullable
-    double* T;            // [(3 dp + 32) x dp]
-    double* sP[2];        // ping-pong full smoothed covariance [d,d]
-    double* smv[2];       // ping-pong full smoothed mean [d]
-    double* G;            // [d,d]
-    double* Dm;           // [d,d]  sP_next - P^-
-    double* Z;            // [d,d]
-    unsigned long long* ctr;
+    double* G;            // gains of step k at G + (k - k0) d d
+    double* T;            // per-CTA slots [3 dp x dp]
 };
 
 template <int FAM>
-__global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
+__global__ void __launch_bounds__(NTH) st_gain_kernel(GainArgs a) {
     constexpr int n = FamilyDim<FAM>::value;
-    __shared__ Smem sm;
-    GridSync gs{a.ctr, 0ULL};
-    const int M = a.M, d = M * n, dp = pad32(d);
-    const int rows = 3 * dp + NB;
-    const long long tid = (long long)blockIdx.x * NTH + threadIdx.x, nthreads = (long long)gridDim.x * NTH;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
+    const int M = a.M, d = M * n, dp = pad32(d), rows = 3 * dp;
+    double* T = a.T + (size_t)blockIdx.x * rows * dp;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double* T = a.T;
-    for (long long e = tid; e < (long long)rows * dp; e += nthreads) {
-        const int r = (int)(e / dp), c = (int)(e % dp);
+    for (int e = threadIdx.x; e < rows * dp; e += NTH) {
+        const int r = e / dp, c = e % dp;
         T[e] = (r == c && r >= d && r < dp) ? 1.0 : 0.0;
     }
-    // the recursion starts from the last filtered state (ops.py:304-305)
-    for (long long e = tid; e < (long long)d * d; e += nthreads) a.sP[1][e] = a.fP[(size_t)(a.N - 1) * d * d + e];
-    for (long long e = tid; e < d; e += nthreads) a.smv[1][e] = a.fm[(size_t)(a.N - 1) * d + e];
-    gs.sync();
-    int cur = 1;  // buffer holding step k+1
-    for (long long k = a.N - 1; k >= 0; --k) {
+    __syncthreads();
+    for (long long k = a.k0 + blockIdx.x; k < a.k1; k += gridDim.x) {
         TBlock<FAM> tb;
         tb.init(a.spec, a.dt[k]);
         const double* fPk = a.fP + (size_t)k * d * d;
-        const double* fmk = a.fm + (size_t)k * d;
-        const double* sPn = a.sP[cur];
-        const double* smn = a.smv[cur];
-        double* sPo = a.sP[cur ^ 1];
-        double* smo = a.smv[cur ^ 1];
-        // ---- T = [P^- ; fP A^T ; I ; (sm_next - A fm)^T],  Dm = sP_next - P^-
-        for (long long e = tid; e < (long long)M * M; e += nthreads) {
-            const int i = (int)(e / M), j = (int)(e % M);
+        // T = [P^- ; fP A^T ; I]
+        for (int e = threadIdx.x; e < M * M; e += NTH) {
+            const int i = e / M, j = e % M;
             double B[n * n], O[n * n];
 #pragma unroll
             for (int p = 0; p < n; ++p)
@@ -496,61 +693,120 @@ __global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
                 for (int q = 0; q < n; ++q) {
                     const size_t r = i * n + p, c = j * n + q;
                     T[r * dp + c] = O[p * n + q];
-                    a.Dm[r * d + c] = ldg(sPn + r * d + c) - O[p * n + q];
-                    double s = 0.0;  // (fP A^T)[r][c] = sum_l fP[r][j n + l] A_t[q][l]
+                    double sv = 0.0;  // (fP A^T)[r][c] = sum_l fP[r][j n + l] A_t[q][l]
 #pragma unroll
-                    for (int l = 0; l < n; ++l) s = fma(B[p * n + l], tb.A[q * n + l], s);
-                    T[(size_t)(dp + r) * dp + c] = s;
+                    for (int l = 0; l < n; ++l) sv = fma(B[p * n + l], tb.A[q * n + l], sv);
+                    T[(size_t)(dp + r) * dp + c] = sv;
                     T[(size_t)(2 * dp + r) * dp + c] = (r == c) ? 1.0 : 0.0;
                 }
         }
-        for (long long i = tid; i < M; i += nthreads) {
-#pragma unroll
-            for (int p = 0; p < n; ++p) {
-                double s = 0.0;
-#pragma unroll
-                for (int q = 0; q < n; ++q) s = fma(tb.A[p * n + q], fmk[i * n + q], s);
-                T[(size_t)(3 * dp) * dp + i * n + p] = ldg(smn + i * n + p) - s;
-            }
-        }
-        gs.sync();
-        // ---- P^- = L L^T;  Y = fP A^T L^-T;  LiT = L^-T;  z = L^-1 (sm_next - A fm)
-        chol_stack_grid(T, dp, rows, nullptr, 0, sm, gs);
+        __syncthreads();
+        __threadfence_block();
+        // P^- = L L^T;  Y = fP A^T L^-T;  LiT = L^-T
+        chol_stack_cta(T, dp, rows, sm);
+        // G = Y L^-1 = Y LiT^T-as-rows  (NT form)
         const double* Y = T + (size_t)dp * dp;
         const double* LiT = T + (size_t)2 * dp * dp;
-        const double* z = T + (size_t)3 * dp * dp;
-        const int tm = (d + 31) / 32, tn = (d + 63) / 64;
-        // ---- G = Y L^-1  (the smoother gain fP A^T (P^-)^-1, ops.py:296);  sm = fm + Y z
-        double* G = a.gains ? a.gains + (size_t)k * d * d : a.G;
-        for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
-            const int i0 = (t / tn) * 32, j0 = (t % tn) * 64;
-            double acc[2][4];
-            tile_nt<32, 64, false>(Y, dp, d, LiT, dp, d, dp, i0, j0, nullptr, acc, sm);
+        double* G = a.G + (size_t)(k - a.k0) * d * d;
+        const int tm = (d + 63) / 64;
+        for (int t = 0; t < tm * tm; ++t) {
+            const int i0 = (t / tm) * 64, j0 = (t % tm) * 64;
+            double acc[4][4];
+            // LiT row j is zero left of column j: start the k-loop at the tile's first row (multiple of 32)
+            tile_nt<64, 64, false>(Y + j0, dp, d, LiT + j0, dp, d, dp - j0, i0, j0, nullptr, acc, sm);
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
                     if (row < d && col < d) G[(size_t)row * d + col] = acc[r][c];
                 }
         }
-        {
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-            for (int row = blockIdx.x * (NTH / 32) + warp; row < d; row += gridDim.x * (NTH / 32)) {
-                double s = 0.0;
-                for (int c = lane; c < d; c += 32) s = fma(ldg(Y + (size_t)row * dp + c), ldg(z + c), s);
+        __syncthreads();
+    }
+}
+
+struct SmootherArgs {
+    bn_kernel_spec spec;
+    int M;
+    long long N;
+    long long k0, k1;     // this launch runs k = k1-1 .. k0
+    int first;            // 1: start the recursion from the last filtered state (ops.py:304-305)
+    const double* dt;
+    const double* fm;     // [N,d]
+    const double* fP;     // [N,d,d]
+    int return_full;
+    double* means;        // [N,M] or [N,d]
+    double* covs;         // [N,M,M] or [N,d,d]
+    const double* G;      // gains of step k at G + (k - k0) d d
+    double* sP;           // [d,d]  full smoothed covariance of the step done last (carried between launches)
+    double* smv;          // [d]
+    double* Dm;           // [d,d]  sP_{k+1} - P^-_k
+    double* v;            // [d]    sm_{k+1} - A_k fm_k
+    double* Z;            // [d,d]
+    unsigned long long* ctr;
+};
+
+// P^-_k[row][col] and (A_k fm_k)[row] from the filtered state of step k, element-wise
+template <int FAM>
+__device__ __forceinline__ double ppred_elem(const TBlock<FAM>& tb, const double* fPk, int d, int row, int col) {
+    constexpr int n = FamilyDim<FAM>::value;
+    const int i = row / n, pa = row % n, j = col / n, pb = col % n;
+    double sv = (i == j) ? tb.Q[pa * n + pb] : 0.0;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                if (lane == 0) {
-                    const double v = fmk[row] + s;
-                    smo[row] = v;
-                    if (a.return_full) a.means[(size_t)k * d + row] = v;
-                    else if (row % n == 0) a.means[(size_t)k * M + row / n] = v;
-                }
-            }
+    for (int p = 0; p < n; ++p) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < n; ++q) t = fma(fPk[(size_t)(i * n + p) * d + j * n + q], tb.A[pb * n + q], t);
+        sv = fma(tb.A[pa * n + p], t, sv);
+    }
+    return sv;
+}
+template <int FAM>
+__device__ __forceinline__ double mpred_elem(const TBlock<FAM>& tb, const double* fmk, int row) {
+    constexpr int n = FamilyDim<FAM>::value;
+    const int i = row / n, pa = row % n;
+    double sv = 0.0;
+#pragma unroll
+    for (int q = 0; q < n; ++q) sv = fma(tb.A[pa * n + q], fmk[i * n + q], sv);
+    return sv;
+}
+
+template <int FAM>
+__global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
+    constexpr int n = FamilyDim<FAM>::value;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
+    GridSync gs{a.ctr, 0ULL};
+    const int M = a.M, d = M * n;
+    const long long tid = (long long)blockIdx.x * NTH + threadIdx.x, nthreads = (long long)gridDim.x * NTH;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tm = (d + 31) / 32, tn = (d + 63) / 64;
+    {   // Dm, v of the first step of this launch from the carried (or last filtered) state
+        const long long k = a.k1 - 1;
+        TBlock<FAM> tb;
+        tb.init(a.spec, a.dt[k]);
+        const double* fPk = a.fP + (size_t)k * d * d;
+        const double* fmk = a.fm + (size_t)k * d;
+        const double* sPn = a.first ? a.fP + (size_t)(a.N - 1) * d * d : a.sP;
+        const double* smn = a.first ? a.fm + (size_t)(a.N - 1) * d : a.smv;
+        for (long long e = tid; e < (long long)d * d; e += nthreads) {
+            const int row = (int)(e / d), col = (int)(e % d);
+            a.Dm[e] = sPn[e] - ppred_elem<FAM>(tb, fPk, d, row, col);
         }
-        gs.sync();
-        // ---- Z = G (sP_next - P^-)   (Dm symmetric: NT form)
+        for (long long e = tid; e < d; e += nthreads) a.v[e] = smn[e] - mpred_elem<FAM>(tb, fmk, (int)e);
+    }
+    gs.sync();
+    for (long long k = a.k1 - 1; k >= a.k0; --k) {
+        long long tp0 = clock64();
+        const double* fPk = a.fP + (size_t)k * d * d;
+        const double* fmk = a.fm + (size_t)k * d;
+        const double* G = a.G + (size_t)(k - a.k0) * d * d;
+        const bool more = k > 0;  // a step k-1 exists (possibly in the next launch): prepare its Dm, v
+        TBlock<FAM> tb;
+        if (more) tb.init(a.spec, a.dt[k - 1]);
+        // ---- Z = G (sP_next - P^-)  (Dm symmetric: NT form);  sm = fm + G v
         for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
             const int i0 = (t / tn) * 32, j0 = (t % tn) * 64;
             double acc[2][4];
@@ -563,8 +819,23 @@ __global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
                     if (row < d && col < d) a.Z[(size_t)row * d + col] = acc[r][c];
                 }
         }
+        for (int row = blockIdx.x * (NTH / 32) + warp; row < d; row += gridDim.x * (NTH / 32)) {
+            double sv = 0.0;
+            for (int c = lane; c < d; c += 32) sv = fma(G[(size_t)row * d + c], ldg(a.v + c), sv);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, off);
+            if (lane == 0) {
+                const double val = fmk[row] + sv;
+                a.smv[row] = val;
+                if (a.return_full) a.means[(size_t)k * d + row] = val;
+                else if (row % n == 0) a.means[(size_t)k * M + row / n] = val;
+            }
+        }
+        if (blockIdx.x == 0) ST_PROF(3, tp0);
         gs.sync();
-        // ---- sP = fP + Z G^T   (ops.py:298)
+        if (blockIdx.x == 0) ST_PROF(4, tp0);
+        // ---- sP = fP + Z G^T (ops.py:298);  next step's Dm = sP - P^-_{k-1},  v = sm - A_{k-1} fm_{k-1}
+        const double* fPm = fPk - (size_t)d * d;
         for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
             const int i0 = (t / tn) * 32, j0 = (t % tn) * 64;
             double acc[2][4];
@@ -575,16 +846,20 @@ __global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
                 for (int c = 0; c < 4; ++c) {
                     const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
                     if (row < d && col < d) {
-                        const double v = fPk[(size_t)row * d + col] + acc[r][c];
-                        sPo[(size_t)row * d + col] = v;
-                        if (a.return_full) a.covs[(size_t)k * d * d + (size_t)row * d + col] = v;
+                        const double val = fPk[(size_t)row * d + col] + acc[r][c];
+                        if (k == a.k0) a.sP[(size_t)row * d + col] = val;  // carried to the next launch
+                        if (more) a.Dm[(size_t)row * d + col] = val - ppred_elem<FAM>(tb, fPm, d, row, col);
+                        if (a.return_full) a.covs[(size_t)k * d * d + (size_t)row * d + col] = val;
                         else if (row % n == 0 && col % n == 0)
-                            a.covs[(size_t)k * M * M + (size_t)(row / n) * M + col / n] = v;
+                            a.covs[(size_t)k * M * M + (size_t)(row / n) * M + col / n] = val;
                     }
                 }
         }
+        if (more)
+            for (long long e = tid; e < d; e += nthreads) a.v[e] = ldg(a.smv + e) - mpred_elem<FAM>(tb, fmk - d, (int)e);
+        if (blockIdx.x == 0) ST_PROF(3, tp0);
         gs.sync();
-        cur ^= 1;
+        if (blockIdx.x == 0) ST_PROF(4, tp0);
     }
 }
 
@@ -609,7 +884,8 @@ struct InvArgs {
 
 template <bool PROJECT>
 __global__ void __launch_bounds__(NTH) st_inverse_kernel(InvArgs a) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
     const int n = a.n, np = pad32(n), rows = 2 * np + NB;
     double* T = a.T + (size_t)blockIdx.x * rows * np;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -715,7 +991,8 @@ __global__ void __launch_bounds__(NTH) st_inverse_kernel(InvArgs a) {
 __global__ void __launch_bounds__(NTH) st_to_data_kernel(long long N, int Ns, int M, const double* B, const double* cdiag,
                                                          const double* pm, const double* pV, double* mean_f,
                                                          double* var_f) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
     double* part = &sm.L[0][0];  // 64 x 16 partial sums (fits the 32 x 33 block buffer)
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     for (long long k = blockIdx.x; k < N; k += gridDim.x) {
@@ -760,7 +1037,8 @@ __global__ void __launch_bounds__(NTH) st_to_data_kernel(long long N, int Ns, in
 // T = [R ; V ; I ; (y - m)^T]:  U = V L^-T, LiT = L^-T  =>  tr(R^-1 V) = sum_ij LiT[i][j] U[i][j].
 __global__ void __launch_bounds__(NTH) st_gell_kernel(long long N, int n, const double* y, const double* m, const double* V,
                                                       const double* R, const uint8_t* mask, double* out, double* Tall) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
     __shared__ double red[NTH];
     const int np = pad32(n), rows = 3 * np + NB;
     double* T = Tall + (size_t)blockIdx.x * rows * np;
@@ -813,6 +1091,23 @@ __global__ void __launch_bounds__(NTH) st_gell_kernel(long long N, int n, const 
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
+template <class Kern>
+static cudaError_t allow_smem(Kern k) {
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+}
+
+static cudaError_t zero_prof(cudaStream_t s) {
+    void* p = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(&p, g_prof);
+    return e != cudaSuccess ? e : cudaMemsetAsync(p, 0, sizeof(long long) * 16, s);
+}
+
+static int sm_count();
+static int sm_count_cached() {
+    static int v = 0;
+    if (v == 0) v = sm_count();
+    return v;
+}
 static int sm_count() {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -837,11 +1132,21 @@ struct Carver {
 
 static size_t filter_ws(int M, int n) {
     size_t d = (size_t)M * n, Mp = pad32(M), dp = pad32((int)d);
-    return ((Mp + dp + NB) * Mp + (Mp + NB) * Mp + d * d + d + 64) * sizeof(double) + 8 * 256;
+    return ((Mp + dp + NB) * Mp + (Mp + NB) * Mp + (2 * Mp + dp + 2 * NB) * NB + 4 * NB * NB + d * d + d + 64) * sizeof(double) + 12 * 256;
 }
-static size_t smoother_ws(int M, int n) {
-    size_t d = (size_t)M * n, dp = pad32((int)d);
-    return ((3 * dp + NB) * dp + 5 * d * d + 2 * d + 64) * sizeof(double) + 12 * 256;
+static long long smoother_chunk(long long N, int M, int n) {
+    // time steps per launch pair when the caller does not keep the gains: ~2 GB of gain scratch
+    const size_t d = (size_t)M * n;
+    long long c = (long long)((2ull << 30) / (d * d * sizeof(double)));
+    if (c < 2 * (long long)sm_count_cached()) c = 2 * (long long)sm_count_cached();
+    return c < N ? c : N;
+}
+static size_t smoother_ws(int M, int n, long long N, bool own_gains) {
+    const size_t d = (size_t)M * n, dp = pad32((int)d);
+    const size_t slots = (size_t)(sm_count_cached() < N ? sm_count_cached() : (N > 0 ? N : 1));
+    size_t doubles = slots * 3 * dp * dp + 3 * d * d + 2 * d + 64;
+    if (own_gains) doubles += (size_t)smoother_chunk(N, M, n) * d * d;
+    return doubles * sizeof(double) + 16 * 256;
 }
 static int batch_grid(long long N) {
     long long g = 2LL * sm_count();
@@ -883,7 +1188,7 @@ static int st_check_spec(const bn_kernel_spec* k, int M, int* n_out) {
 extern "C" size_t bn_st_workspace_bytes(const bn_kernel_spec* temporal, int M, int64_t N, int Ns) {
     int n = 0;
     if (st_check_spec(temporal, M, &n) != 0) return 0;
-    size_t a = filter_ws(M, n), b = smoother_ws(M, n), c = inverse_ws(N, M), e = gell_ws(N, M);
+    size_t a = filter_ws(M, n), b = smoother_ws(M, n, N, true), c = inverse_ws(N, M), e = gell_ws(N, M);
     (void)Ns;
     size_t m = a > b ? a : b;
     if (c > m) m = c;
@@ -909,14 +1214,17 @@ extern "C" int bn_st_kalman_filter(const bn_kernel_spec* temporal, int M, int64_
     a.ellacc = cv.take<double>(32);
     a.T = cv.take<double>((Mp + dp + NB) * Mp);
     a.T2 = cv.take<double>((Mp + NB) * Mp);
+    a.Pacc = cv.take<double>(((Mp + dp + NB) / NB + (Mp + NB) / NB) * NB * NB);
+    a.Lpub = cv.take<double>(4 * NB * NB);
     a.Pcur = cv.take<double>(d * d);
     a.mcur = cv.take<double>(d);
     BN_REQUIRE(cv.ok, "workspace carve failed");
     cudaStream_t s = (cudaStream_t)stream;
     BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
+    BN_CUDA(zero_prof(s));
     const int grid = sm_count();
     BN_REQUIRE(grid >= 2, "the dense path needs at least 2 SMs");
-#define CALL(F) BN_LAUNCH("st_filter", s, st_filter_kernel<F><<<grid, NTH, 0, s>>>(a))
+#define CALL(F) BN_CUDA(allow_smem(st_filter_kernel<F>)); BN_LAUNCH("st_filter", s, st_filter_kernel<F><<<grid, NTH, kSmemBytes, s>>>(a))
     ST_DISPATCH_FAMILY(temporal->family, CALL)
 #undef CALL
     BN_CUDA(cudaGetLastError());
@@ -931,29 +1239,40 @@ extern "C" int bn_st_rts_smoother(const bn_kernel_spec* temporal, int M, int64_t
     BN_REQUIRE(N >= 0, "N must be non-negative");
     if (N == 0) return 0;
     BN_REQUIRE(dt && filter_mean && filter_cov && means && covs, "null array");
-    BN_REQUIRE(workspace && workspace_bytes >= smoother_ws(M, n), "workspace too small: %zu bytes needed", smoother_ws(M, n));
+    const size_t need = smoother_ws(M, n, N, gains == nullptr);
+    BN_REQUIRE(workspace && workspace_bytes >= need, "workspace too small: %zu bytes needed", need);
     const size_t d = (size_t)M * n, dp = pad32((int)d);
+    const long long chunk = gains ? (long long)N : smoother_chunk(N, M, n);
+    const int grid = sm_count_cached();
+    const int ggrid = (int)((long long)grid < N ? (long long)grid : N);
     Carver cv{(char*)workspace, workspace_bytes};
+    GainArgs g;
+    g.spec = *temporal; g.M = M; g.dt = dt; g.fP = filter_cov;
     SmootherArgs a;
     a.spec = *temporal; a.M = M; a.N = N; a.dt = dt; a.fm = filter_mean; a.fP = filter_cov; a.return_full = return_full;
-    a.means = means; a.covs = covs; a.gains = gains;
+    a.means = means; a.covs = covs;
     a.ctr = cv.take<unsigned long long>(32);
-    a.T = cv.take<double>((3 * dp + NB) * dp);
-    a.sP[0] = cv.take<double>(d * d);
-    a.sP[1] = cv.take<double>(d * d);
-    a.smv[0] = cv.take<double>(d);
-    a.smv[1] = cv.take<double>(d);
-    a.G = cv.take<double>(d * d);
+    g.T = cv.take<double>((size_t)ggrid * 3 * dp * dp);
+    a.sP = cv.take<double>(d * d);
+    a.smv = cv.take<double>(d);
     a.Dm = cv.take<double>(d * d);
+    a.v = cv.take<double>(d);
     a.Z = cv.take<double>(d * d);
+    double* gbuf = gains ? gains : cv.take<double>((size_t)chunk * d * d);
     BN_REQUIRE(cv.ok, "workspace carve failed");
     cudaStream_t s = (cudaStream_t)stream;
-    BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
-    const int grid = sm_count();
-#define CALL(F) BN_LAUNCH("st_smoother", s, st_smoother_kernel<F><<<grid, NTH, 0, s>>>(a))
-    ST_DISPATCH_FAMILY(temporal->family, CALL)
+    BN_CUDA(zero_prof(s));
+    for (long long k1 = N; k1 > 0; k1 -= chunk) {
+        const long long k0 = k1 - chunk > 0 ? k1 - chunk : 0;
+        g.k0 = k0; g.k1 = k1; g.G = gains ? gains + (size_t)k0 * d * d : gbuf;
+        a.k0 = k0; a.k1 = k1; a.G = g.G; a.first = (k1 == N);
+        BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
+#define CALL(F) BN_CUDA(allow_smem(st_gain_kernel<F>)); BN_LAUNCH("st_gain", s, st_gain_kernel<F><<<ggrid, NTH, kSmemBytes, s>>>(g)); \
+                BN_CUDA(allow_smem(st_smoother_kernel<F>)); BN_LAUNCH("st_smoother", s, st_smoother_kernel<F><<<grid, NTH, kSmemBytes, s>>>(a))
+        ST_DISPATCH_FAMILY(temporal->family, CALL)
 #undef CALL
-    BN_CUDA(cudaGetLastError());
+        BN_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -968,7 +1287,8 @@ extern "C" int bn_spd_inverse_batched(int64_t N, int n, const double* A, const d
     a.N = N; a.n = n; a.Ns = 0; a.A = A; a.rhs_s = rhs; a.jitter = jitter; a.S = nullptr; a.inv = inv; a.sol = sol;
     a.logdet = logdet; a.T = (double*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
-    BN_LAUNCH("st_inverse", s, st_inverse_kernel<false><<<batch_grid(N), NTH, 0, s>>>(a));
+    BN_CUDA(allow_smem(st_inverse_kernel<false>));
+    BN_LAUNCH("st_inverse", s, st_inverse_kernel<false><<<batch_grid(N), NTH, kSmemBytes, s>>>(a));
     BN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -984,7 +1304,8 @@ extern "C" int bn_st_pseudo_lik(int64_t N, int Ns, int M, const double* Bt, cons
     a.N = N; a.n = M; a.Ns = Ns; a.Bt = Bt; a.lam = nat2_diag; a.rhs_s = nat1; a.jitter = jitter; a.S = nat2_full;
     a.inv = pseudo_var; a.sol = pseudo_y; a.logdet = logdet; a.T = (double*)workspace;
     cudaStream_t s = (cudaStream_t)stream;
-    BN_LAUNCH("st_pseudo_lik", s, st_inverse_kernel<true><<<batch_grid(N), NTH, 0, s>>>(a));
+    BN_CUDA(allow_smem(st_inverse_kernel<true>));
+    BN_LAUNCH("st_pseudo_lik", s, st_inverse_kernel<true><<<batch_grid(N), NTH, kSmemBytes, s>>>(a));
     BN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -996,7 +1317,8 @@ extern "C" int bn_st_posterior_to_data(int64_t N, int Ns, int M, const double* B
     if (N == 0) return 0;
     BN_REQUIRE(B && post_mean && post_cov && mean_f && var_f, "null array");
     cudaStream_t s = (cudaStream_t)stream;
-    BN_LAUNCH("st_to_data", s, st_to_data_kernel<<<batch_grid(N), NTH, 0, s>>>(N, Ns, M, B, cdiag, post_mean, post_cov, mean_f, var_f));
+    BN_CUDA(allow_smem(st_to_data_kernel));
+    BN_LAUNCH("st_to_data", s, st_to_data_kernel<<<batch_grid(N), NTH, kSmemBytes, s>>>(N, Ns, M, B, cdiag, post_mean, post_cov, mean_f, var_f));
     BN_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1009,11 +1331,20 @@ extern "C" int bn_st_gaussian_expected_log_lik(int64_t N, int M, const double* p
     BN_REQUIRE(pseudo_y && post_mean && post_cov && pseudo_var && values, "null array (values[N] is required)");
     BN_REQUIRE(workspace && workspace_bytes >= gell_ws(N, M), "workspace too small: %zu bytes needed", gell_ws(N, M));
     cudaStream_t s = (cudaStream_t)stream;
-    BN_LAUNCH("st_gell", s, st_gell_kernel<<<batch_grid(N), NTH, 0, s>>>(N, M, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, (double*)workspace));
+    BN_CUDA(allow_smem(st_gell_kernel));
+    BN_LAUNCH("st_gell", s, st_gell_kernel<<<batch_grid(N), NTH, kSmemBytes, s>>>(N, M, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, (double*)workspace));
     BN_CUDA(cudaGetLastError());
     if (sum) {
         BN_LAUNCH("sum", s, sum_kernel<false><<<1, 1024, 0, s>>>(values, N, sum, 1.0));
         BN_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+extern "C" int bn_st_profile(int64_t* cycles_host, int n) {
+    BN_REQUIRE(cycles_host && n >= 1 && n <= 16, "bad arguments");
+    long long tmp[16];
+    BN_CUDA(cudaMemcpyFromSymbol(tmp, g_prof, sizeof(tmp)));  // synchronises with the default stream's work
+    for (int i = 0; i < n; ++i) cycles_host[i] = tmp[i];
     return 0;
 }

@@ -294,6 +294,11 @@ int bn_st_rts_smoother(const bn_kernel_spec* temporal, int M, int64_t N,
                        double* means, double* covs, double* gains,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* measurement aid: SM cycles per phase of the LAST bn_st_kalman_filter / bn_st_rts_smoother launch, summed over time
+ * steps (slots: 0 assemble, 1 its barrier, 2 Cholesky sweep, 3 tile phases, 4 their barriers, 5 panel solve, 6 look-ahead,
+ * 7 barrier wait of the last row block's owner, 8 factor+invert of the diagonal blocks).  Synchronises the device. */
+int bn_st_profile(int64_t* cycles_host, int n);
+
 /* inv_vmap (utils.py:30-35): inv[k] = (A[k] + jitter I)^-1 through the Cholesky factor, one CTA per matrix.
  * Optional: sol[N,n] = inv[k] rhs[k] (rhs[N,n]); logdet[N] = log det (A[k] + jitter I). */
 int bn_spd_inverse_batched(int64_t N, int n, const double* A, const double* rhs, double jitter,

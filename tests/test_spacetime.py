@@ -223,20 +223,55 @@ def test_gpu_golden_spacetime(bn):
     assert abs(float(mg.energy()) - float(ref['energy'])) <= TOL_MISSING * abs(float(ref['energy']))
 
 
+def c4_data(Nt, G=16, missing=0.05):
+    """16 x 16 grid on [-3, 3]^2, unit time steps, 5 % missing observations"""
+    t = np.arange(Nt, dtype=np.float64)
+    a = np.linspace(-3, 3, G)
+    r = np.array([[u, v] for u in a for v in a])
+    R = np.tile(r[None], (Nt, 1, 1))
+    Y = (np.sin(t / 10)[:, None] + np.sin(r[:, 0])[None] + np.cos(r[:, 1])[None]
+         + 0.1 * np.random.default_rng(1).standard_normal((Nt, G * G)))
+    if missing:
+        Y[np.random.default_rng(2).uniform(size=Y.shape) < missing] = np.nan
+    return t, Y, R
+
+
+class _LUInverseOracle(ost.SpatioTemporalMarkovGP):
+    """the same model with the M x M inverse of compute_full_pseudo_lik taken by LU instead of Cholesky: the spread
+    between two correct fp64 algorithms = the rounding floor of the problem"""
+
+    def compute_full_pseudo_lik(self):
+        nat1_full = np.swapaxes(self.B, 1, 2) @ self.site_nat1
+        nat2_full = np.swapaxes(self.B, 1, 2) @ self.site_nat2 @ self.B
+        pv = np.linalg.inv(nat2_full + 1e-12 * np.eye(self.M))
+        pv = 0.5 * (pv + np.swapaxes(pv, 1, 2))
+        return pv @ nat1_full, pv
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('missing', [0.0, 0.05])
 def test_gpu_c4_shape_iteration(bn, missing):
-    """the C4 state size (16 x 16 grid, Matern-3/2 in time: d = 512) on a short horizon against the oracle"""
-    Nt, Ns = 6, 256
-    tol = TOL_MISSING if missing else TOL
-    t, Y, R = st_data(Nt, Ns, seed=1, spatial_dims=2, missing=missing)
-    ko = oracle_kernel('Matern32', 1.0, 5.0, 1.0, R[0], spatial_dims=2)
-    kg = gpu_kernel(bn, 'Matern32', 1.0, 5.0, 1.0, R[0], spatial_dims=2)
+    """the C4 configuration (16 x 16 grid, Matern-3/2 in time and space, d = 512) on a short horizon against the
+    oracle.  Without missing data the bar is 1e-9.  With 5 % missing observations nat2_full has condition number
+    5e9 (sites of missing points have precision 1e-6) and two correct fp64 implementations differ by ~5e-8 in the
+    posterior mean, so the bar is 20x the measured Cholesky-vs-LU spread of the oracle itself."""
+    Nt = 5
+    t, Y, R = c4_data(Nt, missing=missing)
+    z = R[0]
+    ko = oracle_kernel('Matern32', 1.0, 5.0, 1.0, z, spatial_dims=2)
+    kg = gpu_kernel(bn, 'Matern32', 1.0, 5.0, 1.0, z, spatial_dims=2)
     mo = ost.SpatioTemporalMarkovGP(ko, sites.Gaussian(1.0), t, Y, R)
     mg = bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(1.0), X=t, Y=Y, R=R)
     mo.inference(lr=1.0)
     mg.inference(lr=1.0)
     E0, E1 = mo.energy(), float(mg.energy())
-    assert rel_err(np_(mg.posterior_mean), mo.post_mean) < tol
-    assert rel_err(np_(mg.posterior_variance), mo.post_cov) < tol
-    assert abs(E1 - E0) <= tol * abs(E0), (E0, E1)
+    tm = tv = te = TOL
+    if missing:
+        ma = _LUInverseOracle(ko, sites.Gaussian(1.0), t, Y, R)
+        ma.inference(lr=1.0)
+        tm = max(TOL, 20 * rel_err(ma.post_mean, mo.post_mean))
+        tv = max(TOL, 20 * rel_err(ma.post_cov, mo.post_cov))
+        te = max(TOL, 20 * abs(ma.energy() - E0) / abs(E0))
+    assert rel_err(np_(mg.posterior_mean), mo.post_mean) < tm
+    assert rel_err(np_(mg.posterior_variance), mo.post_cov) < tv
+    assert abs(E1 - E0) <= te * abs(E0), (E0, E1)
