@@ -73,6 +73,8 @@ SIGNATURES = {
     'bn_expected_density': (_I, [_SA, _P, _P, _P, _Z, _P]),
     'bn_gaussian_expected_log_lik': (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_ep_pseudo_density': (_I, [_L, _I, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'bn_temporal_conditional': (_I, [_KS, _L, _P, _L, _P, _P, _P, _P, _I, _P, _P, _P]),
+    'bn_likelihood_predict': (_I, [_I, _D, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
     'bn_st_workspace_bytes': (_Z, [_KS, _I, _L, _I]),
     'bn_st_kalman_filter': (_I, [_KS, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     'bn_st_rts_smoother': (_I, [_KS, _I, _L, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),

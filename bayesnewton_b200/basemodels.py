@@ -180,9 +180,36 @@ class MarkovGaussianProcess:
         return (self.posterior_mean if post_mean is None else post_mean,
                 self.posterior_variance if post_cov is None else post_cov)
 
-    def predict(self, X=None):
-        """posterior marginals at the training inputs (test-point prediction: SURVEY section 8f, next)"""
-        if X is not None:
-            raise NotImplementedError('prediction at new inputs is a `next` row (utils.temporal_conditional)')
-        self.update_posterior()
-        return self.posterior_mean.reshape(self.num_data, -1), self.posterior_variance
+    @staticmethod
+    def temporal_conditional(*args, **kwargs):
+        return ops.temporal_conditional(*args, **kwargs)
+
+    def predict(self, X=None, R=None, pseudo_lik_params=None):
+        """posterior of the latent function(s) at test inputs X (basemodels.py:766-816): filter, full-state smoother
+        with gains, then the two-sided conditional on the neighbouring training states (utils.py:99-215) and the
+        measurement model.  Returns (mean, var) squeezed like the reference: [N*] each for one latent."""
+        if R is not None:
+            raise NotImplementedError('spatial test inputs need the spatio-temporal model')
+        X = self.X if X is None else np.asarray(X, dtype=np.float64).reshape(-1)
+        pseudo_y, pseudo_var = self.compute_full_pseudo_lik() if pseudo_lik_params is None else pseudo_lik_params
+        _, (fm, fP) = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
+                                  parallel=self.parallel, want_ell=False)
+        sm, sP, gain = self.smoother(self.dt_smoother, self.kernel, fm, fP, return_full=True, parallel=self.parallel)
+        test_mean, test_var = self.temporal_conditional(self.X, X, sm, sP, gain, self.kernel, return_full=False)
+        return test_mean.squeeze(), test_var.squeeze()
+
+    def predict_y(self, X, R=None, cubature=None):
+        """predictive mean and variance of the observations at X (basemodels.py:165-175)"""
+        if getattr(self.likelihood, 'multi_latent', False):
+            raise NotImplementedError('predict_y for multi-latent likelihoods')
+        mean_f, var_f = self.predict(X, R)
+        return self.likelihood.predict(mean_f.reshape(-1), var_f.reshape(-1), cubature)
+
+    def negative_log_predictive_density(self, X, Y, R=None, cubature=None):
+        """-nanmean_n log E_q[p(y_n | f_n)] at test inputs (basemodels.py:177-193), single-latent likelihoods"""
+        if getattr(self.likelihood, 'multi_latent', False):
+            raise NotImplementedError('negative_log_predictive_density for multi-latent likelihoods')
+        mean_f, var_f = self.predict(X, R)
+        ld = self.likelihood.log_density(np.asarray(Y, dtype=np.float64).reshape(-1), mean_f.reshape(-1), var_f.reshape(-1),
+                                         cubature)
+        return -torch.nanmean(ld)

@@ -81,6 +81,27 @@ class Likelihood:
         dummy_cov = torch.ones((f.numel() // D, D, D), dtype=torch.float64, device=f.device)
         return self._stats(_lib.BN_METHOD_NEWTON, y, f, dummy_cov)
 
+    def log_density(self, y, m, v, cubature=None):
+        """log E_q[p(y|f)] = the EP log-partition at power 1 (likelihoods.py:385-388 / Gaussian :784-795)"""
+        return self._stats(_lib.BN_METHOD_EP, y, m, v, cubature, 1.0)[0]
+
+    def predict(self, mean_f, var_f, cubature=None):
+        """(E[y], Var[y]) at every test point from the latent marginals (likelihoods.py:493-506, 802-803;
+        cubature.py:438-465); single-latent likelihoods"""
+        if self.multi_latent:
+            raise NotImplementedError('predict for multi-latent likelihoods')
+        m, v = as_dev(mean_f).reshape(-1), as_dev(var_f).reshape(-1)
+        N = m.shape[0]
+        my, vy = torch.empty_like(m), torch.empty_like(m)
+        cx = cw = None
+        Q = 0
+        if self.lik_id != _lib.BN_LIK_GAUSSIAN:
+            hx, hw, Q = host_table(cubature, 1)
+            cx, cw = as_dev(hx.reshape(-1)), as_dev(hw)
+        _lib.check(_lib.lib().bn_likelihood_predict(self.lik_id, float(self.lik_param), N, ptr(m), ptr(v), Q, ptr(cx), ptr(cw),
+                                                    ptr(my), ptr(vy), stream_ptr()))
+        return my, vy
+
     def statistical_linear_regression(self, m, v, cubature=None):
         """mu = E_q[E[y|f]], omega, dmu/dm  (cubature.py:374-435); single-latent likelihoods"""
         if self.multi_latent:

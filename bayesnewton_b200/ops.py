@@ -19,7 +19,7 @@ from . import _lib
 from ._util import as_dev, as_mask, ptr, stream_ptr, up_workspace, workspace
 from .kernels import discretise
 
-__all__ = ['update_posterior', 'kalman_filter', 'rauch_tung_striebel_smoother', '_sequential_kf', '_parallel_kf', '_sequential_rts',
+__all__ = ['temporal_conditional', 'update_posterior', 'kalman_filter', 'rauch_tung_striebel_smoother', '_sequential_kf', '_parallel_kf', '_sequential_rts',
            '_parallel_rts', 'process_noise_covariance']
 
 
@@ -171,3 +171,29 @@ def update_posterior(dt, kernel, y, noise_cov, mask=None, want_ell=False, want_g
     _lib.check(_lib.lib().bn_update_posterior(spec, N, ptr(dt), ptr(y), ptr(R), ptr(mk), ptr(ell), ptr(means),
                                               ptr(covs), ptr(ws), nb, stream_ptr()))
     return ell, means, covs
+
+
+def temporal_conditional(X, X_test, mean, cov, gain, kernel, return_full=True):
+    """state distribution at the test inputs from the smoothed states of the neighbouring training inputs
+    (utils.py:122-136).  X: the training inputs, with or without the dummy states at -1e10 / +1e10 the reference's
+    predict() adds (basemodels.py:793-794) -- they are implied either way; mean [N,d,1], cov [N,d,d], gain [N,d,d]
+    from rauch_tung_striebel_smoother(..., return_full=True).  Returns (test_mean [N*,d,1], test_cov [N*,d,d]);
+    return_full=False applies the measurement model as predict() does: ([N*,Df,1], [N*,Df,Df])."""
+    spec = kernel.spec() if hasattr(kernel, 'spec') else None
+    if spec is None:
+        raise NotImplementedError('prediction needs a kernel with an in-library discretisation (kernel.spec())')
+    X = as_dev(X).reshape(-1)
+    if X.numel() >= 2 and float(X[0]) <= -1e10 and float(X[-1]) >= 1e10:
+        X = X[1:-1].contiguous()
+    Xs = as_dev(X_test).reshape(-1)
+    mean, cov, gain = as_dev(mean), as_dev(cov), as_dev(gain)
+    N, Ns = X.shape[0], Xs.shape[0]
+    d = _lib.lib().bn_state_dim(spec)
+    if mean.numel() != N * d or cov.numel() != N * d * d or gain.numel() != N * d * d:
+        raise ValueError('mean, cov, gain must be the full-state smoother output for the %d training inputs' % N)
+    od = d if return_full else spec.n_components
+    tm = torch.empty((Ns, od, 1), dtype=torch.float64, device=X.device)
+    tc = torch.empty((Ns, od, od), dtype=torch.float64, device=X.device)
+    _lib.check(_lib.lib().bn_temporal_conditional(spec, N, ptr(X), Ns, ptr(Xs), ptr(mean), ptr(cov), ptr(gain),
+                                                  int(bool(return_full)), ptr(tm), ptr(tc), stream_ptr()))
+    return tm, tc

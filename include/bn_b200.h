@@ -329,6 +329,21 @@ int bn_st_gaussian_expected_log_lik(int64_t N, int M, const double* pseudo_y, co
                                     double* values, double* sum,
                                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- prediction at test inputs ---------------------------------------------------
+ * temporal_conditional(X_aug, X_test, mean, cov, gain, kernel) (utils.py:122-136 -> predict_from_state :99-120 ->
+ * compute_conditional_statistics :173-215) as MarkovGaussianProcess.predict calls it (basemodels.py:766-816): the
+ * dummy states at -1e10 / +1e10 with (minf, Pinf) are implied, `x` are the N sorted training inputs, mean/cov/gain
+ * the smoother output with return_full=1.  return_full=0 applies H: out_mean[Ns,Df,1], out_cov[Ns,Df,Df];
+ * =1 gives the state: [Ns,d,1], [Ns,d,d].  One thread per test point; state dimension <= 4. */
+int bn_temporal_conditional(const bn_kernel_spec* k, int64_t N, const double* x, int64_t N_test, const double* x_test,
+                            const double* mean, const double* cov, const double* gain, int return_full,
+                            double* out_mean, double* out_cov, void* stream);
+
+/* Likelihood.predict (likelihoods.py:493-506; Gaussian :802-803; predict_cubature cubature.py:438-465) for scalar
+ * latents: mean_y[N], var_y[N] from mean_f[N], var_f[N].  cub_x[Q], cub_w[Q]: DEVICE arrays (unused for Gaussian). */
+int bn_likelihood_predict(int likelihood, double lik_param, int64_t N, const double* mean_f, const double* var_f,
+                          int Q, const double* cub_x, const double* cub_w, double* mean_y, double* var_y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
