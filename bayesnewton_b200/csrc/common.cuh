@@ -81,6 +81,8 @@ constexpr int kNotHandled = -1000;
 #define BN_GROUP_A_A(X) X(1, 1) X(2, 1) X(3, 1) X(4, 1)
 #define BN_GROUP_A_B(X) X(2, 2) X(3, 2) X(4, 2) X(3, 3)
 #define BN_GROUP_A_C(X) X(6, 2)
+// pairs filter of the sparse Markov model (ops.py:383-426): state [u_-; u_+], H = I
+#define BN_GROUP_A_D(X) X(4, 4) X(6, 6)
 
 // sum of n doubles in a fixed order (strided partials, then a shared-memory tree): run-to-run
 // bit-stable, unlike atomics.  NANSUM skips NaNs (np.nansum, inference.py:218).

@@ -10,6 +10,7 @@ int kf_group_m_d(const KfCall&);
 int kf_group_a_a(const KfCall&);
 int kf_group_a_b(const KfCall&);
 int kf_group_a_c(const KfCall&);
+int kf_group_a_d(const KfCall&);
 
 static int kf_dispatch(const KfCall& c) {
     int r;
@@ -25,6 +26,7 @@ static int kf_dispatch(const KfCall& c) {
     if ((r = kf_group_a_a(c)) != kNotHandled) return r;
     if ((r = kf_group_a_b(c)) != kNotHandled) return r;
     if ((r = kf_group_a_c(c)) != kNotHandled) return r;
+    if ((r = kf_group_a_d(c)) != kNotHandled) return r;
     set_error("unsupported (state dim, obs dim) = (%d, %d) for the register-resident filter", c.d, c.D);
     return -1;
 }

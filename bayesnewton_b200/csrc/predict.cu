@@ -7,6 +7,7 @@
 //                             cubature.py:438-465): E[y], Var[y] at each test point.
 #include "common.cuh"
 #include "gen.cuh"
+#include "condstats.cuh"
 
 namespace bn {
 
@@ -45,54 +46,8 @@ __global__ void __launch_bounds__(128) temporal_conditional_kernel(Gen gen, TcAr
     }
     const double xl = ind == 0 ? -1e10 : a.x[ind - 1];
     const double xr = ind == a.N ? 1e10 : a.x[ind];
-    double Af[d * d], Ab[d * d], Qf[symn(d)], Qb[symn(d)];
-    gen.step_dt(xt - xl, Af, Qf);
-    gen.step_dt(xr - xt, Ab, Qb);
-    // Q_mp = Q_back + A_back Q_fwd A_back^T + 1e-8 I;  V = Q_mp^-1 A_back   (utils.py:196-202)
-    double AbQf[d * d];
-    mat_sym<d, d>(Ab, Qf, AbQf);
-    double Qmp[symn(d)];
-    abt_sym<d, d>(AbQf, Ab, Qb, Qmp);
-#pragma unroll
-    for (int i = 0; i < d; ++i) Qmp[sidx(i, i)] += 1e-8;
-    chol<d>(Qmp);
-    double V[d * d];
-#pragma unroll
-    for (int i = 0; i < d * d; ++i) V[i] = Ab[i];
-    chol_solve<d, d>(Qmp, V);
-    // W = Q_fwd V^T;  T = Q_fwd - (A_back Q_fwd)^T V Q_fwd = Q_fwd - W A_back Q_fwd   (:204-207)
-    double W[d * d];
-#pragma unroll
-    for (int i = 0; i < d; ++i)
-#pragma unroll
-        for (int j = 0; j < d; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int l = 0; l < d; ++l) s = fma(Qf[sidx(i, l)], V[j * d + l], s);
-            W[i * d + j] = s;
-        }
-    double Tm[d * d];
-#pragma unroll
-    for (int i = 0; i < d; ++i)
-#pragma unroll
-        for (int j = 0; j < d; ++j) {
-            double s = Qf[sidx(i, j)];
-#pragma unroll
-            for (int l = 0; l < d; ++l) s = fma(-W[i * d + l], AbQf[l * d + j], s);
-            Tm[i * d + j] = s;
-        }
-    // P = [A_fwd - W A_back A_fwd, W]   (:208)
-    double WAb[d * d], P1[d * d];
-    matmul<d, d, d>(W, Ab, WAb);
-#pragma unroll
-    for (int i = 0; i < d; ++i)
-#pragma unroll
-        for (int j = 0; j < d; ++j) {
-            double s = Af[i * d + j];
-#pragma unroll
-            for (int l = 0; l < d; ++l) s = fma(-WAb[i * d + l], Af[l * d + j], s);
-            P1[i * d + j] = s;
-        }
+    double P1[d * d], W[d * d], Tm[d * d];
+    cond_stats(gen, xt - xl, xr - xt, P1, W, Tm);
     // neighbouring smoothed states: augmented with (minf, Pinf) at both ends, gains with a leading zero (utils.py:124-128)
     double ml[d], mr[d], Cl[d * d], Cr[d * d], G[d * d];
     double Pinf[symn(d)];

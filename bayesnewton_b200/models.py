@@ -1,6 +1,7 @@
 """Model classes = inference scheme x Markov GP, assembled by multiple inheritance exactly like the
 reference's glue file (bayesnewton/models.py:118-152, build_model in bayesnewton/__init__.py:13-14)."""
 from .basemodels import MarkovGaussianProcess
+from .sparse import SparseMarkovGaussianProcess
 from .inference import ExpectationPropagation, Newton, PosteriorLinearisation, VariationalInference
 
 
@@ -22,6 +23,11 @@ MarkovLaplaceGP = MarkovNewtonGP
 
 
 class MarkovPosteriorLinearisationGP(PosteriorLinearisation, MarkovGaussianProcess):
+    pass
+
+
+class SparseMarkovVariationalGP(SparseMarkovGaussianProcess):
+    """VI on the sparse Markov GP (models.py of the reference); the VI iteration is built into the base class"""
     pass
 
 

@@ -197,3 +197,9 @@ def temporal_conditional(X, X_test, mean, cov, gain, kernel, return_full=True):
     _lib.check(_lib.lib().bn_temporal_conditional(spec, N, ptr(X), Ns, ptr(Xs), ptr(mean), ptr(cov), ptr(gain),
                                                   int(bool(return_full)), ptr(tm), ptr(tc), stream_ptr()))
     return tm, tc
+
+
+def kalman_filter_pairs(dt, kernel, y, noise_cov, mask=None, parallel=False):
+    """ops.py:383-426 (see sparse.kalman_filter_pairs)"""
+    from .sparse import kalman_filter_pairs as kfp
+    return kfp(dt, kernel, y, noise_cov, mask, parallel)

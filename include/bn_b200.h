@@ -344,6 +344,43 @@ int bn_temporal_conditional(const bn_kernel_spec* k, int64_t N, const double* x,
 int bn_likelihood_predict(int likelihood, double lik_param, int64_t N, const double* mean_f, const double* var_f,
                           int Q, const double* cub_x, const double* cub_w, double* mean_y, double* var_y, void* stream);
 
+/* ---- sparse Markov GP ---------------------------------------------------------
+ * kalman_filter_pairs (ops.py:383-426) = bn_pairs_discretise (construct_pair, :411-419: A_pair = [[0,I],[0,A]],
+ * Q_pair = [[1e-32 I,0],[0,Q]] per transition, [Mt,2n,2n] each) followed by bn_kf_arrays with d = D = 2n, H = I,
+ * m0 = 0, P0 = blockdiag(Pinf, Pinf); the caller drops the first step and keeps the leading n x n blocks (:426).
+ * Single-component Matern-1/2, -3/2, -5/2 kernels (n = 1, 2, 3). */
+int bn_pairs_discretise(const bn_kernel_spec* k, int64_t Mt, const double* dz, double* Apairs, double* Qpairs, void* stream);
+
+/* vmap(build_joint) over the Mt transitions (utils.py:544-553 as called at basemodels.py:996-1006): mean[Mt-1,n,1],
+ * cov[Mt-1,n,n], gain[Mt-1,n,n] = the full-state smoother output at the inducing points; the dummy states (minf, Pinf)
+ * at both ends and the leading zero gain are implied.  joint_mean[Mt,2n,1], joint_cov[Mt,2n,2n]. */
+int bn_build_joint(const bn_kernel_spec* k, int64_t Mt, const double* mean, const double* cov, const double* gain,
+                   double* joint_mean, double* joint_cov, void* stream);
+
+size_t bn_sparse_workspace_bytes(int64_t Mz);
+
+/* The site pass of one VI iteration of SparseMarkovGaussianProcess, full batch, single-latent likelihood: for every data
+ * point conditional_posterior_to_data (basemodels.py:1071-1104, compute_conditional_statistics utils.py:173-215), the
+ * variational expectation (likelihoods.py:363-383), ensure_psd, conditional_data_to_posterior (:1106-1112), newton_update
+ * (inference.py:21-39); per transition group_natural_params (:1114-1138), the damped update (inference.py:83-86) and
+ * reparametrise (basemodels.py:85-100).  x[N] sorted data inputs, y[N] (NaN = missing), z[Mz] sorted inducing inputs,
+ * start[Mz+2]: data of transition m are [start[m], start[m+1]) (ind = searchsorted(Z_aug, x) - 1, utils.py:556-559).
+ * post_mean[Mt,2n,1], post_cov[Mt,2n,2n]: joint posterior (bn_build_joint).  cub_x[Q], cub_w[Q]: HOST arrays.
+ * nat1[Mt,2n,1], nat2[Mt,2n,2n] updated in place; site_mean, site_cov written; diffs[2] (nullable) = mean |d nat|. */
+int bn_sparse_site_update(const bn_kernel_spec* k, int likelihood, double lik_param, int64_t N, int64_t Mz,
+                          const double* x, const double* y, const double* z, const int64_t* start,
+                          const double* post_mean, const double* post_cov,
+                          int Q, const double* cub_x_host, const double* cub_w_host, double lr, int ensure_psd,
+                          double* nat1, double* nat2, double* site_mean, double* site_cov, double* diffs,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* nansum_n E_q[log p(y_n | f_n)] through the same conditional (the likelihood term of energy(), inference.py:197-222) */
+int bn_sparse_expected_density(const bn_kernel_spec* k, int likelihood, double lik_param, int64_t N, int64_t Mz,
+                               const double* x, const double* y, const double* z, const int64_t* start,
+                               const double* post_mean, const double* post_cov,
+                               int Q, const double* cub_x_host, const double* cub_w_host, double* sum,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
