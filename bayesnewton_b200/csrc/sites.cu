@@ -297,6 +297,9 @@ extern "C" int bn_gaussian_expected_log_lik(int64_t N, int D, const double* pseu
     if (D == 1) BN_LAUNCH("gaussian_ell", st, gaussian_ell_kernel<1><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part));
     else if (D == 2) gaussian_ell_kernel<2><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part);
     else if (D == 3) gaussian_ell_kernel<3><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part);
+    // pair sites of the sparse Markov model (2n x 2n blocks, basemodels.py:215-223 through :1021-1031)
+    else if (D == 4) BN_LAUNCH("gaussian_ell", st, gaussian_ell_kernel<4><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part));
+    else if (D == 6) BN_LAUNCH("gaussian_ell", st, gaussian_ell_kernel<6><<<grid, kSiteThreads, 0, st>>>(N, pseudo_y, post_mean, post_cov, pseudo_var, mask, values, part));
     else { set_error("unsupported site dimension %d", D); return -1; }
     BN_CUDA(cudaGetLastError());
     sum_kernel<false><<<1, 1024, 0, st>>>(part, grid, sum, 1.0);

@@ -11,10 +11,9 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from ._util import as_dev, device, ptr, stream_ptr
+from ._util import as_dev, device, ptr, stream_ptr, workspace
 from .basemodels import input_admin
 from .cubature import host_table
-from .spacetime import st_workspace
 
 
 def kalman_filter_pairs(dt, kernel, y, noise_cov, mask=None, parallel=False, want_ell=True):
@@ -152,13 +151,11 @@ class SparseMarkovGaussianProcess:
         """sum over transitions of gaussian_expected_log_lik with full 2n x 2n blocks (basemodels.py:215-223)"""
         pl = self.pseudo_likelihood
         Mt, p = self.num_transitions, 2 * self.state_dim
-        vals = torch.empty((Mt,), dtype=torch.float64, device=pl.mean.device)
         out = torch.zeros((), dtype=torch.float64, device=pl.mean.device)
-        spec = _lib.kernel_spec(_lib.BN_MATERN12, [1.0], [1.0])
-        ws, nb = st_workspace(spec, p, Mt, p)
-        _lib.check(_lib.lib().bn_st_gaussian_expected_log_lik(Mt, p, ptr(pl.mean), ptr(self.posterior_mean),
-                                                              ptr(self.posterior_variance), ptr(pl.covariance), None,
-                                                              ptr(vals), ptr(out), ptr(ws), nb, stream_ptr()))
+        ws, nb = workspace(Mt, 1, 1)
+        _lib.check(_lib.lib().bn_gaussian_expected_log_lik(Mt, p, ptr(pl.mean), ptr(self.posterior_mean),
+                                                           ptr(self.posterior_variance), ptr(pl.covariance), None, None,
+                                                           ptr(out), ptr(ws), nb, stream_ptr()))
         return out
 
     def compute_kl(self):
