@@ -59,13 +59,17 @@ class MarkovGaussianProcess:
     """f ~ GP in SDE form; inference by Kalman filtering / RTS smoothing (basemodels.py:625-764)"""
     method = None   # BN_METHOD_*, set by the inference mixin
     power = 1.0
+    _st_mixin = 'SpatioTemporalMixin'
 
     def __new__(cls, kernel=None, *args, **kwargs):
         # spatio-temporal inputs take the dense path: the overrides of spacetime.SpatioTemporalMixin go in front
         if hasattr(kernel, 'temporal_kernel'):
-            from .spacetime import SpatioTemporalMixin
-            if not issubclass(cls, SpatioTemporalMixin):
-                cls = type(cls.__name__, (SpatioTemporalMixin, cls), {})
+            from . import spacetime
+            mixin = getattr(spacetime, cls._st_mixin)
+            if not issubclass(cls, mixin):
+                cls = type(cls.__name__, (mixin, cls), {})
+        elif cls._st_mixin != 'SpatioTemporalMixin':
+            raise NotImplementedError('the mean-field model is built for spatio-temporal kernels')
         return object.__new__(cls)
 
     def __init__(self, kernel, likelihood, X, Y, R=None, parallel=None):
@@ -213,3 +217,11 @@ class MarkovGaussianProcess:
         ld = self.likelihood.log_density(np.asarray(Y, dtype=np.float64).reshape(-1), mean_f.reshape(-1), var_f.reshape(-1),
                                          cubature)
         return -torch.nanmean(ld)
+
+
+class MarkovMeanFieldGaussianProcess(MarkovGaussianProcess):
+    """basemodels.py:1155-1175: mean-field across the spatial (latent) blocks"""
+    _st_mixin = 'MeanFieldMixin'
+
+
+MarkovMeanFieldGP = MarkovMeanFieldGaussianProcess

@@ -646,6 +646,241 @@ __global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && a.ell) *a.ell = ell_reg;
 }
 
+// ---- mean-field filter / smoother ------------------------------------------------------
+// kalman_filter_meanfield / rauch_tung_striebel_smoother_meanfield (ops.py:429-467, 581-611, 614-650, 681-706): the
+// state covariance is truncated to its M diagonal n x n blocks after every update, so the state is M blocks
+// (means [N,M,n,1], covs [N,M,n,n]) and a step needs of the M x M innovation covariance S = diag(P^-_i[0,0]) + R only
+//     S^-1 r,   diag(S^-1),   log det S:
+// P_i = P^-_i - c_i (S^-1)_ii c_i^T,  m_i = m^-_i + c_i (S^-1 r)_i  with c_i = P^-_i[:,0].  The stacked sweep of
+// T = [S ; I ; r^T] gives LiT = L^-T and z = L^-1 r, hence (S^-1 r)_i = LiT[i,:] z and (S^-1)_ii = |LiT[i,:]|^2.
+struct MfFilterArgs {
+    bn_kernel_spec spec;
+    int M;
+    long long N;
+    const double* dt;
+    const double* y;      // [N,M]
+    const double* R;      // [N,M,M]
+    const uint8_t* mask;  // [N,M] nullable
+    double* ell;          // nullable
+    double* means;        // [N,M,n]
+    double* covs;         // [N,M,n,n]
+    double* T;            // [(2 Mp + 32) x Mp]
+    double* T2;           // [(Mp + 32) x Mp]
+    double* Pacc;
+    double* Lpub;
+    unsigned long long* ctr;
+};
+
+template <int FAM>
+__global__ void __launch_bounds__(NTH) st_mf_filter_kernel(MfFilterArgs a) {
+    constexpr int n = FamilyDim<FAM>::value;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
+    GridSync gs{a.ctr, 0ULL};
+    const int M = a.M, Mp = pad32(M);
+    const int rows = 2 * Mp + NB, rows2 = Mp + NB;
+    const long long tid = (long long)blockIdx.x * NTH + threadIdx.x, nthreads = (long long)gridDim.x * NTH;
+    double* T = a.T;
+    double* T2 = a.mask ? a.T2 : nullptr;
+    for (long long e = tid; e < (long long)rows * Mp; e += nthreads) {
+        const int r = (int)(e / Mp), c = (int)(e % Mp);
+        T[e] = ((r == c && r >= M && r < Mp) || (r - Mp == c && r >= Mp && r < 2 * Mp)) ? 1.0 : 0.0;
+    }
+    if (T2)
+        for (long long e = tid; e < (long long)rows2 * Mp; e += nthreads) {
+            const int r = (int)(e / Mp), c = (int)(e % Mp);
+            T2[e] = (r == c && r >= M) ? 1.0 : 0.0;
+        }
+    double ell_reg = 0.0;
+    gs.sync();
+    for (long long k = 0; k < a.N; ++k) {
+        TBlock<FAM> tb;
+        tb.init(a.spec, a.dt[k]);
+        double* Pk = a.covs + (size_t)k * M * n * n;
+        double* mk = a.means + (size_t)k * M * n;
+        const double* Pprev = Pk - (size_t)M * n * n;
+        const double* mprev = mk - (size_t)M * n;
+        const double* Rk = a.R + (size_t)k * M * M;
+        // ---- predict every block, assemble T = [diag(P^-_i[0,0]) + R ; I ; (y - H m^-)^T]
+        for (long long e = tid; e < (long long)M * M; e += nthreads) {
+            const int i = (int)(e / M), j = (int)(e % M);
+            double Sij = Rk[(size_t)i * M + j];
+            double res = 0.0;
+            if (i == j) {
+                double B[n * n], O[n * n], mp[n];
+#pragma unroll
+                for (int p = 0; p < n * n; ++p) B[p] = (k == 0) ? tb.Pinf[p] : ldg(Pprev + (size_t)i * n * n + p);
+                tb.rotate(B, true, O);
+#pragma unroll
+                for (int p = 0; p < n * n; ++p) Pk[(size_t)i * n * n + p] = O[p];
+#pragma unroll
+                for (int p = 0; p < n; ++p) {
+                    double sv = 0.0;
+                    if (k > 0) {
+#pragma unroll
+                        for (int q = 0; q < n; ++q) sv = fma(tb.A[p * n + q], ldg(mprev + i * n + q), sv);
+                    }
+                    mp[p] = sv;
+                    mk[i * n + p] = sv;
+                }
+                Sij += O[0];
+                res = a.y[(size_t)k * M + i] - mp[0];
+                T[(size_t)(2 * Mp) * Mp + i] = res;
+                if (T2) T2[(size_t)Mp * Mp + i] = a.mask[(size_t)k * M + i] ? 0.0 : res;
+            }
+            T[(size_t)i * Mp + j] = Sij;
+            T[(size_t)(Mp + i) * Mp + j] = (i == j) ? 1.0 : 0.0;
+            if (T2) {
+                const bool mi = a.mask[(size_t)k * M + i] != 0, mj = a.mask[(size_t)k * M + j] != 0;
+                T2[(size_t)i * Mp + j] = (mi || mj) ? ((i == j) ? 0.15915494309189535 : 0.0) : Sij;
+            }
+        }
+        gs.sync();
+        {
+            const ChSys s1{T, Mp, rows, a.Pacc, a.Lpub};
+            const ChSys s2{T2, Mp, rows2, a.Pacc + (size_t)(rows / NB) * NB * NB, a.Lpub + 2 * NB * NB};
+            chol_stack_grid(s1, s2, sm, gs);
+        }
+        // ---- per block: (S^-1)_ii and (S^-1 r)_i from row i of LiT, then the rank-one update of the block
+        const double* LiT = T + (size_t)Mp * Mp;
+        const double* z = T + (size_t)(2 * Mp) * Mp;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int i = blockIdx.x * (NTH / 32) + warp; i < M; i += gridDim.x * (NTH / 32)) {
+            double sii = 0.0, gi = 0.0;
+            for (int c = lane; c < M; c += 32) {
+                const double l = ldg(LiT + (size_t)i * Mp + c);
+                sii = fma(l, l, sii);
+                gi = fma(l, ldg(z + c), gi);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                sii += __shfl_xor_sync(0xffffffffu, sii, off);
+                gi += __shfl_xor_sync(0xffffffffu, gi, off);
+            }
+            if (lane == 0) {
+                double P[n * n], c0[n];
+#pragma unroll
+                for (int p = 0; p < n * n; ++p) P[p] = ldg(Pk + (size_t)i * n * n + p);
+#pragma unroll
+                for (int p = 0; p < n; ++p) c0[p] = P[p * n];
+#pragma unroll
+                for (int p = 0; p < n; ++p) {
+                    mk[i * n + p] = ldg(mk + i * n + p) + c0[p] * gi;
+#pragma unroll
+                    for (int q = 0; q < n; ++q) Pk[(size_t)i * n * n + p * n + q] = P[p * n + q] - c0[p] * sii * P[q];
+                }
+            }
+        }
+        if (blockIdx.x == gridDim.x - 1 && warp == 0) {
+            double q = 0.0, ld = 0.0;
+            const double* Tl = T2 ? T2 : T;
+            const double* zl = T2 ? T2 + (size_t)Mp * Mp : z;
+            for (int c = lane; c < M; c += 32) {
+                const double zc = ldg(zl + c);
+                q = fma(zc, zc, q);
+                ld += log(ldg(Tl + (size_t)c * Mp + c));
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                q += __shfl_xor_sync(0xffffffffu, q, off);
+                ld += __shfl_xor_sync(0xffffffffu, ld, off);
+            }
+            if (lane == 0) ell_reg += -0.5 * (q + M * 1.8378770664093453 + 2.0 * ld);
+        }
+        gs.sync();
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && a.ell) *a.ell = ell_reg;
+}
+
+// independent RTS pass per block: one thread per block, time sequential (ops.py:614-650)
+template <int FAM>
+__global__ void st_mf_smoother_kernel(bn_kernel_spec spec, int M, long long N, const double* dt, const double* fm,
+                                      const double* fP, int return_full, double* means, double* covs, double* gains) {
+    constexpr int n = FamilyDim<FAM>::value;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double sm[n], sP[n * n];
+#pragma unroll
+    for (int p = 0; p < n; ++p) sm[p] = fm[((size_t)(N - 1) * M + i) * n + p];
+#pragma unroll
+    for (int p = 0; p < n * n; ++p) sP[p] = fP[((size_t)(N - 1) * M + i) * n * n + p];
+    for (long long k = N - 1; k >= 0; --k) {
+        TBlock<FAM> tb;
+        tb.init(spec, dt[k]);
+        double f[n], F[n * n], pm[n], AfP[n * n], pP[n * n], Lp[symn(n)], Ct[n * n];
+#pragma unroll
+        for (int p = 0; p < n; ++p) f[p] = fm[((size_t)k * M + i) * n + p];
+#pragma unroll
+        for (int p = 0; p < n * n; ++p) F[p] = fP[((size_t)k * M + i) * n * n + p];
+        matvec<n, n>(tb.A, f, pm);
+        matmul<n, n, n>(tb.A, F, AfP);
+#pragma unroll
+        for (int p = 0; p < n; ++p)
+#pragma unroll
+            for (int q = 0; q < n; ++q) {
+                double sv = tb.Q[p * n + q];
+#pragma unroll
+                for (int l = 0; l < n; ++l) sv = fma(AfP[p * n + l], tb.A[q * n + l], sv);
+                pP[p * n + q] = sv;
+            }
+#pragma unroll
+        for (int p = 0; p < n; ++p)
+#pragma unroll
+            for (int q = 0; q <= p; ++q) Lp[sidx(p, q)] = pP[p * n + q];
+        chol<n>(Lp);
+#pragma unroll
+        for (int p = 0; p < n * n; ++p) Ct[p] = AfP[p];   // C^T = pP^-1 (A fP)
+        chol_solve<n, n>(Lp, Ct);
+        double dm[n], D[n * n], CD[n * n], nm[n], nP[n * n];
+#pragma unroll
+        for (int p = 0; p < n; ++p) dm[p] = sm[p] - pm[p];
+#pragma unroll
+        for (int p = 0; p < n * n; ++p) D[p] = sP[p] - pP[p];
+#pragma unroll
+        for (int p = 0; p < n; ++p) {
+            double sv = f[p];
+#pragma unroll
+            for (int l = 0; l < n; ++l) sv = fma(Ct[l * n + p], dm[l], sv);   // C[p][l] = Ct[l][p]
+            nm[p] = sv;
+#pragma unroll
+            for (int q = 0; q < n; ++q) {
+                double t = 0.0;
+#pragma unroll
+                for (int l = 0; l < n; ++l) t = fma(Ct[l * n + p], D[l * n + q], t);
+                CD[p * n + q] = t;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < n; ++p)
+#pragma unroll
+            for (int q = 0; q < n; ++q) {
+                double sv = F[p * n + q];
+#pragma unroll
+                for (int l = 0; l < n; ++l) sv = fma(CD[p * n + l], Ct[l * n + q], sv);
+                nP[p * n + q] = sv;
+            }
+#pragma unroll
+        for (int p = 0; p < n; ++p) sm[p] = nm[p];
+#pragma unroll
+        for (int p = 0; p < n * n; ++p) sP[p] = nP[p];
+        if (gains) {
+#pragma unroll
+            for (int p = 0; p < n; ++p)
+#pragma unroll
+                for (int q = 0; q < n; ++q) gains[((size_t)k * M + i) * n * n + p * n + q] = Ct[q * n + p];
+        }
+        if (return_full) {
+#pragma unroll
+            for (int p = 0; p < n; ++p) means[((size_t)k * M + i) * n + p] = sm[p];
+#pragma unroll
+            for (int p = 0; p < n * n; ++p) covs[((size_t)k * M + i) * n * n + p] = sP[p];
+        } else {
+            means[(size_t)k * M + i] = sm[0];
+            covs[(size_t)k * M * M + (size_t)i * M + i] = sP[0];
+        }
+    }
+}
+
 // ---- smoother ----------------------------------------------------------------------------------------------
 // The smoother gain G_k = fP_k A^T (A fP_k A^T + Q)^-1 (ops.py:293-296) depends on the FILTER output only, not on
 // the backward recursion, so the factorisations of all time steps are independent: a batched kernel (one CTA per
@@ -1185,12 +1420,14 @@ static int st_check_spec(const bn_kernel_spec* k, int M, int* n_out) {
     return 0;
 }
 
+static size_t mf_filter_ws(int M);
 extern "C" size_t bn_st_workspace_bytes(const bn_kernel_spec* temporal, int M, int64_t N, int Ns) {
     int n = 0;
     if (st_check_spec(temporal, M, &n) != 0) return 0;
     size_t a = filter_ws(M, n), b = smoother_ws(M, n, N, true), c = inverse_ws(N, M), e = gell_ws(N, M);
     (void)Ns;
     size_t m = a > b ? a : b;
+    if (mf_filter_ws(M) > m) m = mf_filter_ws(M);
     if (c > m) m = c;
     if (e > m) m = e;
     return m;
@@ -1273,6 +1510,62 @@ extern "C" int bn_st_rts_smoother(const bn_kernel_spec* temporal, int M, int64_t
 #undef CALL
         BN_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+static size_t mf_filter_ws(int M) {
+    size_t Mp = pad32(M);
+    return ((2 * Mp + NB) * Mp + (Mp + NB) * Mp + (3 * Mp + 2 * NB) * NB + 4 * NB * NB + 64) * sizeof(double) + 12 * 256;
+}
+
+extern "C" int bn_st_kalman_filter_meanfield(const bn_kernel_spec* temporal, int M, int64_t N, const double* dt,
+                                             const double* y, const double* noise_cov, const uint8_t* mask, double* ell,
+                                             double* means, double* covs, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+    int n = 0;
+    if (int rc = st_check_spec(temporal, M, &n)) return rc;
+    BN_REQUIRE(N >= 0, "N must be non-negative");
+    if (N == 0) return 0;
+    BN_REQUIRE(dt && y && noise_cov && means && covs, "null array");
+    BN_REQUIRE(workspace && workspace_bytes >= mf_filter_ws(M), "workspace too small: %zu bytes needed", mf_filter_ws(M));
+    const size_t Mp = pad32(M);
+    Carver cv{(char*)workspace, workspace_bytes};
+    MfFilterArgs a;
+    a.spec = *temporal; a.M = M; a.N = N; a.dt = dt; a.y = y; a.R = noise_cov; a.mask = mask; a.ell = ell;
+    a.means = means; a.covs = covs;
+    a.ctr = cv.take<unsigned long long>(32);
+    a.T = cv.take<double>((2 * Mp + NB) * Mp);
+    a.T2 = cv.take<double>((Mp + NB) * Mp);
+    a.Pacc = cv.take<double>(((2 * Mp + NB) / NB + (Mp + NB) / NB) * NB * NB);
+    a.Lpub = cv.take<double>(4 * NB * NB);
+    BN_REQUIRE(cv.ok, "workspace carve failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
+    BN_CUDA(zero_prof(s));
+    const int grid = sm_count();
+    BN_REQUIRE(grid >= 2, "the dense path needs at least 2 SMs");
+#define CALL(F) BN_CUDA(allow_smem(st_mf_filter_kernel<F>)); BN_LAUNCH("st_mf_filter", s, st_mf_filter_kernel<F><<<grid, NTH, kSmemBytes, s>>>(a))
+    ST_DISPATCH_FAMILY(temporal->family, CALL)
+#undef CALL
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bn_st_rts_smoother_meanfield(const bn_kernel_spec* temporal, int M, int64_t N, const double* dt,
+                                            const double* filter_mean, const double* filter_cov, int return_full,
+                                            double* means, double* covs, double* gains, void* stream) {
+    int n = 0;
+    if (int rc = st_check_spec(temporal, M, &n)) return rc;
+    BN_REQUIRE(N >= 0, "N must be non-negative");
+    if (N == 0) return 0;
+    BN_REQUIRE(dt && filter_mean && filter_cov && means && covs, "null array");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!return_full) BN_CUDA(cudaMemsetAsync(covs, 0, (size_t)N * M * M * sizeof(double), s));
+    const unsigned grid = (unsigned)((M + 63) / 64);
+#define CALL(F) BN_LAUNCH("st_mf_smoother", s, st_mf_smoother_kernel<F><<<grid, 64, 0, s>>>(*temporal, M, N, dt, filter_mean, filter_cov, return_full, means, covs, gains))
+    ST_DISPATCH_FAMILY(temporal->family, CALL)
+#undef CALL
+    BN_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -1,6 +1,6 @@
 """Model classes = inference scheme x Markov GP, assembled by multiple inheritance exactly like the
 reference's glue file (bayesnewton/models.py:118-152, build_model in bayesnewton/__init__.py:13-14)."""
-from .basemodels import MarkovGaussianProcess
+from .basemodels import MarkovGaussianProcess, MarkovMeanFieldGaussianProcess
 from .sparse import SparseMarkovGaussianProcess
 from .inference import ExpectationPropagation, Newton, PosteriorLinearisation, VariationalInference
 
@@ -23,6 +23,11 @@ MarkovLaplaceGP = MarkovNewtonGP
 
 
 class MarkovPosteriorLinearisationGP(PosteriorLinearisation, MarkovGaussianProcess):
+    pass
+
+
+class MarkovVariationalMeanFieldGP(VariationalInference, MarkovMeanFieldGaussianProcess):
+    """models.py:154 of the reference"""
     pass
 
 

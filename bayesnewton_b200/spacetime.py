@@ -172,6 +172,47 @@ def st_rts_smoother(dt, kernel, filter_mean, filter_cov, return_full=False, para
     return means, covs, gains
 
 
+def st_kalman_filter_meanfield(dt, kernel, y, noise_cov, mask=None, parallel=False, block_index=None, want_ell=True):
+    """kalman_filter_meanfield (ops.py:581-611): ell, (means [N,M,n,1], covs [N,M,n,n]); the block structure is
+    implied by the kernel, so block_index is accepted and ignored"""
+    dt = as_dev(dt).reshape(-1)
+    N, M, n = dt.shape[0], kernel.M, kernel.state_dim
+    spec = kernel.spec()
+    y, R = as_dev(y), as_dev(noise_cov)
+    if y.numel() != N * M or R.numel() != N * M * M:
+        raise ValueError('y must be [N,%d,1] and noise_cov [N,%d,%d] for N = %d steps' % (M, M, M, N))
+    mk = as_mask(mask)
+    ell = torch.zeros((), dtype=torch.float64, device=dt.device) if want_ell else None
+    means = torch.empty((N, M, n, 1), dtype=torch.float64, device=dt.device)
+    covs = torch.empty((N, M, n, n), dtype=torch.float64, device=dt.device)
+    ws, nb = st_workspace(spec, M, N, M)
+    _lib.check(_lib.lib().bn_st_kalman_filter_meanfield(spec, M, N, ptr(dt), ptr(y), ptr(R), ptr(mk), ptr(ell), ptr(means),
+                                                        ptr(covs), ptr(ws), nb, stream_ptr()))
+    return ell, (means, covs)
+
+
+def st_rts_smoother_meanfield(dt, kernel, filter_mean, filter_cov, return_full=False, parallel=False, block_index=None,
+                              want_gains=True):
+    """rauch_tung_striebel_smoother_meanfield (ops.py:681-706): (means, covs, gains); covariances and gains of the full
+    state are returned as blocks [N,M,n,n]"""
+    dt = as_dev(dt).reshape(-1)
+    N, M, n = dt.shape[0], kernel.M, kernel.state_dim
+    spec = kernel.spec()
+    fm, fP = as_dev(filter_mean), as_dev(filter_cov)
+    if fm.numel() != N * M * n or fP.numel() != N * M * n * n:
+        raise ValueError('filter_mean must be [N,%d,%d,1] and filter_cov [N,%d,%d,%d]' % (M, n, M, n, n))
+    if return_full:
+        means = torch.empty((N, M * n, 1), dtype=torch.float64, device=dt.device)
+        covs = torch.empty((N, M, n, n), dtype=torch.float64, device=dt.device)
+    else:
+        means = torch.empty((N, M, 1), dtype=torch.float64, device=dt.device)
+        covs = torch.empty((N, M, M), dtype=torch.float64, device=dt.device)
+    gains = torch.empty((N, M, n, n), dtype=torch.float64, device=dt.device) if want_gains else None
+    _lib.check(_lib.lib().bn_st_rts_smoother_meanfield(spec, M, N, ptr(dt), ptr(fm), ptr(fP), int(bool(return_full)),
+                                                       ptr(means), ptr(covs), ptr(gains), stream_ptr()))
+    return means, covs, gains
+
+
 def inv_vmap(P, rhs=None, jitter=0.0, want_logdet=False):
     """utils.py:30-35: batched SPD inverse through the Cholesky factor; optionally P^-1 rhs and log det P"""
     P = as_dev(P)
@@ -348,3 +389,16 @@ class SpatioTemporalMixin:
 
     def predict(self, X=None, R=None):
         raise NotImplementedError('prediction at new inputs is a `next` row (utils.temporal_conditional)')
+
+
+class MeanFieldMixin(SpatioTemporalMixin):
+    """MarkovMeanFieldGaussianProcess (basemodels.py:1155-1175): the spatio-temporal model with the mean-field filter
+    and smoother (independent temporal blocks, coupled only through the M x M innovation)"""
+
+    @staticmethod
+    def filter(*args, **kwargs):
+        return st_kalman_filter_meanfield(*args, **kwargs)
+
+    @staticmethod
+    def smoother(*args, **kwargs):
+        return st_rts_smoother_meanfield(*args, **kwargs)

@@ -63,7 +63,11 @@ class ClockSampler:
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.mark_ = index, [], None, 0
+
+    def mark(self):
+        """samples before this point (start-up of nvidia-smi, warm-up) are not counted"""
+        self.mark_ = len(self.lines)
 
     def start(self):
         try:
@@ -82,7 +86,7 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        for ln in self.lines[self.mark_:]:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 6:
                 continue
@@ -195,12 +199,15 @@ def main_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi needs ~0.1 s to come up: start it before the warm-up, count only what it samples from the first
+    # timed region on (the device-timed steps, then the end-to-end and with-gradient steps: all under the same load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream
-    sampler = ClockSampler(local_rank)
     sync_all()
-    sampler.start()
+    sampler.mark()
     L.bn_timing_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -208,7 +215,6 @@ def main_gpu(args):
         E = step()
     e1.record()
     sync_all()
-    clocks = sampler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -290,6 +296,7 @@ def main_gpu(args):
     if world > 1:
         dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
     grad_ms = float(ms3) / args.steps
+    clocks = sampler.stop()
     cbuf2 = ctypes.create_string_buffer(8192)
 
     # fp64 FMA peak of this device, measured now (the second roofline: at d = 3 the path is fp64-pipe bound)

@@ -381,6 +381,23 @@ int bn_sparse_expected_density(const bn_kernel_spec* k, int likelihood, double l
                                int Q, const double* cub_x_host, const double* cub_w_host, double* sum,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- mean-field spatio-temporal filter / smoother -------------------------------
+ * kalman_filter_meanfield (ops.py:581-611 -> _sequential_kf_mf :429-467): the state covariance keeps only its M
+ * diagonal n x n blocks.  means[N,M,n,1], covs[N,M,n,n] (the reference's block layout); y, noise_cov, mask, ell as
+ * bn_st_kalman_filter.  One persistent kernel; a step costs one M x M stacked Cholesky sweep + O(M^2). */
+int bn_st_kalman_filter_meanfield(const bn_kernel_spec* temporal, int M, int64_t N,
+                                  const double* dt, const double* y, const double* noise_cov, const uint8_t* mask,
+                                  double* ell, double* means, double* covs,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* rauch_tung_striebel_smoother_meanfield (ops.py:681-706 -> _sequential_rts_mf :614-650): an independent RTS pass per
+ * block.  return_full=0: means[N,M,1] = H sm, covs[N,M,M] = H blockdiag(sP) H^T (diagonal, zeros written);
+ * return_full=1: means[N,M n,1], covs as BLOCKS [N,M,n,n] (the reference scatters them into a dense [N,d,d]).
+ * gains (nullable) as blocks [N,M,n,n]. */
+int bn_st_rts_smoother_meanfield(const bn_kernel_spec* temporal, int M, int64_t N,
+                                 const double* dt, const double* filter_mean, const double* filter_cov, int return_full,
+                                 double* means, double* covs, double* gains, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

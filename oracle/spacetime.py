@@ -253,3 +253,102 @@ class DenseSpatioTemporalGP:
         edp = (-0.5 * LOG2PI - 0.5 * np.log(self.site_var)
                - 0.5 * ((self.site_mean - self.post_mean) ** 2 + self.post_var) / self.site_var)
         return -(np.sum(E) - (np.sum(edp) - log_lik))
+
+
+# ------------------------------------------------------------------------------------------- mean-field variants
+def _block_diag_dense(Pb):
+    """build_block_diag (ops.py:431-433): [M,n,n] blocks -> dense [M n, M n]"""
+    M, n = Pb.shape[0], Pb.shape[1]
+    P = np.zeros((M * n, M * n))
+    for i in range(M):
+        P[i * n:(i + 1) * n, i * n:(i + 1) * n] = Pb[i]
+    return P
+
+
+def _get_block_cov(P, M, n):
+    """get_block_cov (ops.py:438-439)"""
+    return np.stack([P[i * n:(i + 1) * n, i * n:(i + 1) * n] for i in range(M)])
+
+
+def kalman_filter_meanfield(dt, kernel, y, noise_cov, mask=None):
+    """kalman_filter_meanfield -> _sequential_kf_mf (ops.py:581-611, 429-467): the state covariance is truncated to its
+    M diagonal n x n blocks after every update.  Returns ell, (means [N,M,n,1], covs [N,M,n,n])."""
+    if mask is None:
+        mask = np.zeros_like(y, dtype=bool)
+    kt, M = kernel.temporal_kernel, kernel.M
+    Pinf_t = kt.stationary_covariance()
+    n = Pinf_t.shape[0]
+    H = kernel.measurement_model()
+    N = y.shape[0]
+    m = np.zeros((M, n, 1))
+    P = np.tile(Pinf_t, (M, 1, 1))
+    ell = 0.0
+    fms, fPs = np.zeros((N, M, n, 1)), np.zeros((N, M, n, n))
+    for k in range(N):
+        A = kt.state_transition(dt[k])
+        Q = Pinf_t - A @ Pinf_t @ A.T
+        mv = (A @ m).reshape(-1, 1)
+        Pd = _block_diag_dense(A @ P @ A.T + Q)
+        obs_mean = H @ mv
+        HP = H @ Pd
+        S = HP @ H.T + noise_cov[k]
+        ell = ell + kalman.mvn_logpdf(y[k], obs_mean, S, mask[k])
+        K = solve(S, HP).T
+        m = (mv + K @ (y[k] - obs_mean)).reshape(M, n, 1)
+        P = _get_block_cov(Pd - K @ HP, M, n)
+        fms[k], fPs[k] = m, P
+    return ell, (fms, fPs)
+
+
+def rts_smoother_meanfield(dt, kernel, fms, fPs, return_full=False):
+    """rauch_tung_striebel_smoother_meanfield -> _sequential_rts_mf (ops.py:681-706, 614-650): an independent RTS pass
+    per block.  return_full=False: (H sm [N,M,1], H blockdiag(sP) H^T [N,M,M], gains [N,M,n,n] as blocks);
+    return_full=True: (sm [N,M n,1], sP as blocks [N,M,n,n], gains as blocks)."""
+    kt, M = kernel.temporal_kernel, kernel.M
+    Pinf_t = kt.stationary_covariance()
+    n = Pinf_t.shape[0]
+    H = kernel.measurement_model()
+    N = fms.shape[0]
+    sm, sP = fms[-1], fPs[-1]
+    means = np.zeros((N, M * n if return_full else M, 1))
+    covs = np.zeros((N, M, n, n)) if return_full else np.zeros((N, M, M))
+    gains = np.zeros((N, M, n, n))
+    for k in range(N - 1, -1, -1):
+        A = kt.state_transition(dt[k])
+        Q = Pinf_t - A @ Pinf_t @ A.T
+        pm = A @ fms[k]
+        AfP = A @ fPs[k]
+        pP = AfP @ A.T + Q
+        C = T(solve(pP, AfP))
+        sm = fms[k] + C @ (sm - pm)
+        sP = fPs[k] + C @ (sP - pP) @ T(C)
+        gains[k] = C
+        if return_full:
+            means[k], covs[k] = sm.reshape(-1, 1), sP
+        else:
+            means[k], covs[k] = H @ sm.reshape(-1, 1), H @ _block_diag_dense(sP) @ H.T
+    return means, covs, gains
+
+
+class SpatioTemporalMeanFieldMarkovGP(SpatioTemporalMarkovGP):
+    """MarkovVariationalMeanFieldGP (models.py:154, basemodels.py:1155-1175): the same model with the mean-field
+    filter and smoother"""
+
+    def update_posterior(self):
+        py, pv = self.compute_full_pseudo_lik()
+        ell, (fm, fP) = kalman_filter_meanfield(self.dt, self.kernel, py, pv, self._mask3())
+        dts = np.concatenate([self.dt[1:], [0.0]])
+        sm, sP, _ = rts_smoother_meanfield(dts, self.kernel, fm, fP)
+        self.filter_mean, self.filter_cov = fm, fP
+        self.post_mean, self.post_cov = sm, sP
+        return ell
+
+    def compute_log_lik(self):
+        py, pv = self.compute_full_pseudo_lik()
+        return kalman_filter_meanfield(self.dt, self.kernel, py, pv, self._mask3())[0]
+
+    def compute_kl(self):
+        py, pv = self.compute_full_pseudo_lik()
+        ell = kalman_filter_meanfield(self.dt, self.kernel, py, pv, self._mask3())[0]
+        edp = sites.gaussian_expected_log_lik(py, self.post_mean, self.post_cov, pv, self._mask3())
+        return np.sum(edp) - ell

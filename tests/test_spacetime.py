@@ -275,3 +275,72 @@ def test_gpu_c4_shape_iteration(bn, missing):
     assert rel_err(np_(mg.posterior_mean), mo.post_mean) < tm
     assert rel_err(np_(mg.posterior_variance), mo.post_cov) < tv
     assert abs(E1 - E0) <= te * abs(E0), (E0, E1)
+
+
+# ------------------------------------------------------------------------------------------------ mean-field (8f row 2)
+def test_oracle_meanfield_is_exact_for_diagonal_noise():
+    """no reference test covers the mean-field filter; pinned by the case where it is exact: with a diagonal
+    noise covariance the blocks never couple, so it must equal M independent filters and the full filter"""
+    rng = np.random.default_rng(0)
+    M, N = 5, 12
+    k = oracle_kernel('Matern32', 1.3, 0.7, 0.5, np.linspace(0, 1, M)[:, None])
+    dt = np.concatenate([[0.0], 0.1 + 0.4 * rng.uniform(size=N - 1)])
+    y = rng.standard_normal((N, M, 1))
+    Rn = np.stack([np.diag(0.3 + rng.uniform(size=M)) for _ in range(N)])
+    ell, (fm, fP) = ost.kalman_filter_meanfield(dt, k, y, Rn)
+    e_ind = 0.0
+    for i in range(M):
+        e_i, (m_i, P_i) = kalman.kalman_filter(dt, k.temporal_kernel, y[:, i:i + 1], Rn[:, i:i + 1, i:i + 1])
+        e_ind += e_i
+        assert rel_err(fm[:, i], m_i) < 1e-12 and rel_err(fP[:, i], P_i) < 1e-12
+    assert abs(ell - e_ind) < 1e-10 * abs(ell)
+    dts = np.concatenate([dt[1:], [0.0]])
+    sm, sP, _ = ost.rts_smoother_meanfield(dts, k, fm, fP)
+    _, (fmf, fPf) = kalman.kalman_filter(dt, k, y, Rn)
+    smf, sPf, _ = kalman.rauch_tung_striebel_smoother(dts, k, fmf, fPf)
+    assert rel_err(sm, smf) < 1e-12 and rel_err(sP, sPf) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fam', ['Matern12', 'Matern32', 'Matern52'])
+@pytest.mark.parametrize('M', [3, 16, 37])
+@pytest.mark.parametrize('masked', [False, True])
+def test_gpu_meanfield_filter_smoother_vs_oracle(bn, fam, M, masked):
+    N = 11
+    rng = np.random.default_rng(M)
+    z = np.linspace(0, 1, M)[:, None]
+    ko = oracle_kernel(fam, 1.3, 0.7, 0.5, z)
+    kg = gpu_kernel(bn, fam, 1.3, 0.7, 0.5, z)
+    dt = np.concatenate([[0.0], 0.1 + 0.4 * rng.uniform(size=N - 1)])
+    y = rng.standard_normal((N, M, 1))
+    Rn = spd_batch(N, M, M + 1)
+    mask = (rng.uniform(size=(N, M, 1)) < 0.2) if masked else None
+    e0, (m0, P0) = ost.kalman_filter_meanfield(dt, ko, y, Rn, mask)
+    e1, (m1, P1) = bn.spacetime.st_kalman_filter_meanfield(dt, kg, y, Rn, mask)
+    assert abs(float(e1) - e0) <= TOL * abs(e0)
+    assert rel_err(np_(m1), m0) < TOL and rel_err(np_(P1), P0) < TOL
+    dts = np.concatenate([dt[1:], [0.0]])
+    for full in (False, True):
+        s0, S0, G0 = ost.rts_smoother_meanfield(dts, ko, m0, P0, return_full=full)
+        s1, S1, G1 = bn.spacetime.st_rts_smoother_meanfield(dts, kg, m0, P0, return_full=full)
+        assert rel_err(np_(s1), s0) < TOL and rel_err(np_(S1), S0) < TOL and rel_err(np_(G1), G0) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', ['full', 'sparse'])
+def test_gpu_meanfield_vi_iteration_vs_oracle(bn, case):
+    """MarkovVariationalMeanFieldGP end to end"""
+    Nt, Ns = 14, 16
+    t, Y, R = st_data(Nt, Ns, seed=7, spatial_dims=2)
+    z = st_data(1, 9, spatial_dims=2)[2][0] if case == 'sparse' else R[0]
+    ko = oracle_kernel('Matern32', 1.1, 0.9, 1.2, z, spatial_dims=2)
+    kg = gpu_kernel(bn, 'Matern32', 1.1, 0.9, 1.2, z, spatial_dims=2)
+    mo = ost.SpatioTemporalMeanFieldMarkovGP(ko, sites.Gaussian(0.3), t, Y, R)
+    mg = bn.models.MarkovVariationalMeanFieldGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(0.3), X=t, Y=Y, R=R)
+    for lr in (1.0, 0.5):
+        mo.inference(lr=lr)
+        mg.inference(lr=lr)
+        E0, E1 = mo.energy(), float(mg.energy())
+        assert rel_err(np_(mg.posterior_mean), mo.post_mean) < TOL
+        assert rel_err(np_(mg.posterior_variance), mo.post_cov) < TOL
+        assert abs(E1 - E0) <= TOL * abs(E0), (E0, E1)
