@@ -38,14 +38,16 @@ __device__ long long g_prof[16];
 #define ST_PROF(slot, t0) do { if (threadIdx.x == 0) { long long t1__ = clock64(); atomicAdd((unsigned long long*)&g_prof[slot], (unsigned long long)(t1__ - (t0))); (t0) = t1__; } } while (0)
 
 struct Smem {
-    double a[BK][65];      // A slab, k-major (odd pitch: conflict-free transposing stores)
-    double b[BK][65];
+    double a[64 * 36];     // A slab: [row][k], pitch 36 (conflict-free DMMA fragment loads)
+    double b[64 * 36];     // B slab
     double L[NB][NB + 1];  // diagonal block / its Cholesky factor
     double Li[NB][NB + 1]; // inverse of the factor (lower)
     double X[NB][NB + 1];  // right-hand block before the triangular solve
     double XO[NB][NB + 1]; // solved block (kept for the diagonal update)
     double XA[NB][NB + 1]; // previous panel's column block of this row block
     double XB[NB][NB + 1]; // previous panel's column block of the diagonal row block
+    double col[2][NB];     // column buffer of the in-warp factorisation
+    double dinv[NB];       // reciprocal diagonal of the factor
 };
 constexpr size_t kSmemBytes = sizeof(Smem);  // ~84 KB: dynamic shared memory, one CTA per SM
 
@@ -68,20 +70,43 @@ struct GridSync {
     }
 };
 
-// ---- C tile = A B^T ---------------------------------------------------------------------------------
-// acc[r][c] (rows i0 + ty + 16 r, cols j0 + tx + 16 c) = sum_{k<K} A[row][k] * (SCALE ? s[k] : 1) * B[col][k]
-// rows >= arows / brows and k >= K read as zero.  TM, TN in {32, 64}.  The next k-slab is fetched from L2 into
-// registers while the current one is multiplied out of shared memory.
+// ---- C tile = A B^T on the fp64 tensor pipe ---------------------------------------------------------------------
+// acc (TM x TN outputs per CTA, TM, TN in {32, 64}) = sum_{k<K} A[row][k] * (SCALE ? s[k] : 1) * B[col][k]; rows >=
+// arows / brows and k >= K read as zero.  8 warps as 2 x 4; a warp owns (TM/2) x (TN/4) outputs as m8n8k4 DMMA tiles
+// (mma.sync.aligned.m8n8k4.row.col.f64: lane (g, t) = (lane / 4, lane % 4) feeds A[g][t] and B^T[g][t], and holds
+// C[g][2t], C[g][2t+1]).  Operands are staged [row][k] with pitch 36 doubles, so the 32 lanes of a fragment load hit
+// 16 distinct bank pairs twice -- the 2-wavefront minimum for 256 bytes; one fragment pair feeds 256 FMAs.  The next
+// k-slab is fetched from L2 into registers while the current one is multiplied.
+// acc[r][c] belongs to tile row trow<TM>(r), tile column tcol<TN>(c).
+constexpr int kPitch = 36;
+
+template <int TM>
+__device__ __forceinline__ int trow(int r) {
+    return ((threadIdx.x >> 7) & 1) * (TM / 2) + 8 * r + ((threadIdx.x & 31) >> 2);
+}
+template <int TN>
+__device__ __forceinline__ int tcol(int c) {
+    return ((threadIdx.x >> 5) & 3) * (TN / 4) + 8 * (c >> 1) + 2 * (threadIdx.x & 3) + (c & 1);
+}
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 template <int TM, int TN, bool SCALE>
 __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, int arows, const double* __restrict__ B,
                                         int ldb, int brows, int K, int i0, int j0, const double* __restrict__ s,
                                         double (&acc)[TM / 16][TN / 16], Smem& sm) {
-    constexpr int RM = TM / 16, RN = TN / 16;
+    constexpr int RM = TM / 16, RN = TN / 16, NI = TN / 32;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wm0 = ((threadIdx.x >> 7) & 1) * (TM / 2), wn0 = ((threadIdx.x >> 5) & 3) * (TN / 4);
 #pragma unroll
     for (int r = 0; r < RM; ++r)
 #pragma unroll
         for (int c = 0; c < RN; ++c) acc[r][c] = 0.0;
+    // staging: thread (ty, tx) moves k = tx, tx + 16 of rows ty + 16 r
     double pa[2][RM], pb[2][RN];
     auto fetch = [&](int k0) {
 #pragma unroll
@@ -106,23 +131,23 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, i
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int r = 0; r < RM; ++r) sm.a[tx + 16 * h][ty + 16 * r] = pa[h][r];
+            for (int r = 0; r < RM; ++r) sm.a[(ty + 16 * r) * kPitch + tx + 16 * h] = pa[h][r];
 #pragma unroll
-            for (int r = 0; r < RN; ++r) sm.b[tx + 16 * h][ty + 16 * r] = pb[h][r];
+            for (int r = 0; r < RN; ++r) sm.b[(ty + 16 * r) * kPitch + tx + 16 * h] = pb[h][r];
         }
         __syncthreads();
         if (k0 + BK < K) fetch(k0 + BK);
-#pragma unroll 8
-        for (int k = 0; k < BK; ++k) {
-            double av[RM], bv[RN];
 #pragma unroll
-            for (int r = 0; r < RM; ++r) av[r] = sm.a[k][ty + 16 * r];
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[RM], bf[NI];
 #pragma unroll
-            for (int c = 0; c < RN; ++c) bv[c] = sm.b[k][tx + 16 * c];
+            for (int r = 0; r < RM; ++r) af[r] = sm.a[(wm0 + 8 * r + g) * kPitch + kk + t];
+#pragma unroll
+            for (int c = 0; c < NI; ++c) bf[c] = sm.b[(wn0 + 8 * c + g) * kPitch + kk + t];
 #pragma unroll
             for (int r = 0; r < RM; ++r)
 #pragma unroll
-                for (int c = 0; c < RN; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+                for (int c = 0; c < NI; ++c) dmma(acc[r][2 * c], acc[r][2 * c + 1], af[r], bf[c]);
         }
     }
 }
@@ -131,6 +156,44 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, i
 // T: rows x n (row-major, ld = n, both multiples of 32).  Rows [0,n) hold an SPD matrix S (lower triangle
 // used), the rows below hold stacked right-hand sides Wstack.  After panels 0..n/32-1:
 //     T[0:n] lower triangle = L (S = L L^T),   T[n:] = Wstack L^-T.
+
+// 1 / sqrt(x) to fp64 rounding: fp32 MUFU seed + two Newton steps (error 2^-22 -> 1e-13 -> < 1 ulp); the library
+// routine outside the fp32 range and for non-positive / NaN input (NaN out: a non-PD block poisons like cho_factor)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    if (!(x > 1e-30 && x < 1e30)) return rsqrt(x);
+    double y = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
+}
+
+// sm.L (a 32 x 32 SPD block, lower triangle read) -> its Cholesky factor in sm.L (upper part zeroed), 1 / L_rr in
+// sm.dinv.  Warp 0, lane r owns row r in registers.  Right-looking: once column c is scaled, the update of entry
+// (c+1, c+1) -- the next pivot -- is the first of the rank-one updates, so the serial chain per pivot is
+// shuffle -> rsqrt -> multiply -> one shared-memory round trip -> one FMA; the other updates fill the pipe behind it.
+__device__ __forceinline__ void factor_warp(Smem& sm) {
+    const int r = threadIdx.x;
+    double a[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) a[q] = sm.L[r][q];
+    double dinv = 0.0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, a[c], c);
+        const double inv = fast_rsqrt(piv);
+        const double l = (r >= c) ? a[c] * inv : 0.0;
+        a[c] = l;
+        if (r == c) dinv = inv;
+        sm.col[c & 1][r] = l;
+        __syncwarp();
+#pragma unroll
+        for (int q = c + 1; q < NB; ++q) a[q] = fma(-l, sm.col[c & 1][q], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) sm.L[r][q] = (q <= r) ? a[q] : 0.0;
+    sm.dinv[r] = dinv;
+}
 
 // sm.L (a 32 x 32 SPD block) -> its Cholesky factor in sm.L (upper part zeroed) and the inverse factor in sm.Li.
 // Executed by warp 0; a non-positive pivot gives NaN (cho_factor).  Callers sync before and after.
@@ -191,7 +254,7 @@ __device__ void panel_factor(const double* T, int ld, int j, Smem& sm) {
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int rr = ty + 16 * r, cc = tx + 16 * c;
+            const int rr = trow<32>(r), cc = tcol<32>(c);
             sm.L[rr][cc] = ldg(rowj + (size_t)rr * ld + j * NB + cc) - acc[r][c];
         }
     __syncthreads();
@@ -217,7 +280,7 @@ __device__ void panel_apply(double* T, int ld, int j, int i, Smem& sm) {
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int rr = ty + 16 * r, cc = tx + 16 * c;
+            const int rr = trow<32>(r), cc = tcol<32>(c);
             sm.X[rr][cc] = ldg(out + (size_t)rr * ld + cc) - acc[r][c];
         }
     __syncthreads();
@@ -251,31 +314,33 @@ __device__ void chol_stack_cta(double* T, int n, int rows, Smem& sm) {
 //   * owners keep their own diagonal block up to date (right-looking, rank-32 per phase), so the owner of row
 //     block j+1 can factor and invert it at once and publish L_{j+1}^-1 (double-buffered) before the barrier;
 //   * meanwhile the other owners accumulate Pacc for phase j+1 (the long k-loop), overlapping the factorisation.
+constexpr int kLpub = NB * NB + NB;  // a published diagonal factor: L (32 x 32) and 1 / diag L
 struct ChSys {
     double* T;      // [rows, n]
     int n, rows;
     double* Pacc;   // [rows/32][32*32]  look-ahead accumulators
-    double* Lpub;   // [2][32*32]        published inverse factors
+    double* Lpub;   // [2][kLpub]        published diagonal factors (double-buffered)
 };
 
 __device__ __forceinline__ void publish_factor(const ChSys& s, int jb, Smem& sm) {
-    // sm.L holds the fully updated diagonal block jb: factor, invert, write L to T[jb, jb] and L^-1 to Lpub[jb & 1]
+    // sm.L holds the fully updated diagonal block jb: factor it, write L to T[jb, jb] and (L, 1 / diag L) to Lpub[jb & 1]
     __syncthreads();
     long long tp = clock64();
-    if (threadIdx.x < 32) factor_invert_warp(sm);
+    if (threadIdx.x < 32) factor_warp(sm);
     __syncthreads();
     ST_PROF(8, tp);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double* out = s.T + (size_t)jb * NB * s.n + jb * NB;
-    double* lp = s.Lpub + (size_t)(jb & 1) * NB * NB;
+    double* lp = s.Lpub + (size_t)(jb & 1) * kLpub;
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const int rr = ty + 16 * r, cc = tx + 16 * c;
             out[(size_t)rr * s.n + cc] = sm.L[rr][cc];
-            lp[rr * NB + cc] = sm.Li[rr][cc];
+            lp[rr * NB + cc] = sm.L[rr][cc];
         }
+    if (threadIdx.x < NB) lp[NB * NB + threadIdx.x] = sm.dinv[threadIdx.x];
 }
 
 __device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) {
@@ -285,11 +350,12 @@ __device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) 
     int i0 = lb;
     if (i0 <= j) i0 += ((j - i0) / LG + 1) * LG;
     if (i0 >= ntot) return;
-    const double* lp = s.Lpub + (size_t)(j & 1) * NB * NB;
+    const double* lp = s.Lpub + (size_t)(j & 1) * kLpub;
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < 2; ++c) sm.Li[ty + 16 * r][tx + 16 * c] = ldg(lp + (ty + 16 * r) * NB + tx + 16 * c);
+    if (threadIdx.x < NB) sm.dinv[threadIdx.x] = ldg(lp + NB * NB + threadIdx.x);
     if (j > 0) {
         const double* xb = s.T + (size_t)j * NB * ld + (j - 1) * NB;
 #pragma unroll
@@ -330,23 +396,30 @@ __device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) 
 #pragma unroll
             for (int c = 0; c < 2; ++c) sm.X[ty + 16 * r][tx + 16 * c] = v[r][c];
         __syncthreads();
+        // X L_jj^-T by forward substitution, one lane per row: x_c = (v_c - sum_{q<c} x_q L[c][q]) / L[c][c]
+        if (threadIdx.x < NB) {
+            const int rr = threadIdx.x;
+            double x[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                double s0 = sm.X[rr][c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int q = 0; q < c; ++q) {
+                    const double l = sm.Li[c][q];
+                    if ((q & 3) == 0) s0 = fma(-x[q], l, s0);
+                    else if ((q & 3) == 1) s1 = fma(-x[q], l, s1);
+                    else if ((q & 3) == 2) s2 = fma(-x[q], l, s2);
+                    else s3 = fma(-x[q], l, s3);
+                }
+                x[c] = ((s0 + s1) + (s2 + s3)) * sm.dinv[c];
+                sm.XO[rr][c] = x[c];
+            }
+        }
+        __syncthreads();
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int rr = ty + 16 * r, cc = tx + 16 * c;
-                double s0 = 0.0, s1 = 0.0;
-                int q = 0;
-                for (; q + 1 <= cc; q += 2) {
-                    s0 = fma(sm.X[rr][q], sm.Li[cc][q], s0);
-                    s1 = fma(sm.X[rr][q + 1], sm.Li[cc][q + 1], s1);
-                }
-                if (q <= cc) s0 = fma(sm.X[rr][q], sm.Li[cc][q], s0);
-                const double o = s0 + s1;
-                out[(size_t)rr * ld + cc] = o;
-                sm.XO[rr][cc] = o;
-            }
-        __syncthreads();
+            for (int c = 0; c < 2; ++c) out[(size_t)(ty + 16 * r) * ld + tx + 16 * c] = sm.XO[ty + 16 * r][tx + 16 * c];
         if (i < nsq) {  // keep the own diagonal block current: T[i,i] -= X_ij X_ij^T
             double* dg = s.T + (size_t)i * NB * ld + i * NB;
             double w[2][2];
@@ -373,6 +446,7 @@ __device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) 
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
                             sm.Li[ty + 16 * r][tx + 16 * c] = ldg(lp + (ty + 16 * r) * NB + tx + 16 * c);
+                    if (threadIdx.x < NB) sm.dinv[threadIdx.x] = ldg(lp + NB * NB + threadIdx.x);
                 }
             } else {
 #pragma unroll
@@ -395,7 +469,7 @@ __device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) 
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
-                    s.Pacc[(size_t)i * NB * NB + (ty + 16 * r) * NB + tx + 16 * c] = acc[r][c];
+                    s.Pacc[(size_t)i * NB * NB + trow<32>(r) * NB + tcol<32>(c)] = acc[r][c];
         }
         if (last_owner && threadIdx.x == 0) {
             const long long dtl = clock64() - tl;
@@ -590,7 +664,7 @@ __global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
         // ---- S = L L^T;  X = P^- H^T L^-T;  z = L^-1 (y - H m^-)
         {
             const ChSys s1{T, Mp, rows, a.Pacc, a.Lpub};
-            const ChSys s2{T2, Mp, rows2, a.Pacc + (size_t)(rows / NB) * NB * NB, a.Lpub + 2 * NB * NB};
+            const ChSys s2{T2, Mp, rows2, a.Pacc + (size_t)(rows / NB) * NB * NB, a.Lpub + 2 * kLpub};
             chol_stack_grid(s1, s2, sm, gs);
         }
         if (blockIdx.x == 0) ST_PROF(2, tp0);
@@ -609,7 +683,7 @@ __global__ void __launch_bounds__(NTH) st_filter_kernel(FilterArgs a) {
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    const int row = i0 + trow<32>(r), col = j0 + tcol<64>(c);
                     if (row < d && col < d) Pout[(size_t)row * d + col] = ldg(Pk + (size_t)row * d + col) - acc[r][c];
                 }
         }
@@ -738,7 +812,7 @@ __global__ void __launch_bounds__(NTH) st_mf_filter_kernel(MfFilterArgs a) {
         gs.sync();
         {
             const ChSys s1{T, Mp, rows, a.Pacc, a.Lpub};
-            const ChSys s2{T2, Mp, rows2, a.Pacc + (size_t)(rows / NB) * NB * NB, a.Lpub + 2 * NB * NB};
+            const ChSys s2{T2, Mp, rows2, a.Pacc + (size_t)(rows / NB) * NB * NB, a.Lpub + 2 * kLpub};
             chol_stack_grid(s1, s2, sm, gs);
         }
         // ---- per block: (S^-1)_ii and (S^-1 r)_i from row i of LiT, then the rank-one update of the block
@@ -953,7 +1027,7 @@ __global__ void __launch_bounds__(NTH) st_gain_kernel(GainArgs a) {
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    const int row = i0 + trow<64>(r), col = j0 + tcol<64>(c);
                     if (row < d && col < d) G[(size_t)row * d + col] = acc[r][c];
                 }
         }
@@ -1050,7 +1124,7 @@ __global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    const int row = i0 + trow<32>(r), col = j0 + tcol<64>(c);
                     if (row < d && col < d) a.Z[(size_t)row * d + col] = acc[r][c];
                 }
         }
@@ -1079,7 +1153,7 @@ __global__ void __launch_bounds__(NTH) st_smoother_kernel(SmootherArgs a) {
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    const int row = i0 + trow<32>(r), col = j0 + tcol<64>(c);
                     if (row < d && col < d) {
                         const double val = fPk[(size_t)row * d + col] + acc[r][c];
                         if (k == a.k0) a.sP[(size_t)row * d + col] = val;  // carried to the next launch
@@ -1152,7 +1226,7 @@ __global__ void __launch_bounds__(NTH) st_inverse_kernel(InvArgs a) {
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                        const int row = i0 + trow<64>(r), col = j0 + tcol<64>(c);
                         if (row < n && col < n) {
                             T[(size_t)row * np + col] += acc[r][c];
                             if (j0 < i0) T[(size_t)col * np + row] += acc[r][c];
@@ -1192,7 +1266,7 @@ __global__ void __launch_bounds__(NTH) st_inverse_kernel(InvArgs a) {
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                    const int row = i0 + trow<64>(r), col = j0 + tcol<64>(c);
                     if (row < n && col < n) {
                         a.inv[(size_t)k * n * n + (size_t)row * n + col] = acc[r][c];
                         if (j0 < i0) a.inv[(size_t)k * n * n + (size_t)col * n + row] = acc[r][c];
@@ -1242,13 +1316,13 @@ __global__ void __launch_bounds__(NTH) st_to_data_kernel(long long N, int Ns, in
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int row = i0 + ty + 16 * r, col = j0 + tx + 16 * c;
+                        const int row = i0 + trow<64>(r), col = j0 + tcol<64>(c);
                         if (row < Ns && col < M) dsum[r] = fma(acc[r][c], B[(size_t)row * M + col], dsum[r]);
                     }
             }
             __syncthreads();
 #pragma unroll
-            for (int r = 0; r < 4; ++r) part[(ty + 16 * r) * 16 + tx] = dsum[r];
+            for (int r = 0; r < 4; ++r) part[trow<64>(r) * 16 + ((threadIdx.x >> 5) & 3) * 4 + (threadIdx.x & 3)] = dsum[r];
             __syncthreads();
             if (threadIdx.x < 64) {
                 const int row = i0 + threadIdx.x;
@@ -1367,7 +1441,7 @@ struct Carver {
 
 static size_t filter_ws(int M, int n) {
     size_t d = (size_t)M * n, Mp = pad32(M), dp = pad32((int)d);
-    return ((Mp + dp + NB) * Mp + (Mp + NB) * Mp + (2 * Mp + dp + 2 * NB) * NB + 4 * NB * NB + d * d + d + 64) * sizeof(double) + 12 * 256;
+    return ((Mp + dp + NB) * Mp + (Mp + NB) * Mp + (2 * Mp + dp + 2 * NB) * NB + 4 * kLpub + d * d + d + 64) * sizeof(double) + 12 * 256;
 }
 static long long smoother_chunk(long long N, int M, int n) {
     // time steps per launch pair when the caller does not keep the gains: ~2 GB of gain scratch
@@ -1452,7 +1526,7 @@ extern "C" int bn_st_kalman_filter(const bn_kernel_spec* temporal, int M, int64_
     a.T = cv.take<double>((Mp + dp + NB) * Mp);
     a.T2 = cv.take<double>((Mp + NB) * Mp);
     a.Pacc = cv.take<double>(((Mp + dp + NB) / NB + (Mp + NB) / NB) * NB * NB);
-    a.Lpub = cv.take<double>(4 * NB * NB);
+    a.Lpub = cv.take<double>(4 * kLpub);
     a.Pcur = cv.take<double>(d * d);
     a.mcur = cv.take<double>(d);
     BN_REQUIRE(cv.ok, "workspace carve failed");
@@ -1515,7 +1589,7 @@ extern "C" int bn_st_rts_smoother(const bn_kernel_spec* temporal, int M, int64_t
 
 static size_t mf_filter_ws(int M) {
     size_t Mp = pad32(M);
-    return ((2 * Mp + NB) * Mp + (Mp + NB) * Mp + (3 * Mp + 2 * NB) * NB + 4 * NB * NB + 64) * sizeof(double) + 12 * 256;
+    return ((2 * Mp + NB) * Mp + (Mp + NB) * Mp + (3 * Mp + 2 * NB) * NB + 4 * kLpub + 64) * sizeof(double) + 12 * 256;
 }
 
 extern "C" int bn_st_kalman_filter_meanfield(const bn_kernel_spec* temporal, int M, int64_t N, const double* dt,
@@ -1537,7 +1611,7 @@ extern "C" int bn_st_kalman_filter_meanfield(const bn_kernel_spec* temporal, int
     a.T = cv.take<double>((2 * Mp + NB) * Mp);
     a.T2 = cv.take<double>((Mp + NB) * Mp);
     a.Pacc = cv.take<double>(((2 * Mp + NB) / NB + (Mp + NB) / NB) * NB * NB);
-    a.Lpub = cv.take<double>(4 * NB * NB);
+    a.Lpub = cv.take<double>(4 * kLpub);
     BN_REQUIRE(cv.ok, "workspace carve failed");
     cudaStream_t s = (cudaStream_t)stream;
     BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
