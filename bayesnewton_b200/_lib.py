@@ -71,6 +71,7 @@ SIGNATURES = {
     'bn_site_update': (_I, [_SA, _P, _Z, _P]),
     'bn_likelihood_stats': (_I, [_SA, _P, _P, _P, _P, _Z, _P]),
     'bn_expected_density': (_I, [_SA, _P, _P, _P, _Z, _P]),
+    'bn_energy_terms': (_I, [_SA, _P, _P, _P, _Z, _P]),
     'bn_gaussian_expected_log_lik': (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_ep_pseudo_density': (_I, [_L, _I, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_temporal_conditional': (_I, [_KS, _L, _P, _L, _P, _P, _P, _P, _I, _P, _P, _P]),

@@ -176,6 +176,19 @@ class MarkovGaussianProcess:
             ptr(self.mask_pseudo_y), None, ptr(out), ptr(ws), nb, stream_ptr()))
         return out
 
+    def _energy_terms_fused(self, cubature=None):
+        """(sum_n likelihood term, sum_n E_q[log N(pseudo_y_n | f_n, pseudo_var_n)]) in one kernel for single-latent
+        VI / Newton models; None when the model has more than one latent"""
+        if self.func_dim != 1 or self.method not in (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON):
+            return None
+        a, keep = self._site_args(cubature)
+        pl = self.pseudo_likelihood
+        a.site_mean, a.site_cov = pl.mean.data_ptr(), pl.covariance.data_ptr()
+        parts = torch.zeros(2, dtype=torch.float64, device=self.posterior_mean.device)
+        ws, nb = workspace(a.N, self.state_dim, 1)
+        _lib.check(_lib.lib().bn_energy_terms(a, ptr(self.mask_pseudo_y), parts.data_ptr(), ptr(ws), nb, stream_ptr()))
+        return parts[0], parts[1]
+
     def compute_kl(self):
         """KL[q || p] = sum_n E_q[log N(pseudo_y_n | f_n, pseudo_var_n)] - log Z_pseudo  (basemodels.py:708-724)"""
         return self.expected_density_pseudo() - self.compute_log_lik()

@@ -89,6 +89,24 @@ expected_density_kernel(const __grid_constant__ bn_site_args a, const __grid_con
     block_sum_store<kNT<TAB>>(acc, part);
 }
 
+// the two per-step sums of a VI / Newton energy in one pass over the posterior marginals: the scheme's likelihood term
+// and E_q[log N(pseudo_y | f, pseudo_var)] (utils.py:510-531); the posterior is read once
+template <int LIK, int METHOD, bool TAB>
+__global__ void __launch_bounds__(kNT<TAB>)
+energy_terms_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const unsigned char* mask,
+                    double* part, double* part2) {
+    extern __shared__ double site_smem[];
+    const SiteCtx sc{&cub, stage_table<TAB>(site_smem), nullptr, nullptr};
+    double acc = 0.0, acc2 = 0.0;
+    for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>) {
+        const double v = expected_density_step<LIK, METHOD, TAB>(a, sc, n);
+        if (!isnan(v)) acc += v;  // nansum
+        acc2 += gaussian_ell_step<1>(a.site_mean, a.post_mean, a.post_cov, a.site_cov, mask, n);
+    }
+    block_sum_store<kNT<TAB>>(acc, part);
+    block_sum_store<kNT<TAB>>(acc2, part2);
+}
+
 template <int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(kNT<TAB>)
 likelihood_stats_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
@@ -251,6 +269,38 @@ extern "C" int bn_expected_density(const bn_site_args* a, double* values, double
                   BN_SITE_LAUNCH(expected_density_kernel, L, M, smem, *a, p.cub, p.cx2, p.cw2, values, p.partials)); \
         BN_CUDA(cudaGetLastError());                                                   \
         sum_kernel<false><<<1, 1024, 0, st>>>(p.partials, p.grid, sum, 1.0);           \
+        BN_CUDA(cudaGetLastError());                                                   \
+        return 0;                                                                      \
+    }
+    BN_FOR_EACH_SITE(X)
+#undef X
+    set_error("unsupported (likelihood, method) = (%d, %d)", a->likelihood, a->method);
+    return -1;
+}
+
+extern "C" int bn_energy_terms(const bn_site_args* a, const uint8_t* mask, double* sums, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (int rc = check_site_args(a)) return rc;
+    BN_REQUIRE(sums != nullptr, "sums output is null");
+    BN_REQUIRE(a->D == 1 && (a->method == BN_METHOD_VI || a->method == BN_METHOD_NEWTON),
+               "the fused energy terms are built for single-latent VI / Newton (use bn_expected_density + "
+               "bn_gaussian_expected_log_lik otherwise)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->N == 0) { BN_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st)); return 0; }
+    BN_REQUIRE(a->site_mean && a->site_cov, "site_mean / site_cov (the pseudo observations) are needed");
+    SitePlan p;
+    if (int rc = plan_sites(a, 2, workspace, workspace_bytes, st, p)) return rc;
+#define X(L, M)                                                                        \
+    if (a->likelihood == L && a->method == M && (M == BN_METHOD_VI || M == BN_METHOD_NEWTON) && \
+        L != BN_LIK_HETEROSCEDASTIC_SOFTPLUS && L != BN_LIK_HETEROSCEDASTIC_EXP) {     \
+        int rc;                                                                        \
+        size_t smem = table_smem<L, M>(st, rc);                                        \
+        if (rc) return rc;                                                             \
+        BN_LAUNCH("energy_terms", st,                                                  \
+                  BN_SITE_LAUNCH(energy_terms_kernel, L, M, smem, *a, p.cub, mask, p.partials, p.partials + p.grid)); \
+        BN_CUDA(cudaGetLastError());                                                   \
+        sum_kernel<false><<<1, 1024, 0, st>>>(p.partials, p.grid, sums, 1.0);          \
+        sum_kernel<false><<<1, 1024, 0, st>>>(p.partials + p.grid, p.grid, sums + 1, 1.0); \
         BN_CUDA(cudaGetLastError());                                                   \
         return 0;                                                                      \
     }

@@ -290,10 +290,15 @@ class TimeShardedMarkovGP:
         parts = torch.zeros(3, dtype=torch.float64, device=dev)
         a, keep = self._site_args(cubature)
         ws, nb = self._ws
-        _lib.check(_lib.lib().bn_expected_density(a, None, parts[0:1].data_ptr(), ptr(ws), nb, stream_ptr()))
-        _lib.check(_lib.lib().bn_gaussian_expected_log_lik(
-            self.N, a.D, ptr(pl.mean), ptr(self.posterior_mean), ptr(self.posterior_variance), ptr(pl.covariance),
-            ptr(self.mask_pseudo_y), None, parts[1:2].data_ptr(), ptr(ws), nb, stream_ptr()))
+        if a.D == 1:  # single latent: both sums in one pass over the posterior marginals
+            a.site_mean, a.site_cov = pl.mean.data_ptr(), pl.covariance.data_ptr()
+            _lib.check(_lib.lib().bn_energy_terms(a, ptr(self.mask_pseudo_y), parts[0:2].data_ptr(), ptr(ws), nb,
+                                                  stream_ptr()))
+        else:
+            _lib.check(_lib.lib().bn_expected_density(a, None, parts[0:1].data_ptr(), ptr(ws), nb, stream_ptr()))
+            _lib.check(_lib.lib().bn_gaussian_expected_log_lik(
+                self.N, a.D, ptr(pl.mean), ptr(self.posterior_mean), ptr(self.posterior_variance), ptr(pl.covariance),
+                ptr(self.mask_pseudo_y), None, parts[1:2].data_ptr(), ptr(ws), nb, stream_ptr()))
         cache = getattr(self, '_ell_cache', None)
         if cache is not None and cache[1] == pl.version:  # same sites, same kernel: the filter pass of update_posterior
             parts[2:3] = cache[0]

@@ -62,6 +62,16 @@ class InferenceMixin:
     def energy(self, batch_ind=None, cubature=None, **kwargs):
         raise NotImplementedError
 
+    def _likelihood_and_kl(self, cubature=None):
+        """(likelihood term, KL[q || p]) of the VI / Newton energies; one fused pass over the posterior marginals
+        (bn_energy_terms) where the model offers it, the two separate sums otherwise"""
+        fused = getattr(self, '_energy_terms_fused', None)
+        if fused is not None:
+            r = fused(cubature)
+            if r is not None:
+                return r[0], r[1] - self.compute_log_lik()
+        return self.expected_density(cubature), self.compute_kl()
+
     def energy_and_grad(self, cubature=None):
         """(energy, d energy / d [variance_c...; lengthscale_c...]): the kernel part of what
         objax.GradValues(model.energy, model.vars()) returns (README.md:56-70, demos/regression.py:63-70), for the
@@ -78,7 +88,8 @@ class VariationalInference(InferenceMixin):
     method = _lib.BN_METHOD_VI
 
     def energy(self, batch_ind=None, cubature=None, **kwargs):
-        return -(self.expected_density(cubature) - self.compute_kl())
+        lik, kl = self._likelihood_and_kl(cubature)
+        return -(lik - kl)
 
 
 class Newton(InferenceMixin):
@@ -86,7 +97,8 @@ class Newton(InferenceMixin):
     method = _lib.BN_METHOD_NEWTON
 
     def energy(self, batch_ind=None, cubature=None, **kwargs):
-        return -(self.expected_density(cubature) - self.compute_kl())
+        lik, kl = self._likelihood_and_kl(cubature)
+        return -(lik - kl)
 
 
 Laplace = Newton

@@ -257,6 +257,7 @@ class _DiagSites:
 class SpatioTemporalMixin:
     """overrides of MarkovGaussianProcess for spatio-temporal inputs; mixed in by MarkovGaussianProcess.__new__"""
     _site_state_dim = 1  # the site pass works on scalar (time, space) observations
+    _energy_terms_fused = None  # the KL term lives in the inducing space (M x M blocks): separate kernels
 
     def __init__(self, kernel, likelihood, X, Y, R=None, parallel=None):
         if getattr(likelihood, 'multi_latent', False):

@@ -254,6 +254,13 @@ int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* 
 int bn_expected_density(const bn_site_args* a, double* values, double* sum,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two per-step sums of a single-latent VI / Newton energy in ONE pass over the posterior marginals
+ * (inference.py:130-154, 197-222): sums[0] = nansum_n of the scheme's likelihood term (as bn_expected_density),
+ * sums[1] = sum_n gaussian_expected_log_lik(site_mean_n, post_mean_n, post_cov_n, site_cov_n, mask_n)
+ * (as bn_gaussian_expected_log_lik; a->site_mean / a->site_cov are the pseudo observations). */
+int bn_energy_terms(const bn_site_args* a, const uint8_t* mask, double* sums,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* sum_n gaussian_expected_log_lik(pseudo_y_n, post_mean_n, post_cov_n, pseudo_var_n, mask_n) */
 int bn_gaussian_expected_log_lik(int64_t N, int D, const double* pseudo_y, const double* post_mean,
                                  const double* post_cov, const double* pseudo_var, const uint8_t* mask,

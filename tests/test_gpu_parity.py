@@ -349,3 +349,22 @@ def test_full_size_properties_c2(bn):
     assert abs(float(m.compute_log_lik()) - float(ell)) <= TOL * abs(float(ell))
     del res, res2, sm, sP, fm, fP
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize('lik', ['gaussian', 'probit', 'logit'])
+@pytest.mark.parametrize('method', ['vi', 'newton'])
+def test_fused_energy_terms_match_the_separate_sums(bn, lik, method):
+    """bn_energy_terms = bn_expected_density + bn_gaussian_expected_log_lik in one pass (missing data included)"""
+    x, y = classification_data(700) if lik != 'gaussian' else __import__('_data').regression_data(700)
+    y = y.copy()
+    y[[3, 50, 51]] = np.nan
+    L = bn.likelihoods
+    lk = {'gaussian': L.Gaussian(0.2), 'probit': L.Bernoulli('probit'), 'logit': L.Bernoulli('logit')}[lik]
+    cls = bn.models.MarkovVariationalGP if method == 'vi' else bn.models.MarkovNewtonGP
+    m = cls(kernel=bn.kernels.Matern52(1.2, 0.8), likelihood=lk, X=x, Y=y)
+    m.inference(lr=0.7)
+    fused = m._energy_terms_fused()
+    assert fused is not None
+    e0, x0 = float(m.expected_density()), float(m.expected_density_pseudo())
+    assert abs(float(fused[0]) - e0) <= 1e-12 * abs(e0) and abs(float(fused[1]) - x0) <= 1e-12 * abs(x0)
+    assert abs(float(m.energy()) + (e0 - (x0 - float(m.compute_log_lik())))) <= 1e-12 * abs(float(m.energy()))
