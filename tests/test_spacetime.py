@@ -344,3 +344,63 @@ def test_gpu_meanfield_vi_iteration_vs_oracle(bn, case):
         assert rel_err(np_(mg.posterior_mean), mo.post_mean) < TOL
         assert rel_err(np_(mg.posterior_variance), mo.post_cov) < TOL
         assert abs(E1 - E0) <= TOL * abs(E0), (E0, E1)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.gpu
+@pytest.mark.parametrize('N', [1, 2])
+def test_gpu_dense_and_meanfield_on_one_and_two_steps(bn, N):
+    M = 5
+    rng = np.random.default_rng(N)
+    z = np.linspace(0, 1, M)[:, None]
+    ko, kg = oracle_kernel('Matern32', 1.3, 0.7, 0.5, z), gpu_kernel(bn, 'Matern32', 1.3, 0.7, 0.5, z)
+    dt = np.concatenate([[0.0], 0.3 * np.ones(N - 1)])
+    y = rng.standard_normal((N, M, 1))
+    Rn = spd_batch(N, M, 3)
+    dts = np.concatenate([dt[1:], [0.0]])
+    e0, (m0, P0) = kalman.kalman_filter(dt, ko, y, Rn)
+    e1, (m1, P1) = bn.ops.kalman_filter(dt, kg, y, Rn)
+    assert abs(float(e1) - e0) <= TOL * abs(e0) and rel_err(np_(m1), m0) < TOL and rel_err(np_(P1), P0) < TOL
+    s0, S0, G0 = kalman.rauch_tung_striebel_smoother(dts, ko, m0, P0)
+    s1, S1, G1 = bn.ops.rauch_tung_striebel_smoother(dts, kg, m0, P0)
+    assert rel_err(np_(s1), s0) < TOL and rel_err(np_(S1), S0) < TOL and rel_err(np_(G1), G0) < TOL
+    e0, (m0, P0) = ost.kalman_filter_meanfield(dt, ko, y, Rn)
+    e1, (m1, P1) = bn.spacetime.st_kalman_filter_meanfield(dt, kg, y, Rn)
+    assert abs(float(e1) - e0) <= TOL * abs(e0) and rel_err(np_(m1), m0) < TOL and rel_err(np_(P1), P0) < TOL
+    s0, S0, _ = ost.rts_smoother_meanfield(dts, ko, m0, P0)
+    s1, S1, _ = bn.spacetime.st_rts_smoother_meanfield(dts, kg, m0, P0)
+    assert rel_err(np_(s1), s0) < TOL and rel_err(np_(S1), S0) < TOL
+
+
+@pytest.mark.gpu
+def test_gpu_spatiotemporal_bernoulli_vi_vs_oracle(bn):
+    """a non-conjugate likelihood on the spatio-temporal path: every (time, space) observation is a cubature site"""
+    Nt, Ns = 10, 9
+    t, Y, R = st_data(Nt, Ns, seed=11, spatial_dims=2)
+    Y = (Y > np.median(Y)).astype(np.float64)
+    ko = oracle_kernel('Matern32', 1.1, 0.9, 1.2, R[0], spatial_dims=2)
+    kg = gpu_kernel(bn, 'Matern32', 1.1, 0.9, 1.2, R[0], spatial_dims=2)
+    mo = ost.SpatioTemporalMarkovGP(ko, sites.Bernoulli(), t, Y, R)
+    mg = bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Bernoulli(), X=t, Y=Y, R=R)
+    for lr in (0.5, 0.5):
+        mo.inference(lr=lr)
+        mg.inference(lr=lr)
+    E0, E1 = mo.energy(), float(mg.energy())
+    assert rel_err(np_(mg.posterior_mean), mo.post_mean) < 1e-8
+    assert rel_err(np_(mg.posterior_variance), mo.post_cov) < 1e-8
+    assert abs(E1 - E0) <= 1e-8 * abs(E0), (E0, E1)
+
+
+@pytest.mark.gpu
+def test_gpu_spatiotemporal_rejects_what_it_does_not_cover(bn):
+    t, Y, R = st_data(4, 4, seed=1, spatial_dims=2)
+    kg = gpu_kernel(bn, 'Matern32', 1.0, 1.0, 1.0, R[0], spatial_dims=2)
+    R2 = R.copy()
+    R2[1] += 0.1  # spatial inputs that move in time
+    with pytest.raises(NotImplementedError):
+        bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(0.1), X=t, Y=Y, R=R2)
+    with pytest.raises(NotImplementedError):
+        bn.spacetime.SpatioTemporalKernel(bn.kernels.Matern32(), bn.kernels.Matern32(), z=R[0], sparse=False)
+    L = bn._lib.lib()
+    spec = bn.kernels.Matern72(1.0, 1.0).spec()
+    assert L.bn_st_workspace_bytes(spec, 4, 4, 4) == 0 and b'family' in L.bn_last_error()
