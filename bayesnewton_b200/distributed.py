@@ -117,9 +117,66 @@ class TimeShard:
         return sm, sP
 
 
-def _all_gather(carry, world):
-    """carries[world, len] over the default process group (NCCL on GPUs, gloo in the CPU tests)"""
+class PeerExchange:
+    """carry exchange over NVLink peer memory (csrc/exchange.cu): one symmetric inbox per rank, peer-mapped through
+    torch's symmetric-memory rendezvous; every exchange is ONE kernel on the compute stream (no NCCL on the data path)"""
+
+    def __init__(self, world, rank):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.seq = world, rank, 0
+        n = int(_lib.lib().bn_carry_exchange_bytes(world)) // 8
+        self.buf = symm.empty(n, dtype=torch.float64, device=torch.device('cuda', torch.cuda.current_device()))
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD.group_name)
+        self.ptrs = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=self.buf.device)
+        torch.cuda.synchronize()
+        dist.barrier()  # every inbox is zeroed before anyone stores into it
+
+    def all_gather(self, carry):
+        flat = carry.contiguous().reshape(-1)
+        out = torch.empty((self.world, flat.numel()), dtype=torch.float64, device=flat.device)
+        self.seq += 1
+        _lib.check(_lib.lib().bn_carry_exchange(self.ptrs.data_ptr(), self.world, self.rank, flat.data_ptr(), flat.numel(),
+                                                self.seq, out.data_ptr(), stream_ptr()))
+        return out.reshape((self.world,) + tuple(carry.shape))
+
+
+_peer = {'tried': False, 'px': None}
+
+
+def peer_exchange(world):
+    """the process-wide PeerExchange, or None when it is not available (CPU / gloo runs, BN_B200_CARRY_EXCHANGE=nccl, or
+    the symmetric-memory rendezvous failing on ANY rank: the ranks agree through one all-reduce)"""
+    import os
     import torch.distributed as dist
+    if _peer['tried']:
+        return _peer['px']
+    _peer['tried'] = True
+    if (world <= 1 or not torch.cuda.is_available() or dist.get_backend() != 'nccl'
+            or os.environ.get('BN_B200_CARRY_EXCHANGE', 'p2p') == 'nccl'):
+        return None
+    px, ok = None, 1
+    try:
+        px = PeerExchange(world, dist.get_rank())
+    except Exception as ex:  # noqa: BLE001 -- any failure means: fall back to NCCL, on all ranks
+        ok = 0
+        if dist.get_rank() == 0:
+            print('[bayesnewton_b200] peer-memory carry exchange unavailable (%s): using NCCL all-gather' % repr(ex)[:200],
+                  flush=True)
+    flag = torch.tensor([ok], dtype=torch.int32, device='cuda')
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    _peer['px'] = px if int(flag) == 1 else None
+    return _peer['px']
+
+
+def _all_gather(carry, world):
+    """carries[world, len]: over NVLink peer memory (one kernel, csrc/exchange.cu) when available, else an all-gather
+    on the default process group (NCCL on GPUs, gloo in the CPU tests)"""
+    import torch.distributed as dist
+    px = peer_exchange(world) if carry.is_cuda else None
+    if px is not None:
+        return px.all_gather(carry)
     flat = carry.contiguous().reshape(-1)
     out = torch.empty(world * flat.numel(), dtype=carry.dtype, device=carry.device)  # flat: gloo wants the concatenated form
     dist.all_gather_into_tensor(out, flat)
@@ -304,7 +361,6 @@ class TimeShardedMarkovGP:
             parts[2:3] = cache[0]
         else:
             parts[2:3] = sharded_log_lik(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(parts)
+        if self.world > 1:  # sum over ranks in rank order (bit-stable): gather + fixed-order sum
+            parts = _all_gather(parts, self.world).sum(dim=0)
         return -(parts[0] - (parts[1] - parts[2]))

@@ -405,6 +405,16 @@ int bn_st_rts_smoother_meanfield(const bn_kernel_spec* temporal, int M, int64_t 
                                  const double* dt, const double* filter_mean, const double* filter_cov, int return_full,
                                  double* means, double* covs, double* gains, void* stream);
 
+/* ---- carry exchange of the time-sharded two-level scan over NVLink peer memory ----------
+ * One kernel per exchange does the collective: every rank stores its carry[len] into a slot of every peer's inbox
+ * (symmetric, peer-mapped buffers of bn_carry_exchange_bytes(world) bytes, zero-initialised once;
+ * peer_buffers_dev[world] = their device addresses as seen from THIS rank, a device array), publishes `seq` with a
+ * system-scope release, waits for all peers' `seq` and writes out[world,len].  seq = 1, 2, 3, ... identical on all
+ * ranks; len <= 256.  Replaces the all-gather of bayesnewton_b200.distributed (ops.py:203-219, 328-335 carries). */
+size_t bn_carry_exchange_bytes(int world);
+int bn_carry_exchange(const uint64_t* peer_buffers_dev, int world, int rank, const double* carry, int len,
+                      uint64_t seq, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
