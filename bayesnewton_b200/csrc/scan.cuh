@@ -13,7 +13,7 @@
 
 namespace bn {
 
-constexpr int kScanGroup = 256;
+constexpr int kScanGroup = 288;  // 9 warps: 75 776 chunk elements (one resident wave) scan in two levels (264 groups <= 288)
 
 // in: n elements (SoA stride n_stride).  out_prefix: within-group inclusive prefixes (same
 // indexing).  totals: one element per group (SoA stride t_stride), nullable on the top level.
