@@ -263,7 +263,8 @@ __device__ void panel_factor(const double* T, int ld, int j, Smem& sm) {
 }
 
 // row block i of panel j: T[i, j] <- (T[i, j] - sum_{p<j} T[i, p] L_jp^T) L_jj^-T   (i != j);  T[j, j] <- L_jj
-__device__ void panel_apply(double* T, int ld, int j, int i, Smem& sm) {
+// k0: the first k0 columns of row block i are structurally zero (identity stacks) and are skipped in the k-loop
+__device__ void panel_apply(double* T, int ld, int j, int i, Smem& sm, int k0 = 0) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double* out = T + (size_t)i * NB * ld + j * NB;
     if (i == j) {
@@ -274,7 +275,8 @@ __device__ void panel_apply(double* T, int ld, int j, int i, Smem& sm) {
         return;
     }
     double acc[2][2];
-    tile_nt<32, 32, false>(T + (size_t)i * NB * ld, ld, NB, T + (size_t)j * NB * ld, ld, NB, j * NB, 0, 0, nullptr, acc, sm);
+    tile_nt<32, 32, false>(T + (size_t)i * NB * ld + k0, ld, NB, T + (size_t)j * NB * ld + k0, ld, NB, j * NB - k0, 0, 0, nullptr,
+                           acc, sm);
     __syncthreads();  // sm.X may still be read by the previous row block's solve
 #pragma unroll
     for (int r = 0; r < 2; ++r)
@@ -295,11 +297,22 @@ __device__ void panel_apply(double* T, int ld, int j, int i, Smem& sm) {
         }
 }
 
-__device__ void chol_stack_cta(double* T, int n, int rows, Smem& sm) {
+// Row blocks [id_lo, id_lo + n/32) may hold an identity (the stack that turns into L^-T): block id_lo + b is zero left
+// of column 32 b, so it joins the sweep at panel b and its k-loops start there -- a third of the stacked work of an
+// [S ; Y ; I] sweep disappears.
+__device__ void chol_stack_cta(double* T, int n, int rows, Smem& sm, int id_lo = -1) {
     const int nsq = n / NB, ntot = rows / NB;
     for (int j = 0; j < nsq; ++j) {
         panel_factor(T, n, j, sm);
-        for (int i = j; i < ntot; ++i) panel_apply(T, n, j, i, sm);
+        for (int i = j; i < ntot; ++i) {
+            int k0 = 0;
+            if (id_lo >= 0 && i >= id_lo && i < id_lo + nsq) {
+                const int b = i - id_lo;
+                if (b > j) continue;  // still exactly zero in this block column
+                k0 = b * NB;
+            }
+            panel_apply(T, n, j, i, sm, k0);
+        }
         __syncthreads();
         __threadfence_block();
     }
@@ -1012,7 +1025,7 @@ __global__ void __launch_bounds__(NTH) st_gain_kernel(GainArgs a) {
         __syncthreads();
         __threadfence_block();
         // P^- = L L^T;  Y = fP A^T L^-T;  LiT = L^-T
-        chol_stack_cta(T, dp, rows, sm);
+        chol_stack_cta(T, dp, rows, sm, 2 * dp / NB);
         // G = Y L^-1 = Y LiT^T-as-rows  (NT form)
         const double* Y = T + (size_t)dp * dp;
         const double* LiT = T + (size_t)2 * dp * dp;
@@ -1254,7 +1267,7 @@ __global__ void __launch_bounds__(NTH) st_inverse_kernel(InvArgs a) {
             }
         }
         __syncthreads();
-        chol_stack_cta(T, np, rows, sm);
+        chol_stack_cta(T, np, rows, sm, np / NB);
         // inverse = L^-T L^-1 = LiT LiT^T with LiT = T[np:2np]  (cho_solve(L, I))
         const double* LiT = T + (size_t)np * np;
         for (int t = 0; t < tm * tm; ++t) {
@@ -1377,7 +1390,7 @@ __global__ void __launch_bounds__(NTH) st_gell_kernel(long long N, int n, const 
         }
         __syncthreads();
         __threadfence_block();
-        chol_stack_cta(T, np, rows, sm);
+        chol_stack_cta(T, np, rows, sm, 2 * np / NB);
         const double* U = T + (size_t)np * np;
         const double* LiT = T + (size_t)2 * np * np;
         const double* z = T + (size_t)3 * np * np;
