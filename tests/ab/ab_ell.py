@@ -1,7 +1,7 @@
 """Which filter log-likelihood is right at N = 1e7?  fused update vs stand-alone scan filter vs a long-double
 per-step re-evaluation on the host from the GPU's own filtered states (run on the GPU box)."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # tests/ab -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 import bayesnewton_b200 as bn

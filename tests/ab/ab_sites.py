@@ -1,6 +1,6 @@
 """A/B check of the GPU site kernels against the oracle at large N (run on the GPU box)."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # tests/ab -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 import bayesnewton_b200 as bn
