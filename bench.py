@@ -137,7 +137,8 @@ def main_reference(args):
     if rank != 0:
         return
     n = args.cpu_sample
-    r = run_cpu(n, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1 to its children)
+    r = run_cpu(n, max(1, min(args.steps, 3)), min(args.warmup, 1), threads=os.cpu_count() or 1)
     line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
