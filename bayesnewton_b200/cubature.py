@@ -86,13 +86,28 @@ class Unscented(UnscentedFifthOrder):
 
 
 def host_table(cubature, dim):
-    """(x [dim,Q], w [Q], Q) as contiguous float64 numpy arrays (None = Gauss-Hermite 20, the reference default)"""
-    key = ('gh20', dim) if cubature is None else (id(cubature), dim)
-    hit = _cache.get(key)
+    """(x [dim,Q], w [Q], Q) as contiguous float64 numpy arrays (None = Gauss-Hermite 20, the reference default).
+    The default rule is cached per dimension; a custom rule keeps its tables on the object itself (an id()-keyed
+    cache would hand a new object the table of a collected one)."""
+    if cubature is None:
+        hit = _cache.get(('gh20', dim))
+        if hit is None:
+            hit = _cache[('gh20', dim)] = _as_table(*gauss_hermite(dim))
+        return hit
+    store = getattr(cubature, '_bn_tables', None)
+    if store is None:
+        store = {}
+        try:
+            cubature._bn_tables = store
+        except AttributeError:  # e.g. a plain function with __slots__-like restrictions: no caching
+            pass
+    hit = store.get(dim)
     if hit is None:
-        x, w = gauss_hermite(dim) if cubature is None else cubature(dim)
-        x = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)))
-        w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
-        hit = (x, w, int(w.shape[0]))
-        _cache[key] = hit
+        hit = store[dim] = _as_table(*cubature(dim))
     return hit
+
+
+def _as_table(x, w):
+    x = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)))
+    w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
+    return x, w, int(w.shape[0])
