@@ -58,3 +58,32 @@ def test_no_cpu_path():
     from bayesnewton_b200 import _lib, _util
     with pytest.raises(_lib.BnError):
         _util.device()
+
+
+def test_new_entries_report_bad_arguments():
+    """the dense spatio-temporal, sparse, prediction and exchange entries validate before they launch (no GPU needed)"""
+    from bayesnewton_b200 import _lib
+    L = _lib.lib()
+    m32 = _lib.kernel_spec(_lib.BN_MATERN32, [1.0], [1.0])
+    m72 = _lib.kernel_spec(_lib.BN_MATERN72, [1.0], [1.0])
+    two = _lib.kernel_spec(_lib.BN_MATERN32, [1.0, 1.0], [1.0, 1.0])
+    assert L.bn_st_workspace_bytes(m32, 256, 10_000, 256) > 0
+    assert L.bn_st_workspace_bytes(m72, 256, 10, 256) == 0 and b'family' in L.bn_last_error()
+    assert L.bn_st_workspace_bytes(two, 8, 10, 8) == 0 and b'one component' in L.bn_last_error()
+    rc = L.bn_st_kalman_filter(m32, 8, 5, None, None, None, None, 0, None, None, None, None, 0, None)
+    assert rc < 0 and b'null' in L.bn_last_error()
+    rc = L.bn_st_rts_smoother(m32, 0, 5, None, None, None, 0, None, None, None, None, 0, None)
+    assert rc < 0 and b'out of range' in L.bn_last_error()
+    rc = L.bn_spd_inverse_batched(3, 0, None, None, 0.0, None, None, None, None, 0, None)
+    assert rc < 0
+    rc = L.bn_temporal_conditional(two, 4, None, 3, None, None, None, None, 0, None, None, None)
+    assert rc < 0 and b'null' in L.bn_last_error()
+    rc = L.bn_likelihood_predict(_lib.BN_LIK_HETEROSCEDASTIC_SOFTPLUS, 0.0, 4, None, None, 0, None, None, None, None, None)
+    assert rc < 0 and b'single-latent' in L.bn_last_error()
+    rc = L.bn_pairs_discretise(m72, 4, None, None, None, None)
+    assert rc < 0 and b'sparse Markov' in L.bn_last_error()
+    assert L.bn_sparse_workspace_bytes(100) >= 3 * 101 * 8
+    assert L.bn_carry_exchange_bytes(8) == 2 * 8 * 256 * 8 + 2 * 8 * 8
+    rc = L.bn_carry_exchange(None, 8, 0, None, 33, 1, None, None)
+    assert rc < 0 and b'null' in L.bn_last_error()
+    assert L.bn_st_profile(None, 4) < 0
