@@ -17,6 +17,7 @@ BN_MATERN12, BN_MATERN32, BN_MATERN52, BN_MATERN72 = 1, 2, 3, 4
 FAMILY_DIM = {BN_MATERN12: 1, BN_MATERN32: 2, BN_MATERN52: 3, BN_MATERN72: 4}
 BN_LIK_GAUSSIAN, BN_LIK_BERNOULLI_PROBIT, BN_LIK_BERNOULLI_LOGIT = 1, 2, 3
 BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_LIK_HETEROSCEDASTIC_EXP = 4, 5
+BN_LIK_POISSON_EXP = 6
 BN_METHOD_VI, BN_METHOD_EP, BN_METHOD_NEWTON, BN_METHOD_PL = 1, 2, 3, 4
 BN_MAX_COMPONENTS = 4
 

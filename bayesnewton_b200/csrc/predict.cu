@@ -131,6 +131,12 @@ __global__ void likelihood_predict_kernel(int lik, double param, long long N, co
     double e1 = 0.0, e2 = 0.0;
     for (int i = 0; i < Q; ++i) {
         const double f = fma(sd, cx[i], m);
+        if (lik == BN_LIK_POISSON_EXP) {  // E[y|f] = Var[y|f] = b exp(f)  (likelihoods.py:952-959)
+            const double mu = param * exp(f);
+            e1 = fma(cw[i], mu, e1);
+            e2 = fma(cw[i], mu + mu * mu, e2);
+            continue;
+        }
         const double p = lik == BN_LIK_BERNOULLI_PROBIT ? probit_p(f) : 1.0 / (1.0 + exp(-f));
         e1 = fma(cw[i], p, e1);
         e2 = fma(cw[i], p * (1.0 - p) + p * p, e2);  // Cov[y|f] + E[y|f]^2  (likelihoods.py:854-860)
@@ -171,7 +177,8 @@ extern "C" int bn_temporal_conditional(const bn_kernel_spec* k, int64_t N, const
 extern "C" int bn_likelihood_predict(int likelihood, double lik_param, int64_t N, const double* mean_f, const double* var_f,
                                      int Q, const double* cub_x, const double* cub_w, double* mean_y, double* var_y,
                                      void* stream) {
-    BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || likelihood == BN_LIK_BERNOULLI_PROBIT || likelihood == BN_LIK_BERNOULLI_LOGIT,
+    BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || likelihood == BN_LIK_BERNOULLI_PROBIT || likelihood == BN_LIK_BERNOULLI_LOGIT ||
+                   likelihood == BN_LIK_POISSON_EXP,
                "likelihood %d has no single-latent predict on this path", likelihood);
     BN_REQUIRE(N >= 0, "N must be non-negative");
     if (N == 0) return 0;

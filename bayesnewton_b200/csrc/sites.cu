@@ -149,12 +149,14 @@ static int check_site_args(const bn_site_args* a, bool need_y = true) {
     bool het = a->likelihood == BN_LIK_HETEROSCEDASTIC_SOFTPLUS || a->likelihood == BN_LIK_HETEROSCEDASTIC_EXP;
     BN_REQUIRE(a->D == (het ? 2 : 1), "likelihood %d needs D = %d latents, got %d", a->likelihood, het ? 2 : 1, a->D);
     BN_REQUIRE(a->N == 0 || ((a->y || !need_y) && a->post_mean && a->post_cov), "null input array");
-    bool closed = a->likelihood == BN_LIK_GAUSSIAN && (a->method == BN_METHOD_VI || a->method == BN_METHOD_EP);
+    bool closed = (a->likelihood == BN_LIK_GAUSSIAN && (a->method == BN_METHOD_VI || a->method == BN_METHOD_EP)) ||
+                  (a->likelihood == BN_LIK_POISSON_EXP && a->method == BN_METHOD_VI);
     if (a->method != BN_METHOD_NEWTON && !closed) {
         BN_REQUIRE(a->Q > 0 && a->cub_x && a->cub_w, "cubature table missing");
         if (!het) BN_REQUIRE(a->Q <= kMaxQ1, "at most %d cubature points are supported for a single latent, got %d", kMaxQ1, a->Q);
     }
     if (a->likelihood == BN_LIK_GAUSSIAN) BN_REQUIRE(a->lik_param > 0.0, "Gaussian variance must be positive");
+    if (a->likelihood == BN_LIK_POISSON_EXP) BN_REQUIRE(a->lik_param > 0.0, "Poisson bin size must be positive");
     if (a->method == BN_METHOD_EP) BN_REQUIRE(a->power > 0.0, "EP power must be positive");
     return 0;
 }

@@ -41,7 +41,7 @@ struct SiteCtx {
 // ------------------------------------------------------------------------------ single-latent likelihoods
 template <int LIK, bool TAB = false>
 struct Lik1 {
-    double param;       // Gaussian variance
+    double param;       // Gaussian variance / Poisson bin size
     const double* tab;  // TAB: probit log-density table (probit_table.cuh)
 
     BN_DEV double prob(double f) const {
@@ -52,6 +52,9 @@ struct Lik1 {
         if constexpr (LIK == BN_LIK_GAUSSIAN) {
             double r = y - f;
             return -0.5 * log(2.0 * 3.141592653589793 * param) - 0.5 * r * r / param;
+        } else if constexpr (LIK == BN_LIK_POISSON_EXP) {
+            const double mu = exp(f) * param;  // likelihoods.py:939-940
+            return y * log(mu) - mu - lgamma(y + 1.0);
         } else {
             if constexpr (LIK == BN_LIK_BERNOULLI_PROBIT) {
                 if constexpr (TAB) return probit_log_phi(tab, y == 1.0 ? f : -f);  // log(1 - p(f)) = log p(-f)
@@ -66,6 +69,11 @@ struct Lik1 {
             ll = log_lik(y, f);
             d1 = (y - f) / param;
             d2 = -1.0 / param;
+        } else if constexpr (LIK == BN_LIK_POISSON_EXP) {
+            const double mu = exp(f) * param;
+            ll = y * log(mu) - mu - lgamma(y + 1.0);
+            d1 = y - mu;
+            d2 = -mu;
         } else {
             double p = prob(f), dp, ddp;
             if constexpr (LIK == BN_LIK_BERNOULLI_LOGIT) {
@@ -89,6 +97,8 @@ struct Lik1 {
     BN_DEV void moments(double f, double& E, double& V, double& dE) const {
         if constexpr (LIK == BN_LIK_GAUSSIAN) {
             E = f; V = param; dE = 1.0;
+        } else if constexpr (LIK == BN_LIK_POISSON_EXP) {
+            E = V = dE = exp(f) * param;  // likelihoods.py:952-959
         } else {
             double p = prob(f);
             E = p; V = p - p * p;
@@ -163,6 +173,12 @@ BN_DEV SiteStats1 site_stats_1(const Lik1<LIK, TAB>& lik, double y, double m, do
         val = -0.5 * log(2.0 * 3.141592653589793) - 0.5 * log(lik.param) - 0.5 * (r * r + cov) / lik.param;
         j = r / lik.param;
         h = -1.0 / lik.param;
+    } else if constexpr (METHOD == BN_METHOD_VI && LIK == BN_LIK_POISSON_EXP) {
+        // closed form, likelihoods.py:979-1008: E = y log b + y m - b exp(m + v/2) - log y!
+        const double emc = lik.param * exp(mean + 0.5 * cov);
+        val = y * log(lik.param) + y * mean - emc - lgamma(y + 1.0);
+        j = y - emc;
+        h = -emc;
     } else if constexpr (METHOD == BN_METHOD_EP && LIK == BN_LIK_GAUSSIAN) {
         double var = lik.param / power + cov;  // mvn_logpdf_and_derivs, utils.py:448-466
         double L = sqrt(var);
@@ -623,6 +639,8 @@ inline void make_cub1(int Q, const double* x, const double* w, Cub1& c) {
     X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_NEWTON) X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_PL)             \
     X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_VI) X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_EP)                   \
     X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_NEWTON) X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_PL)               \
+    X(BN_LIK_POISSON_EXP, BN_METHOD_VI) X(BN_LIK_POISSON_EXP, BN_METHOD_EP)                           \
+    X(BN_LIK_POISSON_EXP, BN_METHOD_NEWTON) X(BN_LIK_POISSON_EXP, BN_METHOD_PL)                       \
     X(BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_METHOD_VI) X(BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_METHOD_EP) \
     X(BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_METHOD_NEWTON)                                              \
     X(BN_LIK_HETEROSCEDASTIC_EXP, BN_METHOD_VI) X(BN_LIK_HETEROSCEDASTIC_EXP, BN_METHOD_EP)           \

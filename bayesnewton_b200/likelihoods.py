@@ -40,7 +40,8 @@ class Likelihood:
         a = _lib.SiteArgs()
         a.method, a.likelihood, a.lik_param, a.N, a.D = method, self.lik_id, self.lik_param, N, D
         keep = [mean, cov]
-        closed = self.lik_id == _lib.BN_LIK_GAUSSIAN and method in (_lib.BN_METHOD_VI, _lib.BN_METHOD_EP)
+        closed = ((self.lik_id == _lib.BN_LIK_GAUSSIAN and method in (_lib.BN_METHOD_VI, _lib.BN_METHOD_EP))
+                  or (self.lik_id == _lib.BN_LIK_POISSON_EXP and method == _lib.BN_METHOD_VI))
         if method != _lib.BN_METHOD_NEWTON and not closed:
             cx, cw, Q = host_table(cubature, D)  # host arrays: the rule is a kernel parameter
             a.Q, a.cub_x, a.cub_w = Q, cx.ctypes.data, cw.ctypes.data
@@ -138,6 +139,21 @@ class Bernoulli(Likelihood):
         else:
             raise NotImplementedError('link function not implemented')
         self.link = link
+
+
+class Poisson(Likelihood):
+    """p(y|f) = Poisson(y | binsize * exp(f)) for count data (likelihoods.py:891-1008); the variational expectation is
+    the reference's closed form, EP / PL go through the 1-D cubature rule"""
+    lik_id = _lib.BN_LIK_POISSON_EXP
+
+    def __init__(self, binsize=1, link='exp'):
+        if link != 'exp':
+            raise NotImplementedError('the logistic link of the Poisson likelihood is not compiled into libbn_b200')
+        self.binsize, self.link = float(binsize), link
+
+    @property
+    def lik_param(self):
+        return self.binsize
 
 
 class Probit(Bernoulli):

@@ -69,9 +69,10 @@ typedef struct {
     double lengthscale[BN_MAX_COMPONENTS];
 } bn_kernel_spec;
 
-/* likelihoods of the site kernels (likelihoods.py:684-860, 1244-1281) */
+/* likelihoods of the site kernels (likelihoods.py:684-860, 891-1008, 1244-1281); lik_param = Gaussian variance /
+ * Poisson bin size */
 enum { BN_LIK_GAUSSIAN = 1, BN_LIK_BERNOULLI_PROBIT = 2, BN_LIK_BERNOULLI_LOGIT = 3,
-       BN_LIK_HETEROSCEDASTIC_SOFTPLUS = 4, BN_LIK_HETEROSCEDASTIC_EXP = 5 };
+       BN_LIK_HETEROSCEDASTIC_SOFTPLUS = 4, BN_LIK_HETEROSCEDASTIC_EXP = 5, BN_LIK_POISSON_EXP = 6 };
 
 /* inference schemes (inference.py:99-428) */
 enum { BN_METHOD_VI = 1, BN_METHOD_EP = 2, BN_METHOD_NEWTON = 3, BN_METHOD_PL = 4 };

@@ -113,6 +113,31 @@ class Bernoulli:
         return self.dp(f)
 
 
+class Poisson:
+    """p(y|f) = Poisson(y | binsize exp(f)); likelihoods.py:891-1008 (exp link)"""
+    multi_latent = False
+    name = 'poisson'
+
+    def __init__(self, binsize=1.0):
+        self.binsize = float(binsize)
+
+    def log_lik(self, y, f):
+        from scipy.special import gammaln
+        mu = np.exp(f) * self.binsize
+        return y * np.log(mu) - mu - gammaln(y + 1.0)
+
+    def log_lik_derivs(self, y, f):
+        mu = np.exp(f) * self.binsize
+        return self.log_lik(y, f), y - mu, -mu * np.ones(np.broadcast(y, f).shape)
+
+    def conditional_moments(self, f):
+        mu = np.exp(f) * self.binsize
+        return mu, mu
+
+    def dconditional_mean(self, f):
+        return np.exp(f) * self.binsize
+
+
 class HeteroscedasticNoise:
     """p(y|f1,f2) = N(y | f1, link(f2)^2); likelihoods.py:1244-1281"""
     multi_latent = True
@@ -163,6 +188,12 @@ def variational_expectation(lik, y, m, v, num_quad_pts=20):
         E = -0.5 * np.log(2 * np.pi) - 0.5 * np.log(lik.variance) - 0.5 * ((y - m) ** 2 + v) / lik.variance
         dE = (y - m) / lik.variance
         d2E = np.full_like(m, -1. / lik.variance)
+    elif isinstance(lik, Poisson):  # closed form, likelihoods.py:979-1008
+        from scipy.special import gammaln
+        emc = lik.binsize * np.exp(m + v / 2)
+        E = y * np.log(lik.binsize) + y * m - emc - gammaln(y + 1.0)
+        dE = y - emc
+        d2E = -emc
     else:
         x, w = gauss_hermite(1, num_quad_pts)
         sd = np.sqrt(v)  # 1x1 Cholesky
