@@ -55,8 +55,9 @@ constexpr size_t kSmemBytes = sizeof(Smem);  // ~84 KB: dynamic shared memory, o
 // All CTAs are co-resident (grid <= number of SMs, checked on the host).  The counter only grows; the
 // host zeroes it before the launch.
 struct GridSync {
-    unsigned long long* ctr;
+    unsigned long long* ctr;   // ctr[0]: all CTAs;  ctr[16] (its own 128-byte line): the CTAs of a panel sweep
     unsigned long long epoch;
+    unsigned long long epoch2 = 0ULL;
     __device__ void sync() {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -64,6 +65,19 @@ struct GridSync {
             __threadfence();
             atomicAdd(ctr, 1ULL);
             while (*((volatile unsigned long long*)ctr) < epoch) { }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    // barrier among the n CTAs that take part in a panel sweep: the other CTAs wait at the next full barrier, on a
+    // different line, so their polling does not sit on the line the sweep synchronises through
+    __device__ void sync_sub(int n) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            epoch2 += (unsigned long long)n;
+            __threadfence();
+            atomicAdd(ctr + 16, 1ULL);
+            while (*((volatile unsigned long long*)(ctr + 16)) < epoch2) { }
             __threadfence();
         }
         __syncthreads();
@@ -500,23 +514,30 @@ __device__ void chol_stack_grid(const ChSys& s1, const ChSys& s2, Smem& sm, Grid
     const ChSys& s = (b < G1) ? s1 : s2;
     const int lb = (b < G1) ? b : b - G1, LG = (b < G1) ? G1 : G2;
     const int nsq = s1.n / NB;
+    const int nb1 = s1.rows / NB, nb2 = s2.T ? s2.rows / NB : 0;
+    const int npart = (G1 < nb1 ? G1 : nb1) + (G2 < nb2 ? G2 : nb2);   // CTAs that own row blocks
+    const bool part = lb < ((b < G1) ? nb1 : nb2);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    if (lb == 0) {  // diagonal block 0 needs no update
+    if (part) {
+        if (lb == 0) {  // diagonal block 0 needs no update
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) sm.L[ty + 16 * r][tx + 16 * c] = ldg(s.T + (size_t)(ty + 16 * r) * s.n + tx + 16 * c);
-        publish_factor(s, 0, sm);
+                for (int c = 0; c < 2; ++c)
+                    sm.L[ty + 16 * r][tx + 16 * c] = ldg(s.T + (size_t)(ty + 16 * r) * s.n + tx + 16 * c);
+            publish_factor(s, 0, sm);
+        }
+        gs.sync_sub(npart);
+        const bool last_owner = (b < G1) && ((s1.rows / NB - 1) % LG == lb);
+        for (int j = 0; j < nsq; ++j) {
+            long long t0 = clock64();
+            chol_sys_phase(s, j, lb, LG, sm);
+            if (last_owner) ST_PROF(5, t0);
+            if (j + 1 < nsq) gs.sync_sub(npart);   // the full barrier below closes the last panel
+            if (last_owner) ST_PROF(7, t0);
+        }
     }
     gs.sync();
-    const bool last_owner = (b < G1) && ((s1.rows / NB - 1) % LG == lb);
-    for (int j = 0; j < nsq; ++j) {
-        long long t0 = clock64();
-        chol_sys_phase(s, j, lb, LG, sm);
-        if (last_owner) ST_PROF(5, t0);
-        gs.sync();
-        if (last_owner) ST_PROF(7, t0);
-    }
 }
 
 // ---- temporal block of the discretisation ----------------------------------------------------------------
