@@ -171,11 +171,11 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, i
 // used), the rows below hold stacked right-hand sides Wstack.  After panels 0..n/32-1:
 //     T[0:n] lower triangle = L (S = L L^T),   T[n:] = Wstack L^-T.
 
-// 1 / sqrt(x) to fp64 rounding: fp32 MUFU seed + two Newton steps (error 2^-22 -> 1e-13 -> < 1 ulp); the library
-// routine outside the fp32 range and for non-positive / NaN input (NaN out: a non-PD block poisons like cho_factor)
+// 1 / sqrt(x) to fp64 rounding: the hardware's fp64 approximation (MUFU.RSQ64H, 2^-22 relative) + two Newton steps
+// (error -> 1e-13 -> < 1 ulp); negative / NaN input gives NaN (a non-PD block poisons like cho_factor), 0 gives inf
 __device__ __forceinline__ double fast_rsqrt(double x) {
-    if (!(x > 1e-30 && x < 1e30)) return rsqrt(x);
-    double y = (double)rsqrtf((float)x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double hx = 0.5 * x;
     y = fma(y, fma(-hx * y, y, 0.5), y);
     y = fma(y, fma(-hx * y, y, 0.5), y);
@@ -230,7 +230,7 @@ __device__ __forceinline__ void factor_invert_warp(Smem& sm) {
         }
         const double sv = (s0 + s1) + (s2 + s3);
         const double piv = __shfl_sync(0xffffffffu, sv, c);
-        const double inv = rsqrt(piv);  // NaN for piv < 0
+        const double inv = fast_rsqrt(piv);  // NaN for piv < 0
         const double v = (r == c) ? piv * inv : (r > c ? sv * inv : 0.0);
         lr[c] = v;
         sm.L[r][c] = v;
