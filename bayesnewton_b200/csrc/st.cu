@@ -191,14 +191,23 @@ __device__ __forceinline__ void factor_warp(Smem& sm) {
     double a[NB];
 #pragma unroll
     for (int q = 0; q < NB; ++q) a[q] = sm.L[r][q];
+    double dg = sm.L[r][r];  // the lane's own diagonal entry, kept current from its own column values (no round trip)
     double dinv = 0.0;
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
-        const double piv = __shfl_sync(0xffffffffu, a[c], c);
-        const double inv = fast_rsqrt(piv);
-        const double l = (r >= c) ? a[c] * inv : 0.0;
+        const double piv = __shfl_sync(0xffffffffu, dg, c);
+        // 1 / sqrt(piv): hardware seed, one Newton step, the second one folded into the scaling of the column
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(piv));
+        const double hx = 0.5 * piv;
+        y = fma(y, fma(-hx * y, y, 0.5), y);
+        const double e2 = fma(-hx * y, y, 0.5);
+        const double ay = ((r == c) ? piv : a[c]) * y;
+        double l = fma(ay, e2, ay);
+        l = (r >= c) ? l : 0.0;
+        if (r == c) dinv = fma(y, e2, y);
+        dg = fma(-l, l, dg);
         a[c] = l;
-        if (r == c) dinv = inv;
         sm.col[c & 1][r] = l;
         __syncwarp();
 #pragma unroll
