@@ -387,37 +387,64 @@ __device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) 
     if (i0 <= j) i0 += ((j - i0) / LG + 1) * LG;
     if (i0 >= ntot) return;
     const double* lp = s.Lpub + (size_t)(j & 1) * kLpub;
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) sm.Li[ty + 16 * r][tx + 16 * c] = ldg(lp + (ty + 16 * r) * NB + tx + 16 * c);
-    if (threadIdx.x < NB) sm.dinv[threadIdx.x] = ldg(lp + NB * NB + threadIdx.x);
-    if (j > 0) {
-        const double* xb = s.T + (size_t)j * NB * ld + (j - 1) * NB;
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) sm.XB[ty + 16 * r][tx + 16 * c] = ldg(xb + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
-    }
-    for (int i = i0; i < ntot; i += LG) {
-        double* out = s.T + (size_t)i * NB * ld + j * NB;
-        __syncthreads();
-        if (j > 0) {
-            const double* xa = s.T + (size_t)i * NB * ld + (j - 1) * NB;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) sm.XA[ty + 16 * r][tx + 16 * c] = ldg(xa + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
-        }
-        double v[2][2];
+    // every global operand of the first owned row block is requested before anything waits on one of them: the
+    // published factor, the diagonal row block's previous column block, this block's previous column block, its
+    // current column block, its look-ahead accumulator and (square part) its diagonal block -- ONE L2 round trip
+    double rLi[2][2], rXB[2][2], rXA[2][2], rv[2][2], rw[2][2];
+    {
+        const double* xb = s.T + (size_t)j * NB * ld + (j > 0 ? (j - 1) * NB : 0);
+        const double* xa = s.T + (size_t)i0 * NB * ld + (j > 0 ? (j - 1) * NB : 0);
+        const double* o0 = s.T + (size_t)i0 * NB * ld + j * NB;
+        const double* d0 = s.T + (size_t)i0 * NB * ld + (i0 < nsq ? i0 : 0) * NB;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int rr = ty + 16 * r, cc = tx + 16 * c;
-                v[r][c] = ldg(out + (size_t)rr * ld + cc);
-                if (j > 1) v[r][c] -= ldg(s.Pacc + (size_t)i * NB * NB + rr * NB + cc);
+                rLi[r][c] = ldg(lp + rr * NB + cc);
+                rXB[r][c] = j > 0 ? ldg(xb + (size_t)rr * ld + cc) : 0.0;
+                rXA[r][c] = j > 0 ? ldg(xa + (size_t)rr * ld + cc) : 0.0;
+                rv[r][c] = ldg(o0 + (size_t)rr * ld + cc);
+                if (j > 1) rv[r][c] -= ldg(s.Pacc + (size_t)i0 * NB * NB + rr * NB + cc);
+                rw[r][c] = i0 < nsq ? ldg(d0 + (size_t)rr * ld + cc) : 0.0;
             }
+        if (threadIdx.x < NB) sm.dinv[threadIdx.x] = ldg(lp + NB * NB + threadIdx.x);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                sm.Li[ty + 16 * r][tx + 16 * c] = rLi[r][c];
+                sm.XB[ty + 16 * r][tx + 16 * c] = rXB[r][c];
+                sm.XA[ty + 16 * r][tx + 16 * c] = rXA[r][c];
+            }
+    }
+    for (int i = i0; i < ntot; i += LG) {
+        double* out = s.T + (size_t)i * NB * ld + j * NB;
+        double v[2][2];
+        if (i == i0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) v[r][c] = rv[r][c];
+        } else {
+            __syncthreads();
+            if (j > 0) {
+                const double* xa = s.T + (size_t)i * NB * ld + (j - 1) * NB;
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        sm.XA[ty + 16 * r][tx + 16 * c] = ldg(xa + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int rr = ty + 16 * r, cc = tx + 16 * c;
+                    v[r][c] = ldg(out + (size_t)rr * ld + cc);
+                    if (j > 1) v[r][c] -= ldg(s.Pacc + (size_t)i * NB * NB + rr * NB + cc);
+                }
+        }
         __syncthreads();
         if (j > 0) {
 #pragma unroll 8
@@ -462,7 +489,8 @@ __device__ void chol_sys_phase(const ChSys& s, int j, int lb, int LG, Smem& sm) 
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int c = 0; c < 2; ++c) w[r][c] = ldg(dg + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
+                for (int c = 0; c < 2; ++c)
+                    w[r][c] = (i == i0) ? rw[r][c] : ldg(dg + (size_t)(ty + 16 * r) * ld + tx + 16 * c);
 #pragma unroll 8
             for (int k = 0; k < NB; ++k) {
                 const double a0 = sm.XO[ty][k], a1 = sm.XO[ty + 16][k], b0 = sm.XO[tx][k], b1 = sm.XO[tx + 16][k];
