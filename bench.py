@@ -40,6 +40,7 @@ ALGO_BYTES = {
     'site_update': 72,        # y, m, v, nat1, nat2 in; nat1, nat2, mean, cov out   (= U)
     'expected_density': 24,   # y, m, v                                   (= V)
     'gaussian_ell': 32,       # pseudo_y, m, v, pseudo_var                (= X)
+    'energy_terms': 24 + 33,  # y, m, v + pseudo_y, pseudo_var (+mask): V and X in one pass
 }
 
 
@@ -49,7 +50,8 @@ FP64_OPS = {'up_reduce': 179, 'up_filter': 163, 'up_smooth': 260}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per time step of one launch, from the ncu --set full captures
 # under profiles/ (N = 1e7); reported as `traffic` (scaled by the steps a launch processes)
-NCU_DRAM_BYTES = {'up_reduce': 24.8, 'up_filter': 98.9, 'up_smooth': 95.7, 'site_update': 67.4}
+# dram__bytes_read.sum + dram__bytes_write.sum per time step of one launch at N = 1e7 (profiles/r2l_ncu_full_summary_c2.csv)
+NCU_DRAM_BYTES = {'up_reduce': 26.0, 'up_filter': 97.1, 'up_smooth': 96.9, 'site_update': 67.3, 'energy_terms': 40.7}
 
 
 def bench_inputs(N, seed=0):
@@ -339,7 +341,7 @@ def main_gpu(args):
             traffic = NCU_DRAM_BYTES[dom] * NL if (args.traffic is None and dom in NCU_DRAM_BYTES) else args.traffic
             roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                    'traffic_source': 'ncu --set full dram bytes per step at N=1e7 (profiles/) x steps per launch',
+                    'traffic_source': 'ncu --set full dram bytes per step at N=1e7 (profiles/r2l_ncu_full_summary_c2.csv) x steps per launch',
                     'algorithmic_bytes_per_launch': ab * NL, 'avg_launch_ms': avg_ms,
                     'share_of_step': tot / (ms_per_step * args.steps),
                     'timing': 'CUDA events around every launch of this kernel, on its stream, in a second pass of the same K steps right after the timed region'}
