@@ -86,6 +86,8 @@ SIGNATURES = {
     'bn_st_rts_smoother_meanfield': (_I, [_KS, _I, _L, _P, _P, _P, _I, _P, _P, _P, _P]),
     'bn_carry_exchange_bytes': (_Z, [_I]),
     'bn_carry_exchange': (_I, [_P, _I, _I, _P, _I, C.c_uint64, _P, _P]),
+    'bn_st_predict_workspace_bytes': (_Z, [_KS, _I, _L]),
+    'bn_st_predict_state': (_I, [_KS, _I, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_st_workspace_bytes': (_Z, [_KS, _I, _L, _I]),
     'bn_st_kalman_filter': (_I, [_KS, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     'bn_st_rts_smoother': (_I, [_KS, _I, _L, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),

@@ -19,6 +19,7 @@
 // KL term) use the same panel code with one CTA per time step.
 #include "common.cuh"
 #include "gen.cuh"
+#include "condstats.cuh"
 
 namespace bn {
 namespace st {
@@ -1412,6 +1413,95 @@ __global__ void __launch_bounds__(NTH) st_to_data_kernel(long long N, int Ns, in
     }
 }
 
+// ---- prediction at test times (MarkovGaussianProcess.predict, basemodels.py:766-816, for a SpatioTemporalKernel) -------
+// temporal_conditional (utils.py:99-136, 173-215) on the Kronecker state: with the n x n temporal conditional
+// [P1, W], T of the two gaps around the test time, the state covariance is
+//     (I (x) P1) C_- (I (x) P1)^T + (I (x) P1) X (I (x) W)^T + (I (x) W) X^T (I (x) P1)^T + (I (x) W) C_+ (I (x) W)^T + I (x) T,
+// X = G C_+ (gain of the left neighbour times the covariance of the right one: the only dense product), and what
+// predict() needs is H (.) H^T, i.e. per block pair the quadratic forms with p = P1[0,:], w = W[0,:].  One CTA per
+// test time; C_+ = Pinf-Kronecker (pk) and G = 0 at the ends (the dummy states of basemodels.py:793-794).
+struct StPredArgs {
+    bn_kernel_spec spec;
+    int M;
+    long long N, Nq;
+    const double* x;      // [N] training times
+    const double* xs;     // [Nq] test times
+    const double* sm;     // [N,d]
+    const double* sP;     // [N,d,d]
+    const double* gain;   // [N,d,d]
+    const double* pk;     // [d,d]  I (x) Pinf_t
+    double* fmean;        // [Nq,M]
+    double* fcov;         // [Nq,M,M]
+    double* X;            // per-CTA slots [d,d]
+};
+
+template <int FAM>
+__global__ void __launch_bounds__(NTH) st_predict_kernel(StPredArgs a) {
+    constexpr int n = FamilyDim<FAM>::value;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smraw);
+    const int M = a.M, d = M * n;
+    double* X = a.X + (size_t)blockIdx.x * d * d;
+    MaternGen<FAM, 1> gen;
+    gen.spec = a.spec;
+    gen.dt = nullptr;
+    for (long long q = blockIdx.x; q < a.Nq; q += gridDim.x) {
+        const double xt = a.xs[q];
+        long long lo = 0, hi = a.N;  // number of training times strictly below xt = index into the augmented arrays
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (a.x[mid] < xt) lo = mid + 1; else hi = mid;
+        }
+        const long long ind = lo;
+        const double xl = ind == 0 ? -1e10 : a.x[ind - 1];
+        const double xr = ind == a.N ? 1e10 : a.x[ind];
+        double P1[n * n], W[n * n], Tm[n * n];
+        cond_stats(gen, xt - xl, xr - xt, P1, W, Tm);
+        const double* Cl = ind == 0 ? a.pk : a.sP + (size_t)(ind - 1) * d * d;
+        const double* Cr = ind == a.N ? a.pk : a.sP + (size_t)ind * d * d;
+        const double* G = ind == 0 ? nullptr : a.gain + (size_t)(ind - 1) * d * d;
+        const double* ml = ind == 0 ? nullptr : a.sm + (size_t)(ind - 1) * d;
+        const double* mr = ind == a.N ? nullptr : a.sm + (size_t)ind * d;
+        // X = G C_+  (C_+ symmetric: NT form)
+        const int tm = (d + 63) / 64;
+        for (int t = 0; t < tm * tm; ++t) {
+            const int i0 = (t / tm) * 64, j0 = (t % tm) * 64;
+            double acc[4][4];
+            if (G) tile_nt<64, 64, false>(G, d, d, Cr, d, d, d, i0, j0, nullptr, acc, sm);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int row = i0 + trow<64>(r), col = j0 + tcol<64>(c);
+                    if (row < d && col < d) X[(size_t)row * d + col] = G ? acc[r][c] : 0.0;
+                }
+        }
+        __syncthreads();
+        __threadfence_block();
+        for (int e = threadIdx.x; e < M * M; e += NTH) {
+            const int i = e / M, j = e % M;
+            double v = (i == j) ? Tm[0] : 0.0;
+#pragma unroll
+            for (int p = 0; p < n; ++p)
+#pragma unroll
+                for (int b = 0; b < n; ++b) {
+                    const size_t rij = (size_t)(i * n + p) * d + j * n + b, rji = (size_t)(j * n + p) * d + i * n + b;
+                    v = fma(P1[p] * P1[b], Cl[rij], v);
+                    v = fma(W[p] * W[b], Cr[rij], v);
+                    v = fma(P1[p] * W[b], ldg(X + rij) + ldg(X + rji), v);
+                }
+            a.fcov[(size_t)q * M * M + e] = v;
+        }
+        for (int i = threadIdx.x; i < M; i += NTH) {
+            double v = 0.0;
+#pragma unroll
+            for (int p = 0; p < n; ++p) v = fma(P1[p], ml ? ml[i * n + p] : 0.0, fma(W[p], mr ? mr[i * n + p] : 0.0, v));
+            a.fmean[(size_t)q * M + i] = v;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- Gaussian KL term with full M x M blocks (utils.py:510-531 through basemodels.py:715-721) ------------------
 // out_k = log N(y_k | m_k, R_k) - 0.5 tr(R_k^-1 V_k), both through chol(R_k).  One CTA per time step.
 // T = [R ; V ; I ; (y - m)^T]:  U = V L^-T, LiT = L^-T  =>  tr(R^-1 V) = sum_ij LiT[i][j] U[i][j].
@@ -1708,6 +1798,55 @@ extern "C" int bn_st_rts_smoother_meanfield(const bn_kernel_spec* temporal, int 
     if (!return_full) BN_CUDA(cudaMemsetAsync(covs, 0, (size_t)N * M * M * sizeof(double), s));
     const unsigned grid = (unsigned)((M + 63) / 64);
 #define CALL(F) BN_LAUNCH("st_mf_smoother", s, st_mf_smoother_kernel<F><<<grid, 64, 0, s>>>(*temporal, M, N, dt, filter_mean, filter_cov, return_full, means, covs, gains))
+    ST_DISPATCH_FAMILY(temporal->family, CALL)
+#undef CALL
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+static __global__ void st_pinf_kron_kernel(bn_kernel_spec spec, int M, int n, double* pk) {
+    // I (x) Pinf_t, d x d
+    const int d = M * n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)d * d; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / d), c = (int)(e % d);
+        double v = 0.0;
+        if (r / n == c / n) {
+            double Pp[6];
+            const int a = r % n, b = c % n;
+            if (spec.family == BN_MATERN12) MaternBlock<BN_MATERN12, double>::pinf(spec.variance[0], spec.lengthscale[0], Pp);
+            else if (spec.family == BN_MATERN32) MaternBlock<BN_MATERN32, double>::pinf(spec.variance[0], spec.lengthscale[0], Pp);
+            else MaternBlock<BN_MATERN52, double>::pinf(spec.variance[0], spec.lengthscale[0], Pp);
+            v = Pp[sidx(a, b)];
+        }
+        pk[e] = v;
+    }
+}
+
+extern "C" size_t bn_st_predict_workspace_bytes(const bn_kernel_spec* temporal, int M, int64_t Nq) {
+    int n = 0;
+    if (st_check_spec(temporal, M, &n) != 0) return 0;
+    const size_t d = (size_t)M * n;
+    return ((size_t)batch_grid(Nq) + 1) * d * d * sizeof(double) + 512;
+}
+
+extern "C" int bn_st_predict_state(const bn_kernel_spec* temporal, int M, int64_t N, const double* x, int64_t Nq,
+                                   const double* x_test, const double* mean, const double* cov, const double* gain,
+                                   double* f_mean, double* f_cov, void* workspace, size_t workspace_bytes, void* stream) {
+    int n = 0;
+    if (int rc = st_check_spec(temporal, M, &n)) return rc;
+    BN_REQUIRE(N >= 1 && Nq >= 0, "bad sizes N = %lld, N_test = %lld", (long long)N, (long long)Nq);
+    if (Nq == 0) return 0;
+    BN_REQUIRE(x && x_test && mean && cov && gain && f_mean && f_cov, "null array");
+    BN_REQUIRE(workspace && workspace_bytes >= bn_st_predict_workspace_bytes(temporal, M, Nq), "workspace too small");
+    const size_t d = (size_t)M * n;
+    StPredArgs a;
+    a.spec = *temporal; a.M = M; a.N = N; a.Nq = Nq; a.x = x; a.xs = x_test; a.sm = mean; a.sP = cov; a.gain = gain;
+    a.pk = (double*)workspace; a.X = (double*)workspace + d * d; a.fmean = f_mean; a.fcov = f_cov;
+    cudaStream_t s = (cudaStream_t)stream;
+    st_pinf_kron_kernel<<<64, 256, 0, s>>>(*temporal, M, n, (double*)workspace);
+    BN_CUDA(cudaGetLastError());
+#define CALL(F) BN_CUDA(allow_smem(st_predict_kernel<F>)); BN_LAUNCH("st_predict", s, st_predict_kernel<F><<<batch_grid(Nq), NTH, kSmemBytes, s>>>(a))
     ST_DISPATCH_FAMILY(temporal->family, CALL)
 #undef CALL
     BN_CUDA(cudaGetLastError());

@@ -388,8 +388,40 @@ class SpatioTemporalMixin:
         a.nat1, a.nat2 = pl.nat1_.data_ptr(), pl.nat2_.data_ptr()
         return a, keep + [mean_f, var_f]
 
-    def predict(self, X=None, R=None):
-        raise NotImplementedError('prediction at new inputs is a `next` row (utils.temporal_conditional)')
+    def predict(self, X=None, R=None, pseudo_lik_params=None):
+        """latent mean and variance at test times X [N*] and spatial inputs R [N_s*, n_dims] (the same at every test
+        time; default: the training ones): filter, full-state smoother with gains, the temporal conditional on the
+        Kronecker state (bn_st_predict_state) and the spatial conditional (basemodels.py:766-816).  Returns
+        (mean [N*, N_s*], var [N*, N_s*]) -- the reference discards the spatial covariance as well (:813-815)."""
+        times = self.X if X is None else np.asarray(X, dtype=np.float64).reshape(-1)
+        Rs = self.R[0] if R is None else np.asarray(R, dtype=np.float64)
+        if Rs.ndim == 3:
+            if not np.all(np.abs(Rs - Rs[:1]) < 1e-10):
+                raise NotImplementedError('the dense path predicts on one set of spatial inputs for all test times')
+            Rs = Rs[0]
+        B, C = self.kernel.spatial_conditional(times, Rs, predict=True)
+        Bd = as_dev(B)
+        cdiag = as_dev(np.ascontiguousarray(np.diag(C))) if C.shape[0] == B.shape[0] else None
+        pseudo_y, pseudo_var = self.compute_full_pseudo_lik() if pseudo_lik_params is None else pseudo_lik_params
+        _, (fm, fP) = self.filter(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y, want_ell=False)
+        sm, sP, gain = self.smoother(self.dt_smoother, self.kernel, fm, fP, return_full=True)
+        return self._predict_from_state(times, sm, sP, gain, Bd, cdiag)
+
+    def _predict_from_state(self, times, sm, sP, gain, Bd, cdiag):
+        M, Nq, Ns = self.kernel.M, times.shape[0], Bd.shape[0]
+        spec = self.kernel.spec()
+        xs = as_dev(times)
+        fmean = torch.empty((Nq, M, 1), dtype=torch.float64, device=xs.device)
+        fcov = torch.empty((Nq, M, M), dtype=torch.float64, device=xs.device)
+        need = int(_lib.lib().bn_st_predict_workspace_bytes(spec, M, Nq))
+        ws = torch.empty(need, dtype=torch.uint8, device=xs.device)
+        _lib.check(_lib.lib().bn_st_predict_state(spec, M, self.num_data, ptr(as_dev(self.X)), Nq, ptr(xs), ptr(sm), ptr(sP),
+                                                  ptr(gain), ptr(fmean), ptr(fcov), ptr(ws), need, stream_ptr()))
+        mean = torch.empty((Nq, Ns), dtype=torch.float64, device=xs.device)
+        var = torch.empty((Nq, Ns), dtype=torch.float64, device=xs.device)
+        _lib.check(_lib.lib().bn_st_posterior_to_data(Nq, Ns, M, ptr(Bd), ptr(cdiag), ptr(fmean), ptr(fcov), ptr(mean), ptr(var),
+                                                      stream_ptr()))
+        return mean.squeeze(), var.squeeze()
 
 
 class MeanFieldMixin(SpatioTemporalMixin):

@@ -416,6 +416,15 @@ size_t bn_carry_exchange_bytes(int world);
 int bn_carry_exchange(const uint64_t* peer_buffers_dev, int world, int rank, const double* carry, int len,
                       uint64_t seq, double* out, void* stream);
 
+/* MarkovGaussianProcess.predict for a SpatioTemporalKernel (basemodels.py:766-816): the temporal_conditional step
+ * (utils.py:99-136, 173-215) on the Kronecker state followed by H (.) H^T.  x[N]: training times; x_test[Nq];
+ * mean[N,d,1], cov[N,d,d], gain[N,d,d] from bn_st_rts_smoother(return_full=1).  f_mean[Nq,M,1], f_cov[Nq,M,M]: the
+ * latent at the inducing points at the test times; bn_st_posterior_to_data then maps them to any spatial inputs. */
+size_t bn_st_predict_workspace_bytes(const bn_kernel_spec* temporal, int M, int64_t N_test);
+int bn_st_predict_state(const bn_kernel_spec* temporal, int M, int64_t N, const double* x, int64_t N_test,
+                        const double* x_test, const double* mean, const double* cov, const double* gain,
+                        double* f_mean, double* f_cov, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,6 +213,26 @@ class SpatioTemporalMarkovGP:
         return -(np.nansum(E) - self.compute_kl())
 
 
+def markov_predict(model, X_test, R_test=None):
+    """MarkovGaussianProcess.predict (basemodels.py:766-816) for a SpatioTemporalMarkovGP: latent mean and variance at
+    test times X_test [N*] and spatial inputs R_test [N_s*, n_dims] (default: the training ones) -> ([N*, N_s*], same)"""
+    from .predict import temporal_conditional
+    X_test = np.asarray(X_test, dtype=np.float64).reshape(-1)
+    R_test = model.R[0] if R_test is None else np.asarray(R_test, dtype=np.float64)
+    k = model.kernel
+    py, pv = model.compute_full_pseudo_lik()
+    _, (fm, fP) = kalman.kalman_filter(model.dt, k, py, pv, model._mask3())
+    dts = np.concatenate([model.dt[1:], [0.0]])
+    sm, sP, gain = kalman.rauch_tung_striebel_smoother(dts, k, fm, fP, return_full=True)
+    state_mean, state_cov = temporal_conditional(model.t, X_test, sm, sP, gain, k)
+    H = k.measurement_model()
+    B, C = k.spatial_conditional(X_test, np.tile(R_test[None], (X_test.shape[0], 1, 1)))
+    W = B @ H
+    mean = (W @ state_mean)[..., 0]
+    var = np.diagonal(W @ state_cov @ T(W) + C, axis1=1, axis2=2)
+    return mean, var
+
+
 class DenseSpatioTemporalGP:
     """VariationalGP on the flattened space-time inputs with K = k_t * k_s (basemodels.py:265-357, ops.py:52-80),
     Gaussian sites one per observation; no missing data."""

@@ -404,3 +404,33 @@ def test_gpu_spatiotemporal_rejects_what_it_does_not_cover(bn):
     L = bn._lib.lib()
     spec = bn.kernels.Matern72(1.0, 1.0).spec()
     assert L.bn_st_workspace_bytes(spec, 4, 4, 4) == 0 and b'family' in L.bn_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ prediction
+def test_oracle_st_predict_at_training_inputs_is_the_posterior():
+    t, Y, R = st_data(9, 9, seed=2, spatial_dims=2)
+    k = oracle_kernel('Matern32', 1.1, 0.9, 1.2, R[0], spatial_dims=2)
+    m = ost.SpatioTemporalMarkovGP(k, sites.Gaussian(0.3), t, Y, R)
+    m.inference()
+    mean, var = ost.markov_predict(m, m.t)
+    mf, cf = m.conditional_posterior_to_data()
+    assert rel_err(mean, mf[..., 0]) < 1e-6 and rel_err(var, np.diagonal(cf, axis1=1, axis2=2)) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fam', ['Matern12', 'Matern32', 'Matern52'])
+@pytest.mark.parametrize('new_space', [False, True])
+def test_gpu_spatiotemporal_predict_vs_oracle(bn, fam, new_space):
+    Nt, Ns = 10, 9
+    t, Y, R = st_data(Nt, Ns, seed=5, spatial_dims=2)
+    ko = oracle_kernel(fam, 1.1, 0.9, 1.2, R[0], spatial_dims=2)
+    kg = gpu_kernel(bn, fam, 1.1, 0.9, 1.2, R[0], spatial_dims=2)
+    mo = ost.SpatioTemporalMarkovGP(ko, sites.Gaussian(0.3), t, Y, R)
+    mg = bn.models.MarkovVariationalGP(kernel=kg, likelihood=bn.likelihoods.Gaussian(0.3), X=t, Y=Y, R=R)
+    mo.inference(lr=0.8)
+    mg.inference(lr=0.8)
+    xs = np.concatenate([[t[0] - 2.0], 0.5 * (t[:-1] + t[1:])[::2], t[[0, 4, -1]], [t[-1] + 0.7, t[-1] + 30.0]])
+    Rs = np.random.default_rng(0).uniform(-1, 1, (5, 2)) if new_space else None
+    m0, v0 = ost.markov_predict(mo, xs, Rs)
+    m1, v1 = mg.predict(xs, Rs)
+    assert rel_err(np_(m1), m0) < 1e-8 and rel_err(np_(v1), v0) < 1e-8
