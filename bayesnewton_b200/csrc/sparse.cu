@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(128) sparse_site_kernel(MaternGen<FAM, 1> gen,
 using namespace bn;
 
 #define SPARSE_FAMILIES(X) X(BN_MATERN12) X(BN_MATERN32) X(BN_MATERN52)
-#define SPARSE_LIKS(X, F) X(F, BN_LIK_GAUSSIAN) X(F, BN_LIK_BERNOULLI_PROBIT) X(F, BN_LIK_BERNOULLI_LOGIT)
+#define SPARSE_LIKS(X, F) X(F, BN_LIK_GAUSSIAN) X(F, BN_LIK_BERNOULLI_PROBIT) X(F, BN_LIK_BERNOULLI_LOGIT) X(F, BN_LIK_POISSON_EXP)
 
 static int sparse_check_spec(const bn_kernel_spec* k) {
     BN_REQUIRE(k != nullptr, "kernel spec is null");
@@ -276,7 +276,7 @@ extern "C" int bn_build_joint(const bn_kernel_spec* k, int64_t Mt, const double*
 static int sparse_launch(bool update, const bn_kernel_spec* k, int likelihood, const SparseArgs& a, int Q, const double* cub_x,
                          const double* cub_w, cudaStream_t s) {
     Cub1 cub;
-    make_cub1(likelihood == BN_LIK_GAUSSIAN ? 0 : Q, cub_x, cub_w, cub);
+    make_cub1((likelihood == BN_LIK_GAUSSIAN || likelihood == BN_LIK_POISSON_EXP) ? 0 : Q, cub_x, cub_w, cub);
     const long long Mt = a.Mz + 1;
     const unsigned grid = (unsigned)((Mt * 32 + 127) / 128);
     bool done = false;
@@ -305,7 +305,8 @@ extern "C" int bn_sparse_site_update(const bn_kernel_spec* k, int likelihood, do
     if (int rc = sparse_check_spec(k)) return rc;
     BN_REQUIRE(N >= 0 && Mz >= 1, "bad sizes N = %lld, Mz = %lld", (long long)N, (long long)Mz);
     BN_REQUIRE(x && y && z && start && post_mean && post_cov && nat1 && nat2 && site_mean && site_cov, "null array");
-    BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || (Q >= 1 && Q <= kMaxQ1 && cub_x && cub_w), "a 1-D cubature rule (host arrays, Q <= %d) is needed", kMaxQ1);
+    BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || likelihood == BN_LIK_POISSON_EXP || (Q >= 1 && Q <= kMaxQ1 && cub_x && cub_w),
+               "a 1-D cubature rule (host arrays, Q <= %d) is needed", kMaxQ1);
     BN_REQUIRE(workspace && workspace_bytes >= bn_sparse_workspace_bytes(Mz), "workspace too small");
     SparseArgs a{N, Mz, x, y, z, (const long long*)start, post_mean, post_cov, lik_param, lr, ensure_psd, nat1, nat2,
                  site_mean, site_cov, (double*)workspace};
@@ -329,7 +330,8 @@ extern "C" int bn_sparse_expected_density(const bn_kernel_spec* k, int likelihoo
     if (int rc = sparse_check_spec(k)) return rc;
     BN_REQUIRE(N >= 0 && Mz >= 1, "bad sizes N = %lld, Mz = %lld", (long long)N, (long long)Mz);
     BN_REQUIRE(x && y && z && start && post_mean && post_cov && sum, "null array");
-    BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || (Q >= 1 && Q <= kMaxQ1 && cub_x && cub_w), "a 1-D cubature rule (host arrays, Q <= %d) is needed", kMaxQ1);
+    BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || likelihood == BN_LIK_POISSON_EXP || (Q >= 1 && Q <= kMaxQ1 && cub_x && cub_w),
+               "a 1-D cubature rule (host arrays, Q <= %d) is needed", kMaxQ1);
     BN_REQUIRE(workspace && workspace_bytes >= bn_sparse_workspace_bytes(Mz), "workspace too small");
     SparseArgs a{N, Mz, x, y, z, (const long long*)start, post_mean, post_cov, lik_param, 1.0, 0, nullptr, nullptr, nullptr,
                  nullptr, (double*)workspace};

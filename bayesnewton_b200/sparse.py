@@ -162,7 +162,7 @@ class SparseMarkovGaussianProcess:
         return self.expected_density_pseudo() - self.compute_log_lik()
 
     def _cub(self, cubature):
-        if self.likelihood.lik_id == _lib.BN_LIK_GAUSSIAN:
+        if self.likelihood.lik_id in (_lib.BN_LIK_GAUSSIAN, _lib.BN_LIK_POISSON_EXP):  # closed-form VI statistics
             return 0, None, None
         cx, cw, Q = host_table(cubature, 1)
         return Q, cx, cw

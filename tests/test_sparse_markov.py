@@ -90,16 +90,19 @@ def test_gpu_pairs_filter_vs_oracle(bn, fam, parallel):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('fam', ['Matern12', 'Matern32', 'Matern52'])
-@pytest.mark.parametrize('lik', ['gaussian', 'probit', 'logit'])
+@pytest.mark.parametrize('lik', ['gaussian', 'probit', 'logit', 'poisson'])
 @pytest.mark.parametrize('zmode', ['z_is_x', 'sparse', 'one'])
 def test_gpu_sparse_markov_iteration_vs_oracle(bn, fam, lik, zmode):
     N = 120
     x, y = wiggly(N, 7)
-    if lik != 'gaussian':
+    if lik == 'poisson':
+        y = np.random.default_rng(9).poisson(np.exp(0.8 * y)).astype(np.float64)
+    elif lik != 'gaussian':
         y = (y > 0).astype(np.float64)
     y[[5, 77]] = np.nan  # missing observations
     z = {'z_is_x': x, 'sparse': np.linspace(-12.0, 33.0, 19), 'one': np.array([10.0])}[zmode]
-    lo = {'gaussian': lambda L: L.Gaussian(0.3), 'probit': lambda L: L.Bernoulli('probit'), 'logit': lambda L: L.Bernoulli('logit')}[lik]
+    lo = {'gaussian': lambda L: L.Gaussian(0.3), 'probit': lambda L: L.Bernoulli('probit'), 'logit': lambda L: L.Bernoulli('logit'),
+          'poisson': lambda L: L.Poisson(0.5)}[lik]
     ko, kg = getattr(ssm, fam)(1.1, 5.5), getattr(bn.kernels, fam)(1.1, 5.5)
     mo = osp.SparseMarkovGP(ko, lo(sites), x, y, z)
     mg = bn.models.SparseMarkovVariationalGP(kernel=kg, likelihood=lo(bn.likelihoods), X=x, Y=y, Z=z, parallel=False)
