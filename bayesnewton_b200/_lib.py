@@ -36,12 +36,21 @@ class SiteArgs(C.Structure):
                 ('out_jac', C.c_void_p), ('out_hess', C.c_void_p), ('diffs', C.c_void_p)]
 
 
+class IterArgs(C.Structure):
+    """bn_iter_args (include/bn_b200.h)"""
+    _fields_ = [('N', C.c_int64), ('rank', C.c_int32), ('world', C.c_int32), ('dt_t', C.c_void_p), ('y_t', C.c_void_p),
+                ('site_mean_t', C.c_void_p), ('site_cov_t', C.c_void_p), ('mask_t', C.c_void_p),
+                ('post_mean_t', C.c_void_p), ('post_cov_t', C.c_void_p), ('method', C.c_int32), ('likelihood', C.c_int32),
+                ('lik_param', C.c_double), ('Q', C.c_int32), ('ensure_psd', C.c_int32), ('cub_x_host', C.c_void_p),
+                ('cub_w_host', C.c_void_p), ('lr', C.c_double), ('power', C.c_double)]
+
+
 class BnError(RuntimeError):
     pass
 
 
 _P, _I, _L, _Z, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
-_KS, _SA = C.POINTER(KernelSpec), C.POINTER(SiteArgs)
+_KS, _SA, _IA = C.POINTER(KernelSpec), C.POINTER(SiteArgs), C.POINTER(IterArgs)
 
 # every symbol include/bn_b200.h declares, with its argument types
 SIGNATURES = {
@@ -96,6 +105,16 @@ SIGNATURES = {
     'bn_st_pseudo_lik': (_I, [_L, _I, _I, _P, _P, _P, _D, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_st_posterior_to_data': (_I, [_L, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'bn_st_gaussian_expected_log_lik': (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    'bn_iter_chunk_len': (_I, [_KS, _L]),
+    'bn_iter_tiled_len': (_L, [_KS, _L]),
+    'bn_iter_workspace_bytes': (_Z, [_KS, _L]),
+    'bn_iter_to_tiled': (_I, [_KS, _L, _P, _P, _D, _P]),
+    'bn_iter_from_tiled': (_I, [_KS, _L, _P, _P, _P]),
+    'bn_iter_to_tiled_u8': (_I, [_KS, _L, _P, _P, _P]),
+    'bn_iter_pass': (_I, [_KS, _IA, _I, _P, _P, _P, _Z, _P]),
+    'bn_iter_shard_reduce': (_I, [_KS, _IA, _P, _P, _Z, _P]),
+    'bn_iter_shard_filter': (_I, [_KS, _IA, _P, _P, _P, _P, _Z, _P]),
+    'bn_iter_shard_smooth': (_I, [_KS, _IA, _I, _P, _P, _P, _Z, _P]),
 }
 
 _lib = None

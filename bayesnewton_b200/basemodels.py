@@ -7,7 +7,9 @@ projection is a `next` row of SURVEY section 8f).
 import numpy as np
 import torch
 
-from . import _lib, ops
+import os
+
+from . import _lib, fused, ops
 from ._util import as_dev, as_mask, device, ptr, stream_ptr, workspace
 from .kernels import Independent
 
@@ -23,23 +25,43 @@ def input_admin(t, y):
 
 
 class GaussianDistribution:
-    """sites in (mean, covariance) and natural (nat1, nat2 = cov^-1) form (basemodels.py:52-100)"""
+    """sites in (mean, covariance) and natural (nat1, nat2 = cov^-1) form (basemodels.py:52-100).
+
+    While a fused iteration (fused.FusedShard) owns the sites they live in its tiled arrays; `source` then names it and
+    the four arrays below are materialised on first access (diagonal sites: nat2 = 1 / cov, nat1 = nat2 mean)."""
 
     def __init__(self, mean, covariance, nat1=None, nat2=None):
         self.version = 0  # bumped whenever the parameters change (invalidates anything derived from them)
-        self.mean_, self.covariance_ = as_dev(mean), as_dev(covariance)
+        self.source = None
+        self._mean, self._cov = as_dev(mean), as_dev(covariance)
         if nat1 is None:
-            self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
+            self._nat1, self._nat2 = self.reparametrise(self._mean, self._cov)
         else:  # the caller knows both forms (e.g. the diagonal initial sites): no factorisation needed
-            self.nat1_, self.nat2_ = as_dev(nat1), as_dev(nat2)
+            self._nat1, self._nat2 = as_dev(nat1), as_dev(nat2)
 
     def __call__(self):
         return self.mean, self.covariance
 
-    mean = property(lambda self: self.mean_)
-    covariance = property(lambda self: self.covariance_)
-    nat1 = property(lambda self: self.nat1_)
-    nat2 = property(lambda self: self.nat2_)
+    def _sync(self):
+        src, self.source = self.source, None
+        if src is not None:
+            self._mean, self._cov = src.sites()
+            self._nat2 = 1.0 / self._cov
+            self._nat1 = self._mean * self._nat2
+
+    def _get(name):  # noqa: N805 -- property factory
+        def getter(self):
+            self._sync()
+            return getattr(self, name)
+
+        def setter(self, value):
+            self._sync()
+            setattr(self, name, value)
+        return property(getter, setter)
+
+    mean_, covariance_, nat1_, nat2_ = _get('_mean'), _get('_cov'), _get('_nat1'), _get('_nat2')
+    mean, covariance, nat1, nat2 = mean_, covariance_, nat1_, nat2_
+    del _get
 
     @staticmethod
     def reparametrise(param1, param2):
@@ -51,8 +73,9 @@ class GaussianDistribution:
 
     def update_mean_cov(self, mean, covariance):
         self.version += 1
-        self.mean_, self.covariance_ = as_dev(mean), as_dev(covariance)
-        self.nat1_, self.nat2_ = self.reparametrise(self.mean_, self.covariance_)
+        self.source = None
+        self._mean, self._cov = as_dev(mean), as_dev(covariance)
+        self._nat1, self._nat2 = self.reparametrise(self._mean, self._cov)
 
 
 class MarkovGaussianProcess:
@@ -116,6 +139,51 @@ class MarkovGaussianProcess:
 
     def compute_full_pseudo_lik(self):
         return self.pseudo_likelihood.mean, self.pseudo_likelihood.covariance
+
+    # ---- fused iteration on tiled resident state (fused.py; csrc/iter_impl.cuh)
+    def _fused_ok(self):
+        """the whole iteration can run as two fused passes: scan form, one in-library Matern component, a single-latent
+        likelihood of the site kernels, VI or Newton, and none of the hooks overridden (spatio-temporal mixins)"""
+        if os.environ.get('BN_B200_FUSED', '1') == '0' or not self.parallel or self.func_dim != 1:
+            return False
+        if type(self).update_posterior is not MarkovGaussianProcess.update_posterior:
+            return False
+        spec = self.kernel.spec() if hasattr(self.kernel, 'spec') else None
+        return fused.supported(spec, self.likelihood, self.method)
+
+    def _fused_state(self):
+        """the FusedShard of this model, holding the current sites"""
+        st = getattr(self, '_fused', None)
+        pl = self.pseudo_likelihood
+        if st is None:
+            st = self._fused = fused.FusedShard(self.kernel, self.dt, self.Y, self.mask_pseudo_y)
+            st.sites_version = None
+        if pl.source is not st or st.sites_version != pl.version:
+            st.load_sites(pl.mean, pl.covariance)
+            st.sites_version = pl.version
+        return st
+
+    def load_inputs(self, dt, Y):
+        """replace the step lengths and observations (device or pinned-host tensors of the model's length, already in
+        time order; Y may hold uint8 / bool labels) -- the streaming entry the end-to-end benchmark drives"""
+        dt = as_dev(dt).reshape(-1)
+        labels = torch.is_tensor(Y) and not Y.dtype.is_floating_point  # integer labels cannot hold a missing value
+        Y = as_dev(Y).reshape(-1, 1)
+        if dt.shape[0] != self.num_data or Y.shape[0] != self.num_data:
+            raise ValueError('load_inputs needs %d steps' % self.num_data)
+        self.dt, self.Y = dt, Y
+        self.dt_smoother = torch.cat([dt[1:], torch.zeros(1, dtype=dt.dtype, device=dt.device)])
+        nan = None if labels else torch.isnan(Y)
+        self.mask_pseudo_y = nan.to(torch.uint8).reshape(-1, 1, 1).contiguous() if (nan is not None and bool(nan.any())) else None
+        self._ell_cache = self._grad_cache = self._energy_cache = None
+        st = getattr(self, '_fused', None)
+        if st is not None:
+            st.set_dt(dt)
+            st.set_data(Y, self.mask_pseudo_y, scan_nan=not labels)
+
+    def _energy_key(self, cubature):
+        return (self.pseudo_likelihood.version, self._hyper_key(), float(self.likelihood.lik_param),
+                fused.cubature_key(cubature), self.method)
 
     def _hyper_key(self):
         spec = self.kernel.spec() if hasattr(self.kernel, 'spec') else None
@@ -181,6 +249,9 @@ class MarkovGaussianProcess:
         VI / Newton models; None when the model has more than one latent"""
         if self.func_dim != 1 or self.method not in (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON):
             return None
+        cache = getattr(self, '_energy_cache', None)
+        if cache is not None and cache[2] == self._energy_key(cubature):  # the closing pass of the fused inference()
+            return cache[0], cache[1]
         a, keep = self._site_args(cubature)
         pl = self.pseudo_likelihood
         a.site_mean, a.site_cov = pl.mean.data_ptr(), pl.covariance.data_ptr()

@@ -1,0 +1,182 @@
+// C ABI of the fused inference iteration on chunk-tiled state (include/bn_b200.h: bn_iter_*).
+// Kernels: iter_impl.cuh, instantiated per Matern family in iter_m12.cu .. iter_m72.cu.
+#include "iter_impl.cuh"
+
+namespace bn {
+int it_group_m12(const ItCall&);
+int it_group_m32(const ItCall&);
+int it_group_m52(const ItCall&);
+int it_group_m72(const ItCall&);
+bool probit_table_enabled();
+
+static int it_dispatch(const ItCall& c) {
+    int r;
+    if ((r = it_group_m12(c)) != kNotHandled) return r;
+    if ((r = it_group_m32(c)) != kNotHandled) return r;
+    if ((r = it_group_m52(c)) != kNotHandled) return r;
+    if ((r = it_group_m72(c)) != kNotHandled) return r;
+    set_error("the fused iteration supports one Matern component, got family %d with %d components", c.spec->family,
+              c.spec->n_components);
+    return -1;
+}
+
+static int it_check_spec(const bn_kernel_spec* k, int64_t N) {
+    BN_REQUIRE(k != nullptr, "kernel spec is null");
+    BN_REQUIRE(k->n_components == 1 && family_dim(k->family) > 0,
+               "the fused iteration supports one Matern component, got family %d with %d components", k->family, k->n_components);
+    BN_REQUIRE(N > 0, "N must be positive");
+    return 0;
+}
+
+static size_t it_ws_bytes(const bn_kernel_spec* k, int64_t N) {
+    switch (family_dim(k->family)) {
+        case 1: return (it_ws_doubles<1>(N) + 64) * sizeof(double);
+        case 2: return (it_ws_doubles<2>(N) + 64) * sizeof(double);
+        case 3: return (it_ws_doubles<3>(N) + 64) * sizeof(double);
+        case 4: return (it_ws_doubles<4>(N) + 64) * sizeof(double);
+    }
+    return 0;
+}
+
+// fills an ItCall from the public argument block; the 1-D rule goes by value into `cub`
+static int it_make_call(const bn_kernel_spec* k, const bn_iter_args* a, int mode, int phase, Cub1& cub, ItCall& c) {
+    BN_REQUIRE(a != nullptr, "iteration args are null");
+    if (int rc = it_check_spec(k, a->N)) return rc;
+    BN_REQUIRE(a->rank >= 0 && a->rank < a->world, "rank %d outside world %d", a->rank, a->world);
+    BN_REQUIRE(mode == BN_ITER_PLAIN || mode == BN_ITER_SITES || mode == BN_ITER_ENERGY, "unknown mode %d", mode);
+    BN_REQUIRE(a->dt_t != nullptr, "dt_t is null");
+    const bool front = (phase == UP_ALL || phase == UP_REDUCE || phase == UP_FILTER);
+    const bool back = (phase == UP_ALL || phase == UP_SMOOTH);
+    if (front || (back && mode != BN_ITER_PLAIN)) BN_REQUIRE(a->site_mean_t && a->site_cov_t, "tiled site arrays are null");
+    if (back && mode != BN_ITER_SITES) BN_REQUIRE(a->post_mean_t && a->post_cov_t, "tiled posterior arrays are null");
+    c = ItCall{};
+    c.spec = k;
+    c.io = ItIO{a->N, a->dt_t, a->y_t, a->site_mean_t, a->site_cov_t, a->mask_t, a->post_mean_t, a->post_cov_t};
+    c.mode = mode;
+    c.method = a->method;
+    c.likelihood = a->likelihood;
+    c.use_table = probit_table_enabled() ? 1 : 0;
+    c.sa = ItSiteArgs{a->lik_param, a->lr, a->power, a->ensure_psd, 0, nullptr, nullptr};
+    c.cub = &cub;
+    c.phase = phase;
+    c.rank = a->rank;
+    c.world = a->world;
+    if (back && mode != BN_ITER_PLAIN) {
+        BN_REQUIRE(a->y_t != nullptr, "y_t is null");
+        BN_REQUIRE(a->method == BN_METHOD_VI || a->method == BN_METHOD_NEWTON, "the fused epilogues cover VI and Newton, got method %d", a->method);
+        const bool closed = a->method == BN_METHOD_NEWTON ||
+                            (a->method == BN_METHOD_VI && (a->likelihood == BN_LIK_GAUSSIAN || a->likelihood == BN_LIK_POISSON_EXP));
+        if (!closed) BN_REQUIRE(a->Q > 0 && a->Q <= kMaxQ1 && a->cub_x_host && a->cub_w_host, "cubature rule missing or larger than %d points", kMaxQ1);
+        if (a->likelihood == BN_LIK_GAUSSIAN || a->likelihood == BN_LIK_POISSON_EXP) BN_REQUIRE(a->lik_param > 0.0, "likelihood parameter must be positive");
+        const bool has = a->Q > 0 && a->Q <= kMaxQ1 && a->cub_x_host && a->cub_w_host;
+        make_cub1(has ? a->Q : 0, has ? a->cub_x_host : nullptr, has ? a->cub_w_host : nullptr, cub);
+    } else {
+        make_cub1(0, nullptr, nullptr, cub);
+    }
+    return 0;
+}
+
+template <typename T>
+static int it_transpose(const bn_kernel_spec* k, int64_t N, const T* in, T* out, T fill, bool to_tiled, cudaStream_t st) {
+    if (int rc = it_check_spec(k, N)) return rc;
+    BN_REQUIRE(in && out, "null array");
+    const ChunkPlan cp = up_plan_chunks(N, false);
+    const long long tiles = (cp.nchunks + 31) / 32;
+    dim3 grid((unsigned)tiles, (unsigned)((cp.L + 31) / 32));
+    if (to_tiled) {
+        BN_LAUNCH("it_to_tiled", st, (it_transpose_kernel<T, true><<<grid, 256, 0, st>>>(N, cp.L, cp.nchunks, in, out, fill)));
+        const long long body = tiles * 32LL * cp.L, total = tl_len(cp.nchunks, cp.L);
+        it_fill_pad_kernel<T><<<(unsigned)((total - body + 255) / 256), 256, 0, st>>>(out, body, total, fill);
+    } else {
+        BN_LAUNCH("it_from_tiled", st, (it_transpose_kernel<T, false><<<grid, 256, 0, st>>>(N, cp.L, cp.nchunks, in, out, fill)));
+    }
+    BN_CUDA(cudaGetLastError());
+    return 0;
+}
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N) {
+    if (it_check_spec(k, N)) return -1;
+    return up_plan_chunks(N, false).L;
+}
+
+extern "C" int64_t bn_iter_tiled_len(const bn_kernel_spec* k, int64_t N) {
+    if (it_check_spec(k, N)) return -1;
+    const ChunkPlan cp = up_plan_chunks(N, false);
+    return tl_len(cp.nchunks, cp.L);
+}
+
+extern "C" size_t bn_iter_workspace_bytes(const bn_kernel_spec* k, int64_t N) {
+    if (it_check_spec(k, N)) return 0;
+    return it_ws_bytes(k, N);
+}
+
+extern "C" int bn_iter_to_tiled(const bn_kernel_spec* k, int64_t N, const double* x, double* x_t, double fill, void* stream) {
+    return it_transpose<double>(k, N, x, x_t, fill, true, (cudaStream_t)stream);
+}
+
+extern "C" int bn_iter_from_tiled(const bn_kernel_spec* k, int64_t N, const double* x_t, double* x, void* stream) {
+    return it_transpose<double>(k, N, x_t, x, 0.0, false, (cudaStream_t)stream);
+}
+
+extern "C" int bn_iter_to_tiled_u8(const bn_kernel_spec* k, int64_t N, const uint8_t* x, uint8_t* x_t, void* stream) {
+    return it_transpose<unsigned char>(k, N, x, x_t, (unsigned char)0, true, (cudaStream_t)stream);
+}
+
+extern "C" int bn_iter_pass(const bn_kernel_spec* k, const bn_iter_args* a, int mode, double* ell, double* sums,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    Cub1 cub;
+    ItCall c;
+    if (int rc = it_make_call(k, a, mode, UP_ALL, cub, c)) return rc;
+    BN_REQUIRE(a->world == 1 && a->rank == 0, "bn_iter_pass runs one shard; use the bn_iter_shard_* phases for world %d", a->world);
+    c.ell = ell;
+    c.sums = sums;
+    c.ws = workspace;
+    c.ws_bytes = workspace_bytes;
+    c.st = (cudaStream_t)stream;
+    return it_dispatch(c);
+}
+
+extern "C" int bn_iter_shard_reduce(const bn_kernel_spec* k, const bn_iter_args* a, double* kf_carry, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    Cub1 cub;
+    ItCall c;
+    if (int rc = it_make_call(k, a, BN_ITER_PLAIN, UP_REDUCE, cub, c)) return rc;
+    BN_REQUIRE(kf_carry != nullptr, "carry output is null");
+    c.carry_out = kf_carry;
+    c.ws = workspace;
+    c.ws_bytes = workspace_bytes;
+    c.st = (cudaStream_t)stream;
+    return it_dispatch(c);
+}
+
+extern "C" int bn_iter_shard_filter(const bn_kernel_spec* k, const bn_iter_args* a, const double* kf_carries, double* ell,
+                                    double* rts_carry, void* workspace, size_t workspace_bytes, void* stream) {
+    Cub1 cub;
+    ItCall c;
+    if (int rc = it_make_call(k, a, BN_ITER_PLAIN, UP_FILTER, cub, c)) return rc;
+    BN_REQUIRE(kf_carries && rts_carry, "null carry array");
+    c.carries = kf_carries;
+    c.carry_out = rts_carry;
+    c.ell = ell;
+    c.ws = workspace;
+    c.ws_bytes = workspace_bytes;
+    c.st = (cudaStream_t)stream;
+    return it_dispatch(c);
+}
+
+extern "C" int bn_iter_shard_smooth(const bn_kernel_spec* k, const bn_iter_args* a, int mode, const double* rts_carries,
+                                    double* sums, void* workspace, size_t workspace_bytes, void* stream) {
+    Cub1 cub;
+    ItCall c;
+    if (int rc = it_make_call(k, a, mode, UP_SMOOTH, cub, c)) return rc;
+    BN_REQUIRE(rts_carries != nullptr, "null carry array");
+    c.carries = rts_carries;
+    c.sums = sums;
+    c.ws = workspace;
+    c.ws_bytes = workspace_bytes;
+    c.st = (cudaStream_t)stream;
+    return it_dispatch(c);
+}

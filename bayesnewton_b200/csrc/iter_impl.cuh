@@ -1,0 +1,508 @@
+// Fused inference iteration on chunk-tiled resident state (single latent, one site per step).
+//
+// One iteration of a temporal Markov GP (inference.py:65-90 followed by energy(), inference.py:197-222) is
+//     update_posterior (F, S)  ->  site update (U)  ->  update_posterior (F, S)  ->  energy terms (V, X)
+// and every array that only travels between those stages (dt, the observations, the sites, the filtered states, the
+// posterior marginals) is private to the path.  Here they live in ONE layout, chosen for the thread that consumes
+// them: a step series x[0..N) is cut into the chunks of the temporally parallel filter (one thread per chunk of L
+// steps, 32 consecutive chunks per warp) and stored
+//     x_t[((c >> 5) * L + j) * 32 + (c & 31)]        (chunk c, step j of the chunk)
+// so the lane that owns chunk c reads / writes step j of all 32 chunks of its warp as ONE 256-byte transaction: no
+// shared-memory staging, no transposition, no index arithmetic beyond a pointer bump.  The two smoother sweeps then
+// run the per-step site work in their epilogue, on the smoothed marginal that is still in registers:
+//     sweep 1 (+ BN_ITER_SITES):  variational_expectation / log_likelihood_gradients, ensure_psd, newton_update, damping,
+//                                 reparametrise (inference.py:72-86, 105-128, 170-195) -> new sites, in place
+//     sweep 2 (+ BN_ITER_ENERGY): E_q[log p(y|f)] and E_q[log N(pseudo_y | f, pseudo_var)] (inference.py:208-218,
+//                                 utils.py:510-531) summed per chunk, posterior marginals written once
+// so (H sm, H sP H^T) never round-trip through HBM before the cubature, and the shared-memory-bound table gathers of
+// the probit cubature overlap the fp64-bound RTS recursion of the other warps on the same SM.
+// HBM traffic per step of an iteration (d = 3): 2 x (24 reduce + 24 + 72 filter + 72 + 8 smoother) + 16 + 16 (U: y, old
+// sites in; sites out) + 8 + 16 + 16 (V, X in; marginals out) = 472 B against 636 B on the reference-interface layouts.
+#pragma once
+#include "up_impl.cuh"
+#include "sites_impl.cuh"
+
+namespace bn {
+
+// ------------------------------------------------------------------------------------------ tiled layout
+constexpr int kTlPadRows = 2;  // rows past the last step a prefetch may touch
+BN_DEV long long tl_base(long long c, int L) { return (((c >> 5) * (long long)L) << 5) + (c & 31); }
+inline long long tl_len(long long nchunks, int L) { return ((nchunks + 31) / 32) * 32LL * L + 32LL * kTlPadRows; }
+
+struct ItIO {
+    long long N;
+    const double* dt;           // tiled
+    const double* y;            // tiled observations (the data; site pass / energy pass only)
+    double* sy;                 // tiled pseudo observations (site means)
+    double* sR;                 // tiled pseudo variances (site covariances)
+    const unsigned char* mask;  // tiled, 1 = the pseudo observation of this step is missing; nullable
+    double* pm;                 // tiled posterior marginal means (plain / energy pass)
+    double* pc;                 // tiled posterior marginal variances
+};
+
+// ------------------------------------------------------------------------------------------ chunk bodies
+// phase 1: fold the chunk's steps into one filtering element (ops.py:183-219)
+template <class G>
+BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, double* agg, long long c) {
+    static_assert(G::D == 1, "the tiled path carries one site per step");
+    using Alg = FilterAlg<G::d>;
+    typename Alg::Elem el;
+    Alg::identity(el);
+    const long long k0 = c * L, rem = io.N - k0;
+    const int cnt = rem < L ? (int)rem : L;
+    const long long b = tl_base(c, L);
+    const double* pdt = io.dt + b;
+    const double* py = io.sy + b;
+    const double* pR = io.sR + b;
+    double Abn[G::kBlockA];
+    g.trans(pdt[0], Abn);
+    double yn = py[0], Rn = pR[0], hn = pdt[32];
+#pragma unroll 1
+    for (int j = 0; j < cnt; ++j) {
+        double y[1] = {yn}, R[1] = {Rn}, Ab[G::kBlockA];
+#pragma unroll
+        for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
+        const double h1 = hn;
+        // the next step's inputs are in flight while this step's dependent chain runs (rows past the chunk are padding)
+        py += 32; pR += 32; pdt += 32;
+        yn = py[0]; Rn = pR[0]; hn = pdt[32];
+        g.trans(h1, Abn);
+        fkf_absorb<G>(g, el, Ab, y, R, is_first && k0 + j == 0);
+    }
+    Alg::store(agg, nchunks, c, el);
+}
+
+// phase 3: plain filter from the chunk's incoming state; filtered states -> scratch, log-likelihood partial
+template <class G, bool WANT_ELL>
+BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, const double* prefix,
+                            const double* s0, double* fs, double* ell_partials, long long c) {
+    constexpr int d = G::d;
+    using Alg = FilterAlg<d>;
+    typename Alg::State s;
+    Alg::load_state(s0, 1, 0, s);
+    if (c > 0) {
+        typename Alg::Elem e;
+        Alg::load(prefix, nchunks, c - 1, e);
+        typename Alg::State t;
+        Alg::apply(e, s, t);
+        s = t;
+    } else if (is_first) {  // global step 0 starts from the stationary prior (m0 = 0, P0 = Pinf)
+        Alg::zero_state(s);
+        g.pinf_full(s.P);
+    }
+    double ell = 0.0;
+    const long long k0 = c * L, rem = io.N - k0;
+    const int cnt = rem < L ? (int)rem : L;
+    const long long b = tl_base(c, L);
+    const double* pdt = io.dt + b;
+    const double* py = io.sy + b;
+    const double* pR = io.sR + b;
+    const unsigned char* pk = io.mask ? io.mask + b : nullptr;
+    double* pf = fs + fs_index(c, L, 0, 0, d + symn(d));
+    double Abn[G::kBlockA];
+    g.trans(pdt[0], Abn);
+    double yn = py[0], Rn = pR[0], hn = pdt[32];
+#pragma unroll 1
+    for (int j = 0; j < cnt; ++j) {
+        double y[1] = {yn}, R[1] = {Rn}, Ab[G::kBlockA], mp[d], Pp[symn(d)];
+        unsigned char mk[1] = {0};
+        if (pk) mk[0] = pk[(long long)j * 32];
+#pragma unroll
+        for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
+        const double h1 = hn;
+        py += 32; pR += 32; pdt += 32;
+        yn = py[0]; Rn = pR[0]; hn = pdt[32];
+        g.trans(h1, Abn);
+        ell += fkf_step<G, WANT_ELL>(g, s.m, s.P, Ab, y, R, pk ? mk : nullptr, mp, Pp);
+#pragma unroll
+        for (int f = 0; f < d; ++f) pf[f * 32] = s.m[f];
+#pragma unroll
+        for (int f = 0; f < symn(d); ++f) pf[(d + f) * 32] = s.P[f];
+        pf += (d + symn(d)) * 32;
+    }
+    if (WANT_ELL) ell_partials[c] = ell;
+}
+
+// RTS recursion down the chunk (ops.py:290-301); the epilogue takes the smoothed marginal of every step
+template <class G, class Epi>
+BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks, const double* sprefix,
+                            const double* sinit, const double* fs, long long c, Epi& epi) {
+    constexpr int d = G::d, nf = d + symn(d);
+    using Alg = SmootherAlg<d>;
+    typename Alg::State s;
+    const long long p = nchunks - 1 - c;
+    Alg::load_state(sinit, 1, 0, s);
+    if (p > 0) {
+        typename Alg::Elem e;
+        Alg::load(sprefix, nchunks, p - 1, e);
+        typename Alg::State t;
+        Alg::apply(e, s, t);
+        s = t;
+    }
+    const long long k0 = c * L, rem = io.N - k0;
+    const int j_last = (rem < L ? (int)rem : L) - 1;  // s is the smoothed state of this step
+    const long long b = tl_base(c, L);
+    const double* pdt = io.dt + b + (long long)j_last * 32;
+    const double* pf = fs + fs_index(c, L, j_last, 0, nf);
+    long long ti = b + (long long)j_last * 32;
+    double nfm[d], nfP[symn(d)];              // filtered state of the next step to process, loaded one step ahead
+    double Abn[G::kBlockA], Qbn[G::kBlockS];  // discretisation of the next step to process, formed one step ahead
+#pragma unroll
+    for (int i = 0; i < G::kBlockA; ++i) Abn[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < G::kBlockS; ++i) Qbn[i] = 0.0;
+    double hn = pdt[0];
+    if (j_last >= 1) {
+#pragma unroll
+        for (int f = 0; f < d; ++f) nfm[f] = pf[(f - nf) * 32];
+#pragma unroll
+        for (int f = 0; f < symn(d); ++f) nfP[f] = pf[(d + f - nf) * 32];
+    }
+#pragma unroll 1
+    for (int j = j_last; j >= 0; --j) {
+        double Ab[G::kBlockA], Qb[G::kBlockS];
+#pragma unroll
+        for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
+#pragma unroll
+        for (int i = 0; i < G::kBlockS; ++i) Qb[i] = Qbn[i];
+        const double h_k = hn;
+        pdt -= 32;
+        if (j >= 1) hn = pdt[0];
+        epi.prefetch(ti);
+        // the discretisation of the step below (k-1 -> k, length h_k) is formed while this step's dependent chain runs
+        g.trans(h_k, Abn);
+        g.noise(Abn, Qbn);
+        if (j < j_last) {
+            double fm[d], fP[symn(d)];
+#pragma unroll
+            for (int i = 0; i < d; ++i) fm[i] = nfm[i];
+#pragma unroll
+            for (int i = 0; i < symn(d); ++i) fP[i] = nfP[i];
+            pf -= nf * 32;
+            if (j >= 1) {  // in flight during this step's arithmetic
+#pragma unroll
+                for (int f = 0; f < d; ++f) nfm[f] = pf[(f - nf) * 32];
+#pragma unroll
+                for (int f = 0; f < symn(d); ++f) nfP[f] = pf[(d + f - nf) * 32];
+            }
+            frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
+        }
+        epi.step(ti, s.m[G::sel(0)], s.P[sidx(G::sel(0), G::sel(0))]);
+        ti -= 32;
+    }
+    epi.finish(c);
+}
+
+// ------------------------------------------------------------------------------------------ smoother epilogues
+// plain: the posterior marginals, tiled
+struct EpiStore {
+    double* pm;
+    double* pc;
+    BN_DEV void prefetch(long long) {}
+    BN_DEV void step(long long ti, double m, double v) {
+        pm[ti] = m;
+        pc[ti] = v;
+    }
+    BN_DEV void finish(long long) {}
+};
+
+// what the site epilogues need besides the tiled arrays (kernel parameter)
+struct ItSiteArgs {
+    double lik_param, lr, power;
+    int ensure_psd, pad_;
+    double* part1;  // [nchunks] per-chunk partial sums: SITES |delta nat1|, ENERGY the likelihood term
+    double* part2;  // [nchunks]                         SITES |delta nat2|, ENERGY E_q[log N(pseudo_y | f, pseudo_var)]
+};
+
+// site update on the smoothed marginal (the body of inference.py:72-86 for one step); sites rewritten in place
+template <int LIK, int METHOD, bool TAB>
+struct EpiSites {
+    ItIO io;
+    ItSiteArgs a;
+    Lik1<LIK, TAB> lik;
+    const Cub1* cub;
+    double d1, d2, yq, oy, oR;
+    BN_DEV EpiSites(const ItIO& io_, const ItSiteArgs& a_, const Cub1* cub_, const double* tab)
+        : io(io_), a(a_), lik{a_.lik_param, tab}, cub(cub_), d1(0.0), d2(0.0), yq(0.0), oy(0.0), oR(1.0) {}
+    BN_DEV void prefetch(long long ti) {
+        yq = io.y[ti];
+        oy = io.sy[ti];
+        oR = io.sR[ti];
+    }
+    BN_DEV void step(long long ti, double m, double v) {
+        // natural parameters of the site as reparametrise leaves them (basemodels.py:85-100): nat2 = 1 / cov, nat1 = nat2 mean
+        const double o2 = 1.0 / oR, o1 = oy * o2;
+        SiteStats1 s;
+        double h, r1, r2, e1, e2;
+        site_update_scalar<LIK, METHOD, TAB>(lik, *cub, yq, m, v, o1, o2, a.lr, a.power, a.ensure_psd, s, h, r1, r2, e1, e2);
+        d1 += e1;
+        d2 += e2;
+        const double Lc = sqrt(r2);
+        io.sy[ti] = (r1 / Lc) / Lc;
+        io.sR[ti] = (1.0 / Lc) / Lc;
+    }
+    BN_DEV void finish(long long c) {
+        a.part1[c] = d1;
+        a.part2[c] = d2;
+    }
+};
+
+// energy terms on the smoothed marginal + the marginals themselves
+template <int LIK, int METHOD, bool TAB>
+struct EpiEnergy {
+    ItIO io;
+    ItSiteArgs a;
+    Lik1<LIK, TAB> lik;
+    const Cub1* cub;
+    double accV, accX, yq, oy, oR;
+    unsigned char mk;
+    BN_DEV EpiEnergy(const ItIO& io_, const ItSiteArgs& a_, const Cub1* cub_, const double* tab)
+        : io(io_), a(a_), lik{a_.lik_param, tab}, cub(cub_), accV(0.0), accX(0.0), yq(0.0), oy(0.0), oR(1.0), mk(0) {}
+    BN_DEV void prefetch(long long ti) {
+        yq = io.y[ti];
+        oy = io.sy[ti];
+        oR = io.sR[ti];
+        if (io.mask) mk = io.mask[ti];
+    }
+    BN_DEV void step(long long ti, double m, double v) {
+        io.pm[ti] = m;
+        io.pc[ti] = v;
+        const SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB>(lik, yq, m, v, 0.0, 0.0, a.power, *cub);
+        if (!isnan(s.val)) accV += s.val;  // nansum (inference.py:218)
+        accX += gaussian_ell_step<1>(&oy, &m, &v, &oR, io.mask ? &mk : nullptr, 0);
+    }
+    BN_DEV void finish(long long c) {
+        a.part1[c] = accV;
+        a.part2[c] = accX;
+    }
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------ kernels
+constexpr int kItTabThreads = 512;  // the table-gathering sweeps own a whole SM: one CTA, 16 warps, the table in shared memory
+
+template <class G>
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, double* agg) {
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    if (c < nchunks) it_reduce_chunk(g, io, L, nchunks, is_first, agg, c);
+}
+
+template <class G, bool WANT_ELL>
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const double* prefix, const double* s0, double* fs,
+                 double* ell_partials) {
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    if (c < nchunks) it_filter_chunk<G, WANT_ELL>(g, io, L, nchunks, is_first, prefix, s0, fs, ell_partials, c);
+}
+
+template <class G>
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const double* sprefix, const double* sinit, const double* fs) {
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    if (c >= nchunks) return;
+    EpiStore epi{io.pm, io.pc};
+    it_smooth_chunk(g, io, L, nchunks, sprefix, sinit, fs, c, epi);
+}
+
+// the probit log-density table in device memory (sites.cu fills it once per device and hands out its address)
+int probit_table_device(cudaStream_t st, const double** tab);
+
+template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
+__global__ void __launch_bounds__(TAB ? kItTabThreads : kUpThreads, TAB ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
+it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs a, int L, long long nchunks,
+                      const double* sprefix, const double* sinit, const double* fs, const double* gtab) {
+    extern __shared__ double it_smem[];
+    const double* tab = nullptr;
+    if constexpr (TAB) {
+        for (int i = threadIdx.x; i < kPtDoubles; i += kItTabThreads) it_smem[i] = gtab[i];
+        __syncthreads();
+        tab = it_smem;
+    }
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    Epi<LIK, METHOD, TAB> epi(io, a, &cub, tab);
+    it_smooth_chunk(g, io, L, nchunks, sprefix, sinit, fs, c, epi);
+}
+
+// linear [N] <-> tiled, 32 chunks x 32 steps per CTA through a padded shared-memory tile (both sides coalesced)
+template <typename T, bool TO_TILED>
+__global__ void __launch_bounds__(256) it_transpose_kernel(long long N, int L, long long nchunks, const T* in, T* out, T fill) {
+    __shared__ T sm[32][33];
+    const long long tile = blockIdx.x;
+    const int j0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if constexpr (TO_TILED) {
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {  // r: chunk of the tile, tx: step
+            const long long c = tile * 32 + r, k = c * L + j0 + tx;
+            sm[r][tx] = (j0 + tx < L && c < nchunks && k < N) ? in[k] : fill;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = ty; r < 32; r += 8)  // r: step, tx: chunk
+            if (j0 + r < L) out[((tile * L + j0 + r) << 5) + tx] = sm[tx][r];
+    } else {
+#pragma unroll
+        for (int r = ty; r < 32; r += 8)
+            if (j0 + r < L) sm[r][tx] = in[((tile * L + j0 + r) << 5) + tx];
+        __syncthreads();
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const long long c = tile * 32 + r, k = c * L + j0 + tx;
+            if (j0 + tx < L && c < nchunks && k < N) out[k] = sm[tx][r];
+        }
+    }
+}
+
+template <typename T>
+__global__ void it_fill_pad_kernel(T* x, long long from, long long n, T fill) {
+    const long long i = from + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = fill;
+}
+
+// ------------------------------------------------------------------------------------------ host driver
+enum { IT_PLAIN = 0, IT_SITES = 1, IT_ENERGY = 2 };
+
+struct ItCall {
+    const bn_kernel_spec* spec;
+    ItIO io;
+    int mode;                 // smoother epilogue
+    int method, likelihood, use_table;
+    ItSiteArgs sa;            // part1 / part2 are set by the driver
+    const Cub1* cub;
+    double* ell;              // nullable
+    double* sums;             // [2], SITES: sum |delta nat1|, sum |delta nat2|; ENERGY: likelihood term, pseudo term
+    void* ws;
+    size_t ws_bytes;
+    cudaStream_t st;
+    int phase, rank, world;
+    double* carry_out;
+    const double* carries;
+};
+
+template <int d>
+inline size_t it_ws_doubles(long long N) { return up_ws_doubles<d>(N) + 2 * (size_t)up_plan_chunks(N > 0 ? N : 1).nchunks + 64; }
+
+// fused (likelihood, method) pairs of the site / energy epilogues
+#define BN_FOR_EACH_ITER_SITE(X)                                                       \
+    X(BN_LIK_GAUSSIAN, BN_METHOD_VI) X(BN_LIK_GAUSSIAN, BN_METHOD_NEWTON)               \
+    X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_VI) X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_NEWTON) \
+    X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_VI) X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_NEWTON) \
+    X(BN_LIK_POISSON_EXP, BN_METHOD_VI) X(BN_LIK_POISSON_EXP, BN_METHOD_NEWTON)
+
+template <class G, template <int, int, bool> class Epi>
+inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp, const UpWs& w, const ItSiteArgs& sa) {
+    cudaStream_t st = c.st;
+    const char* name = (c.mode == IT_SITES) ? "it_smooth_sites" : "it_smooth_energy";
+#define X(LK, M)                                                                                                      \
+    if (c.likelihood == LK && c.method == M) {                                                                         \
+        if constexpr (LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI) {                                            \
+            if (c.use_table) {                                                                                         \
+                auto kfn = it_smooth_site_kernel<G, Epi, LK, M, true>;                                                 \
+                const size_t smem = sizeof(double) * kPtDoubles;                                                       \
+                const double* gtab = nullptr;                                                                          \
+                if (int rc = probit_table_device(st, &gtab)) return rc;                                                \
+                BN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+                const unsigned grid = (unsigned)((cp.nchunks + kItTabThreads - 1) / kItTabThreads);                    \
+                BN_LAUNCH(name, st, (kfn<<<grid, kItTabThreads, smem, st>>>(g, c.io, *c.cub, sa, cp.L, cp.nchunks,     \
+                                                                            w.splan.prefix[0], w.sinit, w.fs, gtab))); \
+                BN_CUDA(cudaGetLastError());                                                                           \
+                return 0;                                                                                              \
+            }                                                                                                          \
+        }                                                                                                              \
+        const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);                                  \
+        BN_LAUNCH(name, st, (it_smooth_site_kernel<G, Epi, LK, M, false><<<grid, kUpThreads, 0, st>>>(                 \
+                                g, c.io, *c.cub, sa, cp.L, cp.nchunks, w.splan.prefix[0], w.sinit, w.fs, nullptr)));   \
+        BN_CUDA(cudaGetLastError());                                                                                   \
+        return 0;                                                                                                      \
+    }
+    BN_FOR_EACH_ITER_SITE(X)
+#undef X
+    set_error("the fused iteration has no epilogue for (likelihood, method) = (%d, %d)", c.likelihood, c.method);
+    return -1;
+}
+
+template <class G>
+inline int it_run(const ItCall& c) {
+    constexpr int d = G::d;
+    using FA = FilterAlg<d>;
+    using SA = SmootherAlg<d>;
+    cudaStream_t st = c.st;
+    const ItIO& io = c.io;
+    G g;
+    g.prepare(*c.spec);
+    ChunkPlan cp = up_plan_chunks(io.N, false);
+    const size_t need = it_ws_doubles<d>(io.N) * sizeof(double);
+    BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
+    UpWs w = up_ws<d>(c.ws, cp);
+    double* part = (double*)c.ws + up_ws_doubles<d>(io.N);
+    const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
+    const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
+    const bool sharded = c.phase != UP_ALL;
+
+    if (c.phase == UP_ALL || c.phase == UP_REDUCE) {
+        BN_LAUNCH("it_reduce", st, (it_reduce_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks, is_first, w.fplan.input0)));
+        BN_CUDA(cudaGetLastError());
+        BN_CUDA(run_scan<FA>(w.fplan, st));
+        if (c.carry_out && c.phase == UP_REDUCE) {
+            const int top = w.fplan.levels - 1;
+            export_carry_kernel<FA><<<1, 1, 0, st>>>(w.fplan.prefix[top], w.fplan.count[top], c.carry_out);
+            BN_CUDA(cudaGetLastError());
+        }
+    }
+    if (c.phase == UP_ALL || c.phase == UP_FILTER) {
+        if (sharded) {
+            fold_carries_kernel<FA><<<1, 1, 0, st>>>(c.carries, 0, c.rank, 1, w.s0);
+            BN_CUDA(cudaGetLastError());
+        } else {
+            BN_CUDA(cudaMemsetAsync(w.s0, 0, FA::kState * sizeof(double), st));
+        }
+        if (c.ell) {
+            BN_LAUNCH("it_filter", st, (it_filter_kernel<G, true><<<grid, kUpThreads, 0, st>>>(
+                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, w.partials)));
+            BN_CUDA(cudaGetLastError());
+            BN_LAUNCH("sum", st, (sum_kernel<false><<<1, 1024, 0, st>>>(w.partials, cp.nchunks, c.ell, 1.0)));
+        } else {
+            BN_LAUNCH("it_filter", st, (it_filter_kernel<G, false><<<grid, kUpThreads, 0, st>>>(
+                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, nullptr)));
+        }
+        BN_CUDA(cudaGetLastError());
+        const unsigned g2 = (unsigned)((cp.nchunks + 127) / 128);
+        BN_LAUNCH("up_selem", st, (up_selem_kernel<G><<<g2, 128, 0, st>>>(io.N, cp.L, cp.nchunks, !is_first, w.fplan.input0,
+                                                                          w.s0, w.fs, w.splan.input0)));
+        BN_CUDA(cudaGetLastError());
+        BN_CUDA(run_scan<SA>(w.splan, st));
+        if (c.carry_out && c.phase == UP_FILTER) {
+            const int top = w.splan.levels - 1;
+            up_export_scarry_kernel<d><<<1, 1, 0, st>>>(w.splan.prefix[top], w.splan.count[top], is_last, io.N, cp.L, w.fs,
+                                                        c.carry_out);
+            BN_CUDA(cudaGetLastError());
+        }
+    }
+    if (c.phase == UP_ALL || c.phase == UP_SMOOTH) {
+        if (sharded && !is_last) fold_carries_kernel<SA><<<1, 1, 0, st>>>(c.carries, c.world - 1, c.rank, -1, w.sinit);
+        else up_last_state_kernel<d><<<1, 1, 0, st>>>(io.N, cp.L, w.fs, w.sinit);
+        BN_CUDA(cudaGetLastError());
+        if (c.mode == IT_PLAIN) {
+            BN_LAUNCH("it_smooth", st, (it_smooth_plain_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks,
+                                                                                               w.splan.prefix[0], w.sinit, w.fs)));
+            BN_CUDA(cudaGetLastError());
+        } else {
+            ItSiteArgs sa = c.sa;
+            sa.part1 = part;
+            sa.part2 = part + cp.nchunks;
+            int rc = (c.mode == IT_SITES) ? it_launch_site_sweep<G, EpiSites>(c, g, cp, w, sa)
+                                          : it_launch_site_sweep<G, EpiEnergy>(c, g, cp, w, sa);
+            if (rc) return rc;
+            if (c.sums) {
+                sum_kernel<false><<<1, 1024, 0, st>>>(sa.part1, cp.nchunks, c.sums, 1.0);
+                sum_kernel<false><<<1, 1024, 0, st>>>(sa.part2, cp.nchunks, c.sums + 1, 1.0);
+                BN_CUDA(cudaGetLastError());
+            }
+        }
+    }
+    return 0;
+}
+#endif  // __CUDACC__
+
+}  // namespace bn

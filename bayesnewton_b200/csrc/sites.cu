@@ -2,6 +2,7 @@
 // bn_gaussian_expected_log_lik, bn_ep_pseudo_density.  One thread per time step, coalesced
 // loads/stores of the per-step scalars, deterministic two-stage reductions for the sums.
 #include <cstdlib>
+#include <mutex>
 #include "sites_impl.cuh"
 
 namespace bn {
@@ -17,16 +18,30 @@ template <bool TAB> constexpr int kNT = TAB ? kTabThreads : kSiteThreads;
 // the probit log-density table in device memory, filled once per device (probit_table.cuh)
 __device__ double g_probit_tab[kPtDoubles];
 static bool g_probit_ready[64] = {false};
+static std::mutex g_probit_mutex;
 
-static int ensure_probit_table(cudaStream_t st) {
+// One upload per device, guarded by a mutex and SYNCHRONOUS: when this returns the table is in device memory for
+// every stream and every host thread (an async copy on the first caller's stream would race with a first use
+// on another stream).
+static int ensure_probit_table(cudaStream_t) {
     int dev = 0;
     BN_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return -1; }
+    std::lock_guard<std::mutex> lock(g_probit_mutex);
     if (!g_probit_ready[dev]) {
         const std::vector<double>& t = probit_table_host();
-        BN_CUDA(cudaMemcpyToSymbolAsync(g_probit_tab, t.data(), sizeof(double) * kPtDoubles, 0, cudaMemcpyHostToDevice, st));
+        BN_CUDA(cudaMemcpyToSymbol(g_probit_tab, t.data(), sizeof(double) * kPtDoubles, 0, cudaMemcpyHostToDevice));
         g_probit_ready[dev] = true;
     }
+    return 0;
+}
+
+// the table's device address for kernels of other translation units (iter_impl.cuh)
+int probit_table_device(cudaStream_t st, const double** tab) {
+    if (int rc = ensure_probit_table(st)) return rc;
+    void* p = nullptr;
+    BN_CUDA(cudaGetSymbolAddress(&p, g_probit_tab));
+    *tab = (const double*)p;
     return 0;
 }
 
@@ -36,7 +51,7 @@ constexpr bool kUsesTable = (LIK == BN_LIK_BERNOULLI_PROBIT) && (METHOD == BN_ME
 
 // BN_B200_PROBIT_TABLE=0 in the environment routes the probit schemes through erf()/log() instead
 // (validation aid: A/B of the tabulated log-density against libm on the device)
-static bool probit_table_enabled() {
+bool probit_table_enabled() {
     static const bool on = [] {
         const char* e = getenv("BN_B200_PROBIT_TABLE");
         return !(e && e[0] == '0');

@@ -393,6 +393,27 @@ BN_DEV SiteStats2 site_stats_2(double y, const double* m, const double* V, const
     return o;
 }
 
+// ------------------------------------------------------------------------------ scalar-latent site update on values
+// (y, posterior marginal (pm, pc), old natural parameters (o1, o2)) -> damped new natural parameters (r1, r2):
+// the likelihood statistics of the scheme, ensure_psd (utils.py:89-96), newton_update (inference.py:21-39) and the
+// damping of inference.py:83-86.  s / h receive the (mean, jacobian) and the hessian the reference returns as state;
+// d1 / d2 the absolute change of the natural parameters before damping (the `diff` terms of inference.py:78-79).
+template <int LIK, int METHOD, bool TAB>
+BN_DEV void site_update_scalar(const Lik1<LIK, TAB>& lik, const Cub1& cub, double y, double pm, double pc, double o1,
+                               double o2, double lr, double power, int ensure_psd, SiteStats1& s, double& h, double& r1,
+                               double& r2, double& d1, double& d2) {
+    s = site_stats_1<LIK, METHOD, false, TAB>(lik, y, pm, pc, o1, o2, power, cub);
+    h = s.hess;
+    if (ensure_psd && METHOD != BN_METHOD_PL) h = ensure_psd1(h);
+    const double hh = isnan(h) ? -1e-6 : h;
+    const double j = isnan(s.jac) ? hh * s.mean : s.jac;
+    const double nn1 = j - hh * s.mean, nn2 = -hh;
+    d1 = fabs(nn1 - o1);
+    d2 = fabs(nn2 - o2);
+    r1 = (1.0 - lr) * o1 + lr * nn1;
+    r2 = (1.0 - lr) * o2 + lr * nn2;
+}
+
 // ------------------------------------------------------------------------------ the fused update, one step
 // returns |delta nat1| and |delta nat2| sums of this step through d1/d2
 template <int LIK, int METHOD, bool TAB = false>
@@ -451,19 +472,13 @@ BN_DEV void site_update_step(const bn_site_args& a, const SiteCtx& sc, long long
     } else {
         Lik1<LIK, TAB> lik{a.lik_param, sc.tab};
         double o1 = a.nat1[n], o2 = a.nat2[n];
-        SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB>(lik, a.y[n], a.post_mean[n], a.post_cov[n], o1, o2, a.power, *sc.cub);
-        double h = s.hess;
-        if (a.ensure_psd && METHOD != BN_METHOD_PL) h = ensure_psd1(h);
+        SiteStats1 s;
+        double h, r1, r2;
+        site_update_scalar<LIK, METHOD, TAB>(lik, *sc.cub, a.y[n], a.post_mean[n], a.post_cov[n], o1, o2, a.lr, a.power,
+                                             a.ensure_psd, s, h, r1, r2, d1, d2);
         if (a.out_mean) a.out_mean[n] = s.mean;
         if (a.out_jac) a.out_jac[n] = s.jac;
         if (a.out_hess) a.out_hess[n] = h;
-        h = isnan(h) ? -1e-6 : h;
-        double j = isnan(s.jac) ? h * s.mean : s.jac;
-        double nn1 = j - h * s.mean, nn2 = -h;
-        d1 = fabs(nn1 - o1);
-        d2 = fabs(nn2 - o2);
-        double r1 = (1.0 - a.lr) * o1 + a.lr * nn1;
-        double r2 = (1.0 - a.lr) * o2 + a.lr * nn2;
         a.nat1[n] = r1;
         a.nat2[n] = r2;
         double L = sqrt(r2);

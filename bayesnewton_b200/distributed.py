@@ -27,7 +27,7 @@ class TimeShard:
     the chunk prefixes alive between the reduce and the apply call of a pass"""
 
     def __init__(self, kernel, dt, dt_smoother, rank, world):
-        self.spec = kernel.spec()
+        self.kernel = kernel
         if self.spec is None:
             raise NotImplementedError('time sharding needs a kernel with an in-library discretisation')
         self.rank, self.world = rank, world
@@ -41,6 +41,15 @@ class TimeShard:
         self.kf_len = _lib.lib().bn_kf_carry_len(self.d)
         self.rts_len = _lib.lib().bn_rts_carry_len(self.d)
         self._ws_up = None
+
+    @property
+    def spec(self):
+        """rebuilt from the kernel object on every use: hyper-parameters may change between iterations"""
+        return self.kernel.spec() if hasattr(self.kernel, 'spec') else None
+
+    def hyper_key(self):
+        s = self.spec
+        return (s.family, s.n_components, tuple(s.variance), tuple(s.lengthscale))
 
     # ---- fused posterior update (bn_up_shard_*): reduce -> [all-gather] -> filter -> [all-gather] -> smooth
     def _up_ws(self):
@@ -278,6 +287,7 @@ class TimeShardedMarkovGP:
         from .basemodels import GaussianDistribution
         self.kernel, self.likelihood, self.method, self.power = kernel, likelihood, method, power
         self.rank, self.world = rank, world
+        self._energy_cache = None
         dt = as_dev(dt_local).reshape(-1)
         dts = torch.cat([dt[1:], torch.full((1,), float(dt_next), dtype=dt.dtype, device=dt.device)])
         self.shard = TimeShard(kernel, dt, dts, rank, world)
@@ -299,8 +309,10 @@ class TimeShardedMarkovGP:
         pl = self.pseudo_likelihood
         out = sharded_update_posterior(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y, want_ell=True,
                                        want_grad=want_grad)
-        self._ell_cache = (out[0], pl.version)  # the local log-likelihood partial of exactly these sites
-        self._grad_cache = (out[3], pl.version) if want_grad else None
+        key = (pl.version, self.shard.hyper_key())
+        self._ell_cache = (out[0], key)  # the local log-likelihood partial of exactly these sites and hyper-parameters
+        self._grad_cache = (out[3], key) if want_grad else None
+        self._energy_cache = None
         self.posterior_mean, self.posterior_variance = out[1], out[2]
 
     def _site_args(self, cubature=None):
@@ -309,9 +321,68 @@ class TimeShardedMarkovGP:
         a.nat1, a.nat2 = self.pseudo_likelihood.nat1_.data_ptr(), self.pseudo_likelihood.nat2_.data_ptr()
         return a, keep
 
+    # ---- fused iteration on tiled resident state (fused.py): the same two passes as on one GPU, each in its three
+    # phases with the carries of all ranks exchanged in between
+    def _fused_ok(self):
+        import os
+        from . import fused
+        return (os.environ.get('BN_B200_FUSED', '1') != '0' and self.shard.D == 1
+                and fused.supported(self.shard.spec, self.likelihood, self.method))
+
+    def _fused_state(self):
+        from . import fused
+        st = getattr(self, '_fused', None)
+        pl = self.pseudo_likelihood
+        if st is None:
+            st = self._fused = fused.FusedShard(self.kernel, self.shard.dt, self.Y, self.mask_pseudo_y, self.rank, self.world)
+            st.sites_version = None
+        if pl.source is not st or st.sites_version != pl.version:
+            st.load_sites(pl.mean, pl.covariance)
+            st.sites_version = pl.version
+        return st
+
+    def load_inputs(self, dt, Y, dt_next=None):
+        """replace this shard's step lengths and observations (device or pinned-host tensors; Y may hold uint8 labels)"""
+        dt = as_dev(dt).reshape(-1)
+        labels = torch.is_tensor(Y) and not Y.dtype.is_floating_point  # integer labels cannot hold a missing value
+        self.Y = as_dev(Y).reshape(-1)
+        last = self.shard.dts[-1:] if dt_next is None else torch.full((1,), float(dt_next), dtype=dt.dtype, device=dt.device)
+        self.shard.dt, self.shard.dts = dt, torch.cat([dt[1:], last])
+        nan = None if labels else torch.isnan(self.Y)
+        self.mask_pseudo_y = nan.to(torch.uint8).contiguous() if (nan is not None and self.shard.D == 1 and bool(nan.any())) else None
+        self._ell_cache = self._grad_cache = self._energy_cache = None
+        st = getattr(self, '_fused', None)
+        if st is not None:
+            st.set_dt(dt)
+            st.set_data(self.Y, self.mask_pseudo_y, scan_nan=not labels)
+
+    def _fused_pass(self, st, mode, lr, cubature, ensure_psd, want_ell):
+        c = st.reduce()
+        carries = _all_gather(c, self.world) if self.world > 1 else c.reshape(1, -1)
+        ell, c = st.filter(carries, want_ell=want_ell)
+        carries = _all_gather(c, self.world) if self.world > 1 else c.reshape(1, -1)
+        return ell, st.smooth(mode, carries, self.likelihood, self.method, cubature, lr, self.power, ensure_psd)
+
+    def _inference_fused(self, lr, cubature, ensure_psd):
+        from . import fused
+        st = self._fused_state()
+        pl = self.pseudo_likelihood
+        _, d = self._fused_pass(st, fused.SITES, lr, cubature, ensure_psd, False)
+        pl.version += 1
+        pl.source, st.sites_version = st, pl.version
+        ell, sums = self._fused_pass(st, fused.ENERGY, lr, cubature, ensure_psd, True)
+        self.posterior_mean, self.posterior_variance = st.posterior(self.posterior_mean, self.posterior_variance)
+        key = (pl.version, self.shard.hyper_key())
+        self._ell_cache = (ell, key)
+        self._grad_cache = None
+        self._energy_cache = (sums, key + (float(self.likelihood.lik_param), fused.cubature_key(cubature)))
+        return d  # local sums of |delta nat1|, |delta nat2| (before damping)
+
     def inference(self, lr=1.0, cubature=None, ensure_psd=True, want_grad=False):
         """want_grad: the closing posterior update also accumulates d log-lik / d hyper-parameters, which
         energy_and_grad() then serves without another pass"""
+        if not want_grad and self._fused_ok():
+            return self._inference_fused(lr, cubature, ensure_psd)
         self.update_posterior()
         a, keep = self._site_args(cubature)
         a.lr, a.ensure_psd = float(lr), int(bool(ensure_psd))
@@ -329,7 +400,7 @@ class TimeShardedMarkovGP:
         kernel hyper-parameters only through StateVars)."""
         pl = self.pseudo_likelihood
         cache = getattr(self, '_grad_cache', None)
-        if cache is None or cache[1] != pl.version:
+        if cache is None or cache[1] != (pl.version, self.shard.hyper_key()):
             self.update_posterior(want_grad=True)
         g = self._grad_cache[0].clone()
         E = self.energy(cubature)
@@ -345,6 +416,16 @@ class TimeShardedMarkovGP:
         pl = self.pseudo_likelihood
         dev = self.Y.device
         parts = torch.zeros(3, dtype=torch.float64, device=dev)
+        from . import fused
+        key = (pl.version, self.shard.hyper_key())
+        ec = getattr(self, '_energy_cache', None)
+        if ec is not None and ec[1] == key + (float(self.likelihood.lik_param), fused.cubature_key(cubature)):
+            # the closing pass of the fused inference() summed both terms in its smoother epilogue
+            parts[0:2] = ec[0]
+            parts[2:3] = self._ell_cache[0]
+            if self.world > 1:
+                parts = _all_gather(parts, self.world).sum(dim=0)
+            return -(parts[0] - (parts[1] - parts[2]))
         a, keep = self._site_args(cubature)
         ws, nb = self._ws
         if a.D == 1:  # single latent: both sums in one pass over the posterior marginals
@@ -357,7 +438,7 @@ class TimeShardedMarkovGP:
                 self.N, a.D, ptr(pl.mean), ptr(self.posterior_mean), ptr(self.posterior_variance), ptr(pl.covariance),
                 ptr(self.mask_pseudo_y), None, parts[1:2].data_ptr(), ptr(ws), nb, stream_ptr()))
         cache = getattr(self, '_ell_cache', None)
-        if cache is not None and cache[1] == pl.version:  # same sites, same kernel: the filter pass of update_posterior
+        if cache is not None and cache[1] == key:  # same sites, same kernel: the filter pass of update_posterior
             parts[2:3] = cache[0]
         else:
             parts[2:3] = sharded_log_lik(self.shard, pl.mean, pl.covariance, self.mask_pseudo_y)

@@ -20,13 +20,33 @@ class InferenceMixin:
         a.nat1, a.nat2 = self.pseudo_likelihood.nat1_.data_ptr(), self.pseudo_likelihood.nat2_.data_ptr()
         return a, keep
 
-    def inference(self, lr=1., batch_ind=None, cubature=None, ensure_psd=True, return_state=True, want_grad=False,
+    def _inference_fused(self, lr, cubature, ensure_psd):
+        """the iteration as two fused passes over tiled resident state (fused.py): filter, smoother + site update;
+        filter (+ log-likelihood), smoother + the two sums energy() needs, which are kept for it"""
+        from . import fused
+        st = self._fused_state()
+        pl = self.pseudo_likelihood
+        _, d = st.run(fused.SITES, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=False)
+        pl.version += 1  # the sites were rewritten in place (in the tiled arrays: pl reads them back on access)
+        pl.source, st.sites_version = st, pl.version
+        ell, sums = st.run(fused.ENERGY, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=True)
+        self.posterior_mean, self.posterior_variance = st.posterior(self.posterior_mean, self.posterior_variance)
+        self._ell_cache = (ell, pl.version, self._hyper_key())
+        self._grad_cache = None
+        self._energy_cache = (sums[0], sums[1], self._energy_key(cubature))
+        n = float(self.num_data)
+        return (None, None, None), (d[0] / n, d[1] / n)
+
+    def inference(self, lr=1., batch_ind=None, cubature=None, ensure_psd=True, return_state=False, want_grad=False,
                   **kwargs):
-        """one iteration (inference.py:65-90).  Returns ((mean, jacobian, hessian), (diff1, diff2));
-        with return_state=False the triple is not written to HBM (the reference's jit drops it as dead code).
+        """one iteration (inference.py:65-90).  Returns ((mean, jacobian, hessian), (diff1, diff2)); the triple (the
+        line-search state of the reference) is only formed with return_state=True -- inside the reference's jitted
+        train_op it is dead code and never materialised.
         want_grad: the closing posterior update also accumulates the hyper-gradient energy_and_grad() serves."""
         if batch_ind is not None and len(batch_ind) != self.num_data:
             raise NotImplementedError('mini-batched site updates are outside the hot-path scope (SURVEY A.15)')
+        if not return_state and not want_grad and getattr(self, '_fused_ok', lambda: False)():
+            return self._inference_fused(lr, cubature, ensure_psd)
         self.update_posterior()
         a, keep = self._site_args(cubature)
         N, D = a.N, a.D

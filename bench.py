@@ -1,17 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- Markov-GP inference-iteration throughput (time-steps/s) on B200.
 
-Workload (BASELINE.json configs[1], SURVEY 8d "C2"): MarkovVariationalGP, Matern-5/2 (d = 3),
-Bernoulli-probit likelihood with 20-point Gauss-Hermite sites, N = 10^7 time steps, the temporally
-parallel (scan) filter/smoother, fp64.  One "step" = one train_op-equivalent iteration
-(SURVEY 3.1): model.inference(lr=1) [filter, smoother, site update, filter, smoother] followed by
-model.energy() [expected log-lik, filter log-lik, expected pseudo log-lik].  value = N / time.
+Default workload (BASELINE.json configs[4] / the north_star target; SURVEY 8d "C5"): MarkovVariationalGP,
+Matern-5/2 (d = 3), Bernoulli-probit likelihood with 20-point Gauss-Hermite sites, N = 10^8 time steps, the temporally
+parallel (scan) filter / smoother, fp64.  One "step" = one train_op-equivalent iteration:
+model.inference(lr=1) [filter, smoother, site update, filter, smoother] followed by model.energy() [expected
+log-lik, filter log-lik, expected pseudo log-lik].  value = N / time.
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference ...                     # CPU arm: plain-C port of the reference algorithm
+  python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path (C5; N GPUs share the SAME 10^8 steps)
+  python bench.py --workload C2 ...                          # configs[1]: the same model at N = 10^7
+  python bench.py --impl reference ...                       # CPU arm: plain-C port of the reference algorithm
 
-With N > 1 (torchrun) the time axis is sharded: every rank holds --n-local steps (weak scaling) and
-the ranks exchange the O(d^2) scan carries with NCCL all-gathers (bayesnewton_b200/distributed.py).
+With N > 1 (torchrun) the time axis of the same series is sharded over the ranks (strong scaling); the ranks exchange
+the O(d^2) scan carries over NVLink peer memory / NCCL (bayesnewton_b200/distributed.py).
 """
 import argparse
 import json
@@ -30,33 +31,51 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 METRIC = 'markov_gp_inference_iter_time_steps_per_sec'
 UNIT = 'time-steps/s'
 
-# algorithmic bytes per time step of each kernel at d = 3, D = 1, fp64 (the
-# reference-interface layouts of SURVEY 8d: full matrices, no As/Qs arrays, no gains)
-ALGO_BYTES = {
-    'up_reduce': 24,          # dt, pseudo_y, pseudo_var
-    'up_filter': 24 + 96,     # dt, pseudo_y, pseudo_var in; m[3], P[3,3] out (kept packed, 72 B, in scratch)  (= F)
-    'up_smooth': 8 + 96 + 16,  # dt', fm, fP in; H sm, H sP H^T out                                             (= S)
-    'kf_reduce': 24, 'kf_apply': 24 + 96, 'kf_apply_ell': 24, 'rts_reduce': 8 + 96, 'rts_apply': 8 + 96 + 16,
-    'site_update': 72,        # y, m, v, nat1, nat2 in; nat1, nat2, mean, cov out   (= U)
-    'expected_density': 24,   # y, m, v                                   (= V)
-    'gaussian_ell': 32,       # pseudo_y, m, v, pseudo_var                (= X)
-    'energy_terms': 24 + 33,  # y, m, v + pseudo_y, pseudo_var (+mask): V and X in one pass
+WORKLOADS = {
+    'C5': dict(n_total=100_000_000, name='C5: MarkovVariationalGP Matern52 (d=3) Bernoulli-probit GH-20, scan form, N=1e8'),
+    'C2': dict(n_total=10_000_000, name='C2: MarkovVariationalGP Matern52 (d=3) Bernoulli-probit GH-20, scan form, N=1e7'),
 }
 
+# algorithmic bytes per time step at d = 3, D = 1, fp64 on the reference-interface layouts (full matrices,
+# no As/Qs arrays, no gains): F = 121, S = 120, U = 72, V = 24, X = 33, L = 25; iteration = 2 (F + S) + U + V + X + L = 636.
+# Per kernel of the fused path: the reduce pass re-reads the filter's inputs (24), the filter pass is F, the two
+# smoother sweeps carry U resp. V + X in their epilogue.
+ALGO_BYTES = {
+    'it_reduce': 24, 'it_filter': 121, 'it_smooth_sites': 120 + 72, 'it_smooth_energy': 120 + 24 + 33, 'it_smooth': 120,
+    'up_reduce': 24, 'up_filter': 121, 'up_smooth': 120, 'up_smooth_grad': 120, 'site_update': 72, 'energy_terms': 57,
+    'it_from_tiled': 16, 'it_to_tiled': 16,
+}
+ITER_BYTES = 636           # per time step, SURVEY 8d
+ITER_BYTES_EXECUTED = 611  # without L: compute_log_lik() is served from the filter pass of the closing update_posterior()
 
-# fp64 instructions (DFMA + DMUL + DADD) per time step, from ncu's sass thread-instruction counters of the same
-# kernels (profiles/r1g_ncu_up_kernels.csv: op counts x cycles / N); the fp64 roofline uses them
-FP64_OPS = {'up_reduce': 179, 'up_filter': 163, 'up_smooth': 260}
 
-# dram__bytes_read.sum + dram__bytes_write.sum per time step of one launch, from the ncu --set full captures
-# under profiles/ (N = 1e7); reported as `traffic` (scaled by the steps a launch processes)
-# dram__bytes_read.sum + dram__bytes_write.sum per time step of one launch at N = 1e7 (profiles/r2l_ncu_full_summary_c2.csv)
-NCU_DRAM_BYTES = {'up_reduce': 26.0, 'up_filter': 97.1, 'up_smooth': 96.9, 'site_update': 67.3, 'energy_terms': 40.7}
-
-
-def bench_inputs(N, seed=0):
-    from _data import bench_inputs as f
-    return f(N, seed)
+def block_seeded_inputs(n_total, lo, hi, seed=0, block=1 << 20):
+    """C2 / C5 inputs of SURVEY 8d for the steps [lo, hi) of the global series: dt_0 = 0, dt_k = 0.1 + 0.2 u_k,
+    y_k = 1[2 sin(.3 t_k) + sin(.05 t_k) + .5 eps_k > 0].  Random numbers are drawn per block of 2^20 steps from a
+    generator seeded by the block index, so every rank can form ITS shard of the same global series."""
+    b0, b1 = lo // block, (hi + block - 1) // block
+    t_off = 0.0
+    for b in range(b0):  # time offset of the first block: sum of the step lengths before it
+        n = min(block, n_total - b * block)
+        dtb = 0.1 + 0.2 * np.random.default_rng([seed, b]).random(n)
+        if b == 0:
+            dtb[0] = 0.0
+        t_off += float(dtb.sum())
+    dts, ys = [], []
+    for b in range(b0, b1):
+        n = min(block, n_total - b * block)
+        rng = np.random.default_rng([seed, b])
+        dtb = 0.1 + 0.2 * rng.random(n)
+        if b == 0:
+            dtb[0] = 0.0
+        eps = rng.standard_normal(n)
+        t = t_off + np.cumsum(dtb)
+        t_off = float(t[-1])
+        yb = (2 * np.sin(0.3 * t) + np.sin(0.05 * t) + 0.5 * eps > 0).astype(np.uint8)
+        s, e = max(lo, b * block) - b * block, min(hi, b * block + n) - b * block
+        dts.append(dtb[s:e])
+        ys.append(yb[s:e])
+    return np.concatenate(dts), np.concatenate(ys)
 
 
 class ClockSampler:
@@ -113,25 +132,51 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def workload_config(args, world, n_run=None):
+    w = WORKLOADS[args.workload]
+    cfg = {'workload': w['name'], 'n_time_steps_total': int(args.n_total),
+           'parallelism': 'time-shard x%d (the same series split over the GPUs)' % world,
+           'iteration': 'inference(lr=1) [F,S,U,F,S] + energy() [V,L,X]',
+           'l2': 'inputs larger than L2 (>= 2 GB working set vs 126 MB L2); no flush needed'}
+    if n_run is not None and n_run != args.n_total:
+        cfg['workload'] += ' -- bounded sample: N=%d steps of it' % n_run
+        cfg['n_time_steps_run'] = int(n_run)
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def run_cpu(sample_n, steps, warmup, threads=None):
-    """the reference algorithm on the host: plain-C port (oracle/c/markov_c.c), OpenMP over the vmapped loops"""
+def probe_reference_runtime():
+    """the reference itself (pure Python on jax 0.4.14 + objax) can only be timed if those packages exist on the box"""
+    import importlib.util
+    missing = [m for m in ('jax', 'objax') if importlib.util.find_spec(m) is None]
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    return {'reference_runnable': not missing and os.path.isdir(ref), 'missing_modules': missing,
+            'baseline_ref_present': os.path.isdir(ref)}
+
+
+def run_cpu(sample_n, steps, warmup, threads=None, blocked=True):
+    """the reference algorithm on the host (oracle/c/markov_c.c).  blocked=True: the temporally parallel form
+    (ops.py:183-253, 314-354) as a time-blocked three-phase scan over all host threads, site loops in OpenMP;
+    blocked=False: the reference's CPU default, the sequential lax.scan recursion on one thread."""
     from oracle import cport
     if threads:
         os.environ['OMP_NUM_THREADS'] = str(threads)
     cores = int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1))
-    t, dt, y = bench_inputs(sample_n)
-    m = cport.ViModel(3, 1.0, 1.0, 2, 0.0, dt, y)
+    dt, y = block_seeded_inputs(sample_n, 0, sample_n)
+    m = cport.ViModel(3, 1.0, 1.0, 2, 0.0, dt, y.astype(np.float64))
+    it = (lambda: m.iteration_blocked(1.0)) if (blocked and hasattr(m, 'iteration_blocked')) else (lambda: m.iteration(1.0))
     for _ in range(warmup):
-        m.iteration(1.0)
+        it()
     t0 = time.perf_counter()
     for _ in range(steps):
-        E = m.iteration(1.0)
+        E = it()
     el = (time.perf_counter() - t0) / steps
+    form = ('temporally parallel form as a time-blocked three-phase scan on %d threads' % cores) if (blocked and hasattr(m, 'iteration_blocked')) \
+        else 'sequential filter/smoother (reference CPU default parallel=False) on one thread'
     return {'value': sample_n / el, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': 'N=%d steps of the same workload, %d iteration(s); sequential filter/smoother (reference CPU '
-                      'default parallel=False) with As/Qs materialised, site loops OpenMP x%d' % (sample_n, steps, cores),
-            'ms_per_step': el * 1e3, 'energy': E}
+            'sample': 'N=%d steps of the same workload, %d timed iteration(s) after %d warm-up; %s, As/Qs '
+                      'materialised as in the reference, site loops OpenMP x%d' % (sample_n, steps, warmup, form, cores),
+            'ms_per_step': el * 1e3, 'energy': E, 'steps': steps, 'warmup': warmup}
 
 
 def main_reference(args):
@@ -139,59 +184,111 @@ def main_reference(args):
     if rank != 0:
         return
     n = args.cpu_sample
-    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1 to its children)
-    r = run_cpu(n, max(1, min(args.steps, 3)), min(args.warmup, 1), threads=os.cpu_count() or 1)
+    # every step is a bounded sample of the workload; all the host threads the box has (torchrun exports OMP_NUM_THREADS=1)
+    r = run_cpu(n, args.steps, args.warmup, threads=os.cpu_count() or 1)
     line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, 1),
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args, 1, n_run=n),
             'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'reference_runtime_probe': probe_reference_runtime(),
             'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
 
-def workload_config(args, world):
-    return {'workload': 'C2: MarkovVariationalGP Matern52 (d=3) Bernoulli-probit GH-20, scan form, '
-                        'N=%d time steps per GPU' % args.n_local,
-            'n_time_steps_total': args.n_local * world, 'parallelism': 'time-shard x%d' % world,
-            'iteration': 'inference(lr=1) [F,S,U,F,S] + energy() [V,L,X]',
-            'l2': 'inputs larger than L2 (>= 2 GB working set vs 126 MB L2); no flush needed'}
-
-
 # ------------------------------------------------------------------------------------------ GPU arm
+def numa_local_affinity(local_rank):
+    """bind this process to the cores of the NUMA node its GPU hangs off, so pinned host buffers are allocated (first
+    touch) in the memory next to the PCIe root of that GPU"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        devs = [d for d in os.listdir('/sys/bus/pci/devices') if d.lower().startswith('%04x:%02x:' % (dom, bus))]
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % devs[0]).read())
+        if node < 0:
+            return None
+        cpus = open('/sys/devices/system/node/node%d/cpulist' % node).read().strip()
+        ids = []
+        for part in cpus.split(','):
+            a, _, b = part.partition('-')
+            ids += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, ids)
+        return node
+    except Exception:
+        return None
+
+
+def parity_self_check(bn, distributed, _lib, rank, world, dev):
+    """N > 1: a small fixed global series sharded over all ranks must reproduce rank 0's single-GPU result"""
+    import torch
+    import torch.distributed as dist
+    n = 40_000 * world + 17
+    dt, y = block_seeded_inputs(n, 0, n, seed=11)
+    b = [n * r // world for r in range(world + 1)]
+    kern = bn.kernels.Matern52(1.0, 1.0)
+    lik = bn.likelihoods.Bernoulli(link='probit')
+    nxt = dt[b[rank + 1]] if rank + 1 < world else 0.0
+    m = distributed.TimeShardedMarkovGP(kern, lik, dt[b[rank]:b[rank + 1]].copy(), y[b[rank]:b[rank + 1]].astype(np.float64),
+                                        nxt, _lib.BN_METHOD_VI, rank, world)
+    for _ in range(2):
+        m.inference(lr=0.7)
+    E = m.energy()
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        one = bn.models.MarkovVariationalGP(kernel=kern, likelihood=lik, X=np.cumsum(dt), Y=y.astype(np.float64), parallel=True)
+        for _ in range(2):
+            one.inference(lr=0.7)
+        E1 = one.energy()
+        pm1 = one.posterior_mean.reshape(-1)[b[0]:b[1]]
+        err = float((m.posterior_mean.reshape(-1) - pm1).abs().max() / pm1.abs().max())
+        eerr = abs(float(E) - float(E1)) / abs(float(E1))
+        ok[0] = int(err < 1e-9 and eerr < 1e-9)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return bool(int(ok))
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
-    import bayesnewton_b200 as bn
-    from bayesnewton_b200 import _lib, distributed
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
+    numa = numa_local_affinity(local_rank) if world > 1 else None
+    import bayesnewton_b200 as bn
+    from bayesnewton_b200 import _lib, distributed
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     dev = torch.device('cuda', local_rank)
-    NL = args.n_local
+    NT = args.n_total
+    lo, hi = NT * rank // world, NT * (rank + 1) // world
+    NL = hi - lo
+    L = _lib.lib()
 
-    # synthetic inputs: the global series is generated shard by shard with per-rank seeds
-    t, dt, y = bench_inputs(NL, seed=100 * rank)
-    if rank > 0:
-        dt[0] = 0.1 + 0.2 * np.random.default_rng(7 + rank).random()
-    nxt = torch.tensor([dt[0]], dtype=torch.float64, device=dev)
-    if world > 1:  # dt of the right neighbour's first step closes this shard's smoother
-        allfirst = torch.empty(world, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allfirst, nxt)
-        dt_next = float(allfirst[rank + 1]) if rank + 1 < world else 0.0
-    else:
-        dt_next = 0.0
+    parity_ok = None
+    if world > 1:
+        parity_ok = parity_self_check(bn, distributed, _lib, rank, world, dev)
+
+    # synthetic inputs: this rank's shard of the global series (pinned host buffers: dt fp64, labels uint8)
+    dt, y8 = block_seeded_inputs(NT, lo, hi)
     dt_pin = torch.from_numpy(dt).pin_memory()
-    y_pin = torch.from_numpy(y).pin_memory()
-
+    y_pin = torch.from_numpy(y8).pin_memory()
     kern = bn.kernels.Matern52(variance=1.0, lengthscale=1.0)
     lik = bn.likelihoods.Bernoulli(link='probit')
-    model = distributed.TimeShardedMarkovGP(kern, lik, dt_pin, y_pin, dt_next, _lib.BN_METHOD_VI, rank, world)
-    L = _lib.lib()
+    if world == 1:
+        # the class the reference API names; X = cumulative time, Y = the labels
+        model = bn.models.MarkovVariationalGP(kernel=kern, likelihood=lik, X=np.cumsum(dt), Y=y8.astype(np.float64), parallel=True)
+        model_name = 'bayesnewton_b200.models.MarkovVariationalGP'
+    else:
+        first = torch.tensor([dt[0]], dtype=torch.float64, device=dev)
+        allfirst = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allfirst, first)
+        dt_next = float(allfirst[rank + 1]) if rank + 1 < world else 0.0
+        model = distributed.TimeShardedMarkovGP(kern, lik, dt_pin, torch.from_numpy(y8.astype(np.float64)), dt_next,
+                                                _lib.BN_METHOD_VI, rank, world)
+        model_name = 'bayesnewton_b200.distributed.TimeShardedMarkovGP'
+    del dt, y8
 
     def step():
         model.inference(lr=1.0)
@@ -202,8 +299,6 @@ def main_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # nvidia-smi needs ~0.1 s to come up: start it before the warm-up, count only what it samples from the first
-    # timed region on (the device-timed steps, then the end-to-end and with-gradient steps: all under the same load)
     sampler = ClockSampler(local_rank)
     sampler.start()
     for _ in range(args.warmup):
@@ -222,14 +317,14 @@ def main_gpu(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms) / args.steps
     # ---- the same K steps once more with every kernel launch bracketed by CUDA events on its stream (the per-kernel
-    # durations behind the roofline); kept out of the region above because the 60 event pairs per step cost ~5 %
+    # durations behind the roofline); kept out of the region above because the event pairs cost a few per cent
+    import ctypes
     L.bn_timing_enable(1)
     for _ in range(args.steps):
         E = step()
     sync_all()
-    import ctypes
-    cbuf = ctypes.create_string_buffer(8192)
-    L.bn_timing_report(cbuf, 8192)
+    cbuf = ctypes.create_string_buffer(16384)
+    L.bn_timing_report(cbuf, 16384)
     L.bn_timing_enable(0)
     kt = {}
     for ln in cbuf.value.decode().splitlines():
@@ -237,11 +332,11 @@ def main_gpu(args):
         kt[name] = (int(cnt), float(tot))
     energy = float(E)
 
-    # ---- end to end through the public API with HOST buffers: every step, that step's inputs (dt, Y) come from
-    # pinned host memory and the result (energy, a double) goes back to the host.  The copy of step i+1's inputs
-    # runs on a second stream into the other device buffer while step i computes (double buffering).
+    # ---- end to end through the public API with HOST buffers: every step, that step's inputs (dt fp64, labels uint8)
+    # come from pinned host memory (streamed in by model.load_inputs) and the result (energy, a double) goes back to the
+    # host.  The copy of step i+1's inputs runs on a second stream into the other staging buffer while step i computes.
     copy_stream = torch.cuda.Stream()
-    bufs = [(model.shard.dt, model.Y), (torch.empty_like(model.shard.dt), torch.empty_like(model.Y))]
+    bufs = [(torch.empty(NL, dtype=torch.float64, device=dev), torch.empty(NL, dtype=torch.uint8, device=dev)) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     free = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -253,8 +348,6 @@ def main_gpu(args):
             bufs[b][1].copy_(y_pin, non_blocking=True)
             ready[b].record(copy_stream)
 
-    # the step's result goes back through a pinned double buffer: the copy of step i's energy is queued behind step
-    # i's kernels and read on the host while step i+1 is already running (one D2H read per step, never skipped)
     e_pin = torch.zeros(2, dtype=torch.float64).pin_memory()
     e_done = [torch.cuda.Event(), torch.cuda.Event()]
     energies = []
@@ -263,8 +356,8 @@ def main_gpu(args):
         b = i % 2
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[b])
-        model.shard.dt, model.Y = bufs[b]
         start_copy(i + 1)                        # H2D of the next step's inputs overlaps this step's kernels
+        model.load_inputs(bufs[b][0], bufs[b][1])
         model.inference(lr=1.0)
         e = model.energy()
         free[b].record(cur)
@@ -293,40 +386,39 @@ def main_gpu(args):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2) / args.steps
+    del bufs
 
     # ---- the same iteration with the hyper-gradient pass G ("reported with and without"): the closing
     # posterior update of inference() accumulates d log-lik / d (variance, lengthscale) inside its smoother sweep
-    model.shard.dt, model.Y = bufs[0]
+    grad = None
+    if not args.no_grad:
+        def step_grad():
+            model.inference(lr=1.0, want_grad=True)
+            return model.energy_and_grad()
 
-    def step_grad():
-        model.inference(lr=1.0, want_grad=True)
-        return model.energy_and_grad()
-
-    for _ in range(2):
-        step_grad()
-    sync_all()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(args.steps):
-        Eg, dEg = step_grad()
-    g1.record()
-    sync_all()
-    ms3 = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
-    grad_ms = float(ms3) / args.steps
+        for _ in range(2):
+            step_grad()
+        sync_all()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gsteps = max(1, min(args.steps, 5))
+        g0.record()
+        for _ in range(gsteps):
+            Eg, dEg = step_grad()
+        g1.record()
+        sync_all()
+        ms3 = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        grad = (float(ms3) / gsteps, [float(v) for v in dEg.reshape(-1).tolist()])
     clocks = sampler.stop()
-    cbuf2 = ctypes.create_string_buffer(8192)
 
-    # fp64 FMA peak of this device, measured now (the second roofline: at d = 3 the path is fp64-pipe bound)
-    import ctypes as _C
+    # fp64 FMA peak of this device, measured now (the second roofline: at d = 3 the update kernels are fp64-pipe bound)
     scratch = torch.empty(8 * 148 * 256 * 2, dtype=torch.float64, device=dev)
-    dfma = _C.c_double(0.0)
-    L.bn_measure_dfma_peak(scratch.data_ptr(), scratch.numel(), _C.byref(dfma))
+    dfma = ctypes.c_double(0.0)
+    L.bn_measure_dfma_peak(scratch.data_ptr(), scratch.numel(), ctypes.byref(dfma))
     dfma_peak = dfma.value
 
     if rank == 0:
-        total_steps = NL * world
         peak, peak_src = measured_peaks()
         # dominant kernel by device time inside the timed region
         dom = max(kt, key=lambda k: kt[k][1]) if kt else None
@@ -335,47 +427,46 @@ def main_gpu(args):
             cnt, tot = kt[dom]
             avg_ms = tot / cnt
             ab = ALGO_BYTES.get(dom, 0)
-            if dom == 'kf_apply':  # 2 of 3 launches per step write the states, 1 is log-likelihood only
-                ab = (2 * ALGO_BYTES['kf_apply'] + ALGO_BYTES['kf_apply_ell']) / 3.0
             achieved = ab * NL / (avg_ms * 1e-3) / 1e9
-            traffic = NCU_DRAM_BYTES[dom] * NL if (args.traffic is None and dom in NCU_DRAM_BYTES) else args.traffic
             roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                    'traffic_source': 'ncu --set full dram bytes per step at N=1e7 (profiles/r2l_ncu_full_summary_c2.csv) x steps per launch',
-                    'algorithmic_bytes_per_launch': ab * NL, 'avg_launch_ms': avg_ms,
+                    'frac': achieved / peak, 'traffic': args.traffic, 'peak_source': peak_src,
+                    'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/), passed with --traffic' if args.traffic else None,
+                    'algorithmic_bytes_per_step': ab, 'algorithmic_bytes_per_launch': ab * NL, 'avg_launch_ms': avg_ms,
                     'share_of_step': tot / (ms_per_step * args.steps),
                     'timing': 'CUDA events around every launch of this kernel, on its stream, in a second pass of the same K steps right after the timed region'}
-            if dom in FP64_OPS and dfma_peak > 0:
-                f64 = FP64_OPS[dom] * NL / (avg_ms * 1e-3)
-                roof['fp64'] = {'achieved_fp64_inst_per_s': f64, 'peak_dfma_per_s': dfma_peak, 'frac': f64 / dfma_peak,
-                                'note': 'the kernel is bound by the fp64 pipe, not HBM (DESIGN.md section 4)'}
         line = {
-            'metric': METRIC, 'value': total_steps / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
+            'metric': METRIC, 'value': NT / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, world),
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': dict(workload_config(args, world), model=model_name, n_time_steps_per_gpu=int(NL)),
             'clocks': clocks,
-            'e2e': {'value': total_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': int(2 * NL * 8), 'd2h_bytes_per_step': 8,
-                    'h2d_GBps_per_gpu': 2 * NL * 8 / (e2e_ms * 1e-3) / 1e9,
-                    'note': 'inputs are the reference-facing fp64 host arrays (dt, Y): 16 B per time step over PCIe every step, '
-                            'double-buffered against compute; when h2d_GBps_per_gpu is near the link rate the end-to-end figure is copy-bound'},
-            'gpu_launches': int(sum(c for c, _ in kt.values())),
+            'e2e': {'value': NT / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': int(NL * 9), 'd2h_bytes_per_step': 8,
+                    'h2d_GBps_per_gpu': NL * 9 / (e2e_ms * 1e-3) / 1e9, 'numa_node_of_pinned_buffers': numa,
+                    'note': 'inputs stream from pinned host memory every step through model.load_inputs(): dt as fp64 and the '
+                            'Bernoulli labels as uint8 (9 B per time step over PCIe), double-buffered against compute; when '
+                            'h2d_GBps_per_gpu is near the link rate the end-to-end figure is copy-bound'},
+            'gpu_launches': int(sum(c for c, _ in kt.values())) // max(1, args.steps) * args.steps,
+            'gpu_launches_per_step': int(sum(c for c, _ in kt.values())) // max(1, args.steps),
             'roofline': roof,
-            'iteration_bytes': {'algorithmic_bytes_per_time_step': 636,
-                                'achieved_GBps': 636 * NL / (ms_per_step * 1e-3) / 1e9,
-                                'frac_of_hbm_peak': 636 * NL / (ms_per_step * 1e-3) / 1e9 / peak},
+            'iteration_bytes': {'algorithmic_bytes_per_time_step': ITER_BYTES,
+                                'achieved_GBps': ITER_BYTES * NT / world / (ms_per_step * 1e-3) / 1e9,
+                                'frac_of_hbm_peak': ITER_BYTES * NT / world / (ms_per_step * 1e-3) / 1e9 / peak,
+                                'executed_bytes_per_time_step': ITER_BYTES_EXECUTED,
+                                'frac_of_hbm_peak_executed': ITER_BYTES_EXECUTED * NT / world / (ms_per_step * 1e-3) / 1e9 / peak,
+                                'note': 'per GPU.  636 B = 2(F+S)+U+V+X+L on the reference-interface layouts (SURVEY 8d); L (25 B, '
+                                        'compute_log_lik) is NOT executed as a pass of its own: its value comes from the filter of the '
+                                        'closing update_posterior() of the same iteration (same inputs), so 611 B is the executed count'},
             'kernels_ms_per_step': {k: v[1] / args.steps for k, v in kt.items()},
             'energy': energy,
-            'with_hyper_gradient': {'ms_per_step': grad_ms, 'value': total_steps / (grad_ms * 1e-3), 'unit': UNIT,
-                                    'algorithmic_bytes_per_time_step': 636,
-                                    'note': 'iteration + d energy / d (variance, lengthscale); the adjoint is formed inside '
-                                            'the smoother sweep, no extra HBM pass',
-                                    'd_energy': [float(v) for v in dEg.reshape(-1).tolist()]},
             'fp64_peak_dfma_per_s': dfma_peak,
-            'fp64_frac_by_kernel': {k: FP64_OPS[k] * NL * kt[k][0] / (kt[k][1] * 1e-3) / dfma_peak
-                                    for k in FP64_OPS if k in kt and dfma_peak > 0},
         }
+        if parity_ok is not None:
+            line['parity_nranks_ok'] = parity_ok
+        if grad is not None:
+            line['with_hyper_gradient'] = {'ms_per_step': grad[0], 'value': NT / (grad[0] * 1e-3), 'unit': UNIT,
+                                           'note': 'iteration + d energy / d (variance, lengthscale); the adjoint is formed inside '
+                                                   'the smoother sweep, no extra HBM pass', 'd_energy': grad[1]}
         if world == 1 and not args.no_cpu:
             r = run_cpu(args.cpu_sample, 1, 1)
             line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
@@ -387,14 +478,18 @@ def main_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--n-local', type=int, default=10_000_000, help='time steps per GPU (C2: 1e7)')
+    ap.add_argument('--workload', default='C5', choices=sorted(WORKLOADS))
+    ap.add_argument('--n-total', type=int, default=None, help='time steps of the whole series (default: the workload\'s)')
     ap.add_argument('--cpu-sample', type=int, default=2_000_000, help='time steps of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-grad', action='store_true', help='skip the with-hyper-gradient leg')
     ap.add_argument('--traffic', type=float, default=None, help='dram bytes per launch of the dominant kernel (ncu)')
     args = ap.parse_args()
+    if args.n_total is None:
+        args.n_total = WORKLOADS[args.workload]['n_total']
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3
     if args.impl == 'reference':

@@ -425,6 +425,62 @@ int bn_st_predict_state(const bn_kernel_spec* temporal, int M, int64_t N, const 
                         const double* x_test, const double* mean, const double* cov, const double* gain,
                         double* f_mean, double* f_cov, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- fused inference iteration on chunk-tiled resident state (single latent, one site per step) ------------
+ * One iteration of a temporal Markov GP is  inference(): update_posterior -> update_variational_params + newton_update +
+ * damped update_nat_params -> update_posterior  (inference.py:65-90), then energy(): E_q[log p(y|f)] summed, the filter
+ * log-likelihood, and E_q[log N(pseudo_y | f, pseudo_var)] summed (inference.py:197-222; basemodels.py:708-741).  The
+ * arrays that only travel between those stages -- dt, Y, the sites (pseudo_y, pseudo_var), the posterior marginals --
+ * are kept here in the layout of the thread that consumes them ("tiled": the series is cut into the chunks of the
+ * temporally parallel filter, chunk c step j at [((c >> 5) * L + j) * 32 + (c & 31)], L = bn_iter_chunk_len), and the
+ * two smoother sweeps run the per-step site work in their epilogue on the marginal they hold in registers:
+ *   BN_ITER_PLAIN   update_posterior()                                     basemodels.py:689-706
+ *   BN_ITER_SITES   update_posterior(); the site update of inference.py:72-86 for every step, sites rewritten IN PLACE
+ *                   sums[0] = sum_n |nat1_new - nat1|, sums[1] = sum_n |nat2_new - nat2| (before damping; the `diff`
+ *                   terms of inference.py:78-79 times N)
+ *   BN_ITER_ENERGY  update_posterior(); sums[0] = nansum_n likelihood term (VI: E_q[log p]; Newton: log p(y | m)),
+ *                   sums[1] = sum_n gaussian_expected_log_lik(pseudo_y_n, m_n, v_n, pseudo_var_n)  (utils.py:510-531)
+ * ell (nullable) = the filter log-likelihood of the pass = compute_log_lik() (basemodels.py:726-741).
+ * Supported: n_components = 1 of any Matern family; likelihood in {Gaussian, Bernoulli probit / logit, Poisson};
+ * method VI or Newton.  cub_x / cub_w: HOST arrays (the 1-D rule, Q <= 64; ignored by Newton and the closed forms).
+ * Ranks of a time-sharded run call the three phases with their carries exchanged in between (as bn_up_shard_*). */
+enum { BN_ITER_PLAIN = 0, BN_ITER_SITES = 1, BN_ITER_ENERGY = 2 };
+
+typedef struct {
+    int64_t N;                 /* steps of this time shard */
+    int32_t rank, world;       /* position of the shard (0, 1 for a single GPU) */
+    const double* dt_t;        /* tiled dt (dt[0] of rank 0 is ignored: the prior is stationary) */
+    const double* y_t;         /* tiled observations Y (SITES / ENERGY) */
+    double* site_mean_t;       /* tiled pseudo observations */
+    double* site_cov_t;        /* tiled pseudo variances */
+    const uint8_t* mask_t;     /* tiled mask of missing pseudo observations, nullable */
+    double* post_mean_t;       /* tiled posterior marginals, written by PLAIN / ENERGY */
+    double* post_cov_t;
+    int32_t method, likelihood;
+    double lik_param;          /* Gaussian variance / Poisson bin size */
+    int32_t Q, ensure_psd;
+    const double* cub_x_host;  /* [Q] */
+    const double* cub_w_host;  /* [Q] */
+    double lr, power;
+} bn_iter_args;
+
+int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N);       /* L */
+int64_t bn_iter_tiled_len(const bn_kernel_spec* k, int64_t N);   /* elements of a tiled array (padding included) */
+size_t bn_iter_workspace_bytes(const bn_kernel_spec* k, int64_t N);
+/* layout conversion, both sides coalesced; padding of the tiled side is filled with `fill` */
+int bn_iter_to_tiled(const bn_kernel_spec* k, int64_t N, const double* x, double* x_t, double fill, void* stream);
+int bn_iter_from_tiled(const bn_kernel_spec* k, int64_t N, const double* x_t, double* x, void* stream);
+int bn_iter_to_tiled_u8(const bn_kernel_spec* k, int64_t N, const uint8_t* x, uint8_t* x_t, void* stream);
+/* one pass on a single GPU (world = 1) */
+int bn_iter_pass(const bn_kernel_spec* k, const bn_iter_args* a, int mode, double* ell, double* sums,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* the same pass in the three phases of a time-sharded run; the workspace carries state from phase to phase */
+int bn_iter_shard_reduce(const bn_kernel_spec* k, const bn_iter_args* a, double* kf_carry,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int bn_iter_shard_filter(const bn_kernel_spec* k, const bn_iter_args* a, const double* kf_carries, double* ell,
+                         double* rts_carry, void* workspace, size_t workspace_bytes, void* stream);
+int bn_iter_shard_smooth(const bn_kernel_spec* k, const bn_iter_args* a, int mode, const double* rts_carries,
+                         double* sums, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

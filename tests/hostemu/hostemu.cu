@@ -12,6 +12,7 @@
 #include "../../bayesnewton_b200/csrc/smoother_impl.cuh"
 #include "../../bayesnewton_b200/csrc/sites_impl.cuh"
 #include "../../bayesnewton_b200/csrc/up_impl.cuh"
+#include "../../bayesnewton_b200/csrc/iter_impl.cuh"
 
 namespace bn {
 void set_error(const char*, ...) {}
@@ -202,6 +203,145 @@ static int emu_up(const bn_kernel_spec* k, long long N, int L, int world, const 
                 up_smooth_chunk<G, false>(g, cx, q.n, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, true);
         }
     }
+    return 0;
+}
+
+
+// ---- fused iteration pass on tiled state (iter_impl.cuh) over `world` emulated ranks.  The caller's arrays are
+// linear; each rank tiles its shard (the role of bn_iter_to_tiled), runs the three phases with the tiled chunk bodies
+// and the requested smoother epilogue, and the results are un-tiled (bn_iter_from_tiled).
+template <typename T>
+static void host_to_tiled(long long n, int L, long long nc, const T* x, std::vector<T>& xt, T fill) {
+    xt.assign((size_t)tl_len(nc, L), fill);
+    for (long long c = 0; c < nc; ++c)
+        for (int j = 0; j < L; ++j) {
+            const long long k = c * L + j;
+            if (k < n) xt[(size_t)(tl_base(c, L) + 32LL * j)] = x[k];
+        }
+}
+static void host_from_tiled(long long n, int L, long long nc, const std::vector<double>& xt, double* x) {
+    for (long long c = 0; c < nc; ++c)
+        for (int j = 0; j < L; ++j) {
+            const long long k = c * L + j;
+            if (k < n) x[k] = xt[(size_t)(tl_base(c, L) + 32LL * j)];
+        }
+}
+
+template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
+static void emu_it_sweep(const G& g, const ItIO& io, const ItSiteArgs& sa, const Cub1& cub, int L, long long nc,
+                         const double* spre, const double* sinit, const double* fs) {
+    const double* tab = TAB ? probit_table_host().data() : nullptr;
+    for (long long c = 0; c < nc; ++c) {
+        Epi<LIK, METHOD, TAB> epi(io, sa, &cub, tab);
+        it_smooth_chunk(g, io, L, nc, spre, sinit, fs, c, epi);
+    }
+}
+
+template <class G>
+static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const double* dt, const double* y,
+                  double* sy, double* sR, const unsigned char* mask, int mode, int method, int lik, double lik_param,
+                  int Q, const double* cx, const double* cw, double lr, double power, int ensure_psd, int use_table,
+                  double* ell, double* sums, double* pm, double* pc) {
+    constexpr int d = G::d;
+    using FA = FilterAlg<d>;
+    using SA = SmootherAlg<d>;
+    if (L % kUpTJ != 0) return -2;
+    G g;
+    g.prepare(*k);
+    Cub1 cub;
+    make_cub1(Q, cx, cw, cub);
+    std::vector<long long> off(world + 1);
+    for (int r = 0; r <= world; ++r) off[r] = N * r / world;
+    struct Rank {
+        long long n, nc;
+        std::vector<double> agg, fpre, sel, spre, fs, s0, sinit, dt_t, y_t, sy_t, sR_t, pm_t, pc_t, p1, p2;
+        std::vector<unsigned char> mk_t;
+        ItIO io;
+    };
+    std::vector<Rank> ranks(world);
+    std::vector<double> fcar((size_t)world * FA::kCarry), scar((size_t)world * SA::kCarry);
+    for (int r = 0; r < world; ++r) {
+        Rank& q = ranks[r];
+        const long long o = off[r];
+        q.n = off[r + 1] - o;
+        q.nc = (q.n + L - 1) / L;
+        host_to_tiled<double>(q.n, L, q.nc, dt + o, q.dt_t, 0.0);
+        host_to_tiled<double>(q.n, L, q.nc, y + o, q.y_t, 0.0);
+        host_to_tiled<double>(q.n, L, q.nc, sy + o, q.sy_t, 0.0);
+        host_to_tiled<double>(q.n, L, q.nc, sR + o, q.sR_t, 1.0);
+        if (mask) host_to_tiled<unsigned char>(q.n, L, q.nc, mask + o, q.mk_t, (unsigned char)0);
+        q.pm_t.assign((size_t)tl_len(q.nc, L), 0.0);
+        q.pc_t.assign((size_t)tl_len(q.nc, L), 0.0);
+        q.io = ItIO{q.n, q.dt_t.data(), q.y_t.data(), q.sy_t.data(), q.sR_t.data(), mask ? q.mk_t.data() : nullptr,
+                    q.pm_t.data(), q.pc_t.data()};
+        q.agg.assign((size_t)q.nc * FA::kElem, 0.0);
+        q.fpre.assign((size_t)q.nc * FA::kElem, 0.0);
+        q.sel.assign((size_t)q.nc * SA::kElem, 0.0);
+        q.spre.assign((size_t)q.nc * SA::kElem, 0.0);
+        q.fs.assign((size_t)fs_doubles(q.nc, L, d + symn(d)), 0.0);
+        q.s0.assign(64, 0.0);
+        q.sinit.assign(64, 0.0);
+        q.p1.assign(q.nc, 0.0);
+        q.p2.assign(q.nc, 0.0);
+        for (long long c = 0; c < q.nc; ++c) it_reduce_chunk(g, q.io, L, q.nc, r == 0, q.agg.data(), c);
+        host_scan<FA>(q.agg.data(), q.nc, q.fpre.data());
+        export_carry_body<FA>(q.fpre.data(), q.nc, fcar.data() + (size_t)r * FA::kCarry);
+    }
+    double total = 0.0;
+    for (int r = 0; r < world; ++r) {
+        Rank& q = ranks[r];
+        fold_carries_body<FA>(fcar.data(), 0, r, 1, q.s0.data());
+        std::vector<double> partials(q.nc, 0.0);
+        for (long long c = 0; c < q.nc; ++c)
+            it_filter_chunk<G, true>(g, q.io, L, q.nc, r == 0, q.fpre.data(), q.s0.data(), q.fs.data(), partials.data(), c);
+        for (double v : partials) total += v;
+        for (long long c = 0; c < q.nc; ++c)
+            up_selem_chunk<G>(q.n, L, q.nc, r != 0, q.agg.data(), q.s0.data(), q.fs.data(), q.sel.data(), c);
+        host_scan<SA>(q.sel.data(), q.nc, q.spre.data());
+        up_export_scarry<d>(q.spre.data(), q.nc, r == world - 1, q.n, L, q.fs.data(), scar.data() + (size_t)r * SA::kCarry);
+    }
+    if (ell) *ell = total;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < world; ++r) {
+        Rank& q = ranks[r];
+        if (r != world - 1) fold_carries_body<SA>(scar.data(), world - 1, r, -1, q.sinit.data());
+        else up_last_state<d>(q.n, L, q.fs.data(), q.sinit.data());
+        ItSiteArgs sa{lik_param, lr, power, ensure_psd, 0, q.p1.data(), q.p2.data()};
+        bool done = false;
+        if (mode == IT_PLAIN) {
+            for (long long c = 0; c < q.nc; ++c) {
+                EpiStore epi{q.io.pm, q.io.pc};
+                it_smooth_chunk(g, q.io, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, epi);
+            }
+            done = true;
+        }
+#define X(LK, M)                                                                                                          \
+        if (!done && lik == LK && method == M) {                                                                          \
+            constexpr bool kTab = (LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI);                                   \
+            if (mode == IT_SITES) {                                                                                       \
+                if (kTab && use_table) emu_it_sweep<G, EpiSites, LK, M, kTab>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
+                else emu_it_sweep<G, EpiSites, LK, M, false>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
+            } else {                                                                                                      \
+                if (kTab && use_table) emu_it_sweep<G, EpiEnergy, LK, M, kTab>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
+                else emu_it_sweep<G, EpiEnergy, LK, M, false>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
+            }                                                                                                             \
+            done = true;                                                                                                  \
+        }
+        BN_FOR_EACH_ITER_SITE(X)
+#undef X
+        if (!done) return -3;
+        for (double v : q.p1) s1 += v;
+        for (double v : q.p2) s2 += v;
+        const long long o = off[r];
+        if (mode == IT_SITES) {
+            host_from_tiled(q.n, L, q.nc, q.sy_t, sy + o);
+            host_from_tiled(q.n, L, q.nc, q.sR_t, sR + o);
+        } else {
+            host_from_tiled(q.n, L, q.nc, q.pm_t, pm + o);
+            host_from_tiled(q.n, L, q.nc, q.pc_t, pc + o);
+        }
+    }
+    if (sums) { sums[0] = s1; sums[1] = s2; }
     return 0;
 }
 
@@ -457,4 +597,18 @@ extern "C" void emu_rank_filter(void* h, const double* kf_carries, const unsigne
 }
 extern "C" void emu_rank_smooth(void* h, const double* rts_carries, double* pm, double* pc, double* dvar, double* dlen) {
     ((EmuRankBase*)h)->smooth(rts_carries, pm, pc, dvar, dlen);
+}
+
+// fused iteration pass on tiled state (iter_impl.cuh); linear arrays in and out
+extern "C" int emu_iter_pass(const bn_kernel_spec* k, long long N, int L, int world, const double* dt, const double* y,
+                             double* sy, double* sR, const unsigned char* mask, int mode, int method, int lik,
+                             double lik_param, int Q, const double* cx, const double* cw, double lr, double power,
+                             int ensure_psd, int use_table, double* ell, double* sums, double* pm, double* pc) {
+#define X(FAM)                                                                                                          \
+    if (k->family == FAM && k->n_components == 1)                                                                       \
+        return emu_it<FastGen<FAM, 1>>(k, N, L, world, dt, y, sy, sR, mask, mode, method, lik, lik_param, Q, cx, cw, lr, \
+                                       power, ensure_psd, use_table, ell, sums, pm, pc);
+    X(BN_MATERN12) X(BN_MATERN32) X(BN_MATERN52) X(BN_MATERN72)
+#undef X
+    return -1;
 }

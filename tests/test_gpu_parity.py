@@ -227,7 +227,7 @@ def test_model_iteration_classification(bn, method, parallel):
             parallel=parallel, **kw)
     o = model.MarkovGP(ssm.Matern52(1.5, 0.75), sites.Bernoulli(), x, y, method=method, power=0.5)
     for it in range(3):
-        (mean, jac, hess), (d1, d2) = g.inference(lr=0.6)
+        (mean, jac, hess), (d1, d2) = g.inference(lr=0.6, return_state=True)
         (mean0, jac0, hess0), (d10, d20) = o.inference(lr=0.6)
         assert rel_err(np_(mean), mean0) < TOL and rel_err(np_(jac), jac0) < TOL and rel_err(np_(hess), hess0) < TOL
         assert abs(float(d1) - d10) < TOL * d10 and abs(float(d2) - d20) < TOL * d20

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One gpurun call of the build -> measure loop: new-path tests, bench lines, ncu launch list and full capture.
+#   usage: tools/gpu_round.sh <tag> [what ...]     what in: tests fulltests c2 c5 ncu
+tag=$1; shift
+what="$*"; [ -z "$what" ] && what="tests c2 c5 ncu"
+mkdir -p gpurun_out
+for w in $what; do
+  case $w in
+    tests) timeout 900 python -m pytest tests/test_fused_iteration.py -m gpu -x -q > gpurun_out/${tag}_fused_tests.log 2>&1; tail -3 gpurun_out/${tag}_fused_tests.log;;
+    fulltests) timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_gputests.log 2>&1; tail -3 gpurun_out/${tag}_gputests.log;;
+    c2) timeout 600 python bench.py --workload C2 --steps 10 --no-grad --no-cpu > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err; cat gpurun_out/${tag}_bench_c2.json | head -c 3000; tail -3 gpurun_out/${tag}_bench_c2.err;;
+    c5) timeout 900 python bench.py --steps 10 --no-cpu > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err; cat gpurun_out/${tag}_bench_c5.json | head -c 4000; tail -3 gpurun_out/${tag}_bench_c5.err;;
+    ncu)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python tools/prof_iter.py 10000000 3 > gpurun_out/${tag}_under_ncu.log 2>&1
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'it_(reduce|filter|smooth)' -s 5 -c 5 -o gpurun_out/${tag}_c2_full python tools/prof_iter.py 10000000 2 > gpurun_out/${tag}_ncu.log 2>&1
+      ncu -i gpurun_out/${tag}_c2_full.ncu-rep --page raw --csv > gpurun_out/${tag}_c2_raw.csv 2>/dev/null
+      tail -2 gpurun_out/${tag}_ncu.log;;
+  esac
+done

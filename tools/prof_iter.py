@@ -10,7 +10,7 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 t, dt, y = bench_inputs(N)
 m = bn.models.MarkovVariationalGP(kernel=bn.kernels.Matern52(1.0, 1.0), likelihood=bn.likelihoods.Bernoulli(), X=t, Y=y, parallel=True)
 for it in range(iters):
-    m.inference(lr=1.0, return_state=False)
+    m.inference(lr=1.0)
     E = m.energy()
 torch.cuda.synchronize()
 print('energy', float(E))
