@@ -145,12 +145,12 @@ BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks
     const double* pdt = io.dt + b + (long long)j_last * 32;
     const double* pf = fs + fs_index(c, L, j_last, 0, nf);
     long long ti = b + (long long)j_last * 32;
-    double nfm[d], nfP[symn(d)];              // filtered state of the next step to process, loaded one step ahead
-    double Abn[G::kBlockA], Qbn[G::kBlockS];  // discretisation of the next step to process, formed one step ahead
+    double nfm[d], nfP[symn(d)];  // filtered state of the next step to process, loaded one step ahead
+    double Abn[G::kBlockA];       // transition of the next step to process, formed one step ahead (its exp() chain is
+                                  // independent of the recursion); the noise blocks are formed at their use: keeping
+                                  // them a step ahead as well costs 12 registers the fused epilogues need
 #pragma unroll
     for (int i = 0; i < G::kBlockA; ++i) Abn[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < G::kBlockS; ++i) Qbn[i] = 0.0;
     double hn = pdt[0];
     if (j_last >= 1) {
 #pragma unroll
@@ -160,20 +160,17 @@ BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks
     }
 #pragma unroll 1
     for (int j = j_last; j >= 0; --j) {
-        double Ab[G::kBlockA], Qb[G::kBlockS];
+        double Ab[G::kBlockA];
 #pragma unroll
         for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
-#pragma unroll
-        for (int i = 0; i < G::kBlockS; ++i) Qb[i] = Qbn[i];
         const double h_k = hn;
         pdt -= 32;
         if (j >= 1) hn = pdt[0];
         epi.prefetch(ti);
-        // the discretisation of the step below (k-1 -> k, length h_k) is formed while this step's dependent chain runs
+        // the transition of the step below (k-1 -> k, length h_k) is formed while this step's dependent chain runs
         g.trans(h_k, Abn);
-        g.noise(Abn, Qbn);
         if (j < j_last) {
-            double fm[d], fP[symn(d)];
+            double fm[d], fP[symn(d)], Qb[G::kBlockS];
 #pragma unroll
             for (int i = 0; i < d; ++i) fm[i] = nfm[i];
 #pragma unroll
@@ -185,6 +182,7 @@ BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks
 #pragma unroll
                 for (int f = 0; f < symn(d); ++f) nfP[f] = pf[(d + f - nf) * 32];
             }
+            g.noise(Ab, Qb);
             frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
         }
         epi.step(ti, s.m[G::sel(0)], s.P[sidx(G::sel(0), G::sel(0))]);
@@ -312,7 +310,7 @@ template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, boo
 __global__ void __launch_bounds__(TAB ? kItTabThreads : kUpThreads, TAB ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
 it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs a, int L, long long nchunks,
                       const double* sprefix, const double* sinit, const double* fs, const double* gtab) {
-    extern __shared__ double it_smem[];
+    extern __shared__ __align__(16) double it_smem[];
     const double* tab = nullptr;
     if constexpr (TAB) {
         for (int i = threadIdx.x; i < kPtDoubles; i += kItTabThreads) it_smem[i] = gtab[i];

@@ -3,56 +3,96 @@
 // so that  log p(y=1 | f) = g(f)  and  log p(y!=1 | f) = log(1 - p) = g(-f).
 //
 // The cubature sites evaluate it 20 times per time step; through erf() + log() that is ~100 fp64
-// instructions per point and makes the site kernels the most expensive part of an iteration.  Here
-// g is tabulated once per process as piecewise cubics on 9217 intervals of width
-// 1/512 centred on the grid -9 + i/512 (Chebyshev interpolation in long double); outside [-9, 9]
-// g is constant to fp64.  The nearest singularities of g (zeros of eps + (1-2eps) Phi) sit ~0.95
-// from the real axis near f = -3.2, which is what forces the narrow intervals.
+// instructions per point.  Here g is tabulated once per process as piecewise cubics on 8192 intervals of width
+// 1/512 covering [-8.5, 7.5) (outside it g is constant to 3e-14); the nearest singularities of g (zeros of
+// eps + (1-2eps) Phi) sit ~0.95 from the real axis near f = -3.2, which is what forces the narrow intervals.
 //
-// The table lives in shared memory and is gathered with a different index per lane, so the cost of
-// an evaluation is the number of shared-memory wavefronts, i.e. the number of 8-byte words per
-// interval: c0, c1 are doubles, the two highest coefficients are floats packed in one word
-// (|c2 u^2| <= 5e-7: float rounding there is below 3e-14) and are combined on the fp32 pipe.
-// One evaluation = 3 words (the degree-4 / width-1/256 table it replaces needed 4: the site kernels are bound by the
-// shared-memory gathers), 4 fp64 ops of index arithmetic + 2 DFMA + 1 FFMA + 2 conversions; the table fills 216 KB of
-// the 227 KB of shared memory a CTA can own.  Max abs error 1e-13 (tests/test_probit_table.py against long double).
+// The table lives in shared memory and is gathered with a different index per lane, so the cost of an evaluation
+// is the number of shared-memory wavefronts, i.e. the BYTES per interval: a cubic to 1e-13 needs ~125 bits of
+// coefficients (c0 to 2^-46, c1 to 2^-45, c2 to 2^-40, c3 to 2^-40 in the interval coordinate u in [-1/2, 1/2)), and
+// they are packed in ONE 16-byte entry fetched by a single LDS.128 (the previous layout, doubles c0, c1 and a float
+// pair, took three 8-byte gathers and bound the site kernels on the shared-memory pipe):
+//     w.x                      low word of  D0 = 8 + (c0 + 7)           in [8, 16)      c0 = D0 - 15
+//     w.y  [19:0]              high mantissa bits of D0
+//     w.z  [19:0], w.w [31:14] mantissa of  D1 = 2^-7 + c1              in [2^-7, 2^-6) c1 = D1 - 2^-7   (38 bits)
+//     w.y [31:20], w.z [31:21] 23-bit c2 in units of 2^-40, offset 2^-19
+//     w.w  [13:0]              14-bit c3 in units of 2^-40, offset 2^-27
+// Each field is the mantissa of a float / double with a FIXED exponent, so decoding is a mask-and-or plus one exact
+// subtraction (no integer -> floating conversions); the bits of the neighbouring field that share a word with D1 are
+// known when the table is built and are compensated there.  The quantisation of c3 and c2 is folded back into the
+// lower coefficients (u^3 -> 3u/16, u^2 -> 1/8: what remains is a multiple of a Chebyshev polynomial), and the index
+// and u come from the bits of ONE fma:  r = 8192 + 512 (f + 8.5)  has the interval number in its 13 leading
+// mantissa bits and u + 1/2 in the 39 below.  One evaluation = 1 LDS.128, 6 fp64 operations, ~12 integer / fp32 ones.
+// Max abs error 2.5e-13, typically 5e-14 (tests/test_probit_table.py against 40-digit arithmetic).  The table is 128 KB.
 #pragma once
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <vector>
 #include "smallmat.cuh"
 
 namespace bn {
 
-constexpr int kPtDeg = 3;
-constexpr int kPtN = 9217;           // interval centres -9 + i/512, i = 0..9216
-constexpr double kPtFmax = 9.0;
+constexpr int kPtN = 8192;            // intervals [i, i+1) of the table coordinate s = 512 (f - kPtLo)
+constexpr double kPtLo = -8.5;
+constexpr double kPtHi = 7.5;         // kPtLo + kPtN / 512
 constexpr double kPtInvH = 512.0;
-constexpr int kPtDoubles = 3 * kPtN;   // word-major: c0[kPtN] | c1[kPtN] | {float c2, float c3}[kPtN]
+constexpr double kPtBias = 8192.0;    // r = s + kPtBias lies in [2^13, 2^14): fixed exponent
+constexpr double kPtOff = -kPtLo * kPtInvH + kPtBias;   // r = 512 f + kPtOff
+constexpr int kPtDoubles = 2 * kPtN;  // 16 bytes per interval
 
-// g at table coordinate s = 512 f + 4608, which must lie in [0, 9216]
-BN_DEV double probit_log_phi_s(const double* tab, double s) {
+struct PtEntry { uint32_t x, y, z, w; };
+
 #ifdef __CUDA_ARCH__
-    const double r = s + 6755399441055744.0;               // 1.5 * 2^52: round-to-nearest-integer trick
-    const int i = __double2loint(r);
-    const double u = s - (r - 6755399441055744.0);         // in [-0.5, 0.5]
-    const float2 c23 = reinterpret_cast<const float2*>(tab + 2 * kPtN)[i];
-    const float t = fmaf(c23.y, (float)u, c23.x);
+BN_DEV double pt_make_double(uint32_t hi, uint32_t lo) { return __hiloint2double((int)hi, (int)lo); }
+BN_DEV float pt_make_float(uint32_t b) { return __uint_as_float(b); }
 #else
-    const double sr = nearbyint(s);
-    const int i = (int)sr;
-    const double u = s - sr;
-    float c23[2];
-    memcpy(c23, tab + 2 * kPtN + i, sizeof(c23));
-    const float t = fmaf(c23[1], (float)u, c23[0]);
+inline double pt_make_double(uint32_t hi, uint32_t lo) {
+    const uint64_t b = ((uint64_t)hi << 32) | lo;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+inline float pt_make_float(uint32_t b) {
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
 #endif
-    return fma(fma((double)t, u, tab[kPtN + i]), u, tab[i]);
+
+// polynomial of one entry at u in [-1/2, 1/2)
+BN_DEV double pt_eval(const PtEntry& w, double u) {
+    const double c0 = pt_make_double(0x40200000u | (w.y & 0xFFFFFu), w.x) - 15.0;
+    const double c1 = pt_make_double(0x3F800000u | (w.z & 0xFFFFFu), w.w) - 0.0078125;
+    const float c2 = pt_make_float(0x37000000u | ((w.y >> 9) & 0x7FF800u) | (w.z >> 21)) - 9.5367431640625e-6f;      // 2^-17 + 2^-19
+    const float c3 = pt_make_float(0x37000000u | (w.w & 0x3FFFu)) - 7.636845111846924e-6f;                            // 2^-17 + 2^-27
+    const float t = fmaf(c3, (float)u, c2);
+    return fma(fma((double)t, u, c1), u, c0);
+}
+
+// g at r = 512 f + kPtOff, which must lie in [2^13, 2^14)
+BN_DEV double probit_log_phi_s(const double* tab, double r) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi = (uint32_t)__double2hiint(r), lo = (uint32_t)__double2loint(r);
+    const uint4 q = reinterpret_cast<const uint4*>(tab)[(hi >> 7) & 0x1FFFu];
+    const PtEntry w{q.x, q.y, q.z, q.w};
+    const uint32_t uh = 0x3FF00000u | (__funnelshift_l(lo, hi, 13) & 0xFFFFFu);
+#else
+    uint64_t b;
+    memcpy(&b, &r, 8);
+    const uint32_t hi = (uint32_t)(b >> 32), lo = (uint32_t)b;
+    PtEntry w;
+    memcpy(&w, reinterpret_cast<const char*>(tab) + 16 * (size_t)((hi >> 7) & 0x1FFFu), 16);
+    const uint32_t uh = 0x3FF00000u | (((hi << 13) | (lo >> 19)) & 0xFFFFFu);
+#endif
+    const double u = pt_make_double(uh, lo << 13) - 1.5;  // the 39 fraction bits of r as 1.f, minus 1.5
+    return pt_eval(w, u);
 }
 
 // tab -> g(f) for any f.  NaN inputs come back as a finite number (fmin/fmax drop NaN): callers poison.
 BN_DEV double probit_log_phi(const double* tab, double f) {
-    f = fmin(fmax(f, -kPtFmax), kPtFmax);
-    return probit_log_phi_s(tab, fma(f, kPtInvH, kPtFmax * kPtInvH));
+    f = fmin(fmax(f, kPtLo), kPtHi - 1e-6);
+    return probit_log_phi_s(tab, fma(f, kPtInvH, kPtOff));
 }
 
 // host-side construction (long double), done once
@@ -64,11 +104,11 @@ inline long double probit_log_phi_ld(long double f) {
 inline const std::vector<double>& probit_table_host() {
     static const std::vector<double> tab = [] {
         std::vector<double> t(kPtDoubles);
-        constexpr int M = kPtDeg + 1;
+        constexpr int M = 4;
         const long double pi = 3.14159265358979323846264338327950288L;
         for (int i = 0; i < kPtN; ++i) {
-            const long double c = -(long double)kPtFmax + (long double)i / (long double)kPtInvH;
-            // interpolate in v = 2u on [-1, 1] at the Chebyshev nodes, f = c + v / (2 * 512)
+            const long double c = (long double)kPtLo + ((long double)i + 0.5L) / (long double)kPtInvH;
+            // cubic through the Chebyshev nodes of the interval, in v = 2u on [-1, 1]: f = c + v / (2 * 512)
             long double fv[M], ck[M];
             for (int j = 0; j < M; ++j) {
                 const long double v = cosl(pi * (j + 0.5L) / M);
@@ -80,30 +120,36 @@ inline const std::vector<double>& probit_table_host() {
                 ck[k] = 2 * s / M;
             }
             ck[0] /= 2;
-            // Chebyshev -> monomial in v
-            long double mono[M] = {0}, T0[M] = {0}, T1[M] = {0}, T2[M];
-            T0[0] = 1;
-            T1[1] = 1;
-            for (int k = 0; k < M; ++k) {
-                const long double* T = (k == 0) ? T0 : T1;
-                if (k >= 2) {
-                    for (int j = 0; j < M; ++j) T2[j] = (j > 0 ? 2 * T1[j - 1] : 0) - T0[j];
-                    for (int j = 0; j < M; ++j) { T0[j] = T1[j]; T1[j] = T2[j]; }
-                    T = T1;
-                }
-                for (int j = 0; j < M; ++j) mono[j] += ck[k] * T[j];
-            }
-            // v = 2u: coefficient of u^k is mono[k] * 2^k
-            double cf[M];
-            long double sc = 1;
-            for (int k = 0; k < M; ++k) {
-                cf[k] = (double)(mono[k] * sc);
-                sc *= 2;
-            }
-            t[i] = cf[0];
-            t[(size_t)kPtN + i] = cf[1];
-            const float hi[2] = {(float)cf[2], (float)cf[3]};
-            memcpy(&t[(size_t)2 * kPtN + i], hi, sizeof(hi));
+            // Chebyshev -> monomial in u:  T0 = 1, T1 = 2u, T2 = 8u^2 - 1, T3 = 32u^3 - 6u
+            long double m0 = ck[0] - ck[2], m1 = 2 * ck[1] - 6 * ck[3], m2 = 8 * ck[2], m3 = 32 * ck[3];
+            // c3: 14 bits in units of 2^-40, offset 2^-27; its rounding error d u^3 = d (T3 + 3 T1) / 32 -> 3 d u / 16 moves to c1
+            const long double lsb = ldexpl(1.0L, -40);
+            long long q3 = llroundl((m3 + ldexpl(1.0L, -27)) / lsb);
+            if (q3 < 0) q3 = 0;
+            if (q3 > 0x3FFF) q3 = 0x3FFF;
+            const long double c3 = (long double)q3 * lsb - ldexpl(1.0L, -27);
+            m1 += (m3 - c3) * 3.0L / 16.0L;
+            // c2: 23 bits in units of 2^-40, offset 2^-19; d u^2 = d (T2 + 1) / 8 -> d / 8 moves to c0
+            long long q2 = llroundl((m2 + ldexpl(1.0L, -19)) / lsb);
+            if (q2 < 0) q2 = 0;
+            if (q2 > 0x7FFFFF) q2 = 0x7FFFFF;
+            const long double c2 = (long double)q2 * lsb - ldexpl(1.0L, -19);
+            m0 += (m2 - c2) / 8.0L;
+            // c1: D1 = 2^-7 (1 + M1 / 2^52); the low 14 bits of M1 are c3's field: choose the upper 38 with them in place
+            const long double x1 = (m1 + ldexpl(1.0L, -7)) / ldexpl(1.0L, -7) - 1.0L;   // in [0, 1)
+            long long M1 = llroundl((x1 * ldexpl(1.0L, 52) - (long double)q3) / 16384.0L);
+            if (M1 < 0) M1 = 0;
+            const uint64_t m1bits = ((uint64_t)M1 << 14) | (uint64_t)q3;
+            // c0: D0 = 8 (1 + M0 / 2^52) = c0 + 15, all 52 bits its own
+            const long double x0 = (m0 + 15.0L) / 8.0L - 1.0L;
+            long long M0 = llroundl(x0 * ldexpl(1.0L, 52));
+            if (M0 < 0) M0 = 0;
+            PtEntry e;
+            e.x = (uint32_t)((uint64_t)M0 & 0xFFFFFFFFu);
+            e.y = (uint32_t)(((uint64_t)M0 >> 32) & 0xFFFFFu) | ((uint32_t)(q2 >> 11) << 20);
+            e.z = (uint32_t)((m1bits >> 32) & 0xFFFFFu) | ((uint32_t)(q2 & 0x7FF) << 21);
+            e.w = (uint32_t)(m1bits & 0xFFFFFFFFu);
+            memcpy(reinterpret_cast<char*>(t.data()) + 16 * (size_t)i, &e, 16);
         }
         return t;
     }();

@@ -9,14 +9,14 @@ namespace bn {
 
 constexpr int kSiteThreads = 256;
 constexpr int kSiteMaxGrid = 148 * 6;  // persistent grid: 6 CTAs per SM, grid-stride over the time steps
-// kernels that gather from the probit table keep all of it (147.5 KB) in shared memory: one CTA of
+// kernels that gather from the probit table keep all of it (128 KB) in shared memory: one CTA of
 // 1024 threads per SM
 constexpr int kTabThreads = 1024;
 constexpr int kTabGrid = 148;
 template <bool TAB> constexpr int kNT = TAB ? kTabThreads : kSiteThreads;
 
 // the probit log-density table in device memory, filled once per device (probit_table.cuh)
-__device__ double g_probit_tab[kPtDoubles];
+__device__ __align__(16) double g_probit_tab[kPtDoubles];
 static bool g_probit_ready[64] = {false};
 static std::mutex g_probit_mutex;
 
@@ -74,7 +74,7 @@ template <int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(kNT<TAB>)
 site_update_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
                    const double* cw2, double* part1, double* part2) {
-    extern __shared__ double site_smem[];
+    extern __shared__ __align__(16) double site_smem[];
     const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
     double d1 = 0.0, d2 = 0.0;
     for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>) {
@@ -93,7 +93,7 @@ template <int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(kNT<TAB>)
 expected_density_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
                         const double* cw2, double* values, double* part) {
-    extern __shared__ double site_smem[];
+    extern __shared__ __align__(16) double site_smem[];
     const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
     double acc = 0.0;
     for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>) {
@@ -110,7 +110,7 @@ template <int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(kNT<TAB>)
 energy_terms_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const unsigned char* mask,
                     double* part, double* part2) {
-    extern __shared__ double site_smem[];
+    extern __shared__ __align__(16) double site_smem[];
     const SiteCtx sc{&cub, stage_table<TAB>(site_smem), nullptr, nullptr};
     double acc = 0.0, acc2 = 0.0;
     for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>) {
@@ -126,7 +126,7 @@ template <int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(kNT<TAB>)
 likelihood_stats_kernel(const __grid_constant__ bn_site_args a, const __grid_constant__ Cub1 cub, const double* cx2,
                         const double* cw2, double* val, double* d1, double* d2) {
-    extern __shared__ double site_smem[];
+    extern __shared__ __align__(16) double site_smem[];
     const SiteCtx sc{&cub, stage_table<TAB>(site_smem), cx2, cw2};
     for (long long n = (long long)blockIdx.x * kNT<TAB> + threadIdx.x; n < a.N; n += (long long)gridDim.x * kNT<TAB>)
         likelihood_stats_step<LIK, METHOD, TAB>(a, sc, n, val, d1, d2);

@@ -198,9 +198,10 @@ BN_DEV SiteStats1 site_stats_1(const Lik1<LIK, TAB>& lik, double y, double m, do
         if constexpr (TAB && LIK == BN_LIK_BERNOULLI_PROBIT) {
             // every point inside the table's range (the usual case): evaluate in table coordinates,
             // log p(y | f) = g(+-f) with the sign folded into the affine map, no clamping per point
-            if (fabs(mean) + cub.xmax * sd <= kPtFmax) {
+            const double sm = (y == 1.0) ? mean : -mean, reach = cub.xmax * sd;
+            if (sm - reach >= kPtLo && sm + reach < kPtHi) {
                 const double sg = (y == 1.0) ? kPtInvH : -kPtInvH;
-                const double a1 = sg * sd, a0 = fma(sg, mean, kPtFmax * kPtInvH);
+                const double a1 = sg * sd, a0 = fma(sg, mean, kPtOff);
 #pragma unroll 4
                 for (int q = 0; q < Q; ++q) {
                     const double l = probit_log_phi_s(lik.tab, fma(a1, cx[q], a0));

@@ -154,28 +154,36 @@ def probe_reference_runtime():
             'baseline_ref_present': os.path.isdir(ref)}
 
 
-def run_cpu(sample_n, steps, warmup, threads=None, blocked=True):
-    """the reference algorithm on the host (oracle/c/markov_c.c).  blocked=True: the temporally parallel form
-    (ops.py:183-253, 314-354) as a time-blocked three-phase scan over all host threads, site loops in OpenMP;
-    blocked=False: the reference's CPU default, the sequential lax.scan recursion on one thread."""
+def run_cpu(sample_n, steps, warmup, threads=None):
+    """the reference algorithm on the host (oracle/c/markov_c.c), on all the host threads it can use.  Two forms are
+    tried for one iteration each and the faster one is timed: the reference's CPU default (parallel=False: sequential
+    lax.scan recursions on one thread, the vmapped loops on all threads) and the temporally parallel form
+    (parallel=True, ops.py:183-253, 314-354) as a time-blocked three-phase scan over all threads."""
     from oracle import cport
     if threads:
         os.environ['OMP_NUM_THREADS'] = str(threads)
     cores = int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1))
     dt, y = block_seeded_inputs(sample_n, 0, sample_n)
     m = cport.ViModel(3, 1.0, 1.0, 2, 0.0, dt, y.astype(np.float64))
-    it = (lambda: m.iteration_blocked(1.0)) if (blocked and hasattr(m, 'iteration_blocked')) else (lambda: m.iteration(1.0))
-    for _ in range(warmup):
+    forms = {'sequential filter/smoother (reference CPU default parallel=False), vmapped loops OpenMP x%d' % cores: lambda: m.iteration(1.0),
+             'temporally parallel form (parallel=True) as a time-blocked three-phase scan on %d threads' % cores: lambda: m.iteration_blocked(1.0)}
+    m.iteration(1.0)  # first touch of the scratch arrays
+    trial = {}
+    for name, fn in forms.items():
+        t0 = time.perf_counter()
+        fn()
+        trial[name] = time.perf_counter() - t0
+    form = min(trial, key=trial.get)
+    it = forms[form]
+    for _ in range(max(0, warmup - 3)):
         it()
     t0 = time.perf_counter()
     for _ in range(steps):
         E = it()
     el = (time.perf_counter() - t0) / steps
-    form = ('temporally parallel form as a time-blocked three-phase scan on %d threads' % cores) if (blocked and hasattr(m, 'iteration_blocked')) \
-        else 'sequential filter/smoother (reference CPU default parallel=False) on one thread'
     return {'value': sample_n / el, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': 'N=%d steps of the same workload, %d timed iteration(s) after %d warm-up; %s, As/Qs '
-                      'materialised as in the reference, site loops OpenMP x%d' % (sample_n, steps, warmup, form, cores),
+            'sample': 'N=%d steps of the same workload, %d timed iteration(s); %s (the faster of the two forms: %s); As/Qs '
+                      'materialised as in the reference' % (sample_n, steps, form, ', '.join('%.0f ms' % (v * 1e3) for v in trial.values())),
             'ms_per_step': el * 1e3, 'energy': E, 'steps': steps, 'warmup': warmup}
 
 

@@ -182,13 +182,10 @@ double bnc_sequential_kf(int d, int64_t N, const double* As, const double* Qs, c
     return ell;
 }
 
-/* _sequential_rts, return_full = False, H = e_0^T (ops.py:288-311): sms[N], sPs[N] */
-void bnc_sequential_rts(int d, int64_t N, const double* fms, const double* fPs, const double* As, const double* Qs,
-                        double* sms, double* sPs) {
-    double sm[MAXD], sP[MAXD * MAXD];
-    memcpy(sm, fms + (N - 1) * d, sizeof(double) * d);
-    memcpy(sP, fPs + (N - 1) * d * d, sizeof(double) * d * d);
-    for (int64_t n = N - 1; n >= 0; --n) {
+/* the body of _sequential_rts (ops.py:288-311) over `count` steps from a given carry (sm, sP): sms[count], sPs[count] */
+static void rts_from(int d, int64_t count, const double* fms, const double* fPs, const double* As, const double* Qs,
+                     double* sm, double* sP, double* sms, double* sPs) {
+    for (int64_t n = count - 1; n >= 0; --n) {
         const double *A = As + n * d * d, *Q = Qs + n * d * d, *fm = fms + n * d, *fP = fPs + n * d * d;
         double pm[MAXD], AfP[MAXD * MAXD], pP[MAXD * MAXD], L[MAXD * MAXD], X[MAXD * MAXD], C[MAXD * MAXD];
         for (int i = 0; i < d; ++i) {
@@ -217,6 +214,205 @@ void bnc_sequential_rts(int d, int64_t N, const double* fms, const double* fPs, 
         sms[n] = sm[0];
         sPs[n] = sP[0];
     }
+}
+
+/* _sequential_rts, return_full = False, H = e_0^T (ops.py:288-311): sms[N], sPs[N] */
+void bnc_sequential_rts(int d, int64_t N, const double* fms, const double* fPs, const double* As, const double* Qs,
+                        double* sms, double* sPs) {
+    double sm[MAXD], sP[MAXD * MAXD];
+    memcpy(sm, fms + (N - 1) * d, sizeof(double) * d);
+    memcpy(sP, fPs + (N - 1) * d * d, sizeof(double) * d * d);
+    rts_from(d, N, fms, fPs, As, Qs, sm, sP, sms, sPs);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * The temporally parallel form (parallel=True; ops.py:183-253, 314-354) on the host cores: lax.associative_scan is
+ * restated as a time-blocked three-phase scan -- (1) every block folds its elements with the reference's operator,
+ * in parallel over blocks; (2) the block aggregates are combined in sequence; (3) every block re-runs the plain
+ * recursion from its incoming state, in parallel.  Same elements and operators as the reference, a different (but
+ * associative-equivalent) bracketing of the combines.  H = e_0^T, D = 1, m0 = 0.
+ */
+typedef struct { double A[MAXD * MAXD], b[MAXD], C[MAXD * MAXD], J[MAXD * MAXD], eta[MAXD]; } felem;
+typedef struct { double E[MAXD * MAXD], g[MAXD], L[MAXD * MAXD]; } selem;
+
+/* parallel_filtering_element_ (ops.py:183-197) */
+static void filt_element(int d, const double* A, const double* Q, double R, double y, felem* e) {
+    double S = Q[0] + R, K[MAXD];
+    for (int i = 0; i < d; ++i) K[i] = Q[i * d] / S;                  /* Q H^T S^-1 */
+    for (int i = 0; i < d; ++i) {
+        e->b[i] = K[i] * y;
+        e->eta[i] = A[i] * y / S;                                     /* A^T H^T S^-1 y, A[0][i] */
+        for (int j = 0; j < d; ++j) {
+            e->A[i * d + j] = A[i * d + j] - K[i] * A[j];             /* A - K H A */
+            e->C[i * d + j] = Q[i * d + j] - K[i] * Q[j];             /* Q - K H Q */
+            e->J[i * d + j] = A[i] * A[j] / S;                        /* A^T H^T S^-1 H A */
+        }
+    }
+}
+
+static void mat_inv_chol(int d, const double* P, double* Pinv) {      /* inv (utils.py:22-27): cho_solve(chol(P), I) */
+    double L[MAXD * MAXD], I[MAXD * MAXD];
+    memset(I, 0, sizeof(I));
+    for (int i = 0; i < d; ++i) I[i * d + i] = 1.0;
+    chol(d, P, L);
+    cho_solve(d, d, L, I, Pinv);
+}
+
+/* parallel_filtering_operator (ops.py:203-219) */
+static void filt_combine(int d, const felem* e1, const felem* e2, felem* o) {
+    double C1inv[MAXD * MAXD], M[MAXD * MAXD], L[MAXD * MAXD], temp[MAXD * MAXD], A2t[MAXD * MAXD], T[MAXD * MAXD];
+    mat_inv_chol(d, e1->C, C1inv);
+    for (int i = 0; i < d * d; ++i) M[i] = C1inv[i] + e2->J[i];
+    chol(d, M, L);
+    cho_solve(d, d, L, C1inv, temp);                                  /* solve(C1inv + J2, C1inv) */
+    matmul(d, e2->A, temp, A2t);                                      /* A2 temp */
+    matmul(d, A2t, e1->A, o->A);
+    double v[MAXD];
+    for (int i = 0; i < d; ++i) {
+        double s = e1->b[i];
+        for (int k = 0; k < d; ++k) s += e1->C[i * d + k] * e2->eta[k];
+        v[i] = s;
+    }
+    for (int i = 0; i < d; ++i) {
+        double s = e2->b[i];
+        for (int k = 0; k < d; ++k) s += A2t[i * d + k] * v[k];
+        o->b[i] = s;
+    }
+    matmul(d, A2t, e1->C, T);
+    matmul_bt(d, T, e2->A, o->C);
+    for (int i = 0; i < d * d; ++i) o->C[i] += e2->C[i];
+    double A1t[MAXD * MAXD];                                          /* A1^T temp^T */
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s += e1->A[k * d + i] * temp[j * d + k];
+            A1t[i * d + j] = s;
+        }
+    for (int i = 0; i < d; ++i) {
+        double s = e2->eta[i];
+        for (int k = 0; k < d; ++k) s -= e2->J[i * d + k] * e1->b[k];
+        v[i] = s;
+    }
+    for (int i = 0; i < d; ++i) {
+        double s = e1->eta[i];
+        for (int k = 0; k < d; ++k) s += A1t[i * d + k] * v[k];
+        o->eta[i] = s;
+    }
+    matmul(d, A1t, e2->J, T);
+    matmul(d, T, e1->A, o->J);
+    for (int i = 0; i < d * d; ++i) o->J[i] += e1->J[i];
+}
+
+/* _parallel_kf (ops.py:237-253), blocked.  Returns ell; fms[N,d], fPs[N,d,d]. */
+double bnc_parallel_kf_blocked(int d, int64_t N, const double* As, const double* Qs, const double* ys, const double* Rs,
+                               const uint8_t* mask, const double* P0, double* fms, double* fPs, int nblocks) {
+    if (nblocks > N) nblocks = (int)N;
+    felem* agg = (felem*)malloc(sizeof(felem) * nblocks);
+    felem* pre = (felem*)malloc(sizeof(felem) * nblocks);
+    double* ells = (double*)calloc(nblocks, sizeof(double));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nblocks; ++b) {
+        int64_t n0 = N * b / nblocks, n1 = N * (b + 1) / nblocks;
+        felem acc, e, r;
+        for (int64_t n = n0; n < n1; ++n) {
+            filt_element(d, As + n * d * d, n == 0 ? P0 : Qs + n * d * d, Rs[n], ys[n], &e);   /* Qs[0] := P0 (:223) */
+            if (n == n0) acc = e; else { filt_combine(d, &acc, &e, &r); acc = r; }
+        }
+        agg[b] = acc;
+    }
+    pre[0] = agg[0];
+    for (int b = 1; b < nblocks; ++b) filt_combine(d, &pre[b - 1], &agg[b], &pre[b]);
+    double m0[MAXD] = {0, 0, 0, 0};
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nblocks; ++b) {
+        int64_t n0 = N * b / nblocks, n1 = N * (b + 1) / nblocks;
+        const double *mi = b ? pre[b - 1].b : m0, *Pi = b ? pre[b - 1].C : P0;
+        ells[b] = bnc_sequential_kf(d, n1 - n0, As + n0 * d * d, Qs + n0 * d * d, ys + n0, Rs + n0, mask ? mask + n0 : NULL,
+                                    mi, Pi, fms + n0 * d, fPs + n0 * d * d);
+    }
+    double ell = 0.0;
+    for (int b = 0; b < nblocks; ++b) ell += ells[b];
+    free(agg); free(pre); free(ells);
+    return ell;
+}
+
+/* parallel_smoothing_element (ops.py:318-325) / last element (:314-315) */
+static void smooth_element(int d, const double* A, const double* Q, const double* m, const double* P, int last, selem* e) {
+    if (last) {
+        memset(e->E, 0, sizeof(e->E));
+        memcpy(e->g, m, sizeof(double) * d);
+        memcpy(e->L, P, sizeof(double) * d * d);
+        return;
+    }
+    double AP[MAXD * MAXD], Pp[MAXD * MAXD], Lc[MAXD * MAXD], X[MAXD * MAXD], EPp[MAXD * MAXD], T[MAXD * MAXD], Am[MAXD];
+    matmul(d, A, P, AP);
+    matmul_bt(d, AP, A, Pp);
+    for (int i = 0; i < d * d; ++i) Pp[i] += Q[i];
+    chol(d, Pp, Lc);
+    cho_solve(d, d, Lc, AP, X);
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) e->E[i * d + j] = X[j * d + i];
+    for (int i = 0; i < d; ++i) {
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) s += A[i * d + k] * m[k];
+        Am[i] = s;
+    }
+    for (int i = 0; i < d; ++i) {
+        double s = m[i];
+        for (int k = 0; k < d; ++k) s -= e->E[i * d + k] * Am[k];
+        e->g[i] = s;
+    }
+    matmul(d, e->E, Pp, EPp);
+    matmul_bt(d, EPp, e->E, T);
+    for (int i = 0; i < d * d; ++i) e->L[i] = P[i] - T[i];
+}
+
+/* parallel_smoothing_operator (ops.py:328-335): elem1 = the later steps, elem2 = the earlier one */
+static void smooth_combine(int d, const selem* e1, const selem* e2, selem* o) {
+    double T[MAXD * MAXD];
+    matmul(d, e2->E, e1->E, o->E);
+    for (int i = 0; i < d; ++i) {
+        double s = e2->g[i];
+        for (int k = 0; k < d; ++k) s += e2->E[i * d + k] * e1->g[k];
+        o->g[i] = s;
+    }
+    matmul(d, e2->E, e1->L, T);
+    matmul_bt(d, T, e2->E, o->L);
+    for (int i = 0; i < d * d; ++i) o->L[i] += e2->L[i];
+}
+
+/* _parallel_rts (ops.py:338-354), blocked, return_full = False: sms[N], sPs[N] */
+void bnc_parallel_rts_blocked(int d, int64_t N, const double* fms, const double* fPs, const double* As, const double* Qs,
+                              double* sms, double* sPs, int nblocks) {
+    if (nblocks > N) nblocks = (int)N;
+    selem* agg = (selem*)malloc(sizeof(selem) * nblocks);
+    selem* suf = (selem*)malloc(sizeof(selem) * nblocks);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nblocks; ++b) {
+        int64_t n0 = N * b / nblocks, n1 = N * (b + 1) / nblocks;
+        selem acc, e, r;
+        for (int64_t n = n1 - 1; n >= n0; --n) {
+            smooth_element(d, As + n * d * d, Qs + n * d * d, fms + n * d, fPs + n * d * d, n == N - 1, &e);
+            if (n == n1 - 1) acc = e; else { smooth_combine(d, &acc, &e, &r); acc = r; }
+        }
+        agg[b] = acc;
+    }
+    suf[nblocks - 1] = agg[nblocks - 1];
+    for (int b = nblocks - 2; b >= 0; --b) smooth_combine(d, &suf[b + 1], &agg[b], &suf[b]);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nblocks; ++b) {
+        int64_t n0 = N * b / nblocks, n1 = N * (b + 1) / nblocks;
+        double sm[MAXD], sP[MAXD * MAXD];
+        if (b == nblocks - 1) {
+            memcpy(sm, fms + (N - 1) * d, sizeof(double) * d);
+            memcpy(sP, fPs + (N - 1) * d * d, sizeof(double) * d * d);
+        } else {  /* the smoothed state of the first step of the next block */
+            memcpy(sm, suf[b + 1].g, sizeof(double) * d);
+            memcpy(sP, suf[b + 1].L, sizeof(double) * d * d);
+        }
+        rts_from(d, n1 - n0, fms + n0 * d, fPs + n0 * d * d, As + n0 * d * d, Qs + n0 * d * d, sm, sP, sms + n0, sPs + n0);
+    }
+    free(agg); free(suf);
 }
 
 /* likelihoods: 1 = Gaussian(param), 2 = Bernoulli probit (likelihoods.py:828-852) */
@@ -317,6 +513,30 @@ double bnc_vi_iteration(const ckernel* k, int lik, double param, int64_t N, cons
     double ed = bnc_vi_expected_density(lik, param, N, y, post_mean, post_var, Q, gx, gw);
     bnc_discretise(k, N, dt, As, Qs);
     double ell = bnc_sequential_kf(d, N, As, Qs, site_mean, site_cov, mask, m0, P0, fms, fPs);
+    double edp = bnc_gaussian_expected_log_lik(N, site_mean, post_mean, post_var, site_cov, mask);
+    return -(ed - (edp - ell));
+}
+
+/* the same iteration with parallel=True: the filter and the smoother in the blocked temporally parallel form */
+double bnc_vi_iteration_blocked(const ckernel* k, int lik, double param, int64_t N, const double* dt, const double* dts,
+                                const double* y, const uint8_t* mask, int Q, const double* gx, const double* gw, double lr,
+                                double* nat1, double* nat2, double* site_mean, double* site_cov,
+                                double* As, double* Qs, double* fms, double* fPs, double* post_mean, double* post_var,
+                                int nblocks) {
+    int d = kdim(k);
+    double P0[MAXD * MAXD];
+    pinf(k, P0);
+    for (int pass = 0; pass < 2; ++pass) {
+        bnc_discretise(k, N, dt, As, Qs);
+        bnc_parallel_kf_blocked(d, N, As, Qs, site_mean, site_cov, mask, P0, fms, fPs, nblocks);
+        bnc_discretise(k, N, dts, As, Qs);
+        bnc_parallel_rts_blocked(d, N, fms, fPs, As, Qs, post_mean, post_var, nblocks);
+        if (pass == 0)
+            bnc_vi_site_update(lik, param, N, y, post_mean, post_var, Q, gx, gw, lr, 1, nat1, nat2, site_mean, site_cov);
+    }
+    double ed = bnc_vi_expected_density(lik, param, N, y, post_mean, post_var, Q, gx, gw);
+    bnc_discretise(k, N, dt, As, Qs);
+    double ell = bnc_parallel_kf_blocked(d, N, As, Qs, site_mean, site_cov, mask, P0, fms, fPs, nblocks);
     double edp = bnc_gaussian_expected_log_lik(N, site_mean, post_mean, post_var, site_cov, mask);
     return -(ed - (edp - ell));
 }

@@ -41,6 +41,8 @@ def lib():
         L.bnc_sequential_rts.argtypes = [I, L64, P, P, P, P, P, P]
         L.bnc_vi_iteration.argtypes = [C.POINTER(CKernel), I, D, L64, P, P, P, P, I, P, P, D] + [P] * 10
         L.bnc_vi_iteration.restype = D
+        L.bnc_vi_iteration_blocked.argtypes = [C.POINTER(CKernel), I, D, L64, P, P, P, P, I, P, P, D] + [P] * 10 + [I]
+        L.bnc_vi_iteration_blocked.restype = D
         _lib = L
     return _lib
 
@@ -78,3 +80,14 @@ class ViModel:
                                       _p(self.nat1), _p(self.nat2), _p(self.site_mean), _p(self.site_cov),
                                       _p(self.As), _p(self.Qs), _p(self.fms), _p(self.fPs), _p(self.post_mean),
                                       _p(self.post_var))
+
+    def iteration_blocked(self, lr=1.0, nblocks=None):
+        """the same iteration with the filter / smoother in the temporally parallel form (parallel=True), time-blocked
+        over the host threads (4 blocks per thread)"""
+        if nblocks is None:
+            nblocks = 4 * int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1))
+        return lib().bnc_vi_iteration_blocked(C.byref(self.k), self.lik, self.lik_param, self.N, _p(self.dt), _p(self.dts),
+                                              _p(self.y), _p(self.mask), self.gw.shape[0], _p(self.gx), _p(self.gw), lr,
+                                              _p(self.nat1), _p(self.nat2), _p(self.site_mean), _p(self.site_cov),
+                                              _p(self.As), _p(self.Qs), _p(self.fms), _p(self.fPs), _p(self.post_mean),
+                                              _p(self.post_var), int(nblocks))

@@ -20,7 +20,8 @@ def test_table_accuracy(emu):
                         -9 + (np.arange(576) + 0.5) / 32.0, [-1e3, 1e3, -9.0, 9.0, 0.0]])
     got = np.array([emu.emu_probit_log_phi(float(x)) for x in f])
     err = np.abs(got - g_ref(f).astype(np.float64))
-    assert err.max() < 2e-13, err.max()  # cubic interpolant on width 1/512 + fp32 rounding of the two highest coefficients
+    assert err.max() < 2.5e-13, err.max()  # cubic interpolant on width 1/512, packed 16-byte coefficients, fp32 Horner of the two highest
+    assert np.sqrt(np.mean(err ** 2)) < 5e-14
     # symmetry used by the kernels: log(1 - p(f)) = g(-f)
     p = 0.5 * (1 + special.erf(f / np.sqrt(2))) * (1 - 2e-3) + 1e-3
-    assert np.abs(np.log(1 - p) - np.array([emu.emu_probit_log_phi(float(-x)) for x in f])).max() < 2e-13
+    assert np.abs(np.log(1 - p) - np.array([emu.emu_probit_log_phi(float(-x)) for x in f])).max() < 2.5e-13
