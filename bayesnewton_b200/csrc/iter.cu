@@ -1,8 +1,18 @@
 // C ABI of the fused inference iteration on chunk-tiled state (include/bn_b200.h: bn_iter_*).
 // Kernels: iter_impl.cuh, instantiated per Matern family in iter_m12.cu .. iter_m72.cu.
+#include <cstdlib>
 #include "iter_impl.cuh"
 
 namespace bn {
+// BN_B200_SPEC_FILTER=0 keeps phase 1 a pure reduction (A/B validation of the speculative filter pass)
+static bool spec_filter_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("BN_B200_SPEC_FILTER");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 int it_group_m12(const ItCall&);
 int it_group_m32(const ItCall&);
 int it_group_m52(const ItCall&);
@@ -61,6 +71,8 @@ static int it_make_call(const bn_kernel_spec* k, const bn_iter_args* a, int mode
     c.phase = phase;
     c.rank = a->rank;
     c.world = a->world;
+    c.spec_filter = spec_filter_enabled() ? 1 : 0;
+    c.want_ell = a->want_ell;
     if (back && mode != BN_ITER_PLAIN) {
         BN_REQUIRE(a->y_t != nullptr, "y_t is null");
         BN_REQUIRE(a->method == BN_METHOD_VI || a->method == BN_METHOD_NEWTON, "the fused epilogues cover VI and Newton, got method %d", a->method);
@@ -132,6 +144,7 @@ extern "C" int bn_iter_pass(const bn_kernel_spec* k, const bn_iter_args* a, int 
     if (int rc = it_make_call(k, a, mode, UP_ALL, cub, c)) return rc;
     BN_REQUIRE(a->world == 1 && a->rank == 0, "bn_iter_pass runs one shard; use the bn_iter_shard_* phases for world %d", a->world);
     c.ell = ell;
+    c.want_ell = (ell != nullptr);
     c.sums = sums;
     c.ws = workspace;
     c.ws_bytes = workspace_bytes;
@@ -158,6 +171,7 @@ extern "C" int bn_iter_shard_filter(const bn_kernel_spec* k, const bn_iter_args*
     ItCall c;
     if (int rc = it_make_call(k, a, BN_ITER_PLAIN, UP_FILTER, cub, c)) return rc;
     BN_REQUIRE(kf_carries && rts_carry, "null carry array");
+    BN_REQUIRE((ell != nullptr) == (a->want_ell != 0), "want_ell of the argument block must say whether ell is requested");
     c.carries = kf_carries;
     c.carry_out = rts_carry;
     c.ell = ell;

@@ -72,10 +72,104 @@ BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks
     Alg::store(agg, nchunks, c, el);
 }
 
+// phase 1 with speculation.  The sensitivity A of a chunk aggregate to the state entering the chunk decays
+// geometrically (the filter forgets); once every |A_ij| (in units of the stationary standard deviations) is below 2^-100
+// the incoming state can no longer change anything at fp64 resolution: J and eta stop moving, and (b, C) IS the
+// filtered state of every later step whatever the chunk started from.  From there on the pass runs the plain filter
+// step on (b, C), writes the filtered states and sums the log-likelihood itself, and phase 3 only has to redo the
+// steps before the switch.  For chunks much longer than the forgetting time (N = 1e8: 1320 steps against ~160) that
+// removes most of the second pass over the inputs; for short chunks the switch never happens and phase 3 does what it
+// always did.  The switch is taken by all 32 lanes of a warp together (the tiled layout needs them on the same step).
+constexpr double kSpecThreshold = 7.888609052210118e-31;  // 2^-100
+
+template <class G, bool WANT_ELL>
+struct SpecReduce {
+    static constexpr int d = G::d, nf = G::d + symn(G::d);
+    using Alg = FilterAlg<G::d>;
+    typename Alg::Elem el;
+    const double *pdt, *py, *pR;
+    const unsigned char* pk;
+    double* pf;
+    double Abn[G::kBlockA], yn, Rn, hn, ell, isd[G::d], sd[G::d];
+    int cnt;
+
+    BN_DEV void init(const G& g, const ItIO& io, int L, double* fs, long long c, bool active) {
+        Alg::identity(el);
+        ell = 0.0;
+        const long long k0 = c * L, rem = io.N - k0;
+        cnt = active ? (rem < L ? (int)rem : L) : 0;
+        const long long b = tl_base(c, L);
+        pdt = io.dt + b;
+        py = io.sy + b;
+        pR = io.sR + b;
+        pk = io.mask ? io.mask + b : nullptr;
+        pf = fs + fs_index(c, L, 0, 0, nf);
+        double P[symn(d)];
+        g.pinf_full(P);
+#pragma unroll
+        for (int i = 0; i < d; ++i) {
+            sd[i] = sqrt(P[sidx(i, i)]);
+            isd[i] = kSpecThreshold / sd[i];
+        }
+        if (active) {
+            g.trans(pdt[0], Abn);
+            yn = py[0]; Rn = pR[0]; hn = pdt[32];
+        } else {
+#pragma unroll
+            for (int i = 0; i < G::kBlockA; ++i) Abn[i] = 0.0;
+            yn = Rn = hn = 0.0;
+        }
+    }
+    BN_DEV void advance(const G& g, double* y, double* R, double* Ab) {
+        y[0] = yn; R[0] = Rn;
+#pragma unroll
+        for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
+        const double h1 = hn;
+        py += 32; pR += 32; pdt += 32;
+        yn = py[0]; Rn = pR[0]; hn = pdt[32];
+        g.trans(h1, Abn);
+    }
+    // folds one step into the aggregate; true when the aggregate no longer depends on the incoming state
+    BN_DEV bool absorb(const G& g, bool first) {
+        double y[1], R[1], Ab[G::kBlockA];
+        advance(g, y, R, Ab);
+        fkf_absorb<G>(g, el, Ab, y, R, first);
+        if (pk) pk += 32;
+        pf += nf * 32;
+        bool dec = true;
+#pragma unroll
+        for (int i = 0; i < d; ++i)
+#pragma unroll
+            for (int j = 0; j < d; ++j) dec = dec && (fabs(el.A[i * d + j]) * sd[j] <= isd[i] * (sd[i] * sd[i]));
+        return dec;
+    }
+    // (b, C) of the aggregate after the filter phase (same SoA layout as FilterAlg::store)
+    BN_DEV void store_state(double* agg, long long stride, long long c) const {
+        double* p = agg + c + (long long)(d * d) * stride;
+#pragma unroll
+        for (int k = 0; k < d; ++k) p[k * stride] = el.b[k];
+#pragma unroll
+        for (int k = 0; k < symn(d); ++k) p[(d + k) * stride] = el.C[k];
+    }
+    // one plain filter step on (b, C): the filtered state of this step, stored; log-likelihood increment
+    BN_DEV void filter(const G& g) {
+        double y[1], R[1], Ab[G::kBlockA], mp[d], Pp[symn(d)];
+        unsigned char mk[1] = {0};
+        if (pk) { mk[0] = pk[0]; pk += 32; }
+        advance(g, y, R, Ab);
+        ell += fkf_step<G, WANT_ELL>(g, el.b, el.C, Ab, y, R, pk ? mk : nullptr, mp, Pp);
+#pragma unroll
+        for (int f = 0; f < d; ++f) pf[f * 32] = el.b[f];
+#pragma unroll
+        for (int f = 0; f < symn(d); ++f) pf[(d + f) * 32] = el.C[f];
+        pf += nf * 32;
+    }
+};
+
 // phase 3: plain filter from the chunk's incoming state; filtered states -> scratch, log-likelihood partial
 template <class G, bool WANT_ELL>
 BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, const double* prefix,
-                            const double* s0, double* fs, double* ell_partials, long long c) {
+                            const double* s0, double* fs, double* ell_partials, long long c, const int* jst = nullptr) {
     constexpr int d = G::d;
     using Alg = FilterAlg<d>;
     typename Alg::State s;
@@ -92,7 +186,8 @@ BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks
     }
     double ell = 0.0;
     const long long k0 = c * L, rem = io.N - k0;
-    const int cnt = rem < L ? (int)rem : L;
+    // with a speculative phase 1 only the steps before its switch are left (their states depend on the incoming one)
+    const int cnt = jst ? jst[c] : (rem < L ? (int)rem : L);
     const long long b = tl_base(c, L);
     const double* pdt = io.dt + b;
     const double* py = io.sy + b;
@@ -289,9 +384,53 @@ it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, double* a
 template <class G, bool WANT_ELL>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
 it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const double* prefix, const double* s0, double* fs,
-                 double* ell_partials) {
+                 double* ell_partials, const int* jst) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
-    if (c < nchunks) it_filter_chunk<G, WANT_ELL>(g, io, L, nchunks, is_first, prefix, s0, fs, ell_partials, c);
+    if (c < nchunks) it_filter_chunk<G, WANT_ELL>(g, io, L, nchunks, is_first, prefix, s0, fs, ell_partials, c, jst);
+}
+
+// phase 1 with speculation (SpecReduce): every lane of a warp takes part in the vote, chunk or not
+template <class G, bool WANT_ELL>
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+it_reduce_spec_kernel(G g, ItIO io, int L, long long nchunks, int is_first, double* agg, double* fs, double* ell_partials,
+                      int* jst) {
+    const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    const bool active = c < nchunks;
+    SpecReduce<G, WANT_ELL> sr;
+    sr.init(g, io, L, fs, active ? c : 0, active);
+    int j = 0;
+    bool all_dec = false;
+#pragma unroll 1
+    while (!all_dec) {
+        bool dec = true;
+        if (j < sr.cnt) dec = sr.absorb(g, is_first && c == 0 && j == 0);
+        ++j;
+        all_dec = __all_sync(0xffffffffu, dec);
+    }
+    const int jstar = j < sr.cnt ? j : sr.cnt;
+    // A, J, eta are final here: the whole aggregate goes out now, and the filter phase keeps only (b, C) in registers
+    if (active) FilterAlg<G::d>::store(agg, nchunks, c, sr.el);
+#pragma unroll 1
+    for (; j < sr.cnt; ++j) sr.filter(g);
+    if (active) {
+        if (jstar < sr.cnt) sr.store_state(agg, nchunks, c);
+        jst[c] = jstar;
+        if (WANT_ELL) ell_partials[c] = sr.ell;
+    }
+}
+
+// a + b summed in a fixed order (the two partial arrays of a speculative filter pass)
+static __global__ void __launch_bounds__(1024) it_sum2_kernel(const double* a, const double* b, long long n, double* out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) s += a[i] + b[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
 }
 
 template <class G>
@@ -376,10 +515,15 @@ struct ItCall {
     int phase, rank, world;
     double* carry_out;
     const double* carries;
+    int spec_filter;          // phase 1 may switch to the plain filter once the chunk has forgotten its start (SpecReduce)
+    int want_ell;             // the pass produces the log-likelihood (every phase of one pass must agree on it)
 };
 
 template <int d>
-inline size_t it_ws_doubles(long long N) { return up_ws_doubles<d>(N) + 2 * (size_t)up_plan_chunks(N > 0 ? N : 1).nchunks + 64; }
+inline size_t it_ws_doubles(long long N) { return up_ws_doubles<d>(N) + 4 * (size_t)up_plan_chunks(N > 0 ? N : 1).nchunks + 64; }
+
+// speculative phase 1 pays off when the chunks are much longer than the filter's forgetting time
+constexpr int kSpecMinChunk = 256;
 
 // fused (likelihood, method) pairs of the site / energy epilogues
 #define BN_FOR_EACH_ITER_SITE(X)                                                       \
@@ -434,12 +578,22 @@ inline int it_run(const ItCall& c) {
     BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
     UpWs w = up_ws<d>(c.ws, cp);
     double* part = (double*)c.ws + up_ws_doubles<d>(io.N);
+    double* ell1 = part + 2 * cp.nchunks;              // log-likelihood partials of a speculative phase 1
+    int* jst = (int*)(part + 3 * cp.nchunks);          // its switch step per chunk
     const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
     const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
     const bool sharded = c.phase != UP_ALL;
+    const bool spec = c.spec_filter && cp.L >= kSpecMinChunk;
 
     if (c.phase == UP_ALL || c.phase == UP_REDUCE) {
-        BN_LAUNCH("it_reduce", st, (it_reduce_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks, is_first, w.fplan.input0)));
+        if (spec) {
+            if (c.want_ell) BN_LAUNCH("it_reduce_spec", st, (it_reduce_spec_kernel<G, true><<<grid, kUpThreads, 0, st>>>(
+                                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst)));
+            else BN_LAUNCH("it_reduce_spec", st, (it_reduce_spec_kernel<G, false><<<grid, kUpThreads, 0, st>>>(
+                                                     g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst)));
+        } else {
+            BN_LAUNCH("it_reduce", st, (it_reduce_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks, is_first, w.fplan.input0)));
+        }
         BN_CUDA(cudaGetLastError());
         BN_CUDA(run_scan<FA>(w.fplan, st));
         if (c.carry_out && c.phase == UP_REDUCE) {
@@ -457,12 +611,15 @@ inline int it_run(const ItCall& c) {
         }
         if (c.ell) {
             BN_LAUNCH("it_filter", st, (it_filter_kernel<G, true><<<grid, kUpThreads, 0, st>>>(
-                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, w.partials)));
+                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, w.partials,
+                                           spec ? jst : nullptr)));
             BN_CUDA(cudaGetLastError());
-            BN_LAUNCH("sum", st, (sum_kernel<false><<<1, 1024, 0, st>>>(w.partials, cp.nchunks, c.ell, 1.0)));
+            if (spec) BN_LAUNCH("sum", st, (it_sum2_kernel<<<1, 1024, 0, st>>>(w.partials, ell1, cp.nchunks, c.ell)));
+            else BN_LAUNCH("sum", st, (sum_kernel<false><<<1, 1024, 0, st>>>(w.partials, cp.nchunks, c.ell, 1.0)));
         } else {
             BN_LAUNCH("it_filter", st, (it_filter_kernel<G, false><<<grid, kUpThreads, 0, st>>>(
-                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, nullptr)));
+                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, nullptr,
+                                           spec ? jst : nullptr)));
         }
         BN_CUDA(cudaGetLastError());
         const unsigned g2 = (unsigned)((cp.nchunks + 127) / 128);

@@ -357,7 +357,7 @@ class TimeShardedMarkovGP:
             st.set_data(self.Y, self.mask_pseudo_y, scan_nan=not labels)
 
     def _fused_pass(self, st, mode, lr, cubature, ensure_psd, want_ell):
-        c = st.reduce()
+        c = st.reduce(want_ell=want_ell)
         carries = _all_gather(c, self.world) if self.world > 1 else c.reshape(1, -1)
         ell, c = st.filter(carries, want_ell=want_ell)
         carries = _all_gather(c, self.world) if self.world > 1 else c.reshape(1, -1)

@@ -131,8 +131,10 @@ class FusedShard:
                                            self.ws.numel(), stream_ptr()))
         return ell, sums
 
-    def reduce(self):
+    def reduce(self, want_ell=True):
+        """want_ell must match the filter() call of the same pass"""
         a, _ = self._args(None, 0, None, 1.0, 1.0, True)
+        a.want_ell = int(bool(want_ell))
         carry = torch.empty(self.kf_len, dtype=torch.float64, device=self.dev)
         _lib.check(_lib.lib().bn_iter_shard_reduce(self.kernel.spec(), C.byref(a), ptr(carry), ptr(self.ws), self.ws.numel(),
                                                    stream_ptr()))
@@ -140,6 +142,7 @@ class FusedShard:
 
     def filter(self, kf_carries, want_ell=True):
         a, _ = self._args(None, 0, None, 1.0, 1.0, True)
+        a.want_ell = int(bool(want_ell))
         ell = torch.zeros((), dtype=torch.float64, device=self.dev) if want_ell else None
         carry = torch.empty(self.rts_len, dtype=torch.float64, device=self.dev)
         _lib.check(_lib.lib().bn_iter_shard_filter(self.kernel.spec(), C.byref(a), ptr(kf_carries), ptr(ell), ptr(carry),

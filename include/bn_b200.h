@@ -461,6 +461,8 @@ typedef struct {
     const double* cub_x_host;  /* [Q] */
     const double* cub_w_host;  /* [Q] */
     double lr, power;
+    int32_t want_ell;          /* shard phases: the pass will produce the filter log-likelihood (all phases must agree) */
+    int32_t reserved_;
 } bn_iter_args;
 
 int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N);       /* L */

@@ -167,7 +167,7 @@ def expected_density(lib, method, lik, lik_param, y, post_mean, post_cov, nat1=N
 
 
 def iter_pass(lib, sp, dt, y, site_mean, site_cov, mode, method='vi', lik='probit', lik_param=0.0, cub=None, mask=None,
-              lr=1.0, power=1.0, ensure_psd=True, L=8, world=1, use_table=True):
+              lr=1.0, power=1.0, ensure_psd=True, L=8, world=1, use_table=True, spec=False):
     """fused iteration pass on tiled state (csrc/iter_impl.cuh).  mode 0 plain / 1 sites / 2 energy.
     Returns dict(ell, sums, site_mean, site_cov, post_mean, post_cov) with linear [N] arrays."""
     N = dt.shape[0]
@@ -175,7 +175,7 @@ def iter_pass(lib, sp, dt, y, site_mean, site_cov, mode, method='vi', lik='probi
     sy = np.ascontiguousarray(site_mean, dtype=np.float64).reshape(-1).copy()
     sR = np.ascontiguousarray(site_cov, dtype=np.float64).reshape(-1).copy()
     mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
-    ell, sums = np.zeros(1), np.zeros(2)
+    ell, sums, jm = np.zeros(1), np.zeros(2), np.zeros(1)
     pm, pc = np.zeros(N), np.zeros(N)
     Q, cx, cw = 0, None, None
     if cub is not None:
@@ -185,6 +185,7 @@ def iter_pass(lib, sp, dt, y, site_mean, site_cov, mode, method='vi', lik='probi
     liks = dict(LIKS, poisson=6)
     rc = lib.emu_iter_pass(C.byref(sp), C.c_longlong(N), L, world, _p(dt), _p(y), _p(sy), _p(sR), _p(mk), mode,
                            METHODS[method], liks[lik], C.c_double(lik_param), Q, _p(cx), _p(cw), C.c_double(lr),
-                           C.c_double(power), int(ensure_psd), int(use_table), _p(ell), _p(sums), _p(pm), _p(pc))
+                           C.c_double(power), int(ensure_psd), int(use_table), _p(ell), _p(sums), _p(pm), _p(pc),
+                           int(spec), _p(jm))
     assert rc == 0, rc
-    return dict(ell=ell[0], sums=sums, site_mean=sy, site_cov=sR, post_mean=pm, post_cov=pc)
+    return dict(ell=ell[0], sums=sums, site_mean=sy, site_cov=sR, post_mean=pm, post_cov=pc, jstar_mean=jm[0])

@@ -241,7 +241,7 @@ template <class G>
 static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const double* dt, const double* y,
                   double* sy, double* sR, const unsigned char* mask, int mode, int method, int lik, double lik_param,
                   int Q, const double* cx, const double* cw, double lr, double power, int ensure_psd, int use_table,
-                  double* ell, double* sums, double* pm, double* pc) {
+                  double* ell, double* sums, double* pm, double* pc, int spec = 0, double* jstar_mean = nullptr) {
     constexpr int d = G::d;
     using FA = FilterAlg<d>;
     using SA = SmootherAlg<d>;
@@ -254,8 +254,9 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
     for (int r = 0; r <= world; ++r) off[r] = N * r / world;
     struct Rank {
         long long n, nc;
-        std::vector<double> agg, fpre, sel, spre, fs, s0, sinit, dt_t, y_t, sy_t, sR_t, pm_t, pc_t, p1, p2;
+        std::vector<double> agg, fpre, sel, spre, fs, s0, sinit, dt_t, y_t, sy_t, sR_t, pm_t, pc_t, p1, p2, ell1;
         std::vector<unsigned char> mk_t;
+        std::vector<int> jst;
         ItIO io;
     };
     std::vector<Rank> ranks(world);
@@ -278,12 +279,39 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         q.fpre.assign((size_t)q.nc * FA::kElem, 0.0);
         q.sel.assign((size_t)q.nc * SA::kElem, 0.0);
         q.spre.assign((size_t)q.nc * SA::kElem, 0.0);
-        q.fs.assign((size_t)fs_doubles(q.nc, L, d + symn(d)), 0.0);
+        q.fs.assign((size_t)fs_doubles(q.nc, L, d + symn(d)) + 32 * (d + symn(d)), 0.0);
         q.s0.assign(64, 0.0);
         q.sinit.assign(64, 0.0);
         q.p1.assign(q.nc, 0.0);
         q.p2.assign(q.nc, 0.0);
-        for (long long c = 0; c < q.nc; ++c) it_reduce_chunk(g, q.io, L, q.nc, r == 0, q.agg.data(), c);
+        q.jst.assign(q.nc, 0);
+        q.ell1.assign(q.nc, 0.0);
+        if (spec) {  // SpecReduce: the 32 chunks of a warp advance in lockstep and switch together
+            for (long long c0 = 0; c0 < q.nc; c0 += 32) {
+                std::vector<SpecReduce<G, true>> sr(32);
+                for (int l = 0; l < 32; ++l) sr[l].init(g, q.io, L, q.fs.data(), c0 + l < q.nc ? c0 + l : 0, c0 + l < q.nc);
+                int j = 0;
+                bool all_dec = false;
+                while (!all_dec) {
+                    all_dec = true;
+                    for (int l = 0; l < 32; ++l) {
+                        bool dec = true;
+                        if (j < sr[l].cnt) dec = sr[l].absorb(g, r == 0 && c0 + l == 0 && j == 0);
+                        all_dec = all_dec && dec;
+                    }
+                    ++j;
+                }
+                for (int l = 0; l < 32 && c0 + l < q.nc; ++l) {
+                    q.jst[c0 + l] = j < sr[l].cnt ? j : sr[l].cnt;
+                    FA::store(q.agg.data(), q.nc, c0 + l, sr[l].el);
+                    for (int jj = j; jj < sr[l].cnt; ++jj) sr[l].filter(g);
+                    if (q.jst[c0 + l] < sr[l].cnt) sr[l].store_state(q.agg.data(), q.nc, c0 + l);
+                    q.ell1[c0 + l] = sr[l].ell;
+                }
+            }
+        } else {
+            for (long long c = 0; c < q.nc; ++c) it_reduce_chunk(g, q.io, L, q.nc, r == 0, q.agg.data(), c);
+        }
         host_scan<FA>(q.agg.data(), q.nc, q.fpre.data());
         export_carry_body<FA>(q.fpre.data(), q.nc, fcar.data() + (size_t)r * FA::kCarry);
     }
@@ -293,8 +321,11 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         fold_carries_body<FA>(fcar.data(), 0, r, 1, q.s0.data());
         std::vector<double> partials(q.nc, 0.0);
         for (long long c = 0; c < q.nc; ++c)
-            it_filter_chunk<G, true>(g, q.io, L, q.nc, r == 0, q.fpre.data(), q.s0.data(), q.fs.data(), partials.data(), c);
+            it_filter_chunk<G, true>(g, q.io, L, q.nc, r == 0, q.fpre.data(), q.s0.data(), q.fs.data(), partials.data(), c,
+                                     spec ? q.jst.data() : nullptr);
         for (double v : partials) total += v;
+        for (double v : q.ell1) total += v;
+        if (jstar_mean) { double a = 0; for (int v : q.jst) a += v; *jstar_mean += a / (double)q.nc / world; }
         for (long long c = 0; c < q.nc; ++c)
             up_selem_chunk<G>(q.n, L, q.nc, r != 0, q.agg.data(), q.s0.data(), q.fs.data(), q.sel.data(), c);
         host_scan<SA>(q.sel.data(), q.nc, q.spre.data());
@@ -603,11 +634,13 @@ extern "C" void emu_rank_smooth(void* h, const double* rts_carries, double* pm, 
 extern "C" int emu_iter_pass(const bn_kernel_spec* k, long long N, int L, int world, const double* dt, const double* y,
                              double* sy, double* sR, const unsigned char* mask, int mode, int method, int lik,
                              double lik_param, int Q, const double* cx, const double* cw, double lr, double power,
-                             int ensure_psd, int use_table, double* ell, double* sums, double* pm, double* pc) {
+                             int ensure_psd, int use_table, double* ell, double* sums, double* pm, double* pc, int spec,
+                             double* jstar_mean) {
+    if (jstar_mean) *jstar_mean = 0.0;
 #define X(FAM)                                                                                                          \
     if (k->family == FAM && k->n_components == 1)                                                                       \
         return emu_it<FastGen<FAM, 1>>(k, N, L, world, dt, y, sy, sR, mask, mode, method, lik, lik_param, Q, cx, cw, lr, \
-                                       power, ensure_psd, use_table, ell, sums, pm, pc);
+                                       power, ensure_psd, use_table, ell, sums, pm, pc, spec, jstar_mean);
     X(BN_MATERN12) X(BN_MATERN32) X(BN_MATERN52) X(BN_MATERN72)
 #undef X
     return -1;

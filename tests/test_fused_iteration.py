@@ -148,7 +148,7 @@ def test_fused_shard_phases_stitch(bn, kname, N, world):
     shards = [fused.FusedShard(kg, dt[b[r]:b[r + 1]], y[b[r]:b[r + 1]], rank=r, world=world) for r in range(world)]
     for r, s in enumerate(shards):
         s.load_sites(sy[b[r]:b[r + 1]], sR[b[r]:b[r + 1]])
-    kf = torch.stack([s.reduce() for s in shards])
+    kf = torch.stack([s.reduce(want_ell=True) for s in shards])
     filt = [s.filter(kf) for s in shards]
     rts = torch.stack([f[1] for f in filt])
     sums = [s.smooth(fused.SITES, rts, lk, _lib.BN_METHOD_VI, None, 0.7) for s in shards]

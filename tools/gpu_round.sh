@@ -10,6 +10,7 @@ for w in $what; do
     fulltests) timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_gputests.log 2>&1; tail -3 gpurun_out/${tag}_gputests.log;;
     c2) timeout 600 python bench.py --workload C2 --steps 10 --no-grad --no-cpu > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err; cat gpurun_out/${tag}_bench_c2.json | head -c 3000; tail -3 gpurun_out/${tag}_bench_c2.err;;
     c5) timeout 900 python bench.py --steps 10 --no-cpu > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err; cat gpurun_out/${tag}_bench_c5.json | head -c 4000; tail -3 gpurun_out/${tag}_bench_c5.err;;
+    c5nospec) BN_B200_SPEC_FILTER=0 timeout 900 python bench.py --steps 10 --no-cpu --no-grad > gpurun_out/${tag}_bench_c5_nospec.json 2> gpurun_out/${tag}_bench_c5_nospec.err; cat gpurun_out/${tag}_bench_c5_nospec.json | head -c 1500; tail -3 gpurun_out/${tag}_bench_c5_nospec.err;;
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python tools/prof_iter.py 10000000 3 > gpurun_out/${tag}_under_ncu.log 2>&1
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'it_(reduce|filter|smooth)' -s 5 -c 5 -o gpurun_out/${tag}_c2_full python tools/prof_iter.py 10000000 2 > gpurun_out/${tag}_ncu.log 2>&1
