@@ -24,6 +24,11 @@
 
 namespace bn {
 
+#ifndef BN_IT_SMOOTH_UNROLL
+#define BN_IT_SMOOTH_UNROLL 1
+#endif
+constexpr int kItSmoothUnroll = BN_IT_SMOOTH_UNROLL;  // steps of the RTS recursion unrolled together
+
 // ------------------------------------------------------------------------------------------ tiled layout
 constexpr int kTlPadRows = 2;  // rows past the last step a prefetch may touch
 BN_DEV long long tl_base(long long c, int L) { return (((c >> 5) * (long long)L) << 5) + (c & 31); }
@@ -253,7 +258,7 @@ BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks
 #pragma unroll
         for (int f = 0; f < symn(d); ++f) nfP[f] = pf[(d + f - nf) * 32];
     }
-#pragma unroll 1
+#pragma unroll kItSmoothUnroll
     for (int j = j_last; j >= 0; --j) {
         double Ab[G::kBlockA];
 #pragma unroll
@@ -286,6 +291,10 @@ BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks
     epi.finish(c);
 }
 
+#ifndef BN_IT_TAB_UNROLL
+#define BN_IT_TAB_UNROLL 2  // table evaluations in flight per thread inside the fused sweeps (registers are the constraint there)
+#endif
+
 // ------------------------------------------------------------------------------------------ smoother epilogues
 // plain: the posterior marginals, tiled
 struct EpiStore {
@@ -317,17 +326,16 @@ struct EpiSites {
     double d1, d2, yq, oy, oR;
     BN_DEV EpiSites(const ItIO& io_, const ItSiteArgs& a_, const Cub1* cub_, const double* tab)
         : io(io_), a(a_), lik{a_.lik_param, tab}, cub(cub_), d1(0.0), d2(0.0), yq(0.0), oy(0.0), oR(1.0) {}
-    BN_DEV void prefetch(long long ti) {
-        yq = io.y[ti];
+    BN_DEV void prefetch(long long ti) { yq = io.y[ti]; }
+    BN_DEV void step(long long ti, double m, double v) {
+        // the old site is needed after the cubature loop only: its loads are issued here and land while the loop runs
         oy = io.sy[ti];
         oR = io.sR[ti];
-    }
-    BN_DEV void step(long long ti, double m, double v) {
         // natural parameters of the site as reparametrise leaves them (basemodels.py:85-100): nat2 = 1 / cov, nat1 = nat2 mean
         const double o2 = 1.0 / oR, o1 = oy * o2;
         SiteStats1 s;
         double h, r1, r2, e1, e2;
-        site_update_scalar<LIK, METHOD, TAB>(lik, *cub, yq, m, v, o1, o2, a.lr, a.power, a.ensure_psd, s, h, r1, r2, e1, e2);
+        site_update_scalar<LIK, METHOD, TAB, BN_IT_TAB_UNROLL>(lik, *cub, yq, m, v, o1, o2, a.lr, a.power, a.ensure_psd, s, h, r1, r2, e1, e2);
         d1 += e1;
         d2 += e2;
         const double Lc = sqrt(r2);
@@ -351,16 +359,15 @@ struct EpiEnergy {
     unsigned char mk;
     BN_DEV EpiEnergy(const ItIO& io_, const ItSiteArgs& a_, const Cub1* cub_, const double* tab)
         : io(io_), a(a_), lik{a_.lik_param, tab}, cub(cub_), accV(0.0), accX(0.0), yq(0.0), oy(0.0), oR(1.0), mk(0) {}
-    BN_DEV void prefetch(long long ti) {
-        yq = io.y[ti];
+    BN_DEV void prefetch(long long ti) { yq = io.y[ti]; }
+    BN_DEV void step(long long ti, double m, double v) {
+        // the site of this step enters after the cubature loop only: its loads land while the loop runs
         oy = io.sy[ti];
         oR = io.sR[ti];
         if (io.mask) mk = io.mask[ti];
-    }
-    BN_DEV void step(long long ti, double m, double v) {
         io.pm[ti] = m;
         io.pc[ti] = v;
-        const SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB>(lik, yq, m, v, 0.0, 0.0, a.power, *cub);
+        const SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB, BN_IT_TAB_UNROLL>(lik, yq, m, v, 0.0, 0.0, a.power, *cub);
         if (!isnan(s.val)) accV += s.val;  // nansum (inference.py:218)
         accX += gaussian_ell_step<1>(&oy, &m, &v, &oR, io.mask ? &mk : nullptr, 0);
     }

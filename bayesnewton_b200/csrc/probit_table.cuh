@@ -60,23 +60,47 @@ inline float pt_make_float(uint32_t b) {
 }
 #endif
 
-// polynomial of one entry at u in [-1/2, 1/2)
-BN_DEV double pt_eval(const PtEntry& w, double u) {
-    const double c0 = pt_make_double(0x40200000u | (w.y & 0xFFFFFu), w.x) - 15.0;
-    const double c1 = pt_make_double(0x3F800000u | (w.z & 0xFFFFFu), w.w) - 0.0078125;
+constexpr double kPtC0Bias = 15.0;  // the table stores D0 = c0 + 15 in [8, 16)
+
+// (a & m) | e in one LOP3: the mask travels in a register so the exponent pattern can be the instruction's immediate
+BN_DEV uint32_t pt_mask_or(uint32_t a, uint32_t m, uint32_t e) {
+#ifdef __CUDA_ARCH__
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(m), "r"(e));
+    return d;
+#else
+    return (a & m) | e;
+#endif
+}
+
+// the 20-bit mantissa mask as an opaque register value (a literal would be folded back into two-instruction and / or pairs)
+BN_DEV uint32_t pt_mask20() {
+#ifdef __CUDA_ARCH__
+    uint32_t m;
+    asm volatile("mov.u32 %0, 0xFFFFF;" : "=r"(m));
+    return m;
+#else
+    return 0xFFFFFu;
+#endif
+}
+
+// polynomial of one entry at u in [-1/2, 1/2), PLUS kPtC0Bias (callers that sum many evaluations remove the bias once)
+BN_DEV double pt_eval_biased(const PtEntry& w, double u, uint32_t m20) {
+    const double d0 = pt_make_double(pt_mask_or(w.y, m20, 0x40200000u), w.x);
+    const double c1 = pt_make_double(pt_mask_or(w.z, m20, 0x3F800000u), w.w) - 0.0078125;
     const float c2 = pt_make_float(0x37000000u | ((w.y >> 9) & 0x7FF800u) | (w.z >> 21)) - 9.5367431640625e-6f;      // 2^-17 + 2^-19
     const float c3 = pt_make_float(0x37000000u | (w.w & 0x3FFFu)) - 7.636845111846924e-6f;                            // 2^-17 + 2^-27
     const float t = fmaf(c3, (float)u, c2);
-    return fma(fma((double)t, u, c1), u, c0);
+    return fma(fma((double)t, u, c1), u, d0);
 }
 
-// g at r = 512 f + kPtOff, which must lie in [2^13, 2^14)
-BN_DEV double probit_log_phi_s(const double* tab, double r) {
+// g + kPtC0Bias at r = 512 f + kPtOff, which must lie in [2^13, 2^14)
+BN_DEV double probit_log_phi_sb(const double* tab, double r, uint32_t m20) {
 #ifdef __CUDA_ARCH__
     const uint32_t hi = (uint32_t)__double2hiint(r), lo = (uint32_t)__double2loint(r);
     const uint4 q = reinterpret_cast<const uint4*>(tab)[(hi >> 7) & 0x1FFFu];
     const PtEntry w{q.x, q.y, q.z, q.w};
-    const uint32_t uh = 0x3FF00000u | (__funnelshift_l(lo, hi, 13) & 0xFFFFFu);
+    const uint32_t uh = pt_mask_or(__funnelshift_l(lo, hi, 13), m20, 0x3FF00000u);
 #else
     uint64_t b;
     memcpy(&b, &r, 8);
@@ -86,8 +110,11 @@ BN_DEV double probit_log_phi_s(const double* tab, double r) {
     const uint32_t uh = 0x3FF00000u | (((hi << 13) | (lo >> 19)) & 0xFFFFFu);
 #endif
     const double u = pt_make_double(uh, lo << 13) - 1.5;  // the 39 fraction bits of r as 1.f, minus 1.5
-    return pt_eval(w, u);
+    return pt_eval_biased(w, u, m20);
 }
+
+// g at r = 512 f + kPtOff
+BN_DEV double probit_log_phi_s(const double* tab, double r) { return probit_log_phi_sb(tab, r, pt_mask20()) - kPtC0Bias; }
 
 // tab -> g(f) for any f.  NaN inputs come back as a finite number (fmin/fmax drop NaN): callers poison.
 BN_DEV double probit_log_phi(const double* tab, double f) {

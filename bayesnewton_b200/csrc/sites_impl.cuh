@@ -26,8 +26,14 @@ struct Cub1 {
     int Q;
     int pad_;
     double x[kMaxQ1], w[kMaxQ1], wx[kMaxQ1], wxx[kMaxQ1];
-    double xmax;  // max |x|
+    double wd[kMaxQ1];       // w (x^2 - 1)
+    double xmax;             // max |x|
+    double bw, bwx, bwd;     // kPtC0Bias times the sums of w, wx, wd: what a biased table evaluation adds to the three sums
 };
+
+#ifndef BN_SITE_TAB_UNROLL
+#define BN_SITE_TAB_UNROLL 4
+#endif
 
 // what a site kernel needs besides bn_site_args: the 1-D rule by value, the probit table (shared
 // memory on the device, null = evaluate through erf/log), the multi-latent rule in device memory
@@ -150,7 +156,7 @@ struct SiteStats1 { double mean, jac, hess, val; };
 // Likelihood.variational_expectation / moment_match / log_likelihood_gradients /
 // statistical_linear_regression -- i.e. no cavity, no EP scale factor; PL returns (mu, dmu, omega)
 // in (val, jac, hess).
-template <int LIK, int METHOD, bool RAW = false, bool TAB = false>
+template <int LIK, int METHOD, bool RAW = false, bool TAB = false, int UNR = BN_SITE_TAB_UNROLL>
 BN_DEV SiteStats1 site_stats_1(const Lik1<LIK, TAB>& lik, double y, double m, double v, double n1, double n2, double power,
                                const Cub1& cub) {
     const int Q = cub.Q;
@@ -193,26 +199,32 @@ BN_DEV SiteStats1 site_stats_1(const Lik1<LIK, TAB>& lik, double y, double m, do
         // cubature.py:214-246 with f_i - m = sd x_i taken exactly:
         //   E = sum w l,  dE/dm = (sum w x l) / sd,  d2E/dm2 = (sum w x^2 l - sum w l) / v
         const double sd = sqrt(cov);
-        double E = 0.0, S1 = 0.0, S2 = 0.0;
+        double E = 0.0, S1 = 0.0, Dh = 0.0;  // sum w l, sum w x l, sum w (x^2 - 1) l
         bool done = false;
         if constexpr (TAB && LIK == BN_LIK_BERNOULLI_PROBIT) {
             // every point inside the table's range (the usual case): evaluate in table coordinates,
-            // log p(y | f) = g(+-f) with the sign folded into the affine map, no clamping per point
+            // log p(y | f) = g(+-f) with the sign folded into the affine map, no clamping per point.  The table returns
+            // g + 15 (its c0 field is stored biased); the three sums are corrected once, by 15 x the sums of the weights.
             const double sm = (y == 1.0) ? mean : -mean, reach = cub.xmax * sd;
             if (sm - reach >= kPtLo && sm + reach < kPtHi) {
                 const double sg = (y == 1.0) ? kPtInvH : -kPtInvH;
                 const double a1 = sg * sd, a0 = fma(sg, mean, kPtOff);
-#pragma unroll 4
+                const uint32_t m20 = pt_mask20();
+#pragma unroll UNR
                 for (int q = 0; q < Q; ++q) {
-                    const double l = probit_log_phi_s(lik.tab, fma(a1, cx[q], a0));
+                    const double l = probit_log_phi_sb(lik.tab, fma(a1, cx[q], a0), m20);
                     E = fma(cw[q], l, E);
                     S1 = fma(cub.wx[q], l, S1);
-                    S2 = fma(cub.wxx[q], l, S2);
+                    Dh = fma(cub.wd[q], l, Dh);
                 }
+                E -= cub.bw;
+                S1 -= cub.bwx;
+                Dh -= cub.bwd;
                 done = true;
             }
         }
         if (!done) {
+            double S2 = 0.0;
 #pragma unroll 2
             for (int q = 0; q < Q; ++q) {
                 const double l = lik.log_lik(y, fma(sd, cx[q], mean));
@@ -220,11 +232,12 @@ BN_DEV SiteStats1 site_stats_1(const Lik1<LIK, TAB>& lik, double y, double m, do
                 S1 = fma(cub.wx[q], l, S1);
                 S2 = fma(cub.wxx[q], l, S2);
             }
+            Dh = S2 - E;
         }
         const double poison = (mean - mean) + (sd - sd);  // NaN / inf inputs must come out as NaN
         val = E + poison;
         j = S1 / sd + poison;
-        h = (S2 - E) / cov + poison;
+        h = Dh / cov + poison;
     } else if constexpr (METHOD == BN_METHOD_EP) {
         // cubature.py:328-371 with f_i - m = sd x_i: Z = sum w p, dZ = C^-1 sd sum w x p,
         // d2Z = C^-1 sd^2 C^-1 sum w x^2 p - C^-1 Z,  p_i = exp(power * log-lik_i)
@@ -399,11 +412,11 @@ BN_DEV SiteStats2 site_stats_2(double y, const double* m, const double* V, const
 // the likelihood statistics of the scheme, ensure_psd (utils.py:89-96), newton_update (inference.py:21-39) and the
 // damping of inference.py:83-86.  s / h receive the (mean, jacobian) and the hessian the reference returns as state;
 // d1 / d2 the absolute change of the natural parameters before damping (the `diff` terms of inference.py:78-79).
-template <int LIK, int METHOD, bool TAB>
+template <int LIK, int METHOD, bool TAB, int UNR = BN_SITE_TAB_UNROLL>
 BN_DEV void site_update_scalar(const Lik1<LIK, TAB>& lik, const Cub1& cub, double y, double pm, double pc, double o1,
                                double o2, double lr, double power, int ensure_psd, SiteStats1& s, double& h, double& r1,
                                double& r2, double& d1, double& d2) {
-    s = site_stats_1<LIK, METHOD, false, TAB>(lik, y, pm, pc, o1, o2, power, cub);
+    s = site_stats_1<LIK, METHOD, false, TAB, UNR>(lik, y, pm, pc, o1, o2, power, cub);
     h = s.hess;
     if (ensure_psd && METHOD != BN_METHOD_PL) h = ensure_psd1(h);
     const double hh = isnan(h) ? -1e-6 : h;
@@ -644,8 +657,17 @@ inline void make_cub1(int Q, const double* x, const double* w, Cub1& c) {
         c.w[q] = in ? w[q] : 0.0;
         c.wx[q] = c.w[q] * c.x[q];
         c.wxx[q] = c.w[q] * c.x[q] * c.x[q];
+        c.wd[q] = c.wxx[q] - c.w[q];
         if (fabs(c.x[q]) > c.xmax) c.xmax = fabs(c.x[q]);
     }
+    // the bias sums in the order (and with the fused multiply-adds) the kernels accumulate in
+    double bw = 0.0, bwx = 0.0, bwd = 0.0;
+    for (int q = 0; q < Q && q < kMaxQ1; ++q) {
+        bw = fma(c.w[q], kPtC0Bias, bw);
+        bwx = fma(c.wx[q], kPtC0Bias, bwx);
+        bwd = fma(c.wd[q], kPtC0Bias, bwd);
+    }
+    c.bw = bw; c.bwx = bwx; c.bwd = bwd;
 }
 
 #define BN_FOR_EACH_SITE(X)                                                                           \
