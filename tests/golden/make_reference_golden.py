@@ -66,6 +66,8 @@ def ops_cases():
         N = 61
         dt, y, R, mask = filter_problem(N, D=D, seed=len(name) + D)
         out['%s_dt' % name], out['%s_y' % name], out['%s_R' % name], out['%s_mask' % name] = dt, y, R, mask
+        mask = mask.reshape(N, D)  # the reference's own callers pass the [N, D] form (basemodels.py:138): mvn_logpdf's
+        # np.diag(mask) then builds the D x D selector; the [N, D, 1] form of the docstring takes np.diag of a column
         As = np.stack([A(k.state_transition(d)) for d in dt])
         Pinf = A(k.stationary_covariance())
         out['%s_As' % name] = As
