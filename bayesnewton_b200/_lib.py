@@ -43,7 +43,7 @@ class IterArgs(C.Structure):
                 ('post_mean_t', C.c_void_p), ('post_cov_t', C.c_void_p), ('method', C.c_int32), ('likelihood', C.c_int32),
                 ('lik_param', C.c_double), ('Q', C.c_int32), ('ensure_psd', C.c_int32), ('cub_x_host', C.c_void_p),
                 ('cub_w_host', C.c_void_p), ('lr', C.c_double), ('power', C.c_double), ('want_ell', C.c_int32),
-                ('reserved_', C.c_int32)]
+                ('reserved_', C.c_int32), ('post_mean', C.c_void_p), ('post_cov', C.c_void_p)]
 
 
 class BnError(RuntimeError):

@@ -58,10 +58,13 @@ static int it_make_call(const bn_kernel_spec* k, const bn_iter_args* a, int mode
     const bool front = (phase == UP_ALL || phase == UP_REDUCE || phase == UP_FILTER);
     const bool back = (phase == UP_ALL || phase == UP_SMOOTH);
     if (front || (back && mode != BN_ITER_PLAIN)) BN_REQUIRE(a->site_mean_t && a->site_cov_t, "tiled site arrays are null");
-    if (back && mode != BN_ITER_SITES) BN_REQUIRE(a->post_mean_t && a->post_cov_t, "tiled posterior arrays are null");
+    BN_REQUIRE((a->post_mean == nullptr) == (a->post_cov == nullptr), "give both linear posterior arrays or neither");
+    if (back && mode != BN_ITER_SITES)
+        BN_REQUIRE((a->post_mean_t && a->post_cov_t) || a->post_mean, "posterior output arrays are null");
     c = ItCall{};
     c.spec = k;
-    c.io = ItIO{a->N, a->dt_t, a->y_t, a->site_mean_t, a->site_cov_t, a->mask_t, a->post_mean_t, a->post_cov_t};
+    c.io = ItIO{a->N, a->dt_t, a->y_t, a->site_mean_t, a->site_cov_t, a->mask_t, a->post_mean_t, a->post_cov_t,
+                a->post_mean, a->post_cov};
     c.mode = mode;
     c.method = a->method;
     c.likelihood = a->likelihood;

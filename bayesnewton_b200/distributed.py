@@ -361,7 +361,9 @@ class TimeShardedMarkovGP:
         carries = _all_gather(c, self.world) if self.world > 1 else c.reshape(1, -1)
         ell, c = st.filter(carries, want_ell=want_ell)
         carries = _all_gather(c, self.world) if self.world > 1 else c.reshape(1, -1)
-        return ell, st.smooth(mode, carries, self.likelihood, self.method, cubature, lr, self.power, ensure_psd)
+        from . import fused
+        post = (self.posterior_mean, self.posterior_variance) if (mode != fused.SITES and fused.linear_posterior()) else None
+        return ell, st.smooth(mode, carries, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, post=post)
 
     def _inference_fused(self, lr, cubature, ensure_psd):
         from . import fused
@@ -371,7 +373,8 @@ class TimeShardedMarkovGP:
         pl.version += 1
         pl.source, st.sites_version = st, pl.version
         ell, sums = self._fused_pass(st, fused.ENERGY, lr, cubature, ensure_psd, True)
-        self.posterior_mean, self.posterior_variance = st.posterior(self.posterior_mean, self.posterior_variance)
+        if not fused.linear_posterior():
+            self.posterior_mean, self.posterior_variance = st.posterior(self.posterior_mean, self.posterior_variance)
         key = (pl.version, self.shard.hyper_key())
         self._ell_cache = (ell, key)
         self._grad_cache = None

@@ -122,9 +122,12 @@ class FusedShard:
         return a, keep
 
     def run(self, mode, likelihood=None, method=_lib.BN_METHOD_VI, cubature=None, lr=1.0, power=1.0, ensure_psd=True,
-            want_ell=True):
-        """one pass on a single GPU: returns (ell or None, sums[2] or None) as device tensors"""
+            want_ell=True, post=None):
+        """one pass on a single GPU: returns (ell or None, sums[2] or None) as device tensors.  post = (mean, cov): the
+        marginals are written straight into these [N(,1,1)] tensors in time order instead of the tiled arrays"""
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
+        if post is not None:
+            a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
         ell = torch.zeros((), dtype=torch.float64, device=self.dev) if want_ell else None
         sums = torch.zeros(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
         _lib.check(_lib.lib().bn_iter_pass(self.kernel.spec(), C.byref(a), int(mode), ptr(ell), ptr(sums), ptr(self.ws),
@@ -150,12 +153,20 @@ class FusedShard:
         return ell, carry
 
     def smooth(self, mode, rts_carries, likelihood=None, method=_lib.BN_METHOD_VI, cubature=None, lr=1.0, power=1.0,
-               ensure_psd=True):
+               ensure_psd=True, post=None):
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
+        if post is not None:
+            a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
         sums = torch.zeros(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
         _lib.check(_lib.lib().bn_iter_shard_smooth(self.kernel.spec(), C.byref(a), int(mode), ptr(rts_carries), ptr(sums),
                                                    ptr(self.ws), self.ws.numel(), stream_ptr()))
         return sums
+
+
+def linear_posterior():
+    """BN_B200_LINEAR_POST=0: the sweeps keep the marginals tiled and a transposition kernel converts them (A/B aid)"""
+    import os
+    return os.environ.get('BN_B200_LINEAR_POST', '1') != '0'
 
 
 def cubature_key(cubature):

@@ -29,8 +29,12 @@ class InferenceMixin:
         _, d = st.run(fused.SITES, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=False)
         pl.version += 1  # the sites were rewritten in place (in the tiled arrays: pl reads them back on access)
         pl.source, st.sites_version = st, pl.version
-        ell, sums = st.run(fused.ENERGY, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=True)
-        self.posterior_mean, self.posterior_variance = st.posterior(self.posterior_mean, self.posterior_variance)
+        if fused.linear_posterior():  # the sweep stores the marginals in the reference's [N, 1, 1] layout itself
+            ell, sums = st.run(fused.ENERGY, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=True,
+                               post=(self.posterior_mean, self.posterior_variance))
+        else:
+            ell, sums = st.run(fused.ENERGY, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=True)
+            self.posterior_mean, self.posterior_variance = st.posterior(self.posterior_mean, self.posterior_variance)
         self._ell_cache = (ell, pl.version, self._hyper_key())
         self._grad_cache = None
         self._energy_cache = (sums[0], sums[1], self._energy_key(cubature))

@@ -463,6 +463,8 @@ typedef struct {
     double lr, power;
     int32_t want_ell;          /* shard phases: the pass will produce the filter log-likelihood (all phases must agree) */
     int32_t reserved_;
+    double* post_mean;         /* nullable pair: PLAIN / ENERGY write the marginals to these [N] arrays in time order */
+    double* post_cov;          /* (the reference's posterior_mean / posterior_variance layout) instead of the tiled ones */
 } bn_iter_args;
 
 int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N);       /* L */

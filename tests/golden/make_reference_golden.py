@@ -223,8 +223,96 @@ def regression_case():
     return out
 
 
+def sparse_cases():
+    """SparseMarkovVariationalGP (basemodels.py:928-1152; ops.py:383-426): pairs filter, joint of neighbouring inducing states,
+    grouped site update; Bernoulli-probit and Gaussian likelihoods"""
+    out = {}
+    rng = np.random.default_rng(21)
+    N = 70
+    x = np.sort(np.linspace(-10.0, 30.0, N) + 0.5 * rng.standard_normal(N))
+    f = np.cos(0.04 * x + 0.33 * np.pi) * np.sin(0.2 * x)
+    z = np.linspace(x[0] + 0.7, x[-1] - 0.4, 15)
+    out['x'], out['z'] = x, z
+    for lname, (mk, y) in {'gaussian': (lambda: bn.likelihoods.Gaussian(variance=0.15), f + np.sqrt(0.15) * rng.standard_normal(N)),
+                           'probit': (lambda: bn.likelihoods.Bernoulli(link='probit'), (f + 0.3 * rng.standard_normal(N) > 0).astype(np.float64))}.items():
+        out['y_' + lname] = y
+        m = bn.models.SparseMarkovVariationalGP(kernel=bn.kernels.Matern52(variance=1.2, lengthscale=4.0), likelihood=mk(),
+                                                X=x, Y=y, Z=z)
+        energies = []
+        for it in range(3):
+            m.inference(lr=0.7)
+            energies.append(float(m.energy()))
+        out[lname + '_energy'] = np.array(energies)
+        out[lname + '_post_mean'], out[lname + '_post_var'] = A(m.posterior_mean), A(m.posterior_variance)
+        out[lname + '_site_nat1'], out[lname + '_site_nat2'] = A(m.pseudo_likelihood.nat1), A(m.pseudo_likelihood.nat2)
+        xt = np.linspace(x[0] - 2.0, x[-1] + 2.0, 31)
+        pm, pv = m.predict(X=xt)
+        out[lname + '_xtest'], out[lname + '_pred_mean'], out[lname + '_pred_var'] = xt, A(pm), A(pv)
+    return out
+
+
+def spacetime_cases():
+    """MarkovVariationalGP / MarkovVariationalMeanFieldGP with a SpatioTemporalKernel (kernels.py:385-586; ops.py:429-706;
+    basemodels.py:676-687, 743-764, 1155-1175): gridded data, missing values, Gaussian likelihood"""
+    out = {}
+    rng = np.random.default_rng(31)
+    Nt, Ns = 14, 6
+    t = np.sort(np.linspace(0.0, 6.0, Nt) + 0.05 * rng.standard_normal(Nt))
+    r = np.linspace(-1.5, 1.5, Ns)
+    T, Rr = np.meshgrid(t, r, indexing='ij')
+    Y = np.sin(T) + np.cos(2 * Rr) + 0.1 * rng.standard_normal((Nt, Ns))
+    Y[2, 1] = np.nan
+    Y[9, 4] = np.nan
+    X = t[:, None]
+    R = np.tile(r[None, :, None], [Nt, 1, 1])
+    out['t'], out['r'], out['Y'] = t, r, Y
+    for name, cls in {'full': bn.models.MarkovVariationalGP, 'meanfield': bn.models.MarkovVariationalMeanFieldGP}.items():
+        kern = bn.kernels.SpatioTemporalKernel(temporal_kernel=bn.kernels.Matern32(variance=1.0, lengthscale=2.0),
+                                               spatial_kernel=bn.kernels.Matern32(variance=1.0, lengthscale=1.0),
+                                               z=r[:, None], sparse=True, opt_z=False, conditional='Full')
+        m = cls(kernel=kern, likelihood=bn.likelihoods.Gaussian(variance=0.5), X=X, R=R, Y=Y)
+        energies = []
+        for it in range(2):
+            m.inference(lr=0.7)
+            energies.append(float(m.energy()))
+        out[name + '_energy'] = np.array(energies)
+        out[name + '_post_mean'], out[name + '_post_var'] = A(m.posterior_mean), A(m.posterior_variance)
+        out[name + '_site_nat1'], out[name + '_site_nat2'] = A(m.pseudo_likelihood.nat1), A(m.pseudo_likelihood.nat2)
+        out[name + '_log_lik'] = A(m.compute_log_lik())
+    return out
+
+
+def infinite_horizon_cases():
+    """InfiniteHorizonVariationalGP (basemodels.py:1257-1363; ops.py:796-1186): steady-state gains from the DARE fixed point,
+    evenly spaced inputs, sequential and parallel forms"""
+    out = {}
+    rng = np.random.default_rng(41)
+    N = 120
+    x = np.linspace(0.0, 24.0, N)
+    f = np.sin(x) + 0.5 * np.cos(0.3 * x)
+    out['x'] = x
+    for lname, (mk, y) in {'gaussian': (lambda: bn.likelihoods.Gaussian(variance=0.2), f + np.sqrt(0.2) * rng.standard_normal(N)),
+                           'probit': (lambda: bn.likelihoods.Bernoulli(link='probit'), (f + 0.3 * rng.standard_normal(N) > 0).astype(np.float64))}.items():
+        out['y_' + lname] = y
+        for par in (False, True):
+            for kname, mkk in {'m32': lambda: bn.kernels.Matern32(variance=1.0, lengthscale=1.0),
+                               'm52': lambda: bn.kernels.Matern52(variance=1.3, lengthscale=1.5)}.items():
+                m = bn.models.InfiniteHorizonVariationalGP(kernel=mkk(), likelihood=mk(), X=x, Y=y, parallel=par)
+                tag = '%s_%s_%s' % (lname, kname, 'par' if par else 'seq')
+                energies = []
+                for it in range(3):
+                    m.inference(lr=0.6)
+                    energies.append(float(m.energy()))
+                out[tag + '_energy'] = np.array(energies)
+                out[tag + '_post_mean'], out[tag + '_post_var'] = A(m.posterior_mean), A(m.posterior_variance)
+                out[tag + '_site_nat1'], out[tag + '_site_nat2'] = A(m.pseudo_likelihood.nat1), A(m.pseudo_likelihood.nat2)
+                out[tag + '_log_lik'] = A(m.compute_log_lik())
+    return out
+
+
 CASES = {'ops': ops_cases, 'models': model_cases, 'likelihoods': likelihood_cases, 'heteroscedastic': heteroscedastic_cases,
-         'regression': regression_case}
+         'regression': regression_case, 'sparse': sparse_cases, 'spacetime': spacetime_cases,
+         'infinite_horizon': infinite_horizon_cases}
 
 if __name__ == '__main__':
     which = sys.argv[1:] or sorted(CASES)

@@ -274,7 +274,7 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         q.pm_t.assign((size_t)tl_len(q.nc, L), 0.0);
         q.pc_t.assign((size_t)tl_len(q.nc, L), 0.0);
         q.io = ItIO{q.n, q.dt_t.data(), q.y_t.data(), q.sy_t.data(), q.sR_t.data(), mask ? q.mk_t.data() : nullptr,
-                    q.pm_t.data(), q.pc_t.data()};
+                    q.pm_t.data(), q.pc_t.data(), nullptr, nullptr};
         q.agg.assign((size_t)q.nc * FA::kElem, 0.0);
         q.fpre.assign((size_t)q.nc * FA::kElem, 0.0);
         q.sel.assign((size_t)q.nc * SA::kElem, 0.0);
@@ -341,7 +341,7 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         bool done = false;
         if (mode == IT_PLAIN) {
             for (long long c = 0; c < q.nc; ++c) {
-                EpiStore epi{q.io.pm, q.io.pc};
+                EpiStore epi{q.io.pm, q.io.pc, nullptr, nullptr};
                 it_smooth_chunk(g, q.io, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, epi);
             }
             done = true;

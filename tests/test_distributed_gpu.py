@@ -13,11 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, N, mode, out):
+def _worker(rank, world, port, N, mode, fused, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
     os.environ['BN_B200_CARRY_EXCHANGE'] = mode
+    os.environ['BN_B200_FUSED'] = '1' if fused else '0'
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -41,19 +42,22 @@ def _worker(rank, world, port, N, mode, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('world', [2, 4, 8])
 @pytest.mark.parametrize('mode', ['p2p', 'nccl'])
-def test_gpu_two_process_time_sharded(mode):
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+@pytest.mark.parametrize('fused', [True, False])
+def test_gpu_multi_process_time_sharded(world, mode, fused):
+    """`world` ranks (one process per GPU), the fused tiled iteration and the unfused entry points, against one GPU"""
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs (run with gpurun --gpus %d)' % (world, world))
     import torch.multiprocessing as mp
     import bayesnewton_b200 as bn
     from _data import bench_inputs, rel_err
-    N, world = 200_003, 2
+    N = 200_003
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
     out = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, N, mode, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, N, mode, fused, out), nprocs=world, join=True)
     t, dt, y = bench_inputs(N)
     ref = bn.models.MarkovVariationalGP(kernel=bn.kernels.Matern52(1.0, 1.0), likelihood=bn.likelihoods.Bernoulli(), X=t, Y=y, parallel=True)
     Es = []
@@ -66,4 +70,4 @@ def test_gpu_two_process_time_sharded(mode):
     for r in range(world):
         assert np.allclose(out[r][2], Es, rtol=1e-9, atol=0)
         assert out[r][5] == (mode == 'p2p'), 'the peer-memory exchange was expected to be %s' % ('on' if mode == 'p2p' else 'off')
-    assert out[0][2] == out[1][2]  # both ranks hold the same energy, bit for bit
+    assert all(out[r][2] == out[0][2] for r in range(world))  # every rank holds the same energy, bit for bit

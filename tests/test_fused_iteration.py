@@ -129,6 +129,12 @@ def test_fused_passes_vs_unfused_library_path(bn, kname, lik, method, N):
     sh.run(fused.PLAIN)
     pm2, pc2 = sh.posterior()
     assert rel_err(np_(pm2), np_(pm0)) < 1e-12 and rel_err(np_(pc2), np_(pc0)) < 1e-12
+    # the same marginals written straight to [N, 1, 1] arrays in time order by the sweep itself
+    pl, cl = torch.full((N, 1, 1), -3.0, dtype=torch.float64, device=dev), torch.full((N, 1, 1), -3.0, dtype=torch.float64, device=dev)
+    sh.run(fused.PLAIN, post=(pl, cl))
+    assert np.array_equal(np_(pl), np_(pm2)) and np.array_equal(np_(cl), np_(pc2))
+    ell3, s3 = sh.run(fused.ENERGY, lk, meth, None, 1.0, 1.0, True, post=(pl, cl))
+    assert np.array_equal(np_(pl), np_(pm1)) and np.array_equal(np_(cl), np_(pc1)) and np.array_equal(np_(s3), np_(s))
 
 
 @pytest.mark.parametrize('kname', ['m32', 'm52'])

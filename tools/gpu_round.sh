@@ -11,6 +11,11 @@ for w in $what; do
     c2) timeout 600 python bench.py --workload C2 --steps 10 --no-grad --no-cpu > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err; cat gpurun_out/${tag}_bench_c2.json | head -c 3000; tail -3 gpurun_out/${tag}_bench_c2.err;;
     c5) timeout 900 python bench.py --steps 10 --no-cpu > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err; cat gpurun_out/${tag}_bench_c5.json | head -c 4000; tail -3 gpurun_out/${tag}_bench_c5.err;;
     c5nospec) BN_B200_SPEC_FILTER=0 timeout 900 python bench.py --steps 10 --no-cpu --no-grad > gpurun_out/${tag}_bench_c5_nospec.json 2> gpurun_out/${tag}_bench_c5_nospec.err; cat gpurun_out/${tag}_bench_c5_nospec.json | head -c 1500; tail -3 gpurun_out/${tag}_bench_c5_nospec.err;;
+    c5u4) BN_B200_LIBNAME=libbn_u4.so timeout 900 python bench.py --steps 10 --no-cpu --no-grad > gpurun_out/${tag}_bench_c5_u4.json 2> gpurun_out/${tag}_bench_c5_u4.err; cat gpurun_out/${tag}_bench_c5_u4.json | head -c 1500; tail -3 gpurun_out/${tag}_bench_c5_u4.err;;
+    c5nolin) BN_B200_LINEAR_POST=0 timeout 900 python bench.py --steps 10 --no-cpu --no-grad > gpurun_out/${tag}_bench_c5_nolin.json 2> gpurun_out/${tag}_bench_c5_nolin.err; cat gpurun_out/${tag}_bench_c5_nolin.json | head -c 1500; tail -3 gpurun_out/${tag}_bench_c5_nolin.err;;
+    reftests) timeout 900 python -m pytest tests/test_reference_golden.py -m gpu -q > gpurun_out/${tag}_ref_tests.log 2>&1; tail -15 gpurun_out/${tag}_ref_tests.log;;
+    mgputests) timeout 1500 python -m pytest tests/test_distributed_gpu.py tests/test_latent_sharding.py -m gpu -q > gpurun_out/${tag}_mgpu_tests_n${NG}.log 2>&1; tail -8 gpurun_out/${tag}_mgpu_tests_n${NG}.log;;
+    mgpubench) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${NG} --steps 10 --no-cpu --no-grad > gpurun_out/${tag}_bench_c5_n${NG}.json 2> gpurun_out/${tag}_bench_c5_n${NG}.err; tail -c 3000 gpurun_out/${tag}_bench_c5_n${NG}.json; tail -5 gpurun_out/${tag}_bench_c5_n${NG}.err;;
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python tools/prof_iter.py 10000000 3 > gpurun_out/${tag}_under_ncu.log 2>&1
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'it_(reduce|filter|smooth)' -s 5 -c 5 -o gpurun_out/${tag}_c2_full python tools/prof_iter.py 10000000 2 > gpurun_out/${tag}_ncu.log 2>&1
