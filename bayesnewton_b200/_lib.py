@@ -116,6 +116,9 @@ SIGNATURES = {
     'bn_iter_shard_reduce': (_I, [_KS, _IA, _P, _P, _Z, _P]),
     'bn_iter_shard_filter': (_I, [_KS, _IA, _P, _P, _P, _P, _Z, _P]),
     'bn_iter_shard_smooth': (_I, [_KS, _IA, _I, _P, _P, _P, _Z, _P]),
+    'bn_ih_workspace_bytes': (_Z, [_I, _L]),
+    'bn_ih_filter': (_I, [_I, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'bn_ih_smoother': (_I, [_I, _I, _L, _P, _P, _P, _I, _P, _P, _Z, _P]),
 }
 
 _lib = None

@@ -309,3 +309,62 @@ class MarkovMeanFieldGaussianProcess(MarkovGaussianProcess):
 
 
 MarkovMeanFieldGP = MarkovMeanFieldGaussianProcess
+
+
+class InfiniteHorizonGaussianProcess(MarkovGaussianProcess):
+    """steady-state Markov GP (basemodels.py:1257-1300): the state covariance is the fixed point of the Riccati recursion
+    for the AVERAGED site precision -- 20 iterations per filter call, warm-started from the previous call's result
+    (:1272-1289) -- so filter and smoother are affine recursions in the mean (ops.kalman_filter_infinite_horizon).
+    Evenly spaced inputs, one latent; the spatio-temporal and sparse variants of the reference are not built."""
+
+    def __init__(self, kernel, likelihood, X, Y, R=None, dare_iters=20, parallel=None):
+        from .likelihoods import Gaussian
+        super().__init__(kernel, likelihood, X, Y, R=R, parallel=parallel)
+        if self.func_dim != 1 or self.state_dim > 4:
+            raise NotImplementedError('the infinite-horizon model is built for one latent with state dimension <= 4')
+        if self.num_data > 2 and np.max(np.abs(np.diff(np.diff(self.X)))) >= 1e-6:
+            raise AssertionError('the infinite-horizon model needs equidistant time steps (basemodels.py:1269)')
+        self.heteroscedastic = bool(np.isnan(self.Y_host).any()) or not isinstance(likelihood, Gaussian)
+        self.dare_iters = dare_iters
+        Pinf = np.asarray(kernel.stationary_covariance(), dtype=np.float64)
+        self.dare_init_filter, self.dare_init_smoother = Pinf, Pinf
+        self._dt_host = np.concatenate([[0.0], np.diff(self.X)])
+
+    def _fused_ok(self):
+        return False
+
+    def filter(self, dt, kernel, y, noise_cov, mask=None, parallel=False, want_ell=True, **kw):
+        tied = 1.0 / float(self.pseudo_likelihood.nat2.mean())  # inv(mean of the site precisions), basemodels.py:1280-1281
+        out = ops.kalman_filter_infinite_horizon(dt, kernel, y, noise_cov, mask, parallel=parallel,
+                                                 heteroscedastic=self.heteroscedastic, noise_cov_tied=tied,
+                                                 dare_iters=self.dare_iters, dare_init=self.dare_init_filter,
+                                                 want_ell=want_ell)
+        self.dare_init_filter = out[1][1][0]
+        return out
+
+    def smoother(self, dt, kernel, filter_mean, filter_cov, return_full=False, parallel=False, **kw):
+        means, covs, gains, dare_cov = ops.rauch_tung_striebel_smoother_infinite_horizon(
+            dt, kernel, filter_mean, filter_cov, return_full=return_full, parallel=parallel, dare_iters=self.dare_iters,
+            dare_init=self.dare_init_smoother)
+        self.dare_init_smoother = dare_cov
+        return means, covs, gains
+
+    def update_posterior(self, want_grad=False):
+        if want_grad:
+            raise NotImplementedError('no hyper-gradient pass for the infinite-horizon model')
+        pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
+        dts = np.concatenate([self._dt_host[1:], [0.0]])
+        _, (fm, fcov) = self.filter(self._dt_host, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
+                                    parallel=self.parallel, want_ell=False)
+        self.posterior_mean, self.posterior_variance, _ = self.smoother(dts, self.kernel, fm, fcov, parallel=self.parallel)
+
+    def compute_log_lik(self, pseudo_y=None, pseudo_var=None):
+        """every call runs the filter again: the Riccati warm start makes the result depend on the number of calls, and the
+        reference's sequence of calls is mirrored (no caching)"""
+        if pseudo_y is None:
+            pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
+        ell, _ = self.filter(self._dt_host, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y, parallel=self.parallel)
+        return ell
+
+
+IHGP = InfiniteHorizonGaussianProcess

@@ -1,6 +1,6 @@
 """Model classes = inference scheme x Markov GP, assembled by multiple inheritance exactly like the
 reference's glue file (bayesnewton/models.py:118-152, build_model in bayesnewton/__init__.py:13-14)."""
-from .basemodels import MarkovGaussianProcess, MarkovMeanFieldGaussianProcess
+from .basemodels import InfiniteHorizonGaussianProcess, MarkovGaussianProcess, MarkovMeanFieldGaussianProcess
 from .sparse import SparseMarkovGaussianProcess
 from .inference import ExpectationPropagation, Newton, PosteriorLinearisation, VariationalInference
 
@@ -28,6 +28,29 @@ class MarkovPosteriorLinearisationGP(PosteriorLinearisation, MarkovGaussianProce
 
 class MarkovVariationalMeanFieldGP(VariationalInference, MarkovMeanFieldGaussianProcess):
     """models.py:154 of the reference"""
+    pass
+
+
+class InfiniteHorizonVariationalGP(VariationalInference, InfiniteHorizonGaussianProcess):
+    """models.py:162 of the reference"""
+    pass
+
+
+class InfiniteHorizonExpectationPropagationGP(ExpectationPropagation, InfiniteHorizonGaussianProcess):
+    """models.py:261 of the reference"""
+
+    def __init__(self, kernel, likelihood, X, Y, R=None, power=1., dare_iters=20, parallel=None):
+        self.power = power
+        super().__init__(kernel, likelihood, X, Y, R=R, dare_iters=dare_iters, parallel=parallel)
+
+
+class InfiniteHorizonNewtonGP(Newton, InfiniteHorizonGaussianProcess):
+    """models.py:315 of the reference"""
+    pass
+
+
+class InfiniteHorizonPosteriorLinearisationGP(PosteriorLinearisation, InfiniteHorizonGaussianProcess):
+    """models.py:388 of the reference"""
     pass
 
 

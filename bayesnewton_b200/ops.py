@@ -20,7 +20,8 @@ from ._util import as_dev, as_mask, ptr, stream_ptr, up_workspace, workspace
 from .kernels import discretise
 
 __all__ = ['temporal_conditional', 'update_posterior', 'kalman_filter', 'rauch_tung_striebel_smoother', '_sequential_kf', '_parallel_kf', '_sequential_rts',
-           '_parallel_rts', 'process_noise_covariance']
+           '_parallel_rts', 'process_noise_covariance', 'dare', 'rts_dare', 'kalman_filter_infinite_horizon',
+           'rauch_tung_striebel_smoother_infinite_horizon']
 
 
 def process_noise_covariance(A, Pinf):
@@ -203,3 +204,95 @@ def kalman_filter_pairs(dt, kernel, y, noise_cov, mask=None, parallel=False):
     """ops.py:383-426 (see sparse.kalman_filter_pairs)"""
     from .sparse import kalman_filter_pairs as kfp
     return kfp(dt, kernel, y, noise_cov, mask, parallel)
+
+
+# ---------------------------------------------------------------------------------------------- infinite horizon
+def _np64(x):
+    return x.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(x) else np.asarray(x, dtype=np.float64)
+
+
+def _chol_solve_host(P, B):
+    """solve(P, B) by Cholesky (utils.py:14-19) on small host matrices"""
+    L = np.linalg.cholesky(P)
+    return np.linalg.solve(L.T, np.linalg.solve(L, B))
+
+
+def dare(A, H, Q, R, Pinit, num_iters=20):
+    """fixed-point iterations of the discrete algebraic Riccati equation (ops.py:796-824); d x d host algebra"""
+    X = _np64(Pinit)
+    A, H, Q, R = _np64(A), _np64(H), _np64(Q), _np64(R)
+    for _ in range(num_iters):
+        HX = H @ X
+        S = HX @ H.T + R
+        K = _chol_solve_host(S, HX).T
+        X = A @ (X - K @ HX) @ A.T + Q
+    return X
+
+
+def rts_dare(A, Q, Pinf, num_iters=20):
+    """ops.py:955-975"""
+    X = _np64(Pinf)
+    A, Q = _np64(A), _np64(Q)
+    for _ in range(num_iters):
+        X = A @ X @ A.T + Q
+    return X
+
+
+def _ih_ws(d, N):
+    nb = int(_lib.lib().bn_ih_workspace_bytes(int(d), int(N)))
+    return torch.empty(nb, dtype=torch.uint8, device=torch.device('cuda', torch.cuda.current_device())), nb
+
+
+def kalman_filter_infinite_horizon(dt, kernel, y, noise_cov, mask=None, parallel=False, heteroscedastic=False,
+                                   noise_cov_tied=None, dare_iters=20, dare_init=None, want_ell=True):
+    """ops.py:881-952 for one latent with one site per step: ell, (means [N,d,1], (Pdare, cov)).  The Riccati fixed point
+    and the stationary gain are d x d host algebra; the O(N) mean recursion and the log-likelihood are bn_ih_filter."""
+    y, R = as_dev(y).reshape(-1), as_dev(noise_cov).reshape(-1)
+    N = y.shape[0]
+    dt_h = _np64(dt).reshape(-1)
+    Pinf = _np64(kernel.stationary_covariance())
+    A = _np64(kernel.state_transition(float(dt_h[1])))
+    Q = Pinf - A @ Pinf @ A.T
+    H = _np64(kernel.measurement_model())
+    if H.shape[0] != 1 or not (H[0, 1:] == 0).all():
+        raise NotImplementedError('the infinite-horizon entries are built for one latent (H = e_0^T)')
+    d = A.shape[0]
+    tied = _np64(noise_cov_tied).reshape(1, 1)
+    Pdare = dare(A, H, Q, tied, Pinf if dare_init is None else dare_init, dare_iters)
+    S = H @ Pdare @ H.T + tied
+    K = Pdare @ _chol_solve_host(S, H).T
+    cov = Pdare - K @ H @ Pdare
+    mk = as_mask(mask)
+    ell = torch.zeros((), dtype=torch.float64, device=y.device) if want_ell else None
+    means = torch.empty((N, d, 1), dtype=torch.float64, device=y.device)
+    Rv = R if heteroscedastic else as_dev(tied.reshape(-1))
+    ws, nb = _ih_ws(d, N)
+    Ac, Pc = np.ascontiguousarray(A), np.ascontiguousarray(Pdare)
+    _lib.check(_lib.lib().bn_ih_filter(_form(parallel), d, N, Ac.ctypes.data, Pc.ctypes.data, ptr(y), ptr(Rv),
+                                       int(not heteroscedastic), ptr(mk), ptr(ell), ptr(means), ptr(ws), nb, stream_ptr()))
+    return ell, (means, (Pdare, cov))
+
+
+def rauch_tung_striebel_smoother_infinite_horizon(dt, kernel, filter_mean, filter_cov, return_full=False, parallel=False,
+                                                  dare_iters=20, dare_init=None):
+    """ops.py:1018-1068: means, covs (the fixed point, tiled over time), gains, dare_cov"""
+    fm = as_dev(filter_mean)
+    N, d = fm.shape[0], fm.shape[1]
+    dt_h = _np64(dt).reshape(-1)
+    Pinf = _np64(kernel.stationary_covariance())
+    A = _np64(kernel.state_transition(float(dt_h[0])))
+    H = _np64(kernel.measurement_model())
+    Pdare, fcov = (_np64(c) for c in filter_cov)
+    gain = fcov @ _chol_solve_host(Pdare, A).T
+    Qdare = fcov - gain @ Pdare @ gain.T
+    dare_cov = rts_dare(gain, Qdare, Pinf if dare_init is None else dare_init, dare_iters)
+    od = d if return_full else 1
+    means = torch.empty((N, od, 1), dtype=torch.float64, device=fm.device)
+    ws, nb = _ih_ws(d, N)
+    Ac, Gc = np.ascontiguousarray(A), np.ascontiguousarray(gain)
+    _lib.check(_lib.lib().bn_ih_smoother(_form(parallel), d, N, Ac.ctypes.data, Gc.ctypes.data, ptr(fm), int(bool(return_full)),
+                                         ptr(means), ptr(ws), nb, stream_ptr()))
+    cov = dare_cov if return_full else H @ dare_cov @ H.T
+    covs = as_dev(cov).reshape(1, od, od).expand(N, od, od).contiguous()
+    gains = as_dev(gain).reshape(1, d, d).expand(N, d, d)
+    return means, covs, gains, dare_cov

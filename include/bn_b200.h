@@ -485,6 +485,24 @@ int bn_iter_shard_filter(const bn_kernel_spec* k, const bn_iter_args* a, const d
 int bn_iter_shard_smooth(const bn_kernel_spec* k, const bn_iter_args* a, int mode, const double* rts_carries,
                          double* sums, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- infinite-horizon (steady-state) filter / smoother ---------------------------------
+ * kalman_filter_infinite_horizon (ops.py:881-952) and rauch_tung_striebel_smoother_infinite_horizon (:1018-1068) for one
+ * latent with one site per step (H = e_0^T, d <= 4).  The d x d algebra that does not depend on N -- the Riccati fixed
+ * point Pdare (ops.py:796-824), the stationary gain, the smoother's fixed point -- is formed by the caller on the host
+ * (A_host, Pdare_host, gain_host: row-major [d,d] HOST arrays); these entries run the O(N) affine recursions of the mean
+ *     m_k = (A - K_k H A) m_{k-1} + K_k y_k,  K_k = Pdare H^T / (H Pdare H^T + R_k)     (_sequential_kf_ih / _parallel_kf_ih)
+ *     sm_k = fm_k + G (sm_{k+1} - A fm_k)                                               (_sequential_rts_ih / _parallel_rts_ih)
+ * form BN_SEQUENTIAL: one thread in time order; BN_SCAN: three-phase scan over (M, v) pairs.
+ * noise_var[N] (noise_is_scalar = 0: heteroscedastic) or noise_var[1] (= 1: the tied variance for every step);
+ * mask[N] nullable: only enters ell (utils.py:376-396); ell nullable; means[N,d,1].
+ * bn_ih_smoother: filter_mean[N,d,1] -> means[N,1,1] = H sm (return_full = 0) or [N,d,1]. */
+size_t bn_ih_workspace_bytes(int d, int64_t N);
+int bn_ih_filter(int form, int d, int64_t N, const double* A_host, const double* Pdare_host, const double* y,
+                 const double* noise_var, int noise_is_scalar, const uint8_t* mask, double* ell, double* means,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int bn_ih_smoother(int form, int d, int64_t N, const double* A_host, const double* gain_host, const double* filter_mean,
+                   int return_full, double* means, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

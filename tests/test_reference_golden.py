@@ -298,3 +298,125 @@ def test_gpu_regression_vs_reference(bn, par):
     m.inference(lr=1.0)
     assert rel_err(np_(m.posterior_mean), g['seq_post_mean']) < TOL and rel_err(np_(m.posterior_variance), g['seq_post_var']) < TOL
     assert abs(float(m.energy()) - g['seq_energy']) <= TOL * abs(g['seq_energy'])
+
+
+# ------------------------------------------------------------------------------------------ rows either side of the path
+@pytest.mark.parametrize('lik', ['gaussian', 'probit'])
+def test_oracle_sparse_markov_vs_reference(lik):
+    """SparseMarkovVariationalGP (basemodels.py:928-1152): pairs filter, joint of neighbouring inducing states, grouped sites.
+    The sites carry 1e-8 precisions next to O(1) ones: two correct fp64 orderings agree to ~cond * eps (see test_sparse_markov)"""
+    from oracle import sparse as osp
+    g = golden('sparse')
+    L = sites.Gaussian(0.15) if lik == 'gaussian' else sites.Bernoulli()
+    o = osp.SparseMarkovGP(ssm.Matern52(1.2, 4.0), L, g['x'], g['y_' + lik], g['z'])
+    for it in range(3):
+        o.inference(lr=0.7)
+        assert abs(o.energy() - g[lik + '_energy'][it]) <= 1e-7 * abs(g[lik + '_energy'][it])
+    assert rel_err(o.post_mean, g[lik + '_post_mean']) < 1e-7 and rel_err(o.post_cov, g[lik + '_post_var']) < 1e-7
+    pm, pv = o.predict(g[lik + '_xtest'])
+    assert rel_err(pm, g[lik + '_pred_mean'].reshape(-1)) < 1e-7 and rel_err(pv, g[lik + '_pred_var'].reshape(-1)) < 1e-7
+
+
+@pytest.mark.parametrize('variant', ['full', 'meanfield'])
+def test_oracle_spacetime_vs_reference(variant):
+    """MarkovVariationalGP / MarkovVariationalMeanFieldGP with a SpatioTemporalKernel, gridded data with missing values"""
+    from oracle import spacetime as ost
+    g = golden('spacetime')
+    t, r, Y = g['t'], g['r'], g['Y']
+    R = np.tile(r[None, :, None], [t.shape[0], 1, 1])
+    k = ost.SpatioTemporalKernel(ssm.Matern32(1.0, 2.0), ssm.Matern32(1.0, 1.0), z=r[:, None])
+    cls = ost.SpatioTemporalMarkovGP if variant == 'full' else ost.SpatioTemporalMeanFieldMarkovGP
+    o = cls(k, sites.Gaussian(0.5), t, Y, R)
+    for it in range(2):
+        o.inference(lr=0.7)
+        assert abs(o.energy() - g[variant + '_energy'][it]) <= 1e-7 * abs(g[variant + '_energy'][it])
+    assert rel_err(o.post_mean, g[variant + '_post_mean']) < 1e-7 and rel_err(o.post_cov, g[variant + '_post_var']) < 1e-7
+    assert rel_err(o.site_nat1, g[variant + '_site_nat1']) < 1e-9 and rel_err(o.site_nat2, g[variant + '_site_nat2']) < 1e-9
+    assert abs(o.compute_log_lik() - g[variant + '_log_lik']) <= 1e-7 * abs(g[variant + '_log_lik'])
+
+
+@pytest.mark.parametrize('lik', ['gaussian', 'probit'])
+@pytest.mark.parametrize('kname', ['m32', 'm52'])
+def test_oracle_infinite_horizon_vs_reference(lik, kname):
+    """InfiniteHorizonVariationalGP (basemodels.py:1257-1300; ops.py:796-1068): DARE fixed point warm-started across calls,
+    affine mean recursions.  The reference's sequential form; its parallel form is compared where it is still accurate
+    (homoscedastic: Gaussian likelihood, no missing data -- the heteroscedastic scan multiplies inverses of contractions)."""
+    from oracle import infinite_horizon as oih
+    g = golden('infinite_horizon')
+    L = sites.Gaussian(0.2) if lik == 'gaussian' else sites.Bernoulli()
+    k = ssm.Matern32(1.0, 1.0) if kname == 'm32' else ssm.Matern52(1.3, 1.5)
+    o = oih.InfiniteHorizonGP(k, L, g['x'], g['y_' + lik], method='vi')
+    tag = '%s_%s_seq' % (lik, kname)
+    for it in range(3):
+        o.inference(lr=0.6)
+        assert abs(o.energy() - g[tag + '_energy'][it]) <= 1e-10 * abs(g[tag + '_energy'][it])
+    assert rel_err(o.post_mean, g[tag + '_post_mean']) < 1e-10 and rel_err(o.post_cov, g[tag + '_post_var']) < 1e-10
+    assert rel_err(o.site_nat1, g[tag + '_site_nat1']) < 1e-10 and rel_err(o.site_nat2, g[tag + '_site_nat2']) < 1e-10
+    assert abs(o.compute_log_lik() - g[tag + '_log_lik']) <= 1e-10 * abs(g[tag + '_log_lik'])
+    if lik == 'gaussian':
+        ptag = '%s_%s_par' % (lik, kname)
+        assert rel_err(o.post_mean, g[ptag + '_post_mean']) < 1e-8 and rel_err(o.post_cov, g[ptag + '_post_var']) < 1e-8
+
+
+def test_oracle_infinite_horizon_approaches_the_full_filter():
+    """away from the ends of a long evenly spaced series with a Gaussian likelihood the steady-state posterior IS the
+    Markov GP posterior (the Riccati recursion has converged there)"""
+    from oracle import infinite_horizon as oih
+    rng = np.random.default_rng(0)
+    N = 400
+    x = np.linspace(0.0, 80.0, N)
+    y = np.sin(x) + 0.4 * rng.standard_normal(N)
+    a = oih.InfiniteHorizonGP(ssm.Matern32(1.0, 1.0), sites.Gaussian(0.2), x, y, method='vi', dare_iters=200)
+    b = model.MarkovGP(ssm.Matern32(1.0, 1.0), sites.Gaussian(0.2), x, y, method='vi')
+    a.inference(lr=1.0)
+    b.inference(lr=1.0)
+    mid = slice(60, N - 60)
+    assert np.abs(a.post_mean[mid] - b.post_mean[mid]).max() < 1e-6
+    assert np.abs(a.post_cov[mid] - b.post_cov[mid]).max() < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('lik', ['gaussian', 'probit'])
+@pytest.mark.parametrize('kname', ['m32', 'm52'])
+@pytest.mark.parametrize('par', [False, True])
+def test_gpu_infinite_horizon_vs_reference(bn, lik, kname, par):
+    """InfiniteHorizonVariationalGP through bn_ih_filter / bn_ih_smoother (both forms) against the reference's results"""
+    g = golden('infinite_horizon')
+    L = bn.likelihoods.Gaussian(0.2) if lik == 'gaussian' else bn.likelihoods.Bernoulli()
+    k = bn.kernels.Matern32(1.0, 1.0) if kname == 'm32' else bn.kernels.Matern52(1.3, 1.5)
+    m = bn.models.InfiniteHorizonVariationalGP(kernel=k, likelihood=L, X=g['x'], Y=g['y_' + lik], parallel=par)
+    tag = '%s_%s_seq' % (lik, kname)
+    for it in range(3):
+        m.inference(lr=0.6)
+        assert abs(float(m.energy()) - g[tag + '_energy'][it]) <= TOL * abs(g[tag + '_energy'][it])
+    assert rel_err(np_(m.posterior_mean), g[tag + '_post_mean']) < TOL
+    assert rel_err(np_(m.posterior_variance), g[tag + '_post_var']) < TOL
+    assert rel_err(np_(m.pseudo_likelihood.nat1), g[tag + '_site_nat1']) < TOL
+    assert rel_err(np_(m.pseudo_likelihood.nat2), g[tag + '_site_nat2']) < TOL
+    assert abs(float(m.compute_log_lik()) - g[tag + '_log_lik']) <= TOL * abs(g[tag + '_log_lik'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N', [2, 7, 3001, 200_003])
+def test_gpu_infinite_horizon_forms_agree_with_oracle(bn, N):
+    """bn_ih_filter / bn_ih_smoother, sequential and scan forms, heteroscedastic with a mask, against the oracle"""
+    from oracle import infinite_horizon as oih
+    rng = np.random.default_rng(N)
+    k, ko = bn.kernels.Matern52(1.2, 0.8), ssm.Matern52(1.2, 0.8)
+    dt = np.concatenate([[0.0], np.full(N - 1, 0.2)])
+    y = rng.standard_normal((N, 1, 1))
+    R = 0.3 + rng.random((N, 1, 1))
+    mask = rng.random((N, 1, 1)) < 0.1
+    tied = np.array([[1.0 / np.mean(1.0 / R)]])
+    e0, (m0, (Pd0, c0)) = oih.kalman_filter_infinite_horizon(dt, ko, y, R, mask, heteroscedastic=True, noise_cov_tied=tied)
+    dts = np.concatenate([dt[1:], [0.0]]) if N > 1 else dt
+    s0 = oih.rauch_tung_striebel_smoother_infinite_horizon(np.full(N, 0.2), ko, m0, (Pd0, c0))
+    for par in (False, True):
+        e1, (m1, (Pd1, c1)) = bn.ops.kalman_filter_infinite_horizon(dt, k, y, R, mask, parallel=par, heteroscedastic=True,
+                                                                    noise_cov_tied=tied)
+        assert abs(float(e1) - e0) <= TOL * abs(e0) and rel_err(np_(m1), m0) < TOL
+        assert rel_err(Pd1, Pd0) < 1e-12 and rel_err(c1, c0) < 1e-12
+        for rf in (False, True):
+            s0f = oih.rauch_tung_striebel_smoother_infinite_horizon(np.full(N, 0.2), ko, m0, (Pd0, c0), return_full=rf)
+            s1 = bn.ops.rauch_tung_striebel_smoother_infinite_horizon(np.full(N, 0.2), k, m0, (Pd0, c0), return_full=rf, parallel=par)
+            assert rel_err(np_(s1[0]), s0f[0]) < TOL and rel_err(np_(s1[1]), s0f[1]) < TOL and rel_err(np_(s1[2]), s0f[2]) < TOL
