@@ -60,6 +60,7 @@ SIGNATURES = {
     'bn_timing_enable': (_I, [_I]),
     'bn_timing_report': (_I, [C.c_char_p, _Z]),
     'bn_measure_dfma_peak': (_I, [_P, _Z, C.POINTER(C.c_double)]),
+    'bn_measure_dmma_peak': (_I, [_P, _Z, C.POINTER(C.c_double)]),
     'bn_state_dim': (_I, [_KS]),
     'bn_discretise': (_I, [_KS, _L, _P, _P, _P, _P]),
     'bn_workspace_bytes': (_Z, [_L, _I, _I]),

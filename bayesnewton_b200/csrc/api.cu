@@ -135,6 +135,52 @@ extern "C" int bn_measure_dfma_peak(double* scratch, size_t scratch_doubles, dou
     return 0;
 }
 
+// fp64 tensor-pipe (DMMA) rate of the current device: 8 independent mma.sync.m8n8k4.f64 accumulator chains per warp at full
+// occupancy; reported as fused multiply-adds per second (one DMMA.8x8x4 = 256 of them).  The roofline denominator of
+// the dense spatio-temporal kernels.  Synchronises the device.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[2 * i]), "+d"(c[2 * i + 1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (out) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int bn_measure_dmma_peak(double* scratch, size_t scratch_doubles, double* fma_per_s_host) {
+    BN_REQUIRE(fma_per_s_host != nullptr, "output is null");
+    int dev = 0, sms = 0;
+    BN_CUDA(cudaGetDevice(&dev));
+    BN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256, iters = 4000;
+    BN_REQUIRE(scratch && scratch_doubles >= (size_t)blocks * threads, "scratch of %d doubles needed", blocks * threads);
+    cudaEvent_t e0, e1;
+    BN_CUDA(cudaEventCreate(&e0));
+    BN_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        BN_CUDA(cudaEventRecord(e0, 0));
+        dmma_peak_kernel<<<blocks, threads>>>(scratch, iters, 1e-3, 1e-3);
+        BN_CUDA(cudaEventRecord(e1, 0));
+        BN_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        BN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double r = (double)blocks * (threads / 32) * iters * 8 * 256.0 / (ms * 1e-3);
+        if (r > best) best = r;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *fma_per_s_host = best;
+    return 0;
+}
+
 extern "C" int bn_state_dim(const bn_kernel_spec* k) {
     if (!k || k->n_components < 1 || k->n_components > BN_MAX_COMPONENTS) return -1;
     int n = family_dim(k->family);

@@ -392,6 +392,9 @@ struct EpiEnergy {
 };
 
 #ifdef __CUDACC__
+}  // namespace bn
+#include "tma_stage.cuh"
+namespace bn {
 // ------------------------------------------------------------------------------------------ kernels
 constexpr int kItTabThreads = 512;  // the table-gathering sweeps own a whole SM: one CTA, 16 warps, the table in shared memory
 
@@ -473,8 +476,7 @@ it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs
     extern __shared__ __align__(16) double it_smem[];
     const double* tab = nullptr;
     if constexpr (TAB) {
-        for (int i = threadIdx.x; i < kPtDoubles; i += kItTabThreads) it_smem[i] = gtab[i];
-        __syncthreads();
+        tma_stage_to_smem(it_smem, gtab, (uint32_t)(sizeof(double) * kPtDoubles));  // cp.async.bulk + mbarrier
         tab = it_smem;
     }
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;

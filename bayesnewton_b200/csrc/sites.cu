@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <mutex>
 #include "sites_impl.cuh"
+#include "tma_stage.cuh"
 
 namespace bn {
 
@@ -62,8 +63,7 @@ bool probit_table_enabled() {
 template <bool TAB>
 __device__ __forceinline__ const double* stage_table(double* sm) {
     if constexpr (TAB) {
-        for (int i = threadIdx.x; i < kPtDoubles; i += kTabThreads) sm[i] = g_probit_tab[i];
-        __syncthreads();
+        tma_stage_to_smem(sm, g_probit_tab, (uint32_t)(sizeof(double) * kPtDoubles));
         return sm;
     } else {
         return nullptr;

@@ -87,7 +87,12 @@ class SpatioTemporalKernel:
     def _ks(self, A, B):
         k = self.spatial_kernel
         A, B = np.asarray(A, dtype=np.float64), np.asarray(B, dtype=np.float64)
-        return k.K(A, B) if isinstance(k, Separable) else k.K(A[:, :1], B[:, :1])
+        if isinstance(k, Separable):
+            return k.K(A, B)
+        if A.shape[1] > 1:  # isotropic kernel on several spatial dimensions: the scaled Euclidean distance over ALL columns
+            d2 = ((A[:, None, :] - B[None, :, :]) ** 2).sum(-1) / k.lengthscale ** 2   # kernels.py:97-104
+            return k.K_r(np.sqrt(np.maximum(d2, 1e-36)))
+        return k.K(A[:, :1], B[:, :1])
 
     def K(self, X, X2):
         X, X2 = np.asarray(X, dtype=np.float64), np.asarray(X2, dtype=np.float64)
@@ -262,6 +267,11 @@ class SpatioTemporalMixin:
     def __init__(self, kernel, likelihood, X, Y, R=None, parallel=None):
         if getattr(likelihood, 'multi_latent', False):
             raise NotImplementedError('multi-latent likelihoods on the spatio-temporal path')
+        if self.method not in (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON):
+            # EP / PL form their cavity in the M-dimensional inducing space (B^T Lambda B, basemodels.py:230-245 with
+            # compute_full_pseudo_nat) and project it with B (.) B^T + C; the scalar site kernels work in data space
+            raise NotImplementedError('the spatio-temporal path supports VI and Newton (the EP / PL cavity in the '
+                                      'inducing space is not built)')
         t = np.asarray(X, dtype=np.float64)
         if R is None:  # X = [t, r...] columns (utils.py:251-254) is the flattened-inputs form: not supported here
             raise NotImplementedError('pass the spatial inputs as R [N_t, N_s, n_dims]')

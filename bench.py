@@ -34,6 +34,10 @@ UNIT = 'time-steps/s'
 WORKLOADS = {
     'C5': dict(n_total=100_000_000, name='C5: MarkovVariationalGP Matern52 (d=3) Bernoulli-probit GH-20, scan form, N=1e8'),
     'C2': dict(n_total=10_000_000, name='C2: MarkovVariationalGP Matern52 (d=3) Bernoulli-probit GH-20, scan form, N=1e7'),
+    'C1': dict(n_total=1_000, name='C1: demos/regression.py shape -- MarkovVariationalGP Matern52 (d=3) Gaussian, N=1e3, lr=1'),
+    'C3': dict(n_total=1_000_000, name='C3: MarkovVariationalGP Independent[Matern32 x2] HeteroscedasticNoise (GH 20x20), N=1e6, lr=0.3'),
+    'C4': dict(n_total=10_000, name='C4: MarkovVariationalGP SpatioTemporalKernel(Matern32 time x separable Matern32 space), '
+                                    'N_t=1e4 x 16x16 grid (M=256, d=512), Gaussian, 5% missing, lr=1'),
 }
 
 # algorithmic bytes per time step at d = 3, D = 1, fp64 on the reference-interface layouts (full matrices,
@@ -482,6 +486,221 @@ def main_gpu(args):
     if world > 1:
         dist.destroy_process_group()
 
+# ------------------------------------------------------------------------------------------ C1 / C3 / C4
+def build_generic(args, bn, world, rank):
+    """(model, step(), host inputs to stream in the end-to-end leg, description of the roofline)"""
+    from bayesnewton_b200 import _lib
+    K = bn.kernels
+    w = args.workload
+    if w == 'C1':
+        N = args.n_total
+        x = np.linspace(-17, 147, N)
+        y = np.cos(0.04 * x + 0.33 * np.pi) * np.sin(0.2 * x) + np.sqrt(0.2) * np.random.default_rng(12345).standard_normal(N)
+        m = bn.models.MarkovVariationalGP(kernel=K.Matern52(1.0, 5.0), likelihood=bn.likelihoods.Gaussian(0.2), X=x, Y=y, parallel=True)
+        step = lambda: (m.inference(lr=1.0), m.energy())[1]
+        return m, step, (np.concatenate([[0.0], np.diff(x)]), y), dict(bound='launch latency', bytes_per_step=ITER_BYTES)
+    if w == 'C3':
+        N = args.n_total
+        dt = 0.05 + 0.1 * np.random.default_rng(0).random(N)
+        dt[0] = 0
+        t = np.cumsum(dt)
+        y = np.sin(0.5 * t) + np.log1p(np.exp(np.cos(0.2 * t))) * np.random.default_rng(1).standard_normal(N)
+        y = (y - y.mean()) / y.std()
+        kern = K.Independent([K.Matern32(1.0, 1.0), K.Matern32(1.0, 1.0)])
+        lik = bn.likelihoods.HeteroscedasticNoise()
+        if world == 1:
+            m = bn.models.MarkovVariationalGP(kernel=kern, likelihood=lik, X=t, Y=y, parallel=True)
+        else:
+            from bayesnewton_b200 import latent_sharding as ls
+            m = ls.LatentShardedMarkovGP(kern, lik, t, y, _lib.BN_METHOD_VI, rank, world, power=1.0)
+        step = lambda: (m.inference(lr=0.3), m.energy())[1]
+        # SURVEY 8d: F 216, S 216, U 200, V 56, X 96, L 56 => 1272 B per step; the 400-point cubature makes U, V fp64-bound
+        return m, step, (dt, y), dict(bound='fp64 (400-point cubature) / hbm', bytes_per_step=1272)
+    if w == 'C4':
+        Nt, G = args.n_total, 16
+        t = np.arange(Nt, dtype=np.float64)
+        a = np.linspace(-3, 3, G)
+        r = np.array([[u, v] for u in a for v in a])
+        R = np.tile(r[None], (Nt, 1, 1))
+        Y = (np.sin(t / 10)[:, None] + np.sin(r[:, 0])[None] + np.cos(r[:, 1])[None]
+             + 0.1 * np.random.default_rng(1).standard_normal((Nt, G * G)))
+        Y[np.random.default_rng(2).uniform(size=Y.shape) < 0.05] = np.nan
+        kern = bn.spacetime.SpatioTemporalKernel(K.Matern32(1.0, 5.0), bn.spacetime.Separable([K.Matern32(1.0, 1.0), K.Matern32(1.0, 1.0)]), z=r)
+        m = bn.models.MarkovVariationalGP(kernel=kern, likelihood=bn.likelihoods.Gaussian(1.0), X=t, Y=Y, R=R)
+        step = lambda: (m.inference(lr=1.0), m.energy())[1]
+        M = G * G
+        d = 2 * M
+        fF = M ** 3 / 3 + 2 * M * M * d + 2 * d * d * M + 8 * d * d       # SURVEY 8d: 0.209 GFLOP per filter step
+        fS = d ** 3 / 3 + 2 * d ** 3 + 4 * d ** 3 + 8 * d * d             #            0.852 GFLOP per smoother step
+        return m, step, (None, Y), dict(bound='fp64_tensor', flops_per_step=3 * fF + 2 * fS, flops_filter=fF, flops_smoother=fS)
+    raise ValueError(w)
+
+
+def main_generic(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    import bayesnewton_b200 as bn
+    from bayesnewton_b200 import _lib
+    if world > 1:
+        if args.workload != 'C3' or world != 2:
+            raise SystemExit('%s runs on one GPU (C3 also latent-sharded on 2)' % args.workload)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    L = _lib.lib()
+    model, step, (dt_h, y_h), roofdesc = build_generic(args, bn, world, rank)
+    NT = args.n_total
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        E = step()
+    sync_all()
+    sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        E = step()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    # launch-bound workloads: the same step captured once in a CUDA graph and replayed (C1)
+    graph_ms = None
+    if args.workload == 'C1':
+        try:
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s)
+            with torch.cuda.graph(g):
+                Eg = step()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                g.replay()
+            g1.record()
+            torch.cuda.synchronize()
+            graph_ms = g0.elapsed_time(g1) / args.steps
+        except Exception as ex:  # noqa: BLE001 -- capture is an optimisation: report why it was not available
+            graph_ms = 'unavailable: ' + repr(ex)[:200]
+            torch.cuda.synchronize()
+    # per-kernel device times (second pass, as in the C5 arm)
+    L.bn_timing_enable(1)
+    for _ in range(args.steps):
+        E = step()
+    sync_all()
+    cbuf = ctypes.create_string_buffer(1 << 16)
+    L.bn_timing_report(cbuf, 1 << 16)
+    L.bn_timing_enable(0)
+    kt = {}
+    for ln in cbuf.value.decode().splitlines():
+        name, cnt, tot = ln.split()
+        kt[name] = (int(cnt), float(tot))
+    energy = float(E)
+    # end to end: the observations (and step lengths) of every step come from pinned host memory, the energy goes back
+    y_pin = torch.from_numpy(np.ascontiguousarray(y_h)).pin_memory()
+    dt_pin = torch.from_numpy(np.ascontiguousarray(dt_h)).pin_memory() if dt_h is not None else None
+    y_dev = model.Y
+    h2d = y_pin.numel() * 8 + (dt_pin.numel() * 8 if dt_pin is not None else 0)
+    e_pin = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        y_dev.reshape(-1).copy_(y_pin.reshape(-1), non_blocking=True)
+        if dt_pin is not None and hasattr(model, 'dt'):
+            model.dt.reshape(-1).copy_(dt_pin.reshape(-1), non_blocking=True)
+        st = getattr(model, '_fused', None)
+        if st is not None:  # the fused iteration keeps tiled copies of its inputs
+            st.set_dt(model.dt)
+            st.set_data(model.Y, getattr(model, 'mask_pseudo_y', None))
+        e = step()
+        e_pin.copy_(e.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(e_pin[0])
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    ms2 = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2) / args.steps
+    clocks = sampler.stop()
+    scratch = torch.empty(8 * 148 * 256 * 2, dtype=torch.float64, device=dev)
+    dfma, dmma = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    L.bn_measure_dfma_peak(scratch.data_ptr(), scratch.numel(), ctypes.byref(dfma))
+    L.bn_measure_dmma_peak(scratch.data_ptr(), scratch.numel(), ctypes.byref(dmma))
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        dom = max(kt, key=lambda k: kt[k][1]) if kt else None
+        roof = None
+        if dom:
+            cnt, tot = kt[dom]
+            avg_ms = tot / cnt
+            if roofdesc['bound'] == 'fp64_tensor':
+                per_launch = {'st_filter': roofdesc['flops_filter'], 'st_smoother': roofdesc['flops_smoother'],
+                              'st_gain': roofdesc['flops_smoother']}.get(dom, roofdesc['flops_filter']) * NT
+                achieved = per_launch / (avg_ms * 1e-3) / 1e12
+                pk = 2 * dmma.value / 1e12
+                roof = {'bound': 'fp64_tensor', 'kernel': dom, 'achieved': achieved, 'peak': pk, 'unit': 'TFLOP/s',
+                        'frac': achieved / pk if pk else None, 'traffic': None,
+                        'peak_source': 'measured now: mma.sync.m8n8k4.f64 (DMMA) microbenchmark, bn_measure_dmma_peak; '
+                                       'fp64 FMA pipe %.1f TFLOP/s (bn_measure_dfma_peak)' % (2 * dfma.value / 1e12),
+                        'algorithmic_flops_per_launch': per_launch, 'avg_launch_ms': avg_ms,
+                        'share_of_step': tot / (ms_per_step * args.steps),
+                        'whole_iteration': {'algorithmic_tflop': roofdesc['flops_per_step'] * NT / 1e12,
+                                            'achieved_tflops': roofdesc['flops_per_step'] * NT / (ms_per_step * 1e-3) / 1e12,
+                                            'frac_of_dmma_peak': roofdesc['flops_per_step'] * NT / (ms_per_step * 1e-3) / (2 * dmma.value) if dmma.value else None}}
+            else:
+                ab = ALGO_BYTES.get(dom, 0)
+                achieved = ab * NT / (avg_ms * 1e-3) / 1e9
+                roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                        'traffic': args.traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_step': ab, 'avg_launch_ms': avg_ms,
+                        'share_of_step': tot / (ms_per_step * args.steps), 'note': 'workload bound: ' + roofdesc['bound']}
+        line = {'metric': METRIC, 'value': NT / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': dict(workload_config(args, world), model=type(model).__module__ + '.' + type(model).__name__,
+                               parallelism='single GPU' if world == 1 else 'latent-shard x%d' % world,
+                               l2='working set %s L2 (126 MB)' % ('below: launch-latency bound' if args.workload == 'C1' else 'above')),
+                'clocks': clocks,
+                'e2e': {'value': NT / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': int(h2d),
+                        'd2h_bytes_per_step': 8},
+                'gpu_launches': int(sum(c for c, _ in kt.values())),
+                'gpu_launches_per_step': int(sum(c for c, _ in kt.values())) // max(1, args.steps),
+                'roofline': roof, 'kernels_ms_per_step': {k: v[1] / args.steps for k, v in kt.items()}, 'energy': energy,
+                'fp64_peak_dfma_per_s': dfma.value, 'fp64_peak_dmma_fma_per_s': dmma.value}
+        if 'bytes_per_step' in roofdesc:
+            b = roofdesc['bytes_per_step']
+            line['iteration_bytes'] = {'algorithmic_bytes_per_time_step': b, 'achieved_GBps': b * NT / (ms_per_step * 1e-3) / 1e9,
+                                       'frac_of_hbm_peak': b * NT / (ms_per_step * 1e-3) / 1e9 / peak}
+        if graph_ms is not None:
+            line['cuda_graph_replay'] = ({'ms_per_step': graph_ms, 'value': NT / (graph_ms * 1e-3), 'unit': UNIT,
+                                          'note': 'the same iteration captured once with torch.cuda.graph and replayed'}
+                                         if not isinstance(graph_ms, str) else {'note': graph_ms})
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -502,8 +721,12 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         main_reference(args)
-    else:
+    elif args.workload in ('C2', 'C5'):
         main_gpu(args)
+    else:
+        if args.workload == 'C4' and args.steps > 3:
+            args.steps = 2   # one C4 iteration takes seconds
+        main_generic(args)
 
 
 if __name__ == '__main__':

@@ -89,6 +89,9 @@ int bn_timing_report(char* buf_host, size_t len);
 /* fp64 FMA rate of the current device (DFMA per second, 8 chains/thread, full occupancy): the
  * denominator of the fp64 roofline bench.py reports beside the HBM one.  scratch: >= 8*SMs*256 doubles. */
 int bn_measure_dfma_peak(double* scratch, size_t scratch_doubles, double* dfma_per_s_host);
+/* the same for the fp64 tensor pipe (mma.sync.m8n8k4.f64 = DMMA.8x8x4): fused multiply-adds per second; the roofline
+ * denominator of the dense spatio-temporal kernels (bench.py --workload C4) */
+int bn_measure_dmma_peak(double* scratch, size_t scratch_doubles, double* fma_per_s_host);
 
 /* ---- discretisation: As[N,d,d], Qs[N,d,d] from dt[N] -------------------------------------- */
 int bn_state_dim(const bn_kernel_spec* k);

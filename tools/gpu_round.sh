@@ -16,6 +16,11 @@ for w in $what; do
     reftests) timeout 900 python -m pytest tests/test_reference_golden.py -m gpu -q > gpurun_out/${tag}_ref_tests.log 2>&1; tail -15 gpurun_out/${tag}_ref_tests.log;;
     mgputests) timeout 1500 python -m pytest tests/test_distributed_gpu.py tests/test_latent_sharding.py -m gpu -q > gpurun_out/${tag}_mgpu_tests_n${NG}.log 2>&1; tail -8 gpurun_out/${tag}_mgpu_tests_n${NG}.log;;
     mgpubench) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${NG} --steps 10 --no-cpu --no-grad > gpurun_out/${tag}_bench_c5_n${NG}.json 2> gpurun_out/${tag}_bench_c5_n${NG}.err; tail -c 3000 gpurun_out/${tag}_bench_c5_n${NG}.json; tail -5 gpurun_out/${tag}_bench_c5_n${NG}.err;;
+    c1) timeout 600 python bench.py --workload C1 --steps 50 > gpurun_out/${tag}_bench_c1.json 2> gpurun_out/${tag}_bench_c1.err; head -c 2500 gpurun_out/${tag}_bench_c1.json; tail -3 gpurun_out/${tag}_bench_c1.err;;
+    c3) timeout 900 python bench.py --workload C3 --steps 10 > gpurun_out/${tag}_bench_c3.json 2> gpurun_out/${tag}_bench_c3.err; head -c 2500 gpurun_out/${tag}_bench_c3.json; tail -3 gpurun_out/${tag}_bench_c3.err;;
+    c4) timeout 1500 python bench.py --workload C4 --steps 2 --warmup 3 > gpurun_out/${tag}_bench_c4.json 2> gpurun_out/${tag}_bench_c4.err; head -c 3500 gpurun_out/${tag}_bench_c4.json; tail -3 gpurun_out/${tag}_bench_c4.err;;
+    c5full) timeout 1200 python bench.py > gpurun_out/${tag}_bench_c5_default.json 2> gpurun_out/${tag}_bench_c5_default.err; head -c 5000 gpurun_out/${tag}_bench_c5_default.json; tail -3 gpurun_out/${tag}_bench_c5_default.err;;
+    refarm) timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; head -c 2500 gpurun_out/${tag}_bench_ref.json; tail -3 gpurun_out/${tag}_bench_ref.err;;
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python tools/prof_iter.py 10000000 3 > gpurun_out/${tag}_under_ncu.log 2>&1
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'it_(reduce|filter|smooth)' -s 5 -c 5 -o gpurun_out/${tag}_c2_full python tools/prof_iter.py 10000000 2 > gpurun_out/${tag}_ncu.log 2>&1
