@@ -82,6 +82,7 @@ SIGNATURES = {
     'bn_up_shard_smooth': (_I, [_KS, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_site_update': (_I, [_SA, _P, _Z, _P]),
     'bn_likelihood_stats': (_I, [_SA, _P, _P, _P, _P, _Z, _P]),
+    'bn_likelihood_param_grad': (_I, [_SA, _P, _P, _Z, _P]),
     'bn_expected_density': (_I, [_SA, _P, _P, _P, _Z, _P]),
     'bn_energy_terms': (_I, [_SA, _P, _P, _P, _Z, _P]),
     'bn_gaussian_expected_log_lik': (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

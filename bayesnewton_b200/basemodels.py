@@ -199,9 +199,11 @@ class MarkovGaussianProcess:
         (the reference evaluates the identical filter a second time inside energy(), basemodels.py:733)."""
         pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
         self._grad_cache = None
-        if want_grad and not (self.parallel and self._hyper_key() is not None):
-            raise NotImplementedError('the hyper-gradient needs the fused scan-form update (parallel=True, kernel.spec())')
-        if self.parallel and self._hyper_key() is not None:
+        if want_grad and self._hyper_key() is None:
+            raise NotImplementedError('the hyper-gradient needs a kernel with an in-library discretisation (kernel.spec())')
+        # the gradient pass always runs the fused scan-form update: for parallel=False models too (same posterior and
+        # gradient to rounding; the sequential form has no adjoint kernel of its own)
+        if (self.parallel or want_grad) and self._hyper_key() is not None:
             out = ops.update_posterior(self.dt, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
                                        want_ell=True, want_grad=want_grad)
             ell, sm, sP = out[:3]

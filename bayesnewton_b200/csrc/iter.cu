@@ -95,7 +95,7 @@ template <typename T>
 static int it_transpose(const bn_kernel_spec* k, int64_t N, const T* in, T* out, T fill, bool to_tiled, cudaStream_t st) {
     if (int rc = it_check_spec(k, N)) return rc;
     BN_REQUIRE(in && out, "null array");
-    const ChunkPlan cp = up_plan_chunks(N, false);
+    const ChunkPlan cp = up_plan_chunks(N, false, family_dim(k->family));
     const long long tiles = (cp.nchunks + 31) / 32;
     dim3 grid((unsigned)tiles, (unsigned)((cp.L + 31) / 32));
     if (to_tiled) {
@@ -114,12 +114,12 @@ using namespace bn;
 
 extern "C" int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N) {
     if (it_check_spec(k, N)) return -1;
-    return up_plan_chunks(N, false).L;
+    return up_plan_chunks(N, false, family_dim(k->family)).L;
 }
 
 extern "C" int64_t bn_iter_tiled_len(const bn_kernel_spec* k, int64_t N) {
     if (it_check_spec(k, N)) return -1;
-    const ChunkPlan cp = up_plan_chunks(N, false);
+    const ChunkPlan cp = up_plan_chunks(N, false, family_dim(k->family));
     return tl_len(cp.nchunks, cp.L);
 }
 

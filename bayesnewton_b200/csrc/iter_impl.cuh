@@ -396,7 +396,9 @@ struct EpiEnergy {
 #include "tma_stage.cuh"
 namespace bn {
 // ------------------------------------------------------------------------------------------ kernels
-constexpr int kItTabThreads = 512;  // the table-gathering sweeps own a whole SM: one CTA, 16 warps, the table in shared memory
+// the table-gathering sweeps own a whole SM: one CTA with the table in shared memory, 16 warps (d <= 3) or the 4 warps the
+// registers of a larger state leave room for
+template <class G> constexpr int kItTabThreads = (G::d <= 3) ? 512 : kUpThreads;
 
 template <class G>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
@@ -470,7 +472,7 @@ it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const double* spr
 int probit_table_device(cudaStream_t st, const double** tab);
 
 template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
-__global__ void __launch_bounds__(TAB ? kItTabThreads : kUpThreads, TAB ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
+__global__ void __launch_bounds__(TAB ? kItTabThreads<G> : kUpThreads, TAB ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
 it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs a, int L, long long nchunks,
                       const double* sprefix, const double* sinit, const double* fs, const double* gtab) {
     extern __shared__ __align__(16) double it_smem[];
@@ -543,7 +545,7 @@ struct ItCall {
 };
 
 template <int d>
-inline size_t it_ws_doubles(long long N) { return up_ws_doubles<d>(N) + 4 * (size_t)up_plan_chunks(N > 0 ? N : 1).nchunks + 64; }
+inline size_t it_ws_doubles(long long N) { return up_ws_doubles<d>(N) + 4 * (size_t)up_plan_chunks(N > 0 ? N : 1, false, d).nchunks + 64; }
 
 // speculative phase 1 pays off when the chunks are much longer than the filter's forgetting time
 constexpr int kSpecMinChunk = 256;
@@ -568,8 +570,8 @@ inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp
                 const double* gtab = nullptr;                                                                          \
                 if (int rc = probit_table_device(st, &gtab)) return rc;                                                \
                 BN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-                const unsigned grid = (unsigned)((cp.nchunks + kItTabThreads - 1) / kItTabThreads);                    \
-                BN_LAUNCH(name, st, (kfn<<<grid, kItTabThreads, smem, st>>>(g, c.io, *c.cub, sa, cp.L, cp.nchunks,     \
+                const unsigned grid = (unsigned)((cp.nchunks + kItTabThreads<G> - 1) / kItTabThreads<G>);              \
+                BN_LAUNCH(name, st, (kfn<<<grid, kItTabThreads<G>, smem, st>>>(g, c.io, *c.cub, sa, cp.L, cp.nchunks,  \
                                                                             w.splan.prefix[0], w.sinit, w.fs, gtab))); \
                 BN_CUDA(cudaGetLastError());                                                                           \
                 return 0;                                                                                              \
@@ -596,7 +598,7 @@ inline int it_run(const ItCall& c) {
     const ItIO& io = c.io;
     G g;
     g.prepare(*c.spec);
-    ChunkPlan cp = up_plan_chunks(io.N, false);
+    ChunkPlan cp = up_plan_chunks(io.N, false, d);
     const size_t need = it_ws_doubles<d>(io.N) * sizeof(double);
     BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
     UpWs w = up_ws<d>(c.ws, cp);

@@ -158,6 +158,37 @@ ep_pseudo_kernel(long long N, double power, int with_const, const double* py, co
     block_sum_store<kSiteThreads>(v, part);
 }
 
+// d (likelihood term of energy()) / d (Gaussian variance), summed over the steps: the route from the likelihood's
+// hyper-parameter to the energy (the posterior and the sites are StateVars; objax.GradValues(model.energy, model.vars()),
+// README.md:56-70).  VI: E_q[log N(y | f, s2)] (likelihoods.py:727-753);  Newton: log N(y | m, s2) (:336-355);
+// EP: log N(y | m_c, s2 / a + v_c) + pep_constant(s2, a) at the cavity (:755-782, utils.py:431-445, 534-541).
+template <int METHOD>
+__global__ void __launch_bounds__(kSiteThreads)
+gaussian_param_grad_kernel(const __grid_constant__ bn_site_args a, double* part) {
+    const long long n = (long long)blockIdx.x * kSiteThreads + threadIdx.x;
+    double v = 0.0;
+    if (n < a.N) {
+        const double y = a.y[n], s2 = a.lik_param;
+        if (!isnan(y)) {
+            double m = a.post_mean[n], c = a.post_cov[n];
+            if constexpr (METHOD == BN_METHOD_EP) {  // compute_cavity, utils.py:534-541
+                const double pn2 = inv1(c + 1e-8);
+                c = inv1(pn2 - a.power * a.nat2[n]);
+                m = c * (pn2 * m - a.power * a.nat1[n]);
+                const double var = s2 / a.power + c, r = y - m;
+                v = (-0.5 / var + 0.5 * r * r / (var * var)) / a.power + 0.5 * (1.0 - a.power) / s2;
+            } else if constexpr (METHOD == BN_METHOD_VI) {
+                const double r = y - m;
+                v = -0.5 / s2 + 0.5 * (r * r + c) / (s2 * s2);
+            } else {
+                const double r = y - m;
+                v = -0.5 / s2 + 0.5 * r * r / (s2 * s2);
+            }
+        }
+    }
+    block_sum_store<kSiteThreads>(v, part);
+}
+
 static int check_site_args(const bn_site_args* a, bool need_y = true) {
     BN_REQUIRE(a != nullptr, "site args are null");
     BN_REQUIRE(a->N >= 0, "N must be non-negative");
@@ -325,6 +356,28 @@ extern "C" int bn_energy_terms(const bn_site_args* a, const uint8_t* mask, doubl
 #undef X
     set_error("unsupported (likelihood, method) = (%d, %d)", a->likelihood, a->method);
     return -1;
+}
+
+extern "C" int bn_likelihood_param_grad(const bn_site_args* a, double* sum, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+    if (int rc = check_site_args(a)) return rc;
+    BN_REQUIRE(sum != nullptr, "sum output is null");
+    BN_REQUIRE(a->likelihood == BN_LIK_GAUSSIAN, "only the Gaussian likelihood carries a trainable parameter (its variance)");
+    BN_REQUIRE(a->method == BN_METHOD_VI || a->method == BN_METHOD_NEWTON || a->method == BN_METHOD_EP,
+               "the likelihood-parameter gradient is built for VI, Newton and EP");
+    if (a->method == BN_METHOD_EP) BN_REQUIRE(a->nat1 && a->nat2, "EP needs the site natural parameters for the cavity");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->N == 0) { BN_CUDA(cudaMemsetAsync(sum, 0, sizeof(double), st)); return 0; }
+    const unsigned grid = (unsigned)((a->N + kSiteThreads - 1) / kSiteThreads);
+    BN_REQUIRE(workspace && workspace_bytes >= (size_t)grid * sizeof(double), "workspace too small for %u partials", grid);
+    double* part = (double*)workspace;
+    if (a->method == BN_METHOD_VI) gaussian_param_grad_kernel<BN_METHOD_VI><<<grid, kSiteThreads, 0, st>>>(*a, part);
+    else if (a->method == BN_METHOD_NEWTON) gaussian_param_grad_kernel<BN_METHOD_NEWTON><<<grid, kSiteThreads, 0, st>>>(*a, part);
+    else gaussian_param_grad_kernel<BN_METHOD_EP><<<grid, kSiteThreads, 0, st>>>(*a, part);
+    BN_CUDA(cudaGetLastError());
+    sum_kernel<false><<<1, 1024, 0, st>>>(part, grid, sum, 1.0);
+    BN_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* d2, void* workspace,

@@ -27,9 +27,10 @@ __device__ __forceinline__ void tma_stage_to_smem(void* smem_dst, const void* gs
         }
     }
     uint32_t done = 0;
-    while (!done) {
+    for (uint32_t spins = 0; !done; ++spins) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(bar_a) : "memory");
+        if (spins > (1u << 24)) __trap();  // a copy that never lands is an error, not a hang
     }
 }
 

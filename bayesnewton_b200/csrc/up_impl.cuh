@@ -48,8 +48,10 @@ struct UpIO {
     double* post_cov;           // [N,D,D]   H sP H^T
 };
 
-inline ChunkPlan up_plan_chunks(long long N, bool grad = false) {
-    const long long target = grad ? 148LL * kUpGradBlocksPerSM * kUpThreads : kUpTargetChunks;
+// one resident wave of chunk threads: the kernels of states with d > 3 are compiled for one CTA per SM (registers), so
+// their wave -- and with it the number of chunk elements the scan has to combine -- is four times smaller
+inline ChunkPlan up_plan_chunks(long long N, bool grad = false, int d = 3) {
+    const long long target = (d > 3) ? 148LL * kUpThreads : (grad ? 148LL * kUpGradBlocksPerSM * kUpThreads : kUpTargetChunks);
     long long L = (N + target - 1) / target;
     L = (L + kUpTJ - 1) / kUpTJ * kUpTJ;
     if (L < kUpTJ) L = kUpTJ;  // no upper bound: for large N the chunk count stays at one resident wave
@@ -618,7 +620,7 @@ inline size_t up_ws_doubles(long long N) {
     // sized for the larger of the two chunk plans (with / without the hyper-gradient accumulation)
     size_t need = 0;
     for (int grad = 0; grad < 2; ++grad) {
-        ChunkPlan cp = up_plan_chunks(N > 0 ? N : 1, grad != 0);
+        ChunkPlan cp = up_plan_chunks(N > 0 ? N : 1, grad != 0, d);
         size_t n = 128 + 64 + scan_plan_doubles(cp.nchunks, FilterAlg<d>::kElem) +
                    scan_plan_doubles(cp.nchunks, SmootherAlg<d>::kElem) + cp.nchunks +
                    (size_t)cp.nchunks * kUpMaxGradFields + fs_doubles(cp.nchunks, cp.L, d + symn(d));
@@ -673,7 +675,7 @@ inline int up_run(const UpCall& c) {
     G g;
     g.prepare(*c.spec);
     static_assert(GradAcc<G>::kFields <= kUpMaxGradFields, "raise kUpMaxGradFields");
-    ChunkPlan cp = up_plan_chunks(io.N, c.grad != 0);
+    ChunkPlan cp = up_plan_chunks(io.N, c.grad != 0, d);
     size_t need = up_ws_doubles<d>(io.N) * sizeof(double);
     BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
     UpWs w = up_ws<d>(c.ws, cp);

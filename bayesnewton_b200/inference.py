@@ -106,6 +106,22 @@ class InferenceMixin:
         g = self.log_lik_grad()
         return self.energy(cubature=cubature), -g
 
+    def energy_grad_likelihood(self, cubature=None):
+        """d energy / d (likelihood hyper-parameter): the Gaussian variance, the only trainable likelihood parameter on
+        the path (likelihoods.py:700-703).  The energy holds it in the likelihood term alone -- VI / Newton
+        E = -(L - KL), EP E = -(lZ + (lel - lel_pseudo) / power) -- so one sum over the steps (bn_likelihood_param_grad)
+        gives it; `likelihood.chain_to_transformed` applies the softplus of the stored variable."""
+        if self.likelihood.lik_id != _lib.BN_LIK_GAUSSIAN:
+            raise NotImplementedError('only the Gaussian likelihood has a trainable hyper-parameter here')
+        if self.method == _lib.BN_METHOD_PL:
+            raise NotImplementedError('likelihood-parameter gradient for posterior linearisation')
+        a, keep = self._site_args(cubature)
+        out = torch.zeros((), dtype=torch.float64, device=self.posterior_mean.device)
+        ws, nb = workspace(a.N, getattr(self, '_site_state_dim', self.state_dim), a.D)
+        _lib.check(_lib.lib().bn_likelihood_param_grad(a, ptr(out), ptr(ws), nb, stream_ptr()))
+        scale = 1.0 / self.power if self.method == _lib.BN_METHOD_EP else 1.0
+        return -scale * out
+
 
 class VariationalInference(InferenceMixin):
     """natural-gradient VI, CVI form (inference.py:160-222)"""

@@ -127,6 +127,10 @@ class Gaussian(Likelihood):
     def lik_param(self):
         return self.variance
 
+    def chain_to_transformed(self, grad):
+        """gradient w.r.t. the variance -> w.r.t. the stored softplus-transformed variable (likelihoods.py:700-710)"""
+        return grad / (1.0 + math.exp(-self.transformed_variance))
+
 
 class Bernoulli(Likelihood):
     """p(y|f) = P^y (1-P)^(1-y), P = link(f); probit carries the reference's 1e-3 jitter (likelihoods.py:828-829)"""

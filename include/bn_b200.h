@@ -258,6 +258,13 @@ int bn_likelihood_stats(const bn_site_args* a, double* val, double* d1, double* 
 int bn_expected_density(const bn_site_args* a, double* values, double* sum,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* sum_n d(likelihood term of energy())_n / d(lik_param) for the Gaussian likelihood (lik_param = its variance): the route
+ * from the likelihood hyper-parameter to the energy in objax.GradValues(model.energy, model.vars()) (README.md:56-70;
+ * posterior and sites are StateVars).  VI: E_q[log N(y | f, s2)] (likelihoods.py:727-753); Newton: log N(y | m, s2);
+ * EP: log N(y | m_cav, s2 / power + v_cav) + pep_constant (likelihoods.py:755-782), cavity from post + nat.
+ * Missing observations (NaN) contribute 0. */
+int bn_likelihood_param_grad(const bn_site_args* a, double* sum, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The two per-step sums of a single-latent VI / Newton energy in ONE pass over the posterior marginals
  * (inference.py:130-154, 197-222): sums[0] = nansum_n of the scheme's likelihood term (as bn_expected_density),
  * sums[1] = sum_n gaussian_expected_log_lik(site_mean_n, post_mean_n, post_cov_n, site_cov_n, mask_n)

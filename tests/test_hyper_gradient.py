@@ -216,3 +216,41 @@ def test_gpu_grad_large_n_properties(bn):
         em = float(bn.ops.update_posterior(dt_d, bn.kernels.Matern52(1.0 - dv, 1.0 - dl), y_d, R_d, want_ell=True)[0])
         fd = (ep - em) / (2 * h)
         assert abs(fd - g1[row, 0]) <= 1e-5 * abs(fd), (row, fd, g1[row, 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('method', ['vi', 'newton', 'ep'])
+@pytest.mark.parametrize('parallel', [True, False])
+def test_gpu_regression_gradient_triple(bn, method, parallel):
+    """the (lengthscale, variance, likelihood variance) gradient of the energy that the reference's regression test
+    differentiates (tests/test_gp_vs_markovgp_reg.py:77-114), for a Gaussian likelihood: kernel part from the adjoint inside
+    the smoother sweep (also for parallel=False models: the gradient pass runs the scan form), likelihood part from
+    bn_likelihood_param_grad; against central differences of the ORACLE energy with sites and posterior held fixed"""
+    import copy
+    x, y = classification_data(300, seed=5)
+    rng = np.random.default_rng(2)
+    y = np.sin(0.3 * x) + 0.4 * rng.standard_normal(x.shape[0])
+    cls = {'vi': bn.models.MarkovVariationalGP, 'newton': bn.models.MarkovLaplaceGP, 'ep': bn.models.MarkovExpectationPropagationGP}[method]
+    kw = dict(power=0.5) if method == 'ep' else {}
+    yy = y.copy()  # no missing targets: the kernel-gradient pass is defined without a mask (see bn_update_posterior_grad)
+    g = cls(kernel=bn.kernels.Matern52(1.2, 4.0), likelihood=bn.likelihoods.Gaussian(0.3), X=x, Y=yy, parallel=parallel, **kw)
+    o = model.MarkovGP(ssm.Matern52(1.2, 4.0), sites.Gaussian(0.3), x, yy, method=method, power=0.5)
+    g.inference(lr=0.7, want_grad=True)
+    o.inference(lr=0.7)
+    E, dE = g.energy_and_grad()
+    assert abs(float(E) - o.energy()) <= TOL * abs(o.energy())
+    dlik = float(g.energy_grad_likelihood())
+
+    def energy_at(var_f=1.2, len_f=4.0, var_y=0.3):
+        o2 = copy.copy(o)
+        o2.kernel = ssm.Matern52(var_f, len_f)
+        o2.likelihood = sites.Gaussian(var_y)
+        return o2.energy()
+    h = 1e-6
+    fd_var = (energy_at(var_f=1.2 + h) - energy_at(var_f=1.2 - h)) / (2 * h)
+    fd_len = (energy_at(len_f=4.0 + h) - energy_at(len_f=4.0 - h)) / (2 * h)
+    fd_lik = (energy_at(var_y=0.3 + h) - energy_at(var_y=0.3 - h)) / (2 * h)
+    dE = dE.cpu().numpy()
+    assert abs(dE[0, 0] - fd_var) <= 1e-6 * max(1.0, abs(fd_var))
+    assert abs(dE[1, 0] - fd_len) <= 1e-6 * max(1.0, abs(fd_len))
+    assert abs(dlik - fd_lik) <= 1e-6 * max(1.0, abs(fd_lik)), (dlik, fd_lik)
