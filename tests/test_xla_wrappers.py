@@ -150,3 +150,13 @@ def test_gpu_xla_filter_smoother_sites(bn):
     torch.cuda.synchronize()
     assert float(got) == float(want) and float(got2) == float(want2)
     assert xla.error_count() == e0, L.bn_last_error()
+
+
+def test_jax_glue_is_import_safe_without_jax():
+    """the JAX side of the boundary (primitives, lowering, custom_vjp) must import cleanly where jax is absent"""
+    from bayesnewton_b200 import jax_glue
+    assert jax_glue.available() in (True, False)
+    if not jax_glue.available():
+        import pytest as _pt
+        with _pt.raises(ImportError):
+            jax_glue.register()
