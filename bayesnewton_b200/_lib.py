@@ -18,6 +18,7 @@ FAMILY_DIM = {BN_MATERN12: 1, BN_MATERN32: 2, BN_MATERN52: 3, BN_MATERN72: 4}
 BN_LIK_GAUSSIAN, BN_LIK_BERNOULLI_PROBIT, BN_LIK_BERNOULLI_LOGIT = 1, 2, 3
 BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_LIK_HETEROSCEDASTIC_EXP = 4, 5
 BN_LIK_POISSON_EXP = 6
+BN_LIK_STUDENTS_T, BN_LIK_GAMMA_EXP, BN_LIK_NEGBIN_EXP, BN_LIK_BETA_PROBIT = 7, 8, 9, 10
 BN_METHOD_VI, BN_METHOD_EP, BN_METHOD_NEWTON, BN_METHOD_PL = 1, 2, 3, 4
 BN_MAX_COMPONENTS = 4
 
@@ -33,7 +34,7 @@ class SiteArgs(C.Structure):
                 ('post_mean', C.c_void_p), ('post_cov', C.c_void_p), ('lr', C.c_double), ('power', C.c_double),
                 ('ensure_psd', C.c_int32), ('pad_', C.c_int32), ('nat1', C.c_void_p), ('nat2', C.c_void_p),
                 ('site_mean', C.c_void_p), ('site_cov', C.c_void_p), ('out_mean', C.c_void_p),
-                ('out_jac', C.c_void_p), ('out_hess', C.c_void_p), ('diffs', C.c_void_p)]
+                ('out_jac', C.c_void_p), ('out_hess', C.c_void_p), ('diffs', C.c_void_p), ('lik_param2', C.c_double)]
 
 
 class IterArgs(C.Structure):
@@ -89,6 +90,7 @@ SIGNATURES = {
     'bn_ep_pseudo_density': (_I, [_L, _I, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'bn_temporal_conditional': (_I, [_KS, _L, _P, _L, _P, _P, _P, _P, _I, _P, _P, _P]),
     'bn_likelihood_predict': (_I, [_I, _D, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
+    'bn_likelihood_predict2': (_I, [_I, _D, _D, _L, _P, _P, _I, _P, _P, _P, _P, _P]),
     'bn_pairs_discretise': (_I, [_KS, _L, _P, _P, _P, _P]),
     'bn_build_joint': (_I, [_KS, _L, _P, _P, _P, _P, _P, _P]),
     'bn_sparse_workspace_bytes': (_Z, [_L]),

@@ -182,7 +182,7 @@ class MarkovGaussianProcess:
             st.set_data(Y, self.mask_pseudo_y, scan_nan=not labels)
 
     def _energy_key(self, cubature):
-        return (self.pseudo_likelihood.version, self._hyper_key(), float(self.likelihood.lik_param),
+        return (self.pseudo_likelihood.version, self._hyper_key(), float(self.likelihood.lik_param), float(self.likelihood.lik_param2),
                 fused.cubature_key(cubature), self.method)
 
     def _hyper_key(self):

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) temporal_conditional_kernel(Gen gen, TcAr
 // E[y], Var[y] for a scalar latent per point: Gaussian closed form, Bernoulli by 1-D cubature
 __device__ __forceinline__ double probit_p(double f) { return 0.5 * (1.0 + erf(f * 0.7071067811865476)) * (1.0 - 2e-3) + 1e-3; }
 
-__global__ void likelihood_predict_kernel(int lik, double param, long long N, const double* mean_f, const double* var_f,
+__global__ void likelihood_predict_kernel(int lik, double param, double param2, long long N, const double* mean_f, const double* var_f,
                                           int Q, const double* cx, const double* cw, double* mean_y, double* var_y) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N) return;
@@ -135,6 +135,22 @@ __global__ void likelihood_predict_kernel(int lik, double param, long long N, co
             const double mu = param * exp(f);
             e1 = fma(cw[i], mu, e1);
             e2 = fma(cw[i], mu + mu * mu, e2);
+            continue;
+        }
+        if (lik == BN_LIK_STUDENTS_T || lik == BN_LIK_GAMMA_EXP || lik == BN_LIK_NEGBIN_EXP || lik == BN_LIK_BETA_PROBIT) {
+            double E, V;  // conditional moments, likelihoods.py:1043-1044, 1095-1097, 1136-1138, 1184-1189
+            if (lik == BN_LIK_STUDENTS_T) {
+                E = f; V = (param * param) * (param2 / (param2 - 2.0));
+            } else if (lik == BN_LIK_GAMMA_EXP) {
+                const double sc = exp(f);
+                E = param * sc; V = param * (sc * sc);
+            } else if (lik == BN_LIK_NEGBIN_EXP) {
+                E = exp(f) * param2; V = E + E * E * param;
+            } else {
+                E = probit_p(f); V = (E - E * E) / (param + 1.0);
+            }
+            e1 = fma(cw[i], E, e1);
+            e2 = fma(cw[i], V + E * E, e2);
             continue;
         }
         const double p = lik == BN_LIK_BERNOULLI_PROBIT ? probit_p(f) : 1.0 / (1.0 + exp(-f));
@@ -177,8 +193,15 @@ extern "C" int bn_temporal_conditional(const bn_kernel_spec* k, int64_t N, const
 extern "C" int bn_likelihood_predict(int likelihood, double lik_param, int64_t N, const double* mean_f, const double* var_f,
                                      int Q, const double* cub_x, const double* cub_w, double* mean_y, double* var_y,
                                      void* stream) {
+    return bn_likelihood_predict2(likelihood, lik_param, 0.0, N, mean_f, var_f, Q, cub_x, cub_w, mean_y, var_y, stream);
+}
+
+extern "C" int bn_likelihood_predict2(int likelihood, double lik_param, double lik_param2, int64_t N, const double* mean_f,
+                                      const double* var_f, int Q, const double* cub_x, const double* cub_w, double* mean_y,
+                                      double* var_y, void* stream) {
     BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || likelihood == BN_LIK_BERNOULLI_PROBIT || likelihood == BN_LIK_BERNOULLI_LOGIT ||
-                   likelihood == BN_LIK_POISSON_EXP,
+                   likelihood == BN_LIK_POISSON_EXP || likelihood == BN_LIK_STUDENTS_T || likelihood == BN_LIK_GAMMA_EXP ||
+                   likelihood == BN_LIK_NEGBIN_EXP || likelihood == BN_LIK_BETA_PROBIT,
                "likelihood %d has no single-latent predict on this path", likelihood);
     BN_REQUIRE(N >= 0, "N must be non-negative");
     if (N == 0) return 0;
@@ -186,7 +209,7 @@ extern "C" int bn_likelihood_predict(int likelihood, double lik_param, int64_t N
     BN_REQUIRE(likelihood == BN_LIK_GAUSSIAN || (Q >= 1 && cub_x && cub_w), "a cubature rule (device arrays) is needed");
     const unsigned grid = (unsigned)((N + 255) / 256);
     BN_LAUNCH("likelihood_predict", (cudaStream_t)stream,
-              likelihood_predict_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(likelihood, lik_param, N, mean_f, var_f, Q, cub_x,
+              likelihood_predict_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(likelihood, lik_param, lik_param2, N, mean_f, var_f, Q, cub_x,
                                                                              cub_w, mean_y, var_y));
     BN_CUDA(cudaGetLastError());
     return 0;

@@ -203,6 +203,12 @@ static int check_site_args(const bn_site_args* a, bool need_y = true) {
     }
     if (a->likelihood == BN_LIK_GAUSSIAN) BN_REQUIRE(a->lik_param > 0.0, "Gaussian variance must be positive");
     if (a->likelihood == BN_LIK_POISSON_EXP) BN_REQUIRE(a->lik_param > 0.0, "Poisson bin size must be positive");
+    if (a->likelihood == BN_LIK_STUDENTS_T)
+        BN_REQUIRE(a->lik_param > 0.0 && a->lik_param2 > 0.0, "Student-t scale and degrees of freedom must be positive");
+    if (a->likelihood == BN_LIK_GAMMA_EXP) BN_REQUIRE(a->lik_param > 0.0, "Gamma shape must be positive");
+    if (a->likelihood == BN_LIK_NEGBIN_EXP)
+        BN_REQUIRE(a->lik_param > 0.0 && a->lik_param2 > 0.0, "negative-binomial alpha and scale must be positive");
+    if (a->likelihood == BN_LIK_BETA_PROBIT) BN_REQUIRE(a->lik_param > 0.0, "Beta scale must be positive");
     if (a->method == BN_METHOD_EP) BN_REQUIRE(a->power > 0.0, "EP power must be positive");
     return 0;
 }

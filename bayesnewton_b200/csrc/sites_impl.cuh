@@ -44,11 +44,29 @@ struct SiteCtx {
     const double* cw2;   // [Q]
 };
 
+// digamma / trigamma: upward recurrence to x >= 10, then the asymptotic series (error below 1e-15 there); what the
+// derivatives of gammaln need for the Beta likelihood's Newton statistics
+BN_DEV double digamma(double x) {
+    double r = 0.0;
+    while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+    const double i = 1.0 / x, i2 = i * i;
+    const double ser = i2 * (1.0 / 12 - i2 * (1.0 / 120 - i2 * (1.0 / 252 - i2 * (1.0 / 240 - i2 * (1.0 / 132 - i2 * (691.0 / 32760 - i2 / 12))))));
+    return r + log(x) - 0.5 * i - ser;
+}
+BN_DEV double trigamma(double x) {
+    double r = 0.0;
+    while (x < 10.0) { r += 1.0 / (x * x); x += 1.0; }
+    const double i = 1.0 / x, i2 = i * i;
+    const double ser = i * i2 * (1.0 / 6 - i2 * (1.0 / 30 - i2 * (1.0 / 42 - i2 * (1.0 / 30 - i2 * (5.0 / 66 - i2 * (691.0 / 2730 - i2 * (7.0 / 6)))))));
+    return r + i + 0.5 * i2 + ser;
+}
+
 // ------------------------------------------------------------------------------ single-latent likelihoods
 template <int LIK, bool TAB = false>
 struct Lik1 {
-    double param;       // Gaussian variance / Poisson bin size
+    double param;       // Gaussian variance / Poisson bin size / Student-t scale / Gamma shape / NegBin alpha / Beta scale
     const double* tab;  // TAB: probit log-density table (probit_table.cuh)
+    double param2 = 0.0;  // Student-t degrees of freedom / NegBin scale
 
     BN_DEV double prob(double f) const {
         if constexpr (LIK == BN_LIK_BERNOULLI_LOGIT) return 1.0 / (1.0 + exp(-f));
@@ -61,6 +79,20 @@ struct Lik1 {
         } else if constexpr (LIK == BN_LIK_POISSON_EXP) {
             const double mu = exp(f) * param;  // likelihoods.py:939-940
             return y * log(mu) - mu - lgamma(y + 1.0);
+        } else if constexpr (LIK == BN_LIK_STUDENTS_T) {  // likelihoods.py:1031-1041; param = scale, param2 = df
+            const double df = param2, z = (y - f) / param;
+            const double c = lgamma((df + 1.0) * 0.5) - lgamma(df * 0.5) - 0.5 * (log(param * param) + log(df) + log(3.141592653589793));
+            return c - 0.5 * (df + 1.0) * log(1.0 + (1.0 / df) * (z * z));
+        } else if constexpr (LIK == BN_LIK_GAMMA_EXP) {  // likelihoods.py:1127-1134; param = shape, scale = exp(f)
+            const double sc = exp(f);
+            return -param * log(sc) - lgamma(param) + (param - 1.0) * log(y) - y / sc;
+        } else if constexpr (LIK == BN_LIK_NEGBIN_EXP) {  // likelihoods.py:1141-1149, 1179-1182; param = alpha, param2 = scale
+            const double m = exp(f) * param2, k = 1.0 / param;
+            return lgamma(k + y) - lgamma(y + 1.0) - lgamma(k) + y * log(m / (m + k)) - k * log(1.0 + m * param);
+        } else if constexpr (LIK == BN_LIK_BETA_PROBIT) {  // likelihoods.py:1081-1093; param = scale
+            const double mean = prob(f), al = mean * param, be = param - al;
+            const double yc = fmin(fmax(y, 1e-6), 1.0 - 1e-6);
+            return (al - 1.0) * log(yc) + (be - 1.0) * log(1.0 - yc) + lgamma(al + be) - lgamma(al) - lgamma(be);
         } else {
             if constexpr (LIK == BN_LIK_BERNOULLI_PROBIT) {
                 if constexpr (TAB) return probit_log_phi(tab, y == 1.0 ? f : -f);  // log(1 - p(f)) = log p(-f)
@@ -80,6 +112,31 @@ struct Lik1 {
             ll = y * log(mu) - mu - lgamma(y + 1.0);
             d1 = y - mu;
             d2 = -mu;
+        } else if constexpr (LIK == BN_LIK_STUDENTS_T) {
+            ll = log_lik(y, f);
+            const double r = y - f, den = param2 * param * param + r * r;
+            d1 = (param2 + 1.0) * r / den;
+            d2 = (param2 + 1.0) * (r * r - param2 * param * param) / (den * den);
+        } else if constexpr (LIK == BN_LIK_GAMMA_EXP) {
+            ll = log_lik(y, f);
+            const double t = y * exp(-f);
+            d1 = -param + t;
+            d2 = -t;
+        } else if constexpr (LIK == BN_LIK_NEGBIN_EXP) {
+            ll = log_lik(y, f);
+            const double m = exp(f) * param2, k = 1.0 / param, s = m + k;
+            d1 = k * (y - m) / s;
+            d2 = -k * m * (k + y) / (s * s);
+        } else if constexpr (LIK == BN_LIK_BETA_PROBIT) {
+            ll = log_lik(y, f);
+            const double mean = prob(f), al = mean * param, be = param - al;
+            const double yc = fmin(fmax(y, 1e-6), 1.0 - 1e-6);
+            const double dmu = (1.0 - 2e-3) * exp(-0.5 * f * f) * kInvSqrt2Pi, ddmu = -f * dmu;
+            const double g = log(yc) - log(1.0 - yc) - digamma(al) + digamma(be);   // d ll / d alpha at beta = scale - alpha
+            const double gp = -trigamma(al) - trigamma(be);
+            const double da = param * dmu;
+            d1 = g * da;
+            d2 = gp * da * da + g * param * ddmu;
         } else {
             double p = prob(f), dp, ddp;
             if constexpr (LIK == BN_LIK_BERNOULLI_LOGIT) {
@@ -105,6 +162,17 @@ struct Lik1 {
             E = f; V = param; dE = 1.0;
         } else if constexpr (LIK == BN_LIK_POISSON_EXP) {
             E = V = dE = exp(f) * param;  // likelihoods.py:952-959
+        } else if constexpr (LIK == BN_LIK_STUDENTS_T) {  // likelihoods.py:1043-1044
+            E = f; V = (param * param) * (param2 / (param2 - 2.0)); dE = 1.0;
+        } else if constexpr (LIK == BN_LIK_GAMMA_EXP) {  // likelihoods.py:1136-1138
+            const double sc = exp(f);
+            E = param * sc; V = param * (sc * sc); dE = E;
+        } else if constexpr (LIK == BN_LIK_NEGBIN_EXP) {  // likelihoods.py:1184-1189
+            E = exp(f) * param2; V = E + E * E * param; dE = E;
+        } else if constexpr (LIK == BN_LIK_BETA_PROBIT) {  // likelihoods.py:1095-1097
+            const double p = prob(f);
+            E = p; V = (p - p * p) / (param + 1.0);
+            dE = (1.0 - 2e-3) * exp(-0.5 * f * f) * kInvSqrt2Pi;
         } else {
             double p = prob(f);
             E = p; V = p - p * p;
@@ -484,7 +552,7 @@ BN_DEV void site_update_step(const bn_site_args& a, const SiteCtx& sc, long long
             }
         }
     } else {
-        Lik1<LIK, TAB> lik{a.lik_param, sc.tab};
+        Lik1<LIK, TAB> lik{a.lik_param, sc.tab, a.lik_param2};
         double o1 = a.nat1[n], o2 = a.nat2[n];
         SiteStats1 s;
         double h, r1, r2;
@@ -515,7 +583,7 @@ BN_DEV double expected_density_step(const bn_site_args& a, const SiteCtx& sc, lo
                                                  a.Q, sc.cx2, sc.cw2);
         return s.val;
     } else {
-        Lik1<LIK, TAB> lik{a.lik_param, sc.tab};
+        Lik1<LIK, TAB> lik{a.lik_param, sc.tab, a.lik_param2};
         constexpr int M = (METHOD == BN_METHOD_PL) ? BN_METHOD_EP : METHOD;  // PL energy = EP energy at power 1
         double o1 = 0.0, o2 = 0.0;
         if (M == BN_METHOD_EP) { o1 = a.nat1[n]; o2 = a.nat2[n]; }
@@ -637,7 +705,7 @@ BN_DEV void likelihood_stats_step(const bn_site_args& a, const SiteCtx& sc, long
             for (int i = 0; i < 4; ++i) d2[4 * n + i] = s.hess[i];
         }
     } else {
-        Lik1<LIK, TAB> lik{a.lik_param, sc.tab};
+        Lik1<LIK, TAB> lik{a.lik_param, sc.tab, a.lik_param2};
         SiteStats1 s = site_stats_1<LIK, METHOD, true, TAB>(lik, a.y ? a.y[n] : 0.0, a.post_mean[n], a.post_cov[n], 0.0,
                                                        0.0, a.power, *sc.cub);
         if (val) val[n] = s.val;
@@ -679,6 +747,14 @@ inline void make_cub1(int Q, const double* x, const double* w, Cub1& c) {
     X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_NEWTON) X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_PL)               \
     X(BN_LIK_POISSON_EXP, BN_METHOD_VI) X(BN_LIK_POISSON_EXP, BN_METHOD_EP)                           \
     X(BN_LIK_POISSON_EXP, BN_METHOD_NEWTON) X(BN_LIK_POISSON_EXP, BN_METHOD_PL)                       \
+    X(BN_LIK_STUDENTS_T, BN_METHOD_VI) X(BN_LIK_STUDENTS_T, BN_METHOD_EP)                             \
+    X(BN_LIK_STUDENTS_T, BN_METHOD_NEWTON) X(BN_LIK_STUDENTS_T, BN_METHOD_PL)                         \
+    X(BN_LIK_GAMMA_EXP, BN_METHOD_VI) X(BN_LIK_GAMMA_EXP, BN_METHOD_EP)                               \
+    X(BN_LIK_GAMMA_EXP, BN_METHOD_NEWTON) X(BN_LIK_GAMMA_EXP, BN_METHOD_PL)                           \
+    X(BN_LIK_NEGBIN_EXP, BN_METHOD_VI) X(BN_LIK_NEGBIN_EXP, BN_METHOD_EP)                             \
+    X(BN_LIK_NEGBIN_EXP, BN_METHOD_NEWTON) X(BN_LIK_NEGBIN_EXP, BN_METHOD_PL)                         \
+    X(BN_LIK_BETA_PROBIT, BN_METHOD_VI) X(BN_LIK_BETA_PROBIT, BN_METHOD_EP)                           \
+    X(BN_LIK_BETA_PROBIT, BN_METHOD_NEWTON) X(BN_LIK_BETA_PROBIT, BN_METHOD_PL)                       \
     X(BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_METHOD_VI) X(BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_METHOD_EP) \
     X(BN_LIK_HETEROSCEDASTIC_SOFTPLUS, BN_METHOD_NEWTON)                                              \
     X(BN_LIK_HETEROSCEDASTIC_EXP, BN_METHOD_VI) X(BN_LIK_HETEROSCEDASTIC_EXP, BN_METHOD_EP)           \

@@ -25,6 +25,7 @@ static void note(int rc) {
 static void fill_site(const bn_xla_site_desc& d, bn_site_args& a) {
     memset(&a, 0, sizeof(a));
     a.method = d.method; a.likelihood = d.likelihood; a.lik_param = d.lik_param;
+    a.lik_param2 = d.lik_param2;
     a.N = d.N; a.D = d.D; a.Q = d.Q;
     a.cub_x = d.cub_x; a.cub_w = d.cub_w;
     a.lr = d.lr; a.power = d.power; a.ensure_psd = d.ensure_psd;

@@ -378,7 +378,7 @@ class TimeShardedMarkovGP:
         key = (pl.version, self.shard.hyper_key())
         self._ell_cache = (ell, key)
         self._grad_cache = None
-        self._energy_cache = (sums, key + (float(self.likelihood.lik_param), fused.cubature_key(cubature)))
+        self._energy_cache = (sums, key + (float(self.likelihood.lik_param), float(self.likelihood.lik_param2), fused.cubature_key(cubature)))
         return d  # local sums of |delta nat1|, |delta nat2| (before damping)
 
     def inference(self, lr=1.0, cubature=None, ensure_psd=True, want_grad=False):
@@ -422,7 +422,7 @@ class TimeShardedMarkovGP:
         from . import fused
         key = (pl.version, self.shard.hyper_key())
         ec = getattr(self, '_energy_cache', None)
-        if ec is not None and ec[1] == key + (float(self.likelihood.lik_param), fused.cubature_key(cubature)):
+        if ec is not None and ec[1] == key + (float(self.likelihood.lik_param), float(self.likelihood.lik_param2), fused.cubature_key(cubature)):
             # the closing pass of the fused inference() summed both terms in its smoother epilogue
             parts[0:2] = ec[0]
             parts[2:3] = self._ell_cache[0]

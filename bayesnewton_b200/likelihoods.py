@@ -32,6 +32,10 @@ class Likelihood:
     def lik_param(self):
         return 0.0
 
+    @property
+    def lik_param2(self):
+        return 0.0
+
     def site_args(self, method, y, mean, cov, cubature=None, power=1.0):
         """bn_site_args with the inputs filled in; returns (args, keepalive)"""
         mean, cov = as_dev(mean), as_dev(cov)
@@ -39,6 +43,7 @@ class Likelihood:
         N = mean.numel() // D
         a = _lib.SiteArgs()
         a.method, a.likelihood, a.lik_param, a.N, a.D = method, self.lik_id, self.lik_param, N, D
+        a.lik_param2 = float(self.lik_param2)
         keep = [mean, cov]
         closed = ((self.lik_id == _lib.BN_LIK_GAUSSIAN and method in (_lib.BN_METHOD_VI, _lib.BN_METHOD_EP))
                   or (self.lik_id == _lib.BN_LIK_POISSON_EXP and method == _lib.BN_METHOD_VI))
@@ -99,8 +104,8 @@ class Likelihood:
         if self.lik_id != _lib.BN_LIK_GAUSSIAN:
             hx, hw, Q = host_table(cubature, 1)
             cx, cw = as_dev(hx.reshape(-1)), as_dev(hw)
-        _lib.check(_lib.lib().bn_likelihood_predict(self.lik_id, float(self.lik_param), N, ptr(m), ptr(v), Q, ptr(cx), ptr(cw),
-                                                    ptr(my), ptr(vy), stream_ptr()))
+        _lib.check(_lib.lib().bn_likelihood_predict2(self.lik_id, float(self.lik_param), float(self.lik_param2), N, ptr(m),
+                                                     ptr(v), Q, ptr(cx), ptr(cw), ptr(my), ptr(vy), stream_ptr()))
         return my, vy
 
     def statistical_linear_regression(self, m, v, cubature=None):
@@ -158,6 +163,84 @@ class Poisson(Likelihood):
     @property
     def lik_param(self):
         return self.binsize
+
+
+class StudentsT(Likelihood):
+    """p(y|f) = St(y | f, scale, df) (likelihoods.py:1011-1044); every scheme goes through the 1-D cubature rule
+    (Newton: the closed derivatives of the log-density)"""
+    lik_id = _lib.BN_LIK_STUDENTS_T
+
+    def __init__(self, scale=1.0, df=3.0, fix_scale=False):
+        self.transformed_scale = softplus_inv(float(scale))
+        self.df, self.fix_scale = float(df), fix_scale
+
+    @property
+    def scale(self):
+        return softplus(self.transformed_scale)
+
+    lik_param = scale
+
+    @property
+    def lik_param2(self):
+        return self.df
+
+
+class Gamma(Likelihood):
+    """p(y|f) = Gamma(y | shape, scale = exp(f)) (likelihoods.py:1100-1138)"""
+    lik_id = _lib.BN_LIK_GAMMA_EXP
+
+    def __init__(self, link='exp', shape=1.0):
+        if link != 'exp':
+            raise NotImplementedError('the logistic link of the Gamma likelihood is not compiled into libbn_b200')
+        self.link = link
+        self.transformed_shape = softplus_inv(float(shape))
+
+    @property
+    def shape(self):
+        return softplus(self.transformed_shape)
+
+    lik_param = shape
+
+
+class NegativeBinomial(Likelihood):
+    """p(y|f) = NB(y | mean = scale exp(f), dispersion alpha) (likelihoods.py:1141-1189)"""
+    lik_id = _lib.BN_LIK_NEGBIN_EXP
+
+    def __init__(self, alpha=1.0, link='exp', scale=1.0):
+        if link != 'exp':
+            raise NotImplementedError('the logistic link of the negative-binomial likelihood is not compiled into libbn_b200')
+        self.link = link
+        self.transformed_alpha = softplus_inv(float(alpha))
+        self.scale = float(scale)
+
+    @property
+    def alpha(self):
+        return softplus(self.transformed_alpha)
+
+    lik_param = alpha
+
+    @property
+    def lik_param2(self):
+        return self.scale
+
+
+class Beta(Likelihood):
+    """p(y|f) = Beta(y | scale m, scale (1 - m)), m = probit link with the reference's 1e-3 jitter
+    (likelihoods.py:1047-1097)"""
+    lik_id = _lib.BN_LIK_BETA_PROBIT
+
+    def __init__(self, link='probit', scale=1.0, fix_scale=False):
+        if link != 'probit':
+            raise NotImplementedError('the logit link of the Beta likelihood is not compiled into libbn_b200')
+        self.link = link
+        self.transformed_scale = softplus_inv(float(scale))
+        self.fix_scale = fix_scale
+
+    @property
+    def scale(self):
+        return softplus(self.transformed_scale)
+
+    lik_param = scale
 
 
 class Probit(Bernoulli):

@@ -24,7 +24,7 @@ class SiteDesc(C.Structure):
     _fields_ = [('method', C.c_int32), ('likelihood', C.c_int32), ('lik_param', C.c_double), ('N', C.c_int64),
                 ('D', C.c_int32), ('Q', C.c_int32), ('lr', C.c_double), ('power', C.c_double),
                 ('ensure_psd', C.c_int32), ('has_mask', C.c_int32), ('workspace_bytes', C.c_uint64),
-                ('cub_w', C.c_double * 400), ('cub_x', C.c_double * MAX_CUB)]
+                ('cub_w', C.c_double * 400), ('cub_x', C.c_double * MAX_CUB), ('lik_param2', C.c_double)]
 
 
 def markov_desc(spec, N, workspace_bytes, form=_lib.BN_SCAN, has_mask=False, want_grad=False, return_predict=False,
@@ -41,6 +41,7 @@ def site_desc(site_args, workspace_bytes, cub_x=None, cub_w=None, has_mask=False
     a = site_args
     d = SiteDesc()
     d.method, d.likelihood, d.lik_param, d.N, d.D, d.Q = a.method, a.likelihood, a.lik_param, a.N, a.D, a.Q
+    d.lik_param2 = a.lik_param2
     d.lr, d.power, d.ensure_psd, d.has_mask, d.workspace_bytes = a.lr, a.power, a.ensure_psd, int(has_mask), int(workspace_bytes)
     if a.Q:
         if a.Q > 400 or a.D * a.Q > MAX_CUB:

@@ -69,10 +69,12 @@ typedef struct {
     double lengthscale[BN_MAX_COMPONENTS];
 } bn_kernel_spec;
 
-/* likelihoods of the site kernels (likelihoods.py:684-860, 891-1008, 1244-1281); lik_param = Gaussian variance /
- * Poisson bin size */
+/* likelihoods of the site kernels (likelihoods.py:684-860, 891-1008, 1011-1189, 1244-1281).
+ *   lik_param  = Gaussian variance | Poisson bin size | Student-t scale | Gamma shape | NegBin alpha | Beta scale
+ *   lik_param2 = Student-t degrees of freedom | NegBin scale                         (0 otherwise) */
 enum { BN_LIK_GAUSSIAN = 1, BN_LIK_BERNOULLI_PROBIT = 2, BN_LIK_BERNOULLI_LOGIT = 3,
-       BN_LIK_HETEROSCEDASTIC_SOFTPLUS = 4, BN_LIK_HETEROSCEDASTIC_EXP = 5, BN_LIK_POISSON_EXP = 6 };
+       BN_LIK_HETEROSCEDASTIC_SOFTPLUS = 4, BN_LIK_HETEROSCEDASTIC_EXP = 5, BN_LIK_POISSON_EXP = 6,
+       BN_LIK_STUDENTS_T = 7, BN_LIK_GAMMA_EXP = 8, BN_LIK_NEGBIN_EXP = 9, BN_LIK_BETA_PROBIT = 10 };
 
 /* inference schemes (inference.py:99-428) */
 enum { BN_METHOD_VI = 1, BN_METHOD_EP = 2, BN_METHOD_NEWTON = 3, BN_METHOD_PL = 4 };
@@ -238,6 +240,7 @@ typedef struct {
     double* out_jac;       /* [N,D,1] */
     double* out_hess;      /* [N,D,D] */
     double* diffs;         /* [2] mean |delta nat1|, mean |delta nat2| (inference.py:79-80) */
+    double lik_param2;     /* second likelihood parameter (see BN_LIK_*); appended: older callers leave it 0 */
 } bn_site_args;
 
 int bn_site_update(const bn_site_args* a, void* workspace, size_t workspace_bytes, void* stream);
@@ -361,6 +364,10 @@ int bn_temporal_conditional(const bn_kernel_spec* k, int64_t N, const double* x,
  * latents: mean_y[N], var_y[N] from mean_f[N], var_f[N].  cub_x[Q], cub_w[Q]: DEVICE arrays (unused for Gaussian). */
 int bn_likelihood_predict(int likelihood, double lik_param, int64_t N, const double* mean_f, const double* var_f,
                           int Q, const double* cub_x, const double* cub_w, double* mean_y, double* var_y, void* stream);
+/* the same with the second likelihood parameter (Student-t, negative binomial; likelihoods.py:1043-1044, 1184-1189) */
+int bn_likelihood_predict2(int likelihood, double lik_param, double lik_param2, int64_t N, const double* mean_f,
+                           const double* var_f, int Q, const double* cub_x, const double* cub_w, double* mean_y,
+                           double* var_y, void* stream);
 
 /* ---- sparse Markov GP ---------------------------------------------------------
  * kalman_filter_pairs (ops.py:383-426) = bn_pairs_discretise (construct_pair, :411-419: A_pair = [[0,I],[0,A]],

@@ -54,6 +54,7 @@ typedef struct {
     uint64_t workspace_bytes;
     double cub_w[400];
     double cub_x[BN_XLA_MAX_CUBATURE];
+    double lik_param2;       /* second likelihood parameter (bn_site_args.lik_param2) */
 } bn_xla_site_desc;
 
 /* operands: dt[N], pseudo_y[N,D,1], pseudo_var[N,D,D], (mask[N,D,1] u8)

@@ -150,7 +150,8 @@ _TABLE['sin'] = _unary(np.sin, lambda v: _TABLE['cos'](v))
 _TABLE['cos'] = _unary(np.cos, lambda v: -_TABLE['sin'](v))
 _TABLE['tanh'] = _unary(np.tanh, lambda v: 1.0 - _TABLE['tanh'](v) * _TABLE['tanh'](v))
 _TABLE['abs'] = _unary(np.abs, lambda v: np.sign(_primal(v)))
-_TABLE['gammaln'] = _unary(sps.gammaln, lambda v: sps.digamma(_primal(v)))
+_TABLE['digamma'] = _unary(sps.digamma, lambda v: sps.polygamma(1, _primal(v)))
+_TABLE['gammaln'] = _unary(sps.gammaln, lambda v: _TABLE['digamma'](v))
 _TABLE['log1p'] = _unary(np.log1p, lambda v: 1.0 / (1.0 + v))
 
 

@@ -138,6 +138,120 @@ class Poisson:
         return np.exp(f) * self.binsize
 
 
+class StudentsT:
+    """p(y|f) = St(y | f, scale, df); likelihoods.py:1011-1044"""
+    multi_latent = False
+    name = 'studentst'
+
+    def __init__(self, scale=1.0, df=3.0):
+        self.scale, self.df = float(scale), float(df)
+
+    def log_lik(self, y, f):
+        from scipy.special import gammaln
+        c = gammaln((self.df + 1.0) * 0.5) - gammaln(self.df * 0.5) - 0.5 * (np.log(np.square(self.scale)) + np.log(self.df) + np.log(np.pi))
+        return c - 0.5 * (self.df + 1.0) * np.log(1.0 + (1.0 / self.df) * np.square((y - f) / self.scale))
+
+    def log_lik_derivs(self, y, f):
+        r, a = y - f, self.df * self.scale ** 2
+        return self.log_lik(y, f), (self.df + 1.0) * r / (a + r * r), (self.df + 1.0) * (r * r - a) / (a + r * r) ** 2
+
+    def conditional_moments(self, f):
+        return f, (self.scale ** 2) * (self.df / (self.df - 2.0)) * np.ones_like(f)
+
+    def dconditional_mean(self, f):
+        return np.ones_like(f)
+
+
+class Gamma:
+    """p(y|f) = Gamma(y | shape, scale = exp(f)); likelihoods.py:1100-1138"""
+    multi_latent = False
+    name = 'gamma'
+
+    def __init__(self, shape=1.0):
+        self.shape = float(shape)
+
+    def log_lik(self, y, f):
+        from scipy.special import gammaln
+        sc = np.exp(f)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            return -self.shape * np.log(sc) - gammaln(self.shape) + (self.shape - 1.0) * np.log(y) - y / sc
+
+    def log_lik_derivs(self, y, f):
+        t = y * np.exp(-f)
+        return self.log_lik(y, f), -self.shape + t, -t
+
+    def conditional_moments(self, f):
+        sc = np.exp(f)
+        return self.shape * sc, self.shape * sc ** 2
+
+    def dconditional_mean(self, f):
+        return self.shape * np.exp(f)
+
+
+class NegativeBinomial:
+    """p(y|f) = NB(y | mean scale exp(f), alpha); likelihoods.py:1141-1189"""
+    multi_latent = False
+    name = 'negbin'
+
+    def __init__(self, alpha=1.0, scale=1.0):
+        self.alpha, self.scale = float(alpha), float(scale)
+
+    def log_lik(self, y, f):
+        from scipy.special import gammaln
+        m, k = np.exp(f) * self.scale, 1.0 / self.alpha
+        return gammaln(k + y) - gammaln(y + 1) - gammaln(k) + y * np.log(m / (m + k)) - k * np.log(1 + m * self.alpha)
+
+    def log_lik_derivs(self, y, f):
+        m, k = np.exp(f) * self.scale, 1.0 / self.alpha
+        return self.log_lik(y, f), k * (y - m) / (m + k), -k * m * (k + y) / (m + k) ** 2
+
+    def conditional_moments(self, f):
+        E = np.exp(f) * self.scale
+        return E, E + E ** 2 * self.alpha
+
+    def dconditional_mean(self, f):
+        return np.exp(f) * self.scale
+
+
+class Beta:
+    """p(y|f) = Beta(y | scale m, scale (1 - m)), m = jittered probit link; likelihoods.py:1047-1097"""
+    multi_latent = False
+    name = 'beta'
+
+    def __init__(self, scale=1.0):
+        self.scale = float(scale)
+
+    def link(self, f):
+        return 0.5 * (1.0 + _erf(f / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
+
+    def dlink(self, f):
+        return (1 - 2e-3) * np.exp(-0.5 * f * f) / np.sqrt(2 * np.pi)
+
+    def log_lik(self, y, f):
+        from scipy.special import gammaln
+        al = self.link(f) * self.scale
+        be = self.scale - al
+        y = np.clip(y, 1e-6, 1. - 1e-6)
+        return (al - 1.0) * np.log(y) + (be - 1.0) * np.log(1.0 - y) + gammaln(al + be) - gammaln(al) - gammaln(be)
+
+    def log_lik_derivs(self, y, f):
+        from scipy.special import digamma, polygamma
+        al = self.link(f) * self.scale
+        be = self.scale - al
+        yc = np.clip(y, 1e-6, 1. - 1e-6)
+        g = np.log(yc) - np.log(1.0 - yc) - digamma(al) + digamma(be)
+        gp = -polygamma(1, al) - polygamma(1, be)
+        da = self.scale * self.dlink(f)
+        return self.log_lik(y, f), g * da, gp * da * da + g * self.scale * (-f * self.dlink(f))
+
+    def conditional_moments(self, f):
+        p = self.link(f)
+        return p, (p - p ** 2) / (self.scale + 1.0)
+
+    def dconditional_mean(self, f):
+        return self.dlink(f)
+
+
 class HeteroscedasticNoise:
     """p(y|f1,f2) = N(y | f1, link(f2)^2); likelihoods.py:1244-1281"""
     multi_latent = True

@@ -104,15 +104,16 @@ class SiteArgs(C.Structure):
                 ('post_mean', C.c_void_p), ('post_cov', C.c_void_p), ('lr', C.c_double), ('power', C.c_double),
                 ('ensure_psd', C.c_int32), ('pad_', C.c_int32), ('nat1', C.c_void_p), ('nat2', C.c_void_p),
                 ('site_mean', C.c_void_p), ('site_cov', C.c_void_p), ('out_mean', C.c_void_p),
-                ('out_jac', C.c_void_p), ('out_hess', C.c_void_p), ('diffs', C.c_void_p)]
+                ('out_jac', C.c_void_p), ('out_hess', C.c_void_p), ('diffs', C.c_void_p), ('lik_param2', C.c_double)]
 
 
 METHODS = {'vi': 1, 'ep': 2, 'newton': 3, 'pl': 4}
-LIKS = {'gaussian': 1, 'probit': 2, 'logit': 3, 'het_softplus': 4, 'het_exp': 5}
+LIKS = {'gaussian': 1, 'probit': 2, 'logit': 3, 'het_softplus': 4, 'het_exp': 5, 'poisson': 6, 'studentst': 7, 'gamma': 8,
+        'negbin': 9, 'beta': 10}
 
 
 def site_update(lib, method, lik, lik_param, y, post_mean, post_cov, nat1, nat2, lr=1.0, power=1.0, ensure_psd=True,
-                cub=None, use_table=True):
+                cub=None, use_table=True, lik_param2=0.0):
     """returns dict with new nat1, nat2, site_mean, site_cov, mean, jac, hess, diffs"""
     N, D = post_mean.shape[0], post_mean.shape[1]
     keep = []
@@ -123,6 +124,7 @@ def site_update(lib, method, lik, lik_param, y, post_mean, post_cov, nat1, nat2,
         return a
     a = SiteArgs()
     a.method, a.likelihood, a.lik_param, a.N, a.D = METHODS[method], LIKS[lik], lik_param, N, D
+    a.lik_param2 = lik_param2
     if cub is not None:
         cx, cw = arr(cub[0]), arr(cub[1])
         a.Q, a.cub_x, a.cub_w = cw.shape[0], cx.ctypes.data, cw.ctypes.data

@@ -102,7 +102,17 @@ def test_duplicate_time_stamps_stay_finite_in_scan_form(emu):
 
 
 SITE_CASES = [('probit', lambda: sites.Bernoulli('probit'), 0.0), ('logit', lambda: sites.Bernoulli('logit'), 0.0),
-              ('gaussian', lambda: sites.Gaussian(0.3), 0.3)]
+              ('gaussian', lambda: sites.Gaussian(0.3), 0.3), ('poisson', lambda: sites.Poisson(1.5), 1.5),
+              ('studentst', lambda: sites.StudentsT(0.7, 4.0), (0.7, 4.0)), ('gamma', lambda: sites.Gamma(1.3), 1.3),
+              ('negbin', lambda: sites.NegativeBinomial(0.6, 1.5), (0.6, 1.5)), ('beta', lambda: sites.Beta(3.0), 3.0)]
+
+
+def site_observations(likname, rng, N):
+    return {'gaussian': lambda: rng.standard_normal(N), 'studentst': lambda: 1.5 * rng.standard_t(4.0, size=N),
+            'poisson': lambda: rng.poisson(1.5, size=N).astype(float), 'gamma': lambda: rng.gamma(1.3, 1.3, size=N) + 1e-3,
+            'negbin': lambda: rng.negative_binomial(2, 0.4, size=N).astype(float),
+            'beta': lambda: np.clip(rng.beta(1.5, 2.0, size=N), 1e-3, 1 - 1e-3)}.get(
+                likname, lambda: (rng.uniform(size=N) < 0.5).astype(float))()
 
 
 @pytest.mark.parametrize('likname,mk,lp', SITE_CASES)
@@ -112,15 +122,16 @@ def test_site_update_single_latent(emu, likname, mk, lp, method, lr, power):
     rng = np.random.default_rng(1)
     N = 300
     lik = mk()
-    y = (rng.uniform(size=N) < 0.5).astype(float) if likname != 'gaussian' else rng.standard_normal(N)
+    y = site_observations(likname, rng, N)
     y[::17] = np.nan
+    lp, lp2 = lp if isinstance(lp, tuple) else (lp, 0.0)
     pm = rng.standard_normal((N, 1, 1)); pc = 0.2 + rng.uniform(size=(N, 1, 1))
     n2 = 0.01 + 0.25 * rng.uniform(size=(N, 1, 1)) / pc; n1 = 0.3 * rng.standard_normal((N, 1, 1))
     mean, jac, hess = sites.site_statistics(method, lik, y[:, None], pm, pc, n1, n2, power=power,
                                             mask_pseudo_y=np.isnan(y)[:, None])
     o = sites.damped_site_update(n1, n2, mean, jac, hess, lr)
     e = _emu.site_update(emu, method, likname, lp, y, pm, pc, n1, n2, lr=lr, power=power,
-                         cub=sites.gauss_hermite(1, 20))
+                         cub=sites.gauss_hermite(1, 20), lik_param2=lp2)
     for got, ref in [(e['mean'], mean), (e['jac'], jac), (e['hess'], hess), (e['nat1'], o[0]), (e['nat2'], o[1]),
                      (e['site_mean'], o[2]), (e['site_cov'], o[3])]:
         assert rel_err(got, ref) < TOL

@@ -85,7 +85,12 @@ def test_oracle_filter_smoother_vs_reference(name, par):
 
 def oracle_lik(name):
     return {'probit': sites.Bernoulli(), 'logit': sites.Bernoulli(link='logit'), 'gaussian': sites.Gaussian(0.3),
-            'poisson': sites.Poisson()}[name]
+            'poisson': sites.Poisson(), 'studentst': sites.StudentsT(0.7, 4.0), 'gamma': sites.Gamma(1.0),
+            'negbin': sites.NegativeBinomial(0.6, 1.5), 'beta': sites.Beta(3.0)}[name]
+
+
+LIKS2 = ('studentst', 'gamma', 'negbin', 'beta')
+MODEL2_CASES = [(l, m) for l in LIKS2 for m in ('vi', 'ep', 'newton', 'pl') if not (l == 'negbin' and m == 'newton')]
 
 
 MODEL_CASES = [(l, m) for l in ('probit', 'logit', 'gaussian', 'poisson') for m in ('vi', 'ep', 'newton', 'pl')
@@ -121,9 +126,25 @@ def test_oracle_model_iterations_vs_reference(lik, method, par):
             assert rel_err(ym, g[tag + '_predy_mean'].reshape(-1)) < 1e-10 and rel_err(yv, g[tag + '_predy_var'].reshape(-1)) < 1e-10
 
 
-@pytest.mark.parametrize('lik', ['probit', 'logit', 'gaussian', 'poisson'])
+@pytest.mark.parametrize('lik,method', MODEL2_CASES)
+def test_oracle_model_iterations_more_likelihoods_vs_reference(lik, method):
+    """StudentsT / Gamma / NegativeBinomial / Beta (likelihoods.py:1011-1189): 3 iterations + energy, sequential form"""
+    g = golden('models2')
+    o = model.MarkovGP(ssm.Matern32(0.8, 2.5), oracle_lik(lik), g['x'], g['y_' + lik], method=method, power=0.5, parallel=False)
+    tag = '%s_%s' % (lik, method)
+    for it in range(3):
+        _, (d1, d2) = o.inference(lr=0.3)
+        E = o.energy()
+        assert abs(d1 - g[tag + '_diffs'][it, 0]) <= 1e-10 * abs(g[tag + '_diffs'][it, 0])
+        assert abs(d2 - g[tag + '_diffs'][it, 1]) <= 1e-10 * abs(g[tag + '_diffs'][it, 1])
+        assert abs(E - g[tag + '_energy'][it]) <= 1e-10 * abs(g[tag + '_energy'][it])
+    assert rel_err(o.post_mean, g[tag + '_post_mean']) < 1e-10 and rel_err(o.post_cov, g[tag + '_post_var']) < 1e-10
+    assert rel_err(o.site_nat1, g[tag + '_site_nat1']) < 1e-10 and rel_err(o.site_nat2, g[tag + '_site_nat2']) < 1e-10
+
+
+@pytest.mark.parametrize('lik', ['probit', 'logit', 'gaussian', 'poisson'] + list(LIKS2))
 def test_oracle_likelihood_statistics_vs_reference(lik):
-    g = golden('likelihoods')
+    g = golden('likelihoods2' if lik in LIKS2 else 'likelihoods')
     L = oracle_lik(lik)
     m, v, y = g['m'], g['v'], g['y_' + lik]
     for i in range(m.shape[0]):
@@ -138,6 +159,9 @@ def test_oracle_likelihood_statistics_vs_reference(lik):
         if lik + '_slr' in g.files:
             mu, om, dmu = sites.statistical_linear_regression(L, mi, vi)[:3]
             assert np.allclose([np.squeeze(mu), np.squeeze(om), np.squeeze(dmu)], g[lik + '_slr'][i], rtol=1e-10, atol=1e-13)
+    if lik + '_pred_y' in g.files:
+        ym, yv = predict.likelihood_predict(L, g[lik + '_pred_in'][0], g[lik + '_pred_in'][1])
+        assert np.allclose(ym, g[lik + '_pred_y'][0], rtol=1e-11) and np.allclose(yv, g[lik + '_pred_y'][1], rtol=1e-10)
 
 
 @pytest.mark.parametrize('method', ['vi', 'ep', 'newton'])
@@ -211,8 +235,33 @@ def test_gpu_discretisation_vs_reference(bn, name):
 
 def gpu_lik(bn, name):
     L = bn.likelihoods
-    return {'probit': L.Bernoulli(link='probit'), 'logit': L.Bernoulli(link='logit'), 'gaussian': L.Gaussian(0.3),
-            'poisson': L.Poisson()}[name]
+    return {'probit': lambda: L.Bernoulli(link='probit'), 'logit': lambda: L.Bernoulli(link='logit'),
+            'gaussian': lambda: L.Gaussian(0.3), 'poisson': lambda: L.Poisson(),
+            'studentst': lambda: L.StudentsT(scale=0.7, df=4.0), 'gamma': lambda: L.Gamma(link='exp'),
+            'negbin': lambda: L.NegativeBinomial(alpha=0.6, link='exp', scale=1.5),
+            'beta': lambda: L.Beta(link='probit', scale=3.0)}[name]()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('lik,method', MODEL2_CASES)
+def test_gpu_model_iterations_more_likelihoods_vs_reference(bn, lik, method):
+    g = golden('models2')
+    M = bn.models
+    cls = {'vi': M.MarkovVariationalGP, 'ep': M.MarkovExpectationPropagationGP, 'newton': M.MarkovLaplaceGP,
+           'pl': M.MarkovPosteriorLinearisationGP}[method]
+    kw = dict(power=0.5) if method == 'ep' else {}
+    m = cls(kernel=bn.kernels.Matern32(0.8, 2.5), likelihood=gpu_lik(bn, lik), X=g['x'], Y=g['y_' + lik], parallel=False, **kw)
+    tag = '%s_%s' % (lik, method)
+    for it in range(3):
+        _, (d1, d2) = m.inference(lr=0.3)
+        E = float(m.energy())
+        assert abs(float(d1) - g[tag + '_diffs'][it, 0]) <= TOL * abs(g[tag + '_diffs'][it, 0])
+        assert abs(float(d2) - g[tag + '_diffs'][it, 1]) <= TOL * abs(g[tag + '_diffs'][it, 1])
+        assert abs(E - g[tag + '_energy'][it]) <= TOL * abs(g[tag + '_energy'][it])
+    assert rel_err(np_(m.posterior_mean), g[tag + '_post_mean']) < TOL
+    assert rel_err(np_(m.posterior_variance), g[tag + '_post_var']) < TOL
+    assert rel_err(np_(m.pseudo_likelihood.nat1), g[tag + '_site_nat1']) < TOL
+    assert rel_err(np_(m.pseudo_likelihood.nat2), g[tag + '_site_nat2']) < TOL
 
 
 @pytest.mark.gpu
@@ -251,10 +300,10 @@ def test_gpu_model_iterations_vs_reference(bn, lik, method, par):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('lik', ['probit', 'logit', 'gaussian', 'poisson'])
+@pytest.mark.parametrize('lik', ['probit', 'logit', 'gaussian', 'poisson'] + list(LIKS2))
 def test_gpu_likelihood_statistics_vs_reference(bn, lik):
     """bn_likelihood_stats (the vmapped Likelihood methods) against the reference's per-step results"""
-    g = golden('likelihoods')
+    g = golden('likelihoods2' if lik in LIKS2 else 'likelihoods')
     L = gpu_lik(bn, lik)
     m, v, y = g['m'].reshape(-1, 1, 1), g['v'].reshape(-1, 1, 1), g['y_' + lik]
     e, d1, d2 = L.variational_expectation(y, m, v)
@@ -271,6 +320,9 @@ def test_gpu_likelihood_statistics_vs_reference(bn, lik):
         mu, om, dmu = L.statistical_linear_regression(m, v)
         got = np.stack([np_(mu).reshape(-1), np_(om).reshape(-1), np_(dmu).reshape(-1)], axis=1)
         assert np.allclose(got, g[lik + '_slr'], rtol=1e-9, atol=1e-12)
+    if lik + '_pred_y' in g.files:
+        ym, yv = L.predict(g[lik + '_pred_in'][0], g[lik + '_pred_in'][1])
+        assert np.allclose(np_(ym), g[lik + '_pred_y'][0], rtol=1e-9) and np.allclose(np_(yv), g[lik + '_pred_y'][1], rtol=1e-9)
 
 
 @pytest.mark.gpu
