@@ -54,7 +54,7 @@ def build(force=False, verbose=False, jobs=None):
             futs = [ex.submit(_compile, s, o, verbose) for s, o in todo]
             for f in futs:
                 logs.append(f.result())
-    if todo or not os.path.exists(LIB):
+    if todo or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
         cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -8,8 +8,12 @@
 #include "gen.cuh"
 
 namespace bn {
-
 void set_error(const char* fmt, ...);
+void ktimer_begin(const char* name, cudaStream_t st);
+void ktimer_end(cudaStream_t st);
+}  // namespace bn
+
+namespace BN_NS {
 
 #define BN_REQUIRE(cond, ...)                     \
     do {                                          \
@@ -30,8 +34,6 @@ void set_error(const char* fmt, ...);
 
 // Optional per-kernel device timing (bn_timing_enable / bn_timing_report): when enabled, every
 // launch made through BN_LAUNCH is bracketed by CUDA events on its own stream.
-void ktimer_begin(const char* name, cudaStream_t st);
-void ktimer_end(cudaStream_t st);
 #define BN_LAUNCH(name, st, ...)          \
     do {                                  \
         ::bn::ktimer_begin(name, st);     \
@@ -87,11 +89,11 @@ constexpr int kNotHandled = -1000;
 // sum of n doubles in a fixed order (strided partials, then a shared-memory tree): run-to-run
 // bit-stable, unlike atomics.  NANSUM skips NaNs (np.nansum, inference.py:218).
 template <bool NANSUM>
-__global__ void __launch_bounds__(1024) sum_kernel(const double* x, long long n, double* out, double scale) {
-    __shared__ double sh[1024];
+__global__ void __launch_bounds__(1024) sum_kernel(const real* x, long long n, real* out, real scale) {
+    __shared__ double sh[1024];  // accumulated in fp64 whatever `real` is
     double s = 0.0;
     for (long long i = threadIdx.x; i < n; i += 1024) {
-        double v = x[i];
+        double v = (double)x[i];
         if (NANSUM && isnan(v)) v = 0.0;
         s += v;
     }
@@ -101,22 +103,22 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* x, long long n,
         if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = sh[0] * scale;
+    if (threadIdx.x == 0) *out = real(sh[0] * (double)scale);
 }
 
 // block-level deterministic partial sum: every thread contributes v; thread 0 writes the block total
 template <int THREADS>
-__device__ __forceinline__ void block_sum_store(double v, double* partials) {
+__device__ __forceinline__ void block_sum_store(real v, real* partials) {
     __shared__ double sh_bs[THREADS];
-    sh_bs[threadIdx.x] = v;
+    sh_bs[threadIdx.x] = (double)v;
     __syncthreads();
 #pragma unroll
     for (int off = THREADS / 2; off > 0; off >>= 1) {
         if ((int)threadIdx.x < off) sh_bs[threadIdx.x] += sh_bs[threadIdx.x + off];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partials[blockIdx.x] = sh_bs[0];
+    if (threadIdx.x == 0) partials[blockIdx.x] = real(sh_bs[0]);
     __syncthreads();  // the shared buffer is reused by the next call
 }
 
-}  // namespace bn
+}  // namespace BN_NS

@@ -7,7 +7,7 @@
 #pragma once
 #include "smallmat.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 constexpr double kLog2Pi = 1.8378770664093453;
 constexpr double kInv2Pi = 0.15915494309189535;
@@ -112,7 +112,7 @@ BN_DEV T kf_step(T* m, T* P, const T* A, const T* Q, const T* H, const T* y, con
 // ------------------------------------------------------------------------------------------
 // Filtering algebra.  Element = (A, b, C, J, eta): x_end | x_start, y ~ N(A x_start + b, C) and the
 // information (eta, J) the block's observations carry about x_start.
-template <int d, typename T = double>
+template <int d, typename T = real>
 struct FilterAlg {
     static constexpr int kElem = d * d + d + symn(d) + symn(d) + d;
     static constexpr int kState = d + symn(d);
@@ -438,7 +438,7 @@ BN_DEV void filter_absorb(typename FilterAlg<d, T>::Elem& g, const T* A, const T
 // ------------------------------------------------------------------------------------------
 // Smoothing algebra.  Element (E, g, L): x_k | x_{k+1} ~ N(E x_{k+1} + g, L).  combine(e1, e2)
 // takes e1 = the already accumulated LATER part and e2 = the EARLIER element (ops.py:328-335).
-template <int d, typename T = double>
+template <int d, typename T = real>
 struct SmootherAlg {
     static constexpr int kElem = d * d + d + symn(d);
     static constexpr int kState = d + symn(d);
@@ -589,4 +589,4 @@ BN_DEV void rts_element(const T* fm, const T* fP, const T* A, const T* Q, typena
         }
 }
 
-}  // namespace bn
+}  // namespace BN_NS

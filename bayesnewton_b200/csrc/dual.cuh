@@ -4,7 +4,7 @@
 #pragma once
 #include "smallmat.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 using ::exp;   // keep the double overloads visible next to the Dual ones below
 using ::sqrt;
@@ -32,4 +32,4 @@ BN_DEV Dual sqrt(Dual a) {
     return Dual(s, 0.5 * a.d / s);
 }
 
-}  // namespace bn
+}  // namespace BN_NS

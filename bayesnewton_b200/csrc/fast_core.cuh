@@ -10,7 +10,7 @@
 #include "gen.cuh"
 #include "dual.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 // -------------------------------------------------------------------------------- prepared generator
 template <int FAMILY, int NC_>
@@ -24,33 +24,33 @@ struct FastGen {
     static constexpr int kBlockS = NC * symn(n);
     static __host__ __device__ constexpr int sel(int a) { return a * n; }
 
-    double lam[NC];          // sqrt(2 nu) / lengthscale
-    double Pb[kBlockS];      // Pinf blocks, packed
+    real lam[NC];          // sqrt(2 nu) / lengthscale
+    real Pb[kBlockS];      // Pinf blocks, packed
 
     BN_DEV void prepare(const bn_kernel_spec& s) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            lam[c] = MaternBlock<FAMILY, double>::rate(s.lengthscale[c]);
-            MaternBlock<FAMILY, double>::pinf(s.variance[c], s.lengthscale[c], Pb + c * symn(n));
+            lam[c] = MaternBlock<FAMILY, real>::rate(s.lengthscale[c]);
+            MaternBlock<FAMILY, real>::pinf(s.variance[c], s.lengthscale[c], Pb + c * symn(n));
         }
     }
     // A blocks for a step of length h
-    BN_DEV void trans(double h, double* Ab) const {
+    BN_DEV void trans(real h, real* Ab) const {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) MaternBlock<FAMILY, double>::transition_rate(lam[c], h, Ab + c * n * n);
+        for (int c = 0; c < NC; ++c) MaternBlock<FAMILY, real>::transition_rate(lam[c], h, Ab + c * n * n);
     }
     // Q blocks = Pinf - A Pinf A^T, skipping the structural zeros of Pinf ((i + j) odd)
-    BN_DEV void noise(const double* Ab, double* Qb) const {
+    BN_DEV void noise(const real* Ab, real* Qb) const {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            const double* A = Ab + c * n * n;
-            const double* P = Pb + c * symn(n);
-            double X[n * n];
+            const real* A = Ab + c * n * n;
+            const real* P = Pb + c * symn(n);
+            real X[n * n];
 #pragma unroll
             for (int i = 0; i < n; ++i)
 #pragma unroll
                 for (int j = 0; j < n; ++j) {
-                    double s = 0.0;
+                    real s = 0.0;
                     bool started = false;
 #pragma unroll
                     for (int l = 0; l < n; ++l)
@@ -64,7 +64,7 @@ struct FastGen {
             for (int i = 0; i < n; ++i)
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
-                    double s = (((i + j) & 1) == 0) ? P[sidx(i, j)] : 0.0;
+                    real s = (((i + j) & 1) == 0) ? P[sidx(i, j)] : 0.0;
 #pragma unroll
                     for (int l = 0; l < n; ++l) s = fma(-X[i * n + l], A[j * n + l], s);
                     Qb[c * symn(n) + sidx(i, j)] = s;
@@ -72,7 +72,7 @@ struct FastGen {
         }
     }
     // A blocks and their derivative with respect to the rate lam_c (dual-number evaluation of the same closed form)
-    BN_DEV void trans_d(double h, double* Ab, double* dAb) const {
+    BN_DEV void trans_d(real h, real* Ab, real* dAb) const {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             Dual A[n * n];
@@ -85,7 +85,7 @@ struct FastGen {
         }
     }
     // full packed Pinf (d x d)
-    BN_DEV void pinf_full(double* P) const {
+    BN_DEV void pinf_full(real* P) const {
 #pragma unroll
         for (int i = 0; i < symn(d); ++i) P[i] = 0.0;
 #pragma unroll
@@ -100,13 +100,13 @@ struct FastGen {
 // -------------------------------------------------------------------------------- block-diagonal products
 // y = A x, A = blockdiag(Ab)
 template <class G>
-BN_DEV void bd_matvec(const double* Ab, const double* x, double* y) {
+BN_DEV void bd_matvec(const real* Ab, const real* x, real* y) {
     constexpr int n = G::n;
 #pragma unroll
     for (int c = 0; c < G::NC; ++c)
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-            double s = 0.0;
+            real s = 0.0;
 #pragma unroll
             for (int l = 0; l < n; ++l) s = fma(Ab[c * n * n + i * n + l], x[c * n + l], s);
             y[c * n + i] = s;
@@ -115,7 +115,7 @@ BN_DEV void bd_matvec(const double* Ab, const double* x, double* y) {
 
 // X (d x d full) = A S, S symmetric packed
 template <class G>
-BN_DEV void bd_mat_sym(const double* Ab, const double* S, double* X) {
+BN_DEV void bd_mat_sym(const real* Ab, const real* S, real* X) {
     constexpr int n = G::n, d = G::d;
 #pragma unroll
     for (int c = 0; c < G::NC; ++c)
@@ -123,7 +123,7 @@ BN_DEV void bd_mat_sym(const double* Ab, const double* S, double* X) {
         for (int i = 0; i < n; ++i)
 #pragma unroll
             for (int j = 0; j < d; ++j) {
-                double s = 0.0;
+                real s = 0.0;
 #pragma unroll
                 for (int l = 0; l < n; ++l) s = fma(Ab[c * n * n + i * n + l], S[sidx(c * n + l, j)], s);
                 X[(c * n + i) * d + j] = s;
@@ -132,7 +132,7 @@ BN_DEV void bd_mat_sym(const double* Ab, const double* S, double* X) {
 
 // C (d x cc full) = A B, B (d x cc full)
 template <class G, int cc>
-BN_DEV void bd_matmul(const double* Ab, const double* B, double* C) {
+BN_DEV void bd_matmul(const real* Ab, const real* B, real* C) {
     constexpr int n = G::n;
 #pragma unroll
     for (int c = 0; c < G::NC; ++c)
@@ -140,7 +140,7 @@ BN_DEV void bd_matmul(const double* Ab, const double* B, double* C) {
         for (int i = 0; i < n; ++i)
 #pragma unroll
             for (int j = 0; j < cc; ++j) {
-                double s = 0.0;
+                real s = 0.0;
 #pragma unroll
                 for (int l = 0; l < n; ++l) s = fma(Ab[c * n * n + i * n + l], B[(c * n + l) * cc + j], s);
                 C[(c * n + i) * cc + j] = s;
@@ -149,14 +149,14 @@ BN_DEV void bd_matmul(const double* Ab, const double* B, double* C) {
 
 // out (packed, lower) = X A^T + blockdiag(Sb)   (Sb nullable)
 template <class G>
-BN_DEV void bd_abt_sym(const double* X, const double* Ab, const double* Sb, double* out) {
+BN_DEV void bd_abt_sym(const real* X, const real* Ab, const real* Sb, real* out) {
     constexpr int n = G::n, d = G::d;
 #pragma unroll
     for (int i = 0; i < d; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
             const int cj = j / n, jj = j % n, ci = i / n, ii = i % n;
-            double s = (Sb && ci == cj) ? Sb[cj * symn(n) + sidx(ii, jj)] : 0.0;
+            real s = (Sb && ci == cj) ? Sb[cj * symn(n) + sidx(ii, jj)] : 0.0;
 #pragma unroll
             for (int l = 0; l < n; ++l) s = fma(X[i * d + cj * n + l], Ab[cj * n * n + jj * n + l], s);
             out[sidx(i, j)] = s;
@@ -165,9 +165,9 @@ BN_DEV void bd_abt_sym(const double* X, const double* Ab, const double* Sb, doub
 
 // Pp = Pinf + A (P - Pinf) A^T
 template <class G>
-BN_DEV void predict_cov(const G& g, const double* Ab, const double* P, double* Pp) {
+BN_DEV void predict_cov(const G& g, const real* Ab, const real* P, real* Pp) {
     constexpr int n = G::n, d = G::d;
-    double Dl[symn(d)];
+    real Dl[symn(d)];
 #pragma unroll
     for (int i = 0; i < d; ++i)
 #pragma unroll
@@ -175,7 +175,7 @@ BN_DEV void predict_cov(const G& g, const double* Ab, const double* P, double* P
             const bool in_block = (i / n == j / n) && ((((i % n) + (j % n)) & 1) == 0);
             Dl[sidx(i, j)] = in_block ? P[sidx(i, j)] - g.Pb[(i / n) * symn(n) + sidx(i % n, j % n)] : P[sidx(i, j)];
         }
-    double X[d * d];
+    real X[d * d];
     bd_mat_sym<G>(Ab, Dl, X);
     // + Pinf, skipping its structural zeros
 #pragma unroll
@@ -184,7 +184,7 @@ BN_DEV void predict_cov(const G& g, const double* Ab, const double* P, double* P
         for (int j = 0; j <= i; ++j) {
             const int cj = j / n, jj = j % n, ci = i / n, ii = i % n;
             const bool nz = (ci == cj) && (((ii + jj) & 1) == 0);
-            double s = nz ? g.Pb[cj * symn(n) + sidx(ii, jj)] : 0.0;
+            real s = nz ? g.Pb[cj * symn(n) + sidx(ii, jj)] : 0.0;
             bool started = nz;
 #pragma unroll
             for (int l = 0; l < n; ++l) {
@@ -197,12 +197,12 @@ BN_DEV void predict_cov(const G& g, const double* Ab, const double* P, double* P
 }
 
 // a Cholesky pivot that is not positive poisons the result exactly as sqrt() of it would (utils.py:14-19)
-BN_DEV double pd_guard(double s) { return s > 0.0 ? s : nan(""); }
+BN_DEV real pd_guard(real s) { return s > 0.0 ? s : nan(""); }
 
 // -------------------------------------------------------------------------------- filter step
 // Innovation covariance S (packed D), innovation e, HP rows -- shared by the step and the absorb.
 template <class G>
-BN_DEV void innovation(const double* mp, const double* Pp, const double* y, const double* R, double* S, double* e) {
+BN_DEV void innovation(const real* mp, const real* Pp, const real* y, const real* R, real* S, real* e) {
     constexpr int D = G::D;
 #pragma unroll
     for (int a = 0; a < D; ++a) {
@@ -215,10 +215,10 @@ BN_DEV void innovation(const double* mp, const double* Pp, const double* y, cons
 // Kt (D x d) = S^-1 HP, with HP[a][:] = Pp[sel(a)][:]; returns through Kt.  Sf receives what the
 // caller needs to apply S^-1 again: D == 1: Sf[0] = 1/S; D > 1: the Cholesky factor.
 template <class G>
-BN_DEV void gain(const double* Pp, const double* S, double* Sf, double* Kt) {
+BN_DEV void gain(const real* Pp, const real* S, real* Sf, real* Kt) {
     constexpr int d = G::d, D = G::D;
     if constexpr (D == 1) {
-        const double r = 1.0 / pd_guard(S[0]);
+        const real r = 1.0 / pd_guard(S[0]);
         Sf[0] = r;
 #pragma unroll
         for (int i = 0; i < d; ++i) Kt[i] = Pp[sidx(G::sel(0), i)] * r;
@@ -235,7 +235,7 @@ BN_DEV void gain(const double* Pp, const double* S, double* Sf, double* Kt) {
 }
 
 template <class G>
-BN_DEV double step_logpdf(const double* S, const double* Sf, const double* e, const unsigned char* msk) {
+BN_DEV real step_logpdf(const real* S, const real* Sf, const real* e, const unsigned char* msk) {
     constexpr int D = G::D;
     if constexpr (D == 1) {
         if (msk && msk[0]) return 0.0;  // the masked 1x1 density is exactly 1 (utils.py:376-396)
@@ -248,25 +248,25 @@ BN_DEV double step_logpdf(const double* S, const double* Sf, const double* e, co
 // One predict + update (ops.py:156-175).  (m, P) in: filtered state of the previous step; out:
 // of this step.  mp / Pp receive the prediction.  Returns the log-likelihood increment.
 template <class G, bool WANT_ELL>
-BN_DEV double fkf_step(const G& g, double* m, double* P, const double* Ab, const double* y, const double* R,
-                       const unsigned char* msk, double* mp, double* Pp) {
+BN_DEV real fkf_step(const G& g, real* m, real* P, const real* Ab, const real* y, const real* R,
+                       const unsigned char* msk, real* mp, real* Pp) {
     constexpr int d = G::d, D = G::D;
     bd_matvec<G>(Ab, m, mp);
     predict_cov<G>(g, Ab, P, Pp);
-    double S[symn(D)], Sf[symn(D)], e[D], Kt[D * d];
+    real S[symn(D)], Sf[symn(D)], e[D], Kt[D * d];
     innovation<G>(mp, Pp, y, R, S, e);
     gain<G>(Pp, S, Sf, Kt);
-    double ell = 0.0;
+    real ell = 0.0;
     if constexpr (WANT_ELL) ell = step_logpdf<G>(S, Sf, e, msk);
 #pragma unroll
     for (int i = 0; i < d; ++i) {
-        double s = mp[i];
+        real s = mp[i];
 #pragma unroll
         for (int a = 0; a < D; ++a) s = fma(Kt[a * d + i], e[a], s);
         m[i] = s;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            double t = Pp[sidx(i, j)];
+            real t = Pp[sidx(i, j)];
 #pragma unroll
             for (int a = 0; a < D; ++a) t = fma(-Kt[a * d + i], Pp[sidx(G::sel(a), j)], t);
             P[sidx(i, j)] = t;
@@ -280,10 +280,10 @@ BN_DEV double fkf_step(const G& g, double* m, double* P, const double* Ab, const
 // state entering the chunk.  `first`: global step 0 of the scan form (Q_0 := P_0, m0 = 0;
 // ops.py:222-229), valid only on a fresh aggregate.
 template <class G>
-BN_DEV void fkf_absorb(const G& g, typename FilterAlg<G::d>::Elem& el, const double* Ab, const double* y,
-                       const double* R, bool first) {
+BN_DEV void fkf_absorb(const G& g, typename FilterAlg<G::d>::Elem& el, const real* Ab, const real* y,
+                       const real* R, bool first) {
     constexpr int d = G::d, D = G::D, n = G::n;
-    double mp[d], Pp[symn(d)], Phi[d * d];
+    real mp[d], Pp[symn(d)], Phi[d * d];
     if (first) {
 #pragma unroll
         for (int i = 0; i < d; ++i) mp[i] = 0.0;
@@ -301,11 +301,11 @@ BN_DEV void fkf_absorb(const G& g, typename FilterAlg<G::d>::Elem& el, const dou
         predict_cov<G>(g, Ab, el.C, Pp);
         bd_matmul<G, d>(Ab, el.A, Phi);
     }
-    double S[symn(D)], Sf[symn(D)], e[D], Kt[D * d];
+    real S[symn(D)], Sf[symn(D)], e[D], Kt[D * d];
     innovation<G>(mp, Pp, y, R, S, e);
     gain<G>(Pp, S, Sf, Kt);
     // V = S^-1 [H Phi | e]  (D x (d+1)), H Phi = selected rows of Phi
-    double V[D * (d + 1)];
+    real V[D * (d + 1)];
     if constexpr (D == 1) {
 #pragma unroll
         for (int j = 0; j < d; ++j) V[j] = Phi[G::sel(0) * d + j] * Sf[0];
@@ -321,13 +321,13 @@ BN_DEV void fkf_absorb(const G& g, typename FilterAlg<G::d>::Elem& el, const dou
     }
 #pragma unroll
     for (int i = 0; i < d; ++i) {
-        double s = el.eta[i];
+        real s = el.eta[i];
 #pragma unroll
         for (int a = 0; a < D; ++a) s = fma(Phi[G::sel(a) * d + i], V[a * (d + 1) + d], s);
         el.eta[i] = s;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            double t = el.J[sidx(i, j)];
+            real t = el.J[sidx(i, j)];
 #pragma unroll
             for (int a = 0; a < D; ++a) t = fma(Phi[G::sel(a) * d + i], V[a * (d + 1) + j], t);
             el.J[sidx(i, j)] = t;
@@ -335,20 +335,20 @@ BN_DEV void fkf_absorb(const G& g, typename FilterAlg<G::d>::Elem& el, const dou
     }
 #pragma unroll
     for (int i = 0; i < d; ++i) {
-        double s = mp[i];
+        real s = mp[i];
 #pragma unroll
         for (int a = 0; a < D; ++a) s = fma(Kt[a * d + i], e[a], s);
         el.b[i] = s;
 #pragma unroll
         for (int j = 0; j < d; ++j) {
-            double t = Phi[i * d + j];
+            real t = Phi[i * d + j];
 #pragma unroll
             for (int a = 0; a < D; ++a) t = fma(-Kt[a * d + i], Phi[G::sel(a) * d + j], t);
             el.A[i * d + j] = t;
         }
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            double t = Pp[sidx(i, j)];
+            real t = Pp[sidx(i, j)];
 #pragma unroll
             for (int a = 0; a < D; ++a) t = fma(-Kt[a * d + i], Pp[sidx(G::sel(a), j)], t);
             el.C[sidx(i, j)] = t;
@@ -359,21 +359,21 @@ BN_DEV void fkf_absorb(const G& g, typename FilterAlg<G::d>::Elem& el, const dou
 // -------------------------------------------------------------------------------- LDL^T
 // S (packed, destroyed) -> unit lower factor in the strict lower triangle, 1/d_i on the diagonal.
 template <int n>
-BN_DEV void ldlt(double* S) {
+BN_DEV void ldlt(real* S) {
 #pragma unroll
     for (int j = 0; j < n; ++j) {
-        double w[n];  // w[k] = L[j][k] d_k
-        double dj = S[sidx(j, j)];
+        real w[n];  // w[k] = L[j][k] d_k
+        real dj = S[sidx(j, j)];
 #pragma unroll
         for (int k = 0; k < j; ++k) {
             w[k] = S[sidx(j, k)];                 // still holds L[j][k] d_k (scaled below)
             dj = fma(-w[k], w[k] * S[sidx(k, k)], dj);
         }
-        const double inv = 1.0 / pd_guard(dj);
+        const real inv = 1.0 / pd_guard(dj);
         // rows below: S[i][j] <- (S[i][j] - sum_k (L[i][k] d_k) L[j][k])   kept as L[i][j] d_j
 #pragma unroll
         for (int i = j + 1; i < n; ++i) {
-            double t = S[sidx(i, j)];
+            real t = S[sidx(i, j)];
 #pragma unroll
             for (int k = 0; k < j; ++k) t = fma(-S[sidx(i, k)], w[k] * S[sidx(k, k)], t);
             S[sidx(i, j)] = t;
@@ -385,14 +385,14 @@ BN_DEV void ldlt(double* S) {
 
 // solve (L D L^T) X = B in place, B (n x c) row-major; S as left by ldlt()
 template <int n, int c>
-BN_DEV void ldlt_solve(const double* S, double* B) {
+BN_DEV void ldlt_solve(const real* S, real* B) {
 #pragma unroll
     for (int j = 0; j < c; ++j) {
         // forward: z = L^-1 b with L[i][k] = S[i][k] * S[k][k]
-        double z[n];
+        real z[n];
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-            double s = B[i * c + j];
+            real s = B[i * c + j];
 #pragma unroll
             for (int k = 0; k < i; ++k) s = fma(-S[sidx(i, k)], z[k], s);   // z[k] already scaled by 1/d_k
             z[i] = s * S[sidx(i, i)];                                         // z_i / d_i
@@ -400,7 +400,7 @@ BN_DEV void ldlt_solve(const double* S, double* B) {
         // backward: x = L^-T (D^-1 z);  L^T[i][k] = L[k][i] = S[k][i] * S[i][i]
 #pragma unroll
         for (int i = n - 1; i >= 0; --i) {
-            double s = 0.0;
+            real s = 0.0;
 #pragma unroll
             for (int k = i + 1; k < n; ++k) s = fma(S[sidx(k, i)], z[k], s);
             z[i] = fma(-s, S[sidx(i, i)], z[i]);
@@ -428,8 +428,8 @@ BN_DEV void ldlt_solve(const double* S, double* B) {
 template <class G>
 struct GradAcc {
     static constexpr int kFields = G::NC * (symn(G::n) + 1);
-    double Gam[G::NC * symn(G::n)];  // diagonal blocks of Gamma, packed
-    double gl[G::NC];                // sum_k < dA-coefficient block , dA_k / d lam_c >
+    real Gam[G::NC * symn(G::n)];  // diagonal blocks of Gamma, packed
+    real gl[G::NC];                // sum_k < dA-coefficient block , dA_k / d lam_c >
     BN_DEV void zero() {
 #pragma unroll
         for (int i = 0; i < G::NC * symn(G::n); ++i) Gam[i] = 0.0;
@@ -441,11 +441,11 @@ struct GradAcc {
 // F: P^- factorised by ldlt(); dm = sm - m^-; dP = sP - P^- (packed); (pm_, pP_) = (m_{k-1}, P_{k-1}).
 // first: the step whose incoming state is the stationary prior (Gamma takes the whole of M, no dA term).
 template <class G>
-BN_DEV void grad_accumulate(const G& g, const double* Ab, double h, const double* F, const double* dm,
-                            const double* dP, const double* pm_, const double* pP_, bool first, GradAcc<G>& acc) {
+BN_DEV void grad_accumulate(const G& g, const real* Ab, real h, const real* F, const real* dm,
+                            const real* dP, const real* pm_, const real* pP_, bool first, GradAcc<G>& acc) {
     constexpr int d = G::d, n = G::n, c1 = d + 1;
     // [X | v] = (P^-)^-1 [dP + dm dm^T | dm]
-    double B[d * c1];
+    real B[d * c1];
 #pragma unroll
     for (int i = 0; i < d; ++i) {
 #pragma unroll
@@ -454,7 +454,7 @@ BN_DEV void grad_accumulate(const G& g, const double* Ab, double h, const double
     }
     ldlt_solve<d, c1>(F, B);
     // M2 = (P^-)^-1 X^T = 2 M
-    double M2[d * d], v[d];
+    real M2[d * d], v[d];
 #pragma unroll
     for (int i = 0; i < d; ++i) {
         v[i] = B[i * c1 + d];
@@ -473,14 +473,14 @@ BN_DEV void grad_accumulate(const G& g, const double* Ab, double h, const double
         return;
     }
     // XA = M2 A  (d x d)
-    double XA[d * d];
+    real XA[d * d];
 #pragma unroll
     for (int i = 0; i < d; ++i)
 #pragma unroll
         for (int c = 0; c < G::NC; ++c)
 #pragma unroll
             for (int j = 0; j < n; ++j) {
-                double s = 0.0;
+                real s = 0.0;
 #pragma unroll
                 for (int l = 0; l < n; ++l) s = fma(M2[i * d + c * n + l], Ab[c * n * n + l * n + j], s);
                 XA[i * d + c * n + j] = s;
@@ -492,7 +492,7 @@ BN_DEV void grad_accumulate(const G& g, const double* Ab, double h, const double
         for (int i = 0; i < n; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
-                double s = 0.5 * (M2[(c * n + i) * d + c * n + j] + M2[(c * n + j) * d + c * n + i]);
+                real s = 0.5 * (M2[(c * n + i) * d + c * n + j] + M2[(c * n + j) * d + c * n + i]);
 #pragma unroll
                 for (int l = 0; l < n; ++l) s = fma(-Ab[c * n * n + l * n + i], XA[(c * n + l) * d + c * n + j], s);
                 acc.Gam[c * symn(n) + sidx(i, j)] = fma(0.5, s, acc.Gam[c * symn(n) + sidx(i, j)]);
@@ -502,16 +502,16 @@ BN_DEV void grad_accumulate(const G& g, const double* Ab, double h, const double
         // across the smoother step)
         Dual Ad[n * n];
         MaternBlock<G::family, Dual>::transition_rate(Dual(g.lam[c], 1.0), Dual(h), Ad);
-        double s = 0.0;
+        real s = 0.0;
 #pragma unroll
         for (int i = 0; i < n; ++i)
 #pragma unroll
             for (int j = 0; j < n; ++j) {
-                double z = v[c * n + i] * pm_[c * n + j];
+                real z = v[c * n + i] * pm_[c * n + j];
 #pragma unroll
                 for (int l = 0; l < d; ++l) {
                     const bool nz = (l / n == c) && ((((l % n) + j) & 1) == 0);
-                    const double dl = nz ? pP_[sidx(l, c * n + j)] - g.Pb[c * symn(n) + sidx(l % n, j)]
+                    const real dl = nz ? pP_[sidx(l, c * n + j)] - g.Pb[c * symn(n) + sidx(l % n, j)]
                                          : pP_[sidx(l, c * n + j)];
                     z = fma(XA[(c * n + i) * d + l], dl, z);
                 }
@@ -524,22 +524,22 @@ BN_DEV void grad_accumulate(const G& g, const double* Ab, double h, const double
 // (Gamma blocks, gl) -> d ell / d variance_c, d ell / d lengthscale_c.  Pinf is linear in the variance and A
 // does not depend on it; the lengthscale acts through Pinf and through lam = sqrt(2 nu) / lengthscale.
 template <class G>
-BN_DEV void grad_finish(const bn_kernel_spec& s, const double* fields, double* dvar, double* dlen) {
+BN_DEV void grad_finish(const bn_kernel_spec& s, const real* fields, real* dvar, real* dlen) {
     constexpr int n = G::n, NC = G::NC;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         Dual P[symn(n)];
         MaternBlock<G::family, Dual>::pinf(Dual(s.variance[c]), Dual(s.lengthscale[c], 1.0), P);
-        double a = 0.0, b = 0.0;
+        real a = 0.0, b = 0.0;
 #pragma unroll
         for (int i = 0; i < n; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
-                const double w = (i == j ? 1.0 : 2.0) * fields[c * symn(n) + sidx(i, j)];
+                const real w = (i == j ? 1.0 : 2.0) * fields[c * symn(n) + sidx(i, j)];
                 a = fma(w, P[sidx(i, j)].v, a);
                 b = fma(w, P[sidx(i, j)].d, b);
             }
-        const double lam = MaternBlock<G::family, double>::rate(s.lengthscale[c]);
+        const real lam = MaternBlock<G::family, real>::rate(s.lengthscale[c]);
         dvar[c] = a / s.variance[c];
         dlen[c] = b - fields[NC * symn(n) + c] * lam / s.lengthscale[c];
     }
@@ -549,14 +549,14 @@ BN_DEV void grad_finish(const bn_kernel_spec& s, const double* fields, double* d
 // (sm, sP) at step k+1 in, at step k out (ops.py:290-301); Ab, Qb belong to the step k -> k+1.
 // With GRAD the step also accumulates the hyper-gradient terms of the transition k -> k+1 (see below).
 template <class G, bool GRAD = false>
-BN_DEV void frts_step(const double* Ab, const double* Qb, const double* fm, const double* fP, double* sm,
-                      double* sP, const G* g = nullptr, double h = 0.0, GradAcc<G>* acc = nullptr) {
+BN_DEV void frts_step(const real* Ab, const real* Qb, const real* fm, const real* fP, real* sm,
+                      real* sP, const G* g = nullptr, real h = 0.0, GradAcc<G>* acc = nullptr) {
     constexpr int d = G::d;
-    double pm[d], AfP[d * d], pP[symn(d)];
+    real pm[d], AfP[d * d], pP[symn(d)];
     bd_matvec<G>(Ab, fm, pm);
     bd_mat_sym<G>(Ab, fP, AfP);
     bd_abt_sym<G>(AfP, Ab, Qb, pP);
-    double dm[d], dP[symn(d)];
+    real dm[d], dP[symn(d)];
 #pragma unroll
     for (int i = 0; i < d; ++i) dm[i] = sm[i] - pm[i];
 #pragma unroll
@@ -567,18 +567,18 @@ BN_DEV void frts_step(const double* Ab, const double* Qb, const double* fm, cons
     // sm = fm + G dm,  G[i][j] = AfP[j][i]
 #pragma unroll
     for (int i = 0; i < d; ++i) {
-        double s = fm[i];
+        real s = fm[i];
 #pragma unroll
         for (int l = 0; l < d; ++l) s = fma(AfP[l * d + i], dm[l], s);
         sm[i] = s;
     }
     // sP = fP + G dP G^T
-    double X[d * d];  // X = G dP
+    real X[d * d];  // X = G dP
 #pragma unroll
     for (int i = 0; i < d; ++i)
 #pragma unroll
         for (int j = 0; j < d; ++j) {
-            double s = 0.0;
+            real s = 0.0;
 #pragma unroll
             for (int l = 0; l < d; ++l) s = fma(AfP[l * d + i], dP[sidx(l, j)], s);
             X[i * d + j] = s;
@@ -587,7 +587,7 @@ BN_DEV void frts_step(const double* Ab, const double* Qb, const double* fm, cons
     for (int i = 0; i < d; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            double s = fP[sidx(i, j)];
+            real s = fP[sidx(i, j)];
 #pragma unroll
             for (int l = 0; l < d; ++l) s = fma(X[i * d + l], AfP[l * d + j], s);
             sP[sidx(i, j)] = s;
@@ -603,11 +603,11 @@ BN_DEV void frts_step(const double* Ab, const double* Qb, const double* fm, cons
 // i.e. the composition of the per-step smoothing elements of ops.py:318-335 over the chunk,
 // obtained in O(d^3) per CHUNK instead of a second O(d^3) pass per STEP.
 template <int d>
-BN_DEV void chunk_smoothing_element(const typename FilterAlg<d>::Elem& fe, const double* ma, const double* Pa,
-                                    const double* mb, const double* Pb, typename SmootherAlg<d>::Elem& se) {
+BN_DEV void chunk_smoothing_element(const typename FilterAlg<d>::Elem& fe, const real* ma, const real* Pa,
+                                    const real* mb, const real* Pb, typename SmootherAlg<d>::Elem& se) {
     using FA = FilterAlg<d>;
     constexpr int c = d + 1;
-    double B[d * c], v[d];
+    real B[d * c], v[d];
     symvec<d>(Pa, fe.eta, v);
 #pragma unroll
     for (int i = 0; i < d; ++i) {
@@ -616,16 +616,16 @@ BN_DEV void chunk_smoothing_element(const typename FilterAlg<d>::Elem& fe, const
         B[i * c + d] = ma[i] + v[i];
     }
     FA::template solve_ipcj<c>(Pa, fe.J, B);
-    double Pq[symn(d)], mq[d];
+    real Pq[symn(d)], mq[d];
 #pragma unroll
     for (int i = 0; i < d; ++i) {
 #pragma unroll
         for (int j = 0; j <= i; ++j) Pq[sidx(i, j)] = 0.5 * (B[i * c + j] + B[j * c + i]);
         mq[i] = B[i * c + d];
     }
-    double X[d * d];  // A P'
+    real X[d * d];  // A P'
     mat_sym<d, d>(fe.A, Pq, X);
-    double Lc[symn(d)];
+    real Lc[symn(d)];
 #pragma unroll
     for (int i = 0; i < symn(d); ++i) Lc[i] = Pb[i];
     chol<d>(Lc);
@@ -634,21 +634,21 @@ BN_DEV void chunk_smoothing_element(const typename FilterAlg<d>::Elem& fe, const
     for (int i = 0; i < d; ++i)
 #pragma unroll
         for (int j = 0; j < d; ++j) se.E[i * d + j] = X[j * d + i];
-    double t[d];
+    real t[d];
     matvec<d, d>(se.E, mb, t);
 #pragma unroll
     for (int i = 0; i < d; ++i) se.g[i] = mq[i] - t[i];
-    double Y[d * d];  // E P_b
+    real Y[d * d];  // E P_b
     mat_sym<d, d>(se.E, Pb, Y);
 #pragma unroll
     for (int i = 0; i < d; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            double s = 0.0;
+            real s = 0.0;
 #pragma unroll
             for (int l = 0; l < d; ++l) s = fma(Y[i * d + l], se.E[j * d + l], s);
             se.L[sidx(i, j)] = Pq[sidx(i, j)] - s;
         }
 }
 
-}  // namespace bn
+}  // namespace BN_NS

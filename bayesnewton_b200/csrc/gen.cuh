@@ -7,7 +7,7 @@
 #include "smallmat.cuh"
 #include "../../include/bn_b200.h"
 
-namespace bn {
+namespace BN_NS {
 
 template <int FAMILY> struct FamilyDim;
 template <> struct FamilyDim<BN_MATERN12> { static constexpr int value = 1; };
@@ -204,4 +204,4 @@ struct ArrayGen {
     }
 };
 
-}  // namespace bn
+}  // namespace BN_NS

@@ -3,7 +3,7 @@
 #include <cstdlib>
 #include "iter_impl.cuh"
 
-namespace bn {
+namespace BN_NS {
 // BN_B200_SPEC_FILTER=0 keeps phase 1 a pure reduction (A/B validation of the speculative filter pass)
 static bool spec_filter_enabled() {
     static const bool on = [] {
@@ -108,9 +108,9 @@ static int it_transpose(const bn_kernel_spec* k, int64_t N, const T* in, T* out,
     BN_CUDA(cudaGetLastError());
     return 0;
 }
-}  // namespace bn
+}  // namespace BN_NS
 
-using namespace bn;
+using namespace BN_NS;
 
 extern "C" int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N) {
     if (it_check_spec(k, N)) return -1;

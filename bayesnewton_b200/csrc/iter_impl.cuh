@@ -20,9 +20,9 @@
 // sites in; sites out) + 8 + 16 + 16 (V, X in; marginals out) = 472 B against 636 B on the reference-interface layouts.
 #pragma once
 #include "up_impl.cuh"
-#include "sites_impl.cuh"
+#include "site_math.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 #ifndef BN_IT_SMOOTH_UNROLL
 #define BN_IT_SMOOTH_UNROLL 1
@@ -36,21 +36,21 @@ inline long long tl_len(long long nchunks, int L) { return ((nchunks + 31) / 32)
 
 struct ItIO {
     long long N;
-    const double* dt;           // tiled
-    const double* y;            // tiled observations (the data; site pass / energy pass only)
-    double* sy;                 // tiled pseudo observations (site means)
-    double* sR;                 // tiled pseudo variances (site covariances)
+    const real* dt;           // tiled
+    const real* y;            // tiled observations (the data; site pass / energy pass only)
+    real* sy;                 // tiled pseudo observations (site means)
+    real* sR;                 // tiled pseudo variances (site covariances)
     const unsigned char* mask;  // tiled, 1 = the pseudo observation of this step is missing; nullable
-    double* pm;                 // tiled posterior marginal means (plain / energy pass)
-    double* pc;                 // tiled posterior marginal variances
-    double* pm_lin;             // nullable: the marginals go to these [N] arrays in time order instead (the layout the
-    double* pc_lin;             // reference's posterior_mean / posterior_variance have); one 8-byte store per lane and step
+    real* pm;                 // tiled posterior marginal means (plain / energy pass)
+    real* pc;                 // tiled posterior marginal variances
+    real* pm_lin;             // nullable: the marginals go to these [N] arrays in time order instead (the layout the
+    real* pc_lin;             // reference's posterior_mean / posterior_variance have); one 8-byte store per lane and step
 };
 
 // ------------------------------------------------------------------------------------------ chunk bodies
 // phase 1: fold the chunk's steps into one filtering element (ops.py:183-219)
 template <class G>
-BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, double* agg, long long c) {
+BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, real* agg, long long c) {
     static_assert(G::D == 1, "the tiled path carries one site per step");
     using Alg = FilterAlg<G::d>;
     typename Alg::Elem el;
@@ -58,18 +58,18 @@ BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks
     const long long k0 = c * L, rem = io.N - k0;
     const int cnt = rem < L ? (int)rem : L;
     const long long b = tl_base(c, L);
-    const double* pdt = io.dt + b;
-    const double* py = io.sy + b;
-    const double* pR = io.sR + b;
-    double Abn[G::kBlockA];
+    const real* pdt = io.dt + b;
+    const real* py = io.sy + b;
+    const real* pR = io.sR + b;
+    real Abn[G::kBlockA];
     g.trans(pdt[0], Abn);
-    double yn = py[0], Rn = pR[0], hn = pdt[32];
+    real yn = py[0], Rn = pR[0], hn = pdt[32];
 #pragma unroll 1
     for (int j = 0; j < cnt; ++j) {
-        double y[1] = {yn}, R[1] = {Rn}, Ab[G::kBlockA];
+        real y[1] = {yn}, R[1] = {Rn}, Ab[G::kBlockA];
 #pragma unroll
         for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
-        const double h1 = hn;
+        const real h1 = hn;
         // the next step's inputs are in flight while this step's dependent chain runs (rows past the chunk are padding)
         py += 32; pR += 32; pdt += 32;
         yn = py[0]; Rn = pR[0]; hn = pdt[32];
@@ -87,20 +87,20 @@ BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks
 // steps before the switch.  For chunks much longer than the forgetting time (N = 1e8: 1320 steps against ~160) that
 // removes most of the second pass over the inputs; for short chunks the switch never happens and phase 3 does what it
 // always did.  The switch is taken by all 32 lanes of a warp together (the tiled layout needs them on the same step).
-constexpr double kSpecThreshold = 7.888609052210118e-31;  // 2^-100
+constexpr real kSpecThreshold = 7.888609052210118e-31;  // 2^-100
 
 template <class G, bool WANT_ELL>
 struct SpecReduce {
     static constexpr int d = G::d, nf = G::d + symn(G::d);
     using Alg = FilterAlg<G::d>;
     typename Alg::Elem el;
-    const double *pdt, *py, *pR;
+    const real *pdt, *py, *pR;
     const unsigned char* pk;
-    double* pf;
-    double Abn[G::kBlockA], yn, Rn, hn, ell, isd[G::d], sd[G::d];
+    real* pf;
+    real Abn[G::kBlockA], yn, Rn, hn, ell, isd[G::d], sd[G::d];
     int cnt;
 
-    BN_DEV void init(const G& g, const ItIO& io, int L, double* fs, long long c, bool active) {
+    BN_DEV void init(const G& g, const ItIO& io, int L, real* fs, long long c, bool active) {
         Alg::identity(el);
         ell = 0.0;
         const long long k0 = c * L, rem = io.N - k0;
@@ -111,7 +111,7 @@ struct SpecReduce {
         pR = io.sR + b;
         pk = io.mask ? io.mask + b : nullptr;
         pf = fs + fs_index(c, L, 0, 0, nf);
-        double P[symn(d)];
+        real P[symn(d)];
         g.pinf_full(P);
 #pragma unroll
         for (int i = 0; i < d; ++i) {
@@ -127,18 +127,18 @@ struct SpecReduce {
             yn = Rn = hn = 0.0;
         }
     }
-    BN_DEV void advance(const G& g, double* y, double* R, double* Ab) {
+    BN_DEV void advance(const G& g, real* y, real* R, real* Ab) {
         y[0] = yn; R[0] = Rn;
 #pragma unroll
         for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
-        const double h1 = hn;
+        const real h1 = hn;
         py += 32; pR += 32; pdt += 32;
         yn = py[0]; Rn = pR[0]; hn = pdt[32];
         g.trans(h1, Abn);
     }
     // folds one step into the aggregate; true when the aggregate no longer depends on the incoming state
     BN_DEV bool absorb(const G& g, bool first) {
-        double y[1], R[1], Ab[G::kBlockA];
+        real y[1], R[1], Ab[G::kBlockA];
         advance(g, y, R, Ab);
         fkf_absorb<G>(g, el, Ab, y, R, first);
         if (pk) pk += 32;
@@ -151,8 +151,8 @@ struct SpecReduce {
         return dec;
     }
     // (b, C) of the aggregate after the filter phase (same SoA layout as FilterAlg::store)
-    BN_DEV void store_state(double* agg, long long stride, long long c) const {
-        double* p = agg + c + (long long)(d * d) * stride;
+    BN_DEV void store_state(real* agg, long long stride, long long c) const {
+        real* p = agg + c + (long long)(d * d) * stride;
 #pragma unroll
         for (int k = 0; k < d; ++k) p[k * stride] = el.b[k];
 #pragma unroll
@@ -160,7 +160,7 @@ struct SpecReduce {
     }
     // one plain filter step on (b, C): the filtered state of this step, stored; log-likelihood increment
     BN_DEV void filter(const G& g) {
-        double y[1], R[1], Ab[G::kBlockA], mp[d], Pp[symn(d)];
+        real y[1], R[1], Ab[G::kBlockA], mp[d], Pp[symn(d)];
         unsigned char mk[1] = {0};
         if (pk) { mk[0] = pk[0]; pk += 32; }
         advance(g, y, R, Ab);
@@ -175,43 +175,40 @@ struct SpecReduce {
 
 // phase 3: plain filter from the chunk's incoming state; filtered states -> scratch, log-likelihood partial
 template <class G, bool WANT_ELL>
-BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, const double* prefix,
-                            const double* s0, double* fs, double* ell_partials, long long c, const int* jst = nullptr) {
+BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, const real* prefix,
+                            const real* s0, real* fs, real* ell_partials, long long c, const int* jst = nullptr,
+                            const real* wprefix = nullptr) {
     constexpr int d = G::d;
     using Alg = FilterAlg<d>;
     typename Alg::State s;
     Alg::load_state(s0, 1, 0, s);
     if (c > 0) {
-        typename Alg::Elem e;
-        Alg::load(prefix, nchunks, c - 1, e);
-        typename Alg::State t;
-        Alg::apply(e, s, t);
-        s = t;
+        apply_prefix2<Alg>(prefix, nchunks, wprefix, (nchunks + 31) >> 5, c - 1, s);
     } else if (is_first) {  // global step 0 starts from the stationary prior (m0 = 0, P0 = Pinf)
         Alg::zero_state(s);
         g.pinf_full(s.P);
     }
-    double ell = 0.0;
+    real ell = 0.0;
     const long long k0 = c * L, rem = io.N - k0;
     // with a speculative phase 1 only the steps before its switch are left (their states depend on the incoming one)
     const int cnt = jst ? jst[c] : (rem < L ? (int)rem : L);
     const long long b = tl_base(c, L);
-    const double* pdt = io.dt + b;
-    const double* py = io.sy + b;
-    const double* pR = io.sR + b;
+    const real* pdt = io.dt + b;
+    const real* py = io.sy + b;
+    const real* pR = io.sR + b;
     const unsigned char* pk = io.mask ? io.mask + b : nullptr;
-    double* pf = fs + fs_index(c, L, 0, 0, d + symn(d));
-    double Abn[G::kBlockA];
+    real* pf = fs + fs_index(c, L, 0, 0, d + symn(d));
+    real Abn[G::kBlockA];
     g.trans(pdt[0], Abn);
-    double yn = py[0], Rn = pR[0], hn = pdt[32];
+    real yn = py[0], Rn = pR[0], hn = pdt[32];
 #pragma unroll 1
     for (int j = 0; j < cnt; ++j) {
-        double y[1] = {yn}, R[1] = {Rn}, Ab[G::kBlockA], mp[d], Pp[symn(d)];
+        real y[1] = {yn}, R[1] = {Rn}, Ab[G::kBlockA], mp[d], Pp[symn(d)];
         unsigned char mk[1] = {0};
         if (pk) mk[0] = pk[(long long)j * 32];
 #pragma unroll
         for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
-        const double h1 = hn;
+        const real h1 = hn;
         py += 32; pR += 32; pdt += 32;
         yn = py[0]; Rn = pR[0]; hn = pdt[32];
         g.trans(h1, Abn);
@@ -227,33 +224,27 @@ BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks
 
 // RTS recursion down the chunk (ops.py:290-301); the epilogue takes the smoothed marginal of every step
 template <class G, class Epi>
-BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks, const double* sprefix,
-                            const double* sinit, const double* fs, long long c, Epi& epi) {
+BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks, const real* sprefix,
+                            const real* sinit, const real* fs, long long c, Epi& epi, const real* swprefix = nullptr) {
     constexpr int d = G::d, nf = d + symn(d);
     using Alg = SmootherAlg<d>;
     typename Alg::State s;
     const long long p = nchunks - 1 - c;
     Alg::load_state(sinit, 1, 0, s);
-    if (p > 0) {
-        typename Alg::Elem e;
-        Alg::load(sprefix, nchunks, p - 1, e);
-        typename Alg::State t;
-        Alg::apply(e, s, t);
-        s = t;
-    }
+    if (p > 0) apply_prefix2<Alg>(sprefix, nchunks, swprefix, (nchunks + 31) >> 5, p - 1, s);
     const long long k0 = c * L, rem = io.N - k0;
     const int j_last = (rem < L ? (int)rem : L) - 1;  // s is the smoothed state of this step
     const long long b = tl_base(c, L);
-    const double* pdt = io.dt + b + (long long)j_last * 32;
-    const double* pf = fs + fs_index(c, L, j_last, 0, nf);
+    const real* pdt = io.dt + b + (long long)j_last * 32;
+    const real* pf = fs + fs_index(c, L, j_last, 0, nf);
     long long ti = b + (long long)j_last * 32;
-    double nfm[d], nfP[symn(d)];  // filtered state of the next step to process, loaded one step ahead
-    double Abn[G::kBlockA];       // transition of the next step to process, formed one step ahead (its exp() chain is
+    real nfm[d], nfP[symn(d)];  // filtered state of the next step to process, loaded one step ahead
+    real Abn[G::kBlockA];       // transition of the next step to process, formed one step ahead (its exp() chain is
                                   // independent of the recursion); the noise blocks are formed at their use: keeping
                                   // them a step ahead as well costs 12 registers the fused epilogues need
 #pragma unroll
     for (int i = 0; i < G::kBlockA; ++i) Abn[i] = 0.0;
-    double hn = pdt[0];
+    real hn = pdt[0];
     if (j_last >= 1) {
 #pragma unroll
         for (int f = 0; f < d; ++f) nfm[f] = pf[(f - nf) * 32];
@@ -262,17 +253,17 @@ BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks
     }
 #pragma unroll kItSmoothUnroll
     for (int j = j_last; j >= 0; --j) {
-        double Ab[G::kBlockA];
+        real Ab[G::kBlockA];
 #pragma unroll
         for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
-        const double h_k = hn;
+        const real h_k = hn;
         pdt -= 32;
         if (j >= 1) hn = pdt[0];
         epi.prefetch(ti);
         // the transition of the step below (k-1 -> k, length h_k) is formed while this step's dependent chain runs
         g.trans(h_k, Abn);
         if (j < j_last) {
-            double fm[d], fP[symn(d)], Qb[G::kBlockS];
+            real fm[d], fP[symn(d)], Qb[G::kBlockS];
 #pragma unroll
             for (int i = 0; i < d; ++i) fm[i] = nfm[i];
 #pragma unroll
@@ -300,12 +291,12 @@ BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks
 // ------------------------------------------------------------------------------------------ smoother epilogues
 // plain: the posterior marginals, tiled
 struct EpiStore {
-    double* pm;
-    double* pc;
-    double* pm_lin;
-    double* pc_lin;
+    real* pm;
+    real* pc;
+    real* pm_lin;
+    real* pc_lin;
     BN_DEV void prefetch(long long) {}
-    BN_DEV void step(long long ti, long long k, double m, double v) {
+    BN_DEV void step(long long ti, long long k, real m, real v) {
         if (pm_lin) {
             pm_lin[k] = m;
             pc_lin[k] = v;
@@ -319,10 +310,10 @@ struct EpiStore {
 
 // what the site epilogues need besides the tiled arrays (kernel parameter)
 struct ItSiteArgs {
-    double lik_param, lr, power;
+    real lik_param, lr, power;
     int ensure_psd, pad_;
-    double* part1;  // [nchunks] per-chunk partial sums: SITES |delta nat1|, ENERGY the likelihood term
-    double* part2;  // [nchunks]                         SITES |delta nat2|, ENERGY E_q[log N(pseudo_y | f, pseudo_var)]
+    real* part1;  // [nchunks] per-chunk partial sums: SITES |delta nat1|, ENERGY the likelihood term
+    real* part2;  // [nchunks]                         SITES |delta nat2|, ENERGY E_q[log N(pseudo_y | f, pseudo_var)]
 };
 
 // site update on the smoothed marginal (the body of inference.py:72-86 for one step); sites rewritten in place
@@ -332,22 +323,22 @@ struct EpiSites {
     ItSiteArgs a;
     Lik1<LIK, TAB> lik;
     const Cub1* cub;
-    double d1, d2, yq, oy, oR;
+    real d1, d2, yq, oy, oR;
     BN_DEV EpiSites(const ItIO& io_, const ItSiteArgs& a_, const Cub1* cub_, const double* tab)
         : io(io_), a(a_), lik{a_.lik_param, tab}, cub(cub_), d1(0.0), d2(0.0), yq(0.0), oy(0.0), oR(1.0) {}
     BN_DEV void prefetch(long long ti) { yq = io.y[ti]; }
-    BN_DEV void step(long long ti, long long, double m, double v) {
+    BN_DEV void step(long long ti, long long, real m, real v) {
         // the old site is needed after the cubature loop only: its loads are issued here and land while the loop runs
         oy = io.sy[ti];
         oR = io.sR[ti];
         // natural parameters of the site as reparametrise leaves them (basemodels.py:85-100): nat2 = 1 / cov, nat1 = nat2 mean
-        const double o2 = 1.0 / oR, o1 = oy * o2;
+        const real o2 = 1.0 / oR, o1 = oy * o2;
         SiteStats1 s;
-        double h, r1, r2, e1, e2;
+        real h, r1, r2, e1, e2;
         site_update_scalar<LIK, METHOD, TAB, BN_IT_TAB_UNROLL>(lik, *cub, yq, m, v, o1, o2, a.lr, a.power, a.ensure_psd, s, h, r1, r2, e1, e2);
         d1 += e1;
         d2 += e2;
-        const double Lc = sqrt(r2);
+        const real Lc = sqrt(r2);
         io.sy[ti] = (r1 / Lc) / Lc;
         io.sR[ti] = (1.0 / Lc) / Lc;
     }
@@ -364,12 +355,12 @@ struct EpiEnergy {
     ItSiteArgs a;
     Lik1<LIK, TAB> lik;
     const Cub1* cub;
-    double accV, accX, yq, oy, oR;
+    real accV, accX, yq, oy, oR;
     unsigned char mk;
     BN_DEV EpiEnergy(const ItIO& io_, const ItSiteArgs& a_, const Cub1* cub_, const double* tab)
         : io(io_), a(a_), lik{a_.lik_param, tab}, cub(cub_), accV(0.0), accX(0.0), yq(0.0), oy(0.0), oR(1.0), mk(0) {}
     BN_DEV void prefetch(long long ti) { yq = io.y[ti]; }
-    BN_DEV void step(long long ti, long long k, double m, double v) {
+    BN_DEV void step(long long ti, long long k, real m, real v) {
         // the site of this step enters after the cubature loop only: its loads land while the loop runs
         oy = io.sy[ti];
         oR = io.sR[ti];
@@ -392,35 +383,59 @@ struct EpiEnergy {
 };
 
 #ifdef __CUDACC__
-}  // namespace bn
+}  // namespace BN_NS
 #include "tma_stage.cuh"
-namespace bn {
+namespace BN_NS {
 // ------------------------------------------------------------------------------------------ kernels
 // the table-gathering sweeps own a whole SM: one CTA with the table in shared memory, 16 warps (d <= 3) or the 4 warps the
 // registers of a larger state leave room for
 template <class G> constexpr int kItTabThreads = (G::d <= 3) ? 512 : kUpThreads;
 
+// level 0 of the scan, done by the warp that produced the 32 elements (scan.cuh: warp_prescan); the element is read
+// back from where the chunk body left it so that the body's registers are dead by now
+template <class Alg>
+__device__ __forceinline__ void it_prescan_tail(const real* elems, long long n, long long i, const ScanPlan& plan) {
+    __syncwarp();
+    typename Alg::Elem e;
+    if (i < n) Alg::load(elems, n, i, e);
+    warp_prescan<Alg>(e, i, plan);
+}
+
+// smoothing elements of the chunks in scan order (position p = nchunks - 1 - c), with level 0 of their scan
+template <class G>
+__global__ void __launch_bounds__(128)
+it_selem_kernel(long long N, int L, long long nchunks, int need_first, const real* agg, const real* s0, const real* fs,
+                real* selems, ScanPlan plan) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((p & ~31LL) >= nchunks) return;
+    if (p < nchunks) up_selem_chunk<G>(N, L, nchunks, need_first, agg, s0, fs, selems, nchunks - 1 - p);
+    it_prescan_tail<SmootherAlg<G::d>>(selems, nchunks, p, plan);
+}
+
 template <class G>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, double* agg) {
+it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg, ScanPlan plan) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    if ((c & ~31LL) >= nchunks) return;
     if (c < nchunks) it_reduce_chunk(g, io, L, nchunks, is_first, agg, c);
+    it_prescan_tail<FilterAlg<G::d>>(agg, nchunks, c, plan);
 }
 
 template <class G, bool WANT_ELL>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const double* prefix, const double* s0, double* fs,
-                 double* ell_partials, const int* jst) {
+it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const real* prefix, const real* wprefix,
+                 const real* s0, real* fs, real* ell_partials, const int* jst) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
-    if (c < nchunks) it_filter_chunk<G, WANT_ELL>(g, io, L, nchunks, is_first, prefix, s0, fs, ell_partials, c, jst);
+    if (c < nchunks) it_filter_chunk<G, WANT_ELL>(g, io, L, nchunks, is_first, prefix, s0, fs, ell_partials, c, jst, wprefix);
 }
 
 // phase 1 with speculation (SpecReduce): every lane of a warp takes part in the vote, chunk or not
 template <class G, bool WANT_ELL>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-it_reduce_spec_kernel(G g, ItIO io, int L, long long nchunks, int is_first, double* agg, double* fs, double* ell_partials,
-                      int* jst) {
+it_reduce_spec_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg, real* fs, real* ell_partials,
+                      int* jst, ScanPlan plan) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
+    if ((c & ~31LL) >= nchunks) return;
     const bool active = c < nchunks;
     SpecReduce<G, WANT_ELL> sr;
     sr.init(g, io, L, fs, active ? c : 0, active);
@@ -443,29 +458,66 @@ it_reduce_spec_kernel(G g, ItIO io, int L, long long nchunks, int is_first, doub
         jst[c] = jstar;
         if (WANT_ELL) ell_partials[c] = sr.ell;
     }
+    it_prescan_tail<FilterAlg<G::d>>(agg, nchunks, c, plan);
 }
 
-// a + b summed in a fixed order (the two partial arrays of a speculative filter pass)
-static __global__ void __launch_bounds__(1024) it_sum2_kernel(const double* a, const double* b, long long n, double* out) {
-    __shared__ double sh[1024];
-    double s = 0.0;
-    for (long long i = threadIdx.x; i < n; i += 1024) s += a[i] + b[i];
-    sh[threadIdx.x] = s;
+// Fixed-order sums of the per-chunk partials (run-to-run bit-stable), accumulated in fp64 whatever `real` is, in two
+// small launches: kSumCtas CTAs reduce a fixed slice each, one warp adds the CTA partials in index order.
+//   two = 0: out[0] = sum a (+ sum b when b is given)        two = 1: out[0] = sum a, out[1] = sum b
+constexpr int kSumCtas = 74;
+static __global__ void __launch_bounds__(256) it_sum_stage1_kernel(const real* a, const real* b, long long n, double* scratch) {
+    __shared__ double sh[2][256];
+    const long long per = (n + kSumCtas - 1) / kSumCtas, lo = blockIdx.x * per, hi = (lo + per < n) ? lo + per : n;
+    double sa = 0.0, sb = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+        sa += (double)a[i];
+        if (b) sb += (double)b[i];
+    }
+    sh[0][threadIdx.x] = sa;
+    sh[1][threadIdx.x] = sb;
     __syncthreads();
-    for (int off = 512; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + off];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + off];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = sh[0];
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = sh[0][0];
+        scratch[kSumCtas + blockIdx.x] = sh[1][0];
+    }
+}
+static __global__ void __launch_bounds__(32) it_sum_stage2_kernel(const double* scratch, real* out, int two) {
+    double sa = 0.0, sb = 0.0;
+    for (int i = threadIdx.x; i < kSumCtas; i += 32) {
+        sa += scratch[i];
+        sb += scratch[kSumCtas + i];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sa += __shfl_down_sync(0xffffffffu, sa, off);
+        sb += __shfl_down_sync(0xffffffffu, sb, off);
+    }
+    if (threadIdx.x == 0) {
+        if (two) { out[0] = real(sa); out[1] = real(sb); }
+        else out[0] = real(sa + sb);
+    }
+}
+inline cudaError_t it_sum(const real* a, const real* b, long long n, real* out, int two, double* scratch, cudaStream_t st) {
+    it_sum_stage1_kernel<<<kSumCtas, 256, 0, st>>>(a, b, n, scratch);
+    it_sum_stage2_kernel<<<1, 32, 0, st>>>(scratch, out, two);
+    return cudaGetLastError();
 }
 
 template <class G>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const double* sprefix, const double* sinit, const double* fs) {
+it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const real* sprefix, const real* swprefix, const real* sinit,
+                       const real* fs) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     if (c >= nchunks) return;
     EpiStore epi{io.pm, io.pc, io.pm_lin, io.pc_lin};
-    it_smooth_chunk(g, io, L, nchunks, sprefix, sinit, fs, c, epi);
+    it_smooth_chunk(g, io, L, nchunks, sprefix, sinit, fs, c, epi, swprefix);
 }
 
 // the probit log-density table in device memory (sites.cu fills it once per device and hands out its address)
@@ -474,7 +526,7 @@ int probit_table_device(cudaStream_t st, const double** tab);
 template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(TAB ? kItTabThreads<G> : kUpThreads, TAB ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
 it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs a, int L, long long nchunks,
-                      const double* sprefix, const double* sinit, const double* fs, const double* gtab) {
+                      const real* sprefix, const real* swprefix, const real* sinit, const real* fs, const double* gtab) {
     extern __shared__ __align__(16) double it_smem[];
     const double* tab = nullptr;
     if constexpr (TAB) {
@@ -484,7 +536,7 @@ it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     Epi<LIK, METHOD, TAB> epi(io, a, &cub, tab);
-    it_smooth_chunk(g, io, L, nchunks, sprefix, sinit, fs, c, epi);
+    it_smooth_chunk(g, io, L, nchunks, sprefix, sinit, fs, c, epi, swprefix);
 }
 
 // linear [N] <-> tiled, 32 chunks x 32 steps per CTA through a padded shared-memory tile (both sides coalesced)
@@ -532,20 +584,22 @@ struct ItCall {
     int method, likelihood, use_table;
     ItSiteArgs sa;            // part1 / part2 are set by the driver
     const Cub1* cub;
-    double* ell;              // nullable
-    double* sums;             // [2], SITES: sum |delta nat1|, sum |delta nat2|; ENERGY: likelihood term, pseudo term
+    real* ell;              // nullable
+    real* sums;             // [2], SITES: sum |delta nat1|, sum |delta nat2|; ENERGY: likelihood term, pseudo term
     void* ws;
     size_t ws_bytes;
     cudaStream_t st;
     int phase, rank, world;
-    double* carry_out;
-    const double* carries;
+    real* carry_out;
+    const real* carries;
     int spec_filter;          // phase 1 may switch to the plain filter once the chunk has forgotten its start (SpecReduce)
     int want_ell;             // the pass produces the log-likelihood (every phase of one pass must agree on it)
 };
 
 template <int d>
-inline size_t it_ws_doubles(long long N) { return up_ws_doubles<d>(N) + 4 * (size_t)up_plan_chunks(N > 0 ? N : 1, false, d).nchunks + 64; }
+inline size_t it_ws_doubles(long long N) {
+    return up_ws_doubles<d>(N) + 4 * (size_t)up_plan_chunks(N > 0 ? N : 1, false, d).nchunks + 64 + 4 * kSumCtas + 8;
+}
 
 // speculative phase 1 pays off when the chunks are much longer than the filter's forgetting time
 constexpr int kSpecMinChunk = 256;
@@ -561,9 +615,10 @@ template <class G, template <int, int, bool> class Epi>
 inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp, const UpWs& w, const ItSiteArgs& sa) {
     cudaStream_t st = c.st;
     const char* name = (c.mode == IT_SITES) ? "it_smooth_sites" : "it_smooth_energy";
+    const real* swp = w.splan.levels > 1 ? w.splan.prefix[1] : nullptr;
 #define X(LK, M)                                                                                                      \
     if (c.likelihood == LK && c.method == M) {                                                                         \
-        if constexpr (LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI) {                                            \
+        if constexpr (!kReal32 && LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI) {                                \
             if (c.use_table) {                                                                                         \
                 auto kfn = it_smooth_site_kernel<G, Epi, LK, M, true>;                                                 \
                 const size_t smem = sizeof(double) * kPtDoubles;                                                       \
@@ -572,14 +627,14 @@ inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp
                 BN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
                 const unsigned grid = (unsigned)((cp.nchunks + kItTabThreads<G> - 1) / kItTabThreads<G>);              \
                 BN_LAUNCH(name, st, (kfn<<<grid, kItTabThreads<G>, smem, st>>>(g, c.io, *c.cub, sa, cp.L, cp.nchunks,  \
-                                                                            w.splan.prefix[0], w.sinit, w.fs, gtab))); \
+                                                                            w.splan.prefix[0], swp, w.sinit, w.fs, gtab))); \
                 BN_CUDA(cudaGetLastError());                                                                           \
                 return 0;                                                                                              \
             }                                                                                                          \
         }                                                                                                              \
         const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);                                  \
         BN_LAUNCH(name, st, (it_smooth_site_kernel<G, Epi, LK, M, false><<<grid, kUpThreads, 0, st>>>(                 \
-                                g, c.io, *c.cub, sa, cp.L, cp.nchunks, w.splan.prefix[0], w.sinit, w.fs, nullptr)));   \
+                                g, c.io, *c.cub, sa, cp.L, cp.nchunks, w.splan.prefix[0], swp, w.sinit, w.fs, nullptr))); \
         BN_CUDA(cudaGetLastError());                                                                                   \
         return 0;                                                                                                      \
     }
@@ -599,12 +654,21 @@ inline int it_run(const ItCall& c) {
     G g;
     g.prepare(*c.spec);
     ChunkPlan cp = up_plan_chunks(io.N, false, d);
-    const size_t need = it_ws_doubles<d>(io.N) * sizeof(double);
+    const size_t need = it_ws_doubles<d>(io.N) * sizeof(real);
     BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
     UpWs w = up_ws<d>(c.ws, cp);
-    double* part = (double*)c.ws + up_ws_doubles<d>(io.N);
-    double* ell1 = part + 2 * cp.nchunks;              // log-likelihood partials of a speculative phase 1
+    // level 0 of both scans is done by the kernels that produce the elements (warp_prescan); the upper levels live in
+    // the region the hyper-gradient partials of the unfused update would use
+    w.fplan = make_scan_plan_warp(w.fplan.input0, w.fplan.prefix[0], w.gpart, cp.nchunks, FA::kElem);
+    w.splan = make_scan_plan_warp(w.splan.input0, w.splan.prefix[0], w.gpart + scan_upper_doubles(cp.nchunks, FA::kElem),
+                                  cp.nchunks, SA::kElem);
+    static_assert(2 * (FA::kElem + SA::kElem) <= 32 * kUpMaxGradFields, "upper scan levels do not fit the gradient region");
+    const real* fwp = w.fplan.levels > 1 ? w.fplan.prefix[1] : nullptr;
+    const real* swp = w.splan.levels > 1 ? w.splan.prefix[1] : nullptr;
+    real* part = (real*)c.ws + up_ws_doubles<d>(io.N);
+    real* ell1 = part + 2 * cp.nchunks;              // log-likelihood partials of a speculative phase 1
     int* jst = (int*)(part + 3 * cp.nchunks);          // its switch step per chunk
+    double* sum_scratch = (double*)(((uintptr_t)(part + 4 * cp.nchunks) + 15) & ~(uintptr_t)15);  // 2 kSumCtas fp64 partials
     const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
     const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
     const bool sharded = c.phase != UP_ALL;
@@ -613,14 +677,14 @@ inline int it_run(const ItCall& c) {
     if (c.phase == UP_ALL || c.phase == UP_REDUCE) {
         if (spec) {
             if (c.want_ell) BN_LAUNCH("it_reduce_spec", st, (it_reduce_spec_kernel<G, true><<<grid, kUpThreads, 0, st>>>(
-                                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst)));
+                                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst, w.fplan)));
             else BN_LAUNCH("it_reduce_spec", st, (it_reduce_spec_kernel<G, false><<<grid, kUpThreads, 0, st>>>(
-                                                     g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst)));
+                                                     g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst, w.fplan)));
         } else {
-            BN_LAUNCH("it_reduce", st, (it_reduce_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks, is_first, w.fplan.input0)));
+            BN_LAUNCH("it_reduce", st, (it_reduce_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fplan)));
         }
         BN_CUDA(cudaGetLastError());
-        BN_CUDA(run_scan<FA>(w.fplan, st));
+        BN_CUDA(run_scan_upper<FA>(w.fplan, st));
         if (c.carry_out && c.phase == UP_REDUCE) {
             const int top = w.fplan.levels - 1;
             export_carry_kernel<FA><<<1, 1, 0, st>>>(w.fplan.prefix[top], w.fplan.count[top], c.carry_out);
@@ -632,26 +696,25 @@ inline int it_run(const ItCall& c) {
             fold_carries_kernel<FA><<<1, 1, 0, st>>>(c.carries, 0, c.rank, 1, w.s0);
             BN_CUDA(cudaGetLastError());
         } else {
-            BN_CUDA(cudaMemsetAsync(w.s0, 0, FA::kState * sizeof(double), st));
+            BN_CUDA(cudaMemsetAsync(w.s0, 0, FA::kState * sizeof(real), st));
         }
         if (c.ell) {
             BN_LAUNCH("it_filter", st, (it_filter_kernel<G, true><<<grid, kUpThreads, 0, st>>>(
-                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, w.partials,
+                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], fwp, w.s0, w.fs, w.partials,
                                            spec ? jst : nullptr)));
             BN_CUDA(cudaGetLastError());
-            if (spec) BN_LAUNCH("sum", st, (it_sum2_kernel<<<1, 1024, 0, st>>>(w.partials, ell1, cp.nchunks, c.ell)));
-            else BN_LAUNCH("sum", st, (sum_kernel<false><<<1, 1024, 0, st>>>(w.partials, cp.nchunks, c.ell, 1.0)));
+            BN_LAUNCH("sum", st, (it_sum(w.partials, spec ? ell1 : nullptr, cp.nchunks, c.ell, 0, sum_scratch, st)));
         } else {
             BN_LAUNCH("it_filter", st, (it_filter_kernel<G, false><<<grid, kUpThreads, 0, st>>>(
-                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], w.s0, w.fs, nullptr,
+                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], fwp, w.s0, w.fs, nullptr,
                                            spec ? jst : nullptr)));
         }
         BN_CUDA(cudaGetLastError());
         const unsigned g2 = (unsigned)((cp.nchunks + 127) / 128);
-        BN_LAUNCH("up_selem", st, (up_selem_kernel<G><<<g2, 128, 0, st>>>(io.N, cp.L, cp.nchunks, !is_first, w.fplan.input0,
-                                                                          w.s0, w.fs, w.splan.input0)));
+        BN_LAUNCH("it_selem", st, (it_selem_kernel<G><<<g2, 128, 0, st>>>(io.N, cp.L, cp.nchunks, !is_first, w.fplan.input0,
+                                                                          w.s0, w.fs, w.splan.input0, w.splan)));
         BN_CUDA(cudaGetLastError());
-        BN_CUDA(run_scan<SA>(w.splan, st));
+        BN_CUDA(run_scan_upper<SA>(w.splan, st));
         if (c.carry_out && c.phase == UP_FILTER) {
             const int top = w.splan.levels - 1;
             up_export_scarry_kernel<d><<<1, 1, 0, st>>>(w.splan.prefix[top], w.splan.count[top], is_last, io.N, cp.L, w.fs,
@@ -665,7 +728,7 @@ inline int it_run(const ItCall& c) {
         BN_CUDA(cudaGetLastError());
         if (c.mode == IT_PLAIN) {
             BN_LAUNCH("it_smooth", st, (it_smooth_plain_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks,
-                                                                                               w.splan.prefix[0], w.sinit, w.fs)));
+                                                                                               w.splan.prefix[0], swp, w.sinit, w.fs)));
             BN_CUDA(cudaGetLastError());
         } else {
             ItSiteArgs sa = c.sa;
@@ -675,8 +738,7 @@ inline int it_run(const ItCall& c) {
                                           : it_launch_site_sweep<G, EpiEnergy>(c, g, cp, w, sa);
             if (rc) return rc;
             if (c.sums) {
-                sum_kernel<false><<<1, 1024, 0, st>>>(sa.part1, cp.nchunks, c.sums, 1.0);
-                sum_kernel<false><<<1, 1024, 0, st>>>(sa.part2, cp.nchunks, c.sums + 1, 1.0);
+                BN_LAUNCH("sum", st, (it_sum(sa.part1, sa.part2, cp.nchunks, c.sums, 1, sum_scratch, st)));
                 BN_CUDA(cudaGetLastError());
             }
         }
@@ -685,4 +747,4 @@ inline int it_run(const ItCall& c) {
 }
 #endif  // __CUDACC__
 
-}  // namespace bn
+}  // namespace BN_NS

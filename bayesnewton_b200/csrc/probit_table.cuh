@@ -29,9 +29,10 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include "real.cuh"
 #include "smallmat.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 constexpr int kPtN = 8192;            // intervals [i, i+1) of the table coordinate s = 512 (f - kPtLo)
 constexpr double kPtLo = -8.5;
@@ -183,4 +184,4 @@ inline const std::vector<double>& probit_table_host() {
     return tab;
 }
 
-}  // namespace bn
+}  // namespace BN_NS

@@ -11,7 +11,7 @@
 #include "common.cuh"
 #include "core.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 constexpr int kScanGroup = 288;  // 9 warps: 75 776 chunk elements (one resident wave) scan in two levels (264 groups <= 288)
 
@@ -19,11 +19,11 @@ constexpr int kScanGroup = 288;  // 9 warps: 75 776 chunk elements (one resident
 // indexing).  totals: one element per group (SoA stride t_stride), nullable on the top level.
 template <class Alg>
 __global__ void __launch_bounds__(kScanGroup)
-scan_level_kernel(const double* in, long long n, long long in_stride,
-                  double* out_prefix, long long out_stride,
-                  double* totals, long long t_stride) {
+scan_level_kernel(const real* in, long long n, long long in_stride,
+                  real* out_prefix, long long out_stride,
+                  real* totals, long long t_stride) {
     using Elem = typename Alg::Elem;
-    __shared__ double sh[(kScanGroup / 32) * Alg::kElem];
+    __shared__ real sh[(kScanGroup / 32) * Alg::kElem];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long i = (long long)blockIdx.x * kScanGroup + threadIdx.x;
     Elem mine;
@@ -34,7 +34,7 @@ scan_level_kernel(const double* in, long long n, long long in_stride,
         Alg::shfl_up(other, off);
         if (lane >= off) { Elem r; Alg::combine(other, mine, r); mine = r; }
     }
-    double* mp = reinterpret_cast<double*>(&mine);
+    real* mp = reinterpret_cast<real*>(&mine);
     if (lane == 31) {
 #pragma unroll
         for (int k = 0; k < Alg::kElem; ++k) sh[warp * Alg::kElem + k] = mp[k];
@@ -42,7 +42,7 @@ scan_level_kernel(const double* in, long long n, long long in_stride,
     __syncthreads();
     if (warp == 0) {
         Elem w;
-        double* wp = reinterpret_cast<double*>(&w);
+        real* wp = reinterpret_cast<real*>(&w);
         if (lane < kScanGroup / 32) {
 #pragma unroll
             for (int k = 0; k < Alg::kElem; ++k) wp[k] = sh[lane * Alg::kElem + k];
@@ -63,7 +63,7 @@ scan_level_kernel(const double* in, long long n, long long in_stride,
     __syncthreads();
     if (warp > 0) {
         Elem prev, r;
-        double* pp = reinterpret_cast<double*>(&prev);
+        real* pp = reinterpret_cast<real*>(&prev);
 #pragma unroll
         for (int k = 0; k < Alg::kElem; ++k) pp[k] = sh[(warp - 1) * Alg::kElem + k];
         Alg::combine(prev, mine, r);
@@ -77,8 +77,8 @@ scan_level_kernel(const double* in, long long n, long long in_stride,
 // prefix[] holds inclusive prefixes over the whole level.
 template <class Alg>
 __global__ void __launch_bounds__(kScanGroup)
-scan_down_kernel(double* prefix, long long n, long long stride,
-                 const double* group_prefix, long long g_stride) {
+scan_down_kernel(real* prefix, long long n, long long stride,
+                 const real* group_prefix, long long g_stride) {
     using Elem = typename Alg::Elem;
     const long long i = (long long)blockIdx.x * kScanGroup + threadIdx.x;
     if (blockIdx.x == 0 || i >= n) return;
@@ -94,8 +94,8 @@ struct ScanPlan {
     static constexpr int kMaxLevels = 6;
     int levels = 0;
     long long count[kMaxLevels];
-    double* prefix[kMaxLevels];  // inclusive prefixes of level l (count[l] elements)
-    double* input0 = nullptr;    // level-0 input aggregates
+    real* prefix[kMaxLevels];  // inclusive prefixes of level l (count[l] elements)
+    real* input0 = nullptr;    // level-0 input aggregates
 };
 
 inline long long scan_plan_doubles(long long n0, int elem) {
@@ -109,7 +109,7 @@ inline long long scan_plan_doubles(long long n0, int elem) {
     return tot;
 }
 
-inline ScanPlan make_scan_plan(double* ws, long long n0, int elem) {
+inline ScanPlan make_scan_plan(real* ws, long long n0, int elem) {
     ScanPlan p;
     p.input0 = ws;
     ws += n0 * elem;
@@ -133,7 +133,7 @@ inline cudaError_t run_scan(const ScanPlan& p, cudaStream_t st) {
     for (int l = 0; l < p.levels; ++l) {
         long long n = p.count[l];
         unsigned grid = (unsigned)((n + kScanGroup - 1) / kScanGroup);
-        const double* in = (l == 0) ? p.input0 : p.prefix[l];
+        const real* in = (l == 0) ? p.input0 : p.prefix[l];
         bool top = (l == p.levels - 1);
         BN_LAUNCH("scan_level", st,
                   scan_level_kernel<Alg><<<grid, kScanGroup, 0, st>>>(
@@ -149,16 +149,109 @@ inline cudaError_t run_scan(const ScanPlan& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ---- level 0 scanned by the producer of the elements, one warp per group of 32 consecutive elements -------------
+// The kernel that forms the chunk elements holds 32 consecutive ones in the lanes of a warp: it scans them in registers
+// (5 shuffle rounds) before they leave the SM, stores the within-warp inclusive prefixes and the warp total, and only the
+// totals (n / 32 elements) go through the level kernels.  The consumer applies the two parts one after the other
+// (apply_prefix2): no pass over the level-0 elements is left in the scan itself.
+constexpr int kWarpGroup = 32;
+
+inline long long scan_upper_doubles(long long n0, int elem) {
+    long long tot = 0, n = (n0 + kWarpGroup - 1) / kWarpGroup;
+    while (true) {
+        tot += n * elem;
+        if (n <= kScanGroup) break;
+        n = (n + kScanGroup - 1) / kScanGroup;
+    }
+    return tot;
+}
+
+// levels 0 (input0 / prefix0 given) and >= 1 (laid out in `upper`, scan_upper_doubles elements)
+inline ScanPlan make_scan_plan_warp(real* input0, real* prefix0, real* upper, long long n0, int elem) {
+    ScanPlan p;
+    p.input0 = input0;
+    p.count[0] = n0;
+    p.prefix[0] = prefix0;
+    p.levels = 1;
+    if (n0 <= kWarpGroup) return p;
+    long long n = (n0 + kWarpGroup - 1) / kWarpGroup;
+    while (true) {
+        p.count[p.levels] = n;
+        p.prefix[p.levels] = upper;
+        upper += n * elem;
+        ++p.levels;
+        if (n <= kScanGroup) break;
+        n = (n + kScanGroup - 1) / kScanGroup;
+    }
+    return p;
+}
+
+// after the producer's warp_prescan: prefix[1] <- inclusive prefixes of the warp totals
+template <class Alg>
+inline cudaError_t run_scan_upper(const ScanPlan& p, cudaStream_t st) {
+    for (int l = 1; l < p.levels; ++l) {
+        const long long n = p.count[l];
+        const unsigned grid = (unsigned)((n + kScanGroup - 1) / kScanGroup);
+        const bool top = (l == p.levels - 1);
+        BN_LAUNCH("scan_level", st,
+                  scan_level_kernel<Alg><<<grid, kScanGroup, 0, st>>>(p.prefix[l], n, n, p.prefix[l], n,
+                                                                      top ? nullptr : p.prefix[l + 1], top ? 0 : p.count[l + 1]));
+    }
+    for (int l = p.levels - 2; l >= 1; --l) {
+        const long long n = p.count[l];
+        const unsigned grid = (unsigned)((n + kScanGroup - 1) / kScanGroup);
+        BN_LAUNCH("scan_down", st,
+                  scan_down_kernel<Alg><<<grid, kScanGroup, 0, st>>>(p.prefix[l], n, n, p.prefix[l + 1], p.count[l + 1]));
+    }
+    return cudaGetLastError();
+}
+
+#ifdef __CUDACC__
+// every lane of the warp calls this (i = element index of the lane, consecutive across the lanes and warp-aligned);
+// lanes past the end contribute the identity
+template <class Alg>
+__device__ __forceinline__ void warp_prescan(typename Alg::Elem& mine, long long i, const ScanPlan& p) {
+    const int lane = threadIdx.x & 31;
+    const long long n = p.count[0];
+    if (i >= n) Alg::identity(mine);
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        typename Alg::Elem other = mine;
+        Alg::shfl_up(other, off);
+        if (lane >= off) { typename Alg::Elem r; Alg::combine(other, mine, r); mine = r; }
+    }
+    if (i < n) Alg::store(p.prefix[0], n, i, mine);
+    if (lane == 31 && p.levels > 1) Alg::store(p.prefix[1], p.count[1], i >> 5, mine);
+}
+#endif
+
+// state after the elements 0..q of the scan order, from the incoming state s: prefix0 = within-warp inclusive prefixes,
+// wprefix = inclusive prefixes of the warp totals (null: prefix0 already holds the global prefixes)
+template <class Alg>
+BN_DEV void apply_prefix2(const real* prefix0, long long n0, const real* wprefix, long long n1, long long q,
+                          typename Alg::State& s) {
+    typename Alg::Elem e;
+    typename Alg::State t;
+    if (wprefix && (q >> 5) > 0) {
+        Alg::load(wprefix, n1, (q >> 5) - 1, e);
+        Alg::apply(e, s, t);
+        s = t;
+    }
+    Alg::load(prefix0, n0, q, e);
+    Alg::apply(e, s, t);
+    s = t;
+}
+
 // ---- carries exchanged between time shards (multi-GPU two-level scan)
 template <class Alg>
-BN_DEV void export_carry_body(const double* top_prefix, long long n_top, double* carry) {
+BN_DEV void export_carry_body(const real* top_prefix, long long n_top, real* carry) {
     typename Alg::Elem e;
     Alg::load(top_prefix, n_top, n_top - 1, e);
     Alg::to_carry(e, carry);
 }
 
 template <class Alg>
-__global__ void export_carry_kernel(const double* top_prefix, long long n_top, double* carry) {
+__global__ void export_carry_kernel(const real* top_prefix, long long n_top, real* carry) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     export_carry_body<Alg>(top_prefix, n_top, carry);
 }
@@ -166,7 +259,7 @@ __global__ void export_carry_kernel(const double* top_prefix, long long n_top, d
 // s0 <- fold of the carries of the ranks that precede this one in scan order
 // (filter: ranks 0..rank-1 ascending; smoother: ranks world-1..rank+1 descending)
 template <class Alg>
-BN_DEV void fold_carries_body(const double* carries, int first, int last_excl, int step, double* s0) {
+BN_DEV void fold_carries_body(const real* carries, int first, int last_excl, int step, real* s0) {
     typename Alg::State s;
     Alg::zero_state(s);
     for (int r = first; r != last_excl; r += step) {
@@ -180,9 +273,9 @@ BN_DEV void fold_carries_body(const double* carries, int first, int last_excl, i
 }
 
 template <class Alg>
-__global__ void fold_carries_kernel(const double* carries, int first, int last_excl, int step, double* s0) {
+__global__ void fold_carries_kernel(const real* carries, int first, int last_excl, int step, real* s0) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     fold_carries_body<Alg>(carries, first, last_excl, step, s0);
 }
 
-}  // namespace bn
+}  // namespace BN_NS

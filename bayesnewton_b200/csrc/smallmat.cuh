@@ -5,10 +5,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include "real.cuh"
 
-namespace bn {
-
-#define BN_DEV __host__ __device__ __forceinline__
+namespace BN_NS {
 
 __host__ __device__ constexpr int symn(int d) { return d * (d + 1) / 2; }
 __host__ __device__ constexpr int sidx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
@@ -243,4 +242,4 @@ BN_DEV void lu_solve_nopivot(T* M, T* B) {
     }
 }
 
-}  // namespace bn
+}  // namespace BN_NS

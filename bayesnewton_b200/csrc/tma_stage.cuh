@@ -3,8 +3,9 @@
 // spends load / store instructions or registers on the copy (the probit log-density table, 128 KB per CTA).
 #pragma once
 #include <cstdint>
+#include "real.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 // all threads of the CTA call this; returns when `bytes` (a multiple of 16, dst / src 16-byte aligned) are in shared memory
 __device__ __forceinline__ void tma_stage_to_smem(void* smem_dst, const void* gsrc, uint32_t bytes) {
@@ -34,4 +35,4 @@ __device__ __forceinline__ void tma_stage_to_smem(void* smem_dst, const void* gs
     }
 }
 
-}  // namespace bn
+}  // namespace BN_NS

@@ -20,7 +20,7 @@
 #include "fast_core.cuh"
 #include "scan.cuh"
 
-namespace bn {
+namespace BN_NS {
 
 #ifndef BN_UP_TJ
 #define BN_UP_TJ 8
@@ -40,12 +40,12 @@ constexpr int kUpGradBlocksPerSM = BN_UP_GRAD_BLOCKS;  // the gradient-carrying 
 
 struct UpIO {
     long long N;
-    const double* dt;           // [N]
-    const double* y;            // [N,D]     pseudo observations (site means)
-    const double* R;            // [N,D,D]   site covariances
+    const real* dt;           // [N]
+    const real* y;            // [N,D]     pseudo observations (site means)
+    const real* R;            // [N,D,D]   site covariances
     const unsigned char* mask;  // [N,D] or null
-    double* post_mean;          // [N,D]     H sm
-    double* post_cov;           // [N,D,D]   H sP H^T
+    real* post_mean;          // [N,D]     H sm
+    real* post_cov;           // [N,D,D]   H sP H^T
 };
 
 // one resident wave of chunk threads: the kernels of states with d > 3 are compiled for one CTA per SM (registers), so
@@ -70,7 +70,7 @@ inline long long fs_doubles(long long nchunks, int L, int nfields) {
 }
 
 template <int d>
-BN_DEV void fs_store(double* fs, long long c, int L, int j, const double* m, const double* P) {
+BN_DEV void fs_store(real* fs, long long c, int L, int j, const real* m, const real* P) {
     constexpr int nf = d + symn(d);
 #pragma unroll
     for (int f = 0; f < d; ++f) fs[fs_index(c, L, j, f, nf)] = m[f];
@@ -78,7 +78,7 @@ BN_DEV void fs_store(double* fs, long long c, int L, int j, const double* m, con
     for (int f = 0; f < symn(d); ++f) fs[fs_index(c, L, j, d + f, nf)] = P[f];
 }
 template <int d>
-BN_DEV void fs_load(const double* fs, long long c, int L, int j, double* m, double* P) {
+BN_DEV void fs_load(const real* fs, long long c, int L, int j, real* m, real* P) {
     constexpr int nf = d + symn(d);
 #pragma unroll
     for (int f = 0; f < d; ++f) m[f] = fs[fs_index(c, L, j, f, nf)];
@@ -92,14 +92,14 @@ BN_DEV void fs_load(const double* fs, long long c, int L, int j, double* m, doub
 template <int D>
 struct DirectCtx {
     UpIO io;
-    BN_DEV double dt(long long k, int) const { return k < io.N ? io.dt[k] : 0.0; }
-    BN_DEV void obs(long long k, int, double* y, double* R) const {
+    BN_DEV real dt(long long k, int) const { return k < io.N ? io.dt[k] : 0.0; }
+    BN_DEV void obs(long long k, int, real* y, real* R) const {
 #pragma unroll
         for (int i = 0; i < D; ++i) y[i] = io.y[k * D + i];
 #pragma unroll
         for (int i = 0; i < D * D; ++i) R[i] = io.R[k * (D * D) + i];
     }
-    BN_DEV void put(long long k, int, const double* pm, const double* pc) {
+    BN_DEV void put(long long k, int, const real* pm, const real* pc) {
 #pragma unroll
         for (int i = 0; i < D; ++i) io.post_mean[k * D + i] = pm[i];
 #pragma unroll
@@ -108,7 +108,7 @@ struct DirectCtx {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void cp_async_8(double* dst_smem, const double* src) {
+__device__ __forceinline__ void cp_async_8(real* dst_smem, const real* src) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(a), "l"(src) : "memory");
 }
@@ -119,7 +119,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // WarpCtx: the 32 chunks of a warp stage kUpTJ steps at a time through shared memory.  Global
 // accesses are row segments of kUpTJ * W consecutive doubles per chunk, read and written by
 // consecutive lanes; each lane then walks its own row (odd row pitch: no bank conflicts).
-// For D = 1 the input tiles are double-buffered and filled with cp.async (LDGSTS): the tile of
+// For D = 1 the input tiles are real-buffered and filled with cp.async (LDGSTS): the tile of
 // the next sub-block is in flight while the warp computes the current one, so the HBM latency
 // of the staging loads is off the critical path.
 template <int W>
@@ -127,15 +127,15 @@ struct Tile {
     static constexpr int RW = kUpTJ * W;
     static constexpr int P = RW | 1;
     static constexpr int kDoubles = 32 * P;
-    double* sm;
-    __device__ void load(const double* X, long long N, long long cbase, int L, int j0, int lane) {
+    real* sm;
+    __device__ void load(const real* X, long long N, long long cbase, int L, int j0, int lane) {
         for (int i = lane; i < 32 * RW; i += 32) {
             const int r = i / RW, col = i - r * RW;
             const long long e0 = (cbase + r) * L + j0;
             sm[r * P + col] = (e0 + col / W < N) ? X[e0 * W + col] : 0.0;
         }
     }
-    __device__ void load_async(const double* X, long long N, long long cbase, int L, int j0, int lane) {
+    __device__ void load_async(const real* X, long long N, long long cbase, int L, int j0, int lane) {
 #pragma unroll 4
         for (int i = lane; i < 32 * RW; i += 32) {
             const int r = i / RW, col = i - r * RW;
@@ -143,14 +143,14 @@ struct Tile {
             if (e0 + col / W < N) cp_async_8(sm + r * P + col, X + e0 * W + col);
         }
     }
-    __device__ void store(double* X, long long N, long long cbase, int L, int j0, int lane) const {
+    __device__ void store(real* X, long long N, long long cbase, int L, int j0, int lane) const {
         for (int i = lane; i < 32 * RW; i += 32) {
             const int r = i / RW, col = i - r * RW;
             const long long e0 = (cbase + r) * L + j0;
             if (e0 + col / W < N) X[e0 * W + col] = sm[r * P + col];
         }
     }
-    __device__ double& at(int lane, int jj, int w) { return sm[lane * P + jj * W + w]; }
+    __device__ real& at(int lane, int jj, int w) { return sm[lane * P + jj * W + w]; }
 };
 
 template <int D>
@@ -163,7 +163,7 @@ struct WarpCtx {
     static constexpr int kDoublesPerWarp = (kBuf * kInDoubles > kSmootherDoubles) ? kBuf * kInDoubles : kSmootherDoubles;
 
     UpIO io;
-    double* base;
+    real* base;
     Tile<1> tdt;
     Tile<D> ty;       // observations in (filter) / posterior means out (smoother)
     Tile<D * D> tR;   // site covariances in / posterior covariances out
@@ -171,7 +171,7 @@ struct WarpCtx {
     bool smoother, primed;
 
     // filter layout: [buf0: dt | y | R][buf1: dt | y | R];  smoother layout: [dt buf0][dt buf1][out mean | out cov]
-    __device__ WarpCtx(const UpIO& io_, double* smem_warp, bool smoother_) : io(io_), base(smem_warp) {
+    __device__ WarpCtx(const UpIO& io_, real* smem_warp, bool smoother_) : io(io_), base(smem_warp) {
         lane = threadIdx.x & 31;
         cur = 0;
         smoother = smoother_;
@@ -231,14 +231,14 @@ struct WarpCtx {
         ty.store(io.post_mean, io.N, cbase, L, j0, lane);
         tR.store(io.post_cov, io.N, cbase, L, j0, lane);
     }
-    __device__ double dt(long long, int jj) { return tdt.at(lane, jj, 0); }
-    __device__ void obs(long long, int jj, double* y, double* R) {
+    __device__ real dt(long long, int jj) { return tdt.at(lane, jj, 0); }
+    __device__ void obs(long long, int jj, real* y, real* R) {
 #pragma unroll
         for (int i = 0; i < D; ++i) y[i] = ty.at(lane, jj, i);
 #pragma unroll
         for (int i = 0; i < D * D; ++i) R[i] = tR.at(lane, jj, i);
     }
-    __device__ void put(long long, int jj, const double* pm, const double* pc) {
+    __device__ void put(long long, int jj, const real* pm, const real* pc) {
 #pragma unroll
         for (int i = 0; i < D; ++i) ty.at(lane, jj, i) = pm[i];
 #pragma unroll
@@ -264,7 +264,7 @@ template <int D> __device__ __forceinline__ void ctx_end(WarpCtx<D>& cx, long lo
 // staging hooks stay warp-uniform.
 #pragma nv_exec_check_disable
 template <class G, class Ctx>
-BN_DEV void up_reduce_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, int is_first, double* agg,
+BN_DEV void up_reduce_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, int is_first, real* agg,
                             long long c, bool active) {
     constexpr int D = G::D;
     using Alg = FilterAlg<G::d>;
@@ -276,13 +276,13 @@ BN_DEV void up_reduce_chunk(const G& g, Ctx& cx, long long N, int L, long long n
         ctx_begin(cx, cbase, L, j0, 1);
         // the transition of step k+1 does not depend on the recursion: it is formed while step k runs,
         // so its exp() chain fills the dependency stalls of the update (slot kUpTJ of a tile row is padding)
-        double Abn[G::kBlockA];
+        real Abn[G::kBlockA];
         g.trans(cx.dt(k0 + j0, 0), Abn);
 #pragma unroll 1
         for (int jj = 0; jj < kUpTJ; ++jj) {
             const long long k = k0 + j0 + jj;
             if (active && k < N) {
-                double y[D], R[D * D], Ab[G::kBlockA];
+                real y[D], R[D * D], Ab[G::kBlockA];
                 cx.obs(k, jj, y, R);
 #pragma unroll
                 for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
@@ -297,7 +297,7 @@ BN_DEV void up_reduce_chunk(const G& g, Ctx& cx, long long N, int L, long long n
 #pragma nv_exec_check_disable
 template <class G, bool WANT_ELL, class Ctx>
 BN_DEV void up_filter_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, int is_first,
-                            const double* prefix, const double* s0, double* fs, double* ell_partials, long long c,
+                            const real* prefix, const real* s0, real* fs, real* ell_partials, long long c,
                             bool active) {
     constexpr int d = G::d, D = G::D;
     using Alg = FilterAlg<d>;
@@ -316,18 +316,18 @@ BN_DEV void up_filter_chunk(const G& g, Ctx& cx, long long N, int L, long long n
             g.pinf_full(s.P);
         }
     }
-    double ell = 0.0;
+    real ell = 0.0;
     const long long k0 = c * L, cbase = c & ~31LL;
     for (int j0 = 0; j0 < L; j0 += kUpTJ) {
         if (cbase * L + j0 >= N) break;
         ctx_begin(cx, cbase, L, j0, 1);
-        double Abn[G::kBlockA];  // transition of the next step, formed one step ahead (see up_reduce_chunk)
+        real Abn[G::kBlockA];  // transition of the next step, formed one step ahead (see up_reduce_chunk)
         g.trans(cx.dt(k0 + j0, 0), Abn);
 #pragma unroll 1
         for (int jj = 0; jj < kUpTJ; ++jj) {
             const long long k = k0 + j0 + jj;
             if (active && k < N) {
-                double y[D], R[D * D], Ab[G::kBlockA], mp[d], Pp[symn(d)];
+                real y[D], R[D * D], Ab[G::kBlockA], mp[d], Pp[symn(d)];
                 unsigned char mk[D];
                 cx.obs(k, jj, y, R);
                 if (cx.io.mask) {
@@ -347,8 +347,8 @@ BN_DEV void up_filter_chunk(const G& g, Ctx& cx, long long N, int L, long long n
 
 // smoothing element of chunk c, stored at scan position nchunks-1-c (the smoother scans right to left)
 template <class G>
-BN_DEV void up_selem_chunk(long long N, int L, long long nchunks, int need_first, const double* agg,
-                           const double* s0, const double* fs, double* selems, long long c) {
+BN_DEV void up_selem_chunk(long long N, int L, long long nchunks, int need_first, const real* agg,
+                           const real* s0, const real* fs, real* selems, long long c) {
     constexpr int d = G::d;
     using FA = FilterAlg<d>;
     using SA = SmootherAlg<d>;
@@ -358,7 +358,7 @@ BN_DEV void up_selem_chunk(long long N, int L, long long nchunks, int need_first
     } else {
         typename FA::Elem fe;
         FA::load(agg, nchunks, c, fe);
-        double ma[d], Pa[symn(d)], mb[d], Pb[symn(d)];
+        real ma[d], Pa[symn(d)], mb[d], Pb[symn(d)];
         if (c == 0) {
             typename FA::State s;
             FA::load_state(s0, 1, 0, s);
@@ -382,15 +382,15 @@ BN_DEV void up_selem_chunk(long long N, int L, long long nchunks, int need_first
 // and leaves the GradAcc fields in gpart[field * nchunks + c].
 #pragma nv_exec_check_disable
 template <class G, bool GRAD, class Ctx>
-BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, const double* sprefix,
-                            const double* sinit, const double* fs, long long c, bool active, int is_first = 0,
-                            const double* s0 = nullptr, double* gpart = nullptr) {
+BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long nchunks, const real* sprefix,
+                            const real* sinit, const real* fs, long long c, bool active, int is_first = 0,
+                            const real* s0 = nullptr, real* gpart = nullptr) {
     constexpr int d = G::d, D = G::D;
     using Alg = SmootherAlg<d>;
     typename Alg::State s;
     Alg::zero_state(s);
     GradAcc<G> acc;
-    double h_next = 0.0;  // length of the step out of the state being processed (GRAD only)
+    real h_next = 0.0;  // length of the step out of the state being processed (GRAD only)
     if constexpr (GRAD) acc.zero();
     const long long p = nchunks - 1 - c;
     if (active) {
@@ -406,8 +406,8 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     const long long k0 = c * L, cbase = c & ~31LL;
     const long long kend = ((c + 1) * L < N) ? (c + 1) * L : N;
     const int j_last = (int)(kend - k0) - 1;  // s is the smoothed state of this step
-    double nfm[d], nfP[symn(d)];              // filtered state of the next step to process, loaded one step ahead
-    double Abn[G::kBlockA], Qbn[G::kBlockS];  // discretisation of the next step to process, formed one step ahead
+    real nfm[d], nfP[symn(d)];              // filtered state of the next step to process, loaded one step ahead
+    real Abn[G::kBlockA], Qbn[G::kBlockS];  // discretisation of the next step to process, formed one step ahead
 #pragma unroll
     for (int i = 0; i < G::kBlockA; ++i) Abn[i] = 0.0;
 #pragma unroll
@@ -421,20 +421,20 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
             const int j = j0 + jj;
             const long long k = k0 + j;
             if (active && j <= j_last) {
-                const double h_k = cx.dt(k, jj);
-                double Ab[G::kBlockA], Qb[G::kBlockS];
+                const real h_k = cx.dt(k, jj);
+                real Ab[G::kBlockA], Qb[G::kBlockS];
 #pragma unroll
                 for (int i = 0; i < G::kBlockA; ++i) Ab[i] = Abn[i];
 #pragma unroll
                 for (int i = 0; i < G::kBlockS; ++i) Qb[i] = Qbn[i];
                 // the discretisation of the step below (k-1 -> k, length h_k) is formed while this step's
                 // dependent chain runs
-                const double h_out = h_next;
+                const real h_out = h_next;
                 h_next = h_k;
                 g.trans(h_k, Abn);
                 g.noise(Abn, Qbn);
                 if (j < j_last) {
-                    double fm[d], fP[symn(d)];
+                    real fm[d], fP[symn(d)];
 #pragma unroll
                     for (int i = 0; i < d; ++i) fm[i] = nfm[i];
 #pragma unroll
@@ -443,7 +443,7 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
                     if constexpr (GRAD) frts_step<G, true>(Ab, Qb, fm, fP, s.m, s.P, &g, h_out, &acc);
                     else frts_step<G>(Ab, Qb, fm, fP, s.m, s.P);
                 }
-                double pm[D], pc[D * D];
+                real pm[D], pc[D * D];
 #pragma unroll
                 for (int a = 0; a < D; ++a) {
                     pm[a] = s.m[G::sel(a)];
@@ -458,7 +458,7 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
     if constexpr (GRAD) {
         if (active) {
             // transition into the chunk's first step k0: s is its smoothed state, (Abn, Qbn) its discretisation, h_next its length
-            double pm_[d], pP_[symn(d)], mp[d], Pp[symn(d)], dm[d], dP[symn(d)];
+            real pm_[d], pP_[symn(d)], mp[d], Pp[symn(d)], dm[d], dP[symn(d)];
             const bool prior = (c == 0 && is_first);
             if (prior) {
 #pragma unroll
@@ -477,7 +477,7 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
                 } else {
                     fs_load<d>(fs, c - 1, L, L - 1, pm_, pP_);
                 }
-                double X[d * d];
+                real X[d * d];
                 bd_matvec<G>(Abn, pm_, mp);
                 bd_mat_sym<G>(Abn, pP_, X);
                 bd_abt_sym<G>(X, Abn, Qbn, Pp);
@@ -498,7 +498,7 @@ BN_DEV void up_smooth_chunk(const G& g, Ctx& cx, long long N, int L, long long n
 
 // state of the last step (tiled scratch -> flat state buffer): the smoother's start on the last rank
 template <int d>
-BN_DEV void up_last_state(long long N, int L, const double* fs, double* sinit) {
+BN_DEV void up_last_state(long long N, int L, const real* fs, real* sinit) {
     const long long c = (N - 1) / L;
     typename SmootherAlg<d>::State s;
     fs_load<d>(fs, c, L, (int)(N - 1 - c * L), s.m, s.P);
@@ -508,8 +508,8 @@ BN_DEV void up_last_state(long long N, int L, const double* fs, double* sinit) {
 // carry of this rank for the smoother exchange: composition of all its chunk elements, closed on
 // the last rank by the terminal element (0, fm_N-1, fP_N-1) of ops.py:314-315
 template <int d>
-BN_DEV void up_export_scarry(const double* top_prefix, long long n_top, int is_last, long long N, int L,
-                             const double* fs, double* carry) {
+BN_DEV void up_export_scarry(const real* top_prefix, long long n_top, int is_last, long long N, int L,
+                             const real* fs, real* carry) {
     using SA = SmootherAlg<d>;
     typename SA::Elem tot;
     SA::load(top_prefix, n_top, n_top - 1, tot);
@@ -529,8 +529,8 @@ BN_DEV void up_export_scarry(const double* top_prefix, long long n_top, int is_l
 // ------------------------------------------------------------------------------------------ kernels
 template <class G>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-up_reduce_kernel(G g, UpIO io, int L, long long nchunks, int is_first, double* agg) {
-    extern __shared__ double up_smem[];
+up_reduce_kernel(G g, UpIO io, int L, long long nchunks, int is_first, real* agg) {
+    extern __shared__ real up_smem[];
     WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, false);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     up_reduce_chunk(g, cx, io.N, L, nchunks, is_first, agg, c, c < nchunks);
@@ -538,9 +538,9 @@ up_reduce_kernel(G g, UpIO io, int L, long long nchunks, int is_first, double* a
 
 template <class G, bool WANT_ELL>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-up_filter_kernel(G g, UpIO io, int L, long long nchunks, int is_first, const double* prefix, const double* s0,
-                 double* fs, double* ell_partials) {
-    extern __shared__ double up_smem[];
+up_filter_kernel(G g, UpIO io, int L, long long nchunks, int is_first, const real* prefix, const real* s0,
+                 real* fs, real* ell_partials) {
+    extern __shared__ real up_smem[];
     WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, false);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     up_filter_chunk<G, WANT_ELL>(g, cx, io.N, L, nchunks, is_first, prefix, s0, fs, ell_partials, c, c < nchunks);
@@ -548,17 +548,17 @@ up_filter_kernel(G g, UpIO io, int L, long long nchunks, int is_first, const dou
 
 template <class G>
 __global__ void __launch_bounds__(128)
-up_selem_kernel(long long N, int L, long long nchunks, int need_first, const double* agg, const double* s0,
-                const double* fs, double* selems) {
+up_selem_kernel(long long N, int L, long long nchunks, int need_first, const real* agg, const real* s0,
+                const real* fs, real* selems) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < nchunks) up_selem_chunk<G>(N, L, nchunks, need_first, agg, s0, fs, selems, c);
 }
 
 template <class G>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-up_smooth_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, const double* sinit,
-                 const double* fs) {
-    extern __shared__ double up_smem[];
+up_smooth_kernel(G g, UpIO io, int L, long long nchunks, const real* sprefix, const real* sinit,
+                 const real* fs) {
+    extern __shared__ real up_smem[];
     WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, true);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     up_smooth_chunk<G, false>(g, cx, io.N, L, nchunks, sprefix, sinit, fs, c, c < nchunks);
@@ -567,19 +567,19 @@ up_smooth_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, 
 // the same sweep with the hyper-gradient accumulation (more live registers: its own occupancy bound)
 template <class G>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpGradBlocksPerSM : 1))
-up_smooth_grad_kernel(G g, UpIO io, int L, long long nchunks, const double* sprefix, const double* sinit,
-                      const double* fs, int is_first, const double* s0, double* gpart) {
-    extern __shared__ double up_smem[];
+up_smooth_grad_kernel(G g, UpIO io, int L, long long nchunks, const real* sprefix, const real* sinit,
+                      const real* fs, int is_first, const real* s0, real* gpart) {
+    extern __shared__ real up_smem[];
     WarpCtx<G::D> cx(io, up_smem + (threadIdx.x >> 5) * WarpCtx<G::D>::kDoublesPerWarp, true);
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     up_smooth_chunk<G, true>(g, cx, io.N, L, nchunks, sprefix, sinit, fs, c, c < nchunks, is_first, s0, gpart);
 }
 
 // deterministic sums of the per-chunk GradAcc fields (one block per field), then the chain to (variance, lengthscale)
-static __global__ void __launch_bounds__(1024) up_grad_sum_kernel(const double* gpart, long long nchunks, double* fields) {
-    __shared__ double sh[1024];
-    const double* x = gpart + (long long)blockIdx.x * nchunks;
-    double s = 0.0;
+static __global__ void __launch_bounds__(1024) up_grad_sum_kernel(const real* gpart, long long nchunks, real* fields) {
+    __shared__ real sh[1024];
+    const real* x = gpart + (long long)blockIdx.x * nchunks;
+    real s = 0.0;
     for (long long i = threadIdx.x; i < nchunks; i += 1024) s += x[i];
     sh[threadIdx.x] = s;
     __syncthreads();
@@ -590,18 +590,18 @@ static __global__ void __launch_bounds__(1024) up_grad_sum_kernel(const double* 
     if (threadIdx.x == 0) fields[blockIdx.x] = sh[0];
 }
 template <class G>
-__global__ void up_grad_finish_kernel(bn_kernel_spec spec, const double* fields, double* dvar, double* dlen) {
+__global__ void up_grad_finish_kernel(bn_kernel_spec spec, const real* fields, real* dvar, real* dlen) {
     if (blockIdx.x == 0 && threadIdx.x == 0) grad_finish<G>(spec, fields, dvar, dlen);
 }
 
 template <int d>
-__global__ void up_last_state_kernel(long long N, int L, const double* fs, double* sinit) {
+__global__ void up_last_state_kernel(long long N, int L, const real* fs, real* sinit) {
     if (blockIdx.x == 0 && threadIdx.x == 0) up_last_state<d>(N, L, fs, sinit);
 }
 
 template <int d>
-__global__ void up_export_scarry_kernel(const double* top_prefix, long long n_top, int is_last, long long N, int L,
-                                        const double* fs, double* carry) {
+__global__ void up_export_scarry_kernel(const real* top_prefix, long long n_top, int is_last, long long N, int L,
+                                        const real* fs, real* carry) {
     if (blockIdx.x == 0 && threadIdx.x == 0) up_export_scarry<d>(top_prefix, n_top, is_last, N, L, fs, carry);
 }
 
@@ -611,7 +611,7 @@ enum { UP_ALL = 0, UP_REDUCE = 1, UP_FILTER = 2, UP_SMOOTH = 3 };
 constexpr int kUpMaxGradFields = 16;  // >= NC * (symn(n) + 1) for every instantiated stack
 
 struct UpWs {
-    double *s0, *sinit, *partials, *gpart, *gfields, *fs;
+    real *s0, *sinit, *partials, *gpart, *gfields, *fs;
     ScanPlan fplan, splan;
 };
 
@@ -632,7 +632,7 @@ inline size_t up_ws_doubles(long long N) {
 template <int d>
 inline UpWs up_ws(void* ws, const ChunkPlan& cp) {
     UpWs w;
-    double* p = (double*)ws;
+    real* p = (real*)ws;
     w.s0 = p; p += 64;
     w.sinit = p; p += 64;
     w.fplan = make_scan_plan(p, cp.nchunks, FilterAlg<d>::kElem);
@@ -649,16 +649,16 @@ inline UpWs up_ws(void* ws, const ChunkPlan& cp) {
 struct UpCall {
     const bn_kernel_spec* spec;
     UpIO io;
-    double* ell;
+    real* ell;
     void* ws;
     size_t ws_bytes;
     cudaStream_t st;
     int phase, rank, world;
-    double* carry_out;       // UP_REDUCE: filter carry; UP_FILTER: smoother carry
-    const double* carries;   // UP_FILTER: filter carries [world]; UP_SMOOTH: smoother carries [world]
+    real* carry_out;       // UP_REDUCE: filter carry; UP_FILTER: smoother carry
+    const real* carries;   // UP_FILTER: filter carries [world]; UP_SMOOTH: smoother carries [world]
     int grad;                // 1: hyper-gradient plan; every phase of one update must agree on it
-    double* dvar;            // UP_ALL / UP_SMOOTH with grad: d ell / d variance[NC] (this shard's share)
-    double* dlen;            //                               d ell / d lengthscale[NC]
+    real* dvar;            // UP_ALL / UP_SMOOTH with grad: d ell / d variance[NC] (this shard's share)
+    real* dlen;            //                               d ell / d lengthscale[NC]
 };
 
 template <class G>
@@ -669,18 +669,18 @@ inline int up_run(const UpCall& c) {
     cudaStream_t st = c.st;
     const UpIO& io = c.io;
     if (io.N == 0) {
-        if (c.ell) BN_CUDA(cudaMemsetAsync(c.ell, 0, sizeof(double), st));
+        if (c.ell) BN_CUDA(cudaMemsetAsync(c.ell, 0, sizeof(real), st));
         return 0;
     }
     G g;
     g.prepare(*c.spec);
     static_assert(GradAcc<G>::kFields <= kUpMaxGradFields, "raise kUpMaxGradFields");
     ChunkPlan cp = up_plan_chunks(io.N, c.grad != 0, d);
-    size_t need = up_ws_doubles<d>(io.N) * sizeof(double);
+    size_t need = up_ws_doubles<d>(io.N) * sizeof(real);
     BN_REQUIRE(c.ws != nullptr && c.ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, c.ws_bytes);
     UpWs w = up_ws<d>(c.ws, cp);
     const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
-    const size_t smem = (size_t)kUpWarps * WarpCtx<G::D>::kDoublesPerWarp * sizeof(double);
+    const size_t smem = (size_t)kUpWarps * WarpCtx<G::D>::kDoublesPerWarp * sizeof(real);
     const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
     const bool sharded = c.phase != UP_ALL;
     if (smem > 48 * 1024) {  // multi-latent tiles exceed the default dynamic shared-memory window
@@ -707,7 +707,7 @@ inline int up_run(const UpCall& c) {
             fold_carries_kernel<FA><<<1, 1, 0, st>>>(c.carries, 0, c.rank, 1, w.s0);
             BN_CUDA(cudaGetLastError());
         } else {
-            BN_CUDA(cudaMemsetAsync(w.s0, 0, FA::kState * sizeof(double), st));
+            BN_CUDA(cudaMemsetAsync(w.s0, 0, FA::kState * sizeof(real), st));
         }
         if (c.ell) {
             BN_LAUNCH("up_filter", st,
@@ -763,4 +763,4 @@ inline int up_run(const UpCall& c) {
     if (c.spec->family == FAM && c.spec->n_components == NC) return up_run<FastGen<FAM, NC>>(c);
 #endif  // __CUDACC__
 
-}  // namespace bn
+}  // namespace BN_NS

@@ -128,8 +128,8 @@ class FusedShard:
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
         if post is not None:
             a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
-        ell = torch.zeros((), dtype=torch.float64, device=self.dev) if want_ell else None
-        sums = torch.zeros(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
+        ell = torch.empty((), dtype=torch.float64, device=self.dev) if want_ell else None
+        sums = torch.empty(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
         _lib.check(_lib.lib().bn_iter_pass(self.kernel.spec(), C.byref(a), int(mode), ptr(ell), ptr(sums), ptr(self.ws),
                                            self.ws.numel(), stream_ptr()))
         return ell, sums
@@ -146,7 +146,7 @@ class FusedShard:
     def filter(self, kf_carries, want_ell=True):
         a, _ = self._args(None, 0, None, 1.0, 1.0, True)
         a.want_ell = int(bool(want_ell))
-        ell = torch.zeros((), dtype=torch.float64, device=self.dev) if want_ell else None
+        ell = torch.empty((), dtype=torch.float64, device=self.dev) if want_ell else None
         carry = torch.empty(self.rts_len, dtype=torch.float64, device=self.dev)
         _lib.check(_lib.lib().bn_iter_shard_filter(self.kernel.spec(), C.byref(a), ptr(kf_carries), ptr(ell), ptr(carry),
                                                    ptr(self.ws), self.ws.numel(), stream_ptr()))
@@ -157,7 +157,7 @@ class FusedShard:
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
         if post is not None:
             a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
-        sums = torch.zeros(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
+        sums = torch.empty(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
         _lib.check(_lib.lib().bn_iter_shard_smooth(self.kernel.spec(), C.byref(a), int(mode), ptr(rts_carries), ptr(sums),
                                                    ptr(self.ws), self.ws.numel(), stream_ptr()))
         return sums

@@ -27,6 +27,24 @@ static void host_scan(const double* in, long long n, double* prefix) {
     }
 }
 
+// the scan as the fused iteration does it (scan.cuh: warp_prescan + run_scan_upper): inclusive prefixes inside groups of
+// 32 consecutive elements, and inclusive prefixes of the group totals
+template <class Alg>
+static void host_warp_scan(const double* in, long long n, double* prefix0, std::vector<double>& wprefix) {
+    const long long nw = (n + 31) / 32;
+    wprefix.assign((size_t)nw * Alg::kElem, 0.0);
+    typename Alg::Elem acc, e, r, wacc;
+    for (long long i = 0; i < n; ++i) {
+        Alg::load(in, n, i, e);
+        if ((i & 31) == 0) acc = e; else { Alg::combine(acc, e, r); acc = r; }
+        Alg::store(prefix0, n, i, acc);
+        if ((i & 31) == 31 || i == n - 1) {
+            if ((i >> 5) == 0) wacc = acc; else { Alg::combine(wacc, acc, r); wacc = r; }
+            Alg::store(wprefix.data(), nw, i >> 5, wacc);
+        }
+    }
+}
+
 // time-sharded filter over `world` emulated ranks
 template <class MakeGen>
 static int emu_kf(MakeGen make, int d_unused, int form, long long N, int L, int world, const double* y, int D,
@@ -229,11 +247,11 @@ static void host_from_tiled(long long n, int L, long long nc, const std::vector<
 
 template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
 static void emu_it_sweep(const G& g, const ItIO& io, const ItSiteArgs& sa, const Cub1& cub, int L, long long nc,
-                         const double* spre, const double* sinit, const double* fs) {
+                         const double* spre, const double* sinit, const double* fs, const double* swp) {
     const double* tab = TAB ? probit_table_host().data() : nullptr;
     for (long long c = 0; c < nc; ++c) {
         Epi<LIK, METHOD, TAB> epi(io, sa, &cub, tab);
-        it_smooth_chunk(g, io, L, nc, spre, sinit, fs, c, epi);
+        it_smooth_chunk(g, io, L, nc, spre, sinit, fs, c, epi, swp);
     }
 }
 
@@ -254,7 +272,9 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
     for (int r = 0; r <= world; ++r) off[r] = N * r / world;
     struct Rank {
         long long n, nc;
-        std::vector<double> agg, fpre, sel, spre, fs, s0, sinit, dt_t, y_t, sy_t, sR_t, pm_t, pc_t, p1, p2, ell1;
+        std::vector<double> agg, fpre, sel, spre, fs, s0, sinit, dt_t, y_t, sy_t, sR_t, pm_t, pc_t, p1, p2, ell1, fwp, swp;
+        const double* fw() const { return nc > 32 ? fwp.data() : nullptr; }
+        const double* sw() const { return nc > 32 ? swp.data() : nullptr; }
         std::vector<unsigned char> mk_t;
         std::vector<int> jst;
         ItIO io;
@@ -312,8 +332,9 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         } else {
             for (long long c = 0; c < q.nc; ++c) it_reduce_chunk(g, q.io, L, q.nc, r == 0, q.agg.data(), c);
         }
-        host_scan<FA>(q.agg.data(), q.nc, q.fpre.data());
-        export_carry_body<FA>(q.fpre.data(), q.nc, fcar.data() + (size_t)r * FA::kCarry);
+        host_warp_scan<FA>(q.agg.data(), q.nc, q.fpre.data(), q.fwp);
+        if (q.nc > 32) export_carry_body<FA>(q.fwp.data(), (q.nc + 31) / 32, fcar.data() + (size_t)r * FA::kCarry);
+        else export_carry_body<FA>(q.fpre.data(), q.nc, fcar.data() + (size_t)r * FA::kCarry);
     }
     double total = 0.0;
     for (int r = 0; r < world; ++r) {
@@ -322,14 +343,15 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         std::vector<double> partials(q.nc, 0.0);
         for (long long c = 0; c < q.nc; ++c)
             it_filter_chunk<G, true>(g, q.io, L, q.nc, r == 0, q.fpre.data(), q.s0.data(), q.fs.data(), partials.data(), c,
-                                     spec ? q.jst.data() : nullptr);
+                                     spec ? q.jst.data() : nullptr, q.fw());
         for (double v : partials) total += v;
         for (double v : q.ell1) total += v;
         if (jstar_mean) { double a = 0; for (int v : q.jst) a += v; *jstar_mean += a / (double)q.nc / world; }
         for (long long c = 0; c < q.nc; ++c)
             up_selem_chunk<G>(q.n, L, q.nc, r != 0, q.agg.data(), q.s0.data(), q.fs.data(), q.sel.data(), c);
-        host_scan<SA>(q.sel.data(), q.nc, q.spre.data());
-        up_export_scarry<d>(q.spre.data(), q.nc, r == world - 1, q.n, L, q.fs.data(), scar.data() + (size_t)r * SA::kCarry);
+        host_warp_scan<SA>(q.sel.data(), q.nc, q.spre.data(), q.swp);
+        if (q.nc > 32) up_export_scarry<d>(q.swp.data(), (q.nc + 31) / 32, r == world - 1, q.n, L, q.fs.data(), scar.data() + (size_t)r * SA::kCarry);
+        else up_export_scarry<d>(q.spre.data(), q.nc, r == world - 1, q.n, L, q.fs.data(), scar.data() + (size_t)r * SA::kCarry);
     }
     if (ell) *ell = total;
     double s1 = 0.0, s2 = 0.0;
@@ -342,7 +364,7 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         if (mode == IT_PLAIN) {
             for (long long c = 0; c < q.nc; ++c) {
                 EpiStore epi{q.io.pm, q.io.pc, nullptr, nullptr};
-                it_smooth_chunk(g, q.io, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, epi);
+                it_smooth_chunk(g, q.io, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), c, epi, q.sw());
             }
             done = true;
         }
@@ -350,11 +372,11 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         if (!done && lik == LK && method == M) {                                                                          \
             constexpr bool kTab = (LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI);                                   \
             if (mode == IT_SITES) {                                                                                       \
-                if (kTab && use_table) emu_it_sweep<G, EpiSites, LK, M, kTab>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
-                else emu_it_sweep<G, EpiSites, LK, M, false>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
+                if (kTab && use_table) emu_it_sweep<G, EpiSites, LK, M, kTab>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), q.sw()); \
+                else emu_it_sweep<G, EpiSites, LK, M, false>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), q.sw()); \
             } else {                                                                                                      \
-                if (kTab && use_table) emu_it_sweep<G, EpiEnergy, LK, M, kTab>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
-                else emu_it_sweep<G, EpiEnergy, LK, M, false>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data()); \
+                if (kTab && use_table) emu_it_sweep<G, EpiEnergy, LK, M, kTab>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), q.sw()); \
+                else emu_it_sweep<G, EpiEnergy, LK, M, false>(g, q.io, sa, cub, L, q.nc, q.spre.data(), q.sinit.data(), q.fs.data(), q.sw()); \
             }                                                                                                             \
             done = true;                                                                                                  \
         }

@@ -26,5 +26,12 @@ for w in $what; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'it_(reduce|filter|smooth)' -s 5 -c 5 -o gpurun_out/${tag}_c2_full python tools/prof_iter.py 10000000 2 > gpurun_out/${tag}_ncu.log 2>&1
       ncu -i gpurun_out/${tag}_c2_full.ncu-rep --page raw --csv > gpurun_out/${tag}_c2_raw.csv 2>/dev/null
       tail -2 gpurun_out/${tag}_ncu.log;;
+    ncu5)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_c5_launches.csv python tools/prof_iter.py 100000000 2 > gpurun_out/${tag}_c5_under_ncu.log 2>&1
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'it_(reduce|filter|smooth)' -s 6 -c 6 -o gpurun_out/${tag}_c5_full python tools/prof_iter.py 100000000 2 > gpurun_out/${tag}_c5_ncu.log 2>&1
+      ncu -i gpurun_out/${tag}_c5_full.ncu-rep --page raw --csv > gpurun_out/${tag}_c5_raw.csv 2>/dev/null
+      tail -2 gpurun_out/${tag}_c5_ncu.log;;
+    list12)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_n12m_launches.csv python tools/prof_iter.py 12500000 3 > gpurun_out/${tag}_n12m_under_ncu.log 2>&1; tail -2 gpurun_out/${tag}_n12m_under_ncu.log;;
   esac
 done
