@@ -120,6 +120,13 @@ SIGNATURES = {
     'bn_iter_shard_reduce': (_I, [_KS, _IA, _P, _P, _Z, _P]),
     'bn_iter_shard_filter': (_I, [_KS, _IA, _P, _P, _P, _P, _Z, _P]),
     'bn_iter_shard_smooth': (_I, [_KS, _IA, _I, _P, _P, _P, _Z, _P]),
+    'bn_iter_workspace_bytes_f32': (_Z, [_KS, _L]),
+    'bn_iter_to_tiled_f32': (_I, [_KS, _L, _P, _P, C.c_float, _P]),
+    'bn_iter_from_tiled_f32': (_I, [_KS, _L, _P, _P, _P]),
+    'bn_iter_pass_f32': (_I, [_KS, _IA, _I, _P, _P, _P, _Z, _P]),
+    'bn_iter_shard_reduce_f32': (_I, [_KS, _IA, _P, _P, _Z, _P]),
+    'bn_iter_shard_filter_f32': (_I, [_KS, _IA, _P, _P, _P, _P, _Z, _P]),
+    'bn_iter_shard_smooth_f32': (_I, [_KS, _IA, _I, _P, _P, _P, _Z, _P]),
     'bn_ih_workspace_bytes': (_Z, [_I, _L]),
     'bn_ih_filter': (_I, [_I, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     'bn_ih_smoother': (_I, [_I, _I, _L, _P, _P, _P, _I, _P, _P, _Z, _P]),

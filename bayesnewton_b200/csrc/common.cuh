@@ -14,6 +14,9 @@ void ktimer_end(cudaStream_t st);
 }  // namespace bn
 
 namespace BN_NS {
+#ifdef BN_REAL32
+using ::bn::set_error;
+#endif
 
 #define BN_REQUIRE(cond, ...)                     \
     do {                                          \

@@ -1,7 +1,17 @@
 // C ABI of the fused inference iteration on chunk-tiled state (include/bn_b200.h: bn_iter_*).
 // Kernels: iter_impl.cuh, instantiated per Matern family in iter_m12.cu .. iter_m72.cu.
+// The same text builds the fp32 entry points (bn_iter_*_f32; iter32.cu defines BN_REAL32 and BN_NS = bn32): `real` is
+// then a float, every array of the argument block is fp32, and ell / sums / carries are float.
 #include <cstdlib>
 #include "iter_impl.cuh"
+
+#ifdef BN_REAL32
+#define BN_ITER_FN(name) name##_f32
+typedef float bn_abi_real;
+#else
+#define BN_ITER_FN(name) name
+typedef double bn_abi_real;
+#endif
 
 namespace BN_NS {
 // BN_B200_SPEC_FILTER=0 keeps phase 1 a pure reduction (A/B validation of the speculative filter pass)
@@ -17,7 +27,11 @@ int it_group_m12(const ItCall&);
 int it_group_m32(const ItCall&);
 int it_group_m52(const ItCall&);
 int it_group_m72(const ItCall&);
-bool probit_table_enabled();
+#ifndef BN_REAL32
+}  // namespace BN_NS
+namespace bn { bool probit_table_enabled(); }
+namespace BN_NS {
+#endif
 
 static int it_dispatch(const ItCall& c) {
     int r;
@@ -40,10 +54,10 @@ static int it_check_spec(const bn_kernel_spec* k, int64_t N) {
 
 static size_t it_ws_bytes(const bn_kernel_spec* k, int64_t N) {
     switch (family_dim(k->family)) {
-        case 1: return (it_ws_doubles<1>(N) + 64) * sizeof(double);
-        case 2: return (it_ws_doubles<2>(N) + 64) * sizeof(double);
-        case 3: return (it_ws_doubles<3>(N) + 64) * sizeof(double);
-        case 4: return (it_ws_doubles<4>(N) + 64) * sizeof(double);
+        case 1: return (it_ws_doubles<1>(N) + 64) * sizeof(real);
+        case 2: return (it_ws_doubles<2>(N) + 64) * sizeof(real);
+        case 3: return (it_ws_doubles<3>(N) + 64) * sizeof(real);
+        case 4: return (it_ws_doubles<4>(N) + 64) * sizeof(real);
     }
     return 0;
 }
@@ -63,12 +77,16 @@ static int it_make_call(const bn_kernel_spec* k, const bn_iter_args* a, int mode
         BN_REQUIRE((a->post_mean_t && a->post_cov_t) || a->post_mean, "posterior output arrays are null");
     c = ItCall{};
     c.spec = k;
-    c.io = ItIO{a->N, a->dt_t, a->y_t, a->site_mean_t, a->site_cov_t, a->mask_t, a->post_mean_t, a->post_cov_t,
-                a->post_mean, a->post_cov};
+    c.io = ItIO{a->N, (const real*)a->dt_t, (const real*)a->y_t, (real*)a->site_mean_t, (real*)a->site_cov_t, a->mask_t,
+                (real*)a->post_mean_t, (real*)a->post_cov_t, (real*)a->post_mean, (real*)a->post_cov};
     c.mode = mode;
     c.method = a->method;
     c.likelihood = a->likelihood;
-    c.use_table = probit_table_enabled() ? 1 : 0;
+#ifdef BN_REAL32
+    c.use_table = 0;  // the packed table is an fp64 object; fp32 evaluates log Phi through erff / logf
+#else
+    c.use_table = ::bn::probit_table_enabled() ? 1 : 0;
+#endif
     c.sa = ItSiteArgs{a->lik_param, a->lr, a->power, a->ensure_psd, 0, nullptr, nullptr};
     c.cub = &cub;
     c.phase = phase;
@@ -112,6 +130,7 @@ static int it_transpose(const bn_kernel_spec* k, int64_t N, const T* in, T* out,
 
 using namespace BN_NS;
 
+#ifndef BN_REAL32  // the chunk plan does not depend on the scalar type
 extern "C" int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N) {
     if (it_check_spec(k, N)) return -1;
     return up_plan_chunks(N, false, family_dim(k->family)).L;
@@ -123,75 +142,80 @@ extern "C" int64_t bn_iter_tiled_len(const bn_kernel_spec* k, int64_t N) {
     return tl_len(cp.nchunks, cp.L);
 }
 
-extern "C" size_t bn_iter_workspace_bytes(const bn_kernel_spec* k, int64_t N) {
+extern "C" int bn_iter_to_tiled_u8(const bn_kernel_spec* k, int64_t N, const uint8_t* x, uint8_t* x_t, void* stream) {
+    return it_transpose<unsigned char>(k, N, x, x_t, (unsigned char)0, true, (cudaStream_t)stream);
+}
+#endif
+
+extern "C" size_t BN_ITER_FN(bn_iter_workspace_bytes)(const bn_kernel_spec* k, int64_t N) {
     if (it_check_spec(k, N)) return 0;
     return it_ws_bytes(k, N);
 }
 
-extern "C" int bn_iter_to_tiled(const bn_kernel_spec* k, int64_t N, const double* x, double* x_t, double fill, void* stream) {
-    return it_transpose<double>(k, N, x, x_t, fill, true, (cudaStream_t)stream);
+extern "C" int BN_ITER_FN(bn_iter_to_tiled)(const bn_kernel_spec* k, int64_t N, const bn_abi_real* x, bn_abi_real* x_t,
+                                            bn_abi_real fill, void* stream) {
+    return it_transpose<bn_abi_real>(k, N, x, x_t, fill, true, (cudaStream_t)stream);
 }
 
-extern "C" int bn_iter_from_tiled(const bn_kernel_spec* k, int64_t N, const double* x_t, double* x, void* stream) {
-    return it_transpose<double>(k, N, x_t, x, 0.0, false, (cudaStream_t)stream);
+extern "C" int BN_ITER_FN(bn_iter_from_tiled)(const bn_kernel_spec* k, int64_t N, const bn_abi_real* x_t, bn_abi_real* x,
+                                              void* stream) {
+    return it_transpose<bn_abi_real>(k, N, x_t, x, (bn_abi_real)0, false, (cudaStream_t)stream);
 }
 
-extern "C" int bn_iter_to_tiled_u8(const bn_kernel_spec* k, int64_t N, const uint8_t* x, uint8_t* x_t, void* stream) {
-    return it_transpose<unsigned char>(k, N, x, x_t, (unsigned char)0, true, (cudaStream_t)stream);
-}
-
-extern "C" int bn_iter_pass(const bn_kernel_spec* k, const bn_iter_args* a, int mode, double* ell, double* sums,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int BN_ITER_FN(bn_iter_pass)(const bn_kernel_spec* k, const bn_iter_args* a, int mode, bn_abi_real* ell,
+                                        bn_abi_real* sums, void* workspace, size_t workspace_bytes, void* stream) {
     Cub1 cub;
     ItCall c;
     if (int rc = it_make_call(k, a, mode, UP_ALL, cub, c)) return rc;
     BN_REQUIRE(a->world == 1 && a->rank == 0, "bn_iter_pass runs one shard; use the bn_iter_shard_* phases for world %d", a->world);
-    c.ell = ell;
+    c.ell = (real*)ell;
     c.want_ell = (ell != nullptr);
-    c.sums = sums;
+    c.sums = (real*)sums;
     c.ws = workspace;
     c.ws_bytes = workspace_bytes;
     c.st = (cudaStream_t)stream;
     return it_dispatch(c);
 }
 
-extern "C" int bn_iter_shard_reduce(const bn_kernel_spec* k, const bn_iter_args* a, double* kf_carry, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+extern "C" int BN_ITER_FN(bn_iter_shard_reduce)(const bn_kernel_spec* k, const bn_iter_args* a, bn_abi_real* kf_carry,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
     Cub1 cub;
     ItCall c;
     if (int rc = it_make_call(k, a, BN_ITER_PLAIN, UP_REDUCE, cub, c)) return rc;
     BN_REQUIRE(kf_carry != nullptr, "carry output is null");
-    c.carry_out = kf_carry;
+    c.carry_out = (real*)kf_carry;
     c.ws = workspace;
     c.ws_bytes = workspace_bytes;
     c.st = (cudaStream_t)stream;
     return it_dispatch(c);
 }
 
-extern "C" int bn_iter_shard_filter(const bn_kernel_spec* k, const bn_iter_args* a, const double* kf_carries, double* ell,
-                                    double* rts_carry, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int BN_ITER_FN(bn_iter_shard_filter)(const bn_kernel_spec* k, const bn_iter_args* a, const bn_abi_real* kf_carries,
+                                                bn_abi_real* ell, bn_abi_real* rts_carry, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
     Cub1 cub;
     ItCall c;
     if (int rc = it_make_call(k, a, BN_ITER_PLAIN, UP_FILTER, cub, c)) return rc;
     BN_REQUIRE(kf_carries && rts_carry, "null carry array");
     BN_REQUIRE((ell != nullptr) == (a->want_ell != 0), "want_ell of the argument block must say whether ell is requested");
-    c.carries = kf_carries;
-    c.carry_out = rts_carry;
-    c.ell = ell;
+    c.carries = (const real*)kf_carries;
+    c.carry_out = (real*)rts_carry;
+    c.ell = (real*)ell;
     c.ws = workspace;
     c.ws_bytes = workspace_bytes;
     c.st = (cudaStream_t)stream;
     return it_dispatch(c);
 }
 
-extern "C" int bn_iter_shard_smooth(const bn_kernel_spec* k, const bn_iter_args* a, int mode, const double* rts_carries,
-                                    double* sums, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int BN_ITER_FN(bn_iter_shard_smooth)(const bn_kernel_spec* k, const bn_iter_args* a, int mode,
+                                                const bn_abi_real* rts_carries, bn_abi_real* sums, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
     Cub1 cub;
     ItCall c;
     if (int rc = it_make_call(k, a, mode, UP_SMOOTH, cub, c)) return rc;
     BN_REQUIRE(rts_carries != nullptr, "null carry array");
-    c.carries = rts_carries;
-    c.sums = sums;
+    c.carries = (const real*)rts_carries;
+    c.sums = (real*)sums;
     c.ws = workspace;
     c.ws_bytes = workspace_bytes;
     c.st = (cudaStream_t)stream;

@@ -28,11 +28,19 @@ scan_level_kernel(const real* in, long long n, long long in_stride,
     const long long i = (long long)blockIdx.x * kScanGroup + threadIdx.x;
     Elem mine;
     if (i < n) Alg::load(in, in_stride, i, mine); else Alg::identity(mine);
+    // elements and warps of this group that hold data (CTA-uniform): a short top level skips the rounds it cannot need
+    const long long left = n - (long long)blockIdx.x * kScanGroup;
+    const int nin = left < kScanGroup ? (int)left : kScanGroup, nwarps = (nin + 31) >> 5;
 #pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int off = 1; off < 32 && off < nin; off <<= 1) {
         Elem other = mine;
         Alg::shfl_up(other, off);
         if (lane >= off) { Elem r; Alg::combine(other, mine, r); mine = r; }
+    }
+    if (nwarps == 1) {
+        if (i < n) Alg::store(out_prefix, out_stride, i, mine);
+        if (totals && threadIdx.x == nin - 1) Alg::store(totals, t_stride, blockIdx.x, mine);
+        return;
     }
     real* mp = reinterpret_cast<real*>(&mine);
     if (lane == 31) {
@@ -50,7 +58,7 @@ scan_level_kernel(const real* in, long long n, long long in_stride,
             Alg::identity(w);
         }
 #pragma unroll 1
-        for (int off = 1; off < kScanGroup / 32; off <<= 1) {
+        for (int off = 1; off < nwarps; off <<= 1) {
             Elem other = w;
             Alg::shfl_up(other, off);
             if (lane >= off) { Elem r; Alg::combine(other, w, r); w = r; }
@@ -70,7 +78,7 @@ scan_level_kernel(const real* in, long long n, long long in_stride,
         mine = r;
     }
     if (i < n) Alg::store(out_prefix, out_stride, i, mine);
-    if (totals && threadIdx.x == kScanGroup - 1) Alg::store(totals, t_stride, blockIdx.x, mine);
+    if (totals && threadIdx.x == nin - 1) Alg::store(totals, t_stride, blockIdx.x, mine);
 }
 
 // prefix[i] (within-group inclusive) <- combine(group_prefix[group(i) - 1], prefix[i]) : after this

@@ -1566,6 +1566,17 @@ static cudaError_t allow_smem(Kern k) {
     return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
 }
 
+// The persistent kernels synchronise their CTAs through an L2-atomic grid barrier, which is only safe when every CTA
+// of the grid is resident at once: they are launched cooperatively, so a grid that does not fit (another context
+// holding SMs, a smaller part) fails at launch with cudaErrorCooperativeLaunchTooLarge instead of hanging.
+template <class Kern, class Args>
+static cudaError_t launch_persistent(Kern k, int grid, const Args& a, cudaStream_t s) {
+    cudaError_t e = allow_smem(k);
+    if (e != cudaSuccess) return e;
+    void* params[] = {(void*)&a};
+    return cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)grid), dim3(NTH), params, kSmemBytes, s);
+}
+
 static cudaError_t zero_prof(cudaStream_t s) {
     void* p = nullptr;
     cudaError_t e = cudaGetSymbolAddress(&p, g_prof);
@@ -1696,7 +1707,7 @@ extern "C" int bn_st_kalman_filter(const bn_kernel_spec* temporal, int M, int64_
     BN_CUDA(zero_prof(s));
     const int grid = sm_count();
     BN_REQUIRE(grid >= 2, "the dense path needs at least 2 SMs");
-#define CALL(F) BN_CUDA(allow_smem(st_filter_kernel<F>)); BN_LAUNCH("st_filter", s, st_filter_kernel<F><<<grid, NTH, kSmemBytes, s>>>(a))
+#define CALL(F) BN_LAUNCH("st_filter", s, BN_CUDA(launch_persistent(st_filter_kernel<F>, grid, a, s)))
     ST_DISPATCH_FAMILY(temporal->family, CALL)
 #undef CALL
     BN_CUDA(cudaGetLastError());
@@ -1740,7 +1751,7 @@ extern "C" int bn_st_rts_smoother(const bn_kernel_spec* temporal, int M, int64_t
         a.k0 = k0; a.k1 = k1; a.G = g.G; a.first = (k1 == N);
         BN_CUDA(cudaMemsetAsync(a.ctr, 0, 256, s));
 #define CALL(F) BN_CUDA(allow_smem(st_gain_kernel<F>)); BN_LAUNCH("st_gain", s, st_gain_kernel<F><<<ggrid, NTH, kSmemBytes, s>>>(g)); \
-                BN_CUDA(allow_smem(st_smoother_kernel<F>)); BN_LAUNCH("st_smoother", s, st_smoother_kernel<F><<<grid, NTH, kSmemBytes, s>>>(a))
+                BN_LAUNCH("st_smoother", s, BN_CUDA(launch_persistent(st_smoother_kernel<F>, grid, a, s)))
         ST_DISPATCH_FAMILY(temporal->family, CALL)
 #undef CALL
         BN_CUDA(cudaGetLastError());
@@ -1779,7 +1790,7 @@ extern "C" int bn_st_kalman_filter_meanfield(const bn_kernel_spec* temporal, int
     BN_CUDA(zero_prof(s));
     const int grid = sm_count();
     BN_REQUIRE(grid >= 2, "the dense path needs at least 2 SMs");
-#define CALL(F) BN_CUDA(allow_smem(st_mf_filter_kernel<F>)); BN_LAUNCH("st_mf_filter", s, st_mf_filter_kernel<F><<<grid, NTH, kSmemBytes, s>>>(a))
+#define CALL(F) BN_LAUNCH("st_mf_filter", s, BN_CUDA(launch_persistent(st_mf_filter_kernel<F>, grid, a, s)))
     ST_DISPATCH_FAMILY(temporal->family, CALL)
 #undef CALL
     BN_CUDA(cudaGetLastError());

@@ -33,8 +33,14 @@ def supported(spec, likelihood, method):
 class FusedShard:
     """the tiled arrays of one time shard (rank of world; a single GPU is shard 0 of 1) and the passes over them"""
 
-    def __init__(self, kernel, dt, Y, mask=None, rank=0, world=1):
+    def __init__(self, kernel, dt, Y, mask=None, rank=0, world=1, dtype=torch.float64):
+        """dtype = torch.float32 selects the fp32 build of the same kernels (bn_iter_*_f32: storage and arithmetic in
+        fp32, sums in fp64; parity bar 1e-4 against the fp64 results)"""
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError('the fused iteration is built for float64 and float32')
         self.kernel = kernel
+        self.dtype = dtype
+        self._sfx = '_f32' if dtype == torch.float32 else ''
         spec = kernel.spec()
         L = _lib.lib()
         self.rank, self.world = int(rank), int(world)
@@ -45,29 +51,32 @@ class FusedShard:
         self.tlen = int(L.bn_iter_tiled_len(spec, self.N))
         if self.chunk_len <= 0 or self.tlen <= 0:
             raise _lib.BnError('fused iteration unavailable: ' + L.bn_last_error().decode())
-        nb = int(L.bn_iter_workspace_bytes(spec, self.N))
+        nb = int(self._fn('bn_iter_workspace_bytes')(spec, self.N))
         self.ws = torch.empty(nb, dtype=torch.uint8, device=self.dev)
         self.dt_t = self.to_tiled(dt, 0.0)
         self.set_data(Y, mask)
-        self.sy_t = torch.zeros(self.tlen, dtype=torch.float64, device=self.dev)
-        self.sR_t = torch.ones(self.tlen, dtype=torch.float64, device=self.dev)
-        self.pm_t = torch.zeros(self.tlen, dtype=torch.float64, device=self.dev)
-        self.pc_t = torch.ones(self.tlen, dtype=torch.float64, device=self.dev)
+        self.sy_t = torch.zeros(self.tlen, dtype=self.dtype, device=self.dev)
+        self.sR_t = torch.ones(self.tlen, dtype=self.dtype, device=self.dev)
+        self.pm_t = torch.zeros(self.tlen, dtype=self.dtype, device=self.dev)
+        self.pc_t = torch.ones(self.tlen, dtype=self.dtype, device=self.dev)
         self.d = int(L.bn_state_dim(spec))
         self.kf_len, self.rts_len = int(L.bn_kf_carry_len(self.d)), int(L.bn_rts_carry_len(self.d))
 
+    def _fn(self, name):
+        return getattr(_lib.lib(), name + self._sfx)
+
     # ---- layout conversion at the boundary
     def to_tiled(self, x, fill=0.0, out=None):
-        x = as_dev(x).reshape(-1)
+        x = as_dev(x).reshape(-1).to(self.dtype)
         if x.shape[0] != self.N:
             raise ValueError('expected %d steps, got %d' % (self.N, x.shape[0]))
-        out = torch.empty(self.tlen, dtype=torch.float64, device=self.dev) if out is None else out
-        _lib.check(_lib.lib().bn_iter_to_tiled(self.kernel.spec(), self.N, ptr(x), ptr(out), float(fill), stream_ptr()))
+        out = torch.empty(self.tlen, dtype=self.dtype, device=self.dev) if out is None else out
+        _lib.check(self._fn('bn_iter_to_tiled')(self.kernel.spec(), self.N, ptr(x), ptr(out), float(fill), stream_ptr()))
         return out
 
     def from_tiled(self, x_t, shape=None, out=None):
-        out = torch.empty(self.N, dtype=torch.float64, device=self.dev) if out is None else out
-        _lib.check(_lib.lib().bn_iter_from_tiled(self.kernel.spec(), self.N, ptr(x_t), ptr(out), stream_ptr()))
+        out = torch.empty(self.N, dtype=self.dtype, device=self.dev) if out is None else out
+        _lib.check(self._fn('bn_iter_from_tiled')(self.kernel.spec(), self.N, ptr(x_t), ptr(out), stream_ptr()))
         return out if shape is None else out.reshape(shape)
 
     def set_dt(self, dt):
@@ -77,7 +86,7 @@ class FusedShard:
         """observations (one per step) and the mask of the missing ones (None: taken from the NaNs of Y)"""
         Y = as_dev(Y).reshape(-1)
         if getattr(self, 'y_t', None) is None:
-            self.y_t = torch.empty(self.tlen, dtype=torch.float64, device=self.dev)
+            self.y_t = torch.empty(self.tlen, dtype=self.dtype, device=self.dev)
         self.to_tiled(Y, 0.0, out=self.y_t)
         if mask is None and scan_nan:
             nan = torch.isnan(Y)
@@ -128,9 +137,9 @@ class FusedShard:
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
         if post is not None:
             a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
-        ell = torch.empty((), dtype=torch.float64, device=self.dev) if want_ell else None
-        sums = torch.empty(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
-        _lib.check(_lib.lib().bn_iter_pass(self.kernel.spec(), C.byref(a), int(mode), ptr(ell), ptr(sums), ptr(self.ws),
+        ell = torch.empty((), dtype=self.dtype, device=self.dev) if want_ell else None
+        sums = torch.empty(2, dtype=self.dtype, device=self.dev) if mode != PLAIN else None
+        _lib.check(self._fn('bn_iter_pass')(self.kernel.spec(), C.byref(a), int(mode), ptr(ell), ptr(sums), ptr(self.ws),
                                            self.ws.numel(), stream_ptr()))
         return ell, sums
 
@@ -138,17 +147,17 @@ class FusedShard:
         """want_ell must match the filter() call of the same pass"""
         a, _ = self._args(None, 0, None, 1.0, 1.0, True)
         a.want_ell = int(bool(want_ell))
-        carry = torch.empty(self.kf_len, dtype=torch.float64, device=self.dev)
-        _lib.check(_lib.lib().bn_iter_shard_reduce(self.kernel.spec(), C.byref(a), ptr(carry), ptr(self.ws), self.ws.numel(),
+        carry = torch.empty(self.kf_len, dtype=self.dtype, device=self.dev)
+        _lib.check(self._fn('bn_iter_shard_reduce')(self.kernel.spec(), C.byref(a), ptr(carry), ptr(self.ws), self.ws.numel(),
                                                    stream_ptr()))
         return carry
 
     def filter(self, kf_carries, want_ell=True):
         a, _ = self._args(None, 0, None, 1.0, 1.0, True)
         a.want_ell = int(bool(want_ell))
-        ell = torch.empty((), dtype=torch.float64, device=self.dev) if want_ell else None
-        carry = torch.empty(self.rts_len, dtype=torch.float64, device=self.dev)
-        _lib.check(_lib.lib().bn_iter_shard_filter(self.kernel.spec(), C.byref(a), ptr(kf_carries), ptr(ell), ptr(carry),
+        ell = torch.empty((), dtype=self.dtype, device=self.dev) if want_ell else None
+        carry = torch.empty(self.rts_len, dtype=self.dtype, device=self.dev)
+        _lib.check(self._fn('bn_iter_shard_filter')(self.kernel.spec(), C.byref(a), ptr(kf_carries), ptr(ell), ptr(carry),
                                                    ptr(self.ws), self.ws.numel(), stream_ptr()))
         return ell, carry
 
@@ -157,8 +166,8 @@ class FusedShard:
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
         if post is not None:
             a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
-        sums = torch.empty(2, dtype=torch.float64, device=self.dev) if mode != PLAIN else None
-        _lib.check(_lib.lib().bn_iter_shard_smooth(self.kernel.spec(), C.byref(a), int(mode), ptr(rts_carries), ptr(sums),
+        sums = torch.empty(2, dtype=self.dtype, device=self.dev) if mode != PLAIN else None
+        _lib.check(self._fn('bn_iter_shard_smooth')(self.kernel.spec(), C.byref(a), int(mode), ptr(rts_carries), ptr(sums),
                                                    ptr(self.ws), self.ws.numel(), stream_ptr()))
         return sums
 

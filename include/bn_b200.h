@@ -465,13 +465,14 @@ enum { BN_ITER_PLAIN = 0, BN_ITER_SITES = 1, BN_ITER_ENERGY = 2 };
 typedef struct {
     int64_t N;                 /* steps of this time shard */
     int32_t rank, world;       /* position of the shard (0, 1 for a single GPU) */
-    const double* dt_t;        /* tiled dt (dt[0] of rank 0 is ignored: the prior is stationary) */
-    const double* y_t;         /* tiled observations Y (SITES / ENERGY) */
-    double* site_mean_t;       /* tiled pseudo observations */
-    double* site_cov_t;        /* tiled pseudo variances */
+    /* the arrays below hold fp64 values for the bn_iter_* entry points and fp32 values for bn_iter_*_f32 */
+    const void* dt_t;          /* tiled dt (dt[0] of rank 0 is ignored: the prior is stationary) */
+    const void* y_t;           /* tiled observations Y (SITES / ENERGY) */
+    void* site_mean_t;         /* tiled pseudo observations */
+    void* site_cov_t;          /* tiled pseudo variances */
     const uint8_t* mask_t;     /* tiled mask of missing pseudo observations, nullable */
-    double* post_mean_t;       /* tiled posterior marginals, written by PLAIN / ENERGY */
-    double* post_cov_t;
+    void* post_mean_t;         /* tiled posterior marginals, written by PLAIN / ENERGY */
+    void* post_cov_t;
     int32_t method, likelihood;
     double lik_param;          /* Gaussian variance / Poisson bin size */
     int32_t Q, ensure_psd;
@@ -480,8 +481,8 @@ typedef struct {
     double lr, power;
     int32_t want_ell;          /* shard phases: the pass will produce the filter log-likelihood (all phases must agree) */
     int32_t reserved_;
-    double* post_mean;         /* nullable pair: PLAIN / ENERGY write the marginals to these [N] arrays in time order */
-    double* post_cov;          /* (the reference's posterior_mean / posterior_variance layout) instead of the tiled ones */
+    void* post_mean;           /* nullable pair: PLAIN / ENERGY write the marginals to these [N] arrays in time order */
+    void* post_cov;            /* (the reference's posterior_mean / posterior_variance layout) instead of the tiled ones */
 } bn_iter_args;
 
 int bn_iter_chunk_len(const bn_kernel_spec* k, int64_t N);       /* L */
@@ -501,6 +502,22 @@ int bn_iter_shard_filter(const bn_kernel_spec* k, const bn_iter_args* a, const d
                          double* rts_carry, void* workspace, size_t workspace_bytes, void* stream);
 int bn_iter_shard_smooth(const bn_kernel_spec* k, const bn_iter_args* a, int mode, const double* rts_carries,
                          double* sums, void* workspace, size_t workspace_bytes, void* stream);
+
+/* fp32 mode of the fused iteration: the same kernels compiled with a float scalar type (storage AND arithmetic in fp32;
+ * sums accumulated in fp64; log Phi through erff / logf instead of the packed fp64 table).  Every array of
+ * bn_iter_args, ell, sums and the carries are float; the chunk plan (bn_iter_chunk_len, bn_iter_tiled_len) is shared
+ * with the fp64 entry points.  Parity bar: 1e-4 relative against the fp64 results (tests/test_fp32_mode.py). */
+size_t bn_iter_workspace_bytes_f32(const bn_kernel_spec* k, int64_t N);
+int bn_iter_to_tiled_f32(const bn_kernel_spec* k, int64_t N, const float* x, float* x_t, float fill, void* stream);
+int bn_iter_from_tiled_f32(const bn_kernel_spec* k, int64_t N, const float* x_t, float* x, void* stream);
+int bn_iter_pass_f32(const bn_kernel_spec* k, const bn_iter_args* a, int mode, float* ell, float* sums,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int bn_iter_shard_reduce_f32(const bn_kernel_spec* k, const bn_iter_args* a, float* kf_carry,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int bn_iter_shard_filter_f32(const bn_kernel_spec* k, const bn_iter_args* a, const float* kf_carries, float* ell,
+                             float* rts_carry, void* workspace, size_t workspace_bytes, void* stream);
+int bn_iter_shard_smooth_f32(const bn_kernel_spec* k, const bn_iter_args* a, int mode, const float* rts_carries,
+                             float* sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- infinite-horizon (steady-state) filter / smoother ---------------------------------
  * kalman_filter_infinite_horizon (ops.py:881-952) and rauch_tung_striebel_smoother_infinite_horizon (:1018-1068) for one

@@ -33,5 +33,13 @@ for w in $what; do
       tail -2 gpurun_out/${tag}_c5_ncu.log;;
     list12)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_n12m_launches.csv python tools/prof_iter.py 12500000 3 > gpurun_out/${tag}_n12m_under_ncu.log 2>&1; tail -2 gpurun_out/${tag}_n12m_under_ncu.log;;
+    fp32) timeout 900 python -m pytest tests/test_fp32_mode.py -m gpu -q -x > gpurun_out/${tag}_fp32_tests.log 2>&1; tail -15 gpurun_out/${tag}_fp32_tests.log
+      timeout 600 python tools/bench_fp32.py 10000000 10 > gpurun_out/${tag}_fp32_n1e7.json 2> gpurun_out/${tag}_fp32_n1e7.err; cat gpurun_out/${tag}_fp32_n1e7.json; tail -3 gpurun_out/${tag}_fp32_n1e7.err
+      timeout 600 python tools/bench_fp32.py 100000000 5 > gpurun_out/${tag}_fp32_n1e8.json 2> gpurun_out/${tag}_fp32_n1e8.err; cat gpurun_out/${tag}_fp32_n1e8.json; tail -3 gpurun_out/${tag}_fp32_n1e8.err;;
+    racecheck)
+      for tool in racecheck synccheck memcheck; do
+        timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python tools/racecheck_small.py > gpurun_out/${tag}_sanitizer_${tool}.log 2>&1
+        tail -4 gpurun_out/${tag}_sanitizer_${tool}.log
+      done;;
   esac
 done
