@@ -3,6 +3,7 @@
 // The same text builds the fp32 entry points (bn_iter_*_f32; iter32.cu defines BN_REAL32 and BN_NS = bn32): `real` is
 // then a float, every array of the argument block is fp32, and ell / sums / carries are float.
 #include <cstdlib>
+#include <mutex>
 #include "iter_impl.cuh"
 
 #ifdef BN_REAL32
@@ -27,10 +28,29 @@ int it_group_m12(const ItCall&);
 int it_group_m32(const ItCall&);
 int it_group_m52(const ItCall&);
 int it_group_m72(const ItCall&);
-#ifndef BN_REAL32
 }  // namespace BN_NS
 namespace bn { bool probit_table_enabled(); }
 namespace BN_NS {
+#ifdef BN_REAL32
+// the fp32 table in device memory, filled once per device; handed to the kernels through the same (opaque) pointer
+// the fp64 build uses for its packed table
+__device__ __align__(16) float g_probit_tab32[kPt32N * 4];
+static bool g_probit32_ready[64] = {false};
+static std::mutex g_probit32_mutex;
+int probit_table_device(cudaStream_t, const double** tab) {
+    int dev = 0;
+    BN_CUDA(cudaGetDevice(&dev));
+    BN_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_probit32_mutex);
+    if (!g_probit32_ready[dev]) {  // synchronous: visible to every stream when this returns
+        BN_CUDA(cudaMemcpyToSymbol(g_probit_tab32, probit_table32_host().data(), kPt32Bytes, 0, cudaMemcpyHostToDevice));
+        g_probit32_ready[dev] = true;
+    }
+    void* p = nullptr;
+    BN_CUDA(cudaGetSymbolAddress(&p, g_probit_tab32));
+    *tab = (const double*)p;
+    return 0;
+}
 #endif
 
 static int it_dispatch(const ItCall& c) {
@@ -83,7 +103,7 @@ static int it_make_call(const bn_kernel_spec* k, const bn_iter_args* a, int mode
     c.method = a->method;
     c.likelihood = a->likelihood;
 #ifdef BN_REAL32
-    c.use_table = 0;  // the packed table is an fp64 object; fp32 evaluates log Phi through erff / logf
+    c.use_table = ::bn::probit_table_enabled() ? 1 : 0;  // the fp32 build has its own 8 KB table (probit_table32.cuh)
 #else
     c.use_table = ::bn::probit_table_enabled() ? 1 : 0;
 #endif

@@ -389,7 +389,13 @@ namespace BN_NS {
 // ------------------------------------------------------------------------------------------ kernels
 // the table-gathering sweeps own a whole SM: one CTA with the table in shared memory, 16 warps (d <= 3) or the 4 warps the
 // registers of a larger state leave room for
-template <class G> constexpr int kItTabThreads = (G::d <= 3) ? 512 : kUpThreads;
+// (fp32 build: the table is 8 KB, every CTA of the ordinary configuration stages its own copy)
+template <class G> constexpr int kItTabThreads = (!kReal32 && G::d <= 3) ? 512 : kUpThreads;
+#ifdef BN_REAL32
+constexpr unsigned kItTabBytes = kPt32Bytes;
+#else
+constexpr unsigned kItTabBytes = sizeof(double) * kPtDoubles;
+#endif
 
 // level 0 of the scan, done by the warp that produced the 32 elements (scan.cuh: warp_prescan); the element is read
 // back from where the chunk body left it so that the body's registers are dead by now
@@ -524,13 +530,13 @@ it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const real* spref
 int probit_table_device(cudaStream_t st, const double** tab);
 
 template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
-__global__ void __launch_bounds__(TAB ? kItTabThreads<G> : kUpThreads, TAB ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
+__global__ void __launch_bounds__(TAB ? kItTabThreads<G> : kUpThreads, (TAB && !kReal32) ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
 it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs a, int L, long long nchunks,
                       const real* sprefix, const real* swprefix, const real* sinit, const real* fs, const double* gtab) {
     extern __shared__ __align__(16) double it_smem[];
     const double* tab = nullptr;
     if constexpr (TAB) {
-        tma_stage_to_smem(it_smem, gtab, (uint32_t)(sizeof(double) * kPtDoubles));  // cp.async.bulk + mbarrier
+        tma_stage_to_smem(it_smem, gtab, kItTabBytes);  // cp.async.bulk + mbarrier
         tab = it_smem;
     }
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,10 +624,10 @@ inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp
     const real* swp = w.splan.levels > 1 ? w.splan.prefix[1] : nullptr;
 #define X(LK, M)                                                                                                      \
     if (c.likelihood == LK && c.method == M) {                                                                         \
-        if constexpr (!kReal32 && LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI) {                                \
+        if constexpr (LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI) {                                            \
             if (c.use_table) {                                                                                         \
                 auto kfn = it_smooth_site_kernel<G, Epi, LK, M, true>;                                                 \
-                const size_t smem = sizeof(double) * kPtDoubles;                                                       \
+                const size_t smem = kItTabBytes;                                                                       \
                 const double* gtab = nullptr;                                                                          \
                 if (int rc = probit_table_device(st, &gtab)) return rc;                                                \
                 BN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \

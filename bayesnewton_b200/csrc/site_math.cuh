@@ -10,6 +10,9 @@
 #include "common.cuh"
 #include "core.cuh"
 #include "probit_table.cuh"
+#ifdef BN_REAL32
+#include "probit_table32.cuh"
+#endif
 
 namespace BN_NS {
 constexpr real kSqrt2 = 1.4142135623730951;
@@ -254,6 +257,26 @@ BN_DEV SiteStats1 site_stats_1(const Lik1<LIK, TAB>& lik, real y, real m, real v
                 E -= cub.bw;
                 S1 -= cub.bwx;
                 Dh -= cub.bwd;
+                done = true;
+            }
+        }
+#elif defined(__CUDA_ARCH__)
+        if constexpr (TAB && LIK == BN_LIK_BERNOULLI_PROBIT) {
+            // fp32 build: the 8 KB cubic table of probit_table32.cuh (lik.tab addresses its float4 entries)
+            const float sm = (y == 1.0) ? mean.v : -mean.v, reach = cub.xmax.v * sd.v;
+            if (sm - reach >= kPt32Lo && sm + reach < kPt32Hi) {
+                const float sg = (y == 1.0) ? kPt32InvH : -kPt32InvH;
+                const float a1 = sg * sd.v, a0 = fmaf(sg, mean.v, -kPt32Lo * kPt32InvH);
+                const float4* t4 = reinterpret_cast<const float4*>(lik.tab);
+                float e = 0.0f, s1 = 0.0f, dh = 0.0f;
+#pragma unroll UNR
+                for (int q = 0; q < Q; ++q) {
+                    const float l = probit32_eval(t4, fmaf(a1, cx[q].v, a0));
+                    e = fmaf(cw[q].v, l, e);
+                    s1 = fmaf(cub.wx[q].v, l, s1);
+                    dh = fmaf(cub.wd[q].v, l, dh);
+                }
+                E = e; S1 = s1; Dh = dh;
                 done = true;
             }
         }
