@@ -189,6 +189,8 @@ extern "C" int bn_state_dim(const bn_kernel_spec* k) {
 
 extern "C" int bn_rts_carry_len(int d) { return 2 * d * d + d; }
 
+namespace bn { size_t gd_workspace_doubles(long long N, int d); }
+
 extern "C" size_t bn_workspace_bytes(int64_t N, int d, int D) {
     (void)D;
     if (N < 0 || d < 1) return 0;
@@ -197,6 +199,10 @@ extern "C" size_t bn_workspace_bytes(int64_t N, int d, int D) {
     long long doubles = 64 + scan_plan_doubles(cp.nchunks, (int)elem) + cp.nchunks;
     long long site_partials = 4 * ((N + 127) / 128 + 1024);
     if (site_partials > doubles) doubles = site_partials;
+    if (d <= 16) {  // the warp-cooperative path for the (d, D) pairs without a register-resident instantiation (gd.cu)
+        const long long gd = (long long)gd_workspace_doubles(N, d);
+        if (gd > doubles) doubles = gd;
+    }
     return (size_t)(doubles + 1024) * sizeof(double);
 }
 

@@ -1,6 +1,7 @@
 // C ABI of the Kalman filter (include/bn_b200.h).  The kernels live in filter_impl.cuh and are
 // instantiated per generator group in filter_m_*.cu / filter_a_*.cu.
 #include "filter_impl.cuh"
+#include "gd_impl.cuh"
 
 namespace bn {
 int kf_group_m_a(const KfCall&);
@@ -11,6 +12,7 @@ int kf_group_a_a(const KfCall&);
 int kf_group_a_b(const KfCall&);
 int kf_group_a_c(const KfCall&);
 int kf_group_a_d(const KfCall&);
+int gd_kf_arrays(int form, const GdKf& a, double* ell, void* ws, size_t ws_bytes, cudaStream_t st);
 
 static int kf_dispatch(const KfCall& c) {
     int r;
@@ -27,8 +29,13 @@ static int kf_dispatch(const KfCall& c) {
     if ((r = kf_group_a_b(c)) != kNotHandled) return r;
     if ((r = kf_group_a_c(c)) != kNotHandled) return r;
     if ((r = kf_group_a_d(c)) != kNotHandled) return r;
-    set_error("unsupported (state dim, obs dim) = (%d, %d) for the register-resident filter", c.d, c.D);
-    return -1;
+    // any other (d, D) with D <= d <= 16: the warp-cooperative path (gd.cu), single shard
+    if (c.phase != PHASE_ALL) {
+        set_error("unsupported (state dim, obs dim) = (%d, %d) for the time-sharded filter", c.d, c.D);
+        return -1;
+    }
+    GdKf a{c.io.N, c.d, c.D, c.As, c.Qs, c.H, c.io.y, c.io.R, c.m0, c.P0, c.io.mask, c.io.return_predict, c.io.fms, c.io.fPs};
+    return gd_kf_arrays(c.form, a, c.ell, c.ws, c.ws_bytes, c.st);
 }
 }  // namespace bn
 

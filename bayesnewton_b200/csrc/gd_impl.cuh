@@ -143,7 +143,7 @@ BN_DEV void gd_lu_solve(GdW w, double* M, double* B, int n, int c) {
 
 // ---------------------------------------------------------------------------------------------- shared-memory pool
 // doubles a warp needs: the state, one filtering element, and the temporaries of the heaviest routine (the combine)
-BN_DEV constexpr int gd_pool_doubles(int d) { return 12 * d * d + 12 * d + 64; }
+BN_DEV constexpr int gd_pool_doubles(int d) { return 20 * d * d + 16 * d + 64; }
 
 struct GdPool {
     double* p;

@@ -1,6 +1,7 @@
 // C ABI of the RTS smoother (include/bn_b200.h).  Kernels: smoother_impl.cuh; instantiated per
 // generator group in smoother_m_*.cu / smoother_a_*.cu.
 #include "smoother_impl.cuh"
+#include "gd_impl.cuh"
 
 namespace bn {
 int rts_group_m_a(const RtsCall&);
@@ -10,6 +11,7 @@ int rts_group_m_d(const RtsCall&);
 int rts_group_a_a(const RtsCall&);
 int rts_group_a_b(const RtsCall&);
 int rts_group_a_c(const RtsCall&);
+int gd_rts_arrays(int form, const GdRts& a, void* ws, size_t ws_bytes, cudaStream_t st);
 
 static int rts_dispatch(const RtsCall& c) {
     int r;
@@ -25,8 +27,12 @@ static int rts_dispatch(const RtsCall& c) {
     if ((r = rts_group_a_a(c)) != kNotHandled) return r;
     if ((r = rts_group_a_b(c)) != kNotHandled) return r;
     if ((r = rts_group_a_c(c)) != kNotHandled) return r;
-    set_error("unsupported (state dim, latent dim) = (%d, %d) for the register-resident smoother", c.d, c.Df);
-    return -1;
+    if (c.phase != PHASE_ALL) {
+        set_error("unsupported (state dim, latent dim) = (%d, %d) for the time-sharded smoother", c.d, c.Df);
+        return -1;
+    }
+    GdRts a{c.io.N, c.d, c.Df, c.io.fms, c.io.fPs, c.As, c.Qs, c.H, c.io.return_full, c.io.sms, c.io.sPs, c.io.gains};
+    return gd_rts_arrays(c.form, a, c.ws, c.ws_bytes, c.st);
 }
 }  // namespace bn
 

@@ -191,3 +191,29 @@ def iter_pass(lib, sp, dt, y, site_mean, site_cov, mode, method='vi', lik='probi
                            int(spec), _p(jm))
     assert rc == 0, rc
     return dict(ell=ell[0], sums=sums, site_mean=sy, site_cov=sR, post_mean=pm, post_cov=pc, jstar_mean=jm[0])
+
+
+def gd_kf(lib, form, As, Qs, H, ys, Rs, m0, P0, masks=None, L=16, return_predict=False, want_ell=True):
+    """warp-cooperative small-d filter bodies (csrc/gd_impl.cuh) on the host: ell, fms [N,d,1], fPs [N,d,d]"""
+    As, Qs, H = (np.ascontiguousarray(a, dtype=np.float64) for a in (As, Qs, H))
+    ys, Rs = np.ascontiguousarray(ys, dtype=np.float64), np.ascontiguousarray(Rs, dtype=np.float64)
+    m0, P0 = np.ascontiguousarray(m0, dtype=np.float64), np.ascontiguousarray(P0, dtype=np.float64)
+    N, d, D = As.shape[0], As.shape[1], H.shape[0]
+    mk = None if masks is None else np.ascontiguousarray(masks, dtype=np.uint8)
+    ell, fms, fPs = np.zeros(1), np.zeros((N, d, 1)), np.zeros((N, d, d))
+    lib.emu_gd_kf.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int] + [C.c_void_p] * 3
+    rc = lib.emu_gd_kf(form, N, L, d, D, _p(As), _p(Qs), _p(H), _p(ys), _p(Rs), _p(m0), _p(P0), _p(mk), int(return_predict),
+                       _p(ell) if want_ell else None, _p(fms), _p(fPs))
+    assert rc == 0
+    return ell[0], fms, fPs
+
+
+def gd_rts(lib, form, fms, fPs, As, Qs, H, L=16, return_full=False):
+    fms, fPs, As, Qs, H = (np.ascontiguousarray(a, dtype=np.float64) for a in (fms, fPs, As, Qs, H))
+    N, d, Df = As.shape[0], As.shape[1], H.shape[0]
+    Do = d if return_full else Df
+    sms, sPs, gains = np.zeros((N, Do, 1)), np.zeros((N, Do, Do)), np.zeros((N, d, d))
+    lib.emu_gd_rts.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3
+    rc = lib.emu_gd_rts(form, N, L, d, Df, _p(fms), _p(fPs), _p(As), _p(Qs), _p(H), int(return_full), _p(sms), _p(sPs), _p(gains))
+    assert rc == 0
+    return sms, sPs, gains

@@ -13,6 +13,7 @@
 #include "../../bayesnewton_b200/csrc/sites_impl.cuh"
 #include "../../bayesnewton_b200/csrc/up_impl.cuh"
 #include "../../bayesnewton_b200/csrc/iter_impl.cuh"
+#include "../../bayesnewton_b200/csrc/gd_impl.cuh"
 
 namespace bn {
 void set_error(const char*, ...) {}
@@ -666,4 +667,57 @@ extern "C" int emu_iter_pass(const bn_kernel_spec* k, long long N, int L, int wo
     X(BN_MATERN12) X(BN_MATERN32) X(BN_MATERN52) X(BN_MATERN72)
 #undef X
     return -1;
+}
+
+// ---------------------------------------------------------------------------- warp-cooperative small-d path (gd_impl.cuh)
+// the chunk bodies with (lane, lanes) = (0, 1): every lane-strided loop covers all entries, __syncwarp is a no-op
+extern "C" int emu_gd_kf(int form, long long N, int L, int d, int D, const double* As, const double* Qs, const double* H,
+                         const double* ys, const double* Rs, const double* m0, const double* P0, const unsigned char* masks,
+                         int return_predict, double* ell, double* fms, double* fPs) {
+    if (d < 1 || d > kGdMaxD || D < 1 || D > d) return -1;
+    const GdW w{0, 1};
+    std::vector<double> smem((size_t)gd_pool_doubles(d));
+    GdKf a{N, d, D, As, Qs, H, ys, Rs, m0, P0, masks, return_predict, fms, fPs};
+    if (form == BN_SEQUENTIAL) {
+        GdPool pool{smem.data()};
+        double* m = pool.take(d);
+        double* P = pool.take(d * d);
+        gd_copy(w, m, m0, d);
+        gd_copy(w, P, P0, d * d);
+        const double e = gd_kf_run(w, a, 0, N, m, P, ell != nullptr, pool);
+        if (ell) *ell = e;
+        return 0;
+    }
+    const long long nchunks = (N + L - 1) / L;
+    std::vector<double> agg((size_t)nchunks * gd_felem(d)), prefix((size_t)nchunks * gd_felem(d));
+    for (long long c = 0; c < nchunks; ++c) gd_kf_reduce_chunk(w, a, L, c, agg.data(), GdPool{smem.data()});
+    gd_kf_scan(w, d, nchunks, agg.data(), prefix.data(), GdPool{smem.data()});
+    double tot = 0.0;
+    for (long long c = 0; c < nchunks; ++c) tot += gd_kf_apply_chunk(w, a, L, c, prefix.data(), ell != nullptr, GdPool{smem.data()});
+    if (ell) *ell = tot;
+    return 0;
+}
+
+extern "C" int emu_gd_rts(int form, long long N, int L, int d, int Df, const double* fms, const double* fPs,
+                          const double* As, const double* Qs, const double* H, int return_full, double* sms, double* sPs,
+                          double* gains) {
+    if (d < 1 || d > kGdMaxD || Df < 1 || Df > d) return -1;
+    const GdW w{0, 1};
+    std::vector<double> smem((size_t)gd_pool_doubles(d));
+    GdRts a{N, d, Df, fms, fPs, As, Qs, H, return_full, sms, sPs, gains};
+    if (form == BN_SEQUENTIAL) {
+        GdPool pool{smem.data()};
+        double* sm = pool.take(d);
+        double* sP = pool.take(d * d);
+        gd_fill(w, sm, 0.0, d);
+        gd_fill(w, sP, 0.0, d * d);
+        gd_rts_run(w, a, 0, N, sm, sP, true, pool);
+        return 0;
+    }
+    const long long nchunks = (N + L - 1) / L;
+    std::vector<double> agg((size_t)nchunks * gd_selem(d)), prefix((size_t)nchunks * gd_selem(d));
+    for (long long c = 0; c < nchunks; ++c) gd_rts_reduce_chunk(w, a, L, nchunks, c, agg.data(), GdPool{smem.data()});
+    gd_rts_scan(w, d, nchunks, agg.data(), prefix.data(), GdPool{smem.data()});
+    for (long long c = 0; c < nchunks; ++c) gd_rts_apply_chunk(w, a, L, nchunks, c, prefix.data(), GdPool{smem.data()});
+    return 0;
 }
