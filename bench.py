@@ -422,6 +422,46 @@ def main_gpu(args):
         if world > 1:
             dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
         grad = (float(ms3) / gsteps, [float(v) for v in dEg.reshape(-1).tolist()])
+    # ---- the fp32 build of the same fused iteration (bn_iter_*_f32), reported beside the fp64 headline, never instead of it
+    fp32 = None
+    if world == 1 and not args.no_fp32:
+        from bayesnewton_b200 import fused
+        sh = fused.FusedShard(kern, dt_pin.to(dev), y_pin.to(dev).to(torch.float64), dtype=torch.float32)
+        sh.load_sites(torch.zeros(NL, device=dev), torch.full((NL,), 100.0, device=dev))
+
+        def step32():
+            sh.run(fused.SITES, lik, _lib.BN_METHOD_VI, None, 1.0, 1.0, True, want_ell=False)
+            return sh.run(fused.ENERGY, lik, _lib.BN_METHOD_VI, None, 1.0, 1.0, True)
+        for _ in range(args.warmup):
+            step32()
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(args.steps):
+            ell32, s32 = step32()
+        h1.record()
+        torch.cuda.synchronize()
+        ms32 = h0.elapsed_time(h1) / args.steps
+        # the same number of iterations from the same initial sites through the fp64 build of the same entry points
+        pm32, pv32 = sh.posterior()
+        pm32, pv32 = pm32.reshape(-1).double(), pv32.reshape(-1).double()
+        del sh
+        sh = fused.FusedShard(kern, dt_pin.to(dev), y_pin.to(dev).to(torch.float64))
+        sh.load_sites(torch.zeros(NL, device=dev), torch.full((NL,), 100.0, device=dev))
+        for _ in range(args.warmup + args.steps):
+            ell64, s64 = step32()
+        pm64, pv64 = sh.posterior()
+        pm64, pv64 = pm64.reshape(-1), pv64.reshape(-1)
+        fp32 = {'ms_per_step': ms32, 'value': NT / (ms32 * 1e-3), 'unit': UNIT, 'dtype': 'f32',
+                'algorithmic_bytes_per_time_step': ITER_BYTES // 2,
+                'note': 'storage and arithmetic in fp32 (sums in fp64, 8 KB cubic probit table); parity bar 1e-4 against fp64 '
+                        '(tests/test_fp32_mode.py); two fused passes through FusedShard, no model-level host code in the loop',
+                'vs_fp64_after_%d_iterations' % (args.warmup + args.steps): {
+                    'post_mean_rel': float((pm32 - pm64).abs().max() / pm64.abs().max()),
+                    'post_var_rel': float((pv32 - pv64).abs().max() / pv64.abs().max()),
+                    'log_lik_rel': abs(float(ell32) - float(ell64)) / abs(float(ell64))}}
+        del sh, pm32, pv32, pm64, pv64
+        torch.cuda.empty_cache()
     clocks = sampler.stop()
 
     # fp64 FMA peak of this device, measured now (the second roofline: at d = 3 the update kernels are fp64-pipe bound)
@@ -479,6 +519,8 @@ def main_gpu(args):
             line['with_hyper_gradient'] = {'ms_per_step': grad[0], 'value': NT / (grad[0] * 1e-3), 'unit': UNIT,
                                            'note': 'iteration + d energy / d (variance, lengthscale); the adjoint is formed inside '
                                                    'the smoother sweep, no extra HBM pass', 'd_energy': grad[1]}
+        if fp32 is not None:
+            line['fp32_mode'] = fp32
         if world == 1 and not args.no_cpu:
             r = run_cpu(args.cpu_sample, 1, 1)
             line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
@@ -717,6 +759,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=2_000_000, help='time steps of the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-grad', action='store_true', help='skip the with-hyper-gradient leg')
+    ap.add_argument('--no-fp32', action='store_true', help='skip the fp32-mode leg')
     ap.add_argument('--traffic', type=float, default=None, help='dram bytes per launch of the dominant kernel (ncu)')
     args = ap.parse_args()
     if args.n_total is None:

@@ -41,5 +41,6 @@ for w in $what; do
         timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python tools/racecheck_small.py > gpurun_out/${tag}_sanitizer_${tool}.log 2>&1
         tail -4 gpurun_out/${tag}_sanitizer_${tool}.log
       done;;
+    gd) timeout 900 python -m pytest tests/test_small_d_generic.py tests/test_spacetime.py -m gpu -q > gpurun_out/${tag}_gd_st_tests.log 2>&1; tail -5 gpurun_out/${tag}_gd_st_tests.log;;
   esac
 done
