@@ -16,6 +16,7 @@
 // steps per chunk); the filtered-state scratch is laid out [warp tile][step][field][lane] so every
 // access is a fully coalesced 256-byte warp transaction with no staging.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "fast_core.cuh"
 #include "scan.cuh"
@@ -50,8 +51,17 @@ struct UpIO {
 
 // one resident wave of chunk threads: the kernels of states with d > 3 are compiled for one CTA per SM (registers), so
 // their wave -- and with it the number of chunk elements the scan has to combine -- is four times smaller
+// BN_B200_CHUNK_TARGET=<n> overrides the wave size of the d <= 3 plan (tuning aid; read once per process)
+inline long long up_env_chunk_target() {
+    static const long long v = [] {
+        const char* e = getenv("BN_B200_CHUNK_TARGET");
+        return e ? atoll(e) : 0LL;
+    }();
+    return v;
+}
 inline ChunkPlan up_plan_chunks(long long N, bool grad = false, int d = 3) {
-    const long long target = (d > 3) ? 148LL * kUpThreads : (grad ? 148LL * kUpGradBlocksPerSM * kUpThreads : kUpTargetChunks);
+    long long target = (d > 3) ? 148LL * kUpThreads : (grad ? 148LL * kUpGradBlocksPerSM * kUpThreads : kUpTargetChunks);
+    if (d <= 3 && !grad && up_env_chunk_target() > 0) target = up_env_chunk_target();
     long long L = (N + target - 1) / target;
     L = (L + kUpTJ - 1) / kUpTJ * kUpTJ;
     if (L < kUpTJ) L = kUpTJ;  // no upper bound: for large N the chunk count stays at one resident wave
