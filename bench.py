@@ -49,6 +49,9 @@ ALGO_BYTES = {
     'up_reduce': 24, 'up_filter': 121, 'up_smooth': 120, 'up_smooth_grad': 120, 'site_update': 72, 'energy_terms': 57,
     'it_from_tiled': 16, 'it_to_tiled': 16,
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per TIME STEP of the two dominant kernels, from the ncu --set full capture
+# of this path at N = 1e8 (profiles/r4b_ncu_full_summary_c5_n1e8.csv): 12.00 GB and 13.55 GB per launch
+NCU_DRAM_BYTES_PER_STEP = {'it_smooth_sites': 120.0, 'it_smooth_energy': 135.5}
 ITER_BYTES = 636           # per time step, SURVEY 8d
 ITER_BYTES_EXECUTED = 611  # without L: compute_log_lik() is served from the filter pass of the closing update_posterior()
 
@@ -481,8 +484,13 @@ def main_gpu(args):
             ab = ALGO_BYTES.get(dom, 0)
             achieved = ab * NL / (avg_ms * 1e-3) / 1e9
             roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': args.traffic, 'peak_source': peak_src,
-                    'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/), passed with --traffic' if args.traffic else None,
+                    'frac': achieved / peak,
+                    'traffic': args.traffic if args.traffic else (NCU_DRAM_BYTES_PER_STEP[dom] * NL if dom in NCU_DRAM_BYTES_PER_STEP else None),
+                    'peak_source': peak_src,
+                    'traffic_source': ('--traffic' if args.traffic else 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of this kernel at '
+                                       'N = 1e8 (profiles/r4b_ncu_full_summary_c5_n1e8.csv), scaled per time step to this launch; below '
+                                       'the algorithmic bytes because the filtered states travel packed (72 B, not the 96 B of the '
+                                       'reference layout) and the marginals of the site pass are never stored') if (args.traffic or dom in NCU_DRAM_BYTES_PER_STEP) else None,
                     'algorithmic_bytes_per_step': ab, 'algorithmic_bytes_per_launch': ab * NL, 'avg_launch_ms': avg_ms,
                     'share_of_step': tot / (ms_per_step * args.steps),
                     'timing': 'CUDA events around every launch of this kernel, on its stream, in a second pass of the same K steps right after the timed region'}
