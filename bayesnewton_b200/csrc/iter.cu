@@ -3,6 +3,7 @@
 // The same text builds the fp32 entry points (bn_iter_*_f32; iter32.cu defines BN_REAL32 and BN_NS = bn32): `real` is
 // then a float, every array of the argument block is fp32, and ell / sums / carries are float.
 #include <cstdlib>
+#include <cmath>
 #include <mutex>
 #include "iter_impl.cuh"
 
@@ -22,6 +23,11 @@ static bool spec_filter_enabled() {
         return !(e && e[0] == '0');
     }();
     return on;
+}
+
+static int spec_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 int it_group_m12(const ItCall&);
@@ -113,6 +119,11 @@ static int it_make_call(const bn_kernel_spec* k, const bn_iter_args* a, int mode
     c.rank = a->rank;
     c.world = a->world;
     c.spec_filter = spec_filter_enabled() ? 1 : 0;
+    c.spec_min_chunk = spec_env_int("BN_B200_SPEC_MIN_CHUNK", 0);
+    {
+        const int lg = spec_env_int("BN_B200_SPEC_LOG2", 0);  // threshold 2^-lg (tuning aid; 0 = the built-in one)
+        c.spec_thr = lg > 0 ? ldexp(1.0, -lg) : 0.0;
+    }
     c.want_ell = a->want_ell;
     if (back && mode != BN_ITER_PLAIN) {
         BN_REQUIRE(a->y_t != nullptr, "y_t is null");

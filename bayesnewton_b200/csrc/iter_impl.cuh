@@ -84,10 +84,14 @@ BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks
 // the incoming state can no longer change anything at fp64 resolution: J and eta stop moving, and (b, C) IS the
 // filtered state of every later step whatever the chunk started from.  From there on the pass runs the plain filter
 // step on (b, C), writes the filtered states and sums the log-likelihood itself, and phase 3 only has to redo the
-// steps before the switch.  For chunks much longer than the forgetting time (N = 1e8: 1320 steps against ~160) that
+// steps before the switch.  For chunks much longer than the forgetting time (N = 1e8: 1320 steps against ~90) that
 // removes most of the second pass over the inputs; for short chunks the switch never happens and phase 3 does what it
 // always did.  The switch is taken by all 32 lanes of a warp together (the tiled layout needs them on the same step).
-constexpr real kSpecThreshold = 7.888609052210118e-31;  // 2^-100
+// "Forgotten" = every entry of the sensitivity, scaled by the stationary standard deviations of the states it links, is
+// below 2^-56: what the incoming state could still add to the filtered state is under an eighth of an fp64 ulp of the
+// state's own scale (measured: the energy of C5 agrees to 16 digits with the 2^-100 the path started with; each factor
+// 2^-8 shortens the wait by about 12 steps at C5's lengthscale).  BN_B200_SPEC_LOG2 / BN_B200_SPEC_MIN_CHUNK override.
+constexpr real kSpecThreshold = 1.3877787807814457e-17;  // 2^-56
 
 template <class G, bool WANT_ELL>
 struct SpecReduce {
@@ -100,7 +104,7 @@ struct SpecReduce {
     real Abn[G::kBlockA], yn, Rn, hn, ell, isd[G::d], sd[G::d];
     int cnt;
 
-    BN_DEV void init(const G& g, const ItIO& io, int L, real* fs, long long c, bool active) {
+    BN_DEV void init(const G& g, const ItIO& io, int L, real* fs, long long c, bool active, real thr = kSpecThreshold) {
         Alg::identity(el);
         ell = 0.0;
         const long long k0 = c * L, rem = io.N - k0;
@@ -116,7 +120,7 @@ struct SpecReduce {
 #pragma unroll
         for (int i = 0; i < d; ++i) {
             sd[i] = sqrt(P[sidx(i, i)]);
-            isd[i] = kSpecThreshold / sd[i];
+            isd[i] = thr / sd[i];
         }
         if (active) {
             g.trans(pdt[0], Abn);
@@ -439,12 +443,12 @@ it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const rea
 template <class G, bool WANT_ELL>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
 it_reduce_spec_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg, real* fs, real* ell_partials,
-                      int* jst, ScanPlan plan) {
+                      int* jst, ScanPlan plan, real thr) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     if ((c & ~31LL) >= nchunks) return;
     const bool active = c < nchunks;
     SpecReduce<G, WANT_ELL> sr;
-    sr.init(g, io, L, fs, active ? c : 0, active);
+    sr.init(g, io, L, fs, active ? c : 0, active, thr);
     int j = 0;
     bool all_dec = false;
 #pragma unroll 1
@@ -599,6 +603,8 @@ struct ItCall {
     real* carry_out;
     const real* carries;
     int spec_filter;          // phase 1 may switch to the plain filter once the chunk has forgotten its start (SpecReduce)
+    int spec_min_chunk;       // ... for chunks at least this long
+    double spec_thr;          // ... "forgotten" = scaled sensitivity to the incoming state below this
     int want_ell;             // the pass produces the log-likelihood (every phase of one pass must agree on it)
 };
 
@@ -608,7 +614,7 @@ inline size_t it_ws_doubles(long long N) {
 }
 
 // speculative phase 1 pays off when the chunks are much longer than the filter's forgetting time
-constexpr int kSpecMinChunk = 256;
+constexpr int kSpecMinChunk = 160;  // measured break-even: on at L = 165 (-2.3 % per iteration), off at L = 132 (+1 %)
 
 // fused (likelihood, method) pairs of the site / energy epilogues
 #define BN_FOR_EACH_ITER_SITE(X)                                                       \
@@ -678,14 +684,15 @@ inline int it_run(const ItCall& c) {
     const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
     const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
     const bool sharded = c.phase != UP_ALL;
-    const bool spec = c.spec_filter && cp.L >= kSpecMinChunk;
+    const bool spec = c.spec_filter && cp.L >= (c.spec_min_chunk > 0 ? c.spec_min_chunk : kSpecMinChunk);
+    const real spec_thr = c.spec_thr > 0.0 ? c.spec_thr : (double)kSpecThreshold;
 
     if (c.phase == UP_ALL || c.phase == UP_REDUCE) {
         if (spec) {
             if (c.want_ell) BN_LAUNCH("it_reduce_spec", st, (it_reduce_spec_kernel<G, true><<<grid, kUpThreads, 0, st>>>(
-                                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst, w.fplan)));
+                                                           g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst, w.fplan, spec_thr)));
             else BN_LAUNCH("it_reduce_spec", st, (it_reduce_spec_kernel<G, false><<<grid, kUpThreads, 0, st>>>(
-                                                     g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst, w.fplan)));
+                                                     g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fs, ell1, jst, w.fplan, spec_thr)));
         } else {
             BN_LAUNCH("it_reduce", st, (it_reduce_kernel<G><<<grid, kUpThreads, 0, st>>>(g, io, cp.L, cp.nchunks, is_first, w.fplan.input0, w.fplan)));
         }
