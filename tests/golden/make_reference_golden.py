@@ -388,9 +388,46 @@ def infinite_horizon_cases():
     return out
 
 
+def gradient_cases():
+    """d energy / d (kernel variance, lengthscale, Gaussian likelihood variance) of the REFERENCE'S energy() with sites and
+    posterior held fixed -- what objax.GradValues(model.energy, model.vars()) differentiates (README.md:56-70; the shim has
+    no reverse mode): Richardson-extrapolated central differences (h, h/2 -> O(h^4)) of the reference's own function"""
+    from bayesnewton.utils import softplus_inv
+    out = {}
+    M = bn.models
+    rng = np.random.default_rng(31)
+    N = 120
+    x = np.sort(60 * rng.random(N))
+    y = np.sin(0.3 * x) + 0.4 * rng.standard_normal(N)
+    out['x'], out['y'] = x, y
+    base = dict(var_f=1.2, len_f=4.0, var_y=0.3)
+    for mname, (cls, kw) in {'vi': (M.MarkovVariationalGP, {}), 'newton': (M.MarkovLaplaceGP, {}),
+                             'ep': (M.MarkovExpectationPropagationGP, dict(power=0.5))}.items():
+        m = cls(kernel=bn.kernels.Matern52(variance=base['var_f'], lengthscale=base['len_f']),
+                likelihood=bn.likelihoods.Gaussian(variance=base['var_y']), X=x, Y=y, parallel=False, **kw)
+        m.inference(lr=0.7)
+
+        def energy_at(**over):
+            p = dict(base, **over)
+            m.kernel.transformed_variance.value = np.array(softplus_inv(p['var_f']))
+            m.kernel.transformed_lengthscale.value = np.array(softplus_inv(p['len_f']))
+            m.likelihood.transformed_variance.value = np.array(softplus_inv(p['var_y']))
+            return float(m.energy())
+        out[mname + '_energy'] = energy_at()
+        grads = []
+        for name in ('var_f', 'len_f', 'var_y'):
+            h = 2e-3 * base[name]
+            d1 = (energy_at(**{name: base[name] + h}) - energy_at(**{name: base[name] - h})) / (2 * h)
+            d2 = (energy_at(**{name: base[name] + h / 2}) - energy_at(**{name: base[name] - h / 2})) / h
+            grads.append([(4 * d2 - d1) / 3, d2 - d1])
+        out[mname + '_grad'] = np.array(grads)   # [3, 2]: derivative, and the h -> h/2 change as an error scale
+        out[mname + '_site_mean'], out[mname + '_site_cov'] = A(m.pseudo_likelihood.mean), A(m.pseudo_likelihood.covariance)
+    return out
+
+
 CASES = {'ops': ops_cases, 'models': model_cases, 'likelihoods': likelihood_cases, 'likelihoods2': likelihood2_cases, 'models2': model2_cases, 'heteroscedastic': heteroscedastic_cases,
          'regression': regression_case, 'sparse': sparse_cases, 'spacetime': spacetime_cases,
-         'infinite_horizon': infinite_horizon_cases}
+         'infinite_horizon': infinite_horizon_cases, 'gradient': gradient_cases}
 
 if __name__ == '__main__':
     which = sys.argv[1:] or sorted(CASES)

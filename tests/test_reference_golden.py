@@ -472,3 +472,45 @@ def test_gpu_infinite_horizon_forms_agree_with_oracle(bn, N):
             s0f = oih.rauch_tung_striebel_smoother_infinite_horizon(np.full(N, 0.2), ko, m0, (Pd0, c0), return_full=rf)
             s1 = bn.ops.rauch_tung_striebel_smoother_infinite_horizon(np.full(N, 0.2), k, m0, (Pd0, c0), return_full=rf, parallel=par)
             assert rel_err(np_(s1[0]), s0f[0]) < TOL and rel_err(np_(s1[1]), s0f[1]) < TOL and rel_err(np_(s1[2]), s0f[2]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------- hyper-gradient
+# tests/golden/reference_gradient.npz: d energy / d (kernel variance, lengthscale, likelihood variance) of the REFERENCE'S
+# energy() with sites and posterior held fixed, by Richardson-extrapolated central differences of its own function (the
+# shim has no reverse mode).  Column 1 of *_grad is the h -> h/2 change of the plain central difference: the extrapolated
+# value is good to a small fraction of it.
+GRAD_TOL = 2e-7
+
+
+@pytest.mark.parametrize('method', ['vi', 'newton', 'ep'])
+def test_oracle_energy_gradient_vs_reference(method):
+    from oracle import grad
+    g = golden('gradient')
+    o = model.MarkovGP(ssm.Matern52(1.2, 4.0), sites.Gaussian(0.3), g['x'], g['y'], method=method, power=0.5, parallel=False)
+    o.inference(lr=0.7)
+    assert abs(o.energy() - g[method + '_energy']) <= 1e-11 * abs(g[method + '_energy'])
+    # d energy = - d (filter log-likelihood) for the kernel hyper-parameters (sites and posterior are state)
+    R = o.site_cov
+    _, gk = grad.ell_grad_adjoint(o.kernel, o.dt, o.site_mean, R)
+    ref = g[method + '_grad']
+    got = -np.asarray(gk, dtype=np.float64).reshape(-1)[:2]
+    assert np.all(np.abs(got - ref[:2, 0]) <= GRAD_TOL * np.maximum(1.0, np.abs(ref[:2, 0]))), (got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('method', ['vi', 'newton', 'ep'])
+@pytest.mark.parametrize('parallel', [False, True])
+def test_gpu_energy_gradient_vs_reference(bn, method, parallel):
+    """model.energy_and_grad() / energy_grad_likelihood(): the adjoint inside the smoother sweep (bn_update_posterior_grad)
+    and the likelihood-parameter sum (bn_likelihood_param_grad) against derivatives of the reference's own energy()"""
+    g = golden('gradient')
+    M = bn.models
+    cls = {'vi': M.MarkovVariationalGP, 'newton': M.MarkovLaplaceGP, 'ep': M.MarkovExpectationPropagationGP}[method]
+    kw = dict(power=0.5) if method == 'ep' else {}
+    m = cls(kernel=bn.kernels.Matern52(1.2, 4.0), likelihood=bn.likelihoods.Gaussian(0.3), X=g['x'], Y=g['y'], parallel=parallel, **kw)
+    m.inference(lr=0.7, want_grad=True)
+    E, dE = m.energy_and_grad()
+    assert abs(float(E) - g[method + '_energy']) <= TOL * abs(g[method + '_energy'])
+    ref = g[method + '_grad']
+    got = np.array([float(dE[0, 0]), float(dE[1, 0]), float(m.energy_grad_likelihood())])
+    assert np.all(np.abs(got - ref[:, 0]) <= GRAD_TOL * np.maximum(1.0, np.abs(ref[:, 0]))), (got, ref)

@@ -42,5 +42,7 @@ for w in $what; do
         tail -4 gpurun_out/${tag}_sanitizer_${tool}.log
       done;;
     gd) timeout 900 python -m pytest tests/test_small_d_generic.py tests/test_spacetime.py -m gpu -q > gpurun_out/${tag}_gd_st_tests.log 2>&1; tail -5 gpurun_out/${tag}_gd_st_tests.log;;
+    smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log;;
+    smalld) timeout 600 python tools/bench_small_d.py 200000 > gpurun_out/${tag}_small_d.json 2> gpurun_out/${tag}_small_d.err; cat gpurun_out/${tag}_small_d.json; tail -3 gpurun_out/${tag}_small_d.err;;
   esac
 done
