@@ -91,7 +91,8 @@ BN_DEV void it_reduce_chunk(const G& g, const ItIO& io, int L, long long nchunks
 // below 2^-56: what the incoming state could still add to the filtered state is under an eighth of an fp64 ulp of the
 // state's own scale (measured: the energy of C5 agrees to 16 digits with the 2^-100 the path started with; each factor
 // 2^-8 shortens the wait by about 12 steps at C5's lengthscale).  BN_B200_SPEC_LOG2 / BN_B200_SPEC_MIN_CHUNK override.
-constexpr real kSpecThreshold = 1.3877787807814457e-17;  // 2^-56
+// (fp32 build: 2^-30, the same eighth of an ulp in float)
+constexpr real kSpecThreshold = kReal32 ? 9.313225746154785e-10 : 1.3877787807814457e-17;  // 2^-30 : 2^-56
 
 template <class G, bool WANT_ELL>
 struct SpecReduce {
