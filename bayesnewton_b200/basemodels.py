@@ -45,7 +45,7 @@ class GaussianDistribution:
     def _sync(self):
         src, self.source = self.source, None
         if src is not None:
-            self._mean, self._cov = src.sites()
+            self._mean, self._cov = (t.double() for t in src.sites())  # (an fp32 shard hands back float32)
             self._nat2 = 1.0 / self._cov
             self._nat1 = self._mean * self._nat2
 
@@ -156,12 +156,27 @@ class MarkovGaussianProcess:
         st = getattr(self, '_fused', None)
         pl = self.pseudo_likelihood
         if st is None:
-            st = self._fused = fused.FusedShard(self.kernel, self.dt, self.Y, self.mask_pseudo_y)
+            st = self._fused = fused.FusedShard(self.kernel, self.dt, self.Y, self.mask_pseudo_y,
+                                                dtype=getattr(self, '_fused_dtype', torch.float64))
             st.sites_version = None
         if pl.source is not st or st.sites_version != pl.version:
             st.load_sites(pl.mean, pl.covariance)
             st.sites_version = pl.version
         return st
+
+    def set_precision(self, precision):
+        """'float32' runs the fused iteration in the fp32 build of its kernels (bn_iter_*_f32: storage and arithmetic in
+        fp32, sums in fp64; parity bar 1e-4 against fp64); posterior_mean / posterior_variance become float32 tensors, the
+        sites and everything outside the fused iteration (prediction, the stage-level entries) stay float64"""
+        dtype = {'float64': torch.float64, 'float32': torch.float32}[precision]
+        if dtype == torch.float32 and not self._fused_ok():
+            raise NotImplementedError('the fp32 build covers the fused iteration (scan form, one Matern component, a '
+                                      'single-latent likelihood, VI or Newton)')
+        self.pseudo_likelihood.mean  # noqa: B018 -- materialise the sites before the resident state is rebuilt
+        self._fused_dtype = dtype
+        self._fused = None
+        self.posterior_mean, self.posterior_variance = self.posterior_mean.to(dtype), self.posterior_variance.to(dtype)
+        self._ell_cache = self._grad_cache = self._energy_cache = None
 
     def load_inputs(self, dt, Y):
         """replace the step lengths and observations (device or pinned-host tensors of the model's length, already in
@@ -241,8 +256,9 @@ class MarkovGaussianProcess:
         N, D = pseudo_y.shape[0], pseudo_y.shape[1]
         out = torch.zeros((), dtype=torch.float64, device=pseudo_y.device)
         ws, nb = workspace(N, self.state_dim, D)
+        pm, pv = as_dev(self.posterior_mean), as_dev(self.posterior_variance)  # (float32 after set_precision('float32'))
         _lib.check(_lib.lib().bn_gaussian_expected_log_lik(
-            N, D, ptr(pseudo_y), ptr(self.posterior_mean), ptr(self.posterior_variance), ptr(pseudo_var),
+            N, D, ptr(pseudo_y), ptr(pm), ptr(pv), ptr(pseudo_var),
             ptr(self.mask_pseudo_y), None, ptr(out), ptr(ws), nb, stream_ptr()))
         return out
 

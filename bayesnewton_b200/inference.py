@@ -35,6 +35,7 @@ class InferenceMixin:
         else:
             ell, sums = st.run(fused.ENERGY, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=True)
             self.posterior_mean, self.posterior_variance = st.posterior(self.posterior_mean, self.posterior_variance)
+        ell, sums, d = ell.double(), sums.double(), d.double()  # (no-ops unless the shard runs the fp32 build)
         self._ell_cache = (ell, pl.version, self._hyper_key())
         self._grad_cache = None
         self._energy_cache = (sums[0], sums[1], self._energy_key(cubature))

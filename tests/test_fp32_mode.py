@@ -116,3 +116,35 @@ def test_fp32_large_series_vs_fp64_pass(bn, N):
     for (e32, s32, _), (e64, s64, _) in zip(o32[0], o64[0]):
         assert abs(e32 - e64) <= TOL32 * abs(e64)
         assert np.allclose(s32, s64, rtol=TOL32)
+
+
+@pytest.mark.parametrize('lik,method', [('probit', 'vi'), ('gaussian', 'vi'), ('probit', 'newton')])
+def test_fp32_model_level_precision_switch(bn, lik, method):
+    """model.set_precision('float32'): the reference-shaped model API on the fp32 build; iterations, energy, prediction
+    (which runs outside the fused iteration, in fp64, from the fp32 sites) against the same model in fp64"""
+    N = 20_011
+    t, dt, y = bench_inputs(N, 7)
+    y = observations(lik, t, y, 3)
+    y[::19] = np.nan
+    cls = bn.models.MarkovVariationalGP if method == 'vi' else bn.models.MarkovLaplaceGP
+    mk = lambda: cls(kernel=bn.kernels.Matern52(1.3, 0.9), likelihood=liks(bn)[lik][0], X=t, Y=y, parallel=True)
+    m64, m32 = mk(), mk()
+    m32.set_precision('float32')
+    for _ in range(3):
+        m64.inference(lr=0.7)
+        m32.inference(lr=0.7)
+        E64, E32 = float(m64.energy()), float(m32.energy())
+        assert abs(E32 - E64) <= TOL32 * abs(E64)
+    import torch
+    assert m32.posterior_mean.dtype == torch.float32
+    assert rel_err(np_(m32.posterior_mean), np_(m64.posterior_mean)) < TOL32
+    assert rel_err(np_(m32.posterior_variance), np_(m64.posterior_variance)) < TOL32
+    assert rel_err(np_(m32.pseudo_likelihood.nat2), np_(m64.pseudo_likelihood.nat2)) < TOL32
+    xt = np.linspace(t[0] - 1.0, t[-1] + 1.0, 41)
+    p64, v64 = m64.predict(X=xt)
+    p32, v32 = m32.predict(X=xt)
+    assert rel_err(np_(p32), np_(p64)) < TOL32 and rel_err(np_(v32), np_(v64)) < TOL32
+    m32.set_precision('float64')  # and back: the sites carry over
+    m32.inference(lr=0.7)
+    m64.inference(lr=0.7)
+    assert rel_err(np_(m32.posterior_mean), np_(m64.posterior_mean)) < TOL32
