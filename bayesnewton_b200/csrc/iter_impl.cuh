@@ -182,13 +182,13 @@ struct SpecReduce {
 template <class G, bool WANT_ELL>
 BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks, int is_first, const real* prefix,
                             const real* s0, real* fs, real* ell_partials, long long c, const int* jst = nullptr,
-                            const real* wprefix = nullptr) {
+                            const PrefixParts& up = PrefixParts()) {
     constexpr int d = G::d;
     using Alg = FilterAlg<d>;
     typename Alg::State s;
     Alg::load_state(s0, 1, 0, s);
     if (c > 0) {
-        apply_prefix2<Alg>(prefix, nchunks, wprefix, (nchunks + 31) >> 5, c - 1, s);
+        apply_prefix<Alg>(prefix, nchunks, up, c - 1, s);
     } else if (is_first) {  // global step 0 starts from the stationary prior (m0 = 0, P0 = Pinf)
         Alg::zero_state(s);
         g.pinf_full(s.P);
@@ -230,13 +230,13 @@ BN_DEV void it_filter_chunk(const G& g, const ItIO& io, int L, long long nchunks
 // RTS recursion down the chunk (ops.py:290-301); the epilogue takes the smoothed marginal of every step
 template <class G, class Epi>
 BN_DEV void it_smooth_chunk(const G& g, const ItIO& io, int L, long long nchunks, const real* sprefix,
-                            const real* sinit, const real* fs, long long c, Epi& epi, const real* swprefix = nullptr) {
+                            const real* sinit, const real* fs, long long c, Epi& epi, const PrefixParts& sup = PrefixParts()) {
     constexpr int d = G::d, nf = d + symn(d);
     using Alg = SmootherAlg<d>;
     typename Alg::State s;
     const long long p = nchunks - 1 - c;
     Alg::load_state(sinit, 1, 0, s);
-    if (p > 0) apply_prefix2<Alg>(sprefix, nchunks, swprefix, (nchunks + 31) >> 5, p - 1, s);
+    if (p > 0) apply_prefix<Alg>(sprefix, nchunks, sup, p - 1, s);
     const long long k0 = c * L, rem = io.N - k0;
     const int j_last = (rem < L ? (int)rem : L) - 1;  // s is the smoothed state of this step
     const long long b = tl_base(c, L);
@@ -434,7 +434,7 @@ it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg
 
 template <class G, bool WANT_ELL>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const real* prefix, const real* wprefix,
+it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const real* prefix, PrefixParts wprefix,
                  const real* s0, real* fs, real* ell_partials, const int* jst) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     if (c < nchunks) it_filter_chunk<G, WANT_ELL>(g, io, L, nchunks, is_first, prefix, s0, fs, ell_partials, c, jst, wprefix);
@@ -523,7 +523,7 @@ inline cudaError_t it_sum(const real* a, const real* b, long long n, real* out, 
 
 template <class G>
 __global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
-it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const real* sprefix, const real* swprefix, const real* sinit,
+it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const real* sprefix, PrefixParts swprefix, const real* sinit,
                        const real* fs) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     if (c >= nchunks) return;
@@ -537,7 +537,7 @@ int probit_table_device(cudaStream_t st, const double** tab);
 template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
 __global__ void __launch_bounds__(TAB ? kItTabThreads<G> : kUpThreads, (TAB && !kReal32) ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
 it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs a, int L, long long nchunks,
-                      const real* sprefix, const real* swprefix, const real* sinit, const real* fs, const double* gtab) {
+                      const real* sprefix, PrefixParts swprefix, const real* sinit, const real* fs, const double* gtab) {
     extern __shared__ __align__(16) double it_smem[];
     const double* tab = nullptr;
     if constexpr (TAB) {
@@ -611,7 +611,7 @@ struct ItCall {
 
 template <int d>
 inline size_t it_ws_doubles(long long N) {
-    return up_ws_doubles<d>(N) + 4 * (size_t)up_plan_chunks(N > 0 ? N : 1, false, d).nchunks + 64 + 4 * kSumCtas + 8;
+    return up_ws_doubles<d>(N) + 4 * (size_t)up_plan_chunks(N > 0 ? N : 1, false, d).nchunks + 64 + 4 * kSumCtas + 16;
 }
 
 // speculative phase 1 pays off when the chunks are much longer than the filter's forgetting time
@@ -628,7 +628,7 @@ template <class G, template <int, int, bool> class Epi>
 inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp, const UpWs& w, const ItSiteArgs& sa) {
     cudaStream_t st = c.st;
     const char* name = (c.mode == IT_SITES) ? "it_smooth_sites" : "it_smooth_energy";
-    const real* swp = w.splan.levels > 1 ? w.splan.prefix[1] : nullptr;
+    const PrefixParts swp = upper_parts(w.splan);
 #define X(LK, M)                                                                                                      \
     if (c.likelihood == LK && c.method == M) {                                                                         \
         if constexpr (LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI) {                                            \
@@ -676,12 +676,14 @@ inline int it_run(const ItCall& c) {
     w.splan = make_scan_plan_warp(w.splan.input0, w.splan.prefix[0], w.gpart + scan_upper_doubles(cp.nchunks, FA::kElem),
                                   cp.nchunks, SA::kElem);
     static_assert(2 * (FA::kElem + SA::kElem) <= 32 * kUpMaxGradFields, "upper scan levels do not fit the gradient region");
-    const real* fwp = w.fplan.levels > 1 ? w.fplan.prefix[1] : nullptr;
-    const real* swp = w.splan.levels > 1 ? w.splan.prefix[1] : nullptr;
     real* part = (real*)c.ws + up_ws_doubles<d>(io.N);
     real* ell1 = part + 2 * cp.nchunks;              // log-likelihood partials of a speculative phase 1
     int* jst = (int*)(part + 3 * cp.nchunks);          // its switch step per chunk
     double* sum_scratch = (double*)(((uintptr_t)(part + 4 * cp.nchunks) + 15) & ~(uintptr_t)15);  // 2 kSumCtas fp64 partials
+    // arrival counters of the one-launch upper scan levels (cleared by the kernels that produce the elements)
+    w.fplan.ticket = (unsigned int*)(sum_scratch + 2 * kSumCtas);
+    w.splan.ticket = w.fplan.ticket + 1;
+    const PrefixParts fwp = upper_parts(w.fplan), swp = upper_parts(w.splan);
     const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
     const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
     const bool sharded = c.phase != UP_ALL;

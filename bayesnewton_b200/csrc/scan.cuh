@@ -17,19 +17,36 @@ constexpr int kScanGroup = 288;  // 9 warps: 75 776 chunk elements (one resident
 
 // in: n elements (SoA stride n_stride).  out_prefix: within-group inclusive prefixes (same
 // indexing).  totals: one element per group (SoA stride t_stride), nullable on the top level.
-template <class Alg>
-__global__ void __launch_bounds__(kScanGroup)
-scan_level_kernel(const real* in, long long n, long long in_stride,
-                  real* out_prefix, long long out_stride,
-                  real* totals, long long t_stride) {
+// load that bypasses L1 (data another CTA of the same launch has just written)
+__device__ __forceinline__ real ld_cg(const real* p) {
+#ifdef BN_REAL32
+    return real(__ldcg(&p->v));
+#else
+    return __ldcg(p);
+#endif
+}
+
+// CG: the inputs were written by other CTAs of this launch -- read them from L2.  (An element is kElem reals in the
+// field order of Alg::load.)
+template <class Alg, bool CG = false>
+__device__ __forceinline__ void scan_group(const real* in, long long n, long long in_stride, real* out_prefix, long long out_stride,
+                                           real* totals, long long t_stride, long long group) {
     using Elem = typename Alg::Elem;
     __shared__ real sh[(kScanGroup / 32) * Alg::kElem];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long i = (long long)blockIdx.x * kScanGroup + threadIdx.x;
+    const long long i = group * kScanGroup + threadIdx.x;
     Elem mine;
-    if (i < n) Alg::load(in, in_stride, i, mine); else Alg::identity(mine);
+    if (i >= n) {
+        Alg::identity(mine);
+    } else if constexpr (CG) {
+        real* q = reinterpret_cast<real*>(&mine);
+#pragma unroll
+        for (int k = 0; k < Alg::kElem; ++k) q[k] = ld_cg(in + (long long)k * in_stride + i);
+    } else {
+        Alg::load(in, in_stride, i, mine);
+    }
     // elements and warps of this group that hold data (CTA-uniform): a short top level skips the rounds it cannot need
-    const long long left = n - (long long)blockIdx.x * kScanGroup;
+    const long long left = n - group * kScanGroup;
     const int nin = left < kScanGroup ? (int)left : kScanGroup, nwarps = (nin + 31) >> 5;
 #pragma unroll 1
     for (int off = 1; off < 32 && off < nin; off <<= 1) {
@@ -39,7 +56,7 @@ scan_level_kernel(const real* in, long long n, long long in_stride,
     }
     if (nwarps == 1) {
         if (i < n) Alg::store(out_prefix, out_stride, i, mine);
-        if (totals && threadIdx.x == nin - 1) Alg::store(totals, t_stride, blockIdx.x, mine);
+        if (totals && threadIdx.x == nin - 1) Alg::store(totals, t_stride, group, mine);
         return;
     }
     real* mp = reinterpret_cast<real*>(&mine);
@@ -78,7 +95,34 @@ scan_level_kernel(const real* in, long long n, long long in_stride,
         mine = r;
     }
     if (i < n) Alg::store(out_prefix, out_stride, i, mine);
-    if (totals && threadIdx.x == nin - 1) Alg::store(totals, t_stride, blockIdx.x, mine);
+    if (totals && threadIdx.x == nin - 1) Alg::store(totals, t_stride, group, mine);
+}
+
+template <class Alg>
+__global__ void __launch_bounds__(kScanGroup)
+scan_level_kernel(const real* in, long long n, long long in_stride,
+                  real* out_prefix, long long out_stride,
+                  real* totals, long long t_stride) {
+    scan_group<Alg>(in, n, in_stride, out_prefix, out_stride, totals, t_stride, blockIdx.x);
+}
+
+// The last two levels in ONE launch: every CTA scans its group of level l (within-group prefixes stay as they are) and
+// leaves its total in level l + 1; the CTA that arrives last (ticket) scans those totals in place.  The consumer applies
+// group prefix, within-group prefix and within-warp prefix one after the other (apply_prefix), so no pass goes back down.
+// `ticket` must be zero at launch (the producer kernel clears it); it is left at zero.
+template <class Alg>
+__global__ void __launch_bounds__(kScanGroup)
+scan_last_levels_kernel(real* level, long long n, real* top, long long n_top, unsigned int* ticket) {
+    __shared__ unsigned int last;
+    scan_group<Alg>(level, n, n, level, n, top, n_top, blockIdx.x);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    scan_group<Alg, true>(top, n_top, n_top, top, n_top, nullptr, 0, 0);
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // prefix[i] (within-group inclusive) <- combine(group_prefix[group(i) - 1], prefix[i]) : after this
@@ -104,6 +148,7 @@ struct ScanPlan {
     long long count[kMaxLevels];
     real* prefix[kMaxLevels];  // inclusive prefixes of level l (count[l] elements)
     real* input0 = nullptr;    // level-0 input aggregates
+    unsigned int* ticket = nullptr;  // arrival counter of the one-launch upper levels (scan_last_levels_kernel), or null
 };
 
 inline long long scan_plan_doubles(long long n0, int elem) {
@@ -195,8 +240,16 @@ inline ScanPlan make_scan_plan_warp(real* input0, real* prefix0, real* upper, lo
 }
 
 // after the producer's warp_prescan: prefix[1] <- inclusive prefixes of the warp totals
+// levels == 3 (the wave-sized plans): ONE launch, and the consumer gets the three parts (upper_parts)
 template <class Alg>
 inline cudaError_t run_scan_upper(const ScanPlan& p, cudaStream_t st) {
+    unsigned int* ticket = p.ticket;
+    if (p.levels == 3 && ticket) {
+        const unsigned grid = (unsigned)p.count[2];
+        BN_LAUNCH("scan_level", st,
+                  scan_last_levels_kernel<Alg><<<grid, kScanGroup, 0, st>>>(p.prefix[1], p.count[1], p.prefix[2], p.count[2], ticket));
+        return cudaGetLastError();
+    }
     for (int l = 1; l < p.levels; ++l) {
         const long long n = p.count[l];
         const unsigned grid = (unsigned)((n + kScanGroup - 1) / kScanGroup);
@@ -212,6 +265,25 @@ inline cudaError_t run_scan_upper(const ScanPlan& p, cudaStream_t st) {
                   scan_down_kernel<Alg><<<grid, kScanGroup, 0, st>>>(p.prefix[l], n, n, p.prefix[l + 1], p.count[l + 1]));
     }
     return cudaGetLastError();
+}
+
+// The upper parts of a prefix: warp = inclusive prefixes of the warp totals -- over the whole level (group == null) or
+// within groups of `gsize` warps, in which case group = inclusive prefixes of the group totals.  All null: prefix0
+// already holds the global prefixes.
+struct PrefixParts {
+    const real* warp = nullptr;
+    long long n_warp = 0;
+    const real* group = nullptr;
+    long long n_group = 0;
+    int gsize = 0;
+};
+
+// what the consumer of a plan scanned by run_scan_upper applies (fused = the plan went through the one-launch path)
+inline PrefixParts upper_parts(const ScanPlan& p) {
+    PrefixParts u;
+    if (p.levels > 1) { u.warp = p.prefix[1]; u.n_warp = p.count[1]; }
+    if (p.levels == 3 && p.ticket) { u.group = p.prefix[2]; u.n_group = p.count[2]; u.gsize = kScanGroup; }
+    return u;
 }
 
 #ifdef __CUDACC__
@@ -230,18 +302,23 @@ __device__ __forceinline__ void warp_prescan(typename Alg::Elem& mine, long long
     }
     if (i < n) Alg::store(p.prefix[0], n, i, mine);
     if (lane == 31 && p.levels > 1) Alg::store(p.prefix[1], p.count[1], i >> 5, mine);
+    if (i == 0 && p.ticket) *p.ticket = 0u;  // the upper levels run after this kernel and count their CTAs from zero
 }
 #endif
 
-// state after the elements 0..q of the scan order, from the incoming state s: prefix0 = within-warp inclusive prefixes,
-// wprefix = inclusive prefixes of the warp totals (null: prefix0 already holds the global prefixes)
+// state after the elements 0..q of the scan order, from the incoming state s (prefix0 = within-warp inclusive prefixes)
 template <class Alg>
-BN_DEV void apply_prefix2(const real* prefix0, long long n0, const real* wprefix, long long n1, long long q,
-                          typename Alg::State& s) {
+BN_DEV void apply_prefix(const real* prefix0, long long n0, const PrefixParts& up, long long q, typename Alg::State& s) {
     typename Alg::Elem e;
     typename Alg::State t;
-    if (wprefix && (q >> 5) > 0) {
-        Alg::load(wprefix, n1, (q >> 5) - 1, e);
+    if (up.warp && (q >> 5) > 0) {
+        const long long w1 = (q >> 5) - 1;  // the last whole warp below q
+        if (up.group && w1 / up.gsize > 0) {
+            Alg::load(up.group, up.n_group, w1 / up.gsize - 1, e);
+            Alg::apply(e, s, t);
+            s = t;
+        }
+        Alg::load(up.warp, up.n_warp, w1, e);
         Alg::apply(e, s, t);
         s = t;
     }

@@ -28,21 +28,50 @@ static void host_scan(const double* in, long long n, double* prefix) {
     }
 }
 
-// the scan as the fused iteration does it (scan.cuh: warp_prescan + run_scan_upper): inclusive prefixes inside groups of
-// 32 consecutive elements, and inclusive prefixes of the group totals
+// the scan as the fused iteration does it (scan.cuh: warp_prescan + scan_last_levels_kernel): inclusive prefixes inside
+// groups of 32 consecutive elements, inclusive prefixes of the warp totals inside groups of kEmuGroup warps, and inclusive
+// prefixes of the group totals (the device groups 288 warps; a small group here reaches all three parts at test sizes)
+constexpr int kEmuGroup = 3;
+struct HostPrefix {
+    std::vector<double> warp, group;
+    long long nw = 0, ng = 0;
+    PrefixParts parts() const {
+        PrefixParts u;
+        if (nw > 1) { u.warp = warp.data(); u.n_warp = nw; }
+        if (ng > 1) { u.group = group.data(); u.n_group = ng; u.gsize = kEmuGroup; }
+        return u;
+    }
+    // (array, count) holding the grand total as its last element
+    template <class F> auto total(const double* prefix0, long long n, F f) const {
+        if (ng > 1) return f(group.data(), ng);
+        if (nw > 1) return f(warp.data(), nw);
+        return f(prefix0, n);
+    }
+};
 template <class Alg>
-static void host_warp_scan(const double* in, long long n, double* prefix0, std::vector<double>& wprefix) {
-    const long long nw = (n + 31) / 32;
-    wprefix.assign((size_t)nw * Alg::kElem, 0.0);
-    typename Alg::Elem acc, e, r, wacc;
+static void host_warp_scan(const double* in, long long n, double* prefix0, HostPrefix& hp) {
+    hp.nw = (n + 31) / 32;
+    hp.ng = (hp.nw + kEmuGroup - 1) / kEmuGroup;
+    hp.warp.assign((size_t)hp.nw * Alg::kElem, 0.0);
+    hp.group.assign((size_t)hp.ng * Alg::kElem, 0.0);
+    typename Alg::Elem acc, e, r, wacc, gacc;
     for (long long i = 0; i < n; ++i) {
         Alg::load(in, n, i, e);
         if ((i & 31) == 0) acc = e; else { Alg::combine(acc, e, r); acc = r; }
         Alg::store(prefix0, n, i, acc);
         if ((i & 31) == 31 || i == n - 1) {
-            if ((i >> 5) == 0) wacc = acc; else { Alg::combine(wacc, acc, r); wacc = r; }
-            Alg::store(wprefix.data(), nw, i >> 5, wacc);
+            const long long w = i >> 5;
+            if (w % kEmuGroup == 0) wacc = acc; else { Alg::combine(wacc, acc, r); wacc = r; }
+            Alg::store(hp.warp.data(), hp.nw, w, wacc);
+            if (w % kEmuGroup == kEmuGroup - 1 || i == n - 1) {
+                const long long g = w / kEmuGroup;
+                if (g == 0) gacc = wacc; else { Alg::combine(gacc, wacc, r); gacc = r; }
+                Alg::store(hp.group.data(), hp.ng, g, gacc);
+            }
         }
+    }
+    if (hp.ng <= 1) {  // a single group: its within-group prefixes are the global ones (the device's two-level plans)
+        hp.ng = 0;
     }
 }
 
@@ -248,7 +277,7 @@ static void host_from_tiled(long long n, int L, long long nc, const std::vector<
 
 template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
 static void emu_it_sweep(const G& g, const ItIO& io, const ItSiteArgs& sa, const Cub1& cub, int L, long long nc,
-                         const double* spre, const double* sinit, const double* fs, const double* swp) {
+                         const double* spre, const double* sinit, const double* fs, const PrefixParts& swp) {
     const double* tab = TAB ? probit_table_host().data() : nullptr;
     for (long long c = 0; c < nc; ++c) {
         Epi<LIK, METHOD, TAB> epi(io, sa, &cub, tab);
@@ -273,9 +302,10 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
     for (int r = 0; r <= world; ++r) off[r] = N * r / world;
     struct Rank {
         long long n, nc;
-        std::vector<double> agg, fpre, sel, spre, fs, s0, sinit, dt_t, y_t, sy_t, sR_t, pm_t, pc_t, p1, p2, ell1, fwp, swp;
-        const double* fw() const { return nc > 32 ? fwp.data() : nullptr; }
-        const double* sw() const { return nc > 32 ? swp.data() : nullptr; }
+        std::vector<double> agg, fpre, sel, spre, fs, s0, sinit, dt_t, y_t, sy_t, sR_t, pm_t, pc_t, p1, p2, ell1;
+        HostPrefix fhp, shp;
+        PrefixParts fw() const { return fhp.parts(); }
+        PrefixParts sw() const { return shp.parts(); }
         std::vector<unsigned char> mk_t;
         std::vector<int> jst;
         ItIO io;
@@ -333,9 +363,11 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         } else {
             for (long long c = 0; c < q.nc; ++c) it_reduce_chunk(g, q.io, L, q.nc, r == 0, q.agg.data(), c);
         }
-        host_warp_scan<FA>(q.agg.data(), q.nc, q.fpre.data(), q.fwp);
-        if (q.nc > 32) export_carry_body<FA>(q.fwp.data(), (q.nc + 31) / 32, fcar.data() + (size_t)r * FA::kCarry);
-        else export_carry_body<FA>(q.fpre.data(), q.nc, fcar.data() + (size_t)r * FA::kCarry);
+        host_warp_scan<FA>(q.agg.data(), q.nc, q.fpre.data(), q.fhp);
+        q.fhp.total(q.fpre.data(), q.nc, [&](const double* a, long long n) {
+            export_carry_body<FA>(a, n, fcar.data() + (size_t)r * FA::kCarry);
+            return 0;
+        });
     }
     double total = 0.0;
     for (int r = 0; r < world; ++r) {
@@ -350,9 +382,11 @@ static int emu_it(const bn_kernel_spec* k, long long N, int L, int world, const 
         if (jstar_mean) { double a = 0; for (int v : q.jst) a += v; *jstar_mean += a / (double)q.nc / world; }
         for (long long c = 0; c < q.nc; ++c)
             up_selem_chunk<G>(q.n, L, q.nc, r != 0, q.agg.data(), q.s0.data(), q.fs.data(), q.sel.data(), c);
-        host_warp_scan<SA>(q.sel.data(), q.nc, q.spre.data(), q.swp);
-        if (q.nc > 32) up_export_scarry<d>(q.swp.data(), (q.nc + 31) / 32, r == world - 1, q.n, L, q.fs.data(), scar.data() + (size_t)r * SA::kCarry);
-        else up_export_scarry<d>(q.spre.data(), q.nc, r == world - 1, q.n, L, q.fs.data(), scar.data() + (size_t)r * SA::kCarry);
+        host_warp_scan<SA>(q.sel.data(), q.nc, q.spre.data(), q.shp);
+        q.shp.total(q.spre.data(), q.nc, [&](const double* a, long long n) {
+            up_export_scarry<d>(a, n, r == world - 1, q.n, L, q.fs.data(), scar.data() + (size_t)r * SA::kCarry);
+            return 0;
+        });
     }
     if (ell) *ell = total;
     double s1 = 0.0, s2 = 0.0;
