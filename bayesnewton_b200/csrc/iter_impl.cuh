@@ -429,6 +429,7 @@ it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     if ((c & ~31LL) >= nchunks) return;
     if (c < nchunks) it_reduce_chunk(g, io, L, nchunks, is_first, agg, c);
+    if (c == 0 && plan.ticket) plan.ticket[2] = 0u;  // the arrival counter of this pass's sums (it_sum_kernel)
     it_prescan_tail<FilterAlg<G::d>>(agg, nchunks, c, plan);
 }
 
@@ -469,15 +470,19 @@ it_reduce_spec_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real
         jst[c] = jstar;
         if (WANT_ELL) ell_partials[c] = sr.ell;
     }
+    if (c == 0 && plan.ticket) plan.ticket[2] = 0u;
     it_prescan_tail<FilterAlg<G::d>>(agg, nchunks, c, plan);
 }
 
-// Fixed-order sums of the per-chunk partials (run-to-run bit-stable), accumulated in fp64 whatever `real` is, in two
-// small launches: kSumCtas CTAs reduce a fixed slice each, one warp adds the CTA partials in index order.
+// Fixed-order sums of the per-chunk partials (run-to-run bit-stable), accumulated in fp64 whatever `real` is, in ONE
+// launch: kSumCtas CTAs reduce a fixed slice each; the CTA that arrives last (ticket, zero at launch and left at zero) adds
+// the CTA partials in index order.
 //   two = 0: out[0] = sum a (+ sum b when b is given)        two = 1: out[0] = sum a, out[1] = sum b
 constexpr int kSumCtas = 74;
-static __global__ void __launch_bounds__(256) it_sum_stage1_kernel(const real* a, const real* b, long long n, double* scratch) {
+static __global__ void __launch_bounds__(256) it_sum_kernel(const real* a, const real* b, long long n, real* out, int two,
+                                                            double* scratch, unsigned int* ticket) {
     __shared__ double sh[2][256];
+    __shared__ unsigned int last;
     const long long per = (n + kSumCtas - 1) / kSumCtas, lo = blockIdx.x * per, hi = (lo + per < n) ? lo + per : n;
     double sa = 0.0, sb = 0.0;
     for (long long i = lo + threadIdx.x; i < hi; i += 256) {
@@ -497,13 +502,16 @@ static __global__ void __launch_bounds__(256) it_sum_stage1_kernel(const real* a
     if (threadIdx.x == 0) {
         scratch[blockIdx.x] = sh[0][0];
         scratch[kSumCtas + blockIdx.x] = sh[1][0];
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
-}
-static __global__ void __launch_bounds__(32) it_sum_stage2_kernel(const double* scratch, real* out, int two) {
-    double sa = 0.0, sb = 0.0;
+    __syncthreads();
+    if (!last || threadIdx.x >= 32) return;
+    __threadfence();
+    sa = sb = 0.0;
     for (int i = threadIdx.x; i < kSumCtas; i += 32) {
-        sa += scratch[i];
-        sb += scratch[kSumCtas + i];
+        sa += __ldcg(scratch + i);
+        sb += __ldcg(scratch + kSumCtas + i);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -513,11 +521,12 @@ static __global__ void __launch_bounds__(32) it_sum_stage2_kernel(const double* 
     if (threadIdx.x == 0) {
         if (two) { out[0] = real(sa); out[1] = real(sb); }
         else out[0] = real(sa + sb);
+        *ticket = 0u;
     }
 }
-inline cudaError_t it_sum(const real* a, const real* b, long long n, real* out, int two, double* scratch, cudaStream_t st) {
-    it_sum_stage1_kernel<<<kSumCtas, 256, 0, st>>>(a, b, n, scratch);
-    it_sum_stage2_kernel<<<1, 32, 0, st>>>(scratch, out, two);
+inline cudaError_t it_sum(const real* a, const real* b, long long n, real* out, int two, double* scratch, unsigned int* ticket,
+                          cudaStream_t st) {
+    it_sum_kernel<<<kSumCtas, 256, 0, st>>>(a, b, n, out, two, scratch, ticket);
     return cudaGetLastError();
 }
 
@@ -683,6 +692,7 @@ inline int it_run(const ItCall& c) {
     // arrival counters of the one-launch upper scan levels (cleared by the kernels that produce the elements)
     w.fplan.ticket = (unsigned int*)(sum_scratch + 2 * kSumCtas);
     w.splan.ticket = w.fplan.ticket + 1;
+    unsigned int* sum_ticket = w.fplan.ticket + 2;  // arrival counter of the sums (cleared by the reduce kernels as well)
     const PrefixParts fwp = upper_parts(w.fplan), swp = upper_parts(w.splan);
     const unsigned grid = (unsigned)((cp.nchunks + kUpThreads - 1) / kUpThreads);
     const int is_first = (c.rank == 0), is_last = (c.rank == c.world - 1);
@@ -719,7 +729,7 @@ inline int it_run(const ItCall& c) {
                                            g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], fwp, w.s0, w.fs, w.partials,
                                            spec ? jst : nullptr)));
             BN_CUDA(cudaGetLastError());
-            BN_LAUNCH("sum", st, (it_sum(w.partials, spec ? ell1 : nullptr, cp.nchunks, c.ell, 0, sum_scratch, st)));
+            BN_LAUNCH("sum", st, (it_sum(w.partials, spec ? ell1 : nullptr, cp.nchunks, c.ell, 0, sum_scratch, sum_ticket, st)));
         } else {
             BN_LAUNCH("it_filter", st, (it_filter_kernel<G, false><<<grid, kUpThreads, 0, st>>>(
                                            g, io, cp.L, cp.nchunks, is_first, w.fplan.prefix[0], fwp, w.s0, w.fs, nullptr,
@@ -754,7 +764,7 @@ inline int it_run(const ItCall& c) {
                                           : it_launch_site_sweep<G, EpiEnergy>(c, g, cp, w, sa);
             if (rc) return rc;
             if (c.sums) {
-                BN_LAUNCH("sum", st, (it_sum(sa.part1, sa.part2, cp.nchunks, c.sums, 1, sum_scratch, st)));
+                BN_LAUNCH("sum", st, (it_sum(sa.part1, sa.part2, cp.nchunks, c.sums, 1, sum_scratch, sum_ticket, st)));
                 BN_CUDA(cudaGetLastError());
             }
         }
