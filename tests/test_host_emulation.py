@@ -157,3 +157,59 @@ def test_site_update_heteroscedastic(emu, method, lr, power, psd):
     for got, ref in [(e['mean'], mean), (e['jac'], jac), (e['hess'], hess), (e['nat1'], o[0]), (e['nat2'], o[1]),
                      (e['site_mean'], o[2]), (e['site_cov'], o[3])]:
         assert rel_err(got, ref) < 1e-8  # the EP scale factor inverts ill-conditioned 2x2s: 1e-13 typical
+
+
+# ---------------------------------------------------------------------------- fused iteration on tiled state (iter_impl.cuh)
+ITER_KERNELS = {'m12': (1, lambda: ssm.Matern12(0.8, 1.7), 0.8, 1.7), 'm32': (2, lambda: ssm.Matern32(1.1, 0.6), 1.1, 0.6),
+                'm52': (3, lambda: ssm.Matern52(1.3, 0.9), 1.3, 0.9), 'm72': (4, lambda: ssm.Matern72(0.7, 1.4), 0.7, 1.4)}
+ITER_LIKS = {'probit': (lambda: sites.Bernoulli('probit'), 0.0), 'logit': (lambda: sites.Bernoulli('logit'), 0.0),
+             'gaussian': (lambda: sites.Gaussian(0.3), 0.3), 'poisson': (lambda: sites.Poisson(1.0), 1.0)}
+
+
+def _iter_problem(N, likname, seed):
+    rng = np.random.default_rng(seed)
+    dt = np.concatenate([[0.0], 0.1 + 0.2 * rng.random(N - 1)]) if N > 1 else np.zeros(1)
+    y = site_observations(likname, rng, N)
+    if N > 20:
+        y[::17] = np.nan
+    sy = 0.3 * rng.standard_normal(N)
+    sR = 0.5 + rng.random(N)
+    return dt, y, sy, sR
+
+
+def _oracle_pass(k, lik, method, dt, y, sy, sR, lr, power=1.0):
+    """update_posterior, then the site update of the scheme and the two energy sums, with the oracle"""
+    N = dt.shape[0]
+    mask = np.isnan(y).reshape(N, 1, 1)
+    ell, (fm, fP) = kalman.kalman_filter(dt, k, sy.reshape(N, 1, 1), sR.reshape(N, 1, 1), mask)
+    pm, pc, _ = kalman.rauch_tung_striebel_smoother(np.concatenate([dt[1:], [0.0]]), k, fm, fP)
+    n2 = 1.0 / sR.reshape(N, 1, 1)
+    n1 = sy.reshape(N, 1, 1) * n2
+    mean, jac, hess = sites.site_statistics(method, lik, y[:, None], pm, pc, n1, n2, power=power, mask_pseudo_y=np.isnan(y)[:, None])
+    new = sites.damped_site_update(n1, n2, mean, jac, hess, lr)
+    return ell, pm.reshape(-1), pc.reshape(-1), new[2].reshape(-1), new[3].reshape(-1), (new[4] * N, new[5] * N)
+
+
+@pytest.mark.parametrize('kname', sorted(ITER_KERNELS))
+@pytest.mark.parametrize('likname,method', [('probit', 'vi'), ('probit', 'newton'), ('logit', 'vi'), ('gaussian', 'vi'), ('poisson', 'vi')])
+@pytest.mark.parametrize('N,L,world,spec', [(1, 8, 1, False), (7, 8, 1, False), (203, 8, 3, False), (1500, 8, 1, False),
+                                            (2500, 256, 2, True), (4000, 8, 1, True)])
+def test_fused_iteration_passes(emu, kname, likname, method, N, L, world, spec):
+    """csrc/iter_impl.cuh chunk bodies on the host: the SITES pass (filter, smoother, site update in the epilogue), the
+    PLAIN / ENERGY passes (marginals, log-likelihood), time shards, the speculative phase 1, and the three-part prefix of
+    the scan (the emulation groups 3 warps, so 4000 steps in 8-step chunks reach all three parts)"""
+    fam, mk, var, ls = ITER_KERNELS[kname]
+    lik, lp = ITER_LIKS[likname][0](), ITER_LIKS[likname][1]
+    dt, y, sy, sR = _iter_problem(N, likname, seed=N + L)
+    sp = _emu.spec(fam, [var], [ls])
+    cub = sites.gauss_hermite(1, 20)
+    mask = np.isnan(y).astype(np.uint8) if np.isnan(y).any() else None
+    ell0, pm0, pc0, nsy, nsR, diffs = _oracle_pass(mk(), lik, method, dt, y, sy, sR, lr=0.6)
+    out = _emu.iter_pass(emu, sp, dt, y, sy, sR, 0, method, likname, lp, cub, mask, L=L, world=world, spec=spec)     # PLAIN
+    assert rel_err(out['post_mean'], pm0) < TOL and rel_err(out['post_cov'], pc0) < TOL
+    assert abs(out['ell'] - ell0) <= TOL * abs(ell0)
+    out = _emu.iter_pass(emu, sp, dt, y, sy, sR, 1, method, likname, lp, cub, mask, lr=0.6, L=L, world=world, spec=spec)  # SITES
+    assert rel_err(out['site_mean'], nsy) < 10 * TOL and rel_err(1.0 / out['site_cov'], 1.0 / nsR) < TOL
+    assert np.allclose(out['sums'], diffs, rtol=1e-8)
+    if spec and L >= 256 and kname in ('m32', 'm52'):  # (the other two forget their start more slowly than 256 steps)
+        assert out['jstar_mean'] < 0.75 * L   # the chunks did switch to the plain filter well before their end
