@@ -198,7 +198,7 @@ class MarkovGaussianProcess:
 
     def _energy_key(self, cubature):
         return (self.pseudo_likelihood.version, self._hyper_key(), float(self.likelihood.lik_param), float(self.likelihood.lik_param2),
-                fused.cubature_key(cubature), self.method)
+                fused.cubature_key(cubature), self.method, float(getattr(self, 'power', 1.0)))
 
     def _hyper_key(self):
         spec = self.kernel.spec() if hasattr(self.kernel, 'spec') else None

@@ -127,9 +127,12 @@ static int it_make_call(const bn_kernel_spec* k, const bn_iter_args* a, int mode
     c.want_ell = a->want_ell;
     if (back && mode != BN_ITER_PLAIN) {
         BN_REQUIRE(a->y_t != nullptr, "y_t is null");
-        BN_REQUIRE(a->method == BN_METHOD_VI || a->method == BN_METHOD_NEWTON, "the fused epilogues cover VI and Newton, got method %d", a->method);
+        BN_REQUIRE(a->method == BN_METHOD_VI || a->method == BN_METHOD_NEWTON || a->method == BN_METHOD_EP,
+                   "the fused epilogues cover VI, Newton and EP, got method %d", a->method);
+        if (a->method == BN_METHOD_EP) BN_REQUIRE(a->power > 0.0, "EP power must be positive");
         const bool closed = a->method == BN_METHOD_NEWTON ||
-                            (a->method == BN_METHOD_VI && (a->likelihood == BN_LIK_GAUSSIAN || a->likelihood == BN_LIK_POISSON_EXP));
+                            (a->method == BN_METHOD_VI && (a->likelihood == BN_LIK_GAUSSIAN || a->likelihood == BN_LIK_POISSON_EXP)) ||
+                            (a->method == BN_METHOD_EP && a->likelihood == BN_LIK_GAUSSIAN);
         if (!closed) BN_REQUIRE(a->Q > 0 && a->Q <= kMaxQ1 && a->cub_x_host && a->cub_w_host, "cubature rule missing or larger than %d points", kMaxQ1);
         if (a->likelihood == BN_LIK_GAUSSIAN || a->likelihood == BN_LIK_POISSON_EXP) BN_REQUIRE(a->lik_param > 0.0, "likelihood parameter must be positive");
         const bool has = a->Q > 0 && a->Q <= kMaxQ1 && a->cub_x_host && a->cub_w_host;

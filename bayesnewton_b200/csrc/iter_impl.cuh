@@ -377,9 +377,18 @@ struct EpiEnergy {
             io.pm[ti] = m;
             io.pc[ti] = v;
         }
-        const SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB, BN_IT_TAB_UNROLL>(lik, yq, m, v, 0.0, 0.0, a.power, *cub);
-        if (!isnan(s.val)) accV += s.val;  // nansum (inference.py:218)
-        accX += gaussian_ell_step<1>(&oy, &m, &v, &oR, io.mask ? &mk : nullptr, 0);
+        if constexpr (METHOD == BN_METHOD_EP) {
+            // EP energy (inference.py:286-325): log Z of the tilted distribution at the cavity, and the same for the site
+            // (basemodels.py:247-262) -- the cavity needs the site's natural parameters
+            const real o2 = 1.0 / oR, o1 = oy * o2;
+            const SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB, BN_IT_TAB_UNROLL>(lik, yq, m, v, o1, o2, a.power, *cub);
+            if (!isnan(s.val)) accV += s.val;
+            accX += ep_pseudo_step<1>(a.power, 1, &oy, &oR, &m, &v, &o1, &o2, io.mask ? &mk : nullptr, 0);
+        } else {
+            const SiteStats1 s = site_stats_1<LIK, METHOD, false, TAB, BN_IT_TAB_UNROLL>(lik, yq, m, v, 0.0, 0.0, a.power, *cub);
+            if (!isnan(s.val)) accV += s.val;  // nansum (inference.py:218)
+            accX += gaussian_ell_step<1>(&oy, &m, &v, &oR, io.mask ? &mk : nullptr, 0);
+        }
     }
     BN_DEV void finish(long long c) {
         a.part1[c] = accV;
@@ -627,11 +636,11 @@ inline size_t it_ws_doubles(long long N) {
 constexpr int kSpecMinChunk = 160;  // measured break-even: on at L = 165 (-2.3 % per iteration), off at L = 132 (+1 %)
 
 // fused (likelihood, method) pairs of the site / energy epilogues
-#define BN_FOR_EACH_ITER_SITE(X)                                                       \
-    X(BN_LIK_GAUSSIAN, BN_METHOD_VI) X(BN_LIK_GAUSSIAN, BN_METHOD_NEWTON)               \
-    X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_VI) X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_NEWTON) \
-    X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_VI) X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_NEWTON) \
-    X(BN_LIK_POISSON_EXP, BN_METHOD_VI) X(BN_LIK_POISSON_EXP, BN_METHOD_NEWTON)
+#define BN_FOR_EACH_ITER_SITE(X)                                                                                       \
+    X(BN_LIK_GAUSSIAN, BN_METHOD_VI) X(BN_LIK_GAUSSIAN, BN_METHOD_NEWTON) X(BN_LIK_GAUSSIAN, BN_METHOD_EP)               \
+    X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_VI) X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_NEWTON) X(BN_LIK_BERNOULLI_PROBIT, BN_METHOD_EP) \
+    X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_VI) X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_NEWTON) X(BN_LIK_BERNOULLI_LOGIT, BN_METHOD_EP) \
+    X(BN_LIK_POISSON_EXP, BN_METHOD_VI) X(BN_LIK_POISSON_EXP, BN_METHOD_NEWTON) X(BN_LIK_POISSON_EXP, BN_METHOD_EP)
 
 template <class G, template <int, int, bool> class Epi>
 inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp, const UpWs& w, const ItSiteArgs& sa) {
@@ -640,7 +649,7 @@ inline int it_launch_site_sweep(const ItCall& c, const G& g, const ChunkPlan& cp
     const PrefixParts swp = upper_parts(w.splan);
 #define X(LK, M)                                                                                                      \
     if (c.likelihood == LK && c.method == M) {                                                                         \
-        if constexpr (LK == BN_LIK_BERNOULLI_PROBIT && M == BN_METHOD_VI) {                                            \
+        if constexpr (LK == BN_LIK_BERNOULLI_PROBIT && (M == BN_METHOD_VI || M == BN_METHOD_EP)) {                     \
             if (c.use_table) {                                                                                         \
                 auto kfn = it_smooth_site_kernel<G, Epi, LK, M, true>;                                                 \
                 const size_t smem = kItTabBytes;                                                                       \

@@ -430,6 +430,63 @@ BN_DEV real gaussian_ell_step(const real* py, const real* pm, const real* pV, co
     return ml - 0.5 * tr;
 }
 
+// log N(pseudo_y | cav_mean, pseudo_var/power + cav_cov) [+ pep_constant]  (basemodels.py:247-262)
+template <int D>
+BN_DEV real ep_pseudo_step(real power, int with_const, const real* py, const real* pR, const real* pm,
+                             const real* pV, const real* n1, const real* n2, const unsigned char* mask,
+                             long long n) {
+    real cm[D], cC[symn(D)];
+    {
+        real Vj[symn(D)], pn2[symn(D)], t[symn(D)];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) Vj[sidx(i, j)] = pV[n * D * D + i * D + j] + (i == j ? 1e-8 : 0.0);
+        sym_inverse<D>(Vj, pn2);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) t[sidx(i, j)] = pn2[sidx(i, j)] - power * n2[n * D * D + i * D + j];
+        sym_inverse<D>(t, cC);
+        real r[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            real s = -power * n1[n * D + i];
+#pragma unroll
+            for (int j = 0; j < D; ++j) s = fma(pn2[sidx(i, j)], pm[n * D + j], s);
+            r[i] = s;
+        }
+        symvec<D>(cC, r, cm);
+    }
+    real S[symn(D)], e[D];
+    unsigned char mk[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        mk[i] = mask ? mask[n * D + i] : 0;
+        e[i] = py[n * D + i] - cm[i];
+#pragma unroll
+        for (int j = 0; j <= i; ++j) S[sidx(i, j)] = pR[n * D * D + i * D + j] / power + cC[sidx(i, j)];
+    }
+    real val = mvn_logpdf_masked<D>(S, e, mask ? mk : nullptr);
+    if (with_const) {  // pep_constant (utils.py:431-445)
+        real Rr[symn(D)];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) Rr[sidx(i, j)] = pR[n * D * D + i * D + j];
+        chol<D>(Rr);
+        real dim = D, ld = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            real l = log(fabs(Rr[sidx(i, i)]));
+            if (mk[i]) { l = 0.0; dim -= 1.0; }
+            ld += l;
+        }
+        val += 0.5 * dim * ((1.0 - power) * kLog2Pi - log(power)) + 0.5 * (1.0 - power) * 2.0 * ld;
+    }
+    return val;
+}
+
 // 1-D rule from host arrays (cubature.py:76-84 builds them with numpy on the host as well)
 inline void make_cub1(int Q, const double* x, const double* w, Cub1& c) {
     c.Q = Q;

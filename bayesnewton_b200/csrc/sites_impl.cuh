@@ -240,63 +240,6 @@ BN_DEV double expected_density_step(const bn_site_args& a, const SiteCtx& sc, lo
         return s.val;
     }
 }
-// log N(pseudo_y | cav_mean, pseudo_var/power + cav_cov) [+ pep_constant]  (basemodels.py:247-262)
-template <int D>
-BN_DEV double ep_pseudo_step(double power, int with_const, const double* py, const double* pR, const double* pm,
-                             const double* pV, const double* n1, const double* n2, const unsigned char* mask,
-                             long long n) {
-    double cm[D], cC[symn(D)];
-    {
-        double Vj[symn(D)], pn2[symn(D)], t[symn(D)];
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) Vj[sidx(i, j)] = pV[n * D * D + i * D + j] + (i == j ? 1e-8 : 0.0);
-        sym_inverse<D>(Vj, pn2);
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) t[sidx(i, j)] = pn2[sidx(i, j)] - power * n2[n * D * D + i * D + j];
-        sym_inverse<D>(t, cC);
-        double r[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            double s = -power * n1[n * D + i];
-#pragma unroll
-            for (int j = 0; j < D; ++j) s = fma(pn2[sidx(i, j)], pm[n * D + j], s);
-            r[i] = s;
-        }
-        symvec<D>(cC, r, cm);
-    }
-    double S[symn(D)], e[D];
-    unsigned char mk[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        mk[i] = mask ? mask[n * D + i] : 0;
-        e[i] = py[n * D + i] - cm[i];
-#pragma unroll
-        for (int j = 0; j <= i; ++j) S[sidx(i, j)] = pR[n * D * D + i * D + j] / power + cC[sidx(i, j)];
-    }
-    double val = mvn_logpdf_masked<D>(S, e, mask ? mk : nullptr);
-    if (with_const) {  // pep_constant (utils.py:431-445)
-        double Rr[symn(D)];
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) Rr[sidx(i, j)] = pR[n * D * D + i * D + j];
-        chol<D>(Rr);
-        double dim = D, ld = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            double l = log(fabs(Rr[sidx(i, i)]));
-            if (mk[i]) { l = 0.0; dim -= 1.0; }
-            ld += l;
-        }
-        val += 0.5 * dim * ((1.0 - power) * kLog2Pi - log(power)) + 0.5 * (1.0 - power) * 2.0 * ld;
-    }
-    return val;
-}
-
 // likelihood-level statistics at (m, v) exactly as given (no cavity / scale factor / ensure_psd):
 // val[N], d1[N,D,1], d2[N,D,D]
 template <int LIK, int METHOD, bool TAB = false>

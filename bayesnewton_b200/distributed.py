@@ -327,6 +327,7 @@ class TimeShardedMarkovGP:
         import os
         from . import fused
         return (os.environ.get('BN_B200_FUSED', '1') != '0' and self.shard.D == 1
+                and self.method in (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON)  # (the sharded energy is VI / Newton)
                 and fused.supported(self.shard.spec, self.likelihood, self.method))
 
     def _fused_state(self):

@@ -22,7 +22,7 @@ from .cubature import host_table
 PLAIN, SITES, ENERGY = 0, 1, 2
 
 SUPPORTED_LIKS = (_lib.BN_LIK_GAUSSIAN, _lib.BN_LIK_BERNOULLI_PROBIT, _lib.BN_LIK_BERNOULLI_LOGIT, _lib.BN_LIK_POISSON_EXP)
-SUPPORTED_METHODS = (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON)
+SUPPORTED_METHODS = (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON, _lib.BN_METHOD_EP)
 
 
 def supported(spec, likelihood, method):
@@ -122,7 +122,9 @@ class FusedShard:
         keep = []
         if likelihood is not None:
             a.method, a.likelihood, a.lik_param = int(method), int(likelihood.lik_id), float(likelihood.lik_param)
-            closed = method == _lib.BN_METHOD_NEWTON or likelihood.lik_id in (_lib.BN_LIK_GAUSSIAN, _lib.BN_LIK_POISSON_EXP)
+            closed = (method == _lib.BN_METHOD_NEWTON
+                      or (method == _lib.BN_METHOD_VI and likelihood.lik_id in (_lib.BN_LIK_GAUSSIAN, _lib.BN_LIK_POISSON_EXP))
+                      or (method == _lib.BN_METHOD_EP and likelihood.lik_id == _lib.BN_LIK_GAUSSIAN))
             if not closed:
                 cx, cw, Q = host_table(cubature, 1)
                 a.Q, a.cub_x_host, a.cub_w_host = Q, cx.ctypes.data, cw.ctypes.data

@@ -161,8 +161,12 @@ class ExpectationPropagation(InferenceMixin):
         return out
 
     def energy(self, batch_ind=None, cubature=None, **kwargs):
-        lel = self.expected_density(cubature)
-        lel_pseudo = self._pseudo_density(self.power, True)
+        cache = getattr(self, '_energy_cache', None)
+        if type(self).method == _lib.BN_METHOD_EP and cache is not None and cache[2] == self._energy_key(cubature):
+            lel, lel_pseudo = cache[0], cache[1]  # summed in the smoother epilogue of the pass that closed inference()
+        else:
+            lel = self.expected_density(cubature)
+            lel_pseudo = self._pseudo_density(self.power, True)
         lZ = self.compute_log_lik()
         return -(lZ + 1. / self.power * (lel - lel_pseudo))
 

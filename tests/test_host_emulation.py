@@ -191,7 +191,8 @@ def _oracle_pass(k, lik, method, dt, y, sy, sR, lr, power=1.0):
 
 
 @pytest.mark.parametrize('kname', sorted(ITER_KERNELS))
-@pytest.mark.parametrize('likname,method', [('probit', 'vi'), ('probit', 'newton'), ('logit', 'vi'), ('gaussian', 'vi'), ('poisson', 'vi')])
+@pytest.mark.parametrize('likname,method', [('probit', 'vi'), ('probit', 'newton'), ('logit', 'vi'), ('gaussian', 'vi'), ('poisson', 'vi'),
+                                            ('probit', 'ep'), ('gaussian', 'ep'), ('poisson', 'ep')])
 @pytest.mark.parametrize('N,L,world,spec', [(1, 8, 1, False), (7, 8, 1, False), (203, 8, 3, False), (1500, 8, 1, False),
                                             (2500, 256, 2, True), (4000, 8, 1, True)])
 def test_fused_iteration_passes(emu, kname, likname, method, N, L, world, spec):
@@ -204,12 +205,22 @@ def test_fused_iteration_passes(emu, kname, likname, method, N, L, world, spec):
     sp = _emu.spec(fam, [var], [ls])
     cub = sites.gauss_hermite(1, 20)
     mask = np.isnan(y).astype(np.uint8) if np.isnan(y).any() else None
-    ell0, pm0, pc0, nsy, nsR, diffs = _oracle_pass(mk(), lik, method, dt, y, sy, sR, lr=0.6)
+    power = 0.5 if method == 'ep' else 1.0
+    ell0, pm0, pc0, nsy, nsR, diffs = _oracle_pass(mk(), lik, method, dt, y, sy, sR, lr=0.6, power=power)
     out = _emu.iter_pass(emu, sp, dt, y, sy, sR, 0, method, likname, lp, cub, mask, L=L, world=world, spec=spec)     # PLAIN
     assert rel_err(out['post_mean'], pm0) < TOL and rel_err(out['post_cov'], pc0) < TOL
     assert abs(out['ell'] - ell0) <= TOL * abs(ell0)
-    out = _emu.iter_pass(emu, sp, dt, y, sy, sR, 1, method, likname, lp, cub, mask, lr=0.6, L=L, world=world, spec=spec)  # SITES
+    out = _emu.iter_pass(emu, sp, dt, y, sy, sR, 1, method, likname, lp, cub, mask, lr=0.6, power=power, L=L, world=world,
+                         spec=spec)  # SITES
     assert rel_err(out['site_mean'], nsy) < 10 * TOL and rel_err(1.0 / out['site_cov'], 1.0 / nsR) < TOL
     assert np.allclose(out['sums'], diffs, rtol=1e-8)
+    # ENERGY: the likelihood term of the scheme's energy, summed in the smoother epilogue, against the stand-alone kernel
+    N1 = dt.shape[0]
+    n2 = 1.0 / sR.reshape(N1, 1, 1)
+    n1 = sy.reshape(N1, 1, 1) * n2
+    vals, tot = _emu.expected_density(emu, method, likname, lp, y, pm0.reshape(N1, 1, 1), pc0.reshape(N1, 1, 1), n1, n2, power=power, cub=cub)
+    oe = _emu.iter_pass(emu, sp, dt, y, sy, sR, 2, method, likname, lp, cub, mask, power=power, L=L, world=world, spec=spec)
+    assert abs(oe['sums'][0] - tot) <= 1e-8 * max(1.0, abs(tot))
+    assert rel_err(oe['post_mean'], pm0) < TOL and abs(oe['ell'] - ell0) <= TOL * abs(ell0)
     if spec and L >= 256 and kname in ('m32', 'm52'):  # (the other two forget their start more slowly than 256 steps)
         assert out['jstar_mean'] < 0.75 * L   # the chunks did switch to the plain filter well before their end
