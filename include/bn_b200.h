@@ -454,11 +454,14 @@ int bn_st_predict_state(const bn_kernel_spec* temporal, int M, int64_t N, const 
  *   BN_ITER_SITES   update_posterior(); the site update of inference.py:72-86 for every step, sites rewritten IN PLACE
  *                   sums[0] = sum_n |nat1_new - nat1|, sums[1] = sum_n |nat2_new - nat2| (before damping; the `diff`
  *                   terms of inference.py:78-79 times N)
- *   BN_ITER_ENERGY  update_posterior(); sums[0] = nansum_n likelihood term (VI: E_q[log p]; Newton: log p(y | m)),
+ *   BN_ITER_ENERGY  update_posterior(); sums[0] = nansum_n likelihood term (VI: E_q[log p]; Newton: log p(y | m);
+ *                   EP: log Z_n of the tilted distribution at the cavity, inference.py:297-305),
  *                   sums[1] = sum_n gaussian_expected_log_lik(pseudo_y_n, m_n, v_n, pseudo_var_n)  (utils.py:510-531)
+ *                   (EP: sum_n log Z of the site at the cavity with the power-EP constant, basemodels.py:247-262)
  * ell (nullable) = the filter log-likelihood of the pass = compute_log_lik() (basemodels.py:726-741).
  * Supported: n_components = 1 of any Matern family; likelihood in {Gaussian, Bernoulli probit / logit, Poisson};
- * method VI or Newton.  cub_x / cub_w: HOST arrays (the 1-D rule, Q <= 64; ignored by Newton and the closed forms).
+ * method VI, Newton or EP (power in bn_iter_args).  cub_x / cub_w: HOST arrays (the 1-D rule, Q <= 64; ignored by Newton
+ * and the closed forms).
  * Ranks of a time-sharded run call the three phases with their carries exchanged in between (as bn_up_shard_*). */
 enum { BN_ITER_PLAIN = 0, BN_ITER_SITES = 1, BN_ITER_ENERGY = 2 };
 
