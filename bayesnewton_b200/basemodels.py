@@ -143,7 +143,7 @@ class MarkovGaussianProcess:
     # ---- fused iteration on tiled resident state (fused.py; csrc/iter_impl.cuh)
     def _fused_ok(self):
         """the whole iteration can run as two fused passes: scan form, one in-library Matern component, a single-latent
-        likelihood of the site kernels, VI, Newton or EP, and none of the hooks overridden (spatio-temporal mixins)"""
+        likelihood of the site kernels, VI or Newton (EP with BN_B200_FUSED_EP=1), and none of the hooks overridden (spatio-temporal mixins)"""
         if os.environ.get('BN_B200_FUSED', '1') == '0' or not self.parallel or self.func_dim != 1:
             return False
         if type(self).update_posterior is not MarkovGaussianProcess.update_posterior:
@@ -171,7 +171,7 @@ class MarkovGaussianProcess:
         dtype = {'float64': torch.float64, 'float32': torch.float32}[precision]
         if dtype == torch.float32 and not self._fused_ok():
             raise NotImplementedError('the fp32 build covers the fused iteration (scan form, one Matern component, a '
-                                      'single-latent likelihood, VI, Newton or EP)')
+                                      'single-latent likelihood, VI or Newton)')
         self.pseudo_likelihood.mean  # noqa: B018 -- materialise the sites before the resident state is rebuilt
         self._fused_dtype = dtype
         self._fused = None

@@ -22,12 +22,21 @@ from .cubature import host_table
 PLAIN, SITES, ENERGY = 0, 1, 2
 
 SUPPORTED_LIKS = (_lib.BN_LIK_GAUSSIAN, _lib.BN_LIK_BERNOULLI_PROBIT, _lib.BN_LIK_BERNOULLI_LOGIT, _lib.BN_LIK_POISSON_EXP)
-SUPPORTED_METHODS = (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON, _lib.BN_METHOD_EP)
+SUPPORTED_METHODS = (_lib.BN_METHOD_VI, _lib.BN_METHOD_NEWTON)
+
+
+def fused_ep():
+    """the EP epilogues of the fused passes are built and exact (same energy to 1e-15), but measured 6 % SLOWER than the
+    stage-level kernels at N = 1e7 (3.79 vs 3.58 ms per iteration, profiles/r7c_ep_fused_vs_stage_level_n1e7.json: the
+    exp per cubature point runs at the smoother's 16 warps per SM instead of the site kernel's 32), so EP takes the
+    stage-level path unless BN_B200_FUSED_EP=1"""
+    import os
+    return os.environ.get('BN_B200_FUSED_EP', '0') == '1'
 
 
 def supported(spec, likelihood, method):
-    return (spec is not None and spec.n_components == 1 and getattr(likelihood, 'lik_id', None) in SUPPORTED_LIKS
-            and method in SUPPORTED_METHODS)
+    ok = method in SUPPORTED_METHODS or (method == _lib.BN_METHOD_EP and fused_ep())
+    return spec is not None and spec.n_components == 1 and getattr(likelihood, 'lik_id', None) in SUPPORTED_LIKS and ok
 
 
 class FusedShard:

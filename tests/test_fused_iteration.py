@@ -221,6 +221,43 @@ def test_model_iteration_fused_vs_oracle(bn, kname, lik, method):
     assert abs(float(g.energy()) - o.energy()) <= TOL * abs(o.energy())
 
 
+@pytest.mark.parametrize('kname', ['m32', 'm52'])
+@pytest.mark.parametrize('lik', ['probit', 'logit', 'gaussian', 'poisson'])
+def test_model_iteration_fused_ep_vs_oracle(bn, kname, lik, monkeypatch):
+    """the EP epilogues of the fused passes (opt-in, BN_B200_FUSED_EP=1): power-EP iterations and energy against the
+    oracle model and against the stage-level path the EP models take by default"""
+    kg, ko = kernels(bn)[kname]
+    N = 400
+    x, y = classification_data(N, seed=9)
+    rng = np.random.default_rng(4)
+    if lik == 'gaussian':
+        y = np.sin(0.3 * x) + 0.4 * rng.standard_normal(N)
+    elif lik == 'poisson':
+        y = rng.poisson(np.exp(0.5 * np.sin(0.3 * x))).astype(np.float64)
+    y = y.copy()
+    y[::23] = np.nan
+    olik = {'probit': sites.Bernoulli(), 'logit': sites.Bernoulli(link='logit'), 'gaussian': sites.Gaussian(0.3),
+            'poisson': sites.Poisson()}[lik]
+    mk = lambda: bn.models.MarkovExpectationPropagationGP(kernel=kg, likelihood=_lik(bn, lik), X=x, Y=y, power=0.5, parallel=True)
+    u = mk()
+    assert not u._fused_ok()          # default: stage-level kernels
+    monkeypatch.setenv('BN_B200_FUSED_EP', '1')
+    g = mk()
+    assert g._fused_ok()
+    o = model.MarkovGP(ko, olik, x, y, method='ep', power=0.5)
+    for it in range(3):
+        g.inference(lr=0.6)
+        o.inference(lr=0.6)
+        assert rel_err(np_(g.posterior_mean), o.post_mean) < TOL and rel_err(np_(g.posterior_variance), o.post_cov) < TOL
+        E = float(g.energy())
+        assert abs(E - o.energy()) <= TOL * abs(o.energy())
+    monkeypatch.delenv('BN_B200_FUSED_EP')
+    for it in range(3):
+        u.inference(lr=0.6)
+    assert abs(E - float(u.energy())) <= 1e-10 * abs(E)
+    assert rel_err(np_(g.pseudo_likelihood.nat2), np_(u.pseudo_likelihood.nat2)) < TOL
+
+
 def test_fused_full_size_c2(bn):
     """N = 1e7 (BASELINE config 2): the fused iteration equals the unfused library path step for step"""
     N = 10_000_000
