@@ -404,7 +404,7 @@ namespace BN_NS {
 // the table-gathering sweeps own a whole SM: one CTA with the table in shared memory, 16 warps (d <= 3) or the 4 warps the
 // registers of a larger state leave room for
 // (fp32 build: the table is 8 KB, every CTA of the ordinary configuration stages its own copy)
-template <class G> constexpr int kItTabThreads = (!kReal32 && G::d <= 3) ? 512 : kUpThreads;
+template <class G> constexpr int kItTabThreads = kReal32 ? kUpThreads : (G::d <= 3 ? 512 : kUpBlocksPerSMWide * kUpThreads);
 #ifdef BN_REAL32
 constexpr unsigned kItTabBytes = kPt32Bytes;
 #else
@@ -433,7 +433,7 @@ it_selem_kernel(long long N, int L, long long nchunks, int need_first, const rea
 }
 
 template <class G>
-__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : kUpBlocksPerSMWide))
 it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg, ScanPlan plan) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
     if ((c & ~31LL) >= nchunks) return;
@@ -443,7 +443,7 @@ it_reduce_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg
 }
 
 template <class G, bool WANT_ELL>
-__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : kUpBlocksPerSMWide))
 it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const real* prefix, PrefixParts wprefix,
                  const real* s0, real* fs, real* ell_partials, const int* jst) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
@@ -452,7 +452,7 @@ it_filter_kernel(G g, ItIO io, int L, long long nchunks, int is_first, const rea
 
 // phase 1 with speculation (SpecReduce): every lane of a warp takes part in the vote, chunk or not
 template <class G, bool WANT_ELL>
-__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : kUpBlocksPerSMWide))
 it_reduce_spec_kernel(G g, ItIO io, int L, long long nchunks, int is_first, real* agg, real* fs, real* ell_partials,
                       int* jst, ScanPlan plan, real thr) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
@@ -540,7 +540,7 @@ inline cudaError_t it_sum(const real* a, const real* b, long long n, real* out, 
 }
 
 template <class G>
-__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : 1))
+__global__ void __launch_bounds__(kUpThreads, (G::d <= 3 ? kUpBlocksPerSM : kUpBlocksPerSMWide))
 it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const real* sprefix, PrefixParts swprefix, const real* sinit,
                        const real* fs) {
     const long long c = (long long)blockIdx.x * kUpThreads + threadIdx.x;
@@ -553,7 +553,7 @@ it_smooth_plain_kernel(G g, ItIO io, int L, long long nchunks, const real* spref
 int probit_table_device(cudaStream_t st, const double** tab);
 
 template <class G, template <int, int, bool> class Epi, int LIK, int METHOD, bool TAB>
-__global__ void __launch_bounds__(TAB ? kItTabThreads<G> : kUpThreads, (TAB && !kReal32) ? 1 : (G::d <= 3 ? kUpBlocksPerSM : 1))
+__global__ void __launch_bounds__(TAB ? kItTabThreads<G> : kUpThreads, (TAB && !kReal32) ? 1 : (G::d <= 3 ? kUpBlocksPerSM : kUpBlocksPerSMWide))
 it_smooth_site_kernel(G g, ItIO io, const __grid_constant__ Cub1 cub, ItSiteArgs a, int L, long long nchunks,
                       const real* sprefix, PrefixParts swprefix, const real* sinit, const real* fs, const double* gtab) {
     extern __shared__ __align__(16) double it_smem[];

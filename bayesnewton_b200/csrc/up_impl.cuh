@@ -33,6 +33,8 @@ constexpr int kUpTJ = BN_UP_TJ;          // steps per staged sub-block
 constexpr int kUpWarps = 4;              // warps per CTA
 constexpr int kUpThreads = 32 * kUpWarps;
 constexpr int kUpBlocksPerSM = BN_UP_BLOCKS;  // resident CTAs per SM the single-latent kernels are compiled for
+// states with d > 3 need up to 255 registers per thread: two 128-thread CTAs per SM is what the register file holds
+constexpr int kUpBlocksPerSMWide = 2;
 constexpr long long kUpTargetChunks = 148LL * kUpBlocksPerSM * kUpThreads;  // one resident wave
 #ifndef BN_UP_GRAD_BLOCKS
 #define BN_UP_GRAD_BLOCKS 3
@@ -60,7 +62,7 @@ inline long long up_env_chunk_target() {
     return v;
 }
 inline ChunkPlan up_plan_chunks(long long N, bool grad = false, int d = 3) {
-    long long target = (d > 3) ? 148LL * kUpThreads : (grad ? 148LL * kUpGradBlocksPerSM * kUpThreads : kUpTargetChunks);
+    long long target = (d > 3) ? 148LL * kUpBlocksPerSMWide * kUpThreads : (grad ? 148LL * kUpGradBlocksPerSM * kUpThreads : kUpTargetChunks);
     if (d <= 3 && !grad && up_env_chunk_target() > 0) target = up_env_chunk_target();
     long long L = (N + target - 1) / target;
     L = (L + kUpTJ - 1) / kUpTJ * kUpTJ;
