@@ -374,7 +374,9 @@ class InfiniteHorizonGaussianProcess(MarkovGaussianProcess):
         if want_grad:
             raise NotImplementedError('no hyper-gradient pass for the infinite-horizon model')
         pseudo_y, pseudo_var = self.compute_full_pseudo_lik()
-        dts = np.concatenate([self._dt_host[1:], [0.0]])
+        # the smoother's transition is the step OUT of a state: on the even grid that is dt[1] everywhere (only element 0 is
+        # read; building the shifted series on the host cost 15 ms per update at N = 1e7)
+        dts = self._dt_host[1:2] if self.num_data > 1 else np.zeros(1)
         _, (fm, fcov) = self.filter(self._dt_host, self.kernel, pseudo_y, pseudo_var, mask=self.mask_pseudo_y,
                                     parallel=self.parallel, want_ell=False)
         self.posterior_mean, self.posterior_variance, _ = self.smoother(dts, self.kernel, fm, fcov, parallel=self.parallel)

@@ -243,15 +243,20 @@ def _ih_ws(d, N):
     return torch.empty(nb, dtype=torch.uint8, device=torch.device('cuda', torch.cuda.current_device())), nb
 
 
+def _dt_at(dt, i):
+    """one step length as a host float (ONE element crosses PCIe, not the series)"""
+    flat = dt.reshape(-1) if torch.is_tensor(dt) else np.asarray(dt, dtype=np.float64).reshape(-1)
+    return float(flat[min(i, flat.shape[0] - 1)])
+
+
 def kalman_filter_infinite_horizon(dt, kernel, y, noise_cov, mask=None, parallel=False, heteroscedastic=False,
                                    noise_cov_tied=None, dare_iters=20, dare_init=None, want_ell=True):
     """ops.py:881-952 for one latent with one site per step: ell, (means [N,d,1], (Pdare, cov)).  The Riccati fixed point
     and the stationary gain are d x d host algebra; the O(N) mean recursion and the log-likelihood are bn_ih_filter."""
     y, R = as_dev(y).reshape(-1), as_dev(noise_cov).reshape(-1)
     N = y.shape[0]
-    dt_h = _np64(dt).reshape(-1)
     Pinf = _np64(kernel.stationary_covariance())
-    A = _np64(kernel.state_transition(float(dt_h[1])))
+    A = _np64(kernel.state_transition(_dt_at(dt, 1)))
     Q = Pinf - A @ Pinf @ A.T
     H = _np64(kernel.measurement_model())
     if H.shape[0] != 1 or not (H[0, 1:] == 0).all():
@@ -278,9 +283,8 @@ def rauch_tung_striebel_smoother_infinite_horizon(dt, kernel, filter_mean, filte
     """ops.py:1018-1068: means, covs (the fixed point, tiled over time), gains, dare_cov"""
     fm = as_dev(filter_mean)
     N, d = fm.shape[0], fm.shape[1]
-    dt_h = _np64(dt).reshape(-1)
     Pinf = _np64(kernel.stationary_covariance())
-    A = _np64(kernel.state_transition(float(dt_h[0])))
+    A = _np64(kernel.state_transition(_dt_at(dt, 0)))
     H = _np64(kernel.measurement_model())
     Pdare, fcov = (_np64(c) for c in filter_cov)
     gain = fcov @ _chol_solve_host(Pdare, A).T
