@@ -50,8 +50,22 @@ class InferenceMixin:
         want_grad: the closing posterior update also accumulates the hyper-gradient energy_and_grad() serves."""
         if batch_ind is not None and len(batch_ind) != self.num_data:
             raise NotImplementedError('mini-batched site updates are outside the hot-path scope (SURVEY A.15)')
-        if not return_state and not want_grad and getattr(self, '_fused_ok', lambda: False)():
+        fused_ok = not return_state and getattr(self, '_fused_ok', lambda: False)()
+        if fused_ok and not want_grad:
             return self._inference_fused(lr, cubature, ensure_psd)
+        if fused_ok and getattr(self, '_fused_dtype', torch.float64) == torch.float64:
+            # with the hyper-gradient: the first half (update_posterior + site update) as ONE fused pass; the closing
+            # update is the stage-level one that forms the adjoint inside its smoother sweep
+            from . import fused
+            st = self._fused_state()
+            pl = self.pseudo_likelihood
+            _, d = st.run(fused.SITES, self.likelihood, self.method, cubature, lr, self.power, ensure_psd, want_ell=False)
+            pl.version += 1
+            pl.source, st.sites_version = st, pl.version
+            self._energy_cache = None
+            self.update_posterior(want_grad=True)
+            n = float(self.num_data)
+            return (None, None, None), (d[0] / n, d[1] / n)
         self.update_posterior()
         a, keep = self._site_args(cubature)
         N, D = a.N, a.D
