@@ -1,5 +1,6 @@
 // C ABI of the Kalman filter (include/bn_b200.h).  The kernels live in filter_impl.cuh and are
 // instantiated per generator group in filter_m_*.cu / filter_a_*.cu.
+#include <cstdlib>
 #include "filter_impl.cuh"
 #include "gd_impl.cuh"
 
@@ -24,6 +25,13 @@ static int kf_dispatch(const KfCall& c) {
         set_error("unsupported kernel spec: family %d with %d components (use the array-level entry)",
                   c.spec->family, c.spec->n_components);
         return -1;
+    }
+    // (6, 6) -- the pairs filter of the sparse Markov model at Matern-5/2 -- has a register-resident instantiation, but its
+    // 90-double scan element spills (1 ms per scan level at 25 000 chunks): the warp-cooperative path keeps the element in
+    // shared memory and is ~7x faster end to end.  BN_B200_PAIRS_REGISTERS=1 selects the old instantiation (A/B aid).
+    if (c.d == 6 && c.D == 6 && c.phase == PHASE_ALL && !(getenv("BN_B200_PAIRS_REGISTERS") && getenv("BN_B200_PAIRS_REGISTERS")[0] == '1')) {
+        GdKf a{c.io.N, c.d, c.D, c.As, c.Qs, c.H, c.io.y, c.io.R, c.m0, c.P0, c.io.mask, c.io.return_predict, c.io.fms, c.io.fPs};
+        return gd_kf_arrays(c.form, a, c.ell, c.ws, c.ws_bytes, c.st);
     }
     if ((r = kf_group_a_a(c)) != kNotHandled) return r;
     if ((r = kf_group_a_b(c)) != kNotHandled) return r;

@@ -28,9 +28,61 @@ __global__ void __launch_bounds__(32 * kGdWarps) gd_kf_reduce_kernel(GdKf a, int
     gd_kf_reduce_chunk(gd_lane(), a, L, c, agg, gd_warp_pool(gd_smem, a.d));
 }
 
-__global__ void __launch_bounds__(32) gd_kf_scan_kernel(int d, long long nchunks, const double* agg, double* prefix) {
+template <class K>
+static int gd_allow_smem(K kern, size_t bytes) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+// phase 2 (gd_impl.cuh: gd_scan_group / gd_scan_down), one warp per group resp. per element
+template <bool FILTER>
+__global__ void __launch_bounds__(32 * kGdWarps)
+gd_scan_group_kernel(int d, long long n, const double* in, double* prefix, double* totals) {
     extern __shared__ double gd_smem[];
-    gd_kf_scan(gd_lane(), d, nchunks, agg, prefix, gd_warp_pool(gd_smem, d));
+    const long long g = (long long)blockIdx.x * kGdWarps + (threadIdx.x >> 5);
+    if (g * kGdScanGroup >= n) return;
+    gd_scan_group<FILTER>(gd_lane(), d, n, in, prefix, totals, g, gd_warp_pool(gd_smem, d));
+}
+template <bool FILTER>
+__global__ void __launch_bounds__(32 * kGdWarps) gd_scan_down_kernel(int d, long long n, double* prefix, const double* upper) {
+    extern __shared__ double gd_smem[];
+    const long long i = (long long)blockIdx.x * kGdWarps + (threadIdx.x >> 5) + kGdScanGroup;  // group 0 needs nothing
+    if (i >= n) return;
+    gd_scan_down<FILTER>(gd_lane(), d, prefix, upper, i, gd_warp_pool(gd_smem, d));
+}
+
+// inclusive scan of the n chunk elements agg[] into prefix[]; `upper` = gd_scan_upper_elems(n) elements of scratch
+template <bool FILTER>
+static int gd_run_scan(int d, long long n, const double* agg, double* prefix, double* upper, size_t warp_smem, cudaStream_t st) {
+    const int ne = gd_elem<FILTER>(d);
+    if (int rc = gd_allow_smem(gd_scan_group_kernel<FILTER>, kGdWarps * warp_smem)) return rc;
+    if (int rc = gd_allow_smem(gd_scan_down_kernel<FILTER>, kGdWarps * warp_smem)) return rc;
+    // up: level l scanned in groups; its totals are level l + 1 (scanned in place)
+    constexpr int kMaxLevels = 8;
+    long long cnt[kMaxLevels];
+    double* arr[kMaxLevels];
+    int levels = 0;
+    cnt[0] = n; arr[0] = prefix;
+    const double* in = agg;
+    while (true) {
+        const long long m = cnt[levels], groups = (m + kGdScanGroup - 1) / kGdScanGroup;
+        double* totals = groups > 1 ? upper : nullptr;
+        BN_LAUNCH("gd_scan", st, (gd_scan_group_kernel<FILTER><<<(unsigned)((groups + kGdWarps - 1) / kGdWarps), 32 * kGdWarps,
+                                                              kGdWarps * warp_smem, st>>>(d, m, in, arr[levels], totals)));
+        if (groups <= 1) break;
+        BN_REQUIRE(levels + 1 < kMaxLevels, "scan too deep");
+        ++levels;
+        cnt[levels] = groups; arr[levels] = upper; in = upper;
+        upper += groups * ne;
+    }
+    for (int l = levels - 1; l >= 0; --l) {
+        const long long m = cnt[l] - kGdScanGroup;  // elements outside group 0
+        if (m <= 0) continue;
+        BN_LAUNCH("gd_scan_down", st, (gd_scan_down_kernel<FILTER><<<(unsigned)((m + kGdWarps - 1) / kGdWarps), 32 * kGdWarps,
+                                                                  kGdWarps * warp_smem, st>>>(d, cnt[l], arr[l], arr[l + 1])));
+    }
+    BN_CUDA(cudaGetLastError());
+    return 0;
 }
 
 __global__ void __launch_bounds__(32 * kGdWarps)
@@ -61,10 +113,6 @@ __global__ void __launch_bounds__(32 * kGdWarps) gd_rts_reduce_kernel(GdRts a, i
     gd_rts_reduce_chunk(gd_lane(), a, L, nchunks, c, agg, gd_warp_pool(gd_smem, a.d));
 }
 
-__global__ void __launch_bounds__(32) gd_rts_scan_kernel(int d, long long nchunks, const double* agg, double* prefix) {
-    extern __shared__ double gd_smem[];
-    gd_rts_scan(gd_lane(), d, nchunks, agg, prefix, gd_warp_pool(gd_smem, d));
-}
 
 __global__ void __launch_bounds__(32 * kGdWarps)
 gd_rts_apply_kernel(GdRts a, int L, long long nchunks, const double* prefix) {
@@ -74,15 +122,9 @@ gd_rts_apply_kernel(GdRts a, int L, long long nchunks, const double* prefix) {
     gd_rts_apply_chunk(gd_lane(), a, L, nchunks, c, prefix, gd_warp_pool(gd_smem, a.d));
 }
 
-template <class K>
-static int gd_allow_smem(K kern, size_t bytes) {
-    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return 0;
-}
-
 size_t gd_workspace_doubles(long long N, int d) {
     const GdPlan p = gd_plan(N > 0 ? N : 1);
-    return (size_t)p.nchunks * (2 * (size_t)gd_felem(d) + 1) + 64;
+    return ((size_t)p.nchunks * 2 + (size_t)gd_scan_upper_elems(p.nchunks)) * gd_felem(d) + (size_t)p.nchunks + 64;
 }
 
 int gd_kf_arrays(int form, const GdKf& a, double* ell, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -101,13 +143,13 @@ int gd_kf_arrays(int form, const GdKf& a, double* ell, void* ws, size_t ws_bytes
     BN_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     double* agg = (double*)ws;
     double* prefix = agg + (size_t)p.nchunks * gd_felem(a.d);
-    double* partials = prefix + (size_t)p.nchunks * gd_felem(a.d);
+    double* upper = prefix + (size_t)p.nchunks * gd_felem(a.d);
+    double* partials = upper + (size_t)gd_scan_upper_elems(p.nchunks) * gd_felem(a.d);
     const unsigned grid = (unsigned)((p.nchunks + kGdWarps - 1) / kGdWarps);
     if (int rc = gd_allow_smem(gd_kf_reduce_kernel, kGdWarps * warp_smem)) return rc;
-    if (int rc = gd_allow_smem(gd_kf_scan_kernel, warp_smem)) return rc;
     if (int rc = gd_allow_smem(gd_kf_apply_kernel, kGdWarps * warp_smem)) return rc;
     BN_LAUNCH("gd_kf_reduce", st, (gd_kf_reduce_kernel<<<grid, 32 * kGdWarps, kGdWarps * warp_smem, st>>>(a, p.L, p.nchunks, agg)));
-    BN_LAUNCH("gd_kf_scan", st, (gd_kf_scan_kernel<<<1, 32, warp_smem, st>>>(a.d, p.nchunks, agg, prefix)));
+    if (int rc = gd_run_scan<true>(a.d, p.nchunks, agg, prefix, upper, warp_smem, st)) return rc;
     BN_LAUNCH("gd_kf_apply", st, (gd_kf_apply_kernel<<<grid, 32 * kGdWarps, kGdWarps * warp_smem, st>>>(a, p.L, p.nchunks, prefix, partials,
                                                                                                      ell != nullptr)));
     BN_CUDA(cudaGetLastError());
@@ -136,10 +178,10 @@ int gd_rts_arrays(int form, const GdRts& a, void* ws, size_t ws_bytes, cudaStrea
     double* prefix = agg + (size_t)p.nchunks * gd_selem(a.d);
     const unsigned grid = (unsigned)((p.nchunks + kGdWarps - 1) / kGdWarps);
     if (int rc = gd_allow_smem(gd_rts_reduce_kernel, kGdWarps * warp_smem)) return rc;
-    if (int rc = gd_allow_smem(gd_rts_scan_kernel, warp_smem)) return rc;
     if (int rc = gd_allow_smem(gd_rts_apply_kernel, kGdWarps * warp_smem)) return rc;
     BN_LAUNCH("gd_rts_reduce", st, (gd_rts_reduce_kernel<<<grid, 32 * kGdWarps, kGdWarps * warp_smem, st>>>(a, p.L, p.nchunks, agg)));
-    BN_LAUNCH("gd_rts_scan", st, (gd_rts_scan_kernel<<<1, 32, warp_smem, st>>>(a.d, p.nchunks, agg, prefix)));
+    double* supper = prefix + (size_t)p.nchunks * gd_selem(a.d);
+    if (int rc = gd_run_scan<false>(a.d, p.nchunks, agg, prefix, supper, warp_smem, st)) return rc;
     BN_LAUNCH("gd_rts_apply", st, (gd_rts_apply_kernel<<<grid, 32 * kGdWarps, kGdWarps * warp_smem, st>>>(a, p.L, p.nchunks, prefix)));
     BN_CUDA(cudaGetLastError());
     return 0;

@@ -16,7 +16,7 @@ namespace bn {
 constexpr int kGdMaxD = 16;
 constexpr int kGdWarps = 4;            // warps (chunks) per CTA
 constexpr int kGdMinChunk = 16;        // steps per chunk at least
-constexpr long long kGdMaxChunks = 148LL * 2 * kGdWarps;   // phase 2 is one warp walking the chunk elements
+constexpr long long kGdMaxChunks = 148LL * 2 * kGdWarps;   // one resident wave of warps (2 CTAs of 4 warps per SM)
 
 struct GdW { int lane, nl; };
 #define GD_FOR(i, n) for (int i = w.lane; i < (n); i += w.nl)
@@ -543,20 +543,6 @@ BN_DEV void gd_kf_reduce_chunk(GdW w, const GdKf& a, int L, long long c, double*
     gd_copy(w, agg + c * gd_felem(d), g.A, gd_felem(d));
 }
 
-// phase 2: inclusive prefixes of the chunk elements, one warp walking them in order
-BN_DEV void gd_kf_scan(GdW w, int d, long long nchunks, const double* agg, double* prefix, GdPool pool) {
-    const int ne = gd_felem(d);
-    double* acc = pool.take(ne);
-    double* cur = pool.take(ne);
-    gd_copy(w, acc, agg, ne);
-    gd_copy(w, prefix, acc, ne);
-    for (long long c = 1; c < nchunks; ++c) {
-        gd_copy(w, cur, agg + c * ne, ne);
-        gd_filter_combine(w, d, GdFElem(acc, d), GdFElem(cur, d), GdFElem(acc, d), pool);
-        gd_copy(w, prefix + c * ne, acc, ne);
-    }
-}
-
 // phase 3: chunk c filtered from its incoming state.  The first step of the scan form starts its update from (m0, P0)
 // itself (ops.py:222-229, 245-248); its log-likelihood / predicted outputs use A_0 m0, A_0 P0 A_0^T + Q_0.
 BN_DEV double gd_kf_apply_chunk(GdW w, const GdKf& a, int L, long long c, const double* prefix, bool want_ell, GdPool pool) {
@@ -665,19 +651,6 @@ BN_DEV void gd_rts_reduce_chunk(GdW w, const GdRts& a, int L, long long nchunks,
     gd_copy(w, agg + (nchunks - 1 - c) * ne, acc.E, ne);
 }
 
-BN_DEV void gd_rts_scan(GdW w, int d, long long nchunks, const double* agg, double* prefix, GdPool pool) {
-    const int ne = gd_selem(d);
-    double* acc = pool.take(ne);
-    double* cur = pool.take(ne);
-    gd_copy(w, acc, agg, ne);
-    gd_copy(w, prefix, acc, ne);
-    for (long long p = 1; p < nchunks; ++p) {
-        gd_copy(w, cur, agg + p * ne, ne);
-        gd_smoother_combine(w, d, GdSElem(acc, d), GdSElem(cur, d), GdSElem(acc, d), pool);
-        gd_copy(w, prefix + p * ne, acc, ne);
-    }
-}
-
 BN_DEV void gd_rts_apply_chunk(GdW w, const GdRts& a, int L, long long nchunks, long long c, const double* prefix, GdPool pool) {
     const int d = a.d;
     double* sm = pool.take(d);
@@ -688,6 +661,65 @@ BN_DEV void gd_rts_apply_chunk(GdW w, const GdRts& a, int L, long long nchunks, 
     if (p > 0) gd_smoother_apply(w, d, GdSElem(const_cast<double*>(prefix) + (p - 1) * gd_selem(d), d), sm, sP, pool);
     const long long k0 = c * L, k1 = (k0 + L < a.N) ? k0 + L : a.N;
     gd_rts_run(w, a, k0, k1, sm, sP, true, pool);
+}
+
+
+// ---------------------------------------------------------------------------------------------- phase 2 in groups
+// The scan over the chunk elements, organised for warps: a level cuts its n elements into groups of kGdScanGroup
+// consecutive ones; ONE WARP walks a group in order (31 warp-cooperative combines), leaving within-group inclusive prefixes
+// and the group total; the totals are the next level (n / 32 elements) and so on until one group is left; going back down,
+// every element of a group > 0 takes one combine with the prefix of the groups before it.  1 184 elements -> 37 -> 2 -> 1:
+// about 100 combine latencies on the critical path instead of 1 184.
+constexpr int kGdScanGroup = 32;
+
+template <bool FILTER>
+BN_DEV constexpr int gd_elem(int d) { return FILTER ? gd_felem(d) : gd_selem(d); }
+
+template <bool FILTER>
+BN_DEV void gd_combine(GdW w, int d, double* e1, double* e2, double* out, GdPool pool) {
+    if constexpr (FILTER) gd_filter_combine(w, d, GdFElem(e1, d), GdFElem(e2, d), GdFElem(out, d), pool);
+    else gd_smoother_combine(w, d, GdSElem(e1, d), GdSElem(e2, d), GdSElem(out, d), pool);
+}
+
+// group g of a level: in[n] -> prefix[n] (within-group inclusive), totals[g]
+template <bool FILTER>
+BN_DEV void gd_scan_group(GdW w, int d, long long n, const double* in, double* prefix, double* totals, long long g, GdPool pool) {
+    const int ne = gd_elem<FILTER>(d);
+    double* acc = pool.take(ne);
+    double* cur = pool.take(ne);
+    const long long i0 = g * kGdScanGroup, i1 = (i0 + kGdScanGroup < n) ? i0 + kGdScanGroup : n;
+    gd_copy(w, acc, in + i0 * ne, ne);
+    gd_copy(w, prefix + i0 * ne, acc, ne);
+    for (long long i = i0 + 1; i < i1; ++i) {
+        gd_copy(w, cur, in + i * ne, ne);
+        gd_combine<FILTER>(w, d, acc, cur, acc, pool);
+        gd_copy(w, prefix + i * ne, acc, ne);
+    }
+    if (totals) gd_copy(w, totals + g * ne, acc, ne);
+}
+
+// element i of a level, after the level above has been scanned: prefix[i] <- combine(upper[group(i) - 1], prefix[i])
+template <bool FILTER>
+BN_DEV void gd_scan_down(GdW w, int d, double* prefix, const double* upper, long long i, GdPool pool) {
+    const long long g = i / kGdScanGroup;
+    if (g == 0) return;
+    const int ne = gd_elem<FILTER>(d);
+    double* a = pool.take(ne);
+    double* b = pool.take(ne);
+    gd_copy(w, a, upper + (g - 1) * ne, ne);
+    gd_copy(w, b, prefix + i * ne, ne);
+    gd_combine<FILTER>(w, d, a, b, b, pool);
+    gd_copy(w, prefix + i * ne, b, ne);
+}
+
+// elements of scratch the upper levels need (totals of every level above the first)
+inline long long gd_scan_upper_elems(long long n) {
+    long long tot = 0;
+    while (n > kGdScanGroup) {
+        n = (n + kGdScanGroup - 1) / kGdScanGroup;
+        tot += n;
+    }
+    return tot + 1;
 }
 
 }  // namespace bn

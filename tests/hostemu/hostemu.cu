@@ -704,6 +704,28 @@ extern "C" int emu_iter_pass(const bn_kernel_spec* k, long long N, int L, int wo
 }
 
 // ---------------------------------------------------------------------------- warp-cooperative small-d path (gd_impl.cuh)
+// phase 2 as gd.cu drives it: levels of groups going up, one combine per element going down
+template <bool FILTER>
+static void emu_gd_scan(int d, long long n, const double* agg, double* prefix, std::vector<double>& smem) {
+    const GdW w{0, 1};
+    const int ne = gd_elem<FILTER>(d);
+    std::vector<double> upper((size_t)gd_scan_upper_elems(n) * ne);
+    std::vector<long long> cnt{n};
+    std::vector<double*> arr{prefix};
+    const double* in = agg;
+    double* up = upper.data();
+    while (true) {
+        const long long m = cnt.back(), groups = (m + kGdScanGroup - 1) / kGdScanGroup;
+        for (long long g = 0; g < groups; ++g)
+            gd_scan_group<FILTER>(w, d, m, in, arr.back(), groups > 1 ? up : nullptr, g, GdPool{smem.data()});
+        if (groups <= 1) break;
+        cnt.push_back(groups); arr.push_back(up); in = up;
+        up += groups * ne;
+    }
+    for (int l = (int)cnt.size() - 2; l >= 0; --l)
+        for (long long i = kGdScanGroup; i < cnt[l]; ++i) gd_scan_down<FILTER>(w, d, arr[l], arr[l + 1], i, GdPool{smem.data()});
+}
+
 // the chunk bodies with (lane, lanes) = (0, 1): every lane-strided loop covers all entries, __syncwarp is a no-op
 extern "C" int emu_gd_kf(int form, long long N, int L, int d, int D, const double* As, const double* Qs, const double* H,
                          const double* ys, const double* Rs, const double* m0, const double* P0, const unsigned char* masks,
@@ -725,7 +747,7 @@ extern "C" int emu_gd_kf(int form, long long N, int L, int d, int D, const doubl
     const long long nchunks = (N + L - 1) / L;
     std::vector<double> agg((size_t)nchunks * gd_felem(d)), prefix((size_t)nchunks * gd_felem(d));
     for (long long c = 0; c < nchunks; ++c) gd_kf_reduce_chunk(w, a, L, c, agg.data(), GdPool{smem.data()});
-    gd_kf_scan(w, d, nchunks, agg.data(), prefix.data(), GdPool{smem.data()});
+    emu_gd_scan<true>(d, nchunks, agg.data(), prefix.data(), smem);
     double tot = 0.0;
     for (long long c = 0; c < nchunks; ++c) tot += gd_kf_apply_chunk(w, a, L, c, prefix.data(), ell != nullptr, GdPool{smem.data()});
     if (ell) *ell = tot;
@@ -751,7 +773,7 @@ extern "C" int emu_gd_rts(int form, long long N, int L, int d, int Df, const dou
     const long long nchunks = (N + L - 1) / L;
     std::vector<double> agg((size_t)nchunks * gd_selem(d)), prefix((size_t)nchunks * gd_selem(d));
     for (long long c = 0; c < nchunks; ++c) gd_rts_reduce_chunk(w, a, L, nchunks, c, agg.data(), GdPool{smem.data()});
-    gd_rts_scan(w, d, nchunks, agg.data(), prefix.data(), GdPool{smem.data()});
+    emu_gd_scan<false>(d, nchunks, agg.data(), prefix.data(), smem);
     for (long long c = 0; c < nchunks; ++c) gd_rts_apply_chunk(w, a, L, nchunks, c, prefix.data(), GdPool{smem.data()});
     return 0;
 }
