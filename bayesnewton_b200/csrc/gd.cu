@@ -123,7 +123,7 @@ gd_rts_apply_kernel(GdRts a, int L, long long nchunks, const double* prefix) {
 }
 
 size_t gd_workspace_doubles(long long N, int d) {
-    const GdPlan p = gd_plan(N > 0 ? N : 1);
+    const GdPlan p = gd_plan(N > 0 ? N : 1, d);
     return ((size_t)p.nchunks * 2 + (size_t)gd_scan_upper_elems(p.nchunks)) * gd_felem(d) + (size_t)p.nchunks + 64;
 }
 
@@ -138,7 +138,7 @@ int gd_kf_arrays(int form, const GdKf& a, double* ell, void* ws, size_t ws_bytes
         BN_CUDA(cudaGetLastError());
         return 0;
     }
-    const GdPlan p = gd_plan(a.N);
+    const GdPlan p = gd_plan(a.N, a.d);
     const size_t need = gd_workspace_doubles(a.N, a.d) * sizeof(double);
     BN_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     double* agg = (double*)ws;
@@ -171,7 +171,7 @@ int gd_rts_arrays(int form, const GdRts& a, void* ws, size_t ws_bytes, cudaStrea
         BN_CUDA(cudaGetLastError());
         return 0;
     }
-    const GdPlan p = gd_plan(a.N);
+    const GdPlan p = gd_plan(a.N, a.d);
     const size_t need = gd_workspace_doubles(a.N, a.d) * sizeof(double);
     BN_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     double* agg = (double*)ws;

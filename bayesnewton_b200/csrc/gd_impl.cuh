@@ -16,7 +16,6 @@ namespace bn {
 constexpr int kGdMaxD = 16;
 constexpr int kGdWarps = 4;            // warps (chunks) per CTA
 constexpr int kGdMinChunk = 16;        // steps per chunk at least
-constexpr long long kGdMaxChunks = 148LL * 2 * kGdWarps;   // one resident wave of warps (2 CTAs of 4 warps per SM)
 
 struct GdW { int lane, nl; };
 #define GD_FOR(i, n) for (int i = w.lane; i < (n); i += w.nl)
@@ -497,8 +496,18 @@ struct GdRts {
 };
 
 struct GdPlan { int L; long long nchunks; };
-inline GdPlan gd_plan(long long N) {
-    long long L = (N + kGdMaxChunks - 1) / kGdMaxChunks;
+// one resident wave of warps: as many CTAs of kGdWarps warps per SM as their shared-memory pools allow (32 warps per SM at
+// d <= 6, 16 at d = 8, 4 at d = 16)
+inline long long gd_max_chunks(int d) {
+    const long long warp_bytes = (long long)gd_pool_doubles(d) * 8;
+    long long ctas = (220 * 1024) / (warp_bytes * kGdWarps);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 8) ctas = 8;
+    return 148LL * ctas * kGdWarps;
+}
+inline GdPlan gd_plan(long long N, int d) {
+    const long long maxc = gd_max_chunks(d);
+    long long L = (N + maxc - 1) / maxc;
     if (L < kGdMinChunk) L = kGdMinChunk;
     GdPlan p;
     p.L = (int)L;
