@@ -8,6 +8,7 @@
 // The chunk bodies are __host__ __device__: on the host they run with (lane, lanes) = (0, 1), which is what
 // tests/hostemu executes against the oracle on the CPU.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "core.cuh"
 
@@ -503,6 +504,11 @@ inline long long gd_max_chunks(int d) {
     long long ctas = (220 * 1024) / (warp_bytes * kGdWarps);
     if (ctas < 1) ctas = 1;
     if (ctas > 8) ctas = 8;
+    static const long long env_cap = [] {  // BN_B200_GD_CTAS=<n>: cap on resident CTAs per SM (tuning aid)
+        const char* e = getenv("BN_B200_GD_CTAS");
+        return e ? atoll(e) : 0LL;
+    }();
+    if (env_cap > 0 && ctas > env_cap) ctas = env_cap;
     return 148LL * ctas * kGdWarps;
 }
 inline GdPlan gd_plan(long long N, int d) {
