@@ -120,6 +120,12 @@ class FusedShard:
         v = self.from_tiled(self.pc_t, out=None if out_cov is None else out_cov.reshape(-1))
         return m.reshape(self.N, 1, 1), v.reshape(self.N, 1, 1)
 
+    def _check_post(self, post):
+        """the sweep writes the marginals straight into these: they must be contiguous [N] arrays of the shard's dtype"""
+        for t in post:
+            if t.dtype != self.dtype or t.numel() != self.N or not t.is_contiguous() or t.device != self.dev:
+                raise ValueError('post = (mean, cov): contiguous %s tensors of %d elements on %s are needed' % (self.dtype, self.N, self.dev))
+
     # ---- the passes
     def _args(self, likelihood, method, cubature, lr, power, ensure_psd):
         a = _lib.IterArgs()
@@ -147,6 +153,7 @@ class FusedShard:
         marginals are written straight into these [N(,1,1)] tensors in time order instead of the tiled arrays"""
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
         if post is not None:
+            self._check_post(post)
             a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
         ell = torch.empty((), dtype=self.dtype, device=self.dev) if want_ell else None
         sums = torch.empty(2, dtype=self.dtype, device=self.dev) if mode != PLAIN else None
@@ -176,6 +183,7 @@ class FusedShard:
                ensure_psd=True, post=None):
         a, keep = self._args(likelihood, method, cubature, lr, power, ensure_psd)
         if post is not None:
+            self._check_post(post)
             a.post_mean, a.post_cov = post[0].data_ptr(), post[1].data_ptr()
         sums = torch.empty(2, dtype=self.dtype, device=self.dev) if mode != PLAIN else None
         _lib.check(self._fn('bn_iter_shard_smooth')(self.kernel.spec(), C.byref(a), int(mode), ptr(rts_carries), ptr(sums),
