@@ -123,8 +123,8 @@ class FusedShard:
     def _check_post(self, post):
         """the sweep writes the marginals straight into these: they must be contiguous [N] arrays of the shard's dtype"""
         for t in post:
-            if t.dtype != self.dtype or t.numel() != self.N or not t.is_contiguous() or t.device != self.dev:
-                raise ValueError('post = (mean, cov): contiguous %s tensors of %d elements on %s are needed' % (self.dtype, self.N, self.dev))
+            if t.dtype != self.dtype or t.numel() != self.N or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError('post = (mean, cov): contiguous device tensors of %d %s elements are needed' % (self.N, self.dtype))
 
     # ---- the passes
     def _args(self, likelihood, method, cubature, lr, power, ensure_psd):
