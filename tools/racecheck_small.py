@@ -10,7 +10,7 @@ import torch
 import bayesnewton_b200 as bn
 from _data import bench_inputs
 
-N = 20_011
+N = 200_003  # more than 32 x 288 chunks: the one-launch upper scan levels and the ticketed sums are on the path
 t, dt, y = bench_inputs(N)
 y[::17] = np.nan
 for par in (True, False):
