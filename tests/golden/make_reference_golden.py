@@ -425,9 +425,35 @@ def gradient_cases():
     return out
 
 
+def model_family_cases():
+    """the model-level iteration for the other Matern families (the `models` cases are Matern-5/2): VI and Newton with a
+    Bernoulli-probit likelihood, both forms, missing observations"""
+    out = {}
+    M = bn.models
+    x, y = classification_data(70, seed=17)
+    y = y.copy()
+    y[::9] = np.nan
+    out['x'], out['y'] = x, y
+    fams = {'m12': lambda: bn.kernels.Matern12(variance=0.8, lengthscale=1.7), 'm32': lambda: bn.kernels.Matern32(variance=1.1, lengthscale=0.6),
+            'm72': lambda: bn.kernels.Matern72(variance=0.7, lengthscale=1.4)}
+    for fname, mk in fams.items():
+        for mname, cls in {'vi': M.MarkovVariationalGP, 'newton': M.MarkovLaplaceGP}.items():
+            for par in (False, True):
+                m = cls(kernel=mk(), likelihood=bn.likelihoods.Bernoulli(link='probit'), X=x, Y=y, parallel=par)
+                tag = '%s_%s_%s' % (fname, mname, 'par' if par else 'seq')
+                energies = []
+                for it in range(3):
+                    m.inference(lr=0.6)
+                    energies.append(float(m.energy()))
+                out[tag + '_energy'] = np.array(energies)
+                out[tag + '_post_mean'], out[tag + '_post_var'] = A(m.posterior_mean), A(m.posterior_variance)
+                out[tag + '_site_nat1'], out[tag + '_site_nat2'] = A(m.pseudo_likelihood.nat1), A(m.pseudo_likelihood.nat2)
+    return out
+
+
 CASES = {'ops': ops_cases, 'models': model_cases, 'likelihoods': likelihood_cases, 'likelihoods2': likelihood2_cases, 'models2': model2_cases, 'heteroscedastic': heteroscedastic_cases,
          'regression': regression_case, 'sparse': sparse_cases, 'spacetime': spacetime_cases,
-         'infinite_horizon': infinite_horizon_cases, 'gradient': gradient_cases}
+         'infinite_horizon': infinite_horizon_cases, 'gradient': gradient_cases, 'model_families': model_family_cases}
 
 if __name__ == '__main__':
     which = sys.argv[1:] or sorted(CASES)

@@ -514,3 +514,21 @@ def test_gpu_energy_gradient_vs_reference(bn, method, parallel):
     ref = g[method + '_grad']
     got = np.array([float(dE[0, 0]), float(dE[1, 0]), float(m.energy_grad_likelihood())])
     assert np.all(np.abs(got - ref[:, 0]) <= GRAD_TOL * np.maximum(1.0, np.abs(ref[:, 0]))), (got, ref)
+
+
+# ---------------------------------------------------------------------------------------------- other Matern families
+@pytest.mark.parametrize('fam', ['m12', 'm32', 'm72'])
+@pytest.mark.parametrize('method', ['vi', 'newton'])
+@pytest.mark.parametrize('par', [False, True])
+def test_oracle_model_iterations_other_families_vs_reference(fam, method, par):
+    """the model-level iteration of the reference for Matern-1/2, -3/2 and -7/2 (the `models` goldens are Matern-5/2)"""
+    g = golden('model_families')
+    k = {'m12': ssm.Matern12(0.8, 1.7), 'm32': ssm.Matern32(1.1, 0.6), 'm72': ssm.Matern72(0.7, 1.4)}[fam]
+    o = model.MarkovGP(k, sites.Bernoulli(), g['x'], g['y'], method=method, parallel=par)
+    tag = '%s_%s_%s' % (fam, method, 'par' if par else 'seq')
+    tol = 2e-8 if par else 1e-11  # parallel form with masked steps: see the module docstring
+    for it in range(3):
+        o.inference(lr=0.6)
+        assert abs(o.energy() - g[tag + '_energy'][it]) <= tol * abs(g[tag + '_energy'][it])
+    assert rel_err(o.post_mean, g[tag + '_post_mean']) < tol and rel_err(o.post_cov, g[tag + '_post_var']) < tol
+    assert rel_err(o.site_nat1, g[tag + '_site_nat1']) < tol and rel_err(o.site_nat2, g[tag + '_site_nat2']) < tol
